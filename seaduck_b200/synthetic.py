@@ -1,0 +1,465 @@
+"""Synthetic, grid-shaped datasets for tests, golden vectors and ``bench.py``.
+
+No ECCO / LLC4320 data can be downloaded here, so every workload in ``BASELINE.json`` is run on
+synthetic fields of the same *shape* (SURVEY.md §8d):
+
+* :func:`gyre` / :func:`overturning_cell` -- the idealised double gyre and overturning cell of the
+  reference's own ``tests/test_streamfunction.py:17-92`` (no face dimension).
+* :func:`llc` -- a 13-face lat-lon-cap shaped grid whose geometry is consistent with the reference's
+  ``LLC_FACE_CONNECT`` table (``seaduck/topology.py:8``): every shared edge has the same physical
+  wall on both faces.  Velocities come from an analytic flow projected on the cell walls, so the
+  wall values are single valued across faces.
+* :func:`rectilinear` -- 1-D ``lon``/``lat`` dataset for the ``rectilinear`` readiness branch.
+
+Everything is returned as a :class:`seaduck_b200.minixr.Dataset` (or a real ``xarray.Dataset`` when
+``as_xarray=True`` and xarray is importable).
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from . import minixr
+
+R_EARTH = 6371e3
+
+__all__ = ["gyre", "overturning_cell", "llc", "rectilinear", "llc_seed_particles"]
+
+
+def _dataset(coords, data_vars, as_xarray=False):
+    if as_xarray:
+        import xarray as xr  # noqa: PLC0415
+
+        return xr.Dataset(coords=coords, data_vars=data_vars)
+    return minixr.Dataset(coords=coords, data_vars=data_vars)
+
+
+def _streamfunction(x, z):
+    return np.cos(np.pi * x / 2) * np.cos(np.pi * z / 2)
+
+
+def gyre(ny=50, nx=50, dtype=np.float64, as_xarray=False):
+    """Closed 2-D double gyre on ``[-1,1]^2`` degrees (reference ``tests/test_streamfunction.py:62``).
+
+    ``UVELMASS``/``VVELMASS`` are wall *transports* derived from a corner stream function, so the
+    flow is exactly non-divergent and ``streamfunc`` is conserved along trajectories.
+    """
+    x = np.linspace(-1, 1, nx + 1)
+    y = np.linspace(-1, 1, ny + 1)
+    xg, yg = np.meshgrid(x, y)
+    strmf = _streamfunction(xg, yg)
+    xv = 0.5 * (xg[:, 1:] + xg[:, :-1])
+    yv = 0.5 * (yg[:, 1:] + yg[:, :-1])
+    xc = 0.5 * (xv[1:] + xv[:-1])
+    yc = 0.5 * (yv[1:] + yv[:-1])
+    u = np.diff(strmf, axis=0).astype(dtype)
+    v = (-np.diff(strmf, axis=1)).astype(dtype)
+    return _dataset(
+        dict(
+            XC=(["Y", "X"], xc),
+            YC=(["Y", "X"], yc),
+            XG=(["Yp1", "Xp1"], xg),
+            YG=(["Yp1", "Xp1"], yg),
+            rA=(["Y", "X"], np.ones_like(xc, float)),
+        ),
+        dict(
+            UVELMASS=(["Y", "Xp1"], u),
+            VVELMASS=(["Yp1", "X"], v),
+            streamfunc=(["Yp1", "Xp1"], strmf),
+        ),
+        as_xarray,
+    )
+
+
+def overturning_cell(nx=100, nz=50, dtype=np.float64, as_xarray=False):
+    """x-z overturning cell, one cell wide in y (reference ``tests/test_streamfunction.py:17``)."""
+    x = np.linspace(-1, 1, nx + 1)
+    y = np.linspace(-0.1, 0.1, 2)
+    zl = np.linspace(0, -1000, nz)
+    zp1 = np.append(zl, -1001)
+    xg, yg = np.meshgrid(x, y)
+    xv = 0.5 * (xg[:, 1:] + xg[:, :-1])
+    yv = 0.5 * (yg[:, 1:] + yg[:, :-1])
+    xc = 0.5 * (xv[1:] + xv[:-1])
+    yc = 0.5 * (yv[1:] + yv[:-1])
+    tempx, tempz = np.meshgrid(x, zl)
+    strmf = _streamfunction(tempx, -tempz / 500 - 1).reshape(len(zl), 1, -1)
+    z = 0.5 * (zp1[1:] + zp1[:-1])
+    zl = zp1[:-1]
+    drf = np.abs(np.diff(zp1))
+    u = np.zeros((nz, 1, nx + 1), float)
+    u[:-1] = np.diff(strmf, axis=0)
+    w = np.diff(strmf, axis=-1)
+    v = np.zeros((nz, 2, nx), float)
+    stream = np.zeros((nz, 2, nx + 1))
+    stream[:] = strmf
+    return _dataset(
+        dict(
+            XC=(["Y", "X"], xc),
+            YC=(["Y", "X"], yc),
+            XG=(["Yp1", "Xp1"], xg),
+            YG=(["Yp1", "Xp1"], yg),
+            Zl=(["Zl"], zl),
+            Z=(["Z"], z),
+            drF=(["Z"], drf),
+            rA=(["Y", "X"], np.ones_like(xc, float)),
+        ),
+        dict(
+            UVELMASS=(["Z", "Y", "Xp1"], u.astype(dtype)),
+            VVELMASS=(["Z", "Yp1", "X"], v.astype(dtype)),
+            WVELMASS=(["Zl", "Y", "X"], w.astype(dtype)),
+            streamfunc=(["Zl", "Yp1", "Xp1"], stream),
+        ),
+        as_xarray,
+    )
+
+
+def rectilinear(nlat=60, nlon=120, nt=1, dtype=np.float64, as_xarray=False):
+    """Global 1-D lon/lat grid (``readiness['h'] == 'rectilinear'``, reference ``ocedata.py:255``)."""
+    lon = np.linspace(-180, 180, nlon, endpoint=False)
+    lat = np.linspace(-75, 75, nlat)
+    lam, phi = np.meshgrid(np.deg2rad(lon), np.deg2rad(lat))
+    u = 0.4 * np.cos(phi) * (1 + 0.5 * np.sin(3 * lam))
+    v = 0.12 * np.sin(2 * lam) * np.cos(phi) ** 2
+    coords = dict(lon=(["lon"], lon), lat=(["lat"], lat))
+    if nt > 1:
+        time = np.arange(nt) * 86400.0 * 5
+        coords["time"] = (["time"], time)
+        scale = (1 + 0.25 * np.arange(nt)).reshape(nt, 1, 1)
+        data = dict(
+            u=(["time", "lat", "lon"], (u * scale).astype(dtype)),
+            v=(["time", "lat", "lon"], (v * scale).astype(dtype)),
+        )
+    else:
+        data = dict(u=(["lat", "lon"], u.astype(dtype)), v=(["lat", "lon"], v.astype(dtype)))
+    return _dataset(coords, data, as_xarray)
+
+
+# ----------------------------------------------------------------------------------------------
+# LLC-shaped grid
+# ----------------------------------------------------------------------------------------------
+_LAT_S, _LAT_N = -78.0, 66.0
+_SECTOR_W = (-38.0, 52.0, 142.0, 232.0)  # west edge of the four 90 degree sectors
+_CAP_LON0 = 97.0
+
+
+def _llc_face_lonlat(face, fy, fx, n):
+    """lon/lat (deg) of the point with real-valued index ``(fy, fx)`` on ``face``.
+
+    Integer indices are G (corner) points, ``+0.5`` gives C (centre) points.  The layout follows
+    SURVEY.md §8d and was checked edge by edge against ``LLC_FACE_CONNECT``.
+    """
+    fy = np.asarray(fy, float)
+    fx = np.asarray(fx, float)
+    dlat = (_LAT_N - _LAT_S) / (3 * n)
+    dlon = 90.0 / n
+    if face in (0, 1, 2, 3, 4, 5):
+        sector = 0 if face < 3 else 1
+        row = face % 3  # 0 = southern-most
+        lon = _SECTOR_W[sector] + fx * dlon
+        lat = _LAT_S + (row * n + fy) * dlat
+    elif face in (7, 8, 9, 10, 11, 12):
+        sector = 2 if face < 10 else 3
+        row = (face - 7) % 3  # 0 = northern-most (touches the cap)
+        lon = _SECTOR_W[sector] + fy * dlon
+        lat = _LAT_N - (row * n + fx) * dlat
+    elif face == 6:
+        a = (fx - n / 2) / (n / 2)
+        b = (fy - n / 2) / (n / 2)
+        r = np.maximum(np.abs(a), np.abs(b))
+        rs = np.where(r == 0, 1.0, r)
+        bottom = (b <= -np.abs(a)) & (r > 0)
+        right = (a >= np.abs(b)) & ~bottom & (r > 0)
+        top = (b >= np.abs(a)) & ~bottom & ~right & (r > 0)
+        angle = np.where(
+            bottom,
+            45 * a / rs,
+            np.where(right, 90 + 45 * b / rs, np.where(top, 180 - 45 * a / rs, 270 - 45 * b / rs)),
+        )
+        angle = np.where(r == 0, 0.0, angle)
+        lon = _CAP_LON0 + angle
+        lat = 90.0 - (90.0 - _LAT_N) * r
+    else:
+        raise ValueError(face)
+    lon = (lon + 180.0) % 360.0 - 180.0
+    return lon, lat
+
+
+def _sph2cart(lon, lat):
+    lam = np.deg2rad(lon)
+    phi = np.deg2rad(lat)
+    return np.stack([np.cos(phi) * np.cos(lam), np.cos(phi) * np.sin(lam), np.sin(phi)], axis=-1)
+
+
+def _flow_cart(p, amp_rot=1.0, amp_div=0.0):
+    """Analytic horizontal velocity (m/s, cartesian components) at unit vectors ``p``.
+
+    rotational part: ``ue = cos(phi)(1 + 0.5 sin 3 lam)``, ``vn = 0.3 sin(2 lam) cos^2(phi)``
+    divergent part : ``ue = 0.5 cos(phi) cos(2 lam)``,     ``vn = 0.5 cos^2(phi) sin(3 phi)``
+    both vanish at the poles.
+    """
+    x, y, z = p[..., 0], p[..., 1], p[..., 2]
+    lam = np.arctan2(y, x)
+    cphi = np.sqrt(np.maximum(x * x + y * y, 1e-30))
+    phi = np.arctan2(z, cphi)
+    ue = amp_rot * cphi * (1 + 0.5 * np.sin(3 * lam)) + amp_div * 0.5 * cphi * np.cos(2 * lam)
+    vn = amp_rot * 0.3 * np.sin(2 * lam) * cphi**2 + amp_div * 0.5 * cphi**2 * np.sin(3 * phi)
+    east = np.stack([-np.sin(lam), np.cos(lam), np.zeros_like(lam)], axis=-1)
+    north = np.stack([-z * np.cos(lam), -z * np.sin(lam), cphi], axis=-1)
+    return ue[..., None] * east + vn[..., None] * north
+
+
+def _llc_land(n, land_blobs=False, xc=None, yc=None):
+    """maskC for one level: 1 = wet.  Land where the reference cannot index."""
+    k = max(2, n // 22)  # 4 for n = 90
+    mask = np.ones((13, n, n), np.int8)
+    mask[[0, 3], :2, :] = 0  # southern rows (no neighbour below faces 0 and 3)
+    mask[[9, 12], :, n - 2 :] = 0  # right columns of faces 9, 12 (no neighbour)
+    # the four corners of the cap and the touching corners of the neighbouring faces
+    for sy in (slice(0, k), slice(n - k, n)):
+        for sx in (slice(0, k), slice(n - k, n)):
+            mask[6, sy, sx] = 0
+    mask[2, n - k :, :k] = 0
+    mask[2, n - k :, n - k :] = 0
+    mask[5, n - k :, :k] = 0
+    mask[5, n - k :, n - k :] = 0
+    for f in (7, 10):
+        mask[f, :k, :k] = 0
+        mask[f, n - k :, :k] = 0
+    c = n // 2
+    mask[6, c - k // 2 - 1 : c + k // 2 + 1, c - k // 2 - 1 : c + k // 2 + 1] = 0  # pole
+    if land_blobs:
+        lam = np.deg2rad(xc)
+        phi = np.deg2rad(yc)
+        mask[np.sin(5 * lam) * np.cos(7 * phi) > 0.6] = 0
+    return mask
+
+
+def llc(
+    n=90,
+    nz=50,
+    nt=0,
+    u0=0.5,
+    dtype=np.float64,
+    land_blobs=False,
+    tracers=False,
+    as_xarray=False,
+    seed=0,
+):
+    """LLC-shaped synthetic dataset: 13 faces x n x n, ``nz`` levels (0 = 2-D), ``nt`` snapshots (0 = static).
+
+    Variables: ``XC YC XG YG`` (XG/YG have size ``n`` like ECCO, so ``g_shape == h_shape``),
+    ``dxG dyG rA CS SN``, and for ``nz > 0`` ``Z Zl Zp1 drF drC hFacC maskC``;
+    velocities ``UVELMASS VVELMASS WVELMASS`` (m/s on the walls) and transports
+    ``utrans vtrans wtrans`` (m^3/s, with W from continuity so the 3-D flow is volume conserving
+    away from land); ``T``/``S`` tracers if requested.
+    """
+    rng = np.random.default_rng(seed)
+    idx = np.arange(n + 1, dtype=float)
+    gy, gx = np.meshgrid(idx, idx, indexing="ij")  # (n+1, n+1) corner indices
+    cy, cx = gy[:n, :n] + 0.5, gx[:n, :n] + 0.5
+
+    XG = np.zeros((13, n, n))
+    YG = np.zeros((13, n, n))
+    XC = np.zeros((13, n, n))
+    YC = np.zeros((13, n, n))
+    dxG = np.zeros((13, n, n))
+    dyG = np.zeros((13, n, n))
+    rA = np.zeros((13, n, n))
+    CS = np.zeros((13, n, n))
+    SN = np.zeros((13, n, n))
+    # unit tangent x wall-length products, kept to project the analytic flow on the walls
+    u_nrm = np.zeros((13, n, n, 3))  # normal of the west wall (towards +ix), unit
+    v_nrm = np.zeros((13, n, n, 3))  # normal of the south wall (towards +iy), unit
+    u_mid = np.zeros((13, n, n, 3))
+    v_mid = np.zeros((13, n, n, 3))
+    for f in range(13):
+        lon_g, lat_g = _llc_face_lonlat(f, gy, gx, n)
+        lon_c, lat_c = _llc_face_lonlat(f, cy, cx, n)
+        pg = _sph2cart(lon_g, lat_g)  # (n+1,n+1,3)
+        XG[f], YG[f] = lon_g[:n, :n], lat_g[:n, :n]
+        XC[f], YC[f] = lon_c, lat_c
+        tx = pg[:n, 1:] - pg[:n, :n]  # south wall: G(iy,ix) -> G(iy,ix+1)
+        ty = pg[1:, :n] - pg[:n, :n]  # west wall:  G(iy,ix) -> G(iy+1,ix)
+        dxG[f] = np.linalg.norm(tx, axis=-1) * R_EARTH
+        dyG[f] = np.linalg.norm(ty, axis=-1) * R_EARTH
+        # cell area from the two triangles of the quadrilateral
+        d1 = pg[1:, 1:] - pg[:n, :n]
+        a1 = 0.5 * np.linalg.norm(np.cross(tx, d1), axis=-1)
+        a2 = 0.5 * np.linalg.norm(np.cross(d1, ty), axis=-1)
+        rA[f] = (a1 + a2) * R_EARTH**2
+        mu = pg[:n, :n] + 0.5 * ty
+        mu /= np.linalg.norm(mu, axis=-1, keepdims=True)
+        mv = pg[:n, :n] + 0.5 * tx
+        mv /= np.linalg.norm(mv, axis=-1, keepdims=True)
+        nu = np.cross(ty, mu)  # y_local x up = x_local
+        nv = np.cross(mv, tx)  # up x x_local = y_local
+        with np.errstate(invalid="ignore", divide="ignore"):
+            nu /= np.linalg.norm(nu, axis=-1, keepdims=True)
+            nv /= np.linalg.norm(nv, axis=-1, keepdims=True)
+        u_nrm[f], v_nrm[f] = np.nan_to_num(nu), np.nan_to_num(nv)
+        u_mid[f], v_mid[f] = mu, mv
+        # orientation of local x relative to east at the centre
+        pc = _sph2cart(lon_c, lat_c)
+        xdir = 0.5 * (pg[:n, 1:] + pg[1:, 1:]) - 0.5 * (pg[:n, :n] + pg[1:, :n])
+        lam = np.deg2rad(lon_c)
+        phi = np.deg2rad(lat_c)
+        east = np.stack([-np.sin(lam), np.cos(lam), np.zeros_like(lam)], axis=-1)
+        north = np.stack(
+            [-np.sin(phi) * np.cos(lam), -np.sin(phi) * np.sin(lam), np.cos(phi)], axis=-1
+        )
+        ce = (xdir * east).sum(-1)
+        cn = (xdir * north).sum(-1)
+        nrm = np.hypot(ce, cn)
+        nrm[nrm == 0] = 1.0
+        CS[f], SN[f] = ce / nrm, cn / nrm
+        del pc
+
+    land2d = _llc_land(n, land_blobs, XC, YC)
+
+    coords = dict(
+        XC=(["face", "Y", "X"], XC),
+        YC=(["face", "Y", "X"], YC),
+        XG=(["face", "Yp1", "Xp1"], XG),
+        YG=(["face", "Yp1", "Xp1"], YG),
+        dxG=(["face", "Yp1", "X"], dxG),
+        dyG=(["face", "Y", "Xp1"], dyG),
+        rA=(["face", "Y", "X"], rA),
+        CS=(["face", "Y", "X"], CS),
+        SN=(["face", "Y", "X"], SN),
+    )
+
+    # wet-wall masks: a wall carries flow only if the cells on both sides are wet
+    from .topology import Topology  # noqa: PLC0415  (host-side index logic of the product)
+
+    tp = Topology.from_shape((13, n, n))
+    f_i, y_i, x_i = np.meshgrid(np.arange(13), np.arange(n), np.arange(n), indexing="ij")
+    flat = (f_i.ravel(), y_i.ravel(), x_i.ravel())
+    lf, ly, lx = tp.ind_tend_vec(flat, np.full(f_i.size, 2), swallow=True)  # cell to the left
+    df, dy_, dx_ = tp.ind_tend_vec(flat, np.full(f_i.size, 1), swallow=True)  # cell below
+    wet_u = (land2d * land2d[lf, ly, lx].reshape(13, n, n)).astype(float)
+    wet_v = (land2d * land2d[df, dy_, dx_].reshape(13, n, n)).astype(float)
+    # cells without a left / lower neighbour keep their own index -> treat as closed wall
+    no_left = (lf.reshape(13, n, n) == f_i) & (lx.reshape(13, n, n) == x_i)
+    no_down = (df.reshape(13, n, n) == f_i) & (dy_.reshape(13, n, n) == y_i)
+    wet_u[no_left] = 0.0
+    wet_v[no_down] = 0.0
+
+    vel_u_rot = (_flow_cart(u_mid, 1.0, 0.0) * u_nrm).sum(-1) * wet_u  # (13,n,n) per unit amplitude
+    vel_v_rot = (_flow_cart(v_mid, 1.0, 0.0) * v_nrm).sum(-1) * wet_v
+    vel_u_div = (_flow_cart(u_mid, 0.0, 1.0) * u_nrm).sum(-1) * wet_u
+    vel_v_div = (_flow_cart(v_mid, 0.0, 1.0) * v_nrm).sum(-1) * wet_v
+
+    data = {}
+    if nz > 0:
+        drF = np.linspace(10.0, 450.0, nz)
+        Zp1 = np.concatenate([[0.0], -np.cumsum(drF)])
+        Z = 0.5 * (Zp1[1:] + Zp1[:-1])
+        Zl = Zp1[:-1]
+        drC = np.concatenate([[Z[0] - 0.0], Z[:-1] - Z[1:]]) * -1.0
+        drC = np.abs(drC)
+        maskC = np.broadcast_to(land2d, (nz, 13, n, n)).copy()
+        g_rot = np.exp(Z / 1000.0)
+        g_div = np.cos(np.pi * (np.arange(nz) + 0.5) / nz)
+        g_div = g_div - (g_div * drF).sum() / drF.sum()  # zero vertical integral -> W(surface) = 0
+        g_div *= 0.3
+        uvel = u0 * (g_rot[:, None, None, None] * vel_u_rot + g_div[:, None, None, None] * vel_u_div)
+        vvel = u0 * (g_rot[:, None, None, None] * vel_v_rot + g_div[:, None, None, None] * vel_v_div)
+        utr = uvel * drF[:, None, None, None] * dyG
+        vtr = vvel * drF[:, None, None, None] * dxG
+        # east / north wall transports of every cell (across faces) -> W from continuity
+        rf, ry, rx = tp.wall_source(flat, "right")
+        uf, uy, ux = tp.wall_source(flat, "top")
+        r_is_v = tp.wall_source_is_other(flat, "right").reshape(13, n, n)
+        t_is_u = tp.wall_source_is_other(flat, "top").reshape(13, n, n)
+        east = np.where(r_is_v, vtr[:, rf, ry, rx].reshape(nz, 13, n, n), utr[:, rf, ry, rx].reshape(nz, 13, n, n))
+        nrth = np.where(t_is_u, utr[:, uf, uy, ux].reshape(nz, 13, n, n), vtr[:, uf, uy, ux].reshape(nz, 13, n, n))
+        closed_r = tp.wall_source_missing(flat, "right").reshape(13, n, n)
+        closed_t = tp.wall_source_missing(flat, "top").reshape(13, n, n)
+        east = np.where(closed_r, 0.0, east)
+        nrth = np.where(closed_t, 0.0, nrth)
+        divh = (east - utr) + (nrth - vtr)
+        wtr = np.zeros((nz, 13, n, n))
+        acc = np.zeros((13, n, n))
+        for k in range(nz - 1, -1, -1):  # W(bottom) = 0, integrate upwards
+            acc = acc - divh[k]
+            wtr[k] = acc
+        wtr *= maskC
+        wvel = wtr / np.where(rA > 0, rA, 1.0)
+        coords.update(
+            Z=(["Z"], Z),
+            Zl=(["Zl"], Zl),
+            Zp1=(["Zp1"], Zp1),
+            drF=(["Z"], drF),
+            drC=(["Z"], drC),
+            hFacC=(["Z", "face", "Y", "X"], maskC.astype(float)),
+            maskC=(["Z", "face", "Y", "X"], maskC),
+        )
+        udims, vdims, wdims = (
+            ["Z", "face", "Y", "Xp1"],
+            ["Z", "face", "Yp1", "X"],
+            ["Zl", "face", "Y", "X"],
+        )
+        cdims = ["Z", "face", "Y", "X"]
+        fields = dict(
+            UVELMASS=(udims, uvel),
+            VVELMASS=(vdims, vvel),
+            WVELMASS=(wdims, wvel),
+            utrans=(udims, utr),
+            vtrans=(vdims, vtr),
+            wtrans=(wdims, wtr),
+        )
+        if tracers:
+            lam = np.deg2rad(XC)
+            phi = np.deg2rad(YC)
+            zz = Z[:, None, None, None]
+            fields["T"] = (cdims, 2.0 + 25.0 * np.cos(phi) ** 2 * np.exp(zz / 800.0) + np.sin(2 * lam))
+            fields["S"] = (cdims, 34.5 + 0.8 * np.sin(phi) * np.cos(lam) + zz / 5000.0)
+    else:
+        uvel = u0 * (vel_u_rot + 0.0 * vel_u_div)
+        vvel = u0 * (vel_v_rot + 0.0 * vel_v_div)
+        udims, vdims = ["face", "Y", "Xp1"], ["face", "Yp1", "X"]
+        fields = dict(
+            UVELMASS=(udims, uvel),
+            VVELMASS=(vdims, vvel),
+            utrans=(udims, uvel * dyG),
+            vtrans=(vdims, vvel * dxG),
+        )
+        if tracers:
+            lam = np.deg2rad(XC)
+            phi = np.deg2rad(YC)
+            fields["T"] = (["face", "Y", "X"], 2.0 + 25.0 * np.cos(phi) ** 2 + np.sin(2 * lam))
+
+    if nt > 0:
+        time = np.arange(nt) * 86400.0 * 10
+        coords["time"] = (["time"], time)
+        scale = 1.0 + 0.3 * np.sin(np.arange(nt) * 1.3)
+        for name, (dims, arr) in fields.items():
+            wob = scale.reshape((nt,) + (1,) * arr.ndim)
+            if name in ("T", "S"):
+                wob = 1.0 + 0.01 * (wob - 1.0)
+            data[name] = (["time"] + dims, (arr[None] * wob).astype(dtype))
+    else:
+        for name, (dims, arr) in fields.items():
+            data[name] = (dims, arr.astype(dtype))
+    del rng
+    return _dataset(coords, data, as_xarray)
+
+
+def llc_seed_particles(ds, num, seed=1, lat_range=(-70.0, 85.0), depth_range=(5.0, 1000.0), wet_only=True):
+    """``num`` particle positions uniform on the sphere (normal-vector method), SURVEY.md §8d."""
+    rng = np.random.default_rng(seed)
+    lon = np.empty(0)
+    lat = np.empty(0)
+    while len(lon) < num:
+        v = rng.normal(size=(2 * num + 16, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        la = np.rad2deg(np.arcsin(v[:, 2]))
+        lo = np.rad2deg(np.arctan2(v[:, 1], v[:, 0]))
+        ok = (la > lat_range[0]) & (la < lat_range[1])
+        lon = np.concatenate([lon, lo[ok]])
+        lat = np.concatenate([lat, la[ok]])
+    lon, lat = lon[:num], lat[:num]
+    dep = -rng.uniform(depth_range[0], depth_range[1], num)
+    del wet_only, ds
+    return lon, lat, dep
