@@ -1,0 +1,195 @@
+/* seaduck_b200 -- C ABI of the B200 (sm_100a) library behind seaduck's Lagrangian / interpolation
+ * hot path.  Plain pointers and sizes only; no torch types.
+ *
+ * The reference (MaceKuailv/seaduck) has no FFI: its seams are Python methods.
+ * Each entry point below names the reference method whose body it replaces (file:line into the
+ * reference tree).  INTEGRATION.md shows the ctypes stub a seaduck maintainer would add.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative SDK_E* code on failure; sdk_last_error()
+ *    returns a thread-local message.
+ *  - pointers documented "device" must be device memory on the current CUDA device; the library
+ *    borrows them for the duration of the call (grids: for the lifetime of the handle).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = default stream).  Device-pointer entry
+ *    points are asynchronous with respect to the host; *_host entry points synchronise.
+ */
+#ifndef SEADUCK_B200_H
+#define SEADUCK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDK_ABI_VERSION 1
+
+enum { SDK_OK = 0, SDK_EINVAL = -1, SDK_ECUDA = -2, SDK_EUNSUPPORTED = -3, SDK_ENOMEM = -4 };
+
+/* grid kinds: reference Topology.typ, seaduck/topology.py:303-338 */
+enum { SDK_TYP_BOX = 0, SDK_TYP_XPERIODIC = 1, SDK_TYP_LLC = 2 };
+/* horizontal scheme: reference OceData.readiness["h"], seaduck/ocedata.py:231 */
+enum { SDK_H_OCEANPARCEL = 0, SDK_H_LOCAL_CARTESIAN = 1, SDK_H_RECTILINEAR = 2 };
+/* storage type of velocity / volume fields (math is always fp64) */
+enum { SDK_F64 = 0, SDK_F32 = 1 };
+
+/* per-particle status bits written by sdk_advect */
+enum {
+    SDK_ST_MAX_ITER = 1,   /* still live after max_iteration steps (reference warns, lagrangian.py:794) */
+    SDK_ST_EDGE = 2,       /* tried to leave through an edge without neighbour ("Some points are on the edge") */
+    SDK_ST_BAD_CELL = 4,   /* cell whose walls/corners the reference cannot index (it raises there) */
+    SDK_ST_OUT = 8         /* left a closed (box) domain; particle frozen */
+};
+
+#define SDK_MAX_FACES 16
+
+typedef struct sdk_grid sdk_grid; /* opaque */
+
+/* Replaces the in-memory grid of OceData._grid2array (seaduck/ocedata.py:411) and the Topology
+ * tables (seaduck/topology.py:8-30).  All array pointers are DEVICE pointers except nbr_face /
+ * nbr_edge which are HOST pointers copied into the handle (they end up in constant memory). */
+typedef struct sdk_grid_desc {
+    int32_t typ;       /* SDK_TYP_* */
+    int32_t has_face;  /* 1 if the grid has a face dimension */
+    int32_t nface;     /* 1 when has_face == 0 */
+    int32_t ny, nx;    /* shape of XC (per face) */
+    int32_t gny, gnx;  /* shape of XG (per face) */
+    int32_t hmode;     /* SDK_H_* */
+    int32_t n_zl;      /* len(Zl) (nz + 1), 0 = no vertical staggered grid */
+    int32_t n_z;       /* len(dZl) == number of cells in the vertical, 0 = none */
+    int32_t n_zc;      /* len(Z), 0 = none */
+    int32_t reserved;
+    const int32_t *nbr_face; /* host [nface*4]: face across edge (up,down,left,right), -1 = none */
+    const int32_t *nbr_edge; /* host [nface*4]: which edge of that face touches us */
+    const float *XC, *YC;    /* device [nface*ny*nx] */
+    const float *XG, *YG;    /* device [nface*gny*gnx] */
+    const float *dX, *dY;    /* device [nface*ny*nx] or NULL */
+    const float *CS, *SN;    /* device or NULL */
+    const float *Zl, *dZl;   /* device [n_zl], [n_z] or NULL */
+    const float *Z, *dZ;     /* device [n_zc] or NULL */
+    /* device [nface*(nx+ny)*3] flat XG indices of the LR, UR, UL corners of the cells on the top
+     * row (slot ix) and right column (slot nx+iy) of each face, -1 where the reference raises;
+     * required when gny == ny or gnx == nx (reference find_px_py, seaduck/utils.py:495). */
+    const int32_t *corner_tab;
+} sdk_grid_desc;
+
+/* Velocity (or transport) snapshot slab; replaces Particle.update_uvw_array's uarray/varray/warray
+ * (seaduck/lagrangian.py:175) and OceData["Vol"] (seaduck/ocedata.py:303).  Device pointers.
+ * Layout: U [nt][nzU][nface][nyU][nxU], V [nt][nzU][nface][nyV][nxV], W [nt][nzW][nface][ny][nx],
+ * Vol [nz][nface][ny][nx] (axes of size 1 when absent). */
+typedef struct sdk_velocity {
+    const void *U, *V, *W; /* W may be NULL (wname=None) */
+    const void *Vol;       /* required when transport != 0 */
+    int32_t dtype;         /* SDK_F64 / SDK_F32 for U, V, W */
+    int32_t vol_dtype;
+    int32_t has_time, it0, nt; /* it0 = first snapshot held (reference prefetch_prefix / itmin) */
+    int32_t has_z, nzU, nzW;
+    int32_t nyU, nxU, nyV, nxV;
+    int32_t u_stag, v_stag;    /* U lives on Xp1 / V on Yp1 */
+    int32_t vol_has_z;
+    int32_t transport;         /* divide by Vol instead of dx|dy|dzl (lagrangian.py:268-286) */
+} sdk_velocity;
+
+/* Particle state, structure of arrays, DEVICE pointers, n entries each (px, py: 4*n, corner-major).
+ * Replaces the attributes of Particle / RelCoord that the time loop touches
+ * (seaduck/lagrangian.py:56, seaduck/ocedata.py:119-143). */
+typedef struct sdk_particles {
+    int64_t n;
+    double *lon, *lat, *dep, *t;
+    int32_t *face, *iy, *ix, *izl, *it; /* izl = izl_lin */
+    double *rx, *ry, *rzl;              /* rzl = rzl_lin */
+    double *u, *v, *w, *du, *dv, *dw;
+    double *px, *py;
+    float *dx, *dy;      /* kept as state: the reference never refreshes them in oceanparcel mode */
+    double *bzl, *dzl;   /* bzl_lin, dzl_lin */
+    double *vol;
+    int32_t *status;     /* out, SDK_ST_* bits */
+    int32_t *niter;      /* out, analytic steps taken in this call */
+    int32_t *ncross;     /* out, steps that ended on a wall (tend < 6) */
+    const int32_t *active; /* optional: particles with active[i] == 0 are left untouched (callback) */
+} sdk_particles;
+
+typedef struct sdk_advect_params {
+    double tol;            /* 1e-4  (lagrangian.py:754) */
+    double trim_tol;       /* 1e-14 (lagrangian.py:765) */
+    int32_t max_iteration; /* Particle(max_iteration=200) */
+    int32_t kick_back;     /* free_surface == "kick_back" (lagrangian.py:629) */
+    int32_t has_dep;       /* particles carry a depth (rzl_lin is not None) */
+    int32_t refill_threshold; /* idle lanes per warp that trigger a refill, 0 = library default */
+    int32_t blocks_per_sm;    /* 0 = library default */
+    int32_t threads_per_block;/* 0 = library default */
+} sdk_advect_params;
+
+/* Crossing log, replaces Particle.note_taking (seaduck/lagrangian.py:301).  Device pointers.
+ * Records of particle i go to [offset[i], offset[i] + count[i]).  With offset == NULL only
+ * count[] is written (first pass of count -> scan -> fill). */
+typedef struct sdk_log {
+    int64_t capacity;
+    const int64_t *offset;
+    int32_t *count;
+    int32_t *fc, *it, *izl, *iy, *ix, *vs;
+    double *rzl, *rx, *ry, *tt, *uu, *vv, *ww, *du, *dv, *dw, *xx, *yy, *zz;
+    int32_t emit_start; /* write the stamp-15 record first (lagrangian.py:887) */
+} sdk_log;
+
+int sdk_abi_version(void);
+const char *sdk_last_error(void);
+/* number of SMs of the current device (grid sizing), <0 on error */
+int sdk_sm_count(void);
+
+/* OceData(...) grid staging, seaduck/ocedata.py:164,411 */
+int sdk_grid_create(const sdk_grid_desc *desc, sdk_grid **out);
+int sdk_grid_destroy(sdk_grid *grid);
+
+/* Particle.to_next_stop, seaduck/lagrangian.py:741 (trim :400, analytical_step :561,
+ * cross_cell_wall :706, get_vol :202, get_u_du :218).  In place on the device state.
+ * `commit` = 0 runs the loop without writing the state back (counting pass for the log). */
+int sdk_advect(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, double t_stop,
+               const sdk_advect_params *par, const sdk_log *log, int commit, void *stream);
+
+/* Particle.get_u_du alone, seaduck/lagrangian.py:218 (after a velocity-slab swap). */
+int sdk_get_u_du(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, int has_dep,
+                 void *stream);
+
+/* Same as sdk_advect but every pointer in `p` is HOST memory (pinned for full speed): copies the
+ * state to the device, advects, copies it back, synchronises.  `scratch` is a device buffer of at
+ * least sdk_particles_bytes(n) bytes. */
+int64_t sdk_particles_bytes(int64_t n);
+int sdk_advect_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *host_p,
+                    double t_stop, const sdk_advect_params *par, void *scratch, void *stream);
+
+
+/* Output of sdk_locate: DEVICE pointers, n entries each (px, py: 4*n).  NULL members are skipped.
+ * Mirrors the RelCoord families of the reference (seaduck/ocedata.py:119-143). */
+typedef struct sdk_located {
+    int32_t *face, *iy, *ix;
+    double *rx, *ry;
+    float *cs, *sn, *dx, *dy, *bx, *by;
+    double *px, *py;
+    int32_t *iz;       double *rz, *dz, *bz;                 /* nearest Z      (_find_rel_v)      */
+    int32_t *izl_near; double *rzl_near, *dzl_near, *bzl_near; /* nearest Zl   (_find_rel_vl)     */
+    int32_t *izl;      double *rzl, *dzl, *bzl;              /* linear Zl      (_find_rel_vl_lin) */
+    int32_t *it;       double *rt, *dt, *bt;                 /* nearest time   (_find_rel_t)      */
+    int32_t *status;
+} sdk_located;
+
+/* Build the lat/lon bucket grid used by sdk_locate (replaces create_tree, seaduck/utils.py:225).
+ * Buckets cover [lon0, lon0+span_lon] x [lat0, lat0+span_lat] degrees with nlon x nlat buckets;
+ * span_lon >= 360 means periodic in longitude. */
+int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span_lon, double span_lat,
+                           int32_t nlon, int32_t nlat, void *stream);
+
+/* Position.from_latlon, seaduck/eulerian.py:138 -> OceData._find_rel_h/_v/_vl/_vl_lin/_t
+ * (seaduck/ocedata.py:422-488).  lon/lat, dep, t: device arrays of n doubles or NULL.
+ * ts: device array of the n_t model time levels (seconds) or NULL. */
+int sdk_locate(const sdk_grid *grid, int64_t n, const double *lon, const double *lat, const double *dep,
+               const double *t, const double *ts, int32_t n_t, const sdk_located *out, void *stream);
+
+/* it := 0 before time_midp[0], else find_rel(t, time_midp) + 1 (seaduck/lagrangian.py:796-802). */
+int sdk_time_index(const double *t, const double *time_midp, int32_t n_midp, int32_t *it, int64_t n,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEADUCK_B200_H */

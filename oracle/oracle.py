@@ -482,3 +482,78 @@ class OracleParticle:
                 it, _, _, _ = find_rel(self.t[~before_first], g.time_midp)
                 self.it[~before_first] = it + 1
         return int(self.ncross.sum())
+
+
+def oracle_particle_from_od(od, x, y, z, t, uname="UVELMASS", vname="VVELMASS", wname="WVELMASS", transport=False,
+                            save_raw=False, nthreads=1, **kw):
+    """Build an :class:`OracleParticle` the way ``Particle.__init__`` does (reference lagrangian.py:93):
+    Vol from drF*rA*hFacC when transport, W surface level zeroed for ``free_surface="noflux"``,
+    velocity slab ``[itmin:itmax+1]`` when the data has a time axis."""
+    grid = OracleGrid(od)
+    full_u = np.asarray(od[uname])
+    full_v = np.asarray(od[vname])
+    full_w = np.asarray(od[wname]) if wname is not None else None
+    u_dims, v_dims = tuple(od[uname].dims), tuple(od[vname].dims)
+    if full_w is not None and kw.get("free_surface", "noflux") == "noflux":
+        full_w = full_w.copy()
+        if "time" in u_dims:
+            full_w[:, 0] = 0
+        else:
+            full_w[0] = 0
+    vol = None
+    if transport:
+        try:
+            vol = np.asarray(od["Vol"])
+        except (KeyError, AttributeError):
+            od._add_missing_vol(as_numpy=True)
+            vol = np.asarray(od["Vol"])
+    has_time = "time" in u_dims
+    # first pass to know `it`
+    op = OracleParticle.__new__(OracleParticle)
+    op._full = (full_u, full_v, full_w, vol, u_dims, v_dims, has_time)
+    if has_time:
+        it, _, _, _ = find_rel(np.asarray(t, float), grid.ts, above=False)
+        itmin, itmax = int(it.min()), int(it.max())
+        sl = slice(itmin, itmax + 1)
+        ua, va, wa = full_u[sl], full_v[sl], None if full_w is None else full_w[sl]
+    else:
+        itmin = 0
+        ua, va, wa = full_u, full_v, full_w
+    OracleParticle.__init__(op, grid, x, y, z, t, ua, va, wa, vol, u_dims, v_dims, transport=transport,
+                            save_raw=save_raw, it0=itmin, nthreads=nthreads,
+                            free_surface=kw.get("free_surface", "noflux"), max_iteration=kw.get("max_iteration", 200))
+    return op
+
+
+def oracle_update_uvw(op):
+    """reference Particle.update_uvw_array (lagrangian.py:175) + get_u_du."""
+    full_u, full_v, full_w, vol, u_dims, v_dims, has_time = op._full
+    if not has_time:
+        return
+    itmin, itmax = int(op.it.min()), int(op.it.max())
+    sl = slice(itmin, itmax + 1)
+    op.set_velocity(full_u[sl], full_v[sl], None if full_w is None else full_w[sl], vol, u_dims, v_dims, it0=itmin)
+    op.get_u_du()
+
+
+def oracle_to_list_of_time(op, normal_stops, update_stops="default"):
+    """reference Particle.to_list_of_time (lagrangian.py:804); yields (stop, records, state) per snapshot."""
+    g = op.grid
+    has_time = op._full[6]
+    t0 = op.t[0]
+    t_min = min(np.min(normal_stops), t0)
+    t_max = max(np.max(normal_stops), t0)
+    if isinstance(update_stops, str):
+        update_stops = g.time_midp[(t_min < g.time_midp) & (g.time_midp < t_max)] if has_time else []
+    temp = [(s, 0) for s in normal_stops] + [(s, 1) for s in update_stops]
+    temp.sort(key=lambda x: abs(x[0] - t0))
+    op.get_u_du()
+    out = []
+    for i, (tl, upd) in enumerate(temp):
+        op.to_next_stop(tl, emit_start=True)
+        if upd or i == 0:
+            oracle_update_uvw(op)
+        rec = None if op.records is None else {k: v.copy() for k, v in op.records.items()}
+        state = {k: getattr(op, k).copy() for k in _P_F64 + _P_I32 + ("rx", "ry", "rzl", "u", "v", "w", "du", "dv", "dw")}
+        out.append((tl, rec, state))
+    return out

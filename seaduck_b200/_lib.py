@@ -1,0 +1,180 @@
+"""ctypes binding of ``libseaduck_b200.so`` (C ABI declared in ``include/seaduck_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` / :func:`build`.  There is no CPU
+fallback: if the shared object is missing or cannot be loaded every compute entry point raises.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+SO_PATH = os.path.join(_HERE, "libseaduck_b200.so")
+SOURCES = ["advect.cu", "locate.cu", "interp.cu", "capi.cu"]
+NVCC_FLAGS = [
+    "-gencode",
+    "arch=compute_100a,code=sm_100a",
+    "-O3",
+    "-lineinfo",
+    "-fmad=false",  # reference arithmetic is numpy: no fused multiply-add (index parity)
+    "-std=c++17",
+    "-shared",
+    "-Xcompiler",
+    "-fPIC",
+]
+
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+f32p = C.POINTER(C.c_float)
+f64p = C.POINTER(C.c_double)
+vp = C.c_void_p
+
+
+def _fields(spec):
+    out = []
+    for typ, names in spec:
+        for n in names.split():
+            out.append((n, typ))
+    return out
+
+
+class GridDesc(C.Structure):
+    _fields_ = _fields(
+        [
+            (C.c_int32, "typ has_face nface ny nx gny gnx hmode n_zl n_z n_zc reserved"),
+            (vp, "nbr_face nbr_edge XC YC XG YG dX dY CS SN Zl dZl Z dZ corner_tab"),
+        ]
+    )
+
+
+class Velocity(C.Structure):
+    _fields_ = _fields(
+        [
+            (vp, "U V W Vol"),
+            (
+                C.c_int32,
+                "dtype vol_dtype has_time it0 nt has_z nzU nzW nyU nxU nyV nxV u_stag v_stag vol_has_z transport",
+            ),
+        ]
+    )
+
+
+PARTICLE_F64 = "lon lat dep t".split()
+PARTICLE_I32 = "face iy ix izl it".split()
+PARTICLE_F64B = "rx ry rzl u v w du dv dw px py".split()
+PARTICLE_F32 = "dx dy".split()
+PARTICLE_F64C = "bzl dzl vol".split()
+PARTICLE_OUT = "status niter ncross active".split()
+
+
+class Particles(C.Structure):
+    _fields_ = (
+        [("n", C.c_int64)]
+        + [(n, vp) for n in PARTICLE_F64 + PARTICLE_I32 + PARTICLE_F64B + PARTICLE_F32 + PARTICLE_F64C + PARTICLE_OUT]
+    )
+
+
+class AdvectParams(C.Structure):
+    _fields_ = [
+        ("tol", C.c_double),
+        ("trim_tol", C.c_double),
+        ("max_iteration", C.c_int32),
+        ("kick_back", C.c_int32),
+        ("has_dep", C.c_int32),
+        ("refill_threshold", C.c_int32),
+        ("blocks_per_sm", C.c_int32),
+        ("threads_per_block", C.c_int32),
+    ]
+
+
+LOG_I32 = "fc it izl iy ix vs".split()
+LOG_F64 = "rzl rx ry tt uu vv ww du dv dw xx yy zz".split()
+
+
+class Log(C.Structure):
+    _fields_ = (
+        [("capacity", C.c_int64), ("offset", vp), ("count", vp)]
+        + [(n, vp) for n in LOG_I32 + LOG_F64]
+        + [("emit_start", C.c_int32)]
+    )
+
+
+LOCATED = (
+    "face iy ix rx ry cs sn dx dy bx by px py iz rz dz bz izl_near rzl_near dzl_near bzl_near "
+    "izl rzl dzl bzl it rt dt bt status"
+).split()
+
+
+class Located(C.Structure):
+    _fields_ = [(n, vp) for n in LOCATED]
+
+
+class SdkError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def build(verbose=False):
+    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(_HERE, "csrc", s) for s in SOURCES if os.path.exists(os.path.join(_HERE, "csrc", s))]
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + srcs
+    subprocess.check_call(cmd, cwd=_ROOT)
+    return SO_PATH
+
+
+def is_stale():
+    if not os.path.exists(SO_PATH):
+        return True
+    t = os.path.getmtime(SO_PATH)
+    deps = [os.path.join(_HERE, "csrc", f) for f in os.listdir(os.path.join(_HERE, "csrc"))]
+    deps.append(os.path.join(_ROOT, "include", "seaduck_b200.h"))
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def lib():
+    """Load the library; raise (never fall back) if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise SdkError(
+                f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "seaduck_b200 has no CPU fallback."
+            )
+        L = C.CDLL(SO_PATH)
+        L.sdk_last_error.restype = C.c_char_p
+        L.sdk_particles_bytes.restype = C.c_int64
+        L.sdk_particles_bytes.argtypes = [C.c_int64]
+        L.sdk_grid_create.argtypes = [C.POINTER(GridDesc), C.POINTER(vp)]
+        L.sdk_grid_destroy.argtypes = [vp]
+        L.sdk_advect.argtypes = [vp, C.POINTER(Velocity), C.POINTER(Particles), C.c_double, C.POINTER(AdvectParams), C.POINTER(Log), C.c_int, vp]
+        L.sdk_advect_host.argtypes = [vp, C.POINTER(Velocity), C.POINTER(Particles), C.c_double, C.POINTER(AdvectParams), vp, vp]
+        L.sdk_get_u_du.argtypes = [vp, C.POINTER(Velocity), C.POINTER(Particles), C.c_int, vp]
+        L.sdk_grid_build_locator.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, vp]
+        L.sdk_locate.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, C.POINTER(Located), vp]
+        L.sdk_time_index.argtypes = [vp, vp, C.c_int32, vp, C.c_int64, vp]
+        _lib = L
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().sdk_last_error()
+        raise SdkError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """Device (or pinned host) pointer of a torch tensor, ``None`` -> NULL."""
+    if t is None:
+        return None
+    return t.data_ptr()
+
+
+def current_stream():
+    import torch  # noqa: PLC0415
+
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,464 @@
+// K1: advect particles to a stop time, one analytic in-cell step after the other.
+//
+// Replaces, for one call of Particle.to_next_stop (reference seaduck/lagrangian.py:741), the whole
+// per-iteration numpy pipeline: trim :400 -> analytical_step :561 (time-to-wall, which wall first,
+// move) -> lon/lat/dep sync :539 -> cross_cell_wall :706 (re-index across walls and LLC faces,
+// re-read corners, invert the bilinear map) -> get_vol :202 -> get_u_du :218 (six wall-velocity
+// gathers) -- fused in ONE kernel.
+//
+// Scheduling: persistent grid (a multiple of the SM count).  Each lane owns one particle in
+// registers and steps it until its stop time.  Particles need very different numbers of steps, so
+// warps are kept full by refilling idle lanes from a global work queue (warp-aggregated atomicAdd:
+// one atomic per refill, ranks by ballot/popc) as soon as `refill_threshold` lanes are idle.
+#include <cuda_runtime.h>
+
+#include "advect_args.cuh"
+
+namespace sdk {
+
+struct Lane {
+    double lon, lat, dep, t;
+    double rx, ry, rzl;
+    double u, v, w, du, dv, dw;
+    double px[4], py[4];
+    double bzl, dzl, vol;
+    float dx, dy;
+    int f, iy, ix, izl, it;
+    int status, niter, ncross, nrec;
+    int64_t pid;
+};
+
+__device__ __forceinline__ void load_lane(const sdk_particles &p, int64_t i, int has_dep, Lane &s) {
+    s.pid = i;
+    s.lon = p.lon[i];
+    s.lat = p.lat[i];
+    s.t = p.t[i];
+    s.rx = p.rx[i];
+    s.ry = p.ry[i];
+    s.u = p.u[i];
+    s.v = p.v[i];
+    s.du = p.du[i];
+    s.dv = p.dv[i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s.px[j] = p.px[j * p.n + i];
+        s.py[j] = p.py[j * p.n + i];
+    }
+    s.f = p.face ? p.face[i] : 0;
+    s.iy = p.iy[i];
+    s.ix = p.ix[i];
+    s.it = p.it ? p.it[i] : 0;
+    s.dx = p.dx ? p.dx[i] : 1.0f;
+    s.dy = p.dy ? p.dy[i] : 1.0f;
+    s.vol = p.vol ? p.vol[i] : 1.0;
+    if (has_dep) {
+        s.dep = p.dep[i];
+        s.rzl = p.rzl[i];
+        s.w = p.w[i];
+        s.dw = p.dw[i];
+        s.bzl = p.bzl[i];
+        s.dzl = p.dzl[i];
+        s.izl = p.izl[i];
+    } else {
+        s.dep = p.dep ? p.dep[i] : 0.0;
+        s.rzl = 0.0;
+        s.w = 0.0;
+        s.dw = 0.0;
+        s.bzl = 0.0;
+        s.dzl = 1.0;
+        s.izl = 0;
+    }
+    s.status = 0;
+    s.niter = 0;
+    s.ncross = 0;
+    s.nrec = 0;
+}
+
+__device__ __forceinline__ void store_lane(const sdk_particles &p, int has_dep, const Lane &s) {
+    const int64_t i = s.pid;
+    p.lon[i] = s.lon;
+    p.lat[i] = s.lat;
+    p.t[i] = s.t;
+    p.rx[i] = s.rx;
+    p.ry[i] = s.ry;
+    p.u[i] = s.u;
+    p.v[i] = s.v;
+    p.du[i] = s.du;
+    p.dv[i] = s.dv;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        p.px[j * p.n + i] = s.px[j];
+        p.py[j * p.n + i] = s.py[j];
+    }
+    if (p.face) p.face[i] = s.f;
+    p.iy[i] = s.iy;
+    p.ix[i] = s.ix;
+    if (p.vol) p.vol[i] = s.vol;
+    if (has_dep) {
+        p.dep[i] = s.dep;
+        p.rzl[i] = s.rzl;
+        p.w[i] = s.w;
+        p.dw[i] = s.dw;
+        p.bzl[i] = s.bzl;
+        p.dzl[i] = s.dzl;
+        p.izl[i] = s.izl;
+    }
+}
+
+__device__ __forceinline__ void note(const AdvectArgs &a, Lane &s, int stamp) {
+    const sdk_log &L = a.log;
+    if (L.offset) {
+        const int64_t r = L.offset[s.pid] + s.nrec;
+        if (r < L.capacity) {
+            L.fc[r] = s.f;
+            L.it[r] = s.it;
+            L.izl[r] = s.izl;
+            L.rzl[r] = s.rzl;
+            L.iy[r] = s.iy;
+            L.ix[r] = s.ix;
+            L.rx[r] = s.rx;
+            L.ry[r] = s.ry;
+            L.tt[r] = s.t;
+            L.uu[r] = s.u;
+            L.vv[r] = s.v;
+            L.ww[r] = s.w;
+            L.du[r] = s.du;
+            L.dv[r] = s.dv;
+            L.dw[r] = s.dw;
+            L.xx[r] = s.lon;
+            L.yy[r] = s.lat;
+            L.zz[r] = s.dep;
+            L.vs[r] = stamp;
+        }
+    }
+    s.nrec += 1;
+}
+
+// reference Particle.trim, lagrangian.py:400 (one axis)
+__device__ __forceinline__ void trim_axis(double &x, double &u, double du, double lo, double hi) {
+    if (x >= hi) {
+        const double d = hi - x;
+        x += d;
+        u += du * d;
+    }
+    if (x <= lo) {
+        const double d = lo - x;
+        x += d;
+        u += du * d;
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ int64_t uv_index(const GridDev &g, const VelDev &v, bool is_v, int it,
+                                            int iz, int f, int iy, int ix) {
+    const int ny = is_v ? v.nyV : v.nyU, nx = is_v ? v.nxV : v.nxU;
+    int64_t idx = 0;
+    if (v.has_time) idx = wrap_index(it - v.it0, v.nt);
+    if (v.has_z) idx = idx * v.nzU + wrap_index(iz, v.nzU);
+    idx = idx * g.nface + f;
+    return (idx * ny + wrap_index(iy, ny)) * nx + wrap_index(ix, nx);
+}
+
+// Gather the wall values and form u, du, v, dv, w, dw (reference get_u_du lagrangian.py:218 with the
+// kernels of lagrangian.py:25-53; on LLC grids the right / top wall may live on the neighbouring
+// face and be the other velocity component, reference eulerian.py:887 + topology.py:618-647).
+template <typename T>
+__device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v, int has_dep, Lane &s) {
+    const int iz = s.izl - 1;
+    // ---- where do the right and top wall values live?
+    int rf = s.f, ry_ = s.iy, rx_ = s.ix, r_in;
+    int tf = s.f, ty_ = s.iy, tx_ = s.ix, t_in;
+    bool r_is_v = false, t_is_u = false;
+    if (g.has_face) {
+        int st = cell_move(g, 3, rf, ry_, rx_, r_in);
+        if (st) {
+            s.status |= SDK_ST_BAD_CELL;
+            rf = s.f, ry_ = s.iy, rx_ = s.ix;
+        } else if (r_in >= 0) {
+            if (r_in == 1) r_is_v = true;
+            else if (r_in != 2) s.status |= SDK_ST_BAD_CELL;
+        }
+        st = cell_move(g, 0, tf, ty_, tx_, t_in);
+        if (st) {
+            s.status |= SDK_ST_BAD_CELL;
+            tf = s.f, ty_ = s.iy, tx_ = s.ix;
+        } else if (t_in >= 0) {
+            if (t_in == 2) t_is_u = true;
+            else if (t_in != 1) s.status |= SDK_ST_BAD_CELL;
+        }
+    } else {
+        // scalar kernels on a single face: naive neighbour, topology walk only off the array
+        const int xlim = v.u_stag ? g.gnx : g.nx, ylim = v.v_stag ? g.gny : g.ny;
+        rx_ = s.ix + 1;
+        if (rx_ > xlim - 1) {
+            if (g.typ == SDK_TYP_XPERIODIC) rx_ = rx_ - (g.nx - 1);
+            else { ry_ = -1; rx_ = -1; }
+        }
+        ty_ = s.iy + 1;
+        if (ty_ > ylim - 1) { ty_ = -1; tx_ = -1; }
+    }
+    const int64_t iul = uv_index<T>(g, v, false, s.it, iz, s.f, s.iy, s.ix);
+    const int64_t ivl = uv_index<T>(g, v, true, s.it, iz, s.f, s.iy, s.ix);
+    const int64_t iur = uv_index<T>(g, v, r_is_v, s.it, iz, rf, ry_, rx_);
+    const int64_t ivr = uv_index<T>(g, v, !t_is_u, s.it, iz, tf, ty_, tx_);
+    // issue every load before using any of them
+    const double ul = ldf<T>(v.U, iul);
+    const double vl = ldf<T>(v.V, ivl);
+    const double ur = ldf<T>(r_is_v ? v.V : v.U, iur);
+    const double vr = ldf<T>(t_is_u ? v.U : v.V, ivr);
+    double w0 = 0.0, w1 = 0.0;
+    if (v.has_w) {
+        int64_t base = v.has_time ? wrap_index(s.it - v.it0, v.nt) : 0;
+        const int64_t cell = ((int64_t)s.f * g.ny + wrap_index(s.iy, g.ny)) * g.nx + wrap_index(s.ix, g.nx);
+        const int64_t lev = (int64_t)g.nface * g.ny * g.nx;
+        w0 = ldf<T>(v.W, (base * v.nzW + wrap_index(s.izl, v.nzW)) * lev + cell);
+        w1 = ldf<T>(v.W, (base * v.nzW + wrap_index(s.izl - 1, v.nzW)) * lev + cell);
+    }
+    if (v.transport) {
+        int64_t idx = v.vol_has_z ? wrap_index(s.izl - 1, g.n_z > 0 ? g.n_z : 1) : 0;
+        idx = ((idx * g.nface + s.f) * g.ny + wrap_index(s.iy, g.ny)) * g.nx + wrap_index(s.ix, g.nx);
+        s.vol = v.vol_dtype == SDK_F64 ? ldf<double>(v.Vol, idx) : ldf<float>(v.Vol, idx);
+    }
+    const double ul_ = nan_to_num(ul), ur_ = nan_to_num(ur), vl_ = nan_to_num(vl), vr_ = nan_to_num(vr);
+    const bool stag_x = g.has_face || v.u_stag, stag_y = g.has_face || v.v_stag;
+    const double rxs = stag_x ? s.rx + 0.5 : s.rx;
+    const double rys = stag_y ? s.ry + 0.5 : s.ry;
+    // Lagrange weights of the two-node kernels (reference kernel_weight.py:211-229)
+    const double wx0 = (rxs - 1.0) / (0.0 - 1.0), wx1 = rxs;
+    const double wy0 = (rys - 1.0) / (0.0 - 1.0), wy1 = rys;
+    double u = ul_ * wx0 + ur_ * wx1;
+    double du = ul_ * -1.0 + ur_;
+    double vv = vl_ * wy0 + vr_ * wy1;
+    double dv = vl_ * -1.0 + vr_;
+    const double sx = v.transport ? s.vol : (double)s.dx;
+    const double sy = v.transport ? s.vol : (double)s.dy;
+    s.u = nan_to_num(u / sx);
+    s.v = nan_to_num(vv / sy);
+    s.du = nan_to_num(du / sx);
+    s.dv = nan_to_num(dv / sy);
+    if (v.has_w) {
+        const double w0_ = nan_to_num(w0), w1_ = nan_to_num(w1);
+        const double w = w0_ * (1 - s.rzl) + w1_ * s.rzl;
+        const double dw = w0_ * -1.0 + w1_;
+        const double sz = v.transport ? s.vol : s.dzl;
+        s.w = nan_to_num(w / sz);
+        s.dw = nan_to_num(dw / sz);
+    }
+}
+
+// One iteration of the reference loop (lagrangian.py:766-791) for one particle.
+template <typename T, bool LOG>
+__device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, const float *sdZl, Lane &s,
+                                     bool &live) {
+    const GridDev &g = a.g;
+    const int has_dep = a.has_dep;
+    // trim, lagrangian.py:400
+    const double lo = -0.5 + a.trim_tol, hi = 0.5 - a.trim_tol;
+    trim_axis(s.rx, s.u, s.du, lo, hi);
+    trim_axis(s.ry, s.v, s.dv, lo, hi);
+    if (has_dep) trim_axis(s.rzl, s.w, s.dw, -0.0 + a.trim_tol, 1.0 - a.trim_tol);
+    // analytical_step, lagrangian.py:561
+    const double tf = a.t_stop - s.t;
+    const double sg = sgn(tf);
+    const double z0 = has_dep ? s.rzl - 0.5 : 0.0;
+    double ts[7];
+    wall_times(s.u, s.du, s.rx, sg, ts[0], ts[1]);
+    wall_times(s.v, s.dv, s.ry, sg, ts[2], ts[3]);
+    if (has_dep) {
+        wall_times(s.w, s.dw, z0, sg, ts[4], ts[5]);
+    } else {
+        ts[4] = -sg;
+        ts[5] = -sg;
+    }
+    ts[6] = tf;
+    // _which_early, utils.py:875: first minimum of the directed times, nan / negative = never
+    int tend = 0;
+    double best = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        double d = ts[k] * sg;
+        if (isnan(d) || d < 0) d = INFINITY;
+        if (d < best) {
+            best = d;
+            tend = k;
+        }
+    }
+    double te = ts[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k)
+        if (tend == k) te = ts[k];
+    // _move_within_cell, lagrangian.py:528
+    s.t += te;
+    {
+        const double ix_ = increment(te, s.u, s.du);
+        const double iy_ = increment(te, s.v, s.dv);
+        s.u = s.u + s.du * ix_;
+        s.v = s.v + s.dv * iy_;
+        s.rx = ix_ + s.rx;
+        s.ry = iy_ + s.ry;
+        if (has_dep) {
+            const double iz_ = increment(te, s.w, s.dw);
+            s.w = s.w + s.dw * iz_;
+            s.rzl = (iz_ + z0) + 0.5;
+        }
+    }
+    // _sync_latlondep_before_cross, lagrangian.py:539
+    if (has_dep) s.dep = s.bzl + s.dzl * s.rzl;
+    {
+        const double w0 = (0.5 - s.rx) * (0.5 - s.ry), w1 = (0.5 + s.rx) * (0.5 - s.ry);
+        const double w2 = (0.5 + s.rx) * (0.5 + s.ry), w3 = (0.5 - s.rx) * (0.5 + s.ry);
+        s.lon = ((w0 * s.px[0] + w1 * s.px[1]) + w2 * s.px[2]) + w3 * s.px[3];
+        s.lat = ((w0 * s.py[0] + w1 * s.py[1]) + w2 * s.py[2]) + w3 * s.py[3];
+    }
+    if (LOG) note(a, s, tend);
+    s.ncross += tend < 6;
+    // _cross_cell_wall_index, lagrangian.py:598
+    if (tend <= 3) {
+        const int dir = tend == 0 ? 2 : (tend == 1 ? 3 : (tend == 2 ? 1 : 0));
+        int came_in;
+        const int st = cell_move(g, dir, s.f, s.iy, s.ix, came_in);
+        s.status |= st;
+        if (st & SDK_ST_OUT) {
+            live = false;  // nothing sensible to read outside a closed domain
+            return;
+        }
+    } else if (tend == 4) {
+        s.izl += 1;
+    } else if (tend == 5) {
+        if (!a.kick_back || s.izl != 1) s.izl -= 1;
+        else s.dep = s.bzl + s.dzl / 2;
+    }
+    // _cross_cell_wall_read, lagrangian.py:640 (oceanparcel branch): corners, vertical levels
+    int64_t c[4];
+    s.status |= corner_indices(g, s.f, s.iy, s.ix, c);
+    float gx[4], gy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        gx[j] = __ldg(g.XG + c[j]);
+        gy[j] = __ldg(g.YG + c[j]);
+    }
+    if (has_dep) {
+        s.bzl = (double)sZl[wrap_index(s.izl, g.n_zl)];
+        s.dzl = (double)sdZl[wrap_index(s.izl - 1, g.n_z)];
+        // _cross_cell_wall_rel, lagrangian.py:681
+        s.rzl = (s.dep - s.bzl) / s.dzl;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s.px[j] = s.lon + to_180((double)gx[j] - s.lon);  // eulerian.py:618
+        s.py[j] = (double)gy[j];
+    }
+    inverse_bilinear(s.lon, s.lat, s.px, s.py, s.rx, s.ry);
+    // get_vol + get_u_du
+    read_velocity<T>(g, a.v, has_dep, s);
+    s.niter += 1;
+    live = fabs(a.t_stop - s.t) > a.tol;
+    if (LOG && live) note(a, s, 7);
+}
+
+template <typename T, bool LOG>
+__global__ void __launch_bounds__(128)
+advect_kernel(const __grid_constant__ AdvectArgs a) {
+    extern __shared__ float smem[];
+    float *sZl = smem;
+    float *sdZl = smem + a.g.n_zl;
+    for (int k = threadIdx.x; k < a.g.n_zl; k += blockDim.x) sZl[k] = a.g.Zl[k];
+    for (int k = threadIdx.x; k < a.g.n_z; k += blockDim.x) sdZl[k] = a.g.dZl[k];
+    __syncthreads();
+
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t n = a.p.n;
+    Lane s;
+    bool have = false, live = false;
+    bool queue_empty = false;
+    for (;;) {
+        // ---- refill idle lanes from the global queue (warp-aggregated)
+        const unsigned idle = __ballot_sync(full, !have);
+        if (!queue_empty && (__popc(idle) >= a.refill_threshold || idle == full)) {
+            const int cnt = __popc(idle);
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.queue, (unsigned long long)cnt);
+            base = __shfl_sync(full, base, 0);
+            if ((int64_t)base + cnt >= n) queue_empty = true;
+            if (!have) {
+                const int64_t pid = (int64_t)base + __popc(idle & ((1u << lane) - 1));
+                if (pid < n) {
+                    load_lane(a.p, pid, a.has_dep, s);
+                    have = true;
+                    if (LOG && a.log.emit_start) note(a, s, 15);
+                    live = fabs(a.t_stop - s.t) > a.tol;
+                    if (a.p.active && !a.p.active[pid]) live = false;
+                }
+            }
+        }
+        if (!__any_sync(full, have)) break;
+        if (have) {
+            if (live && s.niter < a.max_iteration) {
+                step<T, LOG>(a, sZl, sdZl, s, live);
+            } else {
+                // done (or out of iterations): write back and free the lane
+                if (live) s.status |= SDK_ST_MAX_ITER;
+                if (a.commit) store_lane(a.p, a.has_dep, s);
+                if (a.p.status) a.p.status[s.pid] = s.status;
+                if (a.p.niter) a.p.niter[s.pid] = s.niter;
+                if (a.p.ncross) a.p.ncross[s.pid] = s.ncross;
+                if (LOG && a.log.count) a.log.count[s.pid] = s.nrec;
+                have = false;
+            }
+        }
+    }
+}
+
+// get_u_du on its own (after Particle.update_uvw_array swapped the velocity slab)
+template <typename T>
+__global__ void __launch_bounds__(128) get_u_du_kernel(const __grid_constant__ AdvectArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.p.n) return;
+    Lane s;
+    load_lane(a.p, i, a.has_dep, s);
+    if (a.has_dep) {
+        // keep dzl as stored; only the velocities change
+    }
+    read_velocity<T>(a.g, a.v, a.has_dep, s);
+    a.p.u[i] = s.u;
+    a.p.v[i] = s.v;
+    a.p.du[i] = s.du;
+    a.p.dv[i] = s.dv;
+    if (a.has_dep && a.v.has_w) {
+        a.p.w[i] = s.w;
+        a.p.dw[i] = s.dw;
+    }
+    if (a.p.vol && a.v.transport) a.p.vol[i] = s.vol;
+}
+
+}  // namespace sdk
+
+// ------------------------------------------------------------------------------------------------
+// host side launchers (called from capi.cu)
+// ------------------------------------------------------------------------------------------------
+namespace sdk {
+
+cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaStream_t stream) {
+    const size_t smem = sizeof(float) * (size_t)(args.g.n_zl + args.g.n_z);
+    const bool f32 = args.v.dtype == SDK_F32;
+    if (args.has_log) {
+        if (f32) advect_kernel<float, true><<<blocks, threads, smem, stream>>>(args);
+        else advect_kernel<double, true><<<blocks, threads, smem, stream>>>(args);
+    } else {
+        if (f32) advect_kernel<float, false><<<blocks, threads, smem, stream>>>(args);
+        else advect_kernel<double, false><<<blocks, threads, smem, stream>>>(args);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_get_u_du(const AdvectArgs &args, cudaStream_t stream) {
+    const int threads = 128;
+    const int blocks = (int)((args.p.n + threads - 1) / threads);
+    if (blocks == 0) return cudaSuccess;
+    if (args.v.dtype == SDK_F32) get_u_du_kernel<float><<<blocks, threads, 0, stream>>>(args);
+    else get_u_du_kernel<double><<<blocks, threads, 0, stream>>>(args);
+    return cudaGetLastError();
+}
+
+}  // namespace sdk

@@ -1,0 +1,23 @@
+// Arguments of the advection kernels and their host launchers (shared by advect.cu and capi.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "sdk_device.cuh"
+
+namespace sdk {
+
+struct AdvectArgs {
+    GridDev g;
+    VelDev v;
+    sdk_particles p;
+    sdk_log log;
+    double t_stop, tol, trim_tol;
+    int max_iteration, kick_back, has_dep, has_log, commit, refill_threshold;
+    unsigned long long *queue;  // work queue head
+};
+
+cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaStream_t stream);
+cudaError_t launch_get_u_du(const AdvectArgs &args, cudaStream_t stream);
+
+}  // namespace sdk

@@ -1,0 +1,324 @@
+// C ABI of libseaduck_b200.so (see include/seaduck_b200.h).  Host-side glue only: argument checks,
+// handle bookkeeping, launch configuration.  All arithmetic lives in the kernels.
+#include <cuda_runtime.h>
+
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "advect_args.cuh"
+#include "locate_args.cuh"
+
+namespace {
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char *what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return SDK_ECUDA;
+}
+}  // namespace
+
+struct sdk_grid {
+    sdk::GridDev dev;
+    int sm_count;
+    unsigned long long *queue;  // device work-queue head shared by the launches on this handle
+    sdk::BucketGrid buckets;
+    bool has_buckets;
+};
+
+extern "C" {
+
+int sdk_abi_version(void) { return SDK_ABI_VERSION; }
+
+const char *sdk_last_error(void) { return g_err.c_str(); }
+
+int sdk_sm_count(void) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return SDK_ECUDA;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return SDK_ECUDA;
+    return n;
+}
+
+int sdk_grid_create(const sdk_grid_desc *d, sdk_grid **out) {
+    if (!d || !out) return fail(SDK_EINVAL, "sdk_grid_create: null argument");
+    if (d->nface < 1 || d->nface > SDK_MAX_FACES) return fail(SDK_EINVAL, "sdk_grid_create: nface out of range");
+    if (d->typ == SDK_TYP_LLC && (!d->nbr_face || !d->nbr_edge))
+        return fail(SDK_EINVAL, "sdk_grid_create: LLC grids need the face tables");
+    if (!d->XC || !d->YC) return fail(SDK_EINVAL, "sdk_grid_create: XC / YC missing");
+    if (d->hmode == SDK_H_OCEANPARCEL && (!d->XG || !d->YG))
+        return fail(SDK_EINVAL, "sdk_grid_create: oceanparcel scheme needs XG / YG");
+    if (d->hmode == SDK_H_OCEANPARCEL && (d->gny <= d->ny || d->gnx <= d->nx) && !d->corner_tab)
+        return fail(SDK_EINVAL, "sdk_grid_create: corner table required when XG has the shape of XC");
+    if (d->n_zl > 0 && (!d->Zl || !d->dZl)) return fail(SDK_EINVAL, "sdk_grid_create: Zl / dZl missing");
+    if ((size_t)(d->n_zl + d->n_z) * sizeof(float) > 40 * 1024)
+        return fail(SDK_EUNSUPPORTED, "sdk_grid_create: too many vertical levels for shared memory staging");
+    sdk_grid *g = new (std::nothrow) sdk_grid();
+    if (!g) return fail(SDK_ENOMEM, "sdk_grid_create: out of host memory");
+    sdk::GridDev &v = g->dev;
+    std::memset(&v, 0, sizeof v);
+    v.typ = d->typ;
+    v.has_face = d->has_face;
+    v.nface = d->nface;
+    v.ny = d->ny;
+    v.nx = d->nx;
+    v.gny = d->gny;
+    v.gnx = d->gnx;
+    v.hmode = d->hmode;
+    v.n_zl = d->n_zl;
+    v.n_z = d->n_z;
+    v.n_zc = d->n_zc;
+    for (int i = 0; i < SDK_MAX_FACES * 4; ++i) {
+        v.nbr_face[i] = -1;
+        v.nbr_edge[i] = -1;
+    }
+    if (d->nbr_face && d->nbr_edge) {
+        for (int i = 0; i < d->nface * 4; ++i) {
+            v.nbr_face[i] = (signed char)d->nbr_face[i];
+            v.nbr_edge[i] = (signed char)d->nbr_edge[i];
+        }
+    }
+    v.XC = d->XC; v.YC = d->YC; v.XG = d->XG; v.YG = d->YG;
+    v.dX = d->dX; v.dY = d->dY; v.CS = d->CS; v.SN = d->SN;
+    v.Zl = d->Zl; v.dZl = d->dZl; v.Z = d->Z; v.dZ = d->dZ;
+    v.corner_tab = d->corner_tab;
+    g->sm_count = sdk_sm_count();
+    if (g->sm_count <= 0) {
+        delete g;
+        return fail(SDK_ECUDA, "sdk_grid_create: no CUDA device");
+    }
+    cudaError_t e = cudaMalloc(&g->queue, sizeof(unsigned long long));
+    if (e != cudaSuccess) {
+        delete g;
+        return cuda_fail(e, "sdk_grid_create: cudaMalloc");
+    }
+    g->has_buckets = false;
+    *out = g;
+    return SDK_OK;
+}
+
+int sdk_grid_destroy(sdk_grid *g) {
+    if (!g) return SDK_OK;
+    cudaFree(g->queue);
+    if (g->has_buckets) cudaFree(g->buckets.table);
+    delete g;
+    return SDK_OK;
+}
+
+static int fill_args(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, double t_stop,
+                     const sdk_advect_params *par, const sdk_log *log, int commit, sdk::AdvectArgs &a) {
+    if (!grid || !vel || !p) return fail(SDK_EINVAL, "null argument");
+    if (grid->dev.hmode != SDK_H_OCEANPARCEL)
+        return fail(SDK_EUNSUPPORTED, "only the oceanparcel horizontal scheme is implemented on the device");
+    if (!vel->U || !vel->V) return fail(SDK_EINVAL, "velocity arrays missing");
+    if (vel->transport && !vel->Vol) return fail(SDK_EINVAL, "transport mode needs Vol");
+    if (vel->dtype != SDK_F64 && vel->dtype != SDK_F32) return fail(SDK_EINVAL, "bad velocity dtype");
+    if (p->n < 0) return fail(SDK_EINVAL, "negative particle count");
+    const int has_dep = par ? par->has_dep : 0;
+    if (p->n > 0) {
+        if (!p->lon || !p->lat || !p->t || !p->iy || !p->ix || !p->rx || !p->ry || !p->u || !p->v || !p->du ||
+            !p->dv || !p->px || !p->py)
+            return fail(SDK_EINVAL, "particle state arrays missing");
+        if (grid->dev.has_face && !p->face) return fail(SDK_EINVAL, "face array missing");
+        if (has_dep && (!p->dep || !p->rzl || !p->w || !p->dw || !p->bzl || !p->dzl || !p->izl))
+            return fail(SDK_EINVAL, "vertical state arrays missing");
+        if (has_dep && grid->dev.n_zl == 0) return fail(SDK_EINVAL, "particles have depth but the grid has no Zl");
+        if (!vel->transport && (!p->dx || !p->dy)) return fail(SDK_EINVAL, "dx / dy missing (velocity mode)");
+        if (vel->has_time && !p->it) return fail(SDK_EINVAL, "time index array missing");
+    }
+    a.g = grid->dev;
+    sdk::VelDev &v = a.v;
+    v.U = vel->U; v.V = vel->V; v.W = vel->W; v.Vol = vel->Vol;
+    v.dtype = vel->dtype; v.vol_dtype = vel->vol_dtype;
+    v.has_time = vel->has_time; v.it0 = vel->it0; v.nt = vel->nt > 0 ? vel->nt : 1;
+    v.has_z = vel->has_z; v.nzU = vel->nzU > 0 ? vel->nzU : 1; v.nzW = vel->nzW > 0 ? vel->nzW : 1;
+    v.nyU = vel->nyU; v.nxU = vel->nxU; v.nyV = vel->nyV; v.nxV = vel->nxV;
+    v.u_stag = vel->u_stag; v.v_stag = vel->v_stag; v.vol_has_z = vel->vol_has_z;
+    v.transport = vel->transport;
+    v.has_w = (vel->W != nullptr) && has_dep;
+    a.p = *p;
+    if (log) a.log = *log; else std::memset(&a.log, 0, sizeof a.log);
+    a.t_stop = t_stop;
+    a.tol = par ? par->tol : 1e-4;
+    a.trim_tol = par ? par->trim_tol : 1e-14;
+    a.max_iteration = par ? par->max_iteration : 200;
+    a.kick_back = par ? par->kick_back : 0;
+    a.has_dep = has_dep;
+    a.has_log = log != nullptr;
+    a.commit = commit;
+    int thr = par ? par->refill_threshold : 0;
+    a.refill_threshold = thr > 0 ? (thr > 32 ? 32 : thr) : 8;
+    a.queue = grid->queue;
+    return SDK_OK;
+}
+
+int sdk_advect(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, double t_stop,
+               const sdk_advect_params *par, const sdk_log *log, int commit, void *stream_) {
+    sdk::AdvectArgs a;
+    int rc = fill_args(grid, vel, p, t_stop, par, log, commit, a);
+    if (rc) return rc;
+    if (p->n == 0) return SDK_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cudaError_t e = cudaMemsetAsync(grid->queue, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_advect: memset");
+    const int threads = (par && par->threads_per_block > 0) ? par->threads_per_block : 128;
+    const int per_sm = (par && par->blocks_per_sm > 0) ? par->blocks_per_sm : 4;
+    int64_t need = (p->n + threads - 1) / threads;
+    int64_t blocks = (int64_t)grid->sm_count * per_sm;
+    if (blocks > need) blocks = need;
+    if (threads > 128 || threads % 32) return fail(SDK_EINVAL, "threads_per_block must be a multiple of 32, <= 128");
+    e = sdk::launch_advect(a, (int)blocks, threads, stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_advect: launch");
+    return SDK_OK;
+}
+
+int sdk_get_u_du(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, int has_dep,
+                 void *stream_) {
+    sdk_advect_params par;
+    std::memset(&par, 0, sizeof par);
+    par.has_dep = has_dep;
+    par.tol = 1e-4;
+    par.trim_tol = 1e-14;
+    par.max_iteration = 200;
+    sdk::AdvectArgs a;
+    int rc = fill_args(grid, vel, p, 0.0, &par, nullptr, 1, a);
+    if (rc) return rc;
+    cudaError_t e = sdk::launch_get_u_du(a, (cudaStream_t)stream_);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_get_u_du: launch");
+    return SDK_OK;
+}
+
+int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span_lon, double span_lat,
+                           int32_t nlon, int32_t nlat, void *stream) {
+    if (!grid) return fail(SDK_EINVAL, "sdk_grid_build_locator: null grid");
+    if (nlon < 1 || nlat < 1 || !(span_lon > 0) || !(span_lat > 0))
+        return fail(SDK_EINVAL, "sdk_grid_build_locator: bad bucket geometry");
+    if (grid->has_buckets) {
+        cudaFree(grid->buckets.table);
+        grid->has_buckets = false;
+    }
+    sdk::BucketGrid &b = grid->buckets;
+    b.lon0 = lon0;
+    b.lat0 = lat0;
+    b.periodic = span_lon >= 360.0;
+    b.span_lon = b.periodic ? 360.0 : span_lon;
+    b.span_lat = span_lat;
+    b.nlon = nlon;
+    b.nlat = nlat;
+    b.inv_dlon = nlon / b.span_lon;
+    b.inv_dlat = nlat / b.span_lat;
+    b.table = nullptr;
+    cudaError_t e = sdk::build_buckets(grid->dev, b, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_grid_build_locator");
+    grid->has_buckets = true;
+    return SDK_OK;
+}
+
+int sdk_locate(const sdk_grid *grid, int64_t n, const double *lon, const double *lat, const double *dep,
+               const double *t, const double *ts, int32_t n_t, const sdk_located *out, void *stream) {
+    if (!grid || !out) return fail(SDK_EINVAL, "sdk_locate: null argument");
+    if (n < 0) return fail(SDK_EINVAL, "sdk_locate: negative count");
+    if ((lon == nullptr) != (lat == nullptr)) return fail(SDK_EINVAL, "sdk_locate: lon and lat go together");
+    if (lon) {
+        if (grid->dev.hmode != SDK_H_OCEANPARCEL)
+            return fail(SDK_EUNSUPPORTED, "sdk_locate: only the oceanparcel horizontal scheme is implemented");
+        if (!grid->has_buckets) return fail(SDK_EINVAL, "sdk_locate: call sdk_grid_build_locator first");
+        if (!out->iy || !out->ix || !out->rx || !out->ry) return fail(SDK_EINVAL, "sdk_locate: output arrays missing");
+    }
+    if (dep && grid->dev.n_zl > 1 && (!out->izl || !out->rzl || !out->dzl || !out->bzl))
+        return fail(SDK_EINVAL, "sdk_locate: vertical output arrays missing");
+    if (t && ts && n_t > 1 && !out->it) return fail(SDK_EINVAL, "sdk_locate: time index output missing");
+    sdk::LocateArgs a;
+    a.g = grid->dev;
+    a.b = grid->buckets;
+    a.n = n;
+    a.lon = lon; a.lat = lat; a.dep = dep; a.t = t; a.ts = ts;
+    a.n_t = n_t;
+    a.max_walk = 4 * (grid->dev.ny + grid->dev.nx);
+    a.out = *out;
+    cudaError_t e = sdk::launch_locate(a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_locate: launch");
+    return SDK_OK;
+}
+
+int sdk_time_index(const double *t, const double *time_midp, int32_t n_midp, int32_t *it, int64_t n,
+                   void *stream) {
+    if (!t || !time_midp || !it || n_midp < 1) return fail(SDK_EINVAL, "sdk_time_index: bad argument");
+    cudaError_t e = sdk::launch_time_index(t, time_midp, n_midp, it, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_time_index: launch");
+    return SDK_OK;
+}
+
+// ---- host-buffer variant ---------------------------------------------------------------------
+namespace {
+struct Field {
+    size_t offset;  // of sdk_particles member
+    size_t elem;    // bytes per element
+    int mult;       // elements per particle
+};
+#define F(member, type, mult) {offsetof(sdk_particles, member), sizeof(type), mult}
+const Field kFields[] = {
+    F(lon, double, 1), F(lat, double, 1), F(dep, double, 1), F(t, double, 1),
+    F(face, int32_t, 1), F(iy, int32_t, 1), F(ix, int32_t, 1), F(izl, int32_t, 1), F(it, int32_t, 1),
+    F(rx, double, 1), F(ry, double, 1), F(rzl, double, 1),
+    F(u, double, 1), F(v, double, 1), F(w, double, 1), F(du, double, 1), F(dv, double, 1), F(dw, double, 1),
+    F(px, double, 4), F(py, double, 4), F(dx, float, 1), F(dy, float, 1),
+    F(bzl, double, 1), F(dzl, double, 1), F(vol, double, 1), F(active, int32_t, 1),
+    F(status, int32_t, 1), F(niter, int32_t, 1), F(ncross, int32_t, 1),
+};
+#undef F
+size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+}  // namespace
+
+int64_t sdk_particles_bytes(int64_t n) {
+    size_t total = 0;
+    for (const Field &f : kFields) total += align256((size_t)n * f.elem * f.mult);
+    return (int64_t)total;
+}
+
+int sdk_advect_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *hp, double t_stop,
+                    const sdk_advect_params *par, void *scratch, void *stream_) {
+    if (!hp || !scratch) return fail(SDK_EINVAL, "sdk_advect_host: null argument");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    sdk_particles dp;
+    std::memset(&dp, 0, sizeof dp);
+    dp.n = hp->n;
+    char *cur = (char *)scratch;
+    const int n_in = (int)(sizeof(kFields) / sizeof(kFields[0])) - 3;  // last three are outputs
+    for (int k = 0; k < (int)(sizeof(kFields) / sizeof(kFields[0])); ++k) {
+        const Field &f = kFields[k];
+        void *const *hsrc = (void *const *)((const char *)hp + f.offset);
+        void **ddst = (void **)((char *)&dp + f.offset);
+        const size_t bytes = (size_t)hp->n * f.elem * f.mult;
+        if (*hsrc) {
+            *ddst = cur;
+            if (k < n_in && bytes) {
+                cudaError_t e = cudaMemcpyAsync(cur, *hsrc, bytes, cudaMemcpyHostToDevice, stream);
+                if (e != cudaSuccess) return cuda_fail(e, "sdk_advect_host: H2D");
+            }
+            cur += align256(bytes);
+        }
+    }
+    int rc = sdk_advect(grid, vel, &dp, t_stop, par, nullptr, 1, stream);
+    if (rc) return rc;
+    for (const Field &f : kFields) {
+        void *const *hdst = (void *const *)((const char *)hp + f.offset);
+        void *const *dsrc = (void *const *)((const char *)&dp + f.offset);
+        const size_t bytes = (size_t)hp->n * f.elem * f.mult;
+        if (*hdst && bytes && f.offset != offsetof(sdk_particles, active)) {
+            cudaError_t e = cudaMemcpyAsync(*hdst, *dsrc, bytes, cudaMemcpyDeviceToHost, stream);
+            if (e != cudaSuccess) return cuda_fail(e, "sdk_advect_host: D2H");
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_advect_host: sync");
+    return SDK_OK;
+}
+
+}  // extern "C"

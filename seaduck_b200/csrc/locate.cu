@@ -1,0 +1,351 @@
+// K2: lat/lon/depth/time -> grid indices + rel-coords.
+//
+// Replaces Position.from_latlon (reference seaduck/eulerian.py:138) -> OceData._find_rel_h
+// (ocedata.py:422) -> find_rel_h_oceanparcel (utils.py:614): nearest cell centre in 3-D chord
+// distance (reference: scipy cKDTree on cartesian XC/YC, utils.py:225,309), the four corner points
+// (find_px_py utils.py:495) and the inverse bilinear map (find_rx_ry_oceanparcel utils.py:532);
+// and the 1-D searches find_rel_nearest / find_rel_z / find_rel_time (utils.py:321-454).
+//
+// Instead of a KD-tree the device uses a lat/lon bucket grid that stores one nearby cell per bucket
+// and a greedy walk over the 8 neighbours (crossing LLC faces through the constant-memory face
+// tables) that ends on the cell whose centre is closest to the query.
+#include <cuda_runtime.h>
+
+#include "locate_args.cuh"
+
+namespace sdk {
+
+__device__ __forceinline__ void unit_vec(double lon, double lat, double &x, double &y, double &z) {
+    const double d2r = 0.017453292519943295;
+    double sl, cl, sp, cp;
+    sincos(lon * d2r, &sl, &cl);
+    sincos(lat * d2r, &sp, &cp);
+    x = cp * cl;
+    y = cp * sl;
+    z = sp;
+}
+
+__device__ __forceinline__ int bucket_of(const BucketGrid &b, double lon, double lat) {
+    double dl = lon - b.lon0;
+    dl = dl - 360.0 * floor(dl / 360.0);  // [0, 360)
+    int bx = (int)(dl * b.inv_dlon);
+    int by = (int)((lat - b.lat0) * b.inv_dlat);
+    if (b.periodic) {
+        bx = bx % b.nlon;
+    } else {
+        // non-global grid: points west of lon0 may have wrapped to ~360
+        if (dl > b.span_lon + 0.5 * (360.0 - b.span_lon)) bx = 0;
+        bx = min(max(bx, 0), b.nlon - 1);
+    }
+    by = min(max(by, 0), b.nlat - 1);
+    return by * b.nlon + bx;
+}
+
+__global__ void bucket_scatter_kernel(GridDev g, BucketGrid b) {
+    const int64_t ncell = (int64_t)g.nface * g.ny * g.nx;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        const float lon = g.XC[c], lat = g.YC[c];
+        if (!(lon == lon) || !(lat == lat)) continue;
+        atomicMin(&b.table[bucket_of(b, (double)lon, (double)lat)], (int)c);
+    }
+}
+
+// one dilation pass: empty buckets copy a filled neighbour; *changed counts buckets still empty
+__global__ void bucket_dilate_kernel(BucketGrid b, const int *src, int *dst, int *remaining) {
+    const int nb = b.nlat * b.nlon;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nb; i += gridDim.x * blockDim.x) {
+        int v = src[i];
+        if (v == INT_MAX) {
+            const int by = i / b.nlon, bx = i % b.nlon;
+            for (int dy = -1; dy <= 1 && v == INT_MAX; ++dy) {
+                const int yy = by + dy;
+                if (yy < 0 || yy >= b.nlat) continue;
+                for (int dx = -1; dx <= 1; ++dx) {
+                    int xx = bx + dx;
+                    if (b.periodic) xx = (xx + b.nlon) % b.nlon;
+                    else if (xx < 0 || xx >= b.nlon) continue;
+                    const int w = src[yy * b.nlon + xx];
+                    if (w != INT_MAX) {
+                        v = w;
+                        break;
+                    }
+                }
+            }
+            if (v == INT_MAX) atomicAdd(remaining, 1);
+        }
+        dst[i] = v;
+    }
+}
+
+// rot in quarter turns when leaving through edge e and arriving through edge ne
+// (reference topology.py:470: rot = pi - DIRECTIONS[e] + DIRECTIONS[ne])
+__device__ __forceinline__ int remap_dir(int dir, int e, int ne) {
+    const int dq[4] = {1, 3, 2, 0};
+    const int q = (2 - dq[e] + dq[ne] + 8) & 3;
+    if (q == 1) {
+        const int r[4] = {2, 3, 1, 0};
+        return r[dir];
+    }
+    if (q == 3) {
+        const int r[4] = {3, 2, 0, 1};
+        return r[dir];
+    }
+    return dir;
+}
+
+// neighbour of a cell after up to two moves (second one re-labelled after a face change)
+__device__ __forceinline__ bool neighbour(const GridDev &g, int f, int iy, int ix, int d1, int d2,
+                                          int &nf, int &ny, int &nx) {
+    nf = f;
+    ny = iy;
+    nx = ix;
+    int came;
+    if (cell_move(g, d1, nf, ny, nx, came)) return false;
+    if (d2 >= 0) {
+        if (came >= 0) d2 = remap_dir(d2, d1, came);
+        if (cell_move(g, d2, nf, ny, nx, came)) return false;
+    }
+    return true;
+}
+
+__device__ __forceinline__ double dist2_to_cell(const GridDev &g, int f, int iy, int ix, double qx,
+                                                double qy, double qz) {
+    const int64_t c = ((int64_t)f * g.ny + iy) * g.nx + ix;
+    const float lon = __ldg(g.XC + c), lat = __ldg(g.YC + c);
+    if (!(lon == lon) || !(lat == lat)) return INFINITY;
+    double x, y, z;
+    unit_vec((double)lon, (double)lat, x, y, z);
+    const double dx = x - qx, dy = y - qy, dz = z - qz;
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// reference find_rel (utils.py:321) with find_ind (utils.py:273) for a 1-D table in shared/global
+__device__ __forceinline__ void find_rel_1d(const float *arr, const float *darr, int n, int n_d,
+                                            double x, int ascending, bool above, bool dx_right,
+                                            int &idx, double &r, double &d, double &b) {
+    int best = 0;
+    double bestv = INFINITY;
+    for (int k = 0; k < n; ++k) {
+        const double a = fabs((double)arr[k] - x);
+        if (a < bestv) {
+            bestv = a;
+            best = k;
+        }
+    }
+    if (above && (double)arr[best] > x) best -= ascending;
+    best = min(max(best, 0), n - 1);  // reference raises "Value out of bound."
+    const double bx = (double)arr[best];
+    const double dx = x - bx;
+    int off = (int)(!dx_right) + (int)(ascending > 0) - 1;
+    if (!above) off = (int)(!dx_right) + (int)(ascending * dx > 0) - 1;
+    int j = best + off;
+    double dval;
+    if (darr) {
+        dval = (double)darr[wrap_index(j, n_d)];
+    } else {
+        // darray = |diff(array)| with the last value repeated (utils.py:361-364), float32 arithmetic
+        j = wrap_index(j, n);
+        const int jj = j < n - 1 ? j : n - 2;
+        dval = (double)fabsf(arr[jj + 1] - arr[jj]);
+    }
+    idx = best;
+    r = dx / dval;
+    d = dval;
+    b = bx;
+}
+
+// same for float64 tables (time axes)
+__device__ __forceinline__ void find_rel_1d_f64(const double *arr, int n, double x, bool above, int &idx,
+                                                double &r, double &d, double &b) {
+    int best = 0;
+    double bestv = INFINITY;
+    for (int k = 0; k < n; ++k) {
+        const double a = fabs(arr[k] - x);
+        if (a < bestv) {
+            bestv = a;
+            best = k;
+        }
+    }
+    if (above && arr[best] > x) best -= 1;
+    best = min(max(best, 0), n - 1);
+    const double bx = arr[best];
+    const double dx = x - bx;
+    int off = 0;
+    if (!above) off = (int)(dx > 0) - 1;
+    int j = wrap_index(best + off, n);
+    const int jj = j < n - 1 ? j : n - 2;
+    const double dval = n > 1 ? fabs(arr[jj + 1] - arr[jj]) : 1.0;
+    idx = best;
+    r = dx / dval;
+    d = dval;
+    b = bx;
+}
+
+__global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ LocateArgs a) {
+    const GridDev &g = a.g;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const sdk_located &o = a.out;
+    int status = 0;
+    if (a.lon && a.lat) {
+        const double lon = a.lon[i], lat = a.lat[i];
+        double qx, qy, qz;
+        unit_vec(lon, lat, qx, qy, qz);
+        int c0 = __ldg(a.b.table + bucket_of(a.b, lon, lat));
+        int f = c0 / (g.ny * g.nx);
+        int rem = c0 - f * (g.ny * g.nx);
+        int iy = rem / g.nx, ix = rem - iy * g.nx;
+        double best = dist2_to_cell(g, f, iy, ix, qx, qy, qz);
+        // greedy walk to the nearest centre
+        for (int iter = 0; iter < a.max_walk; ++iter) {
+            int bf = f, by = iy, bx = ix;
+            double bd = best;
+            const int d1s[8] = {0, 1, 2, 3, 0, 0, 1, 1};
+            const int d2s[8] = {-1, -1, -1, -1, 2, 3, 2, 3};
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                int nf, ny, nx;
+                if (!neighbour(g, f, iy, ix, d1s[k], d2s[k], nf, ny, nx)) continue;
+                const double dd = dist2_to_cell(g, nf, ny, nx, qx, qy, qz);
+                if (dd < bd) {
+                    bd = dd;
+                    bf = nf;
+                    by = ny;
+                    bx = nx;
+                }
+            }
+            if (bd >= best) break;
+            best = bd;
+            f = bf;
+            iy = by;
+            ix = bx;
+        }
+        if (o.face) o.face[i] = f;
+        o.iy[i] = iy;
+        o.ix[i] = ix;
+        const int64_t c = ((int64_t)f * g.ny + iy) * g.nx + ix;
+        if (o.bx) o.bx[i] = __ldg(g.XC + c);
+        if (o.by) o.by[i] = __ldg(g.YC + c);
+        if (o.dx) o.dx[i] = g.dX ? __ldg(g.dX + c) : 0.f;
+        if (o.dy) o.dy[i] = g.dY ? __ldg(g.dY + c) : 0.f;
+        if (o.cs) o.cs[i] = g.CS ? __ldg(g.CS + c) : 1.f;
+        if (o.sn) o.sn[i] = g.SN ? __ldg(g.SN + c) : 0.f;
+        // corners + inverse bilinear map
+        int64_t cc[4];
+        status |= corner_indices(g, f, iy, ix, cc);
+        double px[4], py[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            px[j] = lon + to_180((double)__ldg(g.XG + cc[j]) - lon);
+            py[j] = (double)__ldg(g.YG + cc[j]);
+            if (o.px) {
+                o.px[j * a.n + i] = px[j];
+                o.py[j * a.n + i] = py[j];
+            }
+        }
+        double rx, ry;
+        inverse_bilinear(lon, lat, px, py, rx, ry);
+        o.rx[i] = rx;
+        o.ry[i] = ry;
+    }
+    if (a.dep) {
+        const double z = a.dep[i];
+        int k;
+        double r, d, b;
+        if (g.n_zc > 1 && o.iz) {  // _find_rel_v: nearest Z
+            find_rel_1d(g.Z, nullptr, g.n_zc, 0, z, 1, false, true, k, r, d, b);
+            o.iz[i] = k; o.rz[i] = r; o.dz[i] = d; o.bz[i] = b;
+        }
+        if (g.n_zl > 1) {
+            if (o.izl_near) {  // _find_rel_vl: nearest Zl
+                find_rel_1d(g.Zl, nullptr, g.n_zl, 0, z, 1, false, true, k, r, d, b);
+                o.izl_near[i] = k; o.rzl_near[i] = r; o.dzl_near[i] = d; o.bzl_near[i] = b;
+            }
+            // _find_rel_vl_lin: find_rel_z(z, Zl, dZl, dz_above_z=False) -> ascending=-1, dx_right=True
+            find_rel_1d(g.Zl, g.dZl, g.n_zl, g.n_z, z, -1, true, true, k, r, d, b);
+            o.izl[i] = k; o.rzl[i] = r; o.dzl[i] = d; o.bzl[i] = b;
+        }
+    }
+    if (a.t && a.ts && a.n_t > 1) {  // _find_rel_t: nearest time level
+        int k;
+        double r, d, b;
+        find_rel_1d_f64(a.ts, a.n_t, a.t[i], false, k, r, d, b);
+        o.it[i] = k;
+        if (o.rt) { o.rt[i] = r; o.dt[i] = d; o.bt[i] = b; }
+    }
+    if (o.status) o.status[i] = status;
+}
+
+// it = 0 before time_midp[0], else find_rel(t, time_midp)[0] + 1 (reference lagrangian.py:796-802)
+__global__ void time_index_kernel(const double *t, const double *midp, int n_midp, int32_t *it, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double x = t[i];
+    if (x < midp[0]) {
+        it[i] = 0;
+        return;
+    }
+    int k;
+    double r, d, b;
+    find_rel_1d_f64(midp, n_midp, x, true, k, r, d, b);
+    it[i] = k + 1;
+}
+
+__global__ void fill_int_kernel(int *p, int v, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
+}
+
+// Setup (once per grid): scatter cells into buckets, then grow the filled region until no bucket is
+// empty.  Host-synchronous; not part of any timed path.
+cudaError_t build_buckets(const GridDev &g, BucketGrid &b, cudaStream_t s) {
+    const int nb = b.nlat * b.nlon;
+    int *tmp = nullptr, *remaining = nullptr;
+    cudaError_t e;
+    if ((e = cudaMalloc(&b.table, sizeof(int) * (size_t)nb)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&tmp, sizeof(int) * (size_t)nb)) != cudaSuccess) return e;
+    if ((e = cudaMalloc(&remaining, sizeof(int))) != cudaSuccess) return e;
+    const int threads = 256;
+    const int blocks = min((nb + threads - 1) / threads, 4096);
+    fill_int_kernel<<<blocks, threads, 0, s>>>(b.table, INT_MAX, nb);
+    const int64_t ncell = (int64_t)g.nface * g.ny * g.nx;
+    int64_t sblocks = (ncell + threads - 1) / threads;
+    if (sblocks > 65535) sblocks = 65535;
+    bucket_scatter_kernel<<<(int)sblocks, threads, 0, s>>>(g, b);
+    int *src = b.table, *dst = tmp;
+    for (int pass = 0; pass < b.nlat + b.nlon; ++pass) {
+        int left = 0;
+        cudaMemsetAsync(remaining, 0, sizeof(int), s);
+        bucket_dilate_kernel<<<blocks, threads, 0, s>>>(b, src, dst, remaining);
+        if ((e = cudaMemcpyAsync(&left, remaining, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(s)) != cudaSuccess) break;
+        int *t = src;
+        src = dst;
+        dst = t;
+        if (left == 0) break;
+    }
+    if (e == cudaSuccess && src != b.table)
+        e = cudaMemcpyAsync(b.table, src, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(tmp);
+    cudaFree(remaining);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    return e;
+}
+
+cudaError_t launch_locate(const LocateArgs &a, cudaStream_t s) {
+    if (a.n == 0) return cudaSuccess;
+    const int threads = 128;
+    locate_kernel<<<(unsigned)((a.n + threads - 1) / threads), threads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_time_index(const double *t, const double *midp, int n_midp, int32_t *it, int64_t n,
+                              cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const int threads = 128;
+    time_index_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, s>>>(t, midp, n_midp, it, n);
+    return cudaGetLastError();
+}
+
+}  // namespace sdk

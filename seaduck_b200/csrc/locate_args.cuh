@@ -1,0 +1,31 @@
+// Arguments of the locate kernels (shared by locate.cu and capi.cu).
+#pragma once
+
+#include <climits>
+#include <cuda_runtime.h>
+
+#include "sdk_device.cuh"
+
+namespace sdk {
+
+struct BucketGrid {
+    double lon0, lat0, span_lon, span_lat, inv_dlon, inv_dlat;
+    int nlon, nlat, periodic;
+    int *table;  // one nearby cell (flat index) per bucket
+};
+
+struct LocateArgs {
+    GridDev g;
+    BucketGrid b;
+    int64_t n;
+    const double *lon, *lat, *dep, *t, *ts;
+    int n_t, max_walk;
+    sdk_located out;
+};
+
+cudaError_t build_buckets(const GridDev &g, BucketGrid &b, cudaStream_t s);
+cudaError_t launch_locate(const LocateArgs &a, cudaStream_t s);
+cudaError_t launch_time_index(const double *t, const double *midp, int n_midp, int32_t *it, int64_t n,
+                              cudaStream_t s);
+
+}  // namespace sdk

@@ -1,0 +1,223 @@
+"""Eulerian ``Position``: where the points are on the grid, and interpolation at those points.
+
+Public surface of the reference's ``seaduck.eulerian.Position`` (``eulerian.py:110``):
+``from_latlon`` (:138), ``subset`` (:319), ``update_from_subset`` (:353), ``get_px_py`` (:592),
+``get_f_node_weight`` (:621), ``interpolate`` (:1268).  The work is done by CUDA kernels
+(``sdk_locate``, ``sdk_interp``); numpy arrays on the object are host mirrors.
+"""
+
+from __future__ import annotations
+
+import copy
+import logging
+
+import numpy as np
+
+from .ocedata import HRel, OceData, RelCoord, TRel, VlLinRel, VlRel, VRel, _general_len
+
+
+def to_180(x, peri=360):
+    """Convert any longitude scale to [-180,180) (reference ``utils.py:199``)."""
+    x = x % peri % peri
+    return x + (-1) * (x // (peri / 2)) * peri
+
+
+def weight_f_node(rx, ry):
+    """Bilinear weights of the four corners LL, LR, UR, UL (reference ``utils.py:632``)."""
+    return np.vstack(
+        [
+            (0.5 - rx) * (0.5 - ry),
+            (0.5 + rx) * (0.5 - ry),
+            (0.5 + rx) * (0.5 + ry),
+            (0.5 - rx) * (0.5 + ry),
+        ]
+    ).T
+
+
+class Position:
+    """Points on the grid.  Create empty, then ``from_latlon``."""
+
+    def __new__(cls, *arg, **kwarg):
+        new_position = object.__new__(cls)
+        object.__setattr__(new_position, "rel", RelCoord())
+        return new_position
+
+    def __getattr__(self, attr):
+        # only called when normal lookup fails
+        if attr == "rel":
+            raise AttributeError(attr)
+        rel = object.__getattribute__(self, "rel")
+        if attr in rel.keys():
+            return rel[attr]
+        raise AttributeError(f"'{type(self).__name__}' object has no attribute '{attr}'")
+
+    def __setattr__(self, attr, value):
+        if attr == "rel":
+            object.__setattr__(self, attr, value)
+        elif attr in self.rel.keys():
+            self.rel[attr] = value
+        else:
+            object.__setattr__(self, attr, value)
+
+    def from_latlon(self, x=None, y=None, z=None, t=None, data=None):
+        """Fill in the coordinate info from lat-lon-dep-time (reference ``eulerian.py:138``)."""
+        if data is None:
+            try:
+                self.ocedata
+            except AttributeError as exc:
+                raise ValueError("data not provided") from exc
+        else:
+            if isinstance(data, OceData):
+                self.ocedata = data
+            else:
+                raise ValueError("Input data must be OceData")
+        self.tp = self.ocedata.tp
+        length = [_general_len(i) for i in [x, y, z, t]]
+        self.N = max(length)
+        if any(i != self.N for i in length if i > 1):
+            raise ValueError("Shapes of input coordinates are not compatible")
+        if isinstance(x, (int, float, np.floating)):
+            x = np.ones(self.N, float) * x
+        if isinstance(y, (int, float, np.floating)):
+            y = np.ones(self.N, float) * y
+        if isinstance(z, (int, float, np.floating)):
+            z = np.ones(self.N, float) * z
+        if isinstance(t, (int, float, np.floating)):
+            t = np.ones(self.N, float) * t
+        for thing in [x, y, z, t]:
+            if thing is None:
+                continue
+            if len(np.shape(thing)) > 1:
+                raise ValueError("Input need to be 1D numpy arrays")
+        od = self.ocedata
+        # one fused device pass for all four coordinates
+        loc = od.locate(
+            x=x if (x is not None and y is not None) else None,
+            y=y if (x is not None and y is not None) else None,
+            z=z if (z is not None and (od.readiness["Z"] or od.readiness["Zl"])) else None,
+            t=t if (t is not None and od.readiness["time"]) else None,
+        ) if any(v is not None for v in (x, y, z, t)) else {}
+        self._located = loc  # device tensors, reused by Particle
+        npf = OceData._np
+        if (x is not None) and (y is not None):
+            self.lon = np.array(x, float)
+            self.lat = np.array(y, float)
+            face = npf(loc["face"], np.int64) if "face" in loc else None
+            vals = [npf(loc[k], np.int64) for k in ("iy", "ix")] + [
+                npf(loc[k]) for k in ("rx", "ry", "cs", "sn", "dx", "dy", "bx", "by")
+            ]
+            if od.CS is None:
+                vals[4] = vals[5] = None
+            if od.dX is None:
+                vals[6] = vals[7] = None
+            self.rel.update(HRel._make([face] + vals))
+        else:
+            self.rel.update(HRel._make([None for i in range(11)]))
+            self.lon = None
+            self.lat = None
+        if z is not None:
+            self.dep = np.array(z, float)
+            if od.readiness["Z"]:
+                self.rel.update(VRel(npf(loc["iz"], np.int64), npf(loc["rz"]), npf(loc["dz"]), npf(loc["bz"])))
+            else:
+                self.rel.update(VRel._make(None for i in range(4)))
+            if od.readiness["Zl"]:
+                self.rel.update(
+                    VlRel(npf(loc["izl_near"], np.int64), npf(loc["rzl_near"]), npf(loc["dzl_near"]), npf(loc["bzl_near"]))
+                )
+                self.rel.update(VlLinRel(npf(loc["izl"], np.int64), npf(loc["rzl"]), npf(loc["dzl"]), npf(loc["bzl"])))
+            else:
+                self.rel.update(VlRel._make(None for i in range(4)))
+                self.rel.update(VlLinRel._make(None for i in range(4)))
+        else:
+            self.rel.update(VRel._make(None for i in range(4)))
+            self.rel.update(VlRel._make(None for i in range(4)))
+            self.rel.update(VlLinRel._make(None for i in range(4)))
+            self.dep = None
+        if t is not None:
+            self.t = np.array(t, float)
+            if od.readiness["time"]:
+                self.rel.update(TRel(npf(loc["it"], np.int64), npf(loc["rt"]), npf(loc["dt"]), npf(loc["bt"])))
+            else:
+                self.rel.update(TRel._make(None for i in range(4)))
+        else:
+            self.rel.update(TRel._make(None for i in range(4)))
+            self.t = None
+        return self
+
+    def subset(self, which):
+        """Subset of the points (reference ``eulerian.py:319``)."""
+        p = object.__new__(type(self))
+        for key, item in vars(self).items():
+            if key.startswith("_"):
+                continue
+            if isinstance(item, np.ndarray):
+                if len(item.shape) == 1:
+                    object.__setattr__(p, key, item[which])
+                    object.__setattr__(p, "N", len(item[which]))
+                elif key in ["px", "py"]:
+                    object.__setattr__(p, key, item[:, which])
+                else:
+                    object.__setattr__(p, key, item)
+            elif isinstance(item, RelCoord):
+                object.__setattr__(p, key, item.subset(which))
+            else:
+                object.__setattr__(p, key, item)
+        return p
+
+    def update_from_subset(self, sub, which):
+        """Write a subset back (reference ``eulerian.py:353``)."""
+        for key, item in vars(sub).items():
+            if key.startswith("_"):
+                continue
+            if not hasattr(self, key):
+                logging.warning(f"A new attribute {key} defined after updating from subset")
+                setattr(self, key, item)
+            if getattr(self, key) is None:
+                continue
+            if isinstance(item, np.ndarray):
+                if len(item.shape) == 1:
+                    getattr(self, key)[which] = item
+                elif key in ["px", "py"]:
+                    getattr(self, key)[:, which] = item
+            elif isinstance(item, RelCoord):
+                self.rel.update_from_subset(item, which)
+            elif isinstance(item, list):
+                setattr(self, key, item)
+
+    def get_px_py(self):
+        """Longitude / latitude of the 4 corners around each point (reference ``eulerian.py:592``)."""
+        od = self.ocedata
+        if self.face is not None:
+            ind = (self.face, self.iy, self.ix)
+        else:
+            ind = (self.iy, self.ix)
+        corners = od.tp.corner_indices(ind)
+        gny, gnx = od.tp.g_shape[-2:]
+        xs, ys = [], []
+        for c in corners:
+            c = tuple(np.asarray(a) for a in c)
+            xs.append(od.XG[c])
+            ys.append(od.YG[c])
+        px = np.vstack(xs).astype("float64")
+        py = np.vstack(ys).astype("float64")
+        px = self.lon + to_180(px - self.lon)
+        return px, py
+
+    def get_f_node_weight(self):
+        return weight_f_node(self.rx, self.ry)
+
+    def interpolate(self, var_name, knw, vec_transform=True, prefetched=None, prefetch_prefix=None):
+        """Interpolate / differentiate fields at the points (reference ``eulerian.py:1268``)."""
+        from .interp import interpolate  # noqa: PLC0415
+
+        return interpolate(self, var_name, knw, vec_transform, prefetched, prefetch_prefix)
+
+    def deepcopy_position(self):
+        p = object.__new__(type(self))
+        for key, item in vars(self).items():
+            if isinstance(item, (np.ndarray, RelCoord, list)):
+                object.__setattr__(p, key, copy.deepcopy(item))
+            else:
+                object.__setattr__(p, key, item)
+        return p

@@ -1,0 +1,562 @@
+"""Lagrangian ``Particle``: a ``Position`` that knows how to move itself.
+
+Same constructor and methods as the reference's ``seaduck.lagrangian.Particle``
+(``lagrangian.py:56``): ``update_uvw_array`` :175, ``get_vol`` :202, ``get_u_du`` :218,
+``note_taking`` :301 / ``empty_lists`` :355, ``to_next_stop`` :741, ``to_list_of_time`` :804,
+``deepcopy`` :725.  The particle state lives on the GPU as a structure of arrays; one call of
+``to_next_stop`` is one launch of the fused ``sdk_advect`` kernel.  numpy attributes
+(``pt.lon``, ``pt.ix`` ...) are host mirrors fetched lazily after the device state changed.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import warnings
+
+import numpy as np
+
+from . import _lib
+from .eulerian import Position
+from .kernel_weight import KnW
+from .ocedata import RelCoord
+
+DEG2M = 6271e3 * np.pi / 180  # sic (reference lagrangian.py:22)
+
+uvkernel = np.array([[0, 0], [1, 0], [0, 1]])
+ukernel = np.array([[0, 0], [1, 0]])
+vkernel = np.array([[0, 0], [0, 1]])
+wkernel = np.array([[0, 0]])
+udoll = [[0, 1]]
+vdoll = [[0, 2]]
+wdoll = [[0]]
+wknw = KnW(kernel=wkernel, inheritance=None, vkernel="linear", ignore_mask=True)
+uknw = KnW(kernel=uvkernel, inheritance=udoll, ignore_mask=True)
+vknw = KnW(kernel=uvkernel, inheritance=vdoll, ignore_mask=True)
+dwknw = KnW(kernel=wkernel, inheritance=None, vkernel="dz", ignore_mask=True)
+duknw = KnW(kernel=uvkernel, inheritance=udoll, hkernel="dx", h_order=1, ignore_mask=True)
+dvknw = KnW(kernel=uvkernel, inheritance=vdoll, hkernel="dy", h_order=1, ignore_mask=True)
+uknw_scalar = KnW(kernel=ukernel, inheritance=None, ignore_mask=True)
+vknw_scalar = KnW(kernel=vkernel, inheritance=None, ignore_mask=True)
+duknw_scalar = KnW(kernel=ukernel, inheritance=None, hkernel="dx", h_order=1, ignore_mask=True)
+dvknw_scalar = KnW(kernel=vkernel, inheritance=None, hkernel="dy", h_order=1, ignore_mask=True)
+
+# python attribute -> (device array name, lives in rel?, numpy dtype of the host mirror)
+_STATE = {
+    "lon": ("lon", False, np.float64),
+    "lat": ("lat", False, np.float64),
+    "dep": ("dep", False, np.float64),
+    "t": ("t", False, np.float64),
+    "face": ("face", True, np.int64),
+    "iy": ("iy", True, np.int64),
+    "ix": ("ix", True, np.int64),
+    "izl_lin": ("izl", True, np.int64),
+    "it": ("it", True, np.int64),
+    "rx": ("rx", True, np.float64),
+    "ry": ("ry", True, np.float64),
+    "rzl_lin": ("rzl", True, np.float64),
+    "u": ("u", False, np.float64),
+    "v": ("v", False, np.float64),
+    "w": ("w", False, np.float64),
+    "du": ("du", False, np.float64),
+    "dv": ("dv", False, np.float64),
+    "dw": ("dw", False, np.float64),
+    "px": ("px", False, np.float64),
+    "py": ("py", False, np.float64),
+    "dx": ("dx", True, np.float32),
+    "dy": ("dy", True, np.float32),
+    "bzl_lin": ("bzl", True, np.float64),
+    "dzl_lin": ("dzl", True, np.float64),
+    "vol": ("vol", False, np.float64),
+}
+_LIST_NAMES = {
+    "fclist": "fc", "itlist": "it", "izlist": "izl", "rzlist": "rzl", "iylist": "iy", "ixlist": "ix",
+    "rxlist": "rx", "rylist": "ry", "ttlist": "tt", "uulist": "uu", "vvlist": "vv", "wwlist": "ww",
+    "dulist": "du", "dvlist": "dv", "dwlist": "dw", "xxlist": "xx", "yylist": "yy", "zzlist": "zz",
+    "vslist": "vs",
+}
+
+
+class Particle(Position):
+    """Lagrangian particles advected on the GPU.  Parameters as in the reference (``lagrangian.py:93``)."""
+
+    def __init__(
+        self,
+        uname="UVELMASS",
+        vname="VVELMASS",
+        wname="WVELMASS",
+        free_surface="noflux",
+        save_raw=False,
+        transport=False,
+        callback=None,
+        max_iteration=200,
+        **kwarg,
+    ):
+        Position.__init__(self)
+        if "bool_array" in kwarg.keys():
+            raise NotImplementedError("from_bool_array seeding is not part of the hot path yet (SURVEY §8f-2)")
+        self.from_latlon(**kwarg)
+        od = self.ocedata
+        self.uname, self.vname, self.wname = uname, vname, wname
+        self.wknw, self.dwknw = wknw, dwknw
+        if self.face is not None:
+            self.uknw, self.duknw, self.vknw, self.dvknw = uknw, duknw, vknw, dvknw
+        else:
+            self.uknw, self.duknw, self.vknw, self.dvknw = uknw_scalar, duknw_scalar, vknw_scalar, dvknw_scalar
+        self.callback = callback
+        self.transport = transport
+        if self.transport:
+            try:
+                assert isinstance(od["Vol"], np.ndarray)
+            except (AssertionError, KeyError):
+                od._add_missing_vol(as_numpy=True)
+        self.free_surface = free_surface
+        if free_surface == "noflux" and wname is not None:
+            logging.warning("Setting the surface velocity to zero. Dataset might be modified. ")
+            od[self.wname].loc[{"Zl": 0}] = 0
+            od._field_cache = {k: v for k, v in od._field_cache.items() if k[0] != self.wname}
+        self.too_large = od.too_large
+        self.max_iteration = max_iteration
+        self.save_raw = save_raw
+        self._has_dep = self.dep is not None and od.readiness["Zl"]
+        self._init_device_state()
+        self.update_uvw_array()
+        if self.transport:
+            self.get_vol()
+        self.get_u_du()
+        if self.save_raw:
+            self.empty_lists()
+
+    # ------------------------------------------------------------------------------------------
+    # device state
+    # ------------------------------------------------------------------------------------------
+    def _init_device_state(self):
+        import torch  # noqa: PLC0415
+
+        od = self.ocedata
+        dev = od._torch_device()
+        n = self.N
+        loc = self.__dict__.pop("_located")
+        dlon, dlat, ddep, dt = loc["_inputs"]
+        st = {}
+        f64 = lambda: torch.zeros(n, dtype=torch.float64, device=dev)  # noqa: E731
+        st["lon"], st["lat"] = dlon.clone(), dlat.clone()
+        st["dep"] = ddep.clone() if ddep is not None else (
+            torch.as_tensor(self.dep, dtype=torch.float64).to(dev) if self.dep is not None else f64()
+        )
+        st["t"] = dt.clone() if dt is not None else (
+            torch.as_tensor(self.t, dtype=torch.float64).to(dev) if self.t is not None else f64()
+        )
+        st["face"] = loc["face"] if "face" in loc else None
+        st["iy"], st["ix"] = loc["iy"], loc["ix"]
+        st["rx"], st["ry"] = loc["rx"], loc["ry"]
+        st["px"], st["py"] = loc["px"], loc["py"]
+        st["dx"], st["dy"] = loc["dx"], loc["dy"]
+        if self._has_dep:
+            st["izl"], st["rzl"], st["dzl"], st["bzl"] = loc["izl"], loc["rzl"], loc["dzl"], loc["bzl"]
+        else:
+            st["izl"] = torch.zeros(n, dtype=torch.int32, device=dev)
+            st["rzl"], st["bzl"] = f64(), f64()
+            st["dzl"] = torch.ones(n, dtype=torch.float64, device=dev)
+        st["it"] = loc["it"] if "it" in loc else torch.zeros(n, dtype=torch.int32, device=dev)
+        for name in ("u", "v", "w", "du", "dv", "dw"):
+            st[name] = f64()
+        st["vol"] = torch.ones(n, dtype=torch.float64, device=dev)
+        for name in ("status", "niter", "ncross"):
+            st[name] = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.__dict__["_st"] = st
+        self.__dict__["_crossings"] = torch.zeros((), dtype=torch.int64, device=dev)
+        self.__dict__["_stale"] = set()
+        self.__dict__["_raw"] = []
+        if not od.readiness["h"] == "oceanparcel":
+            raise NotImplementedError("Particle: only the oceanparcel horizontal scheme runs on the GPU")
+        # host mirrors of what the constructor of the reference sets as float32 zeros
+        for name in ("u", "v", "w", "du", "dv", "dw", "vol", "px", "py"):
+            self._stale.add(name)
+        for key in ("izl_lin", "rzl_lin", "dzl_lin", "bzl_lin"):
+            if not self._has_dep and key not in self.rel:
+                self.rel[key] = None
+
+    def _cparticles(self, active=None):
+        st = self._st
+        p = _lib.Particles()
+        p.n = self.N
+        for name in _lib.PARTICLE_F64 + _lib.PARTICLE_I32 + _lib.PARTICLE_F64B + _lib.PARTICLE_F32 + _lib.PARTICLE_F64C + ["status", "niter", "ncross"]:
+            t = st.get(name)
+            setattr(p, name, None if t is None else t.data_ptr())
+        p.active = None if active is None else active.data_ptr()
+        return p
+
+    def _pull(self, attr):
+        """Refresh the host mirror of one attribute from the device."""
+        dev_name, in_rel, dtype = _STATE[attr]
+        t = self._st.get(dev_name)
+        if t is None:
+            val = None
+        else:
+            val = t.cpu().numpy().astype(dtype, copy=False)
+            if attr in ("px", "py"):
+                val = val.reshape(4, -1)
+        if in_rel:
+            self.rel[attr] = val
+        else:
+            self.__dict__[attr] = val
+        self._stale.discard(attr)
+        return val
+
+    def _mark_stale(self, names=None):
+        names = _STATE.keys() if names is None else names
+        for attr in names:
+            _, in_rel, _ = _STATE[attr]
+            if attr in ("izl_lin", "rzl_lin", "dzl_lin", "bzl_lin") and not self._has_dep:
+                continue
+            if attr == "face" and self._st.get("face") is None:
+                continue
+            if attr == "it" and not self.ocedata.readiness["time"]:
+                continue
+            if attr in ("dx", "dy") and self.ocedata.dX is None:
+                continue
+            self._stale.add(attr)
+            if not in_rel:
+                self.__dict__.pop(attr, None)
+        # derived rel-coords are recomputed on demand
+        self.__dict__["_derived_ok"] = False
+
+    def __getattr__(self, attr):
+        d = object.__getattribute__(self, "__dict__")
+        if "_st" in d:
+            if attr in _STATE and attr in d["_stale"]:
+                return self._pull(attr)
+            if attr in _LIST_NAMES:
+                return self._raw_list(attr)
+            if attr in ("bx", "by", "cs", "sn", "iz", "rz", "dz", "bz", "izl", "rzl", "dzl", "bzl", "rt", "dt", "bt") and not d.get("_derived_ok", True):
+                self._refresh_derived()
+        return Position.__getattr__(self, attr)
+
+    def __getattribute__(self, attr):
+        # rel-backed state attributes are found by __getattr__; plain ones that went stale were
+        # removed from __dict__, so the normal path is unchanged and cheap
+        return object.__getattribute__(self, attr)
+
+    def __setattr__(self, attr, value):
+        d = self.__dict__
+        if "_st" in d and attr in _STATE and value is not None:
+            import torch  # noqa: PLC0415
+
+            dev_name, in_rel, dtype = _STATE[attr]
+            tgt = d["_st"].get(dev_name)
+            arr = np.ascontiguousarray(value)
+            tdtype = tgt.dtype if tgt is not None else torch.float64
+            new = torch.as_tensor(arr.reshape(-1)).to(device=self.ocedata._torch_device(), dtype=tdtype)
+            d["_st"][dev_name] = new
+            d["_stale"].discard(attr)
+        Position.__setattr__(self, attr, value)
+
+    def _rel_get(self, key):
+        if key in self._stale:
+            return self._pull(key)
+        return self.rel.get(key)
+
+    def _refresh_derived(self):
+        """bx, by, cs, sn and the nearest-level vertical rel-coords follow the current cell / depth
+        (the reference refreshes them in cross_cell_wall, lagrangian.py:640-686)."""
+        od = self.ocedata
+        self.__dict__["_derived_ok"] = True
+        face, iy, ix = self._rel_get("face"), self._rel_get("iy"), self._rel_get("ix")
+        ind = (face, iy, ix) if face is not None else (iy, ix)
+        self.rel["bx"] = od.XC[ind]
+        self.rel["by"] = od.YC[ind]
+        if od.CS is not None and od.SN is not None:
+            self.rel["cs"] = od.CS[ind]
+            self.rel["sn"] = od.SN[ind]
+        if self._has_dep:
+            dep = self.dep
+            self.rel["iz"] = self._rel_get("izl_lin") - 1
+            if od.readiness["Z"]:
+                v = od._find_rel_v(dep)
+                self.rel["rz"], self.rel["dz"], self.rel["bz"] = v.rz, v.dz, v.bz
+
+    # ------------------------------------------------------------------------------------------
+    # velocity staging
+    # ------------------------------------------------------------------------------------------
+    def update_uvw_array(self):
+        """Stage the velocity slab needed by the particles on the device (reference :175)."""
+        od = self.ocedata
+        if "time" not in od[self.uname].dims:
+            if "_vel" in self.__dict__:
+                return
+            time_slice = None
+            it0 = 0
+        else:
+            it = self._st["it"]
+            self.itmin = int(it.min().item())
+            self.itmax = int(it.max().item())
+            time_slice = slice(self.itmin, self.itmax + 1)
+            it0 = self.itmin
+        ut = od.device_field(self.uname, time_slice)
+        vt = od.device_field(self.vname, time_slice)
+        wt = od.device_field(self.wname, time_slice) if self.wname is not None else None
+        udims, vdims = od[self.uname].dims, od[self.vname].dims
+        v = _lib.Velocity()
+        v.U, v.V = ut.data_ptr(), vt.data_ptr()
+        v.W = wt.data_ptr() if wt is not None else None
+        import torch  # noqa: PLC0415
+
+        if ut.dtype != vt.dtype or (wt is not None and wt.dtype != ut.dtype):
+            raise TypeError("u, v, w must share one storage dtype")
+        v.dtype = 0 if ut.dtype == torch.float64 else 1
+        v.has_time = int("time" in udims)
+        v.it0 = it0
+        v.nt = ut.shape[0] if v.has_time else 1
+        v.has_z = int("Z" in udims)
+        v.nzU = ut.shape[udims.index("Z")] if v.has_z else 1
+        v.nyU, v.nxU = ut.shape[-2:]
+        v.nyV, v.nxV = vt.shape[-2:]
+        v.u_stag = int("Xp1" in udims)
+        v.v_stag = int("Yp1" in vdims)
+        v.nzW = wt.shape[1 if v.has_time else 0] if wt is not None else 1
+        v.transport = int(self.transport)
+        keep = [ut, vt, wt]
+        if self.transport:
+            vol = np.asarray(od["Vol"])
+            vt_ = od.to_device("Vol", vol, np.float64 if vol.dtype != np.float32 else np.float32)
+            v.Vol = vt_.data_ptr()
+            v.vol_dtype = 0 if vt_.dtype == torch.float64 else 1
+            v.vol_has_z = int(vol.ndim == len(od.tp.h_shape) + 1)
+            keep.append(vt_)
+        self.__dict__["_vel"] = v
+        self.__dict__["_vel_keep"] = keep
+
+    def get_vol(self):
+        """Cell volume at the particles (reference :202); done together with get_u_du on the device."""
+        self._mark_stale(["vol"])
+
+    def get_u_du(self):
+        """Velocity and its gradient at the particles with the default kernels (reference :218)."""
+        L = _lib.lib()
+        p = self._cparticles()
+        _lib.check(
+            L.sdk_get_u_du(self.ocedata.grid_handle(), C.byref(self._vel), C.byref(p), int(self._has_dep), _lib.current_stream()),
+            "sdk_get_u_du",
+        )
+        self._mark_stale(["u", "v", "w", "du", "dv", "dw", "vol"])
+
+    def fillna(self):
+        """nan -> 0 for the velocities: already part of the device kernels (reference :289)."""
+
+    # ------------------------------------------------------------------------------------------
+    # crossing log
+    # ------------------------------------------------------------------------------------------
+    def empty_lists(self):
+        self.__dict__["_raw"] = []
+        self.__dict__["_pending_start"] = False
+
+    def note_taking(self, subset_index=None, stamp=-1):
+        """Only the start-of-stop record (stamp 15) is taken from the host; the rest is written by
+        the kernel (reference :301)."""
+        if not self.save_raw:
+            raise AttributeError("This is not a particle_rawlist object")
+        if stamp != 15 or subset_index is not None:
+            raise NotImplementedError("note_taking is done inside the advection kernel")
+        self.__dict__["_pending_start"] = True
+
+    def _raw_list(self, attr):
+        if not self.save_raw:
+            raise AttributeError("This is not a particle_rawlist object")
+        key = _LIST_NAMES[attr]
+        if key == "fc" and self._st.get("face") is None:
+            raise AttributeError(attr)
+        chunks = self._raw
+        out = [[] for _ in range(self.N)]
+        for ch in chunks:
+            vals = ch[key].cpu().numpy()
+            off = ch["offset"]
+            for i in range(self.N):
+                out[i].extend(vals[off[i] : off[i + 1]].tolist())
+        return out
+
+    def raw_arrays(self):
+        """Crossing log of the last stop(s) as flat numpy arrays + per-particle offsets."""
+        out = []
+        for ch in self._raw:
+            out.append({k: (v if k == "offset" else v.cpu().numpy()) for k, v in ch.items()})
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    # time stepping
+    # ------------------------------------------------------------------------------------------
+    def _params(self, max_iteration):
+        par = _lib.AdvectParams()
+        par.tol = 1e-4
+        par.trim_tol = 1e-14
+        par.max_iteration = int(max_iteration)
+        par.kick_back = int(self.free_surface == "kick_back")
+        par.has_dep = int(self._has_dep)
+        tune = getattr(self, "tuning", None) or {}
+        par.refill_threshold = int(tune.get("refill_threshold", 0))
+        par.blocks_per_sm = int(tune.get("blocks_per_sm", 0))
+        par.threads_per_block = int(tune.get("threads_per_block", 0))
+        return par
+
+    def _launch(self, t_stop, max_iteration, active=None, emit_start=False):
+        import torch  # noqa: PLC0415
+
+        L = _lib.lib()
+        handle = self.ocedata.grid_handle()
+        p = self._cparticles(active)
+        par = self._params(max_iteration)
+        stream = _lib.current_stream()
+        if not self.save_raw:
+            _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par), None, 1, stream), "sdk_advect")
+        else:
+            dev = self.ocedata._torch_device()
+            cnt = torch.zeros(self.N, dtype=torch.int32, device=dev)
+            lg = _lib.Log()
+            lg.count = cnt.data_ptr()
+            lg.emit_start = int(emit_start)
+            # pass 1: count the records of every particle without committing the state
+            _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par), C.byref(lg), 0, stream), "sdk_advect(count)")
+            offset = torch.zeros(self.N + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(cnt, 0, out=offset[1:])
+            total = int(offset[-1].item())
+            rec = {k: torch.zeros(total, dtype=torch.int32, device=dev) for k in _lib.LOG_I32}
+            rec.update({k: torch.zeros(total, dtype=torch.float64, device=dev) for k in _lib.LOG_F64})
+            lg.capacity = total
+            lg.offset = offset.data_ptr()
+            for k, tns in rec.items():
+                setattr(lg, k, tns.data_ptr())
+            # pass 2: same trajectory, now writing the records
+            _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par), C.byref(lg), 1, stream), "sdk_advect(log)")
+            rec["offset"] = offset.cpu().numpy()
+            self._raw.append(rec)
+        self._crossings += self._st["ncross"].sum()
+
+    def to_next_stop(self, t_stop):
+        """Integrate all particles to ``t_stop`` (reference ``lagrangian.py:741``)."""
+        import torch  # noqa: PLC0415
+
+        t_stop = float(t_stop)
+        tol = 1e-4
+        st = self._st
+        emit_start = bool(self.__dict__.get("_pending_start", False))
+        self.__dict__["_pending_start"] = False
+        todo = (t_stop - st["t"]).abs() > tol
+        if self.callback is None:
+            if not bool(todo.any().item()):
+                logging.info("Nothing left to simulate")
+                return
+            self._launch(t_stop, self.max_iteration, emit_start=emit_start)
+            self._mark_stale()
+            hit_max = bool((st["status"] & 1).any().item())
+        else:
+            # a host callback decides after every analytic step who keeps going
+            alive = todo.cpu().numpy() & np.asarray(self.callback(self), bool)
+            if not alive.any():
+                logging.info("Nothing left to simulate")
+                return
+            dev = self.ocedata._torch_device()
+            hit_max = False
+            for i in range(self.max_iteration):
+                active = torch.as_tensor(alive.astype(np.int32)).to(dev)
+                self._launch(t_stop, 1, active=active, emit_start=emit_start and i == 0)
+                self._mark_stale()
+                still = ((t_stop - st["t"]).abs() > tol).cpu().numpy()
+                idx = np.where(alive)[0]
+                keep = still[idx] & np.asarray(self.callback(self.subset(idx)), bool)
+                alive = np.zeros_like(alive)
+                alive[idx[keep]] = True
+                if not alive.any():
+                    break
+            if i == self.max_iteration - 1:
+                hit_max = True
+        if hit_max:
+            warnings.warn("maximum iteration count reached")
+        st["t"].fill_(t_stop)
+        od = self.ocedata
+        if od.readiness["time"]:
+            midp = od.to_device("time_midp", od.time_midp, np.float64)
+            _lib.check(
+                _lib.lib().sdk_time_index(st["t"].data_ptr(), midp.data_ptr(), len(od.time_midp), st["it"].data_ptr(), self.N, _lib.current_stream()),
+                "sdk_time_index",
+            )
+        self._mark_stale(["t", "it"])
+
+    @property
+    def crossings(self):
+        """Total number of cell-wall crossings so far (iterations that ended on a wall)."""
+        return int(self._crossings.item())
+
+    def deepcopy(self):
+        """Snapshot of the particles (reference ``lagrangian.py:725``): device-side clone."""
+        p = object.__new__(type(self))
+        object.__setattr__(p, "rel", RelCoord())
+        for key, item in self.__dict__.items():
+            if key in ("_st", "_stale", "_raw", "_crossings"):
+                continue
+            if isinstance(item, np.ndarray):
+                if item.ndim == 1:
+                    p.__dict__[key] = item.copy()
+            elif key == "rel":
+                continue
+            else:
+                p.__dict__[key] = item
+        for k, v in self.rel.items():
+            p.rel[k] = None if v is None else (v.copy() if isinstance(v, np.ndarray) else v)
+        p.__dict__["_st"] = {k: (None if v is None else v.clone()) for k, v in self._st.items()}
+        p.__dict__["_stale"] = set(self._stale)
+        p.__dict__["_raw"] = list(self._raw)
+        p.__dict__["_crossings"] = self._crossings.clone()
+        p.__dict__["_derived_ok"] = False
+        return p
+
+    def to_list_of_time(
+        self, normal_stops, update_stops="default", return_in_between=True, dump_filename=False, store_kwarg={}
+    ):
+        """Integrate to a list of times, returning a snapshot per stop (reference ``lagrangian.py:804``)."""
+        od = self.ocedata
+        t0 = float(self._st["t"][0].item())
+        t_min = np.minimum(np.min(normal_stops), t0)
+        t_max = np.maximum(np.max(normal_stops), t0)
+        if not self.save_raw and dump_filename:
+            raise ValueError("saving to file only available if save_raw = True")
+        has_time = "time" in od[self.uname].dims
+        if has_time:
+            data_tmin = od.ts.min()
+            data_tmax = od.ts.max()
+            if t_min < data_tmin or t_max > data_tmax:
+                raise ValueError("time range not within bound" + f"({data_tmin},{data_tmax})")
+        if isinstance(update_stops, str) and update_stops == "default":
+            if not has_time:
+                update_stops = []
+            else:
+                try:
+                    update_stops = od.time_midp[np.logical_and(t_min < od.time_midp, od.time_midp < t_max)]
+                except AttributeError as exc:
+                    raise AttributeError(
+                        "time_midp is required for update_stops = default, but it is not in the dataset, "
+                        "either create it or specify the update stops."
+                    ) from exc
+        if dump_filename:
+            raise NotImplementedError("dumping the crossing log to zarr is post-processing (SURVEY §8f-1)")
+        temp = list(zip(normal_stops, np.zeros_like(normal_stops))) + list(zip(update_stops, np.ones_like(update_stops)))
+        temp.sort(key=lambda x: abs(x[0] - t0))
+        stops, update = list(zip(*temp))
+        self.get_u_du()
+        to_return = []
+        for i, tl in enumerate(stops):
+            timestr = str(np.datetime64(round(tl), "s"))
+            logging.info(timestr)
+            if self.save_raw:
+                self.note_taking(stamp=15)
+            self.to_next_stop(tl)
+            if update[i] or i == 0:
+                if has_time:
+                    self.update_uvw_array()
+                    self.get_u_du()
+                if return_in_between:
+                    to_return.append(self.deepcopy())
+            else:
+                to_return.append(self.deepcopy())
+            if self.save_raw:
+                self.empty_lists()
+        return stops, to_return

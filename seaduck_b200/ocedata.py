@@ -1,0 +1,515 @@
+"""Ocean dataset wrapper + device staging of the grid.
+
+Same role and public surface as the reference's ``seaduck.ocedata`` (``OceData`` ``ocedata.py:147``,
+``RelCoord`` families ``:34-143``): variable aliasing, readiness checks, grid extraction to float32
+arrays, rel-coordinate lookups.  What differs is where things live: the grid arrays are uploaded
+once to the GPU (``sdk_grid_create``), the KD-tree is replaced by a device bucket grid
+(``sdk_grid_build_locator``) and every ``_find_rel_*`` call runs the ``sdk_locate`` kernel.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import logging
+
+import numpy as np
+
+from . import _lib, minixr
+from .topology import Topology
+
+NO_ALIAS = {
+    "dXC": "dxC",
+    "dYC": "dyC",
+    "dZ": "drC",
+    "dXG": "dxG",
+    "dYG": "dyG",
+    "dZl": "drF",
+}
+
+
+def _general_len(thing):
+    try:
+        return len(thing)
+    except TypeError:
+        return 1
+
+
+class RelCoord(dict):
+    """Relative coordinates: dictionary with attribute access (reference ``ocedata.py:34``)."""
+
+    def __getattr__(self, attr):
+        try:
+            return self[attr]
+        except KeyError as exc:
+            raise AttributeError(f"'RelCoord' object has no attribute '{attr}'") from exc
+
+    def __setattr__(self, attr, value):
+        self[attr] = value
+
+    def subset(self, which):
+        new = RelCoord()
+        for var in self.keys():
+            new[var] = None if self[var] is None else self[var][which]
+        return new
+
+    def update_from_subset(self, sub, which):
+        for var in sub.keys():
+            if var not in self.keys():
+                raise KeyError(f"Key {var} is in subset, but not in the one to update.")
+            if self[var] is not None:
+                self[var][which] = sub[var]
+
+    @classmethod
+    def create_class(cls, class_name, fields):
+        class NewClass(cls):
+            __slots__ = ()
+            _fields = fields
+
+            def __init__(self, *args):
+                if len(args) > len(fields):
+                    raise TypeError(
+                        f"{class_name} takes {len(fields)} positional arguments but {len(args)} were given"
+                    )
+                for name, value in zip(fields, args):
+                    setattr(self, name, value)
+
+            @classmethod
+            def _make(cls, iterable):
+                return cls(*iterable)
+
+            def __repr__(self):
+                vals = ", ".join(f"{name}={getattr(self, name)!r}" for name in self._fields)
+                return f"{class_name}({vals})"
+
+        NewClass.__name__ = class_name
+        return NewClass
+
+
+HRel = RelCoord.create_class("HRel", ["face", "iy", "ix", "rx", "ry", "cs", "sn", "dx", "dy", "bx", "by"])
+VRel = RelCoord.create_class("VRel", ["iz", "rz", "dz", "bz"])
+VLinRel = RelCoord.create_class("VLRel", ["iz_lin", "rz_lin", "dz_lin", "bz_lin"])
+VlRel = RelCoord.create_class("VlRel", ["izl", "rzl", "dzl", "bzl"])
+VlLinRel = RelCoord.create_class("VlLinRel", ["izl_lin", "rzl_lin", "dzl_lin", "bzl_lin"])
+TRel = RelCoord.create_class("TRel", ["it", "rt", "dt", "bt"])
+TLinRel = RelCoord.create_class("TLinRel", ["it_lin", "rt_lin", "dt_lin", "bt_lin"])
+
+_TYP = {"box": 0, "x_periodic": 1, "LLC": 2}
+_HMODE = {"oceanparcel": 0, "local_cartesian": 1, "rectilinear": 2}
+
+
+def _xr_module(data):
+    if isinstance(data, minixr.Dataset):
+        return minixr
+    import xarray as xr  # noqa: PLC0415
+
+    return xr
+
+
+class OceData:
+    """Ocean dataset: aliasing, topology, grid staging on the GPU, 4-D coordinate translation.
+
+    Parameters follow the reference (``ocedata.py:164``).  ``device`` selects the CUDA device
+    (default: current).
+    """
+
+    def __init__(self, data, alias=None, memory_limit=1e7, device=None):
+        self._xr = _xr_module(data)
+        self._ds = data.transpose(
+            "time", "time_midp", "time_outer", "Z", "Zl", "Zp1", "face", "Y", "Yp1", "X", "Xp1",
+            ..., missing_dims="ignore",
+        )
+        self.tp = Topology(self._ds)
+        if alias is None:
+            self.alias = NO_ALIAS
+        elif alias == "auto":
+            raise NotImplementedError("auto alias not yet implemented")
+        elif isinstance(alias, dict):
+            self.alias = alias
+        try:
+            self.too_large = self._ds["XC"].nbytes > memory_limit
+        except KeyError:
+            self.too_large = False
+        self.device = device
+        self._dev = {}  # name -> torch tensor on the GPU
+        self._field_cache = {}
+        self._grid_handle = None
+        readiness = self.check_readiness()
+        self.readiness = readiness
+        if readiness:
+            self._grid2array()
+
+        if self.readiness["Zl"]:
+            # zero bottom level on every Zl variable (reference ocedata.py:197-210)
+            xr = self._xr
+            with_zl = [i for i in self._ds.data_vars if "Zl" in self._ds[i].dims]
+            if len(with_zl) > 0:
+                without_zl = [i for i in self._ds.data_vars if i not in with_zl]
+                bottom_buffer = xr.zeros_like(self._ds[with_zl].isel(Zl=slice(1)))
+                bottom_buffer["Zl"] = [self.Zl[-1]]
+                neods = xr.merge(
+                    [
+                        xr.concat([self._ds[with_zl], bottom_buffer], dim="Zl"),
+                        self._ds[without_zl],
+                    ]
+                )
+                self._ds = neods
+
+    # ---- mapping surface (reference ocedata.py:212-229) ---------------------------------------
+    def __setitem__(self, key, item):
+        if isinstance(item, self._xr.DataArray):
+            if key in self.alias.keys():
+                self._ds[self.alias[key]] = item
+            else:
+                self._ds[key] = item
+        else:
+            object.__setattr__(self, key, item)
+
+    def __getitem__(self, key):
+        varsdict = vars(self)
+        if key in varsdict.keys():
+            return object.__getattribute__(self, key)
+        if key in self.alias.keys():
+            return self._ds[self.alias[key]]
+        return self._ds[key]
+
+    def check_readiness(self):
+        """Which interpolation schemes the dataset supports (reference ``ocedata.py:231``)."""
+        varnames = list(self._ds.variables)
+        readiness = {}
+        if all(i in varnames for i in ["XC", "YC", "XG", "YG"]):
+            readiness["h"] = "oceanparcel"
+        elif all(i in varnames for i in ["XC", "YC", "dxG", "dyG", "CS", "SN"]):
+            readiness["h"] = "local_cartesian"
+        elif all(i in varnames for i in ["lon", "lat"]):
+            ratio = 6371e3 * np.pi / 180
+            self.dlon = np.gradient(self["lon"]) * ratio
+            self.dlat = np.gradient(self["lat"]) * ratio
+            readiness["h"] = "rectilinear"
+        else:
+            readiness["h"] = False
+            raise ValueError(
+                """
+                Need a full set of the following to create the object:
+                {XC,YC,XG,YG} or {XC,YC,dxG,dyG,CS,SN} for curvilinear grid;
+                or {lon, lat} for rectilinear grid.
+
+                See add_missing variable or set_alias.
+                """
+            )
+        for _ in ["time", "Z", "Zl"]:
+            readiness[_] = (_ in varnames) and (_general_len(self[_]) > 1)
+        return readiness
+
+    def _add_missing_vol(self, as_numpy=False):
+        """``Vol = drF * rA * hFacC`` (reference ``ocedata.py:303``)."""
+        if self.readiness["Zl"]:
+            vol = self._ds["drF"] * self._ds["rA"]
+            if "HFacC" in self._ds.variables:
+                vol = vol * self._ds["HFacC"]
+            elif "hFacC" in self._ds.variables:
+                vol = vol * self._ds["hFacC"]
+            vol = vol.transpose("Z", "face", "Y", "X", missing_dims="ignore")
+        else:
+            vol = self._ds["rA"]
+        vol = vol.fillna(0)
+        if as_numpy:
+            self["Vol"] = np.array(vol)
+        else:
+            self["Vol"] = vol
+
+    # ---- grid extraction ----------------------------------------------------------------------
+    def _grid2array(self):
+        if self.readiness["h"] == "oceanparcel":
+            for var in ["XC", "YC", "XG", "YG"]:
+                self[var] = np.array(self[var], dtype="float32")
+            for var in ["rA", "CS", "SN"]:
+                try:
+                    self[var] = np.array(self[var], dtype="float32")
+                except KeyError:
+                    logging.info("no %s in dataset, skip", var)
+                    self[var] = None
+            try:
+                self.dX = np.array(self["dXG"], dtype="float32")
+                self.dY = np.array(self["dYG"], dtype="float32")
+            except KeyError:
+                self.dX = None
+                self.dY = None
+        elif self.readiness["h"] == "local_cartesian":
+            for var in ["XC", "YC", "CS", "SN"]:
+                self[var] = np.array(self[var], dtype="float32")
+            self.dX = np.array(self["dXG"], dtype="float32")
+            self.dY = np.array(self["dYG"], dtype="float32")
+            for var in ["XG", "YG", "dXC", "dYC", "rA"]:
+                try:
+                    self[var] = np.array(self[var], dtype="float32")
+                except KeyError:
+                    self[var] = None
+        elif self.readiness["h"] == "rectilinear":
+            self.lon = np.array(self["lon"], dtype="float32")
+            self.lat = np.array(self["lat"], dtype="float32")
+        if self.readiness["Z"]:
+            self.Z = np.array(self["Z"], dtype="float32")
+            try:
+                self.dZ = np.array(self["dZ"], dtype="float32")
+            except KeyError:
+                self.dZ = np.diff(self.Z)
+                self.dZ = np.append(self.dZ, self.dZ[-1]).astype("float32")
+        if self.readiness["Zl"]:
+            if "Zp1" in self._ds.variables:
+                self.Zl = np.array(self["Zp1"], dtype="float32")
+            else:
+                self.Zl = np.zeros(len(self["Zl"]) + 1)
+                self.Zl[:-1] = np.array(self._ds["Zl"])
+                self.Zl[-1] = 2 * self.Zl[-2] - self.Zl[-3]
+                self.Zl = self.Zl.astype("float32")
+            try:
+                self.dZl = np.array(self["dZl"], dtype="float32")
+            except KeyError:
+                self.dZl = np.diff(self.Zl).astype("float32")
+        if self.readiness["time"]:
+            self.t_base = 0
+            self.ts = np.array(self["time"])
+            if self["time"].dtype != "float":
+                self.ts = (self.ts).astype(float) / 1e9
+            try:
+                self.time_midp = np.array(self["time_midp"])
+                self.time_midp = (self.time_midp).astype(float) / 1e9
+            except KeyError:
+                self.time_midp = (self.ts[1:] + self.ts[:-1]) / 2
+
+    # ---- device side ----------------------------------------------------------------------------
+    def _torch_device(self):
+        import torch  # noqa: PLC0415
+
+        if not torch.cuda.is_available():
+            raise _lib.SdkError("seaduck_b200 needs a CUDA device (B200); there is no CPU fallback")
+        if self.device is None:
+            return torch.device("cuda", torch.cuda.current_device())
+        return torch.device(self.device)
+
+    def to_device(self, name, array, dtype=None):
+        """Upload (once) a host array; returns the cached torch tensor."""
+        import torch  # noqa: PLC0415
+
+        if name not in self._dev:
+            arr = np.ascontiguousarray(array, dtype=dtype)
+            self._dev[name] = torch.from_numpy(arr).to(self._torch_device())
+        return self._dev[name]
+
+    def grid_handle(self):
+        """Create (once) the device grid: uploads the float32 grid and the topology tables."""
+        if self._grid_handle is not None:
+            return self._grid_handle
+        if self.readiness["h"] != "oceanparcel":
+            raise NotImplementedError(
+                "the CUDA path implements the oceanparcel horizontal scheme (XC, YC, XG, YG); "
+                f"this dataset is '{self.readiness['h']}'"
+            )
+        L = _lib.lib()
+        tp = self.tp
+        d = _lib.GridDesc()
+        d.typ = _TYP[tp.typ]
+        d.has_face = int(tp.has_face)
+        d.nface = tp.h_shape[0] if tp.has_face else 1
+        d.ny, d.nx = tp.h_shape[-2:]
+        d.gny, d.gnx = tp.g_shape[-2:]
+        d.hmode = _HMODE[self.readiness["h"]]
+        keep = []
+        if tp.typ == "LLC":
+            nf = np.ascontiguousarray(tp.nbr_face, np.int32)
+            ne = np.ascontiguousarray(tp.nbr_edge, np.int32)
+            keep += [nf, ne]
+            d.nbr_face = nf.ctypes.data
+            d.nbr_edge = ne.ctypes.data
+        for name in ("XC", "YC", "XG", "YG", "dX", "dY", "CS", "SN"):
+            arr = getattr(self, name, None)
+            if arr is not None:
+                setattr(d, name, self.to_device(name, arr, np.float32).data_ptr())
+        if self.readiness["Zl"]:
+            d.n_zl = len(self.Zl)
+            d.n_z = len(self.dZl)
+            d.Zl = self.to_device("Zl", self.Zl, np.float32).data_ptr()
+            d.dZl = self.to_device("dZl", self.dZl, np.float32).data_ptr()
+        if self.readiness["Z"]:
+            d.n_zc = len(self.Z)
+            d.Z = self.to_device("Z", self.Z, np.float32).data_ptr()
+            d.dZ = self.to_device("dZ", self.dZ, np.float32).data_ptr()
+        if d.gny <= d.ny or d.gnx <= d.nx:
+            d.corner_tab = self.to_device("corner_tab", self._corner_table(), np.int32).data_ptr()
+        handle = C.c_void_p()
+        _lib.check(L.sdk_grid_create(C.byref(d), C.byref(handle)), "sdk_grid_create")
+        self._grid_handle = handle
+        self._keep = keep
+        self._build_locator()
+        return handle
+
+    def _corner_table(self):
+        """Flat XG indices of the LR, UR, UL corners of the cells on the top row / right column."""
+        tp = self.tp
+        ny, nx = tp.h_shape[-2:]
+        gny, gnx = tp.g_shape[-2:]
+        nface = tp.h_shape[0] if tp.has_face else 1
+        f = np.repeat(np.arange(nface), nx + ny)
+        slot = np.tile(np.arange(nx + ny), nface)
+        iy = np.where(slot < nx, ny - 1, slot - nx)
+        ix = np.where(slot < nx, slot, nx - 1)
+        ind = (f, iy, ix) if tp.has_face else (iy, ix)
+        n = len(f)
+        table = np.full((n, 3), -1, np.int64)
+        ind1, st1 = tp.ind_tend_vec(ind, np.full(n, 3), cuvwg="G", swallow=True, return_status=True)
+        ind2, st2 = tp.ind_tend_vec(tuple(ind1), np.full(n, 0), cuvwg="G", swallow=True, return_status=True)
+        ind3, st3 = tp.ind_tend_vec(ind, np.full(n, 0), cuvwg="G", swallow=True, return_status=True)
+        for k, (idx, st) in enumerate(((ind1, st1), (ind2, st2 | st1), (ind3, st3))):
+            idx = [np.asarray(a) for a in idx]
+            yy = np.where(idx[-2] < 0, idx[-2] + gny, idx[-2])
+            xx = np.where(idx[-1] < 0, idx[-1] + gnx, idx[-1])
+            ff = idx[0] if tp.has_face else 0
+            flat = (ff * gny + yy) * gnx + xx
+            abnormal = (st == 2) | (yy >= gny) | (xx >= gnx)
+            table[:, k] = np.where(abnormal, -1, flat)
+        return table.astype(np.int32)
+
+    def _build_locator(self):
+        L = _lib.lib()
+        xc = np.asarray(self.XC, np.float64)
+        yc = np.asarray(self.YC, np.float64)
+        ncell = xc.size
+        lat0, lat1 = float(np.nanmin(yc)), float(np.nanmax(yc))
+        lon_min, lon_max = float(np.nanmin(xc)), float(np.nanmax(xc))
+        if self.tp.typ in ("LLC", "x_periodic") or lon_max - lon_min > 300:
+            lon0, span_lon = -180.0, 360.0
+        else:
+            pad = 1e-6 + 0.01 * (lon_max - lon_min)
+            lon0, span_lon = lon_min - pad, (lon_max - lon_min) + 2 * pad
+        pad = 1e-6 + 0.01 * (lat1 - lat0)
+        lat0, span_lat = lat0 - pad, (lat1 - lat0) + 2 * pad
+        # about one cell per bucket
+        aspect = max(span_lon / span_lat, 1e-3)
+        nlat = int(np.clip(np.sqrt(ncell / aspect), 4, 8192))
+        nlon = int(np.clip(nlat * aspect, 4, 16384))
+        _lib.check(
+            L.sdk_grid_build_locator(self._grid_handle, lon0, lat0, span_lon, span_lat, nlon, nlat, _lib.current_stream()),
+            "sdk_grid_build_locator",
+        )
+
+    def __del__(self):
+        try:
+            if self._grid_handle is not None:
+                _lib.lib().sdk_grid_destroy(self._grid_handle)
+        except Exception:  # noqa: BLE001
+            pass
+
+    def device_field(self, name, time_slice=None):
+        """Device copy of a data variable (optionally a slab of snapshots), cached.
+
+        Replaces ``Particle.update_uvw_array`` / ``smart_read`` gathers from host memory
+        (reference ``lagrangian.py:175``, ``smart_read.py:22``): fields stay resident in HBM.
+        """
+        import torch  # noqa: PLC0415
+
+        key = (name, None if time_slice is None else (time_slice.start, time_slice.stop))
+        hit = self._field_cache.get(key)
+        if hit is not None:
+            return hit
+        da = self[name]
+        arr = np.asarray(da[time_slice] if time_slice is not None else da)
+        if arr.dtype not in (np.float32, np.float64):
+            arr = arr.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self._torch_device())
+        # keep at most two slabs per variable (current + previous)
+        same = [k for k in self._field_cache if k[0] == name]
+        for k in same[:-1]:
+            del self._field_cache[k]
+        self._field_cache[key] = t
+        return t
+
+    # ---- rel-coordinate lookups (reference ocedata.py:422-488), all on the device ---------------
+    def locate(self, x=None, y=None, z=None, t=None):
+        """Run ``sdk_locate``; returns a dict of torch tensors on the device."""
+        import torch  # noqa: PLC0415
+
+        L = _lib.lib()
+        handle = self.grid_handle()
+        dev = self._torch_device()
+        n = max(_general_len(v) for v in (x, y, z, t) if v is not None)
+        up = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, np.float64)).to(dev)  # noqa: E731
+        dx, dy, dz, dt = up(x), up(y), up(z), up(t)
+        out = {}
+        loc = _lib.Located()
+
+        def alloc(name, dtype, mult=1):
+            out[name] = torch.empty(n * mult, dtype=dtype, device=dev)
+            setattr(loc, name, out[name].data_ptr())
+
+        if dx is not None:
+            if self.tp.has_face:
+                alloc("face", torch.int32)
+            for nme in ("iy", "ix", "status"):
+                alloc(nme, torch.int32)
+            for nme in ("rx", "ry"):
+                alloc(nme, torch.float64)
+            for nme in ("cs", "sn", "dx", "dy", "bx", "by"):
+                alloc(nme, torch.float32)
+            alloc("px", torch.float64, 4)
+            alloc("py", torch.float64, 4)
+        if dz is not None:
+            if self.readiness["Z"]:
+                alloc("iz", torch.int32)
+                for nme in ("rz", "dz", "bz"):
+                    alloc(nme, torch.float64)
+            if self.readiness["Zl"]:
+                alloc("izl_near", torch.int32)
+                alloc("izl", torch.int32)
+                for nme in ("rzl_near", "dzl_near", "bzl_near", "rzl", "dzl", "bzl"):
+                    alloc(nme, torch.float64)
+        ts_dev = None
+        n_t = 0
+        if dt is not None and self.readiness["time"]:
+            ts_dev = self.to_device("ts", self.ts, np.float64)
+            n_t = len(self.ts)
+            alloc("it", torch.int32)
+            for nme in ("rt", "dt", "bt"):
+                alloc(nme, torch.float64)
+        _lib.check(
+            L.sdk_locate(
+                handle, n, _lib.ptr(dx), _lib.ptr(dy), _lib.ptr(dz), _lib.ptr(dt), _lib.ptr(ts_dev), n_t,
+                C.byref(loc), _lib.current_stream(),
+            ),
+            "sdk_locate",
+        )
+        out["_inputs"] = (dx, dy, dz, dt)
+        return out
+
+    @staticmethod
+    def _np(t, dtype=None):
+        a = t.cpu().numpy()
+        return a.astype(dtype) if dtype is not None else a
+
+    def _find_rel_h(self, x, y):
+        o = self.locate(x=x, y=y)
+        face = self._np(o["face"], np.int64) if "face" in o else None
+        ints = [self._np(o[k], np.int64) for k in ("iy", "ix")]
+        rest = [self._np(o[k]) for k in ("rx", "ry", "cs", "sn", "dx", "dy", "bx", "by")]
+        if self.CS is None:
+            rest[2] = rest[3] = None
+        if self.dX is None:
+            rest[4] = rest[5] = None
+        return HRel._make([face] + ints + rest)
+
+    def _find_rel_v(self, z):
+        o = self.locate(z=z)
+        return VRel(self._np(o["iz"], np.int64), self._np(o["rz"]), self._np(o["dz"]), self._np(o["bz"]))
+
+    def _find_rel_vl(self, z):
+        o = self.locate(z=z)
+        return VlRel(
+            self._np(o["izl_near"], np.int64), self._np(o["rzl_near"]), self._np(o["dzl_near"]), self._np(o["bzl_near"])
+        )
+
+    def _find_rel_vl_lin(self, z):
+        o = self.locate(z=z)
+        return VlLinRel(self._np(o["izl"], np.int64), self._np(o["rzl"]), self._np(o["dzl"]), self._np(o["bzl"]))
+
+    def _find_rel_t(self, t):
+        o = self.locate(t=t)
+        return TRel(self._np(o["it"], np.int64), self._np(o["rt"]), self._np(o["dt"]), self._np(o["bt"]))

@@ -1,0 +1,107 @@
+"""Seeded workloads shared by the golden generator, the oracle tests and the GPU parity tests."""
+
+import numpy as np
+
+from seaduck_b200 import synthetic
+
+DAY = 86400.0
+
+
+def case_gyre(n=120):
+    ds = synthetic.gyre(50, 50)
+    rng = np.random.RandomState(2023)
+    x = rng.random_sample(n) * 2 - 1
+    y = rng.random_sample(n) * 2 - 1
+    return dict(
+        name="gyre",
+        ds=ds,
+        x=x, y=y, z=np.full(n, -1.0), t=np.zeros(n),
+        stops=[300.0, 700.0, 1500.0],
+        kw=dict(wname=None, transport=True),
+    )
+
+
+def case_overturning(n=200):
+    ds = synthetic.overturning_cell(100, 50)
+    rng = np.random.RandomState(7)
+    x = rng.uniform(-1, 1, n)
+    z = rng.uniform(-0.1, -1000, n)
+    return dict(
+        name="overturning",
+        ds=ds,
+        x=x, y=np.zeros(n), z=z, t=np.zeros(n),
+        stops=[-2000.0, -5000.0],
+        kw=dict(transport=True),
+    )
+
+
+def case_llc_transport(n=300, ngrid=30, nz=10):
+    ds = synthetic.llc(n=ngrid, nz=nz)
+    lon, lat, dep = synthetic.llc_seed_particles(ds, n, seed=1, depth_range=(5, 300))
+    return dict(
+        name="llc_transport",
+        ds=ds,
+        x=lon, y=lat, z=dep, t=np.zeros(n),
+        stops=[20 * DAY, 60 * DAY],
+        kw=dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True),
+    )
+
+
+def case_llc_velocity(n=300, ngrid=30, nz=10):
+    ds = synthetic.llc(n=ngrid, nz=nz, dtype=np.float32)
+    lon, lat, dep = synthetic.llc_seed_particles(ds, n, seed=2, depth_range=(5, 300))
+    return dict(
+        name="llc_velocity_f32",
+        ds=ds,
+        x=lon, y=lat, z=dep, t=np.zeros(n),
+        stops=[15 * DAY, -10 * DAY],
+        kw=dict(transport=False),
+    )
+
+
+def case_llc_time(n=200, ngrid=24, nz=6):
+    ds = synthetic.llc(n=ngrid, nz=nz, nt=4)
+    lon, lat, dep = synthetic.llc_seed_particles(ds, n, seed=3, depth_range=(5, 120))
+    return dict(
+        name="llc_time",
+        ds=ds,
+        x=lon, y=lat, z=dep, t=np.full(n, 1.0 * DAY),
+        stops=[4 * DAY, 12 * DAY, 17 * DAY],
+        kw=dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True),
+        list_of_time=True,
+    )
+
+
+def case_llc_surface2d(n=300, ngrid=48):
+    ds = synthetic.llc(n=ngrid, nz=0)
+    lon, lat, _ = synthetic.llc_seed_particles(ds, n, seed=4)
+    return dict(
+        name="llc_surface2d",
+        ds=ds,
+        x=lon, y=lat, z=np.full(n, -1.0), t=np.zeros(n),
+        stops=[10 * DAY, 30 * DAY],
+        kw=dict(wname=None, transport=False),
+    )
+
+
+ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d]
+
+LOG_INT = ["fc", "it", "izl", "iy", "ix", "vs"]
+LOG_FLT = ["rzl", "rx", "ry", "tt", "uu", "vv", "ww", "du", "dv", "dw", "xx", "yy", "zz"]
+FINAL_INT = ["face", "iy", "ix", "izl_lin", "it"]
+FINAL_FLT = ["lon", "lat", "dep", "t", "rx", "ry", "rzl_lin", "u", "v", "w", "du", "dv", "dw"]
+
+
+def assert_close(name, got, ref, rtol=1e-9):
+    """|got - ref| <= rtol * max(|ref|, field scale): the 1e-9 relative bound of the north star."""
+    got = np.asarray(got, float)
+    ref = np.asarray(ref, float)
+    assert got.shape == ref.shape, f"{name}: shape {got.shape} vs {ref.shape}"
+    if ref.size == 0:
+        return
+    scale = max(float(np.nanmax(np.abs(ref))), 1e-300)
+    if name in ("rx", "ry", "rzl", "rzl_lin", "lon", "lat", "xx", "yy"):
+        scale = max(scale, 1.0)
+    err = np.abs(got - ref)
+    bad = err > rtol * np.maximum(np.abs(ref), scale)
+    assert not bad.any(), f"{name}: {int(bad.sum())} of {ref.size} beyond {rtol} (max err {err.max():.3e}, scale {scale:.3e})"

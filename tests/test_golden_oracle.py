@@ -1,0 +1,56 @@
+"""CPU: the oracle (oracle/sd_oracle.c + oracle/oracle.py) against golden vectors produced by the
+unmodified reference (oracle/make_golden.py).  Integer records (stamps, face, iy, ix, izl, it) must be
+bit-exact; floats within 1e-9 relative."""
+
+import os
+
+import numpy as np
+import pytest
+
+import cases
+from seaduck_b200.ocedata import OceData
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+STATE_MAP = dict(face="face", iy="iy", ix="ix", izl_lin="izl", it="it", lon="lon", lat="lat", dep="dep", t="t",
+                 rx="rx", ry="ry", rzl_lin="rzl", u="u", v="v", w="w", du="du", dv="dv", dw="dw")
+
+
+def compare_log(gold, prefix, rec):
+    off = gold[f"{prefix}offset"]
+    np.testing.assert_array_equal(rec["offset"], off)
+    for k in cases.LOG_INT:
+        if f"{prefix}{k}" in gold:
+            np.testing.assert_array_equal(np.asarray(rec[k]), gold[f"{prefix}{k}"], err_msg=k)
+    for k in cases.LOG_FLT:
+        if f"{prefix}{k}" in gold:
+            cases.assert_close(k, rec[k], gold[f"{prefix}{k}"])
+
+
+def compare_state(gold, prefix, get, has_dep=True):
+    for k in cases.FINAL_INT:
+        if f"{prefix}{k}" in gold:
+            np.testing.assert_array_equal(np.asarray(get(k)), gold[f"{prefix}{k}"], err_msg=k)
+    for k in cases.FINAL_FLT:
+        if f"{prefix}{k}" in gold and gold[f"{prefix}{k}"].dtype.kind == "f":
+            cases.assert_close(k, get(k), gold[f"{prefix}{k}"])
+
+
+@pytest.mark.parametrize("make", cases.ALL_CASES, ids=lambda f: f.__name__)
+def test_oracle_matches_reference_golden(make, oracle_lib):
+    case = make()
+    gold = np.load(os.path.join(GOLD, f"lagrangian_{case['name']}.npz"))
+    od = OceData(case["ds"])
+    op = oracle_lib.oracle_particle_from_od(od, case["x"], case["y"], case["z"], case["t"], save_raw=True, **case["kw"])
+    get = lambda k: getattr(op, STATE_MAP[k])  # noqa: E731
+    compare_state(gold, "init_", get)
+    if case.get("list_of_time"):
+        res = oracle_lib.oracle_to_list_of_time(op, case["stops"])
+        np.testing.assert_allclose([r[0] for r in res], gold["stops"])
+        for i, (_, rec, state) in enumerate(res):
+            compare_log(gold, f"s{i}_log_", rec)
+            compare_state(gold, f"s{i}_", lambda k: state[STATE_MAP[k]])
+    else:
+        for i, ts in enumerate(case["stops"]):
+            op.to_next_stop(ts, emit_start=True)
+            compare_log(gold, f"s{i}_log_", op.records)
+            compare_state(gold, f"s{i}_", get)
