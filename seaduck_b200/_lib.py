@@ -12,7 +12,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-SO_PATH = os.path.join(_HERE, "libseaduck_b200.so")
+SO_PATH = os.environ.get("SEADUCK_B200_LIB") or os.path.join(_HERE, "libseaduck_b200.so")
 SOURCES = ["advect.cu", "locate.cu", "interp.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode",

@@ -148,23 +148,12 @@ __device__ __forceinline__ void trim_axis(double &x, double &u, double du, doubl
     }
 }
 
-template <typename T>
-__device__ __forceinline__ int64_t uv_index(const GridDev &g, const VelDev &v, bool is_v, int it,
-                                            int iz, int f, int iy, int ix) {
-    const int ny = is_v ? v.nyV : v.nyU, nx = is_v ? v.nxV : v.nxU;
-    int64_t idx = 0;
-    if (v.has_time) idx = wrap_index(it - v.it0, v.nt);
-    if (v.has_z) idx = idx * v.nzU + wrap_index(iz, v.nzU);
-    idx = idx * g.nface + f;
-    return (idx * ny + wrap_index(iy, ny)) * nx + wrap_index(ix, nx);
-}
-
 // Gather the wall values and form u, du, v, dv, w, dw (reference get_u_du lagrangian.py:218 with the
 // kernels of lagrangian.py:25-53; on LLC grids the right / top wall may live on the neighbouring
 // face and be the other velocity component, reference eulerian.py:887 + topology.py:618-647).
+// Index arithmetic: 32-bit within a horizontal plane, one 64-bit multiply-add for the level/time.
 template <typename T>
 __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v, int has_dep, Lane &s) {
-    const int iz = s.izl - 1;
     // ---- where do the right and top wall values live?
     int rf = s.f, ry_ = s.iy, rx_ = s.ix, r_in;
     int tf = s.f, ty_ = s.iy, tx_ = s.ix, t_in;
@@ -188,35 +177,36 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
         }
     } else {
         // scalar kernels on a single face: naive neighbour, topology walk only off the array
+        // (an index of -1, -1 from a closed box reads the last element, like numpy does)
         const int xlim = v.u_stag ? g.gnx : g.nx, ylim = v.v_stag ? g.gny : g.ny;
         rx_ = s.ix + 1;
         if (rx_ > xlim - 1) {
             if (g.typ == SDK_TYP_XPERIODIC) rx_ = rx_ - (g.nx - 1);
-            else { ry_ = -1; rx_ = -1; }
+            else { ry_ = v.nyU - 1; rx_ = v.nxU - 1; }
         }
         ty_ = s.iy + 1;
-        if (ty_ > ylim - 1) { ty_ = -1; tx_ = -1; }
+        if (ty_ > ylim - 1) { ty_ = v.nyV - 1; tx_ = v.nxV - 1; }
     }
-    const int64_t iul = uv_index<T>(g, v, false, s.it, iz, s.f, s.iy, s.ix);
-    const int64_t ivl = uv_index<T>(g, v, true, s.it, iz, s.f, s.iy, s.ix);
-    const int64_t iur = uv_index<T>(g, v, r_is_v, s.it, iz, rf, ry_, rx_);
-    const int64_t ivr = uv_index<T>(g, v, !t_is_u, s.it, iz, tf, ty_, tx_);
+    const int tlev = v.has_time ? wrap_index(s.it - v.it0, v.nt) : 0;
+    const int64_t lev_uv = v.has_z ? (int64_t)(tlev * v.nzU + wrap_index(s.izl - 1, v.nzU)) : (int64_t)tlev;
+    const int c_ul = (s.f * v.nyU + s.iy) * v.nxU + s.ix;
+    const int c_vl = (s.f * v.nyV + s.iy) * v.nxV + s.ix;
+    const int c_ur = r_is_v ? (rf * v.nyV + ry_) * v.nxV + rx_ : (rf * v.nyU + ry_) * v.nxU + rx_;
+    const int c_vr = t_is_u ? (tf * v.nyU + ty_) * v.nxU + tx_ : (tf * v.nyV + ty_) * v.nxV + tx_;
     // issue every load before using any of them
-    const double ul = ldf<T>(v.U, iul);
-    const double vl = ldf<T>(v.V, ivl);
-    const double ur = ldf<T>(r_is_v ? v.V : v.U, iur);
-    const double vr = ldf<T>(t_is_u ? v.U : v.V, ivr);
+    const double ul = ldf<T>(v.U, lev_uv * v.planeU + c_ul);
+    const double vl = ldf<T>(v.V, lev_uv * v.planeV + c_vl);
+    const double ur = ldf<T>(r_is_v ? v.V : v.U, lev_uv * (r_is_v ? v.planeV : v.planeU) + c_ur);
+    const double vr = ldf<T>(t_is_u ? v.U : v.V, lev_uv * (t_is_u ? v.planeU : v.planeV) + c_vr);
+    const int cell = (s.f * g.ny + s.iy) * g.nx + s.ix;
     double w0 = 0.0, w1 = 0.0;
     if (v.has_w) {
-        int64_t base = v.has_time ? wrap_index(s.it - v.it0, v.nt) : 0;
-        const int64_t cell = ((int64_t)s.f * g.ny + wrap_index(s.iy, g.ny)) * g.nx + wrap_index(s.ix, g.nx);
-        const int64_t lev = (int64_t)g.nface * g.ny * g.nx;
-        w0 = ldf<T>(v.W, (base * v.nzW + wrap_index(s.izl, v.nzW)) * lev + cell);
-        w1 = ldf<T>(v.W, (base * v.nzW + wrap_index(s.izl - 1, v.nzW)) * lev + cell);
+        const int64_t wl = (int64_t)tlev * v.nzW;
+        w0 = ldf<T>(v.W, (wl + wrap_index(s.izl, v.nzW)) * v.planeC + cell);
+        w1 = ldf<T>(v.W, (wl + wrap_index(s.izl - 1, v.nzW)) * v.planeC + cell);
     }
     if (v.transport) {
-        int64_t idx = v.vol_has_z ? wrap_index(s.izl - 1, g.n_z > 0 ? g.n_z : 1) : 0;
-        idx = ((idx * g.nface + s.f) * g.ny + wrap_index(s.iy, g.ny)) * g.nx + wrap_index(s.ix, g.nx);
+        const int64_t idx = (v.vol_has_z ? (int64_t)wrap_index(s.izl - 1, g.n_z > 0 ? g.n_z : 1) : 0) * v.planeC + cell;
         s.vol = v.vol_dtype == SDK_F64 ? ldf<double>(v.Vol, idx) : ldf<float>(v.Vol, idx);
     }
     const double ul_ = nan_to_num(ul), ur_ = nan_to_num(ur), vl_ = nan_to_num(vl), vr_ = nan_to_num(vr);
@@ -356,8 +346,12 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
     if (LOG && live) note(a, s, 7);
 }
 
+#ifndef SDK_ADVECT_MIN_BLOCKS
+#define SDK_ADVECT_MIN_BLOCKS 4
+#endif
+
 template <typename T, bool LOG>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SDK_ADVECT_MIN_BLOCKS)
 advect_kernel(const __grid_constant__ AdvectArgs a) {
     extern __shared__ float smem[];
     float *sZl = smem;

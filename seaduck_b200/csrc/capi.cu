@@ -142,6 +142,9 @@ static int fill_args(const sdk_grid *grid, const sdk_velocity *vel, const sdk_pa
     v.u_stag = vel->u_stag; v.v_stag = vel->v_stag; v.vol_has_z = vel->vol_has_z;
     v.transport = vel->transport;
     v.has_w = (vel->W != nullptr) && has_dep;
+    v.planeU = (int64_t)grid->dev.nface * v.nyU * v.nxU;
+    v.planeV = (int64_t)grid->dev.nface * v.nyV * v.nxV;
+    v.planeC = (int64_t)grid->dev.nface * grid->dev.ny * grid->dev.nx;
     a.p = *p;
     if (log) a.log = *log; else std::memset(&a.log, 0, sizeof a.log);
     a.t_stop = t_stop;

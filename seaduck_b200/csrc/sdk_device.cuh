@@ -27,6 +27,7 @@ struct VelDev {
     const void *U, *V, *W, *Vol;
     int dtype, vol_dtype, has_time, it0, nt, has_z, nzU, nzW, nyU, nxU, nyV, nxV;
     int u_stag, v_stag, vol_has_z, transport, has_w;
+    int64_t planeU, planeV, planeC;  // elements per (time, level) slab of U, V and of cell-centred fields
 };
 
 __device__ __forceinline__ double py_mod360(double a) {
@@ -40,16 +41,24 @@ __device__ __forceinline__ double py_mod360(double a) {
     return m;
 }
 
-// reference to_180, utils.py:199:  x % 360 % 360, then minus 360 in the upper half
+// reference to_180, utils.py:199:  x % 360 % 360, then minus 360 in the upper half.
+// The first "%" leaves m in [0, 360]; m == 360.0 happens when x is a tiny negative number (a
+// particle sitting on a wall, 360 - 1e-14 rounds to 360) and is what the second "%" is there for:
+// fmod(360, 360) = +0.  For m in [360, 720) fmod(m, 360) == m - 360 exactly, so no fmod is needed.
 __device__ __forceinline__ double to_180(double x) {
-    x = py_mod360(py_mod360(x));
+    x = py_mod360(x);
+    if (x >= 360.0) x = x - 360.0;
     double q = (x >= 180.0) ? 1.0 : 0.0;  // == x // 180 for x in [0, 360)
     return x + (-1.0) * q * 360.0;
 }
 
+// numpy.nan_to_num: nan -> 0, +-inf -> +-DBL_MAX.  One integer test on the exponent in the common
+// (finite) case.
 __device__ __forceinline__ double nan_to_num(double x) {
-    if (isnan(x)) return 0.0;
-    if (isinf(x)) return x > 0 ? DBL_MAX : -DBL_MAX;
+    if ((__double2hiint(x) & 0x7ff00000) == 0x7ff00000) {
+        if (x != x) return 0.0;
+        return x > 0 ? DBL_MAX : -DBL_MAX;
+    }
     return x;
 }
 
@@ -157,20 +166,31 @@ __device__ __forceinline__ void inverse_bilinear(double x, double y, const doubl
 
 // Exit times of one axis (reference _stationary_time utils.py:821, _uleftright_from_udu :852 and the
 // closed-wall rule of _time2wall :864-869)
+//
+// The reference evaluates both logarithms and then overwrites the time of a wall the flow cannot
+// reach with -sign(tf).  Only reachable walls matter, and usually just one wall per axis is
+// reachable, so the (expensive) logarithm is evaluated once with the arguments of that wall:
+// tl = log(1 - k(1/2 + x0))/du == log(1 + k(-1/2 - x0))/du bit for bit.
 __device__ __forceinline__ void wall_times(double u, double du, double x0, double sg, double &tl,
                                            double &tr) {
-    if (fabs(du) < 1e-12) {
-        tl = (-x0 - 0.5) / u;
-        tr = (0.5 - x0) / u;
-    } else {
-        const double k = du / u;
-        tl = log(1 - k * (0.5 + x0)) / du;
-        tr = log(1 + k * (0.5 - x0)) / du;
-    }
     const double ul = u - (x0 + 0.5) * du;
     const double ur = u + (0.5 - x0) * du;
-    if (-ul * sg <= 1e-12) tl = -sg;
-    if (ur * sg <= 1e-12) tr = -sg;
+    const bool open_l = !(-ul * sg <= 1e-12);
+    const bool open_r = !(ur * sg <= 1e-12);
+    tl = -sg;
+    tr = -sg;
+    if (!(open_l || open_r)) return;
+    const double dl = -0.5 - x0, dr = 0.5 - x0;
+    if (fabs(du) < 1e-12) {
+        if (open_l) tl = dl / u;
+        if (open_r) tr = dr / u;
+        return;
+    }
+    const double k = du / u;
+    const double t1 = log(1 + k * (open_l ? dl : dr)) / du;
+    if (open_l) tl = t1;
+    else tr = t1;
+    if (open_l && open_r) tr = log(1 + k * dr) / du;  // diverging flow inside the cell: rare
 }
 
 // reference _increment, utils.py:777
