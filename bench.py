@@ -2,24 +2,26 @@
 """Headline benchmark: particle cell-crossings per second (BASELINE.json `metric`).
 
 Workload (BASELINE.json configs[1]): a 3-D LLC90-shaped synthetic field (13 faces x 90 x 90 x 50
-levels, volume transports in fp64) and 10^6 particles per GPU seeded uniformly on the sphere, so
-trajectories cross cell walls, vertical levels and LLC face edges.  One *step* is one call of
-``Particle.to_next_stop`` (one launch of the fused advection kernel) that carries every particle
-`--days` days further; consecutive steps continue the same trajectories, so K steps are K output
-stops of ``Particle.to_list_of_time``.  A crossing is an analytic step that ended on a cell wall
-(``tend < 6``), counted on the device exactly like the instrumented reference does.
+levels, volume transports, fp64) and batches of 10^6 particles per GPU seeded uniformly on the
+sphere, so trajectories cross cell walls, vertical levels and LLC face edges.
+
+One *step* = one pass of the hot path over one batch: ``Particle.to_next_stop`` (one launch of the
+fused advection kernel) carries a fresh batch of 10^6 located particles `--days` days forward.
+Every step works on a different batch (all batches are resident in HBM before the timed region;
+fields 168 MB + 220 MB of state per batch >> L2, so nothing is served from a warm cache).
+A crossing is an analytic step that ended on a cell wall (``tend < 6``), counted on the device
+exactly like the instrumented reference does (wrap ``cross_cell_wall``, sum ``tend < 6``).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-Prints ONE JSON line (see the keys at the bottom).  `value` = crossings/s with the state resident
-in HBM; `e2e` = the same metric through the C-ABI host-buffer call (``sdk_advect_host``: pinned
-host state -> H2D -> kernel -> D2H inside the timed region).
+Prints ONE JSON line.  `value` = crossings/s with the state resident in HBM; `e2e` = the same
+metric through the C-ABI host-buffer call ``sdk_track_host`` (pinned host lon/lat/dep/t -> H2D ->
+locate -> velocity read -> advect -> D2H of positions and indices, all inside the timed region).
 """
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -32,20 +34,22 @@ sys.path.insert(0, ROOT)
 DAY = 86400.0
 ALGO_BYTES_PER_CROSSING = 88  # 6 wall transports + Vol (fp64) + 4 corners x (XG,YG) f32
 STATE_BYTES_PER_PARTICLE = 440  # 220 B of state read + 220 B written once per launch
+KW = dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True)
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU")
+    ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU and batch")
     ap.add_argument("--days", type=float, default=30.0, help="simulated days per step")
     ap.add_argument("--grid", type=int, default=90)
     ap.add_argument("--levels", type=int, default=50)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="field storage (math is fp64)")
     ap.add_argument("--no-sort", action="store_true", help="keep particles in seeding order")
+    ap.add_argument("--max-batches", type=int, default=12, help="distinct batches kept in HBM (reused cyclically)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="particles of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -56,17 +60,14 @@ def parse():
 
 
 def workload_name(a):
-    return f"LLC{a.grid}-shaped 3D synthetic transports ({13}x{a.grid}x{a.grid}x{a.levels}), {a.particles} particles/GPU, {a.days:g} d per step"
-
-
-KW = dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True)
+    return (f"LLC{a.grid}-shaped 3D synthetic transports (13x{a.grid}x{a.grid}x{a.levels}), "
+            f"{a.particles} particles per GPU and step, {a.days:g} d per step")
 
 
 def make_dataset(a):
     from seaduck_b200 import synthetic
 
-    dtype = np.float64 if a.dtype == "f64" else np.float32
-    return synthetic.llc(n=a.grid, nz=a.levels, dtype=dtype)
+    return synthetic.llc(n=a.grid, nz=a.levels, dtype=np.float64 if a.dtype == "f64" else np.float32)
 
 
 def seeds(ds, n, seed):
@@ -76,89 +77,85 @@ def seeds(ds, n, seed):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clock and throttle reasons during the timed region, via NVML (B200_PROFILING.md)."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index = index
-        self.samples = []
-        self.stop_flag = False
+        self.index, self.samples, self.stop_flag = index, [], False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        except Exception:  # noqa: BLE001
+            self.nv = None
 
     def run(self):
-        while not self.stop_flag:
+        nv = self.nv
+        while nv is not None and not self.stop_flag:
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                    capture_output=True, text=True, timeout=5,
-                ).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((sm, mx, rs))
             except Exception:  # noqa: BLE001
                 pass
-            time.sleep(0.1)
+            time.sleep(0.002)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [nm for k, nm in enumerate(names) if any(len(s) > 3 + k and s[3 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+        }
+        reasons = [k for k, bit in names.items() if any(s[2] & bit for s in self.samples)]
+        return {"sm_mhz": float(np.median([s[0] for s in self.samples])), "sm_max_mhz": float(max(s[1] for s in self.samples)),
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def cpu_baseline(a, threads, steps=1, seed=99):
-    """Time the CPU oracle (C port of the reference loop) on a bounded sample of the same workload."""
+def oracle_particle(a, n, threads, seed=99):
     from oracle import oracle
     from seaduck_b200.ocedata import OceData
 
     ds = make_dataset(a)
     od = OceData(ds)
-    n = a.cpu_sample
     lon, lat, dep = seeds(ds, n, seed)
-    op = oracle.oracle_particle_from_od(od, lon, lat, dep, np.zeros(n), nthreads=threads, **KW)
-    total, elapsed, per_step = 0, 0.0, []
-    for k in range(steps):
-        t0 = time.perf_counter()
-        c = op.to_next_stop((k + 1) * a.days * DAY)
-        dt = time.perf_counter() - t0
-        total += c
-        elapsed += dt
-        per_step.append(dt)
-    return total, elapsed, per_step
+    return oracle.oracle_particle_from_od(od, lon, lat, dep, np.zeros(n), nthreads=threads, **KW)
+
+
+def cpu_baseline(a, threads):
+    """Time the CPU oracle (C port of the reference loop) on a bounded sample of the same workload."""
+    op = oracle_particle(a, a.cpu_sample, threads)
+    t0 = time.perf_counter()
+    c = op.to_next_stop(a.days * DAY)
+    return c, time.perf_counter() - t0
 
 
 def run_reference(a):
-    """`--impl reference`: the reference's CPU algorithm (oracle port; the Python reference cannot
-    travel to the GPU box) on all host threads, bounded sample per step."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """`--impl reference`: the reference's CPU algorithm on all host threads.  The reference itself
+    is Python and cannot travel to the GPU box, so this is its C port (oracle/sd_oracle.c, pinned
+    to the reference by golden vectors); each step is a bounded sample of the workload."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     threads = os.cpu_count() or 1
-    # warm-up steps advance the same trajectories, untimed
-    from oracle import oracle
-    from seaduck_b200.ocedata import OceData
-
-    ds = make_dataset(a)
-    od = OceData(ds)
     n = a.cpu_sample
-    lon, lat, dep = seeds(ds, n, 99)
-    op = oracle.oracle_particle_from_od(od, lon, lat, dep, np.zeros(n), nthreads=threads, **KW)
-    k = 0
-    for _ in range(a.warmup):
-        k += 1
-        op.to_next_stop(k * a.days * DAY)
-    total = 0
-    t0 = time.perf_counter()
-    for _ in range(a.steps):
-        k += 1
-        total += op.to_next_stop(k * a.days * DAY)
-    elapsed = time.perf_counter() - t0
+    total, elapsed = 0, 0.0
+    for i in range(a.warmup + a.steps):
+        op = oracle_particle(a, n, threads, seed=99 + i)  # a fresh batch per step, like the CUDA arm
+        t0 = time.perf_counter()
+        c = op.to_next_stop(a.days * DAY)
+        dt = time.perf_counter() - t0
+        if i >= a.warmup:
+            total += c
+            elapsed += dt
     value = total / elapsed
-    sample = f"{n} particles x {a.days:g} d per step (same field, same seeding law), C port of the reference loop, {threads} threads"
+    sample = (f"{n} particles x {a.days:g} d per step (same field, same seeding law), C port of the reference loop "
+              f"(oracle/sd_oracle.c), {threads} threads")
     line = {
         "impl": "reference", "metric": "particle cell-crossings/sec", "value": value, "unit": "crossings/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * elapsed / a.steps,
@@ -171,6 +168,8 @@ def run_reference(a):
 
 
 def run_cuda(a):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
 
@@ -181,91 +180,105 @@ def run_cuda(a):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    import ctypes as C
-
     import seaduck_b200 as sd
     from seaduck_b200 import _lib
 
+    L = _lib.lib()
     ds = make_dataset(a)
     od = sd.OceData(ds)
+    handle = od.grid_handle()
     n = a.particles
-    lon, lat, dep = seeds(ds, n, seed=1000 + rank)  # disjoint particle slice per rank
-    if not a.no_sort:
-        # cell-major order so that the lanes of a warp touch neighbouring memory (K5)
-        loc = od.locate(x=lon, y=lat, z=dep)
-        key = ((loc["izl"].long() * 13 + loc["face"].long()) * a.grid + loc["iy"].long()) * a.grid + loc["ix"].long()
-        order = torch.argsort(key).cpu().numpy()
-        lon, lat, dep = lon[order], lat[order], dep[order]
-    pt = sd.Particle(x=lon, y=lat, z=dep, t=np.zeros(n), data=od, **KW)
-    pt.tuning = dict(refill_threshold=a.refill, blocks_per_sm=a.blocks_per_sm, threads_per_block=a.threads)
-    snap_bytes = n * (3 * 8 + 4 * 4)
-    gather = None
-    if world > 1:
-        gather = torch.empty(world * n * 5, dtype=torch.float64, device=dev)
+    t_stop = a.days * DAY
+    nb = min(a.warmup + a.steps, a.max_batches)
 
-    def snapshot_allgather():
-        # output trajectories of all ranks (lon, lat, dep f64 + face/iy/ix/izl packed) -- the only
-        # collective of the path
-        st = pt._st
-        packed = torch.cat([st["lon"], st["lat"], st["dep"],
-                            (st["face"].double() * 1e6 + st["iy"].double()), (st["ix"].double() * 1e3 + st["izl"].double())])
-        dist.all_gather_into_tensor(gather, packed)
+    def make_batch(b):
+        lon, lat, dep = seeds(ds, n, seed=1000 + 97 * rank + b)  # disjoint particle slices per rank / batch
+        if not a.no_sort:
+            # cell-major order so that the lanes of a warp touch neighbouring memory (K5)
+            loc = od.locate(x=lon, y=lat, z=dep)
+            key = ((loc["izl"].long() * 13 + loc["face"].long()) * a.grid + loc["iy"].long()) * a.grid + loc["ix"].long()
+            order = torch.argsort(key).cpu().numpy()
+            lon, lat, dep = lon[order], lat[order], dep[order]
+        pt = sd.Particle(x=lon, y=lat, z=dep, t=np.zeros(n), data=od, **KW)
+        pt.tuning = dict(refill_threshold=a.refill, blocks_per_sm=a.blocks_per_sm, threads_per_block=a.threads)
+        return pt, (lon, lat, dep)
 
-    def step(k):
-        pt.to_next_stop(k * a.days * DAY)
+    batches, host_inputs = [], []
+    for b in range(nb):
+        pt, xyz = make_batch(b)
+        batches.append(pt)
+        if b == 0:
+            host_inputs = xyz
+    # initial state of every batch: restored (device copy) when a batch is reused
+    reuse = a.warmup + a.steps > nb
+    saved = [{k: (None if v is None else v.clone()) for k, v in pt._st.items()} for pt in batches]
+    gather = torch.empty(world * n * 5, dtype=torch.float64, device=dev) if world > 1 else None
+
+    def restore(b):
+        for k, v in saved[b].items():
+            if v is not None:
+                batches[b]._st[k].copy_(v)
+
+    def step(i):
+        b = i % nb
+        pt = batches[b]
+        if i >= nb:
+            restore(b)
+        pt.to_next_stop(t_stop)
         if world > 1:
-            snapshot_allgather()
+            # output trajectories of all ranks -- the only collective of the path
+            st = pt._st
+            packed = torch.cat([st["lon"], st["lat"], st["dep"], st["face"].double() * 1e6 + st["iy"].double(),
+                                st["ix"].double() * 1e3 + st["izl"].double()])
+            dist.all_gather_into_tensor(gather, packed)
 
-    k = 0
-    for _ in range(a.warmup):
-        k += 1
-        step(k)
+    for i in range(a.warmup):
+        step(i)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    c0 = pt.crossings
+    c0 = sum(pt.crossings for pt in batches)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
-    t_start.record()
     wall0 = time.perf_counter()
+    t_start.record()
     for i in range(a.steps):
-        k += 1
         ev[i][0].record()
-        step(k)
+        step(a.warmup + i)
         ev[i][1].record()
     t_end.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
     if world > 1:
         dist.barrier()
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
     elapsed_ms = t_start.elapsed_time(t_end)
-    crossings = pt.crossings - c0
+    crossings = sum(pt.crossings for pt in batches) - c0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
 
-    # ---- kernel-only timing of the dominant kernel (events right around the C-ABI launch) ------
-    L = _lib.lib()
-    handle = od.grid_handle()
+    # ---- the dominant kernel alone: CUDA events right around the C-ABI launch, fresh state each time
     kern_ms, kern_cross = [], []
-    for i in range(min(a.steps, 5)):
-        k += 1
+    stats = torch.zeros(4, dtype=torch.int64, device=dev)
+    for i in range(min(nb, 8)):
+        pt = batches[i]
+        restore(i)
         p = pt._cparticles()
         par = pt._params(pt.max_iteration)
+        stats.zero_()
+        par.stats = stats.data_ptr()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        _lib.check(L.sdk_advect(handle, C.byref(pt._vel), C.byref(p), float(k * a.days * DAY), C.byref(par), None, 1, _lib.current_stream()), "sdk_advect")
+        _lib.check(L.sdk_advect(handle, C.byref(pt._vel), C.byref(p), float(t_stop), C.byref(par), None, 1, _lib.current_stream()), "sdk_advect")
         e1.record()
         torch.cuda.synchronize()
-        pt._st["t"].fill_(k * a.days * DAY)
         kern_ms.append(e0.elapsed_time(e1))
-        kern_cross.append(int(pt._st["ncross"].sum().item()))
-    kms = float(np.mean(kern_ms))
-    kcr = float(np.mean(kern_cross))
+        kern_cross.append(int(stats[1].item()))
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    kms, kcr = float(np.mean(kern_ms)), float(np.mean(kern_cross))
     algo_bytes = kcr * ALGO_BYTES_PER_CROSSING + n * STATE_BYTES_PER_PARTICLE
     achieved = algo_bytes / (kms * 1e-3) / 1e9
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -278,44 +291,44 @@ def run_cuda(a):
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
 
-    # ---- end-to-end through the C-ABI host-buffer call -------------------------------------------
+    # ---- end to end through the C ABI with host buffers ------------------------------------------------
     e2e = None
     if not a.no_e2e:
-        names = _lib.PARTICLE_F64 + _lib.PARTICLE_I32 + _lib.PARTICLE_F64B + _lib.PARTICLE_F32 + _lib.PARTICLE_F64C + ["status", "niter", "ncross"]
-        host = {nm: (None if pt._st.get(nm) is None else pt._st[nm].cpu().pin_memory()) for nm in names}
-        hp = _lib.Particles()
-        hp.n = n
-        for nm in names:
-            setattr(hp, nm, None if host[nm] is None else host[nm].data_ptr())
-        scratch = torch.empty(int(L.sdk_particles_bytes(n)), dtype=torch.uint8, device=dev)
-        in_bytes = sum(v.numel() * v.element_size() for nm, v in host.items() if v is not None and nm not in ("status", "niter", "ncross"))
-        out_bytes = sum(v.numel() * v.element_size() for nm, v in host.items() if v is not None)
-        par = pt._params(pt.max_iteration)
-        kk = k
+        pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()  # noqa: E731
+        hin = [pin(x) for x in host_inputs] + [torch.zeros(n, dtype=torch.float64).pin_memory()]
+        hout_f = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]
+        hout_i = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(6)]
+        io = _lib.TrackIO()
+        io.n = n
+        io.lon, io.lat, io.dep, io.t = (h.data_ptr() for h in hin)
+        io.out_lon, io.out_lat, io.out_dep = (h.data_ptr() for h in hout_f)
+        io.out_face, io.out_iy, io.out_ix, io.out_izl, io.out_ncross, io.out_status = (h.data_ptr() for h in hout_i)
+        scratch = torch.empty(int(L.sdk_track_scratch_bytes(n)), dtype=torch.uint8, device=dev)
+        par = batches[0]._params(200)
+        par.stats = None
+        in_bytes, out_bytes = 4 * 8 * n, 3 * 8 * n + 6 * 4 * n
         e2e_cross, e2e_t = 0, 0.0
         for i in range(2 + a.steps):
-            kk += 1
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            _lib.check(L.sdk_advect_host(handle, C.byref(pt._vel), C.byref(hp), float(kk * a.days * DAY), C.byref(par), scratch.data_ptr(), _lib.current_stream()), "sdk_advect_host")
+            _lib.check(L.sdk_track_host(handle, C.byref(batches[0]._vel), C.byref(io), None, 0, float(t_stop), C.byref(par),
+                                        scratch.data_ptr(), _lib.current_stream()), "sdk_track_host")
             dt = time.perf_counter() - t0
-            host["t"].fill_(kk * a.days * DAY)
             if i >= 2:
                 e2e_t += dt
-                e2e_cross += int(host["ncross"].sum().item())
+                e2e_cross += int(hout_i[4].sum().item())
         e2e = (e2e_cross, e2e_t, in_bytes, out_bytes)
 
-    # ---- aggregate over ranks ------------------------------------------------------------------------
-    stats = torch.tensor([elapsed_ms, float(crossings), e2e[1] if e2e else 0.0, float(e2e[0]) if e2e else 0.0], dtype=torch.float64, device=dev)
+    # ---- aggregate over ranks ------------------------------------------------------------------------------
+    vals = torch.tensor([elapsed_ms, float(crossings), e2e[1] if e2e else 0.0, float(e2e[0]) if e2e else 0.0],
+                        dtype=torch.float64, device=dev)
     if world > 1:
-        mx = stats.clone()
+        mx, sm = vals.clone(), vals.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        elapsed_ms, crossings_all = float(mx[0]), float(sm[1])
-        e2e_time, e2e_cross_all = float(mx[2]), float(sm[3])
+        elapsed_ms, crossings_all, e2e_time, e2e_cross_all = float(mx[0]), float(sm[1]), float(mx[2]), float(sm[3])
     else:
         crossings_all = float(crossings)
         e2e_time, e2e_cross_all = (e2e[1], float(e2e[0])) if e2e else (0.0, 0.0)
@@ -326,25 +339,28 @@ def run_cuda(a):
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": elapsed_ms / a.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
             "config": {
-                "workload": workload_name(a), "transport": True, "particles_per_gpu": n, "days_per_step": a.days,
-                "crossings_per_step": crossings_all / a.steps, "particle_order": "seeding" if a.no_sort else "cell-sorted at start",
-                "l2": "inputs larger than L2 (fields 168 MB + particle state 220 MB per 1e6 particles); no flush",
+                "workload": workload_name(a), "transport": True, "particles_per_gpu_per_step": n, "days_per_step": a.days,
+                "crossings_per_step": crossings_all / a.steps,
+                "particle_order": "seeding" if a.no_sort else "cell-sorted at seeding time",
+                "batches": f"{nb} distinct batches resident in HBM" + (", reused cyclically with a device-side state restore inside the timed region" if reuse else ", one per step"),
+                "l2": "inputs larger than L2 (fields 168 MB + 220 MB of particle state per batch, a different batch every step); no flush",
                 "collective": "all_gather of the output snapshot per step" if world > 1 else "none",
-                "step_ms": [round(x, 3) for x in step_ms], "host_wall_s": wall,
+                "step_ms_first10": [round(x, 3) for x in step_ms[:10]], "host_wall_s": wall,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "advect_kernel",
-                         "kernel_ms": kms, "crossings_per_launch": kcr,
-                         "algorithmic_bytes_per_launch": algo_bytes},
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "advect_kernel<double,false>",
+                         "kernel_ms": kms, "crossings_per_launch": kcr, "algorithmic_bytes_per_launch": algo_bytes,
+                         "note": "latency/issue bound, not bandwidth bound: see profiles/"},
             "gpu_launches": a.steps * world,
             "clocks": sampler.summary(),
         }
         if e2e:
             line["e2e"] = {"value": e2e_cross_all / e2e_time if e2e_time else None, "unit": "crossings/s",
                            "h2d_bytes_per_step": e2e[2], "d2h_bytes_per_step": e2e[3],
-                           "api": "sdk_advect_host (C ABI, pinned host state in/out)"}
+                           "api": "sdk_track_host (C ABI): pinned host lon/lat/dep/t in, positions + indices out; "
+                                  "locate + velocity read + advect on the device", "gpu_launches_per_step": 3}
         if not a.no_cpu_baseline:
-            tot, el, _ = cpu_baseline(a, threads=1)
+            tot, el = cpu_baseline(a, threads=1)
             line["cpu_baseline"] = {"value": tot / el, "unit": "crossings/s", "cores": 1, "kind": "port",
                                     "sample": f"{a.cpu_sample} particles x {a.days:g} d, one step, C port of the reference loop (oracle/sd_oracle.c), 1 thread"}
         print(json.dumps(line))

@@ -118,6 +118,9 @@ typedef struct sdk_advect_params {
     int32_t refill_threshold; /* idle lanes per warp that trigger a refill, 0 = library default */
     int32_t blocks_per_sm;    /* 0 = library default */
     int32_t threads_per_block;/* 0 = library default */
+    /* optional DEVICE array of 4 counters, ADDED to by the call: particles live at the start,
+     * wall crossings, particles that hit max_iteration, particles with a non-zero status */
+    uint64_t *stats;
 } sdk_advect_params;
 
 /* Crossing log, replaces Particle.note_taking (seaduck/lagrangian.py:301).  Device pointers.
@@ -158,6 +161,24 @@ int64_t sdk_particles_bytes(int64_t n);
 int sdk_advect_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *host_p,
                     double t_stop, const sdk_advect_params *par, void *scratch, void *stream);
 
+
+/* Positions in, positions out, all HOST memory (pinned for full speed): what a user of
+ * `Particle(x=..,y=..,z=..,t=..).to_next_stop(t_stop)` followed by reading lon/lat/dep back gets
+ * (seaduck/lagrangian.py:93,741; seaduck/oceinterp.py:113-126).  Copies the inputs to the device,
+ * locates them (sdk_locate), reads the velocities (sdk_get_u_du), advects (sdk_advect) and copies
+ * the results back; synchronises.  Optional outputs may be NULL.  `scratch` is a device buffer of
+ * sdk_track_scratch_bytes(n) bytes; `ts_dev` the device array of model time levels (or NULL). */
+typedef struct sdk_track_io {
+    int64_t n;
+    const double *lon, *lat, *dep, *t;
+    double *out_lon, *out_lat, *out_dep;
+    int32_t *out_face, *out_iy, *out_ix, *out_izl;
+    int32_t *out_ncross, *out_status;
+} sdk_track_io;
+int64_t sdk_track_scratch_bytes(int64_t n);
+int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io,
+                   const double *ts_dev, int32_t n_t, double t_stop, const sdk_advect_params *par,
+                   void *scratch, void *stream);
 
 /* Output of sdk_locate: DEVICE pointers, n entries each (px, py: 4*n).  NULL members are skipped.
  * Mirrors the RelCoord families of the reference (seaduck/ocedata.py:119-143). */

@@ -87,6 +87,7 @@ class AdvectParams(C.Structure):
         ("refill_threshold", C.c_int32),
         ("blocks_per_sm", C.c_int32),
         ("threads_per_block", C.c_int32),
+        ("stats", vp),
     ]
 
 
@@ -110,6 +111,13 @@ LOCATED = (
 
 class Located(C.Structure):
     _fields_ = [(n, vp) for n in LOCATED]
+
+
+class TrackIO(C.Structure):
+    _fields_ = [("n", C.c_int64)] + [
+        (n, vp)
+        for n in "lon lat dep t out_lon out_lat out_dep out_face out_iy out_ix out_izl out_ncross out_status".split()
+    ]
 
 
 class SdkError(RuntimeError):
@@ -157,6 +165,9 @@ def lib():
         L.sdk_grid_build_locator.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, vp]
         L.sdk_locate.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, C.POINTER(Located), vp]
         L.sdk_time_index.argtypes = [vp, vp, C.c_int32, vp, C.c_int64, vp]
+        L.sdk_track_scratch_bytes.restype = C.c_int64
+        L.sdk_track_scratch_bytes.argtypes = [C.c_int64]
+        L.sdk_track_host.argtypes = [vp, C.POINTER(Velocity), C.POINTER(TrackIO), vp, C.c_int32, C.c_double, C.POINTER(AdvectParams), vp, vp]
         _lib = L
     return _lib
 

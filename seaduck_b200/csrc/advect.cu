@@ -366,6 +366,8 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
     Lane s;
     bool have = false, live = false;
     bool queue_empty = false;
+    // per-lane totals for the call statistics (reduced per warp at the end: a few thousand atomics)
+    unsigned acc_live = 0, acc_cross = 0, acc_max = 0, acc_flag = 0;
     for (;;) {
         // ---- refill idle lanes from the global queue (warp-aggregated)
         const unsigned idle = __ballot_sync(full, !have);
@@ -383,6 +385,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
                     if (LOG && a.log.emit_start) note(a, s, 15);
                     live = fabs(a.t_stop - s.t) > a.tol;
                     if (a.p.active && !a.p.active[pid]) live = false;
+                    acc_live += live;
                 }
             }
         }
@@ -398,8 +401,23 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
                 if (a.p.niter) a.p.niter[s.pid] = s.niter;
                 if (a.p.ncross) a.p.ncross[s.pid] = s.ncross;
                 if (LOG && a.log.count) a.log.count[s.pid] = s.nrec;
+                acc_cross += s.ncross;
+                acc_max += live;
+                acc_flag += s.status != 0;
                 have = false;
             }
+        }
+    }
+    if (a.stats) {
+        acc_live = __reduce_add_sync(full, acc_live);
+        acc_cross = __reduce_add_sync(full, acc_cross);
+        acc_max = __reduce_add_sync(full, acc_max);
+        acc_flag = __reduce_add_sync(full, acc_flag);
+        if (lane == 0) {
+            if (acc_live) atomicAdd(a.stats + 0, (unsigned long long)acc_live);
+            if (acc_cross) atomicAdd(a.stats + 1, (unsigned long long)acc_cross);
+            if (acc_max) atomicAdd(a.stats + 2, (unsigned long long)acc_max);
+            if (acc_flag) atomicAdd(a.stats + 3, (unsigned long long)acc_flag);
         }
     }
 }

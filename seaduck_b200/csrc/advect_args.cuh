@@ -15,6 +15,7 @@ struct AdvectArgs {
     double t_stop, tol, trim_tol;
     int max_iteration, kick_back, has_dep, has_log, commit, refill_threshold;
     unsigned long long *queue;  // work queue head
+    unsigned long long *stats;  // optional [4]: live at start, crossings, hit max_iteration, flagged
 };
 
 cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaStream_t stream);

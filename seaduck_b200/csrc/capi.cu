@@ -158,6 +158,7 @@ static int fill_args(const sdk_grid *grid, const sdk_velocity *vel, const sdk_pa
     int thr = par ? par->refill_threshold : 0;
     a.refill_threshold = thr > 0 ? (thr > 32 ? 32 : thr) : 8;
     a.queue = grid->queue;
+    a.stats = par ? (unsigned long long *)par->stats : nullptr;
     return SDK_OK;
 }
 
@@ -321,6 +322,76 @@ int sdk_advect_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_par
     }
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_advect_host: sync");
+    return SDK_OK;
+}
+
+// ---- positions in, positions out ------------------------------------------------------------------
+int64_t sdk_track_scratch_bytes(int64_t n) { return sdk_particles_bytes(n) + 8 * (int64_t)align256((size_t)n * 8); }
+
+int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev,
+                   int32_t n_t, double t_stop, const sdk_advect_params *par, void *scratch, void *stream_) {
+    if (!grid || !vel || !io || !scratch) return fail(SDK_EINVAL, "sdk_track_host: null argument");
+    if (!io->lon || !io->lat || !io->t || !io->out_lon || !io->out_lat)
+        return fail(SDK_EINVAL, "sdk_track_host: lon / lat / t and their outputs are required");
+    const int64_t n = io->n;
+    if (n <= 0) return n == 0 ? SDK_OK : fail(SDK_EINVAL, "sdk_track_host: negative count");
+    const int has_dep = par ? par->has_dep : 0;
+    if (has_dep && (!io->dep || !io->out_dep)) return fail(SDK_EINVAL, "sdk_track_host: depth arrays missing");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    // carve the device state out of the scratch buffer
+    sdk_particles dp;
+    std::memset(&dp, 0, sizeof dp);
+    dp.n = n;
+    char *cur = (char *)scratch;
+    for (const Field &f : kFields) {
+        if (f.offset == offsetof(sdk_particles, active)) continue;
+        void **ddst = (void **)((char *)&dp + f.offset);
+        *ddst = cur;
+        cur += align256((size_t)n * f.elem * f.mult);
+    }
+    cudaError_t e;
+#define H2D(dst, src) \
+    if ((e = cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyHostToDevice, stream)) != cudaSuccess) \
+        return cuda_fail(e, "sdk_track_host: H2D");
+    H2D(dp.lon, io->lon)
+    H2D(dp.lat, io->lat)
+    H2D(dp.t, io->t)
+    if (io->dep) H2D(dp.dep, io->dep)
+#undef H2D
+    // Position.from_latlon: indices + rel-coords straight into the particle state
+    sdk_located loc;
+    std::memset(&loc, 0, sizeof loc);
+    loc.face = grid->dev.has_face ? dp.face : nullptr;
+    loc.iy = dp.iy; loc.ix = dp.ix; loc.rx = dp.rx; loc.ry = dp.ry;
+    loc.px = dp.px; loc.py = dp.py; loc.dx = dp.dx; loc.dy = dp.dy;
+    loc.izl = dp.izl; loc.rzl = dp.rzl; loc.dzl = dp.dzl; loc.bzl = dp.bzl;
+    loc.it = dp.it;
+    loc.status = dp.status;
+    if (!(vel->has_time && ts_dev && n_t > 1)) {
+        if ((e = cudaMemsetAsync(dp.it, 0, (size_t)n * 4, stream)) != cudaSuccess) return cuda_fail(e, "memset");
+    }
+    int rc = sdk_locate(grid, n, dp.lon, dp.lat, (has_dep && grid->dev.n_zl > 1) ? dp.dep : nullptr,
+                        (vel->has_time && ts_dev && n_t > 1) ? dp.t : nullptr, ts_dev, n_t, &loc, stream);
+    if (rc) return rc;
+    // Particle.__init__: get_vol + get_u_du, then to_next_stop
+    rc = sdk_get_u_du(grid, vel, &dp, has_dep, stream);
+    if (rc) return rc;
+    rc = sdk_advect(grid, vel, &dp, t_stop, par, nullptr, 1, stream);
+    if (rc) return rc;
+#define D2H(dst, src, esz) \
+    if (dst && (e = cudaMemcpyAsync(dst, src, (size_t)n * esz, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) \
+        return cuda_fail(e, "sdk_track_host: D2H");
+    D2H(io->out_lon, dp.lon, 8)
+    D2H(io->out_lat, dp.lat, 8)
+    if (has_dep) D2H(io->out_dep, dp.dep, 8)
+    if (grid->dev.has_face) D2H(io->out_face, dp.face, 4)
+    D2H(io->out_iy, dp.iy, 4)
+    D2H(io->out_ix, dp.ix, 4)
+    if (has_dep) D2H(io->out_izl, dp.izl, 4)
+    D2H(io->out_ncross, dp.ncross, 4)
+    D2H(io->out_status, dp.status, 4)
+#undef D2H
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: sync");
     return SDK_OK;
 }
 

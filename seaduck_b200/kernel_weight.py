@@ -368,3 +368,8 @@ class KnW:
         vmode = {"nearest": 0, "linear": 1, "dz": 2}[self.vkernel]
         tmode = {"nearest": 0, "linear": 1, "dt": 2}[self.tkernel]
         return dict(kernel=self.kernel.astype(int), levels=levels, vmode=vmode, tmode=tmode, ignore_mask=bool(self.ignore_mask))
+
+
+def get_func(kernel, hkernel="interp", h_order=0, **kwargs):
+    """Weight function of a kernel (reference ``kernel_weight.py:608``; no caching needed here)."""
+    return _Stencil(np.asarray(kernel), hkernel, h_order)

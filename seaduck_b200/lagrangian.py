@@ -165,7 +165,8 @@ class Particle(Position):
         for name in ("status", "niter", "ncross"):
             st[name] = torch.zeros(n, dtype=torch.int32, device=dev)
         self.__dict__["_st"] = st
-        self.__dict__["_crossings"] = torch.zeros((), dtype=torch.int64, device=dev)
+        self.__dict__["_crossings"] = 0
+        self.__dict__["_stats"] = torch.zeros(4, dtype=torch.int64, device=dev)
         self.__dict__["_stale"] = set()
         self.__dict__["_raw"] = []
         if not od.readiness["h"] == "oceanparcel":
@@ -396,7 +397,15 @@ class Particle(Position):
         par.refill_threshold = int(tune.get("refill_threshold", 0))
         par.blocks_per_sm = int(tune.get("blocks_per_sm", 0))
         par.threads_per_block = int(tune.get("threads_per_block", 0))
+        par.stats = self._stats.data_ptr()
         return par
+
+    def _read_stats(self):
+        """(live at start, crossings, hit max_iteration, flagged) of the launches since the last
+        call -- one small device-to-host copy, the only synchronisation of a stop."""
+        vals = self._stats.cpu().numpy().astype(np.int64)
+        self._stats.zero_()
+        return vals
 
     def _launch(self, t_stop, max_iteration, active=None, emit_start=False):
         import torch  # noqa: PLC0415
@@ -408,31 +417,36 @@ class Particle(Position):
         stream = _lib.current_stream()
         if not self.save_raw:
             _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par), None, 1, stream), "sdk_advect")
-        else:
-            dev = self.ocedata._torch_device()
-            cnt = torch.zeros(self.N, dtype=torch.int32, device=dev)
-            lg = _lib.Log()
-            lg.count = cnt.data_ptr()
-            lg.emit_start = int(emit_start)
-            # pass 1: count the records of every particle without committing the state
-            _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par), C.byref(lg), 0, stream), "sdk_advect(count)")
-            offset = torch.zeros(self.N + 1, dtype=torch.int64, device=dev)
-            torch.cumsum(cnt, 0, out=offset[1:])
-            total = int(offset[-1].item())
-            rec = {k: torch.zeros(total, dtype=torch.int32, device=dev) for k in _lib.LOG_I32}
-            rec.update({k: torch.zeros(total, dtype=torch.float64, device=dev) for k in _lib.LOG_F64})
-            lg.capacity = total
-            lg.offset = offset.data_ptr()
-            for k, tns in rec.items():
-                setattr(lg, k, tns.data_ptr())
-            # pass 2: same trajectory, now writing the records
-            _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par), C.byref(lg), 1, stream), "sdk_advect(log)")
-            rec["offset"] = offset.cpu().numpy()
-            self._raw.append(rec)
-        self._crossings += self._st["ncross"].sum()
+            return
+        dev = self.ocedata._torch_device()
+        cnt = torch.zeros(self.N, dtype=torch.int32, device=dev)
+        lg = _lib.Log()
+        lg.count = cnt.data_ptr()
+        lg.emit_start = int(emit_start)
+        # pass 1: count the records of every particle without committing the state
+        par_count = self._params(max_iteration)
+        par_count.stats = None
+        _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par_count), C.byref(lg), 0, stream), "sdk_advect(count)")
+        offset = torch.zeros(self.N + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(cnt, 0, out=offset[1:])
+        total = int(offset[-1].item())
+        rec = {k: torch.zeros(total, dtype=torch.int32, device=dev) for k in _lib.LOG_I32}
+        rec.update({k: torch.zeros(total, dtype=torch.float64, device=dev) for k in _lib.LOG_F64})
+        lg.capacity = total
+        lg.offset = offset.data_ptr()
+        for k, tns in rec.items():
+            setattr(lg, k, tns.data_ptr())
+        # pass 2: same trajectory, now writing the records
+        _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par), C.byref(lg), 1, stream), "sdk_advect(log)")
+        rec["offset"] = offset.cpu().numpy()
+        self._raw.append(rec)
 
     def to_next_stop(self, t_stop):
-        """Integrate all particles to ``t_stop`` (reference ``lagrangian.py:741``)."""
+        """Integrate all particles to ``t_stop`` (reference ``lagrangian.py:741``).
+
+        One kernel launch, then one 32-byte read-back (how many particles were live, crossings,
+        who ran out of iterations) that also orders the host with the device.
+        """
         import torch  # noqa: PLC0415
 
         t_stop = float(t_stop)
@@ -440,16 +454,21 @@ class Particle(Position):
         st = self._st
         emit_start = bool(self.__dict__.get("_pending_start", False))
         self.__dict__["_pending_start"] = False
-        todo = (t_stop - st["t"]).abs() > tol
         if self.callback is None:
-            if not bool(todo.any().item()):
+            self._launch(t_stop, self.max_iteration, emit_start=emit_start)
+            n_live, n_cross, n_max, _ = self._read_stats()
+            self.__dict__["_crossings"] += int(n_cross)
+            if n_live == 0:
+                # the kernel touched nothing; like the reference, return before t := t_stop
+                if self.save_raw and self._raw and not emit_start:
+                    self._raw.pop()
                 logging.info("Nothing left to simulate")
                 return
-            self._launch(t_stop, self.max_iteration, emit_start=emit_start)
             self._mark_stale()
-            hit_max = bool((st["status"] & 1).any().item())
+            hit_max = n_max > 0
         else:
             # a host callback decides after every analytic step who keeps going
+            todo = (t_stop - st["t"]).abs() > tol
             alive = todo.cpu().numpy() & np.asarray(self.callback(self), bool)
             if not alive.any():
                 logging.info("Nothing left to simulate")
@@ -459,6 +478,7 @@ class Particle(Position):
             for i in range(self.max_iteration):
                 active = torch.as_tensor(alive.astype(np.int32)).to(dev)
                 self._launch(t_stop, 1, active=active, emit_start=emit_start and i == 0)
+                self.__dict__["_crossings"] += int(self._read_stats()[1])
                 self._mark_stale()
                 still = ((t_stop - st["t"]).abs() > tol).cpu().numpy()
                 idx = np.where(alive)[0]
@@ -484,14 +504,16 @@ class Particle(Position):
     @property
     def crossings(self):
         """Total number of cell-wall crossings so far (iterations that ended on a wall)."""
-        return int(self._crossings.item())
+        return int(self._crossings)
 
     def deepcopy(self):
         """Snapshot of the particles (reference ``lagrangian.py:725``): device-side clone."""
+        import torch  # noqa: PLC0415
+
         p = object.__new__(type(self))
         object.__setattr__(p, "rel", RelCoord())
         for key, item in self.__dict__.items():
-            if key in ("_st", "_stale", "_raw", "_crossings"):
+            if key in ("_st", "_stale", "_raw", "_crossings", "_stats"):
                 continue
             if isinstance(item, np.ndarray):
                 if item.ndim == 1:
@@ -505,7 +527,8 @@ class Particle(Position):
         p.__dict__["_st"] = {k: (None if v is None else v.clone()) for k, v in self._st.items()}
         p.__dict__["_stale"] = set(self._stale)
         p.__dict__["_raw"] = list(self._raw)
-        p.__dict__["_crossings"] = self._crossings.clone()
+        p.__dict__["_crossings"] = self._crossings
+        p.__dict__["_stats"] = torch.zeros_like(self._stats)
         p.__dict__["_derived_ok"] = False
         return p
 

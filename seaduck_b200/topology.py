@@ -444,7 +444,37 @@ class Topology:
                 face = np.where(changed, cur[0], face)
         return cur, status
 
+    # reference-compatible scalar faces of the vectorised routines ---------------------------------
     def _find_wall_between(self, ind1, ind2):
+        """``("U"|"V", index)`` of the wall between two adjacent cells (ref. topology.py:569)."""
+        self._need_faces()
+        a = tuple(np.array([int(i)]) for i in ind1)
+        b = tuple(np.array([int(i)]) for i in ind2)
+        out, is_v, st = self._wall_between_vec(a, b)
+        if st[0] == EDGE:
+            raise IndexError(f"there is no wall between a cell and itself,{ind1},{ind2}")
+        if st[0] == ABNORMAL:
+            raise ValueError(f"The two face connecting the indexes {ind1},{ind2} are not connected in a normal way")
+        return ("V" if is_v[0] else "U"), tuple(int(o[0]) for o in out)
+
+    def _ind_tend_U(self, ind, tend):
+        out, is_v, st = self._umove(tuple(np.array([int(i)]) for i in ind), np.array([int(tend)]))
+        self._raise(st[0], ind)
+        return ("V" if is_v[0] else "U"), tuple(int(o[0]) for o in out)
+
+    def _ind_tend_V(self, ind, tend):
+        out, is_v, st = self._vmove(tuple(np.array([int(i)]) for i in ind), np.array([int(tend)]))
+        self._raise(st[0], ind)
+        return ("V" if is_v[0] else "U"), tuple(int(o[0]) for o in out)
+
+    def _ind_tend_G(self, ind, tend):
+        if tend not in (0, 1, 2, 3):
+            raise ValueError(f"tend {tend} not supported")
+        out, st = self._gmove(tuple(np.array([int(i)]) for i in ind), np.array([int(tend)]))
+        self._raise(st[0], ind)
+        return tuple(int(o[0]) for o in out)
+
+    def _wall_between_vec(self, ind1, ind2):
         """Vectorised wall lookup between adjacent cells (ref. topology.py:569).
 
         Returns ``(index, is_v, status)``; ``is_v`` tells whether the wall is a V wall.
@@ -494,7 +524,7 @@ class Topology:
         alter, st_a = self._walk_pair(sub, 2, tend[go])
         f_sub = tuple(a[go] for a in first)
         equal = (alter[0] == f_sub[0]) & (alter[1] == f_sub[1]) & (alter[2] == f_sub[2]) & (st_a == OK)
-        wall, wv, st_w = self._find_wall_between(f_sub, alter)
+        wall, wv, st_w = self._wall_between_vec(f_sub, alter)
         st_w = np.where(st_a != OK, st_a, st_w)
         out = tuple(np.where(equal, a, w) for a, w in zip(alter, wall))
         out_v = np.where(equal, False, wv)
@@ -518,7 +548,7 @@ class Topology:
         sub = tuple(a[go] for a in ind)
         alter, st_a = self._walk_pair(sub, 1, tend[go])
         f_sub = tuple(a[go] for a in first)
-        wall, wv, st_w = self._find_wall_between(f_sub, alter)
+        wall, wv, st_w = self._wall_between_vec(f_sub, alter)
         st_w = np.where(st_a != OK, st_a, st_w)
         res = tuple(a.copy() for a in first)
         for k in range(3):

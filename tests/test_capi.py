@@ -1,0 +1,55 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/*.h declares."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+from seaduck_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "seaduck_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdk_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    if not os.path.exists(_lib.SO_PATH):
+        _lib.build()
+    lib = ctypes.CDLL(_lib.SO_PATH)
+    names = declared_functions()
+    assert len(names) >= 12
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/seaduck_b200.h but not exported"
+
+
+def test_abi_version_and_error_path_without_gpu():
+    L = _lib.lib()
+    assert L.sdk_abi_version() == 1
+    out = ctypes.c_void_p()
+    rc = L.sdk_grid_create(None, ctypes.byref(out))
+    assert rc == -1  # SDK_EINVAL, no CUDA call was needed to find that out
+    assert b"null" in L.sdk_last_error()
+    assert L.sdk_particles_bytes(1000) > 1000 * 200
+
+
+def test_struct_sizes_match_header():
+    # 64-bit pointers, 4-byte ints: the ctypes mirrors must have the size the C compiler gives
+    assert ctypes.sizeof(_lib.GridDesc) == 12 * 4 + 15 * 8
+    assert ctypes.sizeof(_lib.Velocity) == 4 * 8 + 16 * 4
+    assert ctypes.sizeof(_lib.Particles) == 8 + 29 * 8
+    assert ctypes.sizeof(_lib.AdvectParams) == 2 * 8 + 6 * 4 + 8
+    assert ctypes.sizeof(_lib.Log) == 8 + 2 * 8 + 19 * 8 + 8
+    assert ctypes.sizeof(_lib.Located) == 30 * 8
+    assert ctypes.sizeof(_lib.TrackIO) == 8 + 13 * 8
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "SO_PATH", "/nonexistent/libseaduck_b200.so")
+    with pytest.raises(_lib.SdkError):
+        _lib.lib()
