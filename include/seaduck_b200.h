@@ -206,6 +206,71 @@ int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span
 int sdk_locate(const sdk_grid *grid, int64_t n, const double *lon, const double *lat, const double *dep,
                const double *t, const double *ts, int32_t n_t, const sdk_located *out, void *stream);
 
+/* ---- masked kernel-weight interpolation (Position.interpolate, seaduck/eulerian.py:1268) ---------- */
+#define SDK_MAX_NODES 32
+#define SDK_MAX_LEVELS 8
+#define SDK_MAX_AXIS 9
+enum { SDK_KIND_CROSS_INTERP = 0, SDK_KIND_LINE_X = 1, SDK_KIND_LINE_Y = 2, SDK_KIND_RECT = 3 };
+enum { SDK_MODE_NEAREST = 0, SDK_MODE_LINEAR = 1, SDK_MODE_DERIV = 2 };
+
+/* One level of a KnW inheritance (seaduck/kernel_weight.py:645): which nodes it uses and the 1-D
+ * node sets of its Lagrange weights (kernel_weight_x :84, kernel_weight_s :313). */
+typedef struct sdk_kernel_level {
+    uint32_t node_mask;
+    int32_t kind, nxs, nys, xorder, yorder;
+    int8_t xs[SDK_MAX_AXIS + 3], ys[SDK_MAX_AXIS + 3];
+} sdk_kernel_level;
+
+/* A KnW: horizontal nodes, inheritance levels, vertical / temporal mode.  `rim` is the DEVICE table
+ * of neighbour indices for the cells whose stencil leaves the (per face) array: for every rim cell
+ * (slot order documented in seaduck_b200/interp.py) and node, (face<<28 | iy<<14 | ix) or -1 where
+ * the reference raises; `rim_code` (vectors only) bit0 = value comes from the OTHER component,
+ * bit1 = negative sign (four_matrix_for_uv, seaduck/topology.py:689). */
+typedef struct sdk_kernel_desc {
+    int32_t n_nodes, n_levels, vmode, tmode, ignore_mask, bottom_no_flux;
+    int32_t reach;     /* max(|dx|, |dy|): cells closer than this to a face edge use `rim` */
+    int32_t rim_dense; /* 1: `rim` covers every cell (tiny grids), slot = iy*nx + ix */
+    int8_t dx[SDK_MAX_NODES], dy[SDK_MAX_NODES];
+    sdk_kernel_level level[SDK_MAX_LEVELS];
+    const int32_t *rim;
+    const uint8_t *rim_code;
+} sdk_kernel_desc;
+
+/* A gridded variable on the device: data [t][z][face][ny][nx] (axes of size 1 when absent) and the
+ * wet mask that goes with its grid position (uint8, [mask_nz][face][mask_ny][mask_nx], or NULL). */
+typedef struct sdk_field {
+    const void *data;
+    int32_t dtype, has_time, nt, it0, has_z, nz, ny, nx, xstag, ystag;
+    const uint8_t *mask;
+    int32_t mask_nz, mask_ny, mask_nx, reserved;
+} sdk_field;
+
+/* Points: indices and rel-coords (DEVICE pointers).  kz/rz and kt/rt are the vertical / temporal
+ * index and rel-coordinate that match the variable's grid and the kernel's mode (iz|iz_lin|izl|
+ * izl_lin, it|it_lin); the second vertical node is kz-1, the second time node kt+1. */
+typedef struct sdk_points {
+    int64_t n;
+    const int32_t *face, *iy, *ix;
+    const double *rx, *ry;
+    const int32_t *kz;
+    const double *rz;
+    const int32_t *kt;
+    const double *rt;
+    const float *cs, *sn;
+} sdk_points;
+
+/* scalar variable */
+int sdk_interp_scalar(const sdk_grid *grid, const sdk_points *pts, const sdk_field *field,
+                      const sdk_kernel_desc *knw, double *out, void *stream);
+/* horizontal vector on a grid with faces (components may swap / change sign across faces);
+ * vec_transform != 0 rotates the result to east/north with cs, sn (utils.py:206). */
+int sdk_interp_vector(const sdk_grid *grid, const sdk_points *pts, const sdk_field *fu, const sdk_field *fv,
+                      const sdk_kernel_desc *ku, const sdk_kernel_desc *kv, int vec_transform, double *out_u,
+                      double *out_v, void *stream);
+/* maskU / maskV / maskWvel from maskC (seaduck/get_masks.py:12,46,79), all [nz][face][ny][nx] uint8 */
+int sdk_build_masks(const sdk_grid *grid, const uint8_t *maskC, int32_t nz, uint8_t *maskU, uint8_t *maskV,
+                    uint8_t *maskW, void *stream);
+
 /* it := 0 before time_midp[0], else find_rel(t, time_midp) + 1 (seaduck/lagrangian.py:796-802). */
 int sdk_time_index(const double *t, const double *time_midp, int32_t n_midp, int32_t *it, int64_t n,
                    void *stream);

@@ -9,6 +9,7 @@
 #include <string>
 
 #include "advect_args.cuh"
+#include "interp_args.cuh"
 #include "locate_args.cuh"
 
 namespace {
@@ -322,6 +323,77 @@ int sdk_advect_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_par
     }
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_advect_host: sync");
+    return SDK_OK;
+}
+
+// ---- interpolation ----------------------------------------------------------------------------------
+static int check_interp(const sdk_grid *grid, const sdk_points *pts, const sdk_field *f, const sdk_kernel_desc *k) {
+    if (!grid || !pts || !f || !k) return fail(SDK_EINVAL, "sdk_interp: null argument");
+    if (pts->n < 0) return fail(SDK_EINVAL, "sdk_interp: negative count");
+    if (pts->n > 0 && (!pts->iy || !pts->ix || !pts->rx || !pts->ry)) return fail(SDK_EINVAL, "sdk_interp: point arrays missing");
+    if (grid->dev.has_face && pts->n > 0 && !pts->face) return fail(SDK_EINVAL, "sdk_interp: face array missing");
+    if (!f->data) return fail(SDK_EINVAL, "sdk_interp: field data missing");
+    if (k->n_nodes < 1 || k->n_nodes > SDK_MAX_NODES || k->n_levels < 1 || k->n_levels > SDK_MAX_LEVELS)
+        return fail(SDK_EINVAL, "sdk_interp: kernel too large");
+    if (k->reach > 0 && !k->rim) return fail(SDK_EINVAL, "sdk_interp: rim table missing");
+    if (grid->dev.ny > 16383 || grid->dev.nx > 16383) return fail(SDK_EUNSUPPORTED, "sdk_interp: faces larger than 16383");
+    if (f->has_z && k->vmode != SDK_MODE_NEAREST && !pts->rz && k->vmode == SDK_MODE_LINEAR)
+        return fail(SDK_EINVAL, "sdk_interp: rz missing");
+    if (f->has_z && !pts->kz) return fail(SDK_EINVAL, "sdk_interp: vertical index missing");
+    if (f->has_time && !pts->kt) return fail(SDK_EINVAL, "sdk_interp: time index missing");
+    if (k->tmode == SDK_MODE_LINEAR && !pts->rt) return fail(SDK_EINVAL, "sdk_interp: rt missing");
+    return SDK_OK;
+}
+
+int sdk_interp_scalar(const sdk_grid *grid, const sdk_points *pts, const sdk_field *field,
+                      const sdk_kernel_desc *knw, double *out, void *stream) {
+    int rc = check_interp(grid, pts, field, knw);
+    if (rc) return rc;
+    if (!out) return fail(SDK_EINVAL, "sdk_interp_scalar: output missing");
+    sdk::InterpArgs a;
+    a.g = grid->dev;
+    a.pts = *pts;
+    a.fu = *field;
+    a.fv = *field;
+    a.ku = *knw;
+    a.kv = *knw;
+    a.vec_transform = 0;
+    a.out_u = out;
+    a.out_v = nullptr;
+    cudaError_t e = sdk::launch_interp(a, false, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_interp_scalar: launch");
+    return SDK_OK;
+}
+
+int sdk_interp_vector(const sdk_grid *grid, const sdk_points *pts, const sdk_field *fu, const sdk_field *fv,
+                      const sdk_kernel_desc *ku, const sdk_kernel_desc *kv, int vec_transform, double *out_u,
+                      double *out_v, void *stream) {
+    int rc = check_interp(grid, pts, fu, ku);
+    if (rc) return rc;
+    rc = check_interp(grid, pts, fv, kv);
+    if (rc) return rc;
+    if (!out_u || !out_v) return fail(SDK_EINVAL, "sdk_interp_vector: output missing");
+    if (vec_transform && pts->n > 0 && (!pts->cs || !pts->sn)) return fail(SDK_EINVAL, "sdk_interp_vector: cs / sn missing");
+    sdk::InterpArgs a;
+    a.g = grid->dev;
+    a.pts = *pts;
+    a.fu = *fu;
+    a.fv = *fv;
+    a.ku = *ku;
+    a.kv = *kv;
+    a.vec_transform = vec_transform;
+    a.out_u = out_u;
+    a.out_v = out_v;
+    cudaError_t e = sdk::launch_interp(a, true, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_interp_vector: launch");
+    return SDK_OK;
+}
+
+int sdk_build_masks(const sdk_grid *grid, const uint8_t *maskC, int32_t nz, uint8_t *maskU, uint8_t *maskV,
+                    uint8_t *maskW, void *stream) {
+    if (!grid || !maskC || !maskU || !maskV || !maskW || nz < 1) return fail(SDK_EINVAL, "sdk_build_masks: bad argument");
+    cudaError_t e = sdk::launch_build_masks(grid->dev, maskC, nz, maskU, maskV, maskW, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_build_masks: launch");
     return SDK_OK;
 }
 

@@ -1,0 +1,288 @@
+// K3: masked kernel-weight interpolation at points, K4: wall masks from the centre mask.
+//
+// Replaces Position.interpolate (reference seaduck/eulerian.py:1268) and the stages it is made of:
+// index "fattening" (_fatten_h :386, fatten :520), vector component swaps across faces
+// (_transform_vector_and_register :887, topology.py:689), the gathers (_read_data_and_register
+// :1064), the mask lookup (_mask_value_and_register :959, get_masks.py:169), the choice of the
+// largest all-wet stencil and its Lagrange weights (kernel_weight.py:481-584, :84-428, KnW.get_weight
+// :772) and the final dot product -- fused: one thread per point, nothing materialised.
+//
+// Neighbour indices: naive offsets inside a face; cells closer than `reach` to a face edge read a
+// host-built "rim" table, so the device never walks the topology here.
+#include <cuda_runtime.h>
+
+#include "interp_args.cuh"
+
+namespace sdk {
+
+__device__ __forceinline__ int rim_slot(int ny, int nx, int r, int dense, int iy, int ix) {
+    if (dense) return iy * nx + ix;
+    if (iy >= ny - r) return (iy - (ny - r)) * nx + ix;
+    if (iy < r) return r * nx + iy * nx + ix;
+    if (ix < r) return 2 * r * nx + (iy - r) * r + ix;
+    if (ix >= nx - r) return 2 * r * nx + (ny - 2 * r) * r + (iy - r) * r + (ix - (nx - r));
+    return -1;
+}
+
+// weight of node `target` among the 1-D nodes for the `order`-th derivative
+// (reference kernel_weight.py:84-306: sum over subsets of the other nodes / product of differences)
+__device__ __forceinline__ double axis_weight(const int8_t *nodes, int nn, int target, double r, int order) {
+    double denom = 1.0;
+    double e[SDK_MAX_AXIS + 1];
+    const int k = nn - 1 - order;  // size of the subsets
+    if (k == 0) {
+        double f = 1.0;
+        for (int i = 2; i <= order - 1; ++i) f *= i;
+        for (int j = 0; j < nn; ++j)
+            if (nodes[j] != target) denom *= (double)(target - nodes[j]);
+        return f / denom;
+    }
+    e[0] = 1.0;
+    for (int j = 1; j <= k; ++j) e[j] = 0.0;
+    for (int j = 0; j < nn; ++j) {
+        if (nodes[j] == target) continue;
+        denom *= (double)(target - nodes[j]);
+        const double v = r - (double)nodes[j];
+        for (int q = k; q >= 1; --q) e[q] += e[q - 1] * v;  // elementary symmetric polynomials
+    }
+    return e[k] / denom;
+}
+
+__device__ __forceinline__ void level_weights(const sdk_kernel_desc &K, const sdk_kernel_level &L, double rx,
+                                              double ry, double *w) {
+    for (int m = 0; m < K.n_nodes; ++m) {
+        double v = 0.0;
+        if (L.node_mask >> m & 1u) {
+            const int x = K.dx[m], y = K.dy[m];
+            if (L.kind == SDK_KIND_CROSS_INTERP) {
+                if (x != 0) v = axis_weight(L.xs, L.nxs, x, rx, 0);
+                else if (y != 0) v = axis_weight(L.ys, L.nys, y, ry, 0);
+                else v = axis_weight(L.xs, L.nxs, 0, rx, 0) + axis_weight(L.ys, L.nys, 0, ry, 0) - 1;
+            } else if (L.kind == SDK_KIND_LINE_X) {
+                if (y == 0) v = axis_weight(L.xs, L.nxs, x, rx, L.xorder);
+            } else if (L.kind == SDK_KIND_LINE_Y) {
+                if (x == 0) v = axis_weight(L.ys, L.nys, y, ry, L.yorder);
+            } else {
+                v = axis_weight(L.xs, L.nxs, x, rx, L.xorder) * axis_weight(L.ys, L.nys, y, ry, L.yorder);
+            }
+        }
+        w[m] = v;
+    }
+}
+
+struct NodeSet {
+    int32_t packed[SDK_MAX_NODES];  // face<<28 | iy<<14 | ix, or -1
+    uint8_t code[SDK_MAX_NODES];    // bit0 other component, bit1 negative
+};
+
+__device__ __forceinline__ int find_nodes(const GridDev &g, const sdk_kernel_desc &K, int f, int iy, int ix,
+                                          NodeSet &ns) {
+    const int slot = rim_slot(g.ny, g.nx, K.reach, K.rim_dense, iy, ix);
+    int bad = 0;
+    if (slot < 0 || K.rim == nullptr) {
+        for (int m = 0; m < K.n_nodes; ++m) {
+            ns.packed[m] = (f << 28) | ((iy + K.dy[m]) << 14) | (ix + K.dx[m]);
+            ns.code[m] = 0;
+        }
+        return 0;
+    }
+    const int per_face = K.rim_dense ? g.ny * g.nx : 2 * K.reach * g.nx + 2 * K.reach * (g.ny - 2 * K.reach);
+    const int64_t base = ((int64_t)f * per_face + slot) * K.n_nodes;
+    for (int m = 0; m < K.n_nodes; ++m) {
+        ns.packed[m] = __ldg(K.rim + base + m);
+        ns.code[m] = K.rim_code ? __ldg(K.rim_code + base + m) : 0;
+        bad |= ns.packed[m] < 0;
+    }
+    return bad;
+}
+
+__device__ __forceinline__ int64_t plane_index(int packed, int fny, int fnx) {
+    const int f = packed >> 28 & 0xf, y = packed >> 14 & 0x3fff, x = packed & 0x3fff;
+    return ((int64_t)f * fny + y) * fnx + x;
+}
+
+__device__ __forceinline__ double field_value(const GridDev &g, const sdk_field &F, int packed, int kz, int kt) {
+    int64_t lev = 0;
+    if (F.has_time) lev = wrap_index(kt - F.it0, F.nt);
+    if (F.has_z) lev = lev * F.nz + wrap_index(kz, F.nz);
+    const int64_t idx = lev * ((int64_t)g.nface * F.ny * F.nx) + plane_index(packed, F.ny, F.nx);
+    const double v = F.dtype == SDK_F64 ? ldf<double>(F.data, idx) : ldf<float>(F.data, idx);
+    return nan_to_num(v);
+}
+
+__device__ __forceinline__ bool is_wet(const GridDev &g, const sdk_field &F, int packed, int kz) {
+    if (packed < 0) return false;
+    int z = F.has_z ? kz : 0;
+    if (z < 0) z += F.mask_nz;
+    if (z < 0 || z >= F.mask_nz) return false;
+    const int y = packed >> 14 & 0x3fff, x = packed & 0x3fff;
+    if (y >= F.mask_ny || x >= F.mask_nx) return false;
+    const int64_t idx = (int64_t)z * ((int64_t)g.nface * F.mask_ny * F.mask_nx) + plane_index(packed, F.mask_ny, F.mask_nx);
+    return __ldg(F.mask + idx) != 0;
+}
+
+// One interpolated value.  P = field of the kernel's own component, O = the other component
+// (vectors on multi-face grids), both may be the same.
+__device__ double interp_value(const GridDev &g, const sdk_kernel_desc &K, const sdk_field &P, const sdk_field &O,
+                               const NodeSet &ns, double rxs, double rys, int kz0, double rz, int kt0, double rt) {
+    const int nz = K.vmode == SDK_MODE_NEAREST ? 1 : 2;
+    const int nt = K.tmode == SDK_MODE_NEAREST ? 1 : 2;
+    const bool use_mask = !K.ignore_mask && P.mask != nullptr;
+    double w[SDK_MAX_NODES];
+    int cached_level = -2;
+    double total = 0.0;
+    for (int jt = 0; jt < nt; ++jt) {
+        const int kt = kt0 + jt;
+        const double tw = K.tmode == SDK_MODE_LINEAR ? (jt == 0 ? 1 - rt : rt) : (K.tmode == SDK_MODE_DERIV ? (jt == 0 ? -1.0 : 1.0) : 1.0);
+        double zsum[2] = {0.0, 0.0};
+        bool znan[2] = {false, false};
+        for (int jz = 0; jz < nz; ++jz) {
+            const int kz = kz0 - jz;
+            // which stencil fits the wet nodes (reference find_which_points_for_each_kernel :481)
+            int level = 0;
+            if (use_mask) {
+                unsigned wet = 0;
+                for (int m = 0; m < K.n_nodes; ++m) {
+                    const sdk_field &M = (ns.code[m] & 1) ? O : P;
+                    if (is_wet(g, M, ns.packed[m], kz)) wet |= 1u << m;
+                }
+                level = -1;
+                for (int l = 0; l < K.n_levels; ++l)
+                    if ((wet & K.level[l].node_mask) == K.level[l].node_mask) {
+                        level = l;
+                        break;
+                    }
+            }
+            if (level < 0) {
+                znan[jz] = true;  // weight[:, 0] = nan (reference :557-558)
+                continue;
+            }
+            if (level != cached_level) {
+                level_weights(K, K.level[level], rxs, rys, w);
+                cached_level = level;
+            }
+            double acc = 0.0;
+            for (int m = 0; m < K.n_nodes; ++m) {
+                if (!(K.level[level].node_mask >> m & 1u)) continue;
+                if (ns.packed[m] < 0) {
+                    acc = NAN;
+                    continue;
+                }
+                const sdk_field &S = (ns.code[m] & 1) ? O : P;
+                double v = field_value(g, S, ns.packed[m], kz, kt);
+                if (ns.code[m] & 2) v = -v;
+                acc += v * w[m];
+            }
+            zsum[jz] = acc;
+        }
+        double zw0 = 1.0, zw1 = 0.0;
+        if (K.vmode == SDK_MODE_LINEAR) {
+            zw0 = 1 - rz;
+            zw1 = rz;
+            if (K.bottom_no_flux && znan[0]) {
+                // ghost point below the bottom (reference kernel_weight.py:860-869)
+                znan[0] = false;
+                zsum[0] = 0.0;
+                if (rz < 0.5) {
+                    zsum[1] = 0.0;
+                    znan[1] = false;
+                }
+                zw1 = 1.0;
+            }
+        } else if (K.vmode == SDK_MODE_DERIV) {
+            zw0 = -1.0;
+            zw1 = 1.0;
+        }
+        double part = znan[0] ? NAN : zsum[0] * zw0;
+        if (nz == 2) part += znan[1] ? NAN : zsum[1] * zw1;
+        total += part * tw;
+    }
+    return total;
+}
+
+__global__ void __launch_bounds__(128) interp_scalar_kernel(const __grid_constant__ InterpArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.pts.n) return;
+    const sdk_points &p = a.pts;
+    const int f = p.face ? p.face[i] : 0, iy = p.iy[i], ix = p.ix[i];
+    NodeSet ns;
+    find_nodes(a.g, a.ku, f, iy, ix, ns);
+    const double rxs = a.fu.xstag ? p.rx[i] + 0.5 : p.rx[i];
+    const double rys = a.fu.ystag ? p.ry[i] + 0.5 : p.ry[i];
+    a.out_u[i] = interp_value(a.g, a.ku, a.fu, a.fu, ns, rxs, rys, p.kz ? p.kz[i] : 0, p.rz ? p.rz[i] : 0.0,
+                              p.kt ? p.kt[i] : 0, p.rt ? p.rt[i] : 0.0);
+}
+
+__global__ void __launch_bounds__(128) interp_vector_kernel(const __grid_constant__ InterpArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.pts.n) return;
+    const sdk_points &p = a.pts;
+    const int f = p.face ? p.face[i] : 0, iy = p.iy[i], ix = p.ix[i];
+    const int kz = p.kz ? p.kz[i] : 0, kt = p.kt ? p.kt[i] : 0;
+    const double rz = p.rz ? p.rz[i] : 0.0, rt = p.rt ? p.rt[i] : 0.0;
+    NodeSet ns;
+    find_nodes(a.g, a.ku, f, iy, ix, ns);
+    double u = interp_value(a.g, a.ku, a.fu, a.fv, ns, p.rx[i] + 0.5, p.ry[i], kz, rz, kt, rt);
+    find_nodes(a.g, a.kv, f, iy, ix, ns);
+    double v = interp_value(a.g, a.kv, a.fv, a.fu, ns, p.rx[i], p.ry[i] + 0.5, kz, rz, kt, rt);
+    if (a.vec_transform) {
+        const double cs = (double)p.cs[i], sn = (double)p.sn[i];
+        const double uu = u * cs - v * sn, vv = u * sn + v * cs;
+        u = uu;
+        v = vv;
+    }
+    a.out_u[i] = u;
+    a.out_v[i] = v;
+}
+
+// K4: a dry cell's west / south wall is wet when the cell on the other side is wet; a W point is
+// wet when the cell below or above it is (reference get_masks.py:12,46,79).
+__global__ void build_masks_kernel(GridDev g, const uint8_t *maskC, int nz, uint8_t *maskU, uint8_t *maskV,
+                                   uint8_t *maskW) {
+    const int64_t plane = (int64_t)g.nface * g.ny * g.nx;
+    const int64_t total = plane * nz;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += (int64_t)gridDim.x * blockDim.x) {
+        const int z = (int)(c / plane);
+        const int64_t h = c - (int64_t)z * plane;
+        const int f = (int)(h / (g.ny * g.nx));
+        const int rem = (int)(h - (int64_t)f * g.ny * g.nx);
+        const int iy = rem / g.nx, ix = rem - iy * g.nx;
+        const uint8_t self = maskC[c] != 0;
+        uint8_t mu = self, mv = self;
+        if (!self) {
+            for (int dir = 2; dir >= 1; --dir) {  // 2: left neighbour -> U, 1: lower neighbour -> V
+                int nf = f, ny = iy, nx = ix, came;
+                const int st = cell_move(g, dir, nf, ny, nx, came);
+                uint8_t other = 0;
+                if (st == 0) other = maskC[(int64_t)z * plane + ((int64_t)nf * g.ny + ny) * g.nx + nx] != 0;
+                else if (st & SDK_ST_OUT) other = maskC[(int64_t)z * plane + plane - 1] != 0;  // numpy index -1,-1
+                if (dir == 2) mu = other;
+                else mv = other;
+            }
+        }
+        maskU[c] = mu;
+        maskV[c] = mv;
+        maskW[c] = self || (z > 0 && maskC[c - plane] != 0);
+    }
+}
+
+cudaError_t launch_interp(const InterpArgs &a, bool vector, cudaStream_t s) {
+    if (a.pts.n == 0) return cudaSuccess;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((a.pts.n + threads - 1) / threads);
+    if (vector) interp_vector_kernel<<<blocks, threads, 0, s>>>(a);
+    else interp_scalar_kernel<<<blocks, threads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_build_masks(const GridDev &g, const uint8_t *maskC, int nz, uint8_t *mu, uint8_t *mv, uint8_t *mw,
+                               cudaStream_t s) {
+    const int64_t total = (int64_t)g.nface * g.ny * g.nx * nz;
+    if (total == 0) return cudaSuccess;
+    int64_t blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    build_masks_kernel<<<(unsigned)blocks, 256, 0, s>>>(g, maskC, nz, mu, mv, mw);
+    return cudaGetLastError();
+}
+
+}  // namespace sdk
