@@ -38,7 +38,11 @@ enum {
     SDK_ST_MAX_ITER = 1,   /* still live after max_iteration steps (reference warns, lagrangian.py:794) */
     SDK_ST_EDGE = 2,       /* tried to leave through an edge without neighbour ("Some points are on the edge") */
     SDK_ST_BAD_CELL = 4,   /* cell whose walls/corners the reference cannot index (it raises there) */
-    SDK_ST_OUT = 8         /* left a closed (box) domain; particle frozen */
+    SDK_ST_OUT = 8,        /* left a closed (box) domain; particle frozen */
+    /* sdk_locate: value outside the table, the reference raises "Value out of bound." (utils.py:301) */
+    SDK_ST_OOB = 16,       /* depth below the last Zl level (linear Zl lookup) */
+    SDK_ST_OOB_Z = 32,     /* depth below the last Z level (linear Z lookup, lazily used by interpolation) */
+    SDK_ST_OOB_T = 64      /* time before the first level (linear time lookup, lazily used) */
 };
 
 #define SDK_MAX_FACES 16
@@ -191,7 +195,9 @@ typedef struct sdk_located {
     int32_t *izl_near; double *rzl_near, *dzl_near, *bzl_near; /* nearest Zl   (_find_rel_vl)     */
     int32_t *izl;      double *rzl, *dzl, *bzl;              /* linear Zl      (_find_rel_vl_lin) */
     int32_t *it;       double *rt, *dt, *bt;                 /* nearest time   (_find_rel_t)      */
-    int32_t *status;
+    int32_t *iz_lin;   double *rz_lin, *dz_lin, *bz_lin;     /* linear Z       (_find_rel_v_lin)  */
+    int32_t *it_lin;   double *rt_lin, *dt_lin, *bt_lin;     /* linear time    (_find_rel_t_lin)  */
+    int32_t *status;   /* SDK_ST_BAD_CELL, SDK_ST_OOB* */
 } sdk_located;
 
 /* Build the lat/lon bucket grid used by sdk_locate (replaces create_tree, seaduck/utils.py:225).
@@ -210,6 +216,10 @@ int sdk_locate(const sdk_grid *grid, int64_t n, const double *lon, const double 
 #define SDK_MAX_NODES 32
 #define SDK_MAX_LEVELS 8
 #define SDK_MAX_AXIS 9
+/* neighbour index of a stencil node in the `rim` tables: 5 bits face, 13 bits iy, 13 bits ix */
+#define SDK_PACK(f, iy, ix) (((f) << 26) | ((iy) << 13) | (ix))
+#define SDK_NODE_RAISES (-1) /* the reference raises for this node (no such neighbour): result NaN */
+#define SDK_NODE_LAST (-2)   /* the reference indexes [-1, -1] (stepped out of a closed box) */
 enum { SDK_KIND_CROSS_INTERP = 0, SDK_KIND_LINE_X = 1, SDK_KIND_LINE_Y = 2, SDK_KIND_RECT = 3 };
 enum { SDK_MODE_NEAREST = 0, SDK_MODE_LINEAR = 1, SDK_MODE_DERIV = 2 };
 
@@ -223,8 +233,7 @@ typedef struct sdk_kernel_level {
 
 /* A KnW: horizontal nodes, inheritance levels, vertical / temporal mode.  `rim` is the DEVICE table
  * of neighbour indices for the cells whose stencil leaves the (per face) array: for every rim cell
- * (slot order documented in seaduck_b200/interp.py) and node, (face<<28 | iy<<14 | ix) or -1 where
- * the reference raises; `rim_code` (vectors only) bit0 = value comes from the OTHER component,
+ * (slot order documented in seaduck_b200/interp.py) and node, SDK_PACK(face, iy, ix) or SDK_NODE_*; `rim_code` (vectors only) bit0 = value comes from the OTHER component,
  * bit1 = negative sign (four_matrix_for_uv, seaduck/topology.py:689). */
 typedef struct sdk_kernel_desc {
     int32_t n_nodes, n_levels, vmode, tmode, ignore_mask, bottom_no_flux;

@@ -105,7 +105,7 @@ class Log(C.Structure):
 
 LOCATED = (
     "face iy ix rx ry cs sn dx dy bx by px py iz rz dz bz izl_near rzl_near dzl_near bzl_near "
-    "izl rzl dzl bzl it rt dt bt status"
+    "izl rzl dzl bzl it rt dt bt iz_lin rz_lin dz_lin bz_lin it_lin rt_lin dt_lin bt_lin status"
 ).split()
 
 

@@ -236,9 +236,12 @@ int sdk_locate(const sdk_grid *grid, int64_t n, const double *lon, const double 
         if (!grid->has_buckets) return fail(SDK_EINVAL, "sdk_locate: call sdk_grid_build_locator first");
         if (!out->iy || !out->ix || !out->rx || !out->ry) return fail(SDK_EINVAL, "sdk_locate: output arrays missing");
     }
-    if (dep && grid->dev.n_zl > 1 && (!out->izl || !out->rzl || !out->dzl || !out->bzl))
-        return fail(SDK_EINVAL, "sdk_locate: vertical output arrays missing");
-    if (t && ts && n_t > 1 && !out->it) return fail(SDK_EINVAL, "sdk_locate: time index output missing");
+    if (out->izl && (!out->rzl || !out->dzl || !out->bzl)) return fail(SDK_EINVAL, "sdk_locate: vertical output arrays missing");
+    if (out->iz && (!out->rz || !out->dz || !out->bz)) return fail(SDK_EINVAL, "sdk_locate: vertical output arrays missing");
+    if (out->iz_lin && (!out->rz_lin || !out->dz_lin || !out->bz_lin || !grid->dev.dZ))
+        return fail(SDK_EINVAL, "sdk_locate: vertical output arrays (or dZ) missing");
+    if (out->izl_near && (!out->rzl_near || !out->dzl_near || !out->bzl_near)) return fail(SDK_EINVAL, "sdk_locate: vertical output arrays missing");
+    if (out->it_lin && (!out->rt_lin || !out->dt_lin || !out->bt_lin)) return fail(SDK_EINVAL, "sdk_locate: time output arrays missing");
     sdk::LocateArgs a;
     a.g = grid->dev;
     a.b = grid->buckets;
@@ -336,7 +339,7 @@ static int check_interp(const sdk_grid *grid, const sdk_points *pts, const sdk_f
     if (k->n_nodes < 1 || k->n_nodes > SDK_MAX_NODES || k->n_levels < 1 || k->n_levels > SDK_MAX_LEVELS)
         return fail(SDK_EINVAL, "sdk_interp: kernel too large");
     if (k->reach > 0 && !k->rim) return fail(SDK_EINVAL, "sdk_interp: rim table missing");
-    if (grid->dev.ny > 16383 || grid->dev.nx > 16383) return fail(SDK_EUNSUPPORTED, "sdk_interp: faces larger than 16383");
+    if (grid->dev.gny > 8191 || grid->dev.gnx > 8191 || grid->dev.nface > 32) return fail(SDK_EUNSUPPORTED, "sdk_interp: faces larger than 8191 x 8191");
     if (f->has_z && k->vmode != SDK_MODE_NEAREST && !pts->rz && k->vmode == SDK_MODE_LINEAR)
         return fail(SDK_EINVAL, "sdk_interp: rz missing");
     if (f->has_z && !pts->kz) return fail(SDK_EINVAL, "sdk_interp: vertical index missing");

@@ -71,7 +71,7 @@ __device__ __forceinline__ void level_weights(const sdk_kernel_desc &K, const sd
 }
 
 struct NodeSet {
-    int32_t packed[SDK_MAX_NODES];  // face<<28 | iy<<14 | ix, or -1
+    int32_t packed[SDK_MAX_NODES];  // SDK_PACK(face, iy, ix), SDK_NODE_RAISES or SDK_NODE_LAST
     uint8_t code[SDK_MAX_NODES];    // bit0 other component, bit1 negative
 };
 
@@ -81,7 +81,7 @@ __device__ __forceinline__ int find_nodes(const GridDev &g, const sdk_kernel_des
     int bad = 0;
     if (slot < 0 || K.rim == nullptr) {
         for (int m = 0; m < K.n_nodes; ++m) {
-            ns.packed[m] = (f << 28) | ((iy + K.dy[m]) << 14) | (ix + K.dx[m]);
+            ns.packed[m] = SDK_PACK(f, iy + K.dy[m], ix + K.dx[m]);
             ns.code[m] = 0;
         }
         return 0;
@@ -91,13 +91,15 @@ __device__ __forceinline__ int find_nodes(const GridDev &g, const sdk_kernel_des
     for (int m = 0; m < K.n_nodes; ++m) {
         ns.packed[m] = __ldg(K.rim + base + m);
         ns.code[m] = K.rim_code ? __ldg(K.rim_code + base + m) : 0;
-        bad |= ns.packed[m] < 0;
+        bad |= ns.packed[m] == SDK_NODE_RAISES;
     }
     return bad;
 }
 
-__device__ __forceinline__ int64_t plane_index(int packed, int fny, int fnx) {
-    const int f = packed >> 28 & 0xf, y = packed >> 14 & 0x3fff, x = packed & 0x3fff;
+// SDK_NODE_LAST: the reference walked off a closed box and indexes [-1, -1], numpy's last element
+__device__ __forceinline__ int64_t plane_index(int packed, int nface, int fny, int fnx) {
+    if (packed == SDK_NODE_LAST) return (int64_t)nface * fny * fnx - 1;
+    const int f = packed >> 26 & 0x1f, y = packed >> 13 & 0x1fff, x = packed & 0x1fff;
     return ((int64_t)f * fny + y) * fnx + x;
 }
 
@@ -105,19 +107,21 @@ __device__ __forceinline__ double field_value(const GridDev &g, const sdk_field 
     int64_t lev = 0;
     if (F.has_time) lev = wrap_index(kt - F.it0, F.nt);
     if (F.has_z) lev = lev * F.nz + wrap_index(kz, F.nz);
-    const int64_t idx = lev * ((int64_t)g.nface * F.ny * F.nx) + plane_index(packed, F.ny, F.nx);
+    const int64_t idx = lev * ((int64_t)g.nface * F.ny * F.nx) + plane_index(packed, g.nface, F.ny, F.nx);
     const double v = F.dtype == SDK_F64 ? ldf<double>(F.data, idx) : ldf<float>(F.data, idx);
     return nan_to_num(v);
 }
 
 __device__ __forceinline__ bool is_wet(const GridDev &g, const sdk_field &F, int packed, int kz) {
-    if (packed < 0) return false;
+    if (packed == SDK_NODE_RAISES) return false;
     int z = F.has_z ? kz : 0;
     if (z < 0) z += F.mask_nz;
     if (z < 0 || z >= F.mask_nz) return false;
-    const int y = packed >> 14 & 0x3fff, x = packed & 0x3fff;
-    if (y >= F.mask_ny || x >= F.mask_nx) return false;
-    const int64_t idx = (int64_t)z * ((int64_t)g.nface * F.mask_ny * F.mask_nx) + plane_index(packed, F.mask_ny, F.mask_nx);
+    if (packed != SDK_NODE_LAST) {
+        const int y = packed >> 13 & 0x1fff, x = packed & 0x1fff;
+        if (y >= F.mask_ny || x >= F.mask_nx) return false;
+    }
+    const int64_t idx = (int64_t)z * ((int64_t)g.nface * F.mask_ny * F.mask_nx) + plane_index(packed, g.nface, F.mask_ny, F.mask_nx);
     return __ldg(F.mask + idx) != 0;
 }
 
@@ -164,7 +168,7 @@ __device__ double interp_value(const GridDev &g, const sdk_kernel_desc &K, const
             double acc = 0.0;
             for (int m = 0; m < K.n_nodes; ++m) {
                 if (!(K.level[level].node_mask >> m & 1u)) continue;
-                if (ns.packed[m] < 0) {
+                if (ns.packed[m] == SDK_NODE_RAISES) {
                     acc = NAN;
                     continue;
                 }

@@ -123,7 +123,7 @@ __device__ __forceinline__ double dist2_to_cell(const GridDev &g, int f, int iy,
 // reference find_rel (utils.py:321) with find_ind (utils.py:273) for a 1-D table in shared/global
 __device__ __forceinline__ void find_rel_1d(const float *arr, const float *darr, int n, int n_d,
                                             double x, int ascending, bool above, bool dx_right,
-                                            int &idx, double &r, double &d, double &b) {
+                                            int &idx, double &r, double &d, double &b, int &status) {
     int best = 0;
     double bestv = INFINITY;
     for (int k = 0; k < n; ++k) {
@@ -134,7 +134,8 @@ __device__ __forceinline__ void find_rel_1d(const float *arr, const float *darr,
         }
     }
     if (above && (double)arr[best] > x) best -= ascending;
-    best = min(max(best, 0), n - 1);  // reference raises "Value out of bound."
+    if (best < 0 || best > n - 1) status |= SDK_ST_OOB;  // reference raises "Value out of bound."
+    best = min(max(best, 0), n - 1);
     const double bx = (double)arr[best];
     const double dx = x - bx;
     int off = (int)(!dx_right) + (int)(ascending > 0) - 1;
@@ -157,7 +158,7 @@ __device__ __forceinline__ void find_rel_1d(const float *arr, const float *darr,
 
 // same for float64 tables (time axes)
 __device__ __forceinline__ void find_rel_1d_f64(const double *arr, int n, double x, bool above, int &idx,
-                                                double &r, double &d, double &b) {
+                                                double &r, double &d, double &b, int &status) {
     int best = 0;
     double bestv = INFINITY;
     for (int k = 0; k < n; ++k) {
@@ -168,6 +169,7 @@ __device__ __forceinline__ void find_rel_1d_f64(const double *arr, int n, double
         }
     }
     if (above && arr[best] > x) best -= 1;
+    if (best < 0) status |= SDK_ST_OOB;
     best = min(max(best, 0), n - 1);
     const double bx = arr[best];
     const double dx = x - bx;
@@ -254,25 +256,41 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
         int k;
         double r, d, b;
         if (g.n_zc > 1 && o.iz) {  // _find_rel_v: nearest Z
-            find_rel_1d(g.Z, nullptr, g.n_zc, 0, z, 1, false, true, k, r, d, b);
+            find_rel_1d(g.Z, nullptr, g.n_zc, 0, z, 1, false, true, k, r, d, b, status);
             o.iz[i] = k; o.rz[i] = r; o.dz[i] = d; o.bz[i] = b;
+        }
+        if (g.n_zc > 1 && o.iz_lin) {  // _find_rel_v_lin: find_rel_z(z, Z, dZ) -> ascending=-1, dx_right=False
+            int st = 0;
+            find_rel_1d(g.Z, g.dZ, g.n_zc, g.n_zc, z, -1, true, false, k, r, d, b, st);
+            if (st) status |= SDK_ST_OOB_Z;
+            o.iz_lin[i] = k; o.rz_lin[i] = r; o.dz_lin[i] = d; o.bz_lin[i] = b;
         }
         if (g.n_zl > 1) {
             if (o.izl_near) {  // _find_rel_vl: nearest Zl
-                find_rel_1d(g.Zl, nullptr, g.n_zl, 0, z, 1, false, true, k, r, d, b);
+                find_rel_1d(g.Zl, nullptr, g.n_zl, 0, z, 1, false, true, k, r, d, b, status);
                 o.izl_near[i] = k; o.rzl_near[i] = r; o.dzl_near[i] = d; o.bzl_near[i] = b;
             }
             // _find_rel_vl_lin: find_rel_z(z, Zl, dZl, dz_above_z=False) -> ascending=-1, dx_right=True
-            find_rel_1d(g.Zl, g.dZl, g.n_zl, g.n_z, z, -1, true, true, k, r, d, b);
-            o.izl[i] = k; o.rzl[i] = r; o.dzl[i] = d; o.bzl[i] = b;
+            if (o.izl) {
+                find_rel_1d(g.Zl, g.dZl, g.n_zl, g.n_z, z, -1, true, true, k, r, d, b, status);
+                o.izl[i] = k; o.rzl[i] = r; o.dzl[i] = d; o.bzl[i] = b;
+            }
         }
     }
     if (a.t && a.ts && a.n_t > 1) {  // _find_rel_t: nearest time level
         int k;
         double r, d, b;
-        find_rel_1d_f64(a.ts, a.n_t, a.t[i], false, k, r, d, b);
-        o.it[i] = k;
-        if (o.rt) { o.rt[i] = r; o.dt[i] = d; o.bt[i] = b; }
+        if (o.it) {
+            find_rel_1d_f64(a.ts, a.n_t, a.t[i], false, k, r, d, b, status);
+            o.it[i] = k;
+            if (o.rt) { o.rt[i] = r; o.dt[i] = d; o.bt[i] = b; }
+        }
+        if (o.it_lin) {  // _find_rel_t_lin: find_rel_time -> find_rel(t, ts), above
+            int st = 0;
+            find_rel_1d_f64(a.ts, a.n_t, a.t[i], true, k, r, d, b, st);
+            if (st) status |= SDK_ST_OOB_T;
+            o.it_lin[i] = k; o.rt_lin[i] = r; o.dt_lin[i] = d; o.bt_lin[i] = b;
+        }
     }
     if (o.status) o.status[i] = status;
 }
@@ -286,9 +304,9 @@ __global__ void time_index_kernel(const double *t, const double *midp, int n_mid
         it[i] = 0;
         return;
     }
-    int k;
+    int k, st = 0;
     double r, d, b;
-    find_rel_1d_f64(midp, n_midp, x, true, k, r, d, b);
+    find_rel_1d_f64(midp, n_midp, x, true, k, r, d, b, st);
     it[i] = k + 1;
 }
 

@@ -34,6 +34,13 @@ def weight_f_node(rx, ry):
     ).T
 
 
+_LAZY_REL = {}
+for _n in ("iz_lin", "rz_lin", "dz_lin", "bz_lin"):
+    _LAZY_REL[_n] = ("_find_rel_v_lin", "dep")
+for _n in ("it_lin", "rt_lin", "dt_lin", "bt_lin"):
+    _LAZY_REL[_n] = ("_find_rel_t_lin", "t")
+
+
 class Position:
     """Points on the grid.  Create empty, then ``from_latlon``."""
 
@@ -49,6 +56,13 @@ class Position:
         rel = object.__getattribute__(self, "rel")
         if attr in rel.keys():
             return rel[attr]
+        if attr in _LAZY_REL:
+            # linear Z / time rel-coords are looked up on first use (reference eulerian.py:465,508)
+            func, src = _LAZY_REL[attr]
+            coord = self.__dict__.get(src)
+            if coord is not None:
+                rel.update(getattr(self.ocedata, func)(coord))
+                return rel[attr]
         raise AttributeError(f"'{type(self).__name__}' object has no attribute '{attr}'")
 
     def __setattr__(self, attr, value):
@@ -56,6 +70,8 @@ class Position:
             object.__setattr__(self, attr, value)
         elif attr in self.rel.keys():
             self.rel[attr] = value
+            # the device copy made by from_latlon no longer describes these points
+            self.__dict__.pop("_located", None)
         else:
             object.__setattr__(self, attr, value)
 

@@ -350,6 +350,10 @@ class Dataset:
         try:
             return self._vars[key]
         except KeyError:
+            # a dimension without coordinate variable: xarray hands out its integer index
+            dims = self.dims
+            if key in dims:
+                return DataArray(np.arange(dims[key]), dims=(key,), name=key)
             raise KeyError(key) from None
 
     def __setitem__(self, key, value):

@@ -132,6 +132,7 @@ class OceData:
         self.device = device
         self._dev = {}  # name -> torch tensor on the GPU
         self._field_cache = {}
+        self._interp_cache = {}  # rim tables and masks of the interpolation kernel
         self._grid_handle = None
         readiness = self.check_readiness()
         self.readiness = readiness
@@ -441,10 +442,12 @@ class OceData:
             out[name] = torch.empty(n * mult, dtype=dtype, device=dev)
             setattr(loc, name, out[name].data_ptr())
 
+        out["status"] = torch.zeros(n, dtype=torch.int32, device=dev)
+        loc.status = out["status"].data_ptr()
         if dx is not None:
             if self.tp.has_face:
                 alloc("face", torch.int32)
-            for nme in ("iy", "ix", "status"):
+            for nme in ("iy", "ix"):
                 alloc(nme, torch.int32)
             for nme in ("rx", "ry"):
                 alloc(nme, torch.float64)
@@ -455,7 +458,8 @@ class OceData:
         if dz is not None:
             if self.readiness["Z"]:
                 alloc("iz", torch.int32)
-                for nme in ("rz", "dz", "bz"):
+                alloc("iz_lin", torch.int32)
+                for nme in ("rz", "dz", "bz", "rz_lin", "dz_lin", "bz_lin"):
                     alloc(nme, torch.float64)
             if self.readiness["Zl"]:
                 alloc("izl_near", torch.int32)
@@ -468,7 +472,8 @@ class OceData:
             ts_dev = self.to_device("ts", self.ts, np.float64)
             n_t = len(self.ts)
             alloc("it", torch.int32)
-            for nme in ("rt", "dt", "bt"):
+            alloc("it_lin", torch.int32)
+            for nme in ("rt", "dt", "bt", "rt_lin", "dt_lin", "bt_lin"):
                 alloc(nme, torch.float64)
         _lib.check(
             L.sdk_locate(
@@ -478,6 +483,10 @@ class OceData:
             "sdk_locate",
         )
         out["_inputs"] = (dx, dy, dz, dt)
+        flags = int(out["status"].max().item()) if n > 0 else 0
+        if flags & 16:
+            raise ValueError("Value out of bound.")  # reference find_ind, utils.py:301
+        out["_flags"] = flags
         return out
 
     @staticmethod
@@ -499,6 +508,18 @@ class OceData:
     def _find_rel_v(self, z):
         o = self.locate(z=z)
         return VRel(self._np(o["iz"], np.int64), self._np(o["rz"]), self._np(o["dz"]), self._np(o["bz"]))
+
+    def _find_rel_v_lin(self, z):
+        o = self.locate(z=z)
+        if o["_flags"] & 32:
+            raise ValueError("Value out of bound.")
+        return VLinRel(self._np(o["iz_lin"], np.int64), self._np(o["rz_lin"]), self._np(o["dz_lin"]), self._np(o["bz_lin"]))
+
+    def _find_rel_t_lin(self, t):
+        o = self.locate(t=t)
+        if o["_flags"] & 64:
+            raise ValueError("Value out of bound.")
+        return TLinRel(self._np(o["it_lin"], np.int64), self._np(o["rt_lin"]), self._np(o["dt_lin"]), self._np(o["bt_lin"]))
 
     def _find_rel_vl(self, z):
         o = self.locate(z=z)

@@ -1,0 +1,94 @@
+"""GPU: ``Position.from_latlon`` + ``Position.interpolate`` (CUDA, through the C ABI) against the
+golden vectors produced by the unmodified reference (``oracle/make_golden_interp.py``).
+Indices bit-exact, NaN pattern identical, values within 1e-9 relative."""
+
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases_interp as ci
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _position(case, gold):
+    import seaduck_b200 as sd
+
+    od = sd.OceData(case["ds"])
+    get = lambda k: gold[f"in_{k}"] if f"in_{k}" in gold else None  # noqa: E731
+    pos = sd.Position().from_latlon(x=get("x"), y=get("y"), z=get("z"), t=get("t"), data=od)
+    return sd, od, pos
+
+
+@pytest.mark.parametrize("make", ci.ALL_CASES, ids=lambda f: f.__name__)
+def test_locate_matches_reference(make):
+    case = make()
+    gold = np.load(os.path.join(GOLD, f"interp_{case['name']}.npz"))
+    _, _, pos = _position(case, gold)
+    for key in ("face", "iy", "ix", "iz", "izl", "izl_lin", "it", "iz_lin", "it_lin"):
+        if f"pos_{key}" in gold:
+            np.testing.assert_array_equal(getattr(pos, key), gold[f"pos_{key}"], err_msg=key)
+    for key in ("rx", "ry", "rz", "rzl", "rzl_lin", "rt", "rz_lin", "rt_lin"):
+        if f"pos_{key}" in gold:
+            ci.assert_values_close(key, getattr(pos, key), gold[f"pos_{key}"])
+
+
+@pytest.mark.parametrize("make", ci.ALL_CASES, ids=lambda f: f.__name__)
+def test_interpolate_matches_reference(make):
+    case = make()
+    gold = np.load(os.path.join(GOLD, f"interp_{case['name']}.npz"))
+    sd, _, pos = _position(case, gold)
+    failures = []
+    for label, var, spec, vec_transform in case["jobs"]:
+        knw = ci.make_knw(sd.KnW, spec)
+        res = pos.interpolate(var, knw, vec_transform=vec_transform)
+        flat = ci.flatten_result(res)
+        for k, arr in enumerate(flat):
+            try:
+                ci.assert_values_close(f"{label}[{k}]", arr, gold[f"job_{label}_{k}"])
+            except AssertionError as exc:
+                failures.append(str(exc))
+        assert len(flat) == len([k for k in gold.files if re.fullmatch(rf"job_{label}_\d+", k)]), label
+    assert not failures, "\n".join(failures)
+
+
+def test_interpolate_output_nesting():
+    """str -> array, tuple -> (u, v), list -> list; dict kernels; repeated entries."""
+    case = ci.case_llc2d(n=64)
+    import seaduck_b200 as sd
+
+    od = sd.OceData(case["ds"])
+    pos = sd.Position().from_latlon(x=case["x"], y=case["y"], data=od)
+    k = sd.KnW(ignore_mask=True)
+    a = pos.interpolate("T", k)
+    assert isinstance(a, np.ndarray) and a.shape == (64,)
+    uv = pos.interpolate(("UVELMASS", "VVELMASS"), (k, k))
+    assert isinstance(uv, tuple) and len(uv) == 2
+    out = pos.interpolate(["T", ("UVELMASS", "VVELMASS"), "T"], {"T": k, ("UVELMASS", "VVELMASS"): (k, k)})
+    assert isinstance(out, list) and len(out) == 3
+    np.testing.assert_array_equal(out[0], a)
+    np.testing.assert_array_equal(out[2], a)
+    np.testing.assert_array_equal(out[1][0], uv[0])
+    with pytest.raises(ValueError):
+        pos.interpolate(["T", "T"], [k])
+    with pytest.raises(ValueError):
+        pos.interpolate("T", (k, k, k))
+
+
+def test_interpolate_after_editing_position():
+    """Setting a rel-coord by hand invalidates the device copy made by from_latlon."""
+    case = ci.case_llc2d(n=32)
+    import seaduck_b200 as sd
+
+    od = sd.OceData(case["ds"])
+    pos = sd.Position().from_latlon(x=case["x"], y=case["y"], data=od)
+    k = sd.KnW(ignore_mask=True, kernel=ci.STENCILS["one"], inheritance=None)
+    a = pos.interpolate("T", k)
+    pos.ix = (pos.ix + 1) % 30
+    b = pos.interpolate("T", k)
+    t = np.asarray(case["ds"]["T"])
+    np.testing.assert_allclose(b, t[pos.face, pos.iy, pos.ix])
+    assert not np.allclose(a, b)
