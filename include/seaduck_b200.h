@@ -140,6 +140,10 @@ typedef struct sdk_log {
 } sdk_log;
 
 int sdk_abi_version(void);
+/* sizeof() of the structures above as the library was compiled (binding self-check): 0 sdk_grid_desc,
+ * 1 sdk_velocity, 2 sdk_particles, 3 sdk_advect_params, 4 sdk_log, 5 sdk_located, 6 sdk_track_io,
+ * 7 sdk_kernel_desc, 8 sdk_field, 9 sdk_points; -1 for anything else */
+int64_t sdk_struct_size(int which);
 const char *sdk_last_error(void);
 /* number of SMs of the current device (grid sizing), <0 on error */
 int sdk_sm_count(void);
@@ -283,6 +287,14 @@ int sdk_build_masks(const sdk_grid *grid, const uint8_t *maskC, int32_t nz, uint
 /* it := 0 before time_midp[0], else find_rel(t, time_midp) + 1 (seaduck/lagrangian.py:796-802). */
 int sdk_time_index(const double *t, const double *time_midp, int32_t n_midp, int32_t *it, int64_t n,
                    void *stream);
+
+/* Self-test of the device math helpers used by sdk_advect (csrc/fastmath.cuh): out[i] = op(a[i], b[i]),
+ * bad[i] = 1 where the helper asked for the slow path.  Device pointers; b may be NULL for unary ops. */
+enum {
+    SDK_SELFTEST_DIV = 0, SDK_SELFTEST_LOG = 1, SDK_SELFTEST_EXP = 2,
+    SDK_SELFTEST_DIV_IEEE = 3, SDK_SELFTEST_LOG_CUDA = 4, SDK_SELFTEST_EXP_CUDA = 5
+};
+int sdk_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad, void *stream);
 
 #ifdef __cplusplus
 }

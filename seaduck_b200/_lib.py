@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.environ.get("SEADUCK_B200_LIB") or os.path.join(_HERE, "libseaduck_b200.so")
-SOURCES = ["advect.cu", "locate.cu", "interp.cu", "capi.cu"]
+SOURCES = ["advect.cu", "locate.cu", "interp.cu", "selftest.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",
@@ -168,6 +168,7 @@ def lib():
         L.sdk_track_scratch_bytes.restype = C.c_int64
         L.sdk_track_scratch_bytes.argtypes = [C.c_int64]
         L.sdk_track_host.argtypes = [vp, C.POINTER(Velocity), C.POINTER(TrackIO), vp, C.c_int32, C.c_double, C.POINTER(AdvectParams), vp, vp]
+        L.sdk_selftest_math.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 

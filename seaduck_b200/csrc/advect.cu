@@ -209,30 +209,53 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
         const int64_t idx = (v.vol_has_z ? (int64_t)wrap_index(s.izl - 1, g.n_z > 0 ? g.n_z : 1) : 0) * v.planeC + cell;
         s.vol = v.vol_dtype == SDK_F64 ? ldf<double>(v.Vol, idx) : ldf<float>(v.Vol, idx);
     }
-    const double ul_ = nan_to_num(ul), ur_ = nan_to_num(ur), vl_ = nan_to_num(vl), vr_ = nan_to_num(vr);
+    double ul_ = ul, ur_ = ur, vl_ = vl, vr_ = vr;
+    nan_to_num4(ul_, ur_, vl_, vr_);
     const bool stag_x = g.has_face || v.u_stag, stag_y = g.has_face || v.v_stag;
     const double rxs = stag_x ? s.rx + 0.5 : s.rx;
     const double rys = stag_y ? s.ry + 0.5 : s.ry;
     // Lagrange weights of the two-node kernels (reference kernel_weight.py:211-229)
-    const double wx0 = (rxs - 1.0) / (0.0 - 1.0), wx1 = rxs;
-    const double wy0 = (rys - 1.0) / (0.0 - 1.0), wy1 = rys;
+    // (r - 1) / (0 - 1) is an exact negation
+    const double wx0 = -(rxs - 1.0), wx1 = rxs;
+    const double wy0 = -(rys - 1.0), wy1 = rys;
     double u = ul_ * wx0 + ur_ * wx1;
     double du = ul_ * -1.0 + ur_;
     double vv = vl_ * wy0 + vr_ * wy1;
     double dv = vl_ * -1.0 + vr_;
     const double sx = v.transport ? s.vol : (double)s.dx;
     const double sy = v.transport ? s.vol : (double)s.dy;
-    s.u = nan_to_num(u / sx);
-    s.v = nan_to_num(vv / sy);
-    s.du = nan_to_num(du / sx);
-    s.dv = nan_to_num(dv / sy);
+    const double sz = v.transport ? s.vol : s.dzl;
+    double w = 0.0, dw = 0.0;
     if (v.has_w) {
         const double w0_ = nan_to_num(w0), w1_ = nan_to_num(w1);
-        const double w = w0_ * (1 - s.rzl) + w1_ * s.rzl;
-        const double dw = w0_ * -1.0 + w1_;
-        const double sz = v.transport ? s.vol : s.dzl;
-        s.w = nan_to_num(w / sz);
-        s.dw = nan_to_num(dw / sz);
+        w = w0_ * (1 - s.rzl) + w1_ * s.rzl;
+        dw = w0_ * -1.0 + w1_;
+    }
+    // six IEEE divisions by at most three denominators (one, the cell volume, for transports): the
+    // refined reciprocal is shared, each quotient costs three more operations (fastmath.cuh)
+    bool redo = false;
+    const double yx = rcp_refined(sx);
+    const double yy = v.transport ? yx : rcp_refined(sy);
+    const double yz = v.transport ? yx : rcp_refined(sz);
+    double qu = div_with(u, sx, yx, redo), qdu = div_with(du, sx, yx, redo);
+    double qv = div_with(vv, sy, yy, redo), qdv = div_with(dv, sy, yy, redo);
+    double qw = 0.0, qdw = 0.0;
+    if (v.has_w) {
+        qw = div_with(w, sz, yz, redo);
+        qdw = div_with(dw, sz, yz, redo);
+    }
+    if (redo) {  // zero / denormal / non-finite scale: plain operators
+        qu = u / sx, qdu = du / sx, qv = vv / sy, qdv = dv / sy;
+        if (v.has_w) qw = w / sz, qdw = dw / sz;
+    }
+    nan_to_num4(qu, qv, qdu, qdv);
+    s.u = qu;
+    s.v = qv;
+    s.du = qdu;
+    s.dv = qdv;
+    if (v.has_w) {
+        s.w = nan_to_num(qw);
+        s.dw = nan_to_num(qdw);
     }
 }
 
@@ -247,19 +270,50 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
     trim_axis(s.rx, s.u, s.du, lo, hi);
     trim_axis(s.ry, s.v, s.dv, lo, hi);
     if (has_dep) trim_axis(s.rzl, s.w, s.dw, -0.0 + a.trim_tol, 1.0 - a.trim_tol);
-    // analytical_step, lagrangian.py:561
+    // analytical_step, lagrangian.py:561: exit times, one axis at a time (one copy of the code)
     const double tf = a.t_stop - s.t;
     const double sg = sgn(tf);
     const double z0 = has_dep ? s.rzl - 0.5 : 0.0;
     double ts[7];
-    wall_times(s.u, s.du, s.rx, sg, ts[0], ts[1]);
-    wall_times(s.v, s.dv, s.ry, sg, ts[2], ts[3]);
-    if (has_dep) {
-        wall_times(s.w, s.dw, z0, sg, ts[4], ts[5]);
-    } else {
-        ts[4] = -sg;
-        ts[5] = -sg;
+#if SDK_ADVECT_INLINE_AXES
+    {
+        // three independent straight-line copies that ptxas interleaves; rare cases out of line
+        bool redo_x = false, redo_y = false, redo_z = false;
+        wall_times_fast_inline(s.u, s.du, s.rx, sg, ts[0], ts[1], redo_x);
+        wall_times_fast_inline(s.v, s.dv, s.ry, sg, ts[2], ts[3], redo_y);
+        if (has_dep) {
+            wall_times_fast_inline(s.w, s.dw, z0, sg, ts[4], ts[5], redo_z);
+        } else {
+            ts[4] = -sg;
+            ts[5] = -sg;
+        }
+        if (redo_x) {
+            const AxisTimes t = axis_wall_times(s.u, s.du, s.rx, sg);
+            ts[0] = t.x, ts[1] = t.y;
+        }
+        if (redo_y) {
+            const AxisTimes t = axis_wall_times(s.v, s.dv, s.ry, sg);
+            ts[2] = t.x, ts[3] = t.y;
+        }
+        if (redo_z) {
+            const AxisTimes t = axis_wall_times(s.w, s.dw, z0, sg);
+            ts[4] = t.x, ts[5] = t.y;
+        }
     }
+#else
+    {
+        const AxisTimes tx = axis_wall_times(s.u, s.du, s.rx, sg);
+        const AxisTimes ty = axis_wall_times(s.v, s.dv, s.ry, sg);
+        ts[0] = tx.x, ts[1] = tx.y, ts[2] = ty.x, ts[3] = ty.y;
+        if (has_dep) {
+            const AxisTimes tz = axis_wall_times(s.w, s.dw, z0, sg);
+            ts[4] = tz.x, ts[5] = tz.y;
+        } else {
+            ts[4] = -sg;
+            ts[5] = -sg;
+        }
+    }
+#endif
     ts[6] = tf;
     // _which_early, utils.py:875: first minimum of the directed times, nan / negative = never
     int tend = 0;
@@ -280,14 +334,24 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
     // _move_within_cell, lagrangian.py:528
     s.t += te;
     {
-        const double ix_ = increment(te, s.u, s.du);
-        const double iy_ = increment(te, s.v, s.dv);
+#if SDK_ADVECT_INLINE_AXES
+        bool redo_x = false, redo_y = false, redo_z = false;
+        double ix_ = increment_fast_inline(te, s.u, s.du, redo_x);
+        double iy_ = increment_fast_inline(te, s.v, s.dv, redo_y);
+        double iz_ = has_dep ? increment_fast_inline(te, s.w, s.dw, redo_z) : 0.0;
+        if (redo_x) ix_ = axis_increment(te, s.u, s.du);
+        if (redo_y) iy_ = axis_increment(te, s.v, s.dv);
+        if (redo_z) iz_ = axis_increment(te, s.w, s.dw);
+#else
+        const double ix_ = axis_increment(te, s.u, s.du);
+        const double iy_ = axis_increment(te, s.v, s.dv);
+        const double iz_ = has_dep ? axis_increment(te, s.w, s.dw) : 0.0;
+#endif
         s.u = s.u + s.du * ix_;
         s.v = s.v + s.dv * iy_;
         s.rx = ix_ + s.rx;
         s.ry = iy_ + s.ry;
         if (has_dep) {
-            const double iz_ = increment(te, s.w, s.dw);
             s.w = s.w + s.dw * iz_;
             s.rzl = (iz_ + z0) + 0.5;
         }
@@ -331,14 +395,26 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
         s.bzl = (double)sZl[wrap_index(s.izl, g.n_zl)];
         s.dzl = (double)sdZl[wrap_index(s.izl - 1, g.n_z)];
         // _cross_cell_wall_rel, lagrangian.py:681
-        s.rzl = (s.dep - s.bzl) / s.dzl;
+        s.rzl = div_maybe_zero(s.dep - s.bzl, s.dzl);
     }
+    {
+        bool redo = false;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        s.px[j] = s.lon + to_180((double)gx[j] - s.lon);  // eulerian.py:618
-        s.py[j] = (double)gy[j];
+        for (int j = 0; j < 4; ++j) {
+            s.px[j] = s.lon + to_180_fast((double)gx[j] - s.lon, redo);  // eulerian.py:618
+            s.py[j] = (double)gy[j];
+        }
+        if (redo) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s.px[j] = s.lon + to_180((double)gx[j] - s.lon);
+        }
+        redo = false;
+        inverse_bilinear_fast(s.lon, s.lat, s.px, s.py, s.rx, s.ry, redo);
+        if (redo) {
+            const double2 r = inverse_bilinear_slow(s.lon, s.lat, s.px[0], s.px[1], s.px[2], s.px[3], s.py[0], s.py[1], s.py[2], s.py[3]);
+            s.rx = r.x, s.ry = r.y;
+        }
     }
-    inverse_bilinear(s.lon, s.lat, s.px, s.py, s.rx, s.ry);
     // get_vol + get_u_du
     read_velocity<T>(g, a.v, has_dep, s);
     s.niter += 1;
@@ -346,12 +422,29 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
     if (LOG && live) note(a, s, 7);
 }
 
+// Tuning knobs (profiles/README.md, round 1 iterations d-g).  The particle step is ~2000 SASS
+// instructions; 16 resident warps walking through it independently overflow the SM's 32 KB
+// instruction cache and saturate the GPC-level instruction cache behind it.  LOCKSTEP makes the
+// warps of one 512-thread CTA start every step together (one barrier per step) so that they share
+// the fetched lines (hit rate 79 % -> 95 %, but the barrier wait costs what the misses did);
+// INLINE_AXES picks between three interleaved copies of the per-axis code and one out-of-line copy
+// (smaller loop body).  Measured on the bench workload: all four combinations within 10 %, the
+// defaults below are the fastest.
+#ifndef SDK_ADVECT_LOCKSTEP
+#define SDK_ADVECT_LOCKSTEP 0
+#endif
+#ifndef SDK_ADVECT_THREADS
+#define SDK_ADVECT_THREADS (SDK_ADVECT_LOCKSTEP ? 512 : 128)
+#endif
 #ifndef SDK_ADVECT_MIN_BLOCKS
-#define SDK_ADVECT_MIN_BLOCKS 4
+#define SDK_ADVECT_MIN_BLOCKS (SDK_ADVECT_LOCKSTEP ? 1 : 4)
+#endif
+#ifndef SDK_ADVECT_INLINE_AXES
+#define SDK_ADVECT_INLINE_AXES 0
 #endif
 
 template <typename T, bool LOG>
-__global__ void __launch_bounds__(128, SDK_ADVECT_MIN_BLOCKS)
+__global__ void __launch_bounds__(SDK_ADVECT_THREADS, SDK_ADVECT_MIN_BLOCKS)
 advect_kernel(const __grid_constant__ AdvectArgs a) {
     extern __shared__ float smem[];
     float *sZl = smem;
@@ -389,7 +482,11 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
                 }
             }
         }
+#if SDK_ADVECT_LOCKSTEP
+        if (!__syncthreads_or(have)) break;
+#else
         if (!__any_sync(full, have)) break;
+#endif
         if (have) {
             if (live && s.niter < a.max_iteration) {
                 step<T, LOG>(a, sZl, sdZl, s, live);
@@ -450,6 +547,9 @@ __global__ void __launch_bounds__(128) get_u_du_kernel(const __grid_constant__ A
 // host side launchers (called from capi.cu)
 // ------------------------------------------------------------------------------------------------
 namespace sdk {
+
+int advect_max_threads() { return SDK_ADVECT_THREADS; }
+int advect_default_blocks_per_sm() { return SDK_ADVECT_MIN_BLOCKS; }
 
 cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaStream_t stream) {
     const size_t smem = sizeof(float) * (size_t)(args.g.n_zl + args.g.n_z);

@@ -12,6 +12,11 @@
 #include "interp_args.cuh"
 #include "locate_args.cuh"
 
+namespace sdk {
+cudaError_t launch_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad,
+                                 cudaStream_t s);
+}
+
 namespace {
 thread_local std::string g_err;
 
@@ -172,12 +177,13 @@ int sdk_advect(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particle
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaError_t e = cudaMemsetAsync(grid->queue, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_advect: memset");
-    const int threads = (par && par->threads_per_block > 0) ? par->threads_per_block : 128;
-    const int per_sm = (par && par->blocks_per_sm > 0) ? par->blocks_per_sm : 4;
+    const int threads = (par && par->threads_per_block > 0) ? par->threads_per_block : sdk::advect_max_threads();
+    const int per_sm = (par && par->blocks_per_sm > 0) ? par->blocks_per_sm : sdk::advect_default_blocks_per_sm();
     int64_t need = (p->n + threads - 1) / threads;
     int64_t blocks = (int64_t)grid->sm_count * per_sm;
     if (blocks > need) blocks = need;
-    if (threads > 128 || threads % 32) return fail(SDK_EINVAL, "threads_per_block must be a multiple of 32, <= 128");
+    if (threads > sdk::advect_max_threads() || threads % 32)
+        return fail(SDK_EINVAL, "threads_per_block must be a multiple of 32 and at most the compiled block size");
     e = sdk::launch_advect(a, (int)blocks, threads, stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_advect: launch");
     return SDK_OK;
@@ -397,6 +403,31 @@ int sdk_build_masks(const sdk_grid *grid, const uint8_t *maskC, int32_t nz, uint
     if (!grid || !maskC || !maskU || !maskV || !maskW || nz < 1) return fail(SDK_EINVAL, "sdk_build_masks: bad argument");
     cudaError_t e = sdk::launch_build_masks(grid->dev, maskC, nz, maskU, maskV, maskW, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_build_masks: launch");
+    return SDK_OK;
+}
+
+// ---- device math self-test --------------------------------------------------------------------------
+int64_t sdk_struct_size(int which) {
+    switch (which) {
+        case 0: return sizeof(sdk_grid_desc);
+        case 1: return sizeof(sdk_velocity);
+        case 2: return sizeof(sdk_particles);
+        case 3: return sizeof(sdk_advect_params);
+        case 4: return sizeof(sdk_log);
+        case 5: return sizeof(sdk_located);
+        case 6: return sizeof(sdk_track_io);
+        case 7: return sizeof(sdk_kernel_desc);
+        case 8: return sizeof(sdk_field);
+        case 9: return sizeof(sdk_points);
+        default: return -1;
+    }
+}
+
+int sdk_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad, void *stream) {
+    if (n < 0 || (n > 0 && (!a || !out || !bad))) return fail(SDK_EINVAL, "sdk_selftest_math: bad argument");
+    if ((op == SDK_SELFTEST_DIV || op == SDK_SELFTEST_DIV_IEEE) && n > 0 && !b) return fail(SDK_EINVAL, "sdk_selftest_math: b missing");
+    cudaError_t e = sdk::launch_selftest_math(op, n, a, b ? b : a, out, bad, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_selftest_math: launch");
     return SDK_OK;
 }
 

@@ -10,6 +10,7 @@
 #include <cstdint>
 
 #include "../../include/seaduck_b200.h"
+#include "fastmath.cuh"
 
 namespace sdk {
 
@@ -30,9 +31,12 @@ struct VelDev {
     int64_t planeU, planeV, planeC;  // elements per (time, level) slab of U, V and of cell-centred fields
 };
 
+// fmod is ~70 instructions; it is only needed for |a| >= 360, so keep one copy out of line
+static __device__ __noinline__ double fmod360(double a) { return fmod(a, 360.0); }
+
 __device__ __forceinline__ double py_mod360(double a) {
     // python / numpy float "%" with a positive modulus (reference utils.py:201)
-    double m = (fabs(a) < 360.0) ? a : fmod(a, 360.0);
+    double m = (fabs(a) < 360.0) ? a : fmod360(a);
     if (m != 0.0) {
         if (m < 0.0) m += 360.0;
     } else {
@@ -52,6 +56,22 @@ __device__ __forceinline__ double to_180(double x) {
     return x + (-1.0) * q * 360.0;
 }
 
+// to_180 for |x| < 720 (differences of two longitudes, one of which may have drifted past the date
+// line) in a dozen instructions and without the fmod branch; anything else sets `bad` and the
+// caller redoes the stage with to_180.  Step by step equal to the reference's x % 360 % 360 followed
+// by x + (-1) * (x // 180) * 360:
+//   fmod(x, 360) == x -+ 360 exactly for 360 <= |x| < 720 (Sterbenz);
+//   first "%": a negative remainder gets + 360 (rounded), -0.0 becomes +0.0 (x + 0.0 does both);
+//   the second "%" only ever turns exactly 360.0 into 0.0, which the last line does as well
+//   (360 - 360); the last line adds -360 in the upper half and -0.0 otherwise.
+__device__ __forceinline__ double to_180_fast(double x, bool &bad) {
+    const double ax = fabs(x);
+    bad = bad || !(ax < 720.0);
+    x = x - copysign(ax >= 360.0 ? 360.0 : 0.0, x);
+    const double m = x + (x < 0.0 ? 360.0 : 0.0);
+    return m + (m >= 180.0 ? -360.0 : -0.0);
+}
+
 // numpy.nan_to_num: nan -> 0, +-inf -> +-DBL_MAX.  One integer test on the exponent in the common
 // (finite) case.
 __device__ __forceinline__ double nan_to_num(double x) {
@@ -60,6 +80,29 @@ __device__ __forceinline__ double nan_to_num(double x) {
         return x > 0 ? DBL_MAX : -DBL_MAX;
     }
     return x;
+}
+
+// a / b, bit for bit, for numerators that are often exactly zero (a particle that has just crossed
+// a wall of a lat-lon aligned cell sits exactly on the wall coordinate): CUDA's division takes a
+// ~60 instruction slow path for a zero numerator, 1 / b does not.  0 * (1 / b) has the sign and
+// the NaN behaviour of 0 / b for every b.
+__device__ __forceinline__ double div_maybe_zero(double a, double b) {
+    const bool z = a == 0.0;
+    const double q = (z ? 1.0 : a) / b;
+    return z ? a * q : q;
+}
+
+// nan_to_num of four values at once: one test in the (finite) common case
+__device__ __forceinline__ void nan_to_num4(double &a, double &b, double &c, double &d) {
+    const int e = 0x7ff00000;
+    const bool fin = ((__double2hiint(a) & e) != e) && ((__double2hiint(b) & e) != e) && ((__double2hiint(c) & e) != e) &&
+                     ((__double2hiint(d) & e) != e);
+    if (!fin) {
+        a = nan_to_num(a);
+        b = nan_to_num(b);
+        c = nan_to_num(c);
+        d = nan_to_num(d);
+    }
 }
 
 __device__ __forceinline__ double sgn(double x) { return (double)((x > 0) - (x < 0)); }
@@ -134,7 +177,8 @@ __device__ __forceinline__ int corner_indices(const GridDev &g, int f, int iy, i
     return 0;
 }
 
-// reference find_rx_ry_oceanparcel, utils.py:532
+// reference find_rx_ry_oceanparcel, utils.py:532 (plain operators; also the slow path of
+// inverse_bilinear_fast)
 __device__ __forceinline__ void inverse_bilinear(double x, double y, const double pxi[4],
                                                  const double py[4], double &rx, double &ry) {
     const double x0 = pxi[0];
@@ -152,14 +196,56 @@ __device__ __forceinline__ void inverse_bilinear(double x, double y, const doubl
     const double det2 = bb * bb - 4 * aa * cc;
     const bool order1 = fabs(aa) < 1e-12;
     const bool order2 = !order1 && det2 >= 0;
-    double r = -(cc / bb);
+    double r = -div_maybe_zero(cc, bb);
     if (order2) r = (-bb + sqrt(det2)) / (2 * aa);
     const double den = a1 + a3 * r;
     double q;
     if (fabs(den) < 1e-12)
         q = ((y - py[0]) / (py[1] - py[0]) + (y - py[3]) / (py[2] - py[3])) * 0.5;
     else
-        q = (x - a0 - a2 * r) / den;
+        q = div_maybe_zero(x - a0 - a2 * r, den);
+    rx = q - 0.5;
+    ry = r - 0.5;
+}
+
+// (everything by value: an out-of-line call must not force the caller's arrays into local memory)
+static __device__ __noinline__ double2 inverse_bilinear_slow(double x, double y, double px0, double px1, double px2,
+                                                             double px3, double py0, double py1, double py2, double py3) {
+    const double px[4] = {px0, px1, px2, px3}, py[4] = {py0, py1, py2, py3};
+    double2 r;
+    inverse_bilinear(x, y, px, py, r.x, r.y);
+    return r;
+}
+
+// Same arithmetic with the branch-free helpers of fastmath.cuh; `bad` asks for inverse_bilinear_slow.
+__device__ __forceinline__ void inverse_bilinear_fast(double x, double y, const double pxi[4], const double py[4],
+                                                      double &rx, double &ry, bool &bad) {
+    const double x0 = pxi[0];
+    double px[4];
+    x = to_180_fast(x - x0, bad);
+    px[0] = 0.0;  // to_180(x0 - x0)
+#pragma unroll
+    for (int j = 1; j < 4; ++j) px[j] = to_180_fast(pxi[j] - x0, bad);
+    const double a0 = px[0], a1 = -px[0] + px[1], a2 = -px[0] + px[3];
+    const double a3 = ((px[0] - px[1]) + px[2]) - px[3];
+    const double b0 = py[0], b1 = -py[0] + py[1], b2 = -py[0] + py[3];
+    const double b3 = ((py[0] - py[1]) + py[2]) - py[3];
+    const double aa = a3 * b2 - a2 * b3;
+    const double bb = a3 * b0 - a0 * b3 + a1 * b2 - a2 * b1 + x * b3 - y * a3;
+    const double cc = a1 * b0 - a0 * b1 + x * b1 - y * a1;
+    const double det2 = bb * bb - 4 * aa * cc;
+    const bool order1 = fabs(aa) < 1e-12;
+    const bool order2 = !order1 && det2 >= 0;
+    bool b1_ = false, b2_ = false;
+    double r = -fdiv(cc, bb, b1_);
+    if (order2) r = (-bb + sqrt(det2)) / (2 * aa);  // curved cells only (polar cap)
+    const double den = a1 + a3 * r;
+    double q;
+    if (fabs(den) < 1e-12)  // cells whose x axis runs along a meridian (the rotated LLC faces)
+        q = (div_maybe_zero(y - py[0], py[1] - py[0]) + div_maybe_zero(y - py[3], py[2] - py[3])) * 0.5;
+    else
+        q = fdiv(x - a0 - a2 * r, den, b2_);
+    bad = bad || (!order2 && b1_) || b2_;
     rx = q - 0.5;
     ry = r - 0.5;
 }
@@ -193,10 +279,82 @@ __device__ __forceinline__ void wall_times(double u, double du, double x0, doubl
     if (open_l && open_r) tr = log(1 + k * dr) / du;  // diverging flow inside the cell: rare
 }
 
+// One copy of the per-axis code, called for x, y and z: the particle step has to stay inside the
+// SM's instruction cache (32 KB); with everything inlined three times the loop body was 43 KB and
+// instruction fetch the top stall reason (profiles/README.md, r01d).
+//
+// Exit times of one axis (_stationary_time utils.py:821 + the closed-wall rule of _time2wall :864-869), branch-free for the
+// usual case; operands the fast helpers cannot take fall back to wall_times above.
+// (x = time to the left wall, y = to the right wall, -sign(tf) = never; double2 comes back in
+// registers, a struct of two doubles would go through the stack)
+typedef double2 AxisTimes;
+static __device__ __noinline__ AxisTimes axis_wall_times(double u, double du, double x0, double sg) {
+    double tl, tr;
+    const double ul = u - (x0 + 0.5) * du;
+    const double ur = u + (0.5 - x0) * du;
+    const bool open_l = !(-ul * sg <= 1e-12);
+    const bool open_r = !(ur * sg <= 1e-12);
+    const bool lin = fabs(du) < 1e-12;
+    const double dl = -0.5 - x0, dr = 0.5 - x0;
+    bool bk = false, bl = false, bt = false;
+    const double k = fdiv(du, u, bk);
+    const double inv = rcp_refined(lin ? u : du);
+    const double den = lin ? u : du;
+    // left wall if it is open, else the right one
+    const double d1 = open_l ? dl : dr;
+    const double lg1 = flog(lin ? 1.0 : 1 + k * d1, bl);
+    const double t1 = div_with(lin ? d1 : lg1, den, inv, bt);
+    tl = open_l ? t1 : -sg;
+    tr = (open_r && !open_l) ? t1 : -sg;
+    bool redo = (open_l || open_r) && (bt || (!lin && (bk || bl)));
+    if (open_l && open_r) {  // diverging flow inside the cell: the right wall needs its own logarithm
+        const double lg2 = flog(lin ? 1.0 : 1 + k * dr, bl);
+        tr = div_with(lin ? dr : lg2, den, inv, bt);
+        redo = bt || (!lin && (bk || bl));
+    }
+    if (redo) wall_times(u, du, x0, sg, tl, tr);
+    return make_double2(tl, tr);
+}
+
+// The same for the usual case only (exactly one reachable wall), to be inlined three times so that
+// ptxas can interleave the axes; `redo` asks for axis_wall_times.
+__device__ __forceinline__ void wall_times_fast_inline(double u, double du, double x0, double sg, double &tl, double &tr,
+                                                       bool &redo) {
+    const double ul = u - (x0 + 0.5) * du;
+    const double ur = u + (0.5 - x0) * du;
+    const bool open_l = !(-ul * sg <= 1e-12);
+    const bool open_r = !(ur * sg <= 1e-12);
+    const bool lin = fabs(du) < 1e-12;
+    const double dsel = open_l ? -0.5 - x0 : 0.5 - x0;
+    bool bk = false, bl = false, bt = false;
+    const double k = fdiv(du, u, bk);
+    const double lg = flog(lin ? 1.0 : 1 + k * dsel, bl);
+    const double t1 = fdiv(lin ? dsel : lg, lin ? u : du, bt);
+    tl = open_l ? t1 : -sg;
+    tr = (open_r && !open_l) ? t1 : -sg;
+    redo = redo || (open_l && open_r) || ((open_l || open_r) && (bt || (!lin && (bk || bl))));
+}
+
 // reference _increment, utils.py:777
 __device__ __forceinline__ double increment(double t, double u, double du) {
     if (fabs(du) < 1e-12) return u * t;
     return u / du * (exp(du * t) - 1);
+}
+
+__device__ __forceinline__ double increment_fast_inline(double t, double u, double du, bool &redo) {
+    const bool lin = fabs(du) < 1e-12;
+    bool bq = false, be = false;
+    const double q = fdiv(u, du, bq);
+    const double e = fexp(du * t, be);
+    redo = redo || (!lin && (bq || be));
+    return lin ? u * t : q * (e - 1);
+}
+
+static __device__ __noinline__ double axis_increment(double t, double u, double du) {
+    bool redo = false;
+    double r = increment_fast_inline(t, u, du, redo);
+    if (redo) r = increment(t, u, du);
+    return r;
 }
 
 }  // namespace sdk

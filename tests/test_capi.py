@@ -38,14 +38,18 @@ def test_abi_version_and_error_path_without_gpu():
 
 
 def test_struct_sizes_match_header():
-    # 64-bit pointers, 4-byte ints: the ctypes mirrors must have the size the C compiler gives
-    assert ctypes.sizeof(_lib.GridDesc) == 12 * 4 + 15 * 8
-    assert ctypes.sizeof(_lib.Velocity) == 4 * 8 + 16 * 4
-    assert ctypes.sizeof(_lib.Particles) == 8 + 29 * 8
-    assert ctypes.sizeof(_lib.AdvectParams) == 2 * 8 + 6 * 4 + 8
-    assert ctypes.sizeof(_lib.Log) == 8 + 2 * 8 + 19 * 8 + 8
-    assert ctypes.sizeof(_lib.Located) == 30 * 8
-    assert ctypes.sizeof(_lib.TrackIO) == 8 + 13 * 8
+    """The ctypes mirrors have exactly the size the C compiler gave the structures."""
+    from seaduck_b200 import interp
+
+    L = _lib.lib()
+    L.sdk_struct_size.restype = ctypes.c_int64
+    mirrors = [
+        _lib.GridDesc, _lib.Velocity, _lib.Particles, _lib.AdvectParams, _lib.Log, _lib.Located, _lib.TrackIO,
+        interp.KernelDesc, interp.Field, interp.Points,
+    ]
+    for which, cls in enumerate(mirrors):
+        assert ctypes.sizeof(cls) == L.sdk_struct_size(which), cls.__name__
+    assert L.sdk_struct_size(99) == -1
 
 
 def test_missing_library_fails_loudly(monkeypatch):
