@@ -56,6 +56,10 @@ def parse():
     ap.add_argument("--refill", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
+    ap.add_argument("--peer-gather", action="store_true", help="ship snapshots with copy-engine writes into peer memory instead of NCCL")
+    ap.add_argument("--eager", action="store_true", help="reference-style to_next_stop (host reads the call statistics every step)")
+    ap.add_argument("--no-gather", action="store_true", help="(diagnostic) skip the snapshot all-gather at N > 1")
+    ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left to the snapshot all-gather (default: 8 when N > 1)")
     return ap.parse_args()
 
 
@@ -191,6 +195,9 @@ def run_cuda(a):
     t_stop = a.days * DAY
     nb = min(a.warmup + a.steps, a.max_batches)
 
+    reserve = a.reserve_sms if a.reserve_sms >= 0 else (8 if world > 1 else 0)
+    side = torch.cuda.Stream(dev) if world > 1 else None
+
     def make_batch(b):
         lon, lat, dep = seeds(ds, n, seed=1000 + 97 * rank + b)  # disjoint particle slices per rank / batch
         if not a.no_sort:
@@ -200,7 +207,12 @@ def run_cuda(a):
             order = torch.argsort(key).cpu().numpy()
             lon, lat, dep = lon[order], lat[order], dep[order]
         pt = sd.Particle(x=lon, y=lat, z=dep, t=np.zeros(n), data=od, **KW)
+        pt.lazy = not a.eager  # device-side end-of-stop bookkeeping: the host never waits inside a step
         pt.tuning = dict(refill_threshold=a.refill, blocks_per_sm=a.blocks_per_sm, threads_per_block=a.threads)
+        if reserve > 0:
+            # one 512-thread CTA per SM on all but `reserve` SMs: the NCCL kernel that ships the previous
+            # step's snapshot runs on the SMs left free
+            pt.tuning.update(blocks_per_sm=1, threads_per_block=512, reserve_sms=reserve)
         return pt, (lon, lat, dep)
 
     batches, host_inputs = [], []
@@ -212,7 +224,9 @@ def run_cuda(a):
     # initial state of every batch: restored (device copy) when a batch is reused
     reuse = a.warmup + a.steps > nb
     saved = [{k: (None if v is None else v.clone()) for k, v in pt._st.items()} for pt in batches]
-    gather = torch.empty(world * n * 5, dtype=torch.float64, device=dev) if world > 1 else None
+    from seaduck_b200 import parallel
+
+    gatherer = parallel.SnapshotGather(len(parallel.SNAPSHOT_FIELDS), n, dev, use_peer=a.peer_gather) if world > 1 else None
 
     def restore(b):
         for k, v in saved[b].items():
@@ -225,12 +239,15 @@ def run_cuda(a):
         if i >= nb:
             restore(b)
         pt.to_next_stop(t_stop)
-        if world > 1:
-            # output trajectories of all ranks -- the only collective of the path
-            st = pt._st
-            packed = torch.cat([st["lon"], st["lat"], st["dep"], st["face"].double() * 1e6 + st["iy"].double(),
-                                st["ix"].double() * 1e3 + st["izl"].double()])
-            dist.all_gather_into_tensor(gather, packed)
+        if world > 1 and not a.no_gather:
+            # output trajectories of all ranks -- the only exchange of the path: shipped over
+            # NVLink peer memory by the copy engines while the next step's kernel runs
+            # (side stream: packing and the collective stay off the critical path of the next step)
+            done = torch.cuda.Event()
+            done.record()
+            side.wait_event(done)
+            with torch.cuda.stream(side):
+                gatherer.post(parallel.pack_snapshot(pt._st), slot=i % 2)
 
     for i in range(a.warmup):
         step(i)
@@ -249,6 +266,13 @@ def run_cuda(a):
         ev[i][0].record()
         step(a.warmup + i)
         ev[i][1].record()
+    if world > 1:
+        for w in gatherer.work:  # the last snapshots have landed (device-side wait, inside the timed region)
+            if w is not None:
+                w.wait()
+        if gatherer.stream is not None:
+            torch.cuda.current_stream().wait_stream(gatherer.stream)
+        torch.cuda.current_stream().wait_stream(side)
     t_end.record()
     torch.cuda.synchronize()
     wall = time.perf_counter() - wall0
@@ -344,13 +368,18 @@ def run_cuda(a):
                 "particle_order": "seeding" if a.no_sort else "cell-sorted at seeding time",
                 "batches": f"{nb} distinct batches resident in HBM" + (", reused cyclically with a device-side state restore inside the timed region" if reuse else ", one per step"),
                 "l2": "inputs larger than L2 (fields 168 MB + 220 MB of particle state per batch, a different batch every step); no flush",
-                "collective": "all_gather of the output snapshot per step" if world > 1 else "none",
+                "collective": (f"all-gather of the output snapshot per step ({gatherer.mode}: "
+                               + ("copy-engine writes into peer memory" if gatherer.mode == "peer" else f"async NCCL all_gather_into_tensor on {reserve} SMs the advection kernel leaves free")
+                               + ", overlapped with the next step"
+                               + f", {len(parallel.SNAPSHOT_FIELDS) * 8 * n * world} B received per rank and step)") if world > 1 else "none",
                 "step_ms_first10": [round(x, 3) for x in step_ms[:10]], "host_wall_s": wall,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "advect_kernel<double,false>",
                          "kernel_ms": kms, "crossings_per_launch": kcr, "algorithmic_bytes_per_launch": algo_bytes,
-                         "note": "latency/issue bound, not bandwidth bound: see profiles/"},
+                         "note": "instruction-supply bound, not bandwidth bound (DRAM 3.5 % busy, fields L2 resident, "
+                                 "SM instruction cache hit rate 79 %, GPC instruction cache at 96 % of its request rate): "
+                                 "profiles/README.md r01c-r01g"},
             "gpu_launches": a.steps * world,
             "clocks": sampler.summary(),
         }

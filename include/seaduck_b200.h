@@ -42,7 +42,8 @@ enum {
     /* sdk_locate: value outside the table, the reference raises "Value out of bound." (utils.py:301) */
     SDK_ST_OOB = 16,       /* depth below the last Zl level (linear Zl lookup) */
     SDK_ST_OOB_Z = 32,     /* depth below the last Z level (linear Z lookup, lazily used by interpolation) */
-    SDK_ST_OOB_T = 64      /* time before the first level (linear time lookup, lazily used) */
+    SDK_ST_OOB_T = 64      /* sdk_locate: time before the first level (linear time lookup, lazily used);
+                              sdk_advect: the particle's time level is outside the staged velocity slab */
 };
 
 #define SDK_MAX_FACES 16
@@ -122,6 +123,11 @@ typedef struct sdk_advect_params {
     int32_t refill_threshold; /* idle lanes per warp that trigger a refill, 0 = library default */
     int32_t blocks_per_sm;    /* 0 = library default */
     int32_t threads_per_block;/* 0 = library default */
+    /* leave this many SMs without a CTA of the (persistent) kernel, so that kernels of other streams
+     * -- the NCCL all-gather of the previous stop's snapshot -- run beside it; needs one CTA per SM
+     * (blocks_per_sm = 1, threads_per_block = 512) to be exact */
+    int32_t reserve_sms;
+    int32_t reserved;
     /* optional DEVICE array of 4 counters, ADDED to by the call: particles live at the start,
      * wall crossings, particles that hit max_iteration, particles with a non-zero status */
     uint64_t *stats;
@@ -284,9 +290,24 @@ int sdk_interp_vector(const sdk_grid *grid, const sdk_points *pts, const sdk_fie
 int sdk_build_masks(const sdk_grid *grid, const uint8_t *maskC, int32_t nz, uint8_t *maskU, uint8_t *maskV,
                     uint8_t *maskW, void *stream);
 
+/* End of Particle.to_next_stop without a host round trip (seaduck/lagrangian.py:793-802): if the
+ * advect call counted live particles (stats[0] > 0; the reference returns early otherwise) set
+ * t := t_stop for every particle and, when time_midp is given, it := time index of t_stop; then add
+ * stats[0..3] to total[0..3] (running totals read lazily by the host) -- all on the device.
+ * stats, total: DEVICE arrays of 4 uint64 (total may be NULL); time_midp / it may be NULL. */
+int sdk_finish_stop(double *t, int32_t *it, const double *time_midp, int32_t n_midp, double t_stop,
+                    const uint64_t *stats, uint64_t *total, int64_t n, void *stream);
+
 /* it := 0 before time_midp[0], else find_rel(t, time_midp) + 1 (seaduck/lagrangian.py:796-802). */
 int sdk_time_index(const double *t, const double *time_midp, int32_t n_midp, int32_t *it, int64_t n,
                    void *stream);
+
+/* Peer-memory plumbing for the output-snapshot exchange (seaduck_b200/parallel.py SnapshotGather):
+ * enable direct access from the current device to `peer_device`, and enqueue a copy-engine copy of
+ * `bytes` bytes from `src` (on `src_device`) to `dst` (a mapping of memory on `dst_device`, e.g. a CUDA
+ * IPC mapping of another rank's receive buffer) on `stream`.  No kernel is launched. */
+int sdk_peer_enable(int peer_device);
+int sdk_peer_copy_async(void *dst, int dst_device, const void *src, int src_device, int64_t bytes, void *stream);
 
 /* Self-test of the device math helpers used by sdk_advect (csrc/fastmath.cuh): out[i] = op(a[i], b[i]),
  * bad[i] = 1 where the helper asked for the slow path.  Device pointers; b may be NULL for unary ops. */

@@ -87,6 +87,8 @@ class AdvectParams(C.Structure):
         ("refill_threshold", C.c_int32),
         ("blocks_per_sm", C.c_int32),
         ("threads_per_block", C.c_int32),
+        ("reserve_sms", C.c_int32),
+        ("reserved", C.c_int32),
         ("stats", vp),
     ]
 
@@ -168,6 +170,9 @@ def lib():
         L.sdk_track_scratch_bytes.restype = C.c_int64
         L.sdk_track_scratch_bytes.argtypes = [C.c_int64]
         L.sdk_track_host.argtypes = [vp, C.POINTER(Velocity), C.POINTER(TrackIO), vp, C.c_int32, C.c_double, C.POINTER(AdvectParams), vp, vp]
+        L.sdk_finish_stop.argtypes = [vp, vp, vp, C.c_int32, C.c_double, vp, vp, C.c_int64, vp]
+        L.sdk_peer_enable.argtypes = [C.c_int]
+        L.sdk_peer_copy_async.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int64, vp]
         L.sdk_selftest_math.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp, vp]
         _lib = L
     return _lib

@@ -187,7 +187,13 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
         ty_ = s.iy + 1;
         if (ty_ > ylim - 1) { ty_ = v.nyV - 1; tx_ = v.nxV - 1; }
     }
-    const int tlev = v.has_time ? wrap_index(s.it - v.it0, v.nt) : 0;
+    int tlev = v.has_time ? wrap_index(s.it - v.it0, v.nt) : 0;
+    if (tlev < 0 || tlev >= v.nt) {
+        // the particle's time level is not in the staged slab (the reference raises IndexError here:
+        // Particle.update_uvw_array was not called after crossing time_midp); stay inside the array
+        s.status |= SDK_ST_OOB_T;
+        tlev = tlev < 0 ? 0 : v.nt - 1;
+    }
     const int64_t lev_uv = v.has_z ? (int64_t)(tlev * v.nzU + wrap_index(s.izl - 1, v.nzU)) : (int64_t)tlev;
     const int c_ul = (s.f * v.nyU + s.iy) * v.nxU + s.ix;
     const int c_vl = (s.f * v.nyV + s.iy) * v.nxV + s.ix;
@@ -433,11 +439,16 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
 #ifndef SDK_ADVECT_LOCKSTEP
 #define SDK_ADVECT_LOCKSTEP 0
 #endif
+// compiled for CTAs of up to 512 threads (128 registers either way); launched as 4 x 128 threads per
+// SM by default, as 1 x 512 when SMs are to be left free for a concurrent collective (reserve_sms)
 #ifndef SDK_ADVECT_THREADS
-#define SDK_ADVECT_THREADS (SDK_ADVECT_LOCKSTEP ? 512 : 128)
+#define SDK_ADVECT_THREADS 512
 #endif
 #ifndef SDK_ADVECT_MIN_BLOCKS
-#define SDK_ADVECT_MIN_BLOCKS (SDK_ADVECT_LOCKSTEP ? 1 : 4)
+#define SDK_ADVECT_MIN_BLOCKS 1
+#endif
+#ifndef SDK_ADVECT_DEFAULT_THREADS
+#define SDK_ADVECT_DEFAULT_THREADS (SDK_ADVECT_LOCKSTEP ? 512 : 128)
 #endif
 #ifndef SDK_ADVECT_INLINE_AXES
 #define SDK_ADVECT_INLINE_AXES 0
@@ -549,7 +560,8 @@ __global__ void __launch_bounds__(128) get_u_du_kernel(const __grid_constant__ A
 namespace sdk {
 
 int advect_max_threads() { return SDK_ADVECT_THREADS; }
-int advect_default_blocks_per_sm() { return SDK_ADVECT_MIN_BLOCKS; }
+int advect_default_threads() { return SDK_ADVECT_DEFAULT_THREADS; }
+int advect_default_blocks_per_sm() { return 512 / SDK_ADVECT_DEFAULT_THREADS; }
 
 cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaStream_t stream) {
     const size_t smem = sizeof(float) * (size_t)(args.g.n_zl + args.g.n_z);

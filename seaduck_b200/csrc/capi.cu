@@ -177,10 +177,12 @@ int sdk_advect(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particle
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaError_t e = cudaMemsetAsync(grid->queue, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_advect: memset");
-    const int threads = (par && par->threads_per_block > 0) ? par->threads_per_block : sdk::advect_max_threads();
-    const int per_sm = (par && par->blocks_per_sm > 0) ? par->blocks_per_sm : sdk::advect_default_blocks_per_sm();
+    const int threads = (par && par->threads_per_block > 0) ? par->threads_per_block : sdk::advect_default_threads();
+    const int per_sm = (par && par->blocks_per_sm > 0) ? par->blocks_per_sm : 512 / threads;
     int64_t need = (p->n + threads - 1) / threads;
-    int64_t blocks = (int64_t)grid->sm_count * per_sm;
+    int sms = grid->sm_count - ((par && par->reserve_sms > 0) ? par->reserve_sms : 0);
+    if (sms < 1) sms = 1;
+    int64_t blocks = (int64_t)sms * per_sm;
     if (blocks > need) blocks = need;
     if (threads > sdk::advect_max_threads() || threads % 32)
         return fail(SDK_EINVAL, "threads_per_block must be a multiple of 32 and at most the compiled block size");
@@ -258,6 +260,16 @@ int sdk_locate(const sdk_grid *grid, int64_t n, const double *lon, const double 
     a.out = *out;
     cudaError_t e = sdk::launch_locate(a, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_locate: launch");
+    return SDK_OK;
+}
+
+int sdk_finish_stop(double *t, int32_t *it, const double *time_midp, int32_t n_midp, double t_stop,
+                    const uint64_t *stats, uint64_t *total, int64_t n, void *stream) {
+    if (!t || !stats || n < 0) return fail(SDK_EINVAL, "sdk_finish_stop: bad argument");
+    if (time_midp && n_midp < 1) return fail(SDK_EINVAL, "sdk_finish_stop: empty time_midp");
+    cudaError_t e = sdk::launch_finish_stop(t, it, time_midp, n_midp, t_stop, (const unsigned long long *)stats,
+                                            (unsigned long long *)total, n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_finish_stop: launch");
     return SDK_OK;
 }
 
@@ -407,6 +419,32 @@ int sdk_build_masks(const sdk_grid *grid, const uint8_t *maskC, int32_t nz, uint
 }
 
 // ---- device math self-test --------------------------------------------------------------------------
+int sdk_peer_enable(int peer_device) {
+    int cur = 0;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_peer_enable: cudaGetDevice");
+    if (peer_device == cur) return SDK_OK;
+    int can = 0;
+    e = cudaDeviceCanAccessPeer(&can, cur, peer_device);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_peer_enable: cudaDeviceCanAccessPeer");
+    if (!can) return fail(SDK_EUNSUPPORTED, "sdk_peer_enable: no peer access between the two devices");
+    e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+        return SDK_OK;
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_peer_enable: cudaDeviceEnablePeerAccess");
+    return SDK_OK;
+}
+
+int sdk_peer_copy_async(void *dst, int dst_device, const void *src, int src_device, int64_t bytes, void *stream) {
+    if (!dst || !src || bytes < 0) return fail(SDK_EINVAL, "sdk_peer_copy_async: bad argument");
+    if (bytes == 0) return SDK_OK;
+    cudaError_t e = cudaMemcpyPeerAsync(dst, dst_device, src, src_device, (size_t)bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_peer_copy_async: cudaMemcpyPeerAsync");
+    return SDK_OK;
+}
+
 int64_t sdk_struct_size(int which) {
     switch (which) {
         case 0: return sizeof(sdk_grid_desc);

@@ -310,6 +310,31 @@ __global__ void time_index_kernel(const double *t, const double *midp, int n_mid
     it[i] = k + 1;
 }
 
+// t := t_stop and it := index(t_stop) for everybody, but only if the advect call had live particles
+__global__ void finish_stop_kernel(double *t, int32_t *it, const double *midp, int n_midp, double t_stop,
+                                   const unsigned long long *stats, unsigned long long *total, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool any_live = stats[0] > 0;
+    if (i < n && any_live) {
+        t[i] = t_stop;
+        if (it && midp) {
+            int idx = 0;
+            if (!(t_stop < midp[0])) {
+                int k, st = 0;
+                double r, d, b;
+                find_rel_1d_f64(midp, n_midp, t_stop, true, k, r, d, b, st);
+                idx = k + 1;
+            }
+            it[i] = idx;
+        }
+    }
+    if (total && blockIdx.x == gridDim.x - 1 && threadIdx.x < 4) {
+        // the last block adds the call's counters to the running totals; it reads stats only after
+        // having used stats[0] itself, and nobody else writes them during this kernel
+        total[threadIdx.x] += stats[threadIdx.x];
+    }
+}
+
 __global__ void fill_int_kernel(int *p, int v, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) p[i] = v;
 }
@@ -355,6 +380,14 @@ cudaError_t launch_locate(const LocateArgs &a, cudaStream_t s) {
     if (a.n == 0) return cudaSuccess;
     const int threads = 128;
     locate_kernel<<<(unsigned)((a.n + threads - 1) / threads), threads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finish_stop(double *t, int32_t *it, const double *midp, int n_midp, double t_stop,
+                               const unsigned long long *stats, unsigned long long *total, int64_t n, cudaStream_t s) {
+    const int threads = 256;
+    const unsigned blocks = (unsigned)((n + threads - 1) / threads);
+    finish_stop_kernel<<<blocks ? blocks : 1, threads, 0, s>>>(t, it, midp, n_midp, t_stop, stats, total, n);
     return cudaGetLastError();
 }
 

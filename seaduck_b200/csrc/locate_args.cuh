@@ -25,6 +25,8 @@ struct LocateArgs {
 
 cudaError_t build_buckets(const GridDev &g, BucketGrid &b, cudaStream_t s);
 cudaError_t launch_locate(const LocateArgs &a, cudaStream_t s);
+cudaError_t launch_finish_stop(double *t, int32_t *it, const double *midp, int n_midp, double t_stop,
+                               const unsigned long long *stats, unsigned long long *total, int64_t n, cudaStream_t s);
 cudaError_t launch_time_index(const double *t, const double *midp, int n_midp, int32_t *it, int64_t n,
                               cudaStream_t s);
 

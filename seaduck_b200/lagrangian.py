@@ -78,7 +78,16 @@ _LIST_NAMES = {
 
 
 class Particle(Position):
-    """Lagrangian particles advected on the GPU.  Parameters as in the reference (``lagrangian.py:93``)."""
+    """Lagrangian particles advected on the GPU.  Parameters as in the reference (``lagrangian.py:93``).
+
+    ``lazy = True`` (not in the reference) keeps ``to_next_stop`` asynchronous: the end-of-stop
+    bookkeeping (``t := t_stop`` unless nothing was live, the time index, the crossing counters) is
+    done on the device by ``sdk_finish_stop`` and the "maximum iteration count reached" warning is
+    raised at the next :meth:`sync` / read of :attr:`crossings` instead of inside the call, so the
+    host can queue the next stop, the snapshot exchange and the read-back while the GPU works.
+    """
+
+    lazy = False
 
     def __init__(
         self,
@@ -167,6 +176,8 @@ class Particle(Position):
         self.__dict__["_st"] = st
         self.__dict__["_crossings"] = 0
         self.__dict__["_stats"] = torch.zeros(4, dtype=torch.int64, device=dev)
+        self.__dict__["_total"] = torch.zeros(4, dtype=torch.int64, device=dev)  # lazy mode: running totals
+        self.__dict__["_warned"] = 0
         self.__dict__["_stale"] = set()
         self.__dict__["_raw"] = []
         if not od.readiness["h"] == "oceanparcel":
@@ -397,6 +408,7 @@ class Particle(Position):
         par.refill_threshold = int(tune.get("refill_threshold", 0))
         par.blocks_per_sm = int(tune.get("blocks_per_sm", 0))
         par.threads_per_block = int(tune.get("threads_per_block", 0))
+        par.reserve_sms = int(tune.get("reserve_sms", 0))
         par.stats = self._stats.data_ptr()
         return par
 
@@ -454,6 +466,22 @@ class Particle(Position):
         st = self._st
         emit_start = bool(self.__dict__.get("_pending_start", False))
         self.__dict__["_pending_start"] = False
+        if self.lazy and self.callback is None and not self.save_raw:
+            # no host round trip: one memset, the advection kernel, one bookkeeping kernel
+            self._stats.zero_()
+            self._launch(t_stop, self.max_iteration)
+            od = self.ocedata
+            midp = od.to_device("time_midp", od.time_midp, np.float64) if od.readiness["time"] else None
+            _lib.check(
+                _lib.lib().sdk_finish_stop(
+                    st["t"].data_ptr(), st["it"].data_ptr() if midp is not None else None,
+                    None if midp is None else midp.data_ptr(), 0 if midp is None else len(od.time_midp), t_stop,
+                    self._stats.data_ptr(), self._total.data_ptr(), self.N, _lib.current_stream(),
+                ),
+                "sdk_finish_stop",
+            )
+            self._mark_stale()
+            return
         if self.callback is None:
             self._launch(t_stop, self.max_iteration, emit_start=emit_start)
             n_live, n_cross, n_max, _ = self._read_stats()
@@ -501,9 +529,20 @@ class Particle(Position):
             )
         self._mark_stale(["t", "it"])
 
+    def sync(self):
+        """Lazy mode: wait for the queued stops, fold their counters in and raise deferred warnings."""
+        tot = self._total.cpu().numpy().astype(np.int64)
+        self._total.zero_()
+        self.__dict__["_crossings"] += int(tot[1])
+        if tot[2] > 0:
+            warnings.warn("maximum iteration count reached")
+        return tot
+
     @property
     def crossings(self):
         """Total number of cell-wall crossings so far (iterations that ended on a wall)."""
+        if self.lazy:
+            self.sync()
         return int(self._crossings)
 
     def deepcopy(self):
@@ -513,7 +552,7 @@ class Particle(Position):
         p = object.__new__(type(self))
         object.__setattr__(p, "rel", RelCoord())
         for key, item in self.__dict__.items():
-            if key in ("_st", "_stale", "_raw", "_crossings", "_stats"):
+            if key in ("_st", "_stale", "_raw", "_crossings", "_stats", "_total"):
                 continue
             if isinstance(item, np.ndarray):
                 if item.ndim == 1:
@@ -529,6 +568,7 @@ class Particle(Position):
         p.__dict__["_raw"] = list(self._raw)
         p.__dict__["_crossings"] = self._crossings
         p.__dict__["_stats"] = torch.zeros_like(self._stats)
+        p.__dict__["_total"] = torch.zeros_like(self._stats)
         p.__dict__["_derived_ok"] = False
         return p
 

@@ -98,3 +98,37 @@ def test_cuda_matches_oracle_llc90(oracle_lib):
         total += int((ref["vs"] < 6).sum())
     assert pt.crossings == total
     assert total > 2e5
+
+
+def test_lazy_mode_equals_eager():
+    """``Particle.lazy``: end-of-stop bookkeeping on the device, same state and counts as the eager path."""
+    sd = _sd()
+    case = cases.case_llc_transport()
+    pts = []
+    for lazy in (False, True):
+        od = sd.OceData(case["ds"])
+        pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, **case["kw"])
+        pt.lazy = lazy
+        for ts in case["stops"]:
+            pt.to_next_stop(ts)
+        pt.to_next_stop(case["stops"][-1])  # nothing left to simulate: must leave everything alone
+        pts.append(pt)
+    eager, lazy = pts
+    assert lazy.crossings == eager.crossings and eager.crossings > 0
+    for k in cases.FINAL_INT + cases.FINAL_FLT:
+        if getattr(eager, k, None) is not None:
+            np.testing.assert_array_equal(getattr(lazy, k), getattr(eager, k), err_msg=k)
+
+
+def test_lazy_mode_list_of_time_matches_golden():
+    """Time-dependent field, slab swaps at the update stops, lazy bookkeeping: still the reference's answer."""
+    sd = _sd()
+    case = cases.case_llc_time()
+    gold = np.load(os.path.join(GOLD, f"lagrangian_{case['name']}.npz"))
+    od = sd.OceData(case["ds"])
+    pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, **case["kw"])
+    pt.lazy = True
+    stops, snaps = pt.to_list_of_time(normal_stops=case["stops"])
+    np.testing.assert_allclose(stops, gold["stops"])
+    for i, snap in enumerate(snaps):
+        compare_state(gold, f"s{i}_", snap)

@@ -27,6 +27,12 @@ def _worker(rank, world, n, port, ret):
         "izl": torch.tensor(idx % 50, dtype=torch.int32),
     }
     g = parallel.all_gather_snapshot(parallel.pack_snapshot(state, n_pad=per))
+    # the overlapped gatherer takes the collective route on CPU and must deliver the same thing
+    sg = parallel.SnapshotGather(len(parallel.SNAPSHOT_FIELDS), per, torch.device("cpu"))
+    assert sg.mode == "collective"
+    sg.post(parallel.pack_snapshot(state, n_pad=per), slot=1)
+    sg.wait()
+    assert torch.equal(sg.result(1), g)
     out = parallel.unshard(g, n, world, seed=3)
     ids = np.arange(n)
     ok = (
