@@ -226,7 +226,7 @@ def run_cuda(a):
     saved = [{k: (None if v is None else v.clone()) for k, v in pt._st.items()} for pt in batches]
     from seaduck_b200 import parallel
 
-    gatherer = parallel.SnapshotGather(len(parallel.SNAPSHOT_FIELDS), n, dev, use_peer=a.peer_gather) if world > 1 else None
+    gatherer = parallel.SnapshotGather(parallel.SNAPSHOT_ROWS, n, dev, use_peer=a.peer_gather) if world > 1 else None
 
     def restore(b):
         for k, v in saved[b].items():
@@ -371,7 +371,7 @@ def run_cuda(a):
                 "collective": (f"all-gather of the output snapshot per step ({gatherer.mode}: "
                                + ("copy-engine writes into peer memory" if gatherer.mode == "peer" else f"async NCCL all_gather_into_tensor on {reserve} SMs the advection kernel leaves free")
                                + ", overlapped with the next step"
-                               + f", {len(parallel.SNAPSHOT_FIELDS) * 8 * n * world} B received per rank and step)") if world > 1 else "none",
+                               + f", {parallel.SNAPSHOT_ROWS * 8 * n * world} B received per rank and step)") if world > 1 else "none",
                 "step_ms_first10": [round(x, 3) for x in step_ms[:10]], "host_wall_s": wall,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

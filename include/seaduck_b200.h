@@ -302,6 +302,13 @@ int sdk_finish_stop(double *t, int32_t *it, const double *time_midp, int32_t n_m
 int sdk_time_index(const double *t, const double *time_midp, int32_t n_midp, int32_t *it, int64_t n,
                    void *stream);
 
+/* Output snapshot of a stop in 40 bytes per particle (what Particle.to_list_of_time returns per stop
+ * and the ranks exchange): out[0..2][n_pad] = lon, lat, dep; out[3] = (face, iy) and
+ * out[4] = (ix, izl) as pairs of int32 in one 8-byte slot.  NULL inputs read as zero; device pointers. */
+int sdk_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
+                      const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl, double *out,
+                      void *stream);
+
 /* Peer-memory plumbing for the output-snapshot exchange (seaduck_b200/parallel.py SnapshotGather):
  * enable direct access from the current device to `peer_device`, and enqueue a copy-engine copy of
  * `bytes` bytes from `src` (on `src_device`) to `dst` (a mapping of memory on `dst_device`, e.g. a CUDA

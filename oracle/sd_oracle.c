@@ -806,6 +806,57 @@ static void *worker(void *arg) {
     return NULL;
 }
 
+/* Position._fatten_h, eulerian.py:386: the index of every kernel node (kx, ky) of every point --
+ * naive offset, and a topology walk (ind_moves with the moves of _translate_to_tendency,
+ * kernel_weight.py:46) where the naive index is illegal.  Output arrays are n*m; oerr[j*m+i] is the
+ * ORA_* code of the walk (the reference raises there and aborts the whole call). */
+int ora_fatten_h(const ora_grid *g, int64_t n, const int32_t *face, const int32_t *iy, const int32_t *ix, int m,
+                 const int32_t *kx, const int32_t *ky, char cuvwg, int32_t *of, int32_t *oy, int32_t *ox,
+                 int32_t *oerr) {
+    for (int64_t j = 0; j < n; ++j) {
+        for (int i = 0; i < m; ++i) {
+            const int64_t o = j * m + i;
+            int32_t ind[3] = {g->has_face ? face[j] : 0, iy[j] + ky[i], ix[j] + kx[i]};
+            oerr[o] = ORA_OK;
+            if (!illegal(g, ind, cuvwg == 'C' ? 'C' : 'G')) {
+                of[o] = ind[0];
+                oy[o] = ind[1];
+                ox[o] = ind[2];
+                continue;
+            }
+            int moves[32], nm = 0;
+            const int x = kx[i], y = ky[i];
+            for (int k = 0; k < (y > 0 ? y : -y) && nm < 32; ++k) moves[nm++] = y > 0 ? 0 : 1;
+            for (int k = 0; k < (x > 0 ? x : -x) && nm < 32; ++k) moves[nm++] = x < 0 ? 2 : 3;
+            const int32_t start[3] = {g->has_face ? face[j] : 0, iy[j], ix[j]};
+            int32_t out[3] = {start[0], start[1], start[2]};
+            oerr[o] = ora_ind_moves(g, start, moves, nm, cuvwg, out);
+            of[o] = out[0];
+            oy[o] = out[1];
+            ox[o] = out[2];
+        }
+    }
+    return ORA_OK;
+}
+
+/* Topology.four_matrix_for_uv, topology.py:689, rounded as in eulerian.py:934-937: for an (n, m) array
+ * of faces (node 0 is the reference) the four coefficients UfromU, UfromV, VfromU, VfromV. */
+int ora_four_matrix_for_uv(const ora_grid *g, int64_t n, int m, const int32_t *faces, double *ufu, double *ufv,
+                           double *vfu, double *vfv, int32_t *oerr) {
+    for (int64_t j = 0; j < n; ++j) {
+        for (int i = 0; i < m; ++i) {
+            double c[4];
+            const int64_t o = j * m + i;
+            oerr[o] = uv_rotation(g, faces[j * m], faces[o], c);
+            ufu[o] = c[0];
+            ufv[o] = c[1];
+            vfu[o] = c[2];
+            vfv[o] = c[3];
+        }
+    }
+    return ORA_OK;
+}
+
 int ora_advect(const ora_grid *g, const ora_vel *vel, ora_particles *p, double t_stop,
                const ora_params *par, ora_log *log) {
     if (g->hmode != ORA_H_OCEANPARCEL) return -1;

@@ -95,6 +95,11 @@ int ora_advect(const ora_grid *g, const ora_vel *vel, ora_particles *p, double t
 int ora_ind_tend(const ora_grid *g, const int32_t ind[3], int tend, char cuvwg, int32_t out[3]);
 int ora_ind_moves(const ora_grid *g, const int32_t ind[3], const int *moves, int nmoves, char cuvwg,
                   int32_t out[3]);
+int ora_fatten_h(const ora_grid *g, int64_t n, const int32_t *face, const int32_t *iy, const int32_t *ix, int m,
+                 const int32_t *kx, const int32_t *ky, char cuvwg, int32_t *of, int32_t *oy, int32_t *ox,
+                 int32_t *oerr);
+int ora_four_matrix_for_uv(const ora_grid *g, int64_t n, int m, const int32_t *faces, double *ufu, double *ufv,
+                           double *vfu, double *vfv, int32_t *oerr);
 int ora_corners(const ora_grid *g, const int32_t ind[3], int32_t out[4][3]);
 void ora_get_u_du(const ora_grid *g, const ora_vel *vel, ora_particles *p, int64_t i, int has_dep);
 void ora_analytic(const double x0[3], const double u[3], const double du[3], double tf, int *tend,

@@ -13,6 +13,9 @@
 #include "locate_args.cuh"
 
 namespace sdk {
+cudaError_t launch_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
+                                 const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl, double *out,
+                                 cudaStream_t s);
 cudaError_t launch_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad,
                                  cudaStream_t s);
 }
@@ -419,6 +422,15 @@ int sdk_build_masks(const sdk_grid *grid, const uint8_t *maskC, int32_t nz, uint
 }
 
 // ---- device math self-test --------------------------------------------------------------------------
+int sdk_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
+                      const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl, double *out,
+                      void *stream) {
+    if (n < 0 || n_pad < n || (n_pad > 0 && !out)) return fail(SDK_EINVAL, "sdk_pack_snapshot: bad argument");
+    cudaError_t e = sdk::launch_pack_snapshot(n, n_pad, lon, lat, dep, face, iy, ix, izl, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_pack_snapshot: launch");
+    return SDK_OK;
+}
+
 int sdk_peer_enable(int peer_device) {
     int cur = 0;
     cudaError_t e = cudaGetDevice(&cur);

@@ -22,6 +22,32 @@ __global__ void selftest_math_kernel(int op, int64_t n, const double *a, const d
     bad[i] = flag;
 }
 
+__global__ void pack_snapshot_kernel(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
+                                     const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl,
+                                     double *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    const bool in = i < n;
+    out[i] = in && lon ? lon[i] : 0.0;
+    out[n_pad + i] = in && lat ? lat[i] : 0.0;
+    out[2 * n_pad + i] = in && dep ? dep[i] : 0.0;
+    int2 a, b;
+    a.x = in && face ? face[i] : 0;
+    a.y = in && iy ? iy[i] : 0;
+    b.x = in && ix ? ix[i] : 0;
+    b.y = in && izl ? izl[i] : 0;
+    reinterpret_cast<int2 *>(out + 3 * n_pad)[i] = a;
+    reinterpret_cast<int2 *>(out + 4 * n_pad)[i] = b;
+}
+
+cudaError_t launch_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
+                                 const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl, double *out,
+                                 cudaStream_t s) {
+    if (n_pad == 0) return cudaSuccess;
+    pack_snapshot_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, s>>>(n, n_pad, lon, lat, dep, face, iy, ix, izl, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad,
                                  cudaStream_t s) {
     if (n == 0) return cudaSuccess;

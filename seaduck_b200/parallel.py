@@ -25,17 +25,48 @@ def shard_indices(n, world, rank, seed=0):
     return perm[rank * per : min((rank + 1) * per, n)]
 
 
+SNAPSHOT_ROWS = 5  # lon, lat, dep, (face, iy), (ix, izl): 40 bytes per particle
+
+
 def pack_snapshot(state, n_pad=None):
-    """One contiguous float64 tensor [7, n] from a particle state dict (ints are exact in fp64)."""
+    """One contiguous float64 tensor [5, n_pad] from a particle state dict: positions as they are, the
+    four indices as two pairs of int32 sharing an 8-byte slot (one ``sdk_pack_snapshot`` launch on the
+    GPU; plain torch ops for host tensors)."""
     import torch
 
     n = state["lon"].shape[0]
     n_pad = n if n_pad is None else n_pad
-    out = torch.zeros((len(SNAPSHOT_FIELDS), n_pad), dtype=torch.float64, device=state["lon"].device)
-    for k, name in enumerate(SNAPSHOT_FIELDS):
-        v = state.get(name)
-        if v is not None:
-            out[k, :n] = v.to(torch.float64)
+    dev = state["lon"].device
+    out = torch.empty((SNAPSHOT_ROWS, n_pad), dtype=torch.float64, device=dev)
+    if dev.type == "cuda":
+        from . import _lib
+
+        ptr = lambda k: None if state.get(k) is None else state[k].data_ptr()  # noqa: E731
+        _lib.check(
+            _lib.lib().sdk_pack_snapshot(n, n_pad, ptr("lon"), ptr("lat"), ptr("dep"), ptr("face"), ptr("iy"), ptr("ix"),
+                                         ptr("izl"), out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream),
+            "sdk_pack_snapshot",
+        )
+        return out
+    out.zero_()
+    for k, name in enumerate(("lon", "lat", "dep")):
+        if state.get(name) is not None:
+            out[k, :n] = state[name].to(torch.float64)
+    ints = out[3:].view(torch.int32).view(2, n_pad, 2)
+    for (row, col), name in zip(((0, 0), (0, 1), (1, 0), (1, 1)), ("face", "iy", "ix", "izl")):
+        if state.get(name) is not None:
+            ints[row, :n, col] = state[name].to(torch.int32)
+    return out
+
+
+def unpack_snapshot(packed):
+    """Inverse of :func:`pack_snapshot` for one rank's [5, n] block -> dict of numpy arrays."""
+    g = packed.cpu().numpy() if hasattr(packed, "cpu") else np.asarray(packed)
+    g = np.ascontiguousarray(g)
+    out = {"lon": g[0], "lat": g[1], "dep": g[2]}
+    a = g[3].view(np.int32).reshape(-1, 2)
+    b = g[4].view(np.int32).reshape(-1, 2)
+    out["face"], out["iy"], out["ix"], out["izl"] = a[:, 0], a[:, 1], b[:, 0], b[:, 1]
     return out
 
 
@@ -56,13 +87,12 @@ def unshard(gathered, n, world, seed=0):
     perm = permutation(n, seed)
     per = -(-n // world)
     g = gathered.cpu().numpy() if hasattr(gathered, "cpu") else np.asarray(gathered)
-    out = {}
-    for k, name in enumerate(SNAPSHOT_FIELDS):
-        full = np.empty(n, np.float64)
-        for r in range(world):
-            idx = perm[r * per : min((r + 1) * per, n)]
-            full[idx] = g[r, k, : len(idx)]
-        out[name] = full if name in ("lon", "lat", "dep") else full.astype(np.int64)
+    out = {name: np.empty(n, np.float64 if name in ("lon", "lat", "dep") else np.int64) for name in SNAPSHOT_FIELDS}
+    for r in range(world):
+        idx = perm[r * per : min((r + 1) * per, n)]
+        block = unpack_snapshot(g[r])
+        for name in SNAPSHOT_FIELDS:
+            out[name][idx] = block[name][: len(idx)]
     return out
 
 

@@ -132,3 +132,31 @@ def test_lazy_mode_list_of_time_matches_golden():
     np.testing.assert_allclose(stops, gold["stops"])
     for i, snap in enumerate(snaps):
         compare_state(gold, f"s{i}_", snap)
+
+
+def test_pack_snapshot_device_equals_host():
+    """sdk_pack_snapshot (one launch) writes the same 40-byte records as the torch fallback."""
+    import torch
+
+    from seaduck_b200 import parallel
+
+    rng = np.random.default_rng(0)
+    n, n_pad = 1000, 1024
+    host = {
+        "lon": torch.from_numpy(rng.uniform(-180, 180, n)), "lat": torch.from_numpy(rng.uniform(-90, 90, n)),
+        "dep": torch.from_numpy(rng.uniform(-5000, 0, n)),
+        "face": torch.from_numpy(rng.integers(0, 13, n).astype(np.int32)), "iy": torch.from_numpy(rng.integers(0, 4320, n).astype(np.int32)),
+        "ix": torch.from_numpy(rng.integers(0, 4320, n).astype(np.int32)), "izl": torch.from_numpy(rng.integers(0, 90, n).astype(np.int32)),
+    }
+    dev = {k: v.cuda() for k, v in host.items()}
+    a = parallel.pack_snapshot(host, n_pad)
+    b = parallel.pack_snapshot(dev, n_pad).cpu()
+    assert torch.equal(a.view(torch.int64), b.view(torch.int64))
+    back = parallel.unpack_snapshot(b)
+    for k, v in host.items():
+        np.testing.assert_array_equal(back[k][:n], v.numpy(), err_msg=k)
+    # 2-D runs have no depth / level, single-face grids no face
+    dev2 = dict(dev, dep=None, izl=None, face=None)
+    c = parallel.unpack_snapshot(parallel.pack_snapshot(dev2).cpu())
+    assert (c["dep"] == 0).all() and (c["izl"] == 0).all() and (c["face"] == 0).all()
+    np.testing.assert_array_equal(c["ix"], host["ix"].numpy())

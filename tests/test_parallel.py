@@ -28,7 +28,7 @@ def _worker(rank, world, n, port, ret):
     }
     g = parallel.all_gather_snapshot(parallel.pack_snapshot(state, n_pad=per))
     # the overlapped gatherer takes the collective route on CPU and must deliver the same thing
-    sg = parallel.SnapshotGather(len(parallel.SNAPSHOT_FIELDS), per, torch.device("cpu"))
+    sg = parallel.SnapshotGather(parallel.SNAPSHOT_ROWS, per, torch.device("cpu"))
     assert sg.mode == "collective"
     sg.post(parallel.pack_snapshot(state, n_pad=per), slot=1)
     sg.wait()
