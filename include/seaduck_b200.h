@@ -225,32 +225,39 @@ int sdk_locate(const sdk_grid *grid, int64_t n, const double *lon, const double 
 /* ---- masked kernel-weight interpolation (Position.interpolate, seaduck/eulerian.py:1268) ---------- */
 #define SDK_MAX_NODES 32
 #define SDK_MAX_LEVELS 8
-#define SDK_MAX_AXIS 9
+#define SDK_MAX_COEF 9
 /* neighbour index of a stencil node in the `rim` tables: 5 bits face, 13 bits iy, 13 bits ix */
 #define SDK_PACK(f, iy, ix) (((f) << 26) | ((iy) << 13) | (ix))
 #define SDK_NODE_RAISES (-1) /* the reference raises for this node (no such neighbour): result NaN */
 #define SDK_NODE_LAST (-2)   /* the reference indexes [-1, -1] (stepped out of a closed box) */
-enum { SDK_KIND_CROSS_INTERP = 0, SDK_KIND_LINE_X = 1, SDK_KIND_LINE_Y = 2, SDK_KIND_RECT = 3 };
 enum { SDK_MODE_NEAREST = 0, SDK_MODE_LINEAR = 1, SDK_MODE_DERIV = 2 };
+/* how the weight of a node is put together from its two polynomials A(rx), C(ry) */
+enum { SDK_W_A = 0, SDK_W_C = 1, SDK_W_A_PLUS_C = 2, SDK_W_A_TIMES_C = 3 };
 
-/* One level of a KnW inheritance (seaduck/kernel_weight.py:645): which nodes it uses and the 1-D
- * node sets of its Lagrange weights (kernel_weight_x :84, kernel_weight_s :313). */
+/* One level of a KnW inheritance (seaduck/kernel_weight.py:645): which nodes it uses and how each
+ * node's Lagrange weight (kernel_weight_x :84, kernel_weight_s :313) is formed. */
 typedef struct sdk_kernel_level {
     uint32_t node_mask;
-    int32_t kind, nxs, nys, xorder, yorder;
-    int8_t xs[SDK_MAX_AXIS + 3], ys[SDK_MAX_AXIS + 3];
+    uint32_t reserved;
+    uint8_t mode[SDK_MAX_NODES]; /* SDK_W_* per node */
 } sdk_kernel_level;
 
-/* A KnW: horizontal nodes, inheritance levels, vertical / temporal mode.  `rim` is the DEVICE table
- * of neighbour indices for the cells whose stencil leaves the (per face) array: for every rim cell
- * (slot order documented in seaduck_b200/interp.py) and node, SDK_PACK(face, iy, ix) or SDK_NODE_*; `rim_code` (vectors only) bit0 = value comes from the OTHER component,
- * bit1 = negative sign (four_matrix_for_uv, seaduck/topology.py:689). */
+/* A KnW: horizontal nodes, inheritance levels, vertical / temporal mode.
+ * `coef` is the DEVICE table of the weight polynomials, [n_levels][n_nodes][2][n_coef] doubles: for
+ * every level and node the coefficients (ascending powers) of A(rx) and of C(ry); the host expands the
+ * reference's products of (r - node) factors, derivative order included.
+ * `rim` is the DEVICE table of neighbour indices for the cells whose stencil leaves the (per face)
+ * array: for every rim cell (slot order documented in seaduck_b200/interp.py) and node,
+ * SDK_PACK(face, iy, ix) or SDK_NODE_*; `rim_code` (vectors only) bit0 = value comes from the OTHER
+ * component, bit1 = negative sign (four_matrix_for_uv, seaduck/topology.py:689). */
 typedef struct sdk_kernel_desc {
     int32_t n_nodes, n_levels, vmode, tmode, ignore_mask, bottom_no_flux;
     int32_t reach;     /* max(|dx|, |dy|): cells closer than this to a face edge use `rim` */
     int32_t rim_dense; /* 1: `rim` covers every cell (tiny grids), slot = iy*nx + ix */
+    int32_t n_coef, reserved;
     int8_t dx[SDK_MAX_NODES], dy[SDK_MAX_NODES];
     sdk_kernel_level level[SDK_MAX_LEVELS];
+    const double *coef;
     const int32_t *rim;
     const uint8_t *rim_code;
 } sdk_kernel_desc;

@@ -24,76 +24,35 @@ __device__ __forceinline__ int rim_slot(int ny, int nx, int r, int dense, int iy
     return -1;
 }
 
-// weight of node `target` among the 1-D nodes for the `order`-th derivative
-// (reference kernel_weight.py:84-306: sum over subsets of the other nodes / product of differences)
-__device__ __forceinline__ double axis_weight(const int8_t *nodes, int nn, int target, double r, int order) {
-    double denom = 1.0;
-    double e[SDK_MAX_AXIS + 1];
-    const int k = nn - 1 - order;  // size of the subsets
-    if (k == 0) {
-        double f = 1.0;
-        for (int i = 2; i <= order - 1; ++i) f *= i;
-        for (int j = 0; j < nn; ++j)
-            if (nodes[j] != target) denom *= (double)(target - nodes[j]);
-        return f / denom;
-    }
-    e[0] = 1.0;
-    for (int j = 1; j <= k; ++j) e[j] = 0.0;
-    for (int j = 0; j < nn; ++j) {
-        if (nodes[j] == target) continue;
-        denom *= (double)(target - nodes[j]);
-        const double v = r - (double)nodes[j];
-        for (int q = k; q >= 1; --q) e[q] += e[q - 1] * v;  // elementary symmetric polynomials
-    }
-    return e[k] / denom;
-}
-
-__device__ __forceinline__ void level_weights(const sdk_kernel_desc &K, const sdk_kernel_level &L, double rx,
-                                              double ry, double *w) {
-    for (int m = 0; m < K.n_nodes; ++m) {
-        double v = 0.0;
-        if (L.node_mask >> m & 1u) {
-            const int x = K.dx[m], y = K.dy[m];
-            if (L.kind == SDK_KIND_CROSS_INTERP) {
-                if (x != 0) v = axis_weight(L.xs, L.nxs, x, rx, 0);
-                else if (y != 0) v = axis_weight(L.ys, L.nys, y, ry, 0);
-                else v = axis_weight(L.xs, L.nxs, 0, rx, 0) + axis_weight(L.ys, L.nys, 0, ry, 0) - 1;
-            } else if (L.kind == SDK_KIND_LINE_X) {
-                if (y == 0) v = axis_weight(L.xs, L.nxs, x, rx, L.xorder);
-            } else if (L.kind == SDK_KIND_LINE_Y) {
-                if (x == 0) v = axis_weight(L.ys, L.nys, y, ry, L.yorder);
-            } else {
-                v = axis_weight(L.xs, L.nxs, x, rx, L.xorder) * axis_weight(L.ys, L.nys, y, ry, L.yorder);
-            }
-        }
-        w[m] = v;
-    }
-}
-
+// Everything per point lives in registers: the loops over nodes are fully unrolled up to the
+// compile-time bound MAXM (9 covers the default 9-point cross, 3 x 3 squares and the particle
+// kernels; 32 is the general case), with `m < n_nodes` guards that cost a predicate each.
+template <int MAXM>
 struct NodeSet {
-    int32_t packed[SDK_MAX_NODES];  // SDK_PACK(face, iy, ix), SDK_NODE_RAISES or SDK_NODE_LAST
-    uint8_t code[SDK_MAX_NODES];    // bit0 other component, bit1 negative
+    int32_t packed[MAXM];  // SDK_PACK(face, iy, ix), SDK_NODE_RAISES or SDK_NODE_LAST
+    uint8_t code[MAXM];    // bit0 other component, bit1 negative
 };
 
-__device__ __forceinline__ int find_nodes(const GridDev &g, const sdk_kernel_desc &K, int f, int iy, int ix,
-                                          NodeSet &ns) {
+template <int MAXM>
+__device__ __forceinline__ void find_nodes(const GridDev &g, const sdk_kernel_desc &K, int f, int iy, int ix,
+                                           NodeSet<MAXM> &ns) {
     const int slot = rim_slot(g.ny, g.nx, K.reach, K.rim_dense, iy, ix);
-    int bad = 0;
     if (slot < 0 || K.rim == nullptr) {
-        for (int m = 0; m < K.n_nodes; ++m) {
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
             ns.packed[m] = SDK_PACK(f, iy + K.dy[m], ix + K.dx[m]);
             ns.code[m] = 0;
         }
-        return 0;
+        return;
     }
     const int per_face = K.rim_dense ? g.ny * g.nx : 2 * K.reach * g.nx + 2 * K.reach * (g.ny - 2 * K.reach);
     const int64_t base = ((int64_t)f * per_face + slot) * K.n_nodes;
-    for (int m = 0; m < K.n_nodes; ++m) {
-        ns.packed[m] = __ldg(K.rim + base + m);
-        ns.code[m] = K.rim_code ? __ldg(K.rim_code + base + m) : 0;
-        bad |= ns.packed[m] == SDK_NODE_RAISES;
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) {
+        const bool on = m < K.n_nodes;
+        ns.packed[m] = on ? __ldg(K.rim + base + m) : SDK_NODE_RAISES;
+        ns.code[m] = (on && K.rim_code) ? __ldg(K.rim_code + base + m) : 0;
     }
-    return bad;
 }
 
 // SDK_NODE_LAST: the reference walked off a closed box and indexes [-1, -1], numpy's last element
@@ -125,16 +84,40 @@ __device__ __forceinline__ bool is_wet(const GridDev &g, const sdk_field &F, int
     return __ldg(F.mask + idx) != 0;
 }
 
+// Lagrange weight of node m in one inheritance level: two polynomials A(rx), C(ry) (Horner on the
+// host-expanded coefficients; every lane of a warp that picked the same level reads the same
+// coefficients) combined as the node's mode says.  Evaluated on the fly inside the dot product: the
+// kernel is bound by the latency of its gathers, so registers (occupancy) matter more than ALU work.
+__device__ __forceinline__ double node_weight(const sdk_kernel_desc &K, int level, int m, double rx, double ry) {
+    const int nc = K.n_coef;
+    const double *ca = K.coef + ((int64_t)level * K.n_nodes + m) * 2 * nc, *cc = ca + nc;
+    const int mode = K.level[level].mode[m];
+    double a = 0.0, c = 0.0;
+    if (mode != SDK_W_C) {
+        a = __ldg(ca + nc - 1);
+        for (int k = nc - 2; k >= 0; --k) a = a * rx + __ldg(ca + k);
+    }
+    if (mode != SDK_W_A) {
+        c = __ldg(cc + nc - 1);
+        for (int k = nc - 2; k >= 0; --k) c = c * ry + __ldg(cc + k);
+    }
+    return mode == SDK_W_A ? a : (mode == SDK_W_C ? c : (mode == SDK_W_A_PLUS_C ? a + c : a * c));
+}
+
 // One interpolated value.  P = field of the kernel's own component, O = the other component
 // (vectors on multi-face grids), both may be the same.
-__device__ double interp_value(const GridDev &g, const sdk_kernel_desc &K, const sdk_field &P, const sdk_field &O,
-                               const NodeSet &ns, double rxs, double rys, int kz0, double rz, int kt0, double rt) {
+template <int MAXM>
+__device__ __forceinline__ double interp_value(const GridDev &g, const sdk_kernel_desc &K, const sdk_field &P,
+                                               const sdk_field &O, const NodeSet<MAXM> &ns, double rxs, double rys, int kz0,
+                                               double rz, int kt0, double rt) {
     const int nz = K.vmode == SDK_MODE_NEAREST ? 1 : 2;
     const int nt = K.tmode == SDK_MODE_NEAREST ? 1 : 2;
     const bool use_mask = !K.ignore_mask && P.mask != nullptr;
-    double w[SDK_MAX_NODES];
-    int cached_level = -2;
     double total = 0.0;
+    // Per vertical level: the wet flags of all nodes and (speculatively) their values are requested
+    // together, so a point costs one round trip to memory instead of two; the values of nodes that
+    // the chosen (smaller) stencil does not use are simply dropped.  Masks do not depend on time.
+    int level_z[2] = {0, 0};
     for (int jt = 0; jt < nt; ++jt) {
         const int kt = kt0 + jt;
         const double tw = K.tmode == SDK_MODE_LINEAR ? (jt == 0 ? 1 - rt : rt) : (K.tmode == SDK_MODE_DERIV ? (jt == 0 ? -1.0 : 1.0) : 1.0);
@@ -142,41 +125,39 @@ __device__ double interp_value(const GridDev &g, const sdk_kernel_desc &K, const
         bool znan[2] = {false, false};
         for (int jz = 0; jz < nz; ++jz) {
             const int kz = kz0 - jz;
-            // which stencil fits the wet nodes (reference find_which_points_for_each_kernel :481)
-            int level = 0;
-            if (use_mask) {
-                unsigned wet = 0;
-                for (int m = 0; m < K.n_nodes; ++m) {
-                    const sdk_field &M = (ns.code[m] & 1) ? O : P;
-                    if (is_wet(g, M, ns.packed[m], kz)) wet |= 1u << m;
-                }
-                level = -1;
-                for (int l = 0; l < K.n_levels; ++l)
-                    if ((wet & K.level[l].node_mask) == K.level[l].node_mask) {
-                        level = l;
-                        break;
+            double val[MAXM];
+            unsigned wet = 0;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m) {
+                val[m] = 0.0;
+                if (m < K.n_nodes) {
+                    const bool other = ns.code[m] & 1;
+                    if (use_mask && jt == 0 && is_wet(g, other ? O : P, ns.packed[m], kz)) wet |= 1u << m;
+                    if (ns.packed[m] == SDK_NODE_RAISES) {
+                        val[m] = NAN;
+                    } else {
+                        const double v = field_value(g, other ? O : P, ns.packed[m], kz, kt);
+                        val[m] = (ns.code[m] & 2) ? -v : v;
                     }
+                }
             }
+            if (use_mask && jt == 0) {
+                // the largest stencil whose nodes are all wet (reference find_which_points_for_each_kernel :481)
+                int level = -1;
+                for (int l = K.n_levels - 1; l >= 0; --l)
+                    if ((wet & K.level[l].node_mask) == K.level[l].node_mask) level = l;
+                level_z[jz] = level;
+            }
+            const int level = level_z[jz];
             if (level < 0) {
                 znan[jz] = true;  // weight[:, 0] = nan (reference :557-558)
                 continue;
             }
-            if (level != cached_level) {
-                level_weights(K, K.level[level], rxs, rys, w);
-                cached_level = level;
-            }
+            const uint32_t mask = K.level[level].node_mask;
             double acc = 0.0;
-            for (int m = 0; m < K.n_nodes; ++m) {
-                if (!(K.level[level].node_mask >> m & 1u)) continue;
-                if (ns.packed[m] == SDK_NODE_RAISES) {
-                    acc = NAN;
-                    continue;
-                }
-                const sdk_field &S = (ns.code[m] & 1) ? O : P;
-                double v = field_value(g, S, ns.packed[m], kz, kt);
-                if (ns.code[m] & 2) v = -v;
-                acc += v * w[m];
-            }
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m)
+                if (m < K.n_nodes && (mask >> m & 1u)) acc += val[m] * node_weight(K, level, m, rxs, rys);
             zsum[jz] = acc;
         }
         double zw0 = 1.0, zw1 = 0.0;
@@ -204,31 +185,37 @@ __device__ double interp_value(const GridDev &g, const sdk_kernel_desc &K, const
     return total;
 }
 
-__global__ void __launch_bounds__(128) interp_scalar_kernel(const __grid_constant__ InterpArgs a) {
+#ifndef SDK_INTERP_MIN_BLOCKS
+#define SDK_INTERP_MIN_BLOCKS 8
+#endif
+
+template <int MAXM>
+__global__ void __launch_bounds__(128, MAXM <= 9 ? SDK_INTERP_MIN_BLOCKS : 1) interp_scalar_kernel(const __grid_constant__ InterpArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.pts.n) return;
     const sdk_points &p = a.pts;
     const int f = p.face ? p.face[i] : 0, iy = p.iy[i], ix = p.ix[i];
-    NodeSet ns;
-    find_nodes(a.g, a.ku, f, iy, ix, ns);
+    NodeSet<MAXM> ns;
+    find_nodes<MAXM>(a.g, a.ku, f, iy, ix, ns);
     const double rxs = a.fu.xstag ? p.rx[i] + 0.5 : p.rx[i];
     const double rys = a.fu.ystag ? p.ry[i] + 0.5 : p.ry[i];
-    a.out_u[i] = interp_value(a.g, a.ku, a.fu, a.fu, ns, rxs, rys, p.kz ? p.kz[i] : 0, p.rz ? p.rz[i] : 0.0,
-                              p.kt ? p.kt[i] : 0, p.rt ? p.rt[i] : 0.0);
+    a.out_u[i] = interp_value<MAXM>(a.g, a.ku, a.fu, a.fu, ns, rxs, rys, p.kz ? p.kz[i] : 0, p.rz ? p.rz[i] : 0.0,
+                                    p.kt ? p.kt[i] : 0, p.rt ? p.rt[i] : 0.0);
 }
 
-__global__ void __launch_bounds__(128) interp_vector_kernel(const __grid_constant__ InterpArgs a) {
+template <int MAXM>
+__global__ void __launch_bounds__(128, MAXM <= 9 ? SDK_INTERP_MIN_BLOCKS : 1) interp_vector_kernel(const __grid_constant__ InterpArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.pts.n) return;
     const sdk_points &p = a.pts;
     const int f = p.face ? p.face[i] : 0, iy = p.iy[i], ix = p.ix[i];
     const int kz = p.kz ? p.kz[i] : 0, kt = p.kt ? p.kt[i] : 0;
     const double rz = p.rz ? p.rz[i] : 0.0, rt = p.rt ? p.rt[i] : 0.0;
-    NodeSet ns;
-    find_nodes(a.g, a.ku, f, iy, ix, ns);
-    double u = interp_value(a.g, a.ku, a.fu, a.fv, ns, p.rx[i] + 0.5, p.ry[i], kz, rz, kt, rt);
-    find_nodes(a.g, a.kv, f, iy, ix, ns);
-    double v = interp_value(a.g, a.kv, a.fv, a.fu, ns, p.rx[i], p.ry[i] + 0.5, kz, rz, kt, rt);
+    NodeSet<MAXM> ns;
+    find_nodes<MAXM>(a.g, a.ku, f, iy, ix, ns);
+    double u = interp_value<MAXM>(a.g, a.ku, a.fu, a.fv, ns, p.rx[i] + 0.5, p.ry[i], kz, rz, kt, rt);
+    find_nodes<MAXM>(a.g, a.kv, f, iy, ix, ns);
+    double v = interp_value<MAXM>(a.g, a.kv, a.fv, a.fu, ns, p.rx[i], p.ry[i] + 0.5, kz, rz, kt, rt);
     if (a.vec_transform) {
         const double cs = (double)p.cs[i], sn = (double)p.sn[i];
         const double uu = u * cs - v * sn, vv = u * sn + v * cs;
@@ -274,8 +261,14 @@ cudaError_t launch_interp(const InterpArgs &a, bool vector, cudaStream_t s) {
     if (a.pts.n == 0) return cudaSuccess;
     const int threads = 128;
     const unsigned blocks = (unsigned)((a.pts.n + threads - 1) / threads);
-    if (vector) interp_vector_kernel<<<blocks, threads, 0, s>>>(a);
-    else interp_scalar_kernel<<<blocks, threads, 0, s>>>(a);
+    const bool small = a.ku.n_nodes <= 9 && (!vector || a.kv.n_nodes <= 9);
+    if (vector) {
+        if (small) interp_vector_kernel<9><<<blocks, threads, 0, s>>>(a);
+        else interp_vector_kernel<SDK_MAX_NODES><<<blocks, threads, 0, s>>>(a);
+    } else {
+        if (small) interp_scalar_kernel<9><<<blocks, threads, 0, s>>>(a);
+        else interp_scalar_kernel<SDK_MAX_NODES><<<blocks, threads, 0, s>>>(a);
+    }
     return cudaGetLastError();
 }
 

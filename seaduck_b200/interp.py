@@ -138,20 +138,12 @@ def _rim_on_device(od, knw, cuvwg):
 # ------------------------------------------------------------------------------------------------
 # ctypes mirrors of the structures in include/seaduck_b200.h
 # ------------------------------------------------------------------------------------------------
-MAX_NODES, MAX_LEVELS, MAX_AXIS = 32, 8, 9
+MAX_NODES, MAX_LEVELS, MAX_COEF = 32, 8, 9
+W_A, W_C, W_A_PLUS_C, W_A_TIMES_C = 0, 1, 2, 3
 
 
 class KernelLevel(C.Structure):
-    _fields_ = [
-        ("node_mask", C.c_uint32),
-        ("kind", C.c_int32),
-        ("nxs", C.c_int32),
-        ("nys", C.c_int32),
-        ("xorder", C.c_int32),
-        ("yorder", C.c_int32),
-        ("xs", C.c_int8 * (MAX_AXIS + 3)),
-        ("ys", C.c_int8 * (MAX_AXIS + 3)),
-    ]
+    _fields_ = [("node_mask", C.c_uint32), ("reserved", C.c_uint32), ("mode", C.c_uint8 * MAX_NODES)]
 
 
 class KernelDesc(C.Structure):
@@ -164,9 +156,12 @@ class KernelDesc(C.Structure):
         ("bottom_no_flux", C.c_int32),
         ("reach", C.c_int32),
         ("rim_dense", C.c_int32),
+        ("n_coef", C.c_int32),
+        ("reserved", C.c_int32),
         ("dx", C.c_int8 * MAX_NODES),
         ("dy", C.c_int8 * MAX_NODES),
         ("level", KernelLevel * MAX_LEVELS),
+        ("coef", C.c_void_p),
         ("rim", C.c_void_p),
         ("rim_code", C.c_void_p),
     ]
@@ -182,8 +177,64 @@ class Points(C.Structure):
     _fields_ = [("n", C.c_int64)] + [(n, C.c_void_p) for n in "face iy ix rx ry kz rz kt rt cs sn".split()]
 
 
+def axis_polynomial(nodes, target, order):
+    """Coefficients (ascending powers of r) of the Lagrange weight of ``target`` among the 1-D
+    ``nodes`` for the ``order``-th derivative, as the reference defines it (kernel_weight.py:136-230:
+    sum over the subsets of the other nodes of prod (r - o), over prod (target - o); at the maximum
+    order the numerator is (order - 1)!).  Small-integer arithmetic: exact in float64."""
+    from itertools import combinations  # noqa: PLC0415
+    from math import factorial  # noqa: PLC0415
+
+    others = [o for o in nodes if o != target]
+    denom = 1.0
+    for o in others:
+        denom *= target - o
+    if order > len(nodes) - 1:
+        raise ValueError("Kernel is too small for this derivative")
+    if order == len(nodes) - 1:
+        return np.array([float(factorial(max(order - 1, 0))) / denom])
+    num = np.zeros(1)
+    for sub in combinations(others, len(others) - order):
+        term = np.ones(1)
+        for o in sub:
+            term = np.convolve(term, np.array([-float(o), 1.0]))
+        num = np.pad(num, (0, max(0, len(term) - len(num)))) + np.pad(term, (0, max(0, len(num) - len(term))))
+    return num / denom
+
+
+def level_polynomials(stencil, nodes_xy):
+    """Per node of one inheritance level: (mode, A coefficients, C coefficients) so that the weight is
+    A(rx), C(ry), A(rx) + C(ry) or A(rx) * C(ry) (``_Stencil.__call__`` in kernel_weight.py)."""
+    from .kernel_weight import KIND_CROSS_INTERP, KIND_LINE_X, KIND_LINE_Y  # noqa: PLC0415
+
+    xs, ys = stencil.xs, stencil.ys
+    zero, one = np.zeros(1), np.ones(1)
+    out = []
+    for x, y in nodes_xy:
+        x, y = int(x), int(y)
+        if stencil.kind == KIND_CROSS_INTERP:
+            if x != 0:
+                out.append((W_A, axis_polynomial(xs, x, 0), zero))
+            elif y != 0:
+                out.append((W_C, zero, axis_polynomial(ys, y, 0)))
+            else:
+                c = axis_polynomial(ys, 0, 0).copy()
+                c[0] -= 1.0
+                out.append((W_A_PLUS_C, axis_polynomial(xs, 0, 0), c))
+        elif stencil.kind == KIND_LINE_X:
+            out.append((W_A, axis_polynomial(xs, x, stencil.xorder) if y == 0 else zero, zero))
+        elif stencil.kind == KIND_LINE_Y:
+            out.append((W_C, zero, axis_polynomial(ys, y, stencil.yorder) if x == 0 else zero))
+        else:
+            out.append((W_A_TIMES_C, axis_polynomial(xs, x, stencil.xorder), axis_polynomial(ys, y, stencil.yorder)))
+    del one
+    return out
+
+
 def kernel_desc(od, knw, cuvwg, ignore_mask, bottom_no_flux):
     """``sdk_kernel_desc`` of a KnW (plus the tensors that must outlive the call)."""
+    import torch  # noqa: PLC0415
+
     d = knw.describe()
     kern = d["kernel"]
     if len(kern) > MAX_NODES or len(d["levels"]) > MAX_LEVELS:
@@ -196,23 +247,37 @@ def kernel_desc(od, knw, cuvwg, ignore_mask, bottom_no_flux):
     k.bottom_no_flux = int(bottom_no_flux)
     for j, (x, y) in enumerate(kern):
         k.dx[j], k.dy[j] = int(x), int(y)
+    key = ("coef", hash(knw))
+    hit = od._interp_cache.get(key)
+    if hit is None:
+        polys = []
+        for lev, st in zip(d["levels"], knw.hfuncs):
+            polys.append(level_polynomials(st, [kern[i] for i in lev["nodes"]]))
+        n_coef = max(max(len(a), len(c)) for lp in polys for _, a, c in lp)
+        if n_coef > MAX_COEF:
+            raise NotImplementedError("more than 9 distinct node positions along one axis")
+        table = np.zeros((k.n_levels, k.n_nodes, 2, n_coef))
+        modes = np.zeros((k.n_levels, k.n_nodes), np.uint8)
+        for li, (lev, lp) in enumerate(zip(d["levels"], polys)):
+            for node, (mode, a, c) in zip(lev["nodes"], lp):
+                modes[li, node] = mode
+                table[li, node, 0, : len(a)] = a
+                table[li, node, 1, : len(c)] = c
+        hit = (n_coef, modes, torch.from_numpy(table).to(od._torch_device()))
+        od._interp_cache[key] = hit
+    n_coef, modes, table = hit
+    k.n_coef = n_coef
+    k.coef = table.data_ptr()
     for li, lev in enumerate(d["levels"]):
         L = k.level[li]
-        if len(lev["xs"]) > MAX_AXIS or len(lev["ys"]) > MAX_AXIS:
-            raise NotImplementedError("more than 9 distinct node positions along one axis")
         L.node_mask = sum(1 << int(i) for i in lev["nodes"])
-        L.kind = lev["kind"]
-        L.nxs, L.nys = len(lev["xs"]), len(lev["ys"])
-        L.xorder, L.yorder = lev["xorder"], lev["yorder"]
-        for j, v in enumerate(lev["xs"]):
-            L.xs[j] = int(v)
-        for j, v in enumerate(lev["ys"]):
-            L.ys[j] = int(v)
+        for node in range(k.n_nodes):
+            L.mode[node] = int(modes[li, node])
     reach, dense, rim, code = _rim_on_device(od, knw, cuvwg)
     k.reach, k.rim_dense = reach, dense
     k.rim = None if rim is None else rim.data_ptr()
     k.rim_code = None if code is None else code.data_ptr()
-    return k, (rim, code)
+    return k, (rim, code, table)
 
 
 # ------------------------------------------------------------------------------------------------
