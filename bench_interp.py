@@ -121,8 +121,8 @@ def main():
             res = p2.interpolate(list(var), list(kernels))
             tt.append(time.perf_counter() - t0)
         best = min(tt[1:])
-        line["e2e"] = {"value": n / best, "unit": "points/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 32 * n + 120 * n,
-                       "api": "Position.from_latlon + Position.interpolate (numpy in, numpy out; includes the host mirrors from_latlon fills)"}
+        line["e2e"] = {"value": n / best, "unit": "points/s", "h2d_bytes_per_step": 24 * n, "d2h_bytes_per_step": 32 * n,
+                       "api": "Position.from_latlon + Position.interpolate (numpy in, numpy out; rel-coords stay on the device until somebody reads them)"}
         del res
     if not a.no_cpu_baseline:
         from oracle import interp_oracle as io

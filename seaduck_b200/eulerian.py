@@ -13,7 +13,7 @@ import logging
 
 import numpy as np
 
-from .ocedata import HRel, OceData, RelCoord, TRel, VlLinRel, VlRel, VRel, _general_len
+from .ocedata import Deferred, HRel, OceData, RelCoord, TRel, VlLinRel, VlRel, VRel, _general_len
 
 
 def to_180(x, peri=360):
@@ -114,7 +114,7 @@ class Position:
             t=t if (t is not None and od.readiness["time"]) else None,
         ) if any(v is not None for v in (x, y, z, t)) else {}
         self._located = loc  # device tensors, reused by Particle
-        npf = OceData._np
+        npf = Deferred  # host mirrors are fetched on first use
         if (x is not None) and (y is not None):
             self.lon = np.array(x, float)
             self.lat = np.array(y, float)

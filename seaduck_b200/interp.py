@@ -437,7 +437,13 @@ class _DevicePoints:
                 t = loc[key]
         if t is None:
             val = None
-            if name in pos.rel and pos.rel[name] is not None:
+            if "_st" in d:
+                # a Particle: attribute access knows which host mirrors are stale / derived
+                try:
+                    val = getattr(pos, name)
+                except AttributeError:
+                    val = None
+            elif name in pos.rel and pos.rel[name] is not None:
                 val = pos.rel[name]
             elif name in _LAZY and name not in pos.rel:
                 func, src = _LAZY[name]
@@ -655,7 +661,7 @@ def interpolate_device(pos, var_name, knw, vec_transform=True, prefetched=None, 
     """Like :func:`interpolate` but the results stay on the device (torch tensors)."""
     single, var_name, knw, prefetched, prefetch_prefix = _broadcast_inputs(pos, var_name, knw, prefetched, prefetch_prefix)
     od = pos.ocedata
-    has_face = pos.face is not None
+    has_face = pos.rel.has("face") if "_st" not in pos.__dict__ else pos.__dict__["_st"].get("face") is not None
     pts = _DevicePoints(pos)
     ori_list = list(zip(var_name, knw))
     jobs = []  # (key, kind, names, kernels, prefetched, prefix)

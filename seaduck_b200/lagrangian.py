@@ -278,14 +278,14 @@ class Particle(Position):
         ind = (face, iy, ix) if face is not None else (iy, ix)
         self.rel["bx"] = od.XC[ind]
         self.rel["by"] = od.YC[ind]
-        if od.CS is not None and od.SN is not None:
-            self.rel["cs"] = od.CS[ind]
-            self.rel["sn"] = od.SN[ind]
+        # cs, sn keep the values of the starting cell: the reference only refreshes bx, by, px, py in the
+        # oceanparcel scheme (_cross_cell_wall_read, lagrangian.py:660-665), and vec_transform uses them
         if self._has_dep:
-            dep = self.dep
+            # get_u_du leaves iz = izl_lin - 1 (lagrangian.py:247) while rz, dz, bz come from the nearest
+            # cell centre of the current depth (_cross_cell_wall_rel, lagrangian.py:683)
             self.rel["iz"] = self._rel_get("izl_lin") - 1
             if od.readiness["Z"]:
-                v = od._find_rel_v(dep)
+                v = od._find_rel_v(self.dep)
                 self.rel["rz"], self.rel["dz"], self.rel["bz"] = v.rz, v.dz, v.bz
 
     # ------------------------------------------------------------------------------------------

@@ -34,8 +34,44 @@ def _general_len(thing):
         return 1
 
 
+class Deferred:
+    """A rel-coordinate that still lives on the GPU: fetched (and converted to the reference's numpy
+    dtype) the first time somebody looks at it.  ``from_latlon`` of 10^7 points would otherwise copy
+    ~1.5 GB of rel-coords to the host that a following ``interpolate`` never reads."""
+
+    __slots__ = ("tensor", "dtype")
+
+    def __init__(self, tensor, dtype=None):
+        self.tensor, self.dtype = tensor, dtype
+
+    def fetch(self):
+        a = self.tensor.cpu().numpy()
+        return a.astype(self.dtype) if self.dtype is not None else a
+
+
 class RelCoord(dict):
-    """Relative coordinates: dictionary with attribute access (reference ``ocedata.py:34``)."""
+    """Relative coordinates: dictionary with attribute access (reference ``ocedata.py:34``).
+    Values may be :class:`Deferred`; every read access materialises them."""
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if isinstance(v, Deferred):
+            v = v.fetch()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+    def has(self, key):
+        """True if ``key`` holds something (without fetching it)."""
+        return dict.get(self, key) is not None
+
+    def values(self):
+        return [self[k] for k in self.keys()]
+
+    def items(self):
+        return [(k, self[k]) for k in self.keys()]
 
     def __getattr__(self, attr):
         try:

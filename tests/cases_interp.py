@@ -189,3 +189,17 @@ def assert_values_close(label, got, ref, rtol=1e-9):
     err = np.abs(got[ok] - ref[ok])
     bad = err > rtol * np.maximum(np.abs(ref[ok]), scale) + 1e-300
     assert not bad.any(), f"{label}: {int(bad.sum())} of {int(ok.sum())} beyond {rtol} (max err {err.max():.3e}, scale {scale:.3e})"
+
+
+def case_oceinterp(n=150, ngrid=24, nz=8):
+    """``OceInterp`` (reference oceinterp.py:14): Eulerian call and Lagrangian call on one dataset."""
+    ds = synthetic.llc(n=ngrid, nz=nz, nt=4, tracers=True)
+    lon, lat, dep, _ = _sphere_points(n, seed=41, lat_range=(-55.0, 60.0), depth=(5.0, 400.0))
+    return dict(
+        name="oceinterp", ds=ds, x=lon, y=lat, z=dep,
+        t_euler=12.5 * DAY,
+        t_lagrange=np.array([1.0, 4.0, 12.0, 17.0]) * DAY,
+        var_euler=["T", ("UVELMASS", "VVELMASS"), "WVELMASS"],
+        var_lagrange=["T", "__particle.lon", "__particle.lat", "__particle.dep", "__particle.ix", ("UVELMASS", "VVELMASS")],
+        lagrange_kwarg=dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True),
+    )

@@ -92,3 +92,30 @@ def test_interpolate_after_editing_position():
     t = np.asarray(case["ds"]["T"])
     np.testing.assert_allclose(b, t[pos.face, pos.iy, pos.ix])
     assert not np.allclose(a, b)
+
+
+def test_oceinterp_matches_reference():
+    """``OceInterp`` in both modes (reference oceinterp.py:14) against the reference's own output."""
+    import seaduck_b200 as sd
+
+    case = ci.case_oceinterp()
+    gold = np.load(os.path.join(GOLD, "oceinterp.npz"))
+    od = sd.OceData(case["ds"])
+    res = sd.OceInterp(od, case["var_euler"], case["x"], case["y"], case["z"], case["t_euler"])
+    flat = ci.flatten_result(res)
+    assert len(flat) == len([k for k in gold.files if k.startswith("euler_")])
+    for k, arr in enumerate(flat):
+        ci.assert_values_close(f"euler[{k}]", arr, gold[f"euler_{k}"])
+    stops, res = sd.OceInterp(
+        od, case["var_lagrange"], case["x"], case["y"], case["z"], case["t_lagrange"], lagrangian=True,
+        lagrange_kwarg=case["lagrange_kwarg"],
+    )
+    np.testing.assert_allclose(stops, gold["stops"])
+    flat = ci.flatten_result(res)
+    assert len(flat) == len([k for k in gold.files if k.startswith("lagrange_")])
+    for k, arr in enumerate(flat):
+        ci.assert_values_close(f"lagrange[{k}]", arr, gold[f"lagrange_{k}"])
+    with pytest.raises(ValueError):
+        sd.OceInterp(od, "T", case["x"], case["y"], case["z"], 5)  # int time: "time format not supported"
+    with pytest.raises(AttributeError):
+        sd.OceInterp(od, ["__particle.lon"], case["x"], case["y"], case["z"], case["t_euler"])
