@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--levels", type=int, default=50)
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="field storage (math is fp64)")
     ap.add_argument("--no-sort", action="store_true", help="keep particles in seeding order")
-    ap.add_argument("--max-batches", type=int, default=12, help="distinct batches kept in HBM (reused cyclically)")
+    ap.add_argument("--max-batches", type=int, default=24, help="distinct batches kept in HBM (reused cyclically)")
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="particles of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -34,10 +34,19 @@ int cuda_fail(cudaError_t e, const char *what) {
 }
 }  // namespace
 
+constexpr unsigned kQueueSlots = 64;
+constexpr int kTrackChunks = 8;
+
 struct sdk_grid {
     sdk::GridDev dev;
     int sm_count;
-    unsigned long long *queue;  // device work-queue head shared by the launches on this handle
+    // device work-queue heads: one slot per launch, taken round robin, so that launches on
+    // different streams (the chunks of sdk_track_host) never share a counter
+    unsigned long long *queue;
+    mutable unsigned next_queue;
+    mutable cudaStream_t pipe[3];  // lazily created by sdk_track_host
+    mutable cudaEvent_t pipe_ev[4];
+    mutable bool has_pipe;
     sdk::BucketGrid buckets;
     bool has_buckets;
 };
@@ -102,7 +111,9 @@ int sdk_grid_create(const sdk_grid_desc *d, sdk_grid **out) {
         delete g;
         return fail(SDK_ECUDA, "sdk_grid_create: no CUDA device");
     }
-    cudaError_t e = cudaMalloc(&g->queue, sizeof(unsigned long long));
+    g->next_queue = 0;
+    g->has_pipe = false;
+    cudaError_t e = cudaMalloc(&g->queue, kQueueSlots * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         delete g;
         return cuda_fail(e, "sdk_grid_create: cudaMalloc");
@@ -115,6 +126,10 @@ int sdk_grid_create(const sdk_grid_desc *d, sdk_grid **out) {
 int sdk_grid_destroy(sdk_grid *g) {
     if (!g) return SDK_OK;
     cudaFree(g->queue);
+    if (g->has_pipe) {
+        for (auto &st : g->pipe) cudaStreamDestroy(st);
+        for (auto &ev : g->pipe_ev) cudaEventDestroy(ev);
+    }
     if (g->has_buckets) cudaFree(g->buckets.table);
     delete g;
     return SDK_OK;
@@ -166,7 +181,7 @@ static int fill_args(const sdk_grid *grid, const sdk_velocity *vel, const sdk_pa
     a.commit = commit;
     int thr = par ? par->refill_threshold : 0;
     a.refill_threshold = thr > 0 ? (thr > 32 ? 32 : thr) : 8;
-    a.queue = grid->queue;
+    a.queue = grid->queue + (grid->next_queue++ % kQueueSlots);
     a.stats = par ? (unsigned long long *)par->stats : nullptr;
     return SDK_OK;
 }
@@ -178,7 +193,7 @@ int sdk_advect(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particle
     if (rc) return rc;
     if (p->n == 0) return SDK_OK;
     cudaStream_t stream = (cudaStream_t)stream_;
-    cudaError_t e = cudaMemsetAsync(grid->queue, 0, sizeof(unsigned long long), stream);
+    cudaError_t e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_advect: memset");
     const int threads = (par && par->threads_per_block > 0) ? par->threads_per_block : sdk::advect_default_threads();
     const int per_sm = (par && par->blocks_per_sm > 0) ? par->blocks_per_sm : 512 / threads;
@@ -482,18 +497,14 @@ int sdk_selftest_math(int op, int64_t n, const double *a, const double *b, doubl
 }
 
 // ---- positions in, positions out ------------------------------------------------------------------
-int64_t sdk_track_scratch_bytes(int64_t n) { return sdk_particles_bytes(n) + 8 * (int64_t)align256((size_t)n * 8); }
+// (room for the per-chunk alignment of the pipelined path: up to kTrackChunks carvings of ~30 arrays)
+int64_t sdk_track_scratch_bytes(int64_t n) { return sdk_particles_bytes(n) + 8 * (int64_t)align256((size_t)n * 8) + kTrackChunks * 40 * 256; }
 
-int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev,
-                   int32_t n_t, double t_stop, const sdk_advect_params *par, void *scratch, void *stream_) {
-    if (!grid || !vel || !io || !scratch) return fail(SDK_EINVAL, "sdk_track_host: null argument");
-    if (!io->lon || !io->lat || !io->t || !io->out_lon || !io->out_lat)
-        return fail(SDK_EINVAL, "sdk_track_host: lon / lat / t and their outputs are required");
+// One chunk of sdk_track_host: H2D, locate, velocity read, advect, D2H -- all asynchronous on `stream`.
+static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev,
+                       int32_t n_t, double t_stop, const sdk_advect_params *par, void *scratch, cudaStream_t stream) {
     const int64_t n = io->n;
-    if (n <= 0) return n == 0 ? SDK_OK : fail(SDK_EINVAL, "sdk_track_host: negative count");
     const int has_dep = par ? par->has_dep : 0;
-    if (has_dep && (!io->dep || !io->out_dep)) return fail(SDK_EINVAL, "sdk_track_host: depth arrays missing");
-    cudaStream_t stream = (cudaStream_t)stream_;
     // carve the device state out of the scratch buffer
     sdk_particles dp;
     std::memset(&dp, 0, sizeof dp);
@@ -547,6 +558,63 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
     D2H(io->out_ncross, dp.ncross, 4)
     D2H(io->out_status, dp.status, 4)
 #undef D2H
+    return SDK_OK;
+}
+
+int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev,
+                   int32_t n_t, double t_stop, const sdk_advect_params *par, void *scratch, void *stream_) {
+    if (!grid || !vel || !io || !scratch) return fail(SDK_EINVAL, "sdk_track_host: null argument");
+    if (!io->lon || !io->lat || !io->t || !io->out_lon || !io->out_lat)
+        return fail(SDK_EINVAL, "sdk_track_host: lon / lat / t and their outputs are required");
+    const int64_t n = io->n;
+    if (n <= 0) return n == 0 ? SDK_OK : fail(SDK_EINVAL, "sdk_track_host: negative count");
+    const int has_dep = par ? par->has_dep : 0;
+    if (has_dep && (!io->dep || !io->out_dep)) return fail(SDK_EINVAL, "sdk_track_host: depth arrays missing");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cudaError_t e;
+    // Small batches: one pass.  Large ones: chunks on three internal streams, so that the upload of
+    // chunk k+1 and the read-back of chunk k-1 (copy engines) overlap the kernels of chunk k.
+    const int64_t min_chunk = 65536;
+    int nchunks = (int)(n / min_chunk);
+    if (nchunks > kTrackChunks) nchunks = kTrackChunks;
+    if (nchunks < 2) {
+        int rc = track_chunk(grid, vel, io, ts_dev, n_t, t_stop, par, scratch, stream);
+        if (rc) return rc;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: sync");
+        return SDK_OK;
+    }
+    if (!grid->has_pipe) {
+        for (auto &st : grid->pipe)
+            if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: stream");
+        for (auto &ev : grid->pipe_ev)
+            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event");
+        grid->has_pipe = true;
+    }
+    // the internal streams start after whatever the caller queued on `stream`
+    if ((e = cudaEventRecord(grid->pipe_ev[3], stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");
+    for (auto &st : grid->pipe)
+        if ((e = cudaStreamWaitEvent(st, grid->pipe_ev[3], 0)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: wait");
+    const int64_t per = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
+    char *cur = (char *)scratch;
+    for (int c = 0; c < nchunks; ++c) {
+        const int64_t off = (int64_t)c * per;
+        const int64_t cnt = off + per <= n ? per : n - off;
+        if (cnt <= 0) break;
+        sdk_track_io sub = *io;
+        sub.n = cnt;
+#define SHIFT(member) \
+    if (sub.member) sub.member = sub.member + off;
+        SHIFT(lon) SHIFT(lat) SHIFT(dep) SHIFT(t) SHIFT(out_lon) SHIFT(out_lat) SHIFT(out_dep) SHIFT(out_face)
+        SHIFT(out_iy) SHIFT(out_ix) SHIFT(out_izl) SHIFT(out_ncross) SHIFT(out_status)
+#undef SHIFT
+        int rc = track_chunk(grid, vel, &sub, ts_dev, n_t, t_stop, par, cur, grid->pipe[c % 3]);
+        if (rc) return rc;
+        cur += sdk_particles_bytes(cnt);
+    }
+    for (int k = 0; k < 3; ++k) {
+        if ((e = cudaEventRecord(grid->pipe_ev[k], grid->pipe[k])) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");
+        if ((e = cudaStreamWaitEvent(stream, grid->pipe_ev[k], 0)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: wait");
+    }
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: sync");
     return SDK_OK;
 }

@@ -160,3 +160,74 @@ def test_pack_snapshot_device_equals_host():
     c = parallel.unpack_snapshot(parallel.pack_snapshot(dev2).cpu())
     assert (c["dep"] == 0).all() and (c["izl"] == 0).all() and (c["face"] == 0).all()
     np.testing.assert_array_equal(c["ix"], host["ix"].numpy())
+
+
+@pytest.mark.parametrize("n", [1000, 300_000])
+def test_track_host_equals_particle_api(n):
+    """sdk_track_host (host buffers in and out; chunked and pipelined over three streams for large
+    batches) gives exactly what Particle(...).to_next_stop(...) gives."""
+    import ctypes as C
+
+    import torch
+
+    from seaduck_b200 import _lib, synthetic
+
+    sd = _sd()
+    ds = synthetic.llc(n=45, nz=12)
+    lon, lat, dep = synthetic.llc_seed_particles(ds, n, seed=8, depth_range=(5, 600))
+    kw = dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True)
+    od = sd.OceData(ds)
+    t_stop = 20 * cases.DAY
+    pt = sd.Particle(x=lon, y=lat, z=dep, t=np.zeros(n), data=od, **kw)
+    pt.to_next_stop(t_stop)
+    L = _lib.lib()
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()  # noqa: E731
+    hin = [pin(lon), pin(lat), pin(dep), pin(np.zeros(n))]
+    outf = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]
+    outi = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(6)]
+    io = _lib.TrackIO()
+    io.n = n
+    io.lon, io.lat, io.dep, io.t = (h.data_ptr() for h in hin)
+    io.out_lon, io.out_lat, io.out_dep = (h.data_ptr() for h in outf)
+    io.out_face, io.out_iy, io.out_ix, io.out_izl, io.out_ncross, io.out_status = (h.data_ptr() for h in outi)
+    scratch = torch.empty(int(L.sdk_track_scratch_bytes(n)), dtype=torch.uint8, device="cuda")
+    par = pt._params(200)
+    par.stats = None
+    _lib.check(
+        L.sdk_track_host(od.grid_handle(), C.byref(pt._vel), C.byref(io), None, 0, float(t_stop), C.byref(par), scratch.data_ptr(), _lib.current_stream()),
+        "sdk_track_host",
+    )
+    for got, name in zip(outf, ("lon", "lat", "dep")):
+        np.testing.assert_array_equal(got.numpy(), getattr(pt, name), err_msg=name)
+    for got, name in zip(outi[:4], ("face", "iy", "ix", "izl_lin")):
+        np.testing.assert_array_equal(got.numpy(), getattr(pt, name), err_msg=name)
+    assert int(outi[4].numpy().sum()) == pt.crossings
+
+
+def test_sharded_run_equals_single_run():
+    """disjoint particle slices advected separately and un-sharded give bit for bit what
+    one run over all particles gives (particles do not interact)."""
+    import torch
+
+    from seaduck_b200 import parallel, synthetic
+
+    sd = _sd()
+    n, world = 5000, 4
+    ds = synthetic.llc(n=30, nz=8)
+    lon, lat, dep = synthetic.llc_seed_particles(ds, n, seed=9, depth_range=(5, 300))
+    kw = dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True)
+    od = sd.OceData(ds)
+    t_stop = 30 * cases.DAY
+    whole = sd.Particle(x=lon, y=lat, z=dep, t=np.zeros(n), data=od, **kw)
+    whole.to_next_stop(t_stop)
+    per = -(-n // world)
+    blocks = []
+    for r in range(world):
+        idx = parallel.shard_indices(n, world, r, seed=5)
+        pt = sd.Particle(x=lon[idx], y=lat[idx], z=dep[idx], t=np.zeros(len(idx)), data=od, **kw)
+        pt.to_next_stop(t_stop)
+        blocks.append(parallel.pack_snapshot(pt._st, n_pad=per))
+    out = parallel.unshard(torch.stack(blocks), n, world, seed=5)
+    for name, ref in (("lon", whole.lon), ("lat", whole.lat), ("dep", whole.dep), ("face", whole.face), ("iy", whole.iy),
+                      ("ix", whole.ix), ("izl", whole.izl_lin)):
+        np.testing.assert_array_equal(out[name], ref, err_msg=name)
