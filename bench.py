@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--peer-gather", action="store_true", help="ship snapshots with copy-engine writes into peer memory instead of NCCL")
     ap.add_argument("--eager", action="store_true", help="reference-style to_next_stop (host reads the call statistics every step)")
     ap.add_argument("--no-gather", action="store_true", help="(diagnostic) skip the snapshot all-gather at N > 1")
-    ap.add_argument("--reserve-sms", type=int, default=-1, help="SMs left to the snapshot all-gather (default: 8 when N > 1)")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="SMs the advection kernel leaves to the snapshot all-gather (default 0: measured best, NCCL runs in the kernel tails)")
     return ap.parse_args()
 
 
@@ -182,7 +182,12 @@ def run_cuda(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    reserve = max(a.reserve_sms, 0)
     if world > 1:
+        if reserve > 0:
+            # one NCCL channel = one CTA: no more channels than SMs the advection kernel leaves free,
+            # or the collective's remaining CTAs would have to wait for the end of that kernel
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(reserve))
         dist.init_process_group("nccl", device_id=dev)
     import seaduck_b200 as sd
     from seaduck_b200 import _lib
@@ -195,7 +200,6 @@ def run_cuda(a):
     t_stop = a.days * DAY
     nb = min(a.warmup + a.steps, a.max_batches)
 
-    reserve = a.reserve_sms if a.reserve_sms >= 0 else (8 if world > 1 else 0)
     side = torch.cuda.Stream(dev) if world > 1 else None
 
     def make_batch(b):
@@ -369,7 +373,7 @@ def run_cuda(a):
                 "batches": f"{nb} distinct batches resident in HBM" + (", reused cyclically with a device-side state restore inside the timed region" if reuse else ", one per step"),
                 "l2": "inputs larger than L2 (fields 168 MB + 220 MB of particle state per batch, a different batch every step); no flush",
                 "collective": (f"all-gather of the output snapshot per step ({gatherer.mode}: "
-                               + ("copy-engine writes into peer memory" if gatherer.mode == "peer" else f"async NCCL all_gather_into_tensor on {reserve} SMs the advection kernel leaves free")
+                               + ("copy-engine writes into peer memory" if gatherer.mode == "peer" else "async NCCL all_gather_into_tensor on a side stream" + (f", {reserve} SMs left free by the advection kernel" if reserve else ""))
                                + ", overlapped with the next step"
                                + f", {parallel.SNAPSHOT_ROWS * 8 * n * world} B received per rank and step)") if world > 1 else "none",
                 "step_ms_first10": [round(x, 3) for x in step_ms[:10]], "host_wall_s": wall,

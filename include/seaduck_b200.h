@@ -309,9 +309,9 @@ int sdk_finish_stop(double *t, int32_t *it, const double *time_midp, int32_t n_m
 int sdk_time_index(const double *t, const double *time_midp, int32_t n_midp, int32_t *it, int64_t n,
                    void *stream);
 
-/* Output snapshot of a stop in 40 bytes per particle (what Particle.to_list_of_time returns per stop
- * and the ranks exchange): out[0..2][n_pad] = lon, lat, dep; out[3] = (face, iy) and
- * out[4] = (ix, izl) as pairs of int32 in one 8-byte slot.  NULL inputs read as zero; device pointers. */
+/* Output snapshot of a stop in 32 bytes per particle (what Particle.to_list_of_time returns per stop
+ * and the ranks exchange): out[0..2][n_pad] = lon, lat, dep; out[3][n_pad] = one 64-bit word
+ * face << 34 | iy << 21 | ix << 8 | izl (6 + 13 + 13 + 8 bits).  NULL inputs read as zero; device pointers. */
 int sdk_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
                       const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl, double *out,
                       void *stream);

@@ -31,13 +31,10 @@ __global__ void pack_snapshot_kernel(int64_t n, int64_t n_pad, const double *lon
     out[i] = in && lon ? lon[i] : 0.0;
     out[n_pad + i] = in && lat ? lat[i] : 0.0;
     out[2 * n_pad + i] = in && dep ? dep[i] : 0.0;
-    int2 a, b;
-    a.x = in && face ? face[i] : 0;
-    a.y = in && iy ? iy[i] : 0;
-    b.x = in && ix ? ix[i] : 0;
-    b.y = in && izl ? izl[i] : 0;
-    reinterpret_cast<int2 *>(out + 3 * n_pad)[i] = a;
-    reinterpret_cast<int2 *>(out + 4 * n_pad)[i] = b;
+    // face (6 bits) | iy (13) | ix (13) | izl (8) in one word: 32 bytes per particle on the wire
+    const unsigned long long f = in && face ? (unsigned)face[i] : 0u, y = in && iy ? (unsigned)iy[i] : 0u;
+    const unsigned long long x = in && ix ? (unsigned)ix[i] : 0u, z = in && izl ? (unsigned)izl[i] : 0u;
+    reinterpret_cast<unsigned long long *>(out + 3 * n_pad)[i] = (f & 63) << 34 | (y & 8191) << 21 | (x & 8191) << 8 | (z & 255);
 }
 
 cudaError_t launch_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,

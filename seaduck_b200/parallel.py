@@ -25,13 +25,15 @@ def shard_indices(n, world, rank, seed=0):
     return perm[rank * per : min((rank + 1) * per, n)]
 
 
-SNAPSHOT_ROWS = 5  # lon, lat, dep, (face, iy), (ix, izl): 40 bytes per particle
+SNAPSHOT_ROWS = 4  # lon, lat, dep, one word of indices: 32 bytes per particle
+_SHIFT = {"face": 34, "iy": 21, "ix": 8, "izl": 0}
+_BITS = {"face": 6, "iy": 13, "ix": 13, "izl": 8}
 
 
 def pack_snapshot(state, n_pad=None):
-    """One contiguous float64 tensor [5, n_pad] from a particle state dict: positions as they are, the
-    four indices as two pairs of int32 sharing an 8-byte slot (one ``sdk_pack_snapshot`` launch on the
-    GPU; plain torch ops for host tensors)."""
+    """One contiguous float64 tensor [4, n_pad] from a particle state dict: positions as they are, the
+    four indices bit-packed into one 64-bit word (face 6 bits, iy 13, ix 13, izl 8) -- one
+    ``sdk_pack_snapshot`` launch on the GPU, plain torch ops for host tensors."""
     import torch
 
     n = state["lon"].shape[0]
@@ -52,21 +54,22 @@ def pack_snapshot(state, n_pad=None):
     for k, name in enumerate(("lon", "lat", "dep")):
         if state.get(name) is not None:
             out[k, :n] = state[name].to(torch.float64)
-    ints = out[3:].view(torch.int32).view(2, n_pad, 2)
-    for (row, col), name in zip(((0, 0), (0, 1), (1, 0), (1, 1)), ("face", "iy", "ix", "izl")):
+    word = torch.zeros(n_pad, dtype=torch.int64)
+    for name in ("face", "iy", "ix", "izl"):
         if state.get(name) is not None:
-            ints[row, :n, col] = state[name].to(torch.int32)
+            word[:n] |= (state[name].to(torch.int64) & ((1 << _BITS[name]) - 1)) << _SHIFT[name]
+    out[3] = word.view(torch.float64)
     return out
 
 
 def unpack_snapshot(packed):
-    """Inverse of :func:`pack_snapshot` for one rank's [5, n] block -> dict of numpy arrays."""
+    """Inverse of :func:`pack_snapshot` for one rank's [4, n] block -> dict of numpy arrays."""
     g = packed.cpu().numpy() if hasattr(packed, "cpu") else np.asarray(packed)
     g = np.ascontiguousarray(g)
     out = {"lon": g[0], "lat": g[1], "dep": g[2]}
-    a = g[3].view(np.int32).reshape(-1, 2)
-    b = g[4].view(np.int32).reshape(-1, 2)
-    out["face"], out["iy"], out["ix"], out["izl"] = a[:, 0], a[:, 1], b[:, 0], b[:, 1]
+    word = g[3].view(np.int64)
+    for name in ("face", "iy", "ix", "izl"):
+        out[name] = ((word >> _SHIFT[name]) & ((1 << _BITS[name]) - 1)).astype(np.int32)
     return out
 
 

@@ -135,7 +135,7 @@ def test_lazy_mode_list_of_time_matches_golden():
 
 
 def test_pack_snapshot_device_equals_host():
-    """sdk_pack_snapshot (one launch) writes the same 40-byte records as the torch fallback."""
+    """sdk_pack_snapshot (one launch) writes the same 32-byte records as the torch fallback."""
     import torch
 
     from seaduck_b200 import parallel
