@@ -46,7 +46,9 @@ def parse():
     ap.add_argument("--particles", type=int, default=1_000_000, help="particles per GPU and batch")
     ap.add_argument("--days", type=float, default=30.0, help="simulated days per step")
     ap.add_argument("--grid", type=int, default=90)
-    ap.add_argument("--levels", type=int, default=50)
+    ap.add_argument("--levels", type=int, default=50, help="vertical levels; 0 = surface-only 2-D run (configs[3] shape)")
+    ap.add_argument("--snapshots", type=int, default=0, help="time snapshots of the velocity field (0 = steady)")
+    ap.add_argument("--save-raw", action="store_true", help="write the reference's crossing log (configs[4]): count pass + fill pass per step")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="field storage (math is fp64)")
     ap.add_argument("--no-sort", action="store_true", help="keep particles in seeding order")
     ap.add_argument("--max-batches", type=int, default=24, help="distinct batches kept in HBM (reused cyclically)")
@@ -64,14 +66,19 @@ def parse():
 
 
 def workload_name(a):
-    return (f"LLC{a.grid}-shaped 3D synthetic transports (13x{a.grid}x{a.grid}x{a.levels}), "
-            f"{a.particles} particles per GPU and step, {a.days:g} d per step")
+    shape = f"3D synthetic transports (13x{a.grid}x{a.grid}x{a.levels})" if a.levels else f"surface-only 2D synthetic transports (13x{a.grid}x{a.grid})"
+    extra = (f", {a.snapshots} time snapshots" if a.snapshots else "") + (", crossing log written (save_raw)" if a.save_raw else "")
+    return f"LLC{a.grid}-shaped {shape}{extra}, {a.particles} particles per GPU and step, {a.days:g} d per step"
+
+
+def kwargs_of(a):
+    return dict(KW) if a.levels else dict(uname="utrans", vname="vtrans", wname=None, transport=True)
 
 
 def make_dataset(a):
     from seaduck_b200 import synthetic
 
-    return synthetic.llc(n=a.grid, nz=a.levels, dtype=np.float64 if a.dtype == "f64" else np.float32)
+    return synthetic.llc(n=a.grid, nz=a.levels, nt=a.snapshots, dtype=np.float64 if a.dtype == "f64" else np.float32)
 
 
 def seeds(ds, n, seed):
@@ -129,7 +136,7 @@ def oracle_particle(a, n, threads, seed=99):
     ds = make_dataset(a)
     od = OceData(ds)
     lon, lat, dep = seeds(ds, n, seed)
-    return oracle.oracle_particle_from_od(od, lon, lat, dep, np.zeros(n), nthreads=threads, **KW)
+    return oracle.oracle_particle_from_od(od, lon, lat, dep if a.levels else np.full(n, -1.0), np.zeros(n), nthreads=threads, **kwargs_of(a))
 
 
 def cpu_baseline(a, threads):
@@ -206,11 +213,12 @@ def run_cuda(a):
         lon, lat, dep = seeds(ds, n, seed=1000 + 97 * rank + b)  # disjoint particle slices per rank / batch
         if not a.no_sort:
             # cell-major order so that the lanes of a warp touch neighbouring memory (K5)
-            loc = od.locate(x=lon, y=lat, z=dep)
-            key = ((loc["izl"].long() * 13 + loc["face"].long()) * a.grid + loc["iy"].long()) * a.grid + loc["ix"].long()
+            loc = od.locate(x=lon, y=lat, z=dep if a.levels else None)
+            lev = loc["izl"].long() if a.levels else 0
+            key = ((lev * 13 + loc["face"].long()) * a.grid + loc["iy"].long()) * a.grid + loc["ix"].long()
             order = torch.argsort(key).cpu().numpy()
             lon, lat, dep = lon[order], lat[order], dep[order]
-        pt = sd.Particle(x=lon, y=lat, z=dep, t=np.zeros(n), data=od, **KW)
+        pt = sd.Particle(x=lon, y=lat, z=dep if a.levels else np.full(n, -1.0), t=np.zeros(n), data=od, save_raw=a.save_raw, **kwargs_of(a))
         pt.lazy = not a.eager  # device-side end-of-stop bookkeeping: the host never waits inside a step
         pt.tuning = dict(refill_threshold=a.refill, blocks_per_sm=a.blocks_per_sm, threads_per_block=a.threads)
         if reserve > 0:
@@ -242,6 +250,8 @@ def run_cuda(a):
         pt = batches[b]
         if i >= nb:
             restore(b)
+        if a.save_raw:
+            pt.empty_lists()  # the log of this step only (the reference's to_list_of_time does the same)
         pt.to_next_stop(t_stop)
         if world > 1 and not a.no_gather:
             # output trajectories of all ranks -- the only exchange of the path: shipped over
@@ -307,7 +317,10 @@ def run_cuda(a):
     sampler.stop_flag = True
     sampler.join(timeout=2)
     kms, kcr = float(np.mean(kern_ms)), float(np.mean(kern_cross))
-    algo_bytes = kcr * ALGO_BYTES_PER_CROSSING + n * STATE_BYTES_PER_PARTICLE
+    per_crossing = ALGO_BYTES_PER_CROSSING if a.levels else 72  # 2-D crossing = 4 walls + Vol + corners
+    if a.dtype == "f32":
+        per_crossing = 60 if a.levels else 52
+    algo_bytes = kcr * per_crossing + n * STATE_BYTES_PER_PARTICLE
     achieved = algo_bytes / (kms * 1e-3) / 1e9
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -321,7 +334,7 @@ def run_cuda(a):
 
     # ---- end to end through the C ABI with host buffers ------------------------------------------------
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and a.levels and not a.save_raw:
         pin = lambda arr: torch.from_numpy(np.ascontiguousarray(arr)).pin_memory()  # noqa: E731
         hin = [pin(x) for x in host_inputs] + [torch.zeros(n, dtype=torch.float64).pin_memory()]
         hout_f = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]

@@ -442,8 +442,9 @@ class Particle(Position):
         offset = torch.zeros(self.N + 1, dtype=torch.int64, device=dev)
         torch.cumsum(cnt, 0, out=offset[1:])
         total = int(offset[-1].item())
-        rec = {k: torch.zeros(total, dtype=torch.int32, device=dev) for k in _lib.LOG_I32}
-        rec.update({k: torch.zeros(total, dtype=torch.float64, device=dev) for k in _lib.LOG_F64})
+        # (every record up to `total` is written by the fill pass: no need to clear 150 B x total first)
+        rec = {k: torch.empty(total, dtype=torch.int32, device=dev) for k in _lib.LOG_I32}
+        rec.update({k: torch.empty(total, dtype=torch.float64, device=dev) for k in _lib.LOG_F64})
         lg.capacity = total
         lg.offset = offset.data_ptr()
         for k, tns in rec.items():
