@@ -133,16 +133,23 @@ typedef struct sdk_advect_params {
     uint64_t *stats;
 } sdk_advect_params;
 
+/* One record of the crossing log: the 19 fields Particle.note_taking appends (seaduck/lagrangian.py:301),
+ * 128 bytes, so a lane writes four full 32-byte sectors per record. */
+typedef struct sdk_log_record {
+    double rzl, rx, ry, tt, uu, vv, ww, du, dv, dw, xx, yy, zz;
+    int32_t fc, it, izl, iy, ix, vs; /* vs = stamp: 0..6 tend, 7 after a crossing, 15 start of a stop */
+} sdk_log_record;
+
 /* Crossing log, replaces Particle.note_taking (seaduck/lagrangian.py:301).  Device pointers.
- * Records of particle i go to [offset[i], offset[i] + count[i]).  With offset == NULL only
+ * Records of particle i go to records[offset[i] .. offset[i] + count[i]).  With offset == NULL only
  * count[] is written (first pass of count -> scan -> fill). */
 typedef struct sdk_log {
     int64_t capacity;
     const int64_t *offset;
     int32_t *count;
-    int32_t *fc, *it, *izl, *iy, *ix, *vs;
-    double *rzl, *rx, *ry, *tt, *uu, *vv, *ww, *du, *dv, *dw, *xx, *yy, *zz;
+    sdk_log_record *records;
     int32_t emit_start; /* write the stamp-15 record first (lagrangian.py:887) */
+    int32_t reserved;
 } sdk_log;
 
 int sdk_abi_version(void);

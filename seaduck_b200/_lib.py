@@ -98,11 +98,11 @@ LOG_F64 = "rzl rx ry tt uu vv ww du dv dw xx yy zz".split()
 
 
 class Log(C.Structure):
-    _fields_ = (
-        [("capacity", C.c_int64), ("offset", vp), ("count", vp)]
-        + [(n, vp) for n in LOG_I32 + LOG_F64]
-        + [("emit_start", C.c_int32)]
-    )
+    _fields_ = [("capacity", C.c_int64), ("offset", vp), ("count", vp), ("records", vp), ("emit_start", C.c_int32), ("reserved", C.c_int32)]
+
+
+# numpy view of sdk_log_record (128 bytes)
+LOG_RECORD = [(n, "<f8") for n in LOG_F64] + [(n, "<i4") for n in LOG_I32]
 
 
 LOCATED = (

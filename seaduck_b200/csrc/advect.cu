@@ -110,25 +110,17 @@ __device__ __forceinline__ void note(const AdvectArgs &a, Lane &s, int stamp) {
     if (L.offset) {
         const int64_t r = L.offset[s.pid] + s.nrec;
         if (r < L.capacity) {
-            L.fc[r] = s.f;
-            L.it[r] = s.it;
-            L.izl[r] = s.izl;
-            L.rzl[r] = s.rzl;
-            L.iy[r] = s.iy;
-            L.ix[r] = s.ix;
-            L.rx[r] = s.rx;
-            L.ry[r] = s.ry;
-            L.tt[r] = s.t;
-            L.uu[r] = s.u;
-            L.vv[r] = s.v;
-            L.ww[r] = s.w;
-            L.du[r] = s.du;
-            L.dv[r] = s.dv;
-            L.dw[r] = s.dw;
-            L.xx[r] = s.lon;
-            L.yy[r] = s.lat;
-            L.zz[r] = s.dep;
-            L.vs[r] = stamp;
+            // one 128-byte record = eight 16-byte stores to consecutive addresses
+            double2 *dst = reinterpret_cast<double2 *>(L.records + r);
+            dst[0] = make_double2(s.rzl, s.rx);
+            dst[1] = make_double2(s.ry, s.t);
+            dst[2] = make_double2(s.u, s.v);
+            dst[3] = make_double2(s.w, s.du);
+            dst[4] = make_double2(s.dv, s.dw);
+            dst[5] = make_double2(s.lon, s.lat);
+            int4 *idst = reinterpret_cast<int4 *>(dst + 6);
+            idst[0] = make_int4(__double2loint(s.dep), __double2hiint(s.dep), s.f, s.it);
+            idst[1] = make_int4(s.izl, s.iy, s.ix, stamp);
         }
     }
     s.nrec += 1;

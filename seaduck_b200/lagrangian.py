@@ -372,26 +372,37 @@ class Particle(Position):
             raise NotImplementedError("note_taking is done inside the advection kernel")
         self.__dict__["_pending_start"] = True
 
+    @staticmethod
+    def _host_chunk(ch):
+        """Host view of one chunk of the log: numpy structured array + offsets (fetched once)."""
+        if "host" not in ch:
+            rec = ch["records"].cpu().numpy().view(np.dtype(_lib.LOG_RECORD)).reshape(-1)
+            ch["host"] = (rec, ch["offset"].cpu().numpy())
+        return ch["host"]
+
     def _raw_list(self, attr):
         if not self.save_raw:
             raise AttributeError("This is not a particle_rawlist object")
         key = _LIST_NAMES[attr]
         if key == "fc" and self._st.get("face") is None:
             raise AttributeError(attr)
-        chunks = self._raw
         out = [[] for _ in range(self.N)]
-        for ch in chunks:
-            vals = ch[key].cpu().numpy()
-            off = ch["offset"]
+        for ch in self._raw:
+            rec, off = self._host_chunk(ch)
+            vals = rec[key]
             for i in range(self.N):
                 out[i].extend(vals[off[i] : off[i + 1]].tolist())
         return out
 
     def raw_arrays(self):
-        """Crossing log of the last stop(s) as flat numpy arrays + per-particle offsets."""
+        """Crossing log of the last stop(s): per chunk a dict of flat numpy arrays (views into the
+        128-byte records) + per-particle ``offset``."""
         out = []
         for ch in self._raw:
-            out.append({k: (v if k == "offset" else v.cpu().numpy()) for k, v in ch.items()})
+            rec, off = self._host_chunk(ch)
+            d = {k: rec[k] for k in _lib.LOG_I32 + _lib.LOG_F64}
+            d["offset"] = off
+            out.append(d)
         return out
 
     # ------------------------------------------------------------------------------------------
@@ -442,17 +453,14 @@ class Particle(Position):
         offset = torch.zeros(self.N + 1, dtype=torch.int64, device=dev)
         torch.cumsum(cnt, 0, out=offset[1:])
         total = int(offset[-1].item())
-        # (every record up to `total` is written by the fill pass: no need to clear 150 B x total first)
-        rec = {k: torch.empty(total, dtype=torch.int32, device=dev) for k in _lib.LOG_I32}
-        rec.update({k: torch.empty(total, dtype=torch.float64, device=dev) for k in _lib.LOG_F64})
+        # one array of 128-byte records (every record up to `total` is written by the fill pass)
+        records = torch.empty((total, 128), dtype=torch.uint8, device=dev)
         lg.capacity = total
         lg.offset = offset.data_ptr()
-        for k, tns in rec.items():
-            setattr(lg, k, tns.data_ptr())
+        lg.records = records.data_ptr()
         # pass 2: same trajectory, now writing the records
         _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par), C.byref(lg), 1, stream), "sdk_advect(log)")
-        rec["offset"] = offset.cpu().numpy()
-        self._raw.append(rec)
+        self._raw.append({"records": records, "offset": offset})
 
     def to_next_stop(self, t_stop):
         """Integrate all particles to ``t_stop`` (reference ``lagrangian.py:741``).
