@@ -464,6 +464,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
     bool queue_empty = false;
     // per-lane totals for the call statistics (reduced per warp at the end: a few thousand atomics)
     unsigned acc_live = 0, acc_cross = 0, acc_max = 0, acc_flag = 0;
+    unsigned iter = 0;
     for (;;) {
         // ---- refill idle lanes from the global queue (warp-aggregated)
         const unsigned idle = __ballot_sync(full, !have);
@@ -486,7 +487,9 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
             }
         }
 #if SDK_ADVECT_LOCKSTEP
-        if (!__syncthreads_or(have)) break;
+        // meet the other warps of the CTA every SDK_ADVECT_LOCKSTEP-th iteration (the exit test has
+        // to be block-uniform, so it is only made there; a warp without work idles in between)
+        if ((iter++ % SDK_ADVECT_LOCKSTEP) == 0 && !__syncthreads_or(have)) break;
 #else
         if (!__any_sync(full, have)) break;
 #endif
