@@ -16,6 +16,46 @@
 
 namespace sdk {
 
+// Per-particle state of a lane.  The hot half (position, velocity, cell) lives in registers.  The
+// cold half -- read or written once or twice per step -- can live in shared memory
+// (SDK_ADVECT_COLD_SMEM=1): one column per thread, [field][thread] so that a warp's access is
+// conflict free.  That takes the kernel from 128 to 96 / 80 registers (5 / 6 instead of 4 CTAs per
+// SM) without the compiler choosing what to spill; the members are references, so the rest of the
+// code reads the same either way.  Measured (profiles/README.md, r01i): the extra warps only win
+// back what the shared-memory traffic costs (1.63 ms vs 1.59 ms per launch), because the kernel is
+// bound by instruction supply, not by latency -- off by default.
+#ifndef SDK_ADVECT_COLD_SMEM
+#define SDK_ADVECT_COLD_SMEM 0
+#endif
+constexpr int kColdDoubles = 12;  // px[4], py[4], bzl, dzl, vol, pid
+[[maybe_unused]] constexpr int kColdInts = 7;  // dx, dy (float bits), it, status, niter, ncross, nrec
+
+#if SDK_ADVECT_COLD_SMEM
+struct ColdArr {
+    double *b;
+    int stride;
+    __device__ __forceinline__ double &operator[](int j) const { return b[j * stride]; }
+};
+
+struct Lane {
+    double lon, lat, dep, t;
+    double rx, ry, rzl;
+    double u, v, w, du, dv, dw;
+    int f, iy, ix, izl;
+    ColdArr px, py;
+    double &bzl, &dzl, &vol;
+    float &dx, &dy;
+    int &it, &status, &niter, &ncross, &nrec;
+    long long &pid;
+    // cd / ci: this thread's column of the cold doubles / ints, consecutive fields `stride` apart
+    __device__ __forceinline__ Lane(double *cd, int *ci, int stride)
+        : px{cd, stride}, py{cd + 4 * stride, stride}, bzl(cd[8 * stride]), dzl(cd[9 * stride]), vol(cd[10 * stride]),
+          dx(reinterpret_cast<float &>(ci[0])), dy(reinterpret_cast<float &>(ci[stride])), it(ci[2 * stride]),
+          status(ci[3 * stride]), niter(ci[4 * stride]), ncross(ci[5 * stride]), nrec(ci[6 * stride]),
+          pid(reinterpret_cast<long long &>(cd[11 * stride])) {}
+};
+#define SDK_LANE(name, cd, ci, stride) Lane name(cd, ci, stride)
+#else
 struct Lane {
     double lon, lat, dep, t;
     double rx, ry, rzl;
@@ -25,8 +65,19 @@ struct Lane {
     float dx, dy;
     int f, iy, ix, izl, it;
     int status, niter, ncross, nrec;
-    int64_t pid;
+    long long pid;
 };
+#define SDK_LANE(name, cd, ci, stride) Lane name
+#endif
+
+// bytes of dynamic shared memory of a CTA: the two vertical tables + the cold columns
+__host__ __device__ inline size_t advect_smem_bytes(int n_zl, int n_z, int threads) {
+    size_t b = (sizeof(float) * (size_t)(n_zl + n_z) + 15) & ~(size_t)15;
+#if SDK_ADVECT_COLD_SMEM
+    b += (size_t)threads * (kColdDoubles * sizeof(double) + kColdInts * sizeof(int));
+#endif
+    return b;
+}
 
 __device__ __forceinline__ void load_lane(const sdk_particles &p, int64_t i, int has_dep, Lane &s) {
     s.pid = i;
@@ -75,7 +126,7 @@ __device__ __forceinline__ void load_lane(const sdk_particles &p, int64_t i, int
 }
 
 __device__ __forceinline__ void store_lane(const sdk_particles &p, int has_dep, const Lane &s) {
-    const int64_t i = s.pid;
+    const long long i = s.pid;
     p.lon[i] = s.lon;
     p.lat[i] = s.lat;
     p.t[i] = s.t;
@@ -407,7 +458,8 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
             for (int j = 0; j < 4; ++j) s.px[j] = s.lon + to_180((double)gx[j] - s.lon);
         }
         redo = false;
-        inverse_bilinear_fast(s.lon, s.lat, s.px, s.py, s.rx, s.ry, redo);
+        const double qx[4] = {s.px[0], s.px[1], s.px[2], s.px[3]}, qy[4] = {s.py[0], s.py[1], s.py[2], s.py[3]};
+        inverse_bilinear_fast(s.lon, s.lat, qx, qy, s.rx, s.ry, redo);
         if (redo) {
             const double2 r = inverse_bilinear_slow(s.lon, s.lat, s.px[0], s.px[1], s.px[2], s.px[3], s.py[0], s.py[1], s.py[2], s.py[3]);
             s.rx = r.x, s.ry = r.y;
@@ -449,22 +501,27 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
 template <typename T, bool LOG>
 __global__ void __launch_bounds__(SDK_ADVECT_THREADS, SDK_ADVECT_MIN_BLOCKS)
 advect_kernel(const __grid_constant__ AdvectArgs a) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     float *sZl = smem;
     float *sdZl = smem + a.g.n_zl;
     for (int k = threadIdx.x; k < a.g.n_zl; k += blockDim.x) sZl[k] = a.g.Zl[k];
     for (int k = threadIdx.x; k < a.g.n_z; k += blockDim.x) sdZl[k] = a.g.dZl[k];
     __syncthreads();
+    double *cold_d = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + advect_smem_bytes(a.g.n_zl, a.g.n_z, 0)) + threadIdx.x;
+    int *cold_i = reinterpret_cast<int *>(cold_d - threadIdx.x + kColdDoubles * blockDim.x) + threadIdx.x;
+    (void)cold_i;
 
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int64_t n = a.p.n;
-    Lane s;
+    SDK_LANE(s, cold_d, cold_i, (int)blockDim.x);
     bool have = false, live = false;
     bool queue_empty = false;
     // per-lane totals for the call statistics (reduced per warp at the end: a few thousand atomics)
     unsigned acc_live = 0, acc_cross = 0, acc_max = 0, acc_flag = 0;
+#if SDK_ADVECT_LOCKSTEP
     unsigned iter = 0;
+#endif
     for (;;) {
         // ---- refill idle lanes from the global queue (warp-aggregated)
         const unsigned idle = __ballot_sync(full, !have);
@@ -530,7 +587,11 @@ template <typename T>
 __global__ void __launch_bounds__(128) get_u_du_kernel(const __grid_constant__ AdvectArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.p.n) return;
-    Lane s;
+    extern __shared__ __align__(16) float smem[];
+    double *cold_d = reinterpret_cast<double *>(smem) + threadIdx.x;
+    int *cold_i = reinterpret_cast<int *>(cold_d - threadIdx.x + kColdDoubles * blockDim.x) + threadIdx.x;
+    (void)cold_i;
+    SDK_LANE(s, cold_d, cold_i, (int)blockDim.x);
     load_lane(a.p, i, a.has_dep, s);
     if (a.has_dep) {
         // keep dzl as stored; only the velocities change
@@ -556,11 +617,20 @@ namespace sdk {
 
 int advect_max_threads() { return SDK_ADVECT_THREADS; }
 int advect_default_threads() { return SDK_ADVECT_DEFAULT_THREADS; }
-int advect_default_blocks_per_sm() { return 512 / SDK_ADVECT_DEFAULT_THREADS; }
+int advect_default_blocks_per_sm() { return SDK_ADVECT_MIN_BLOCKS * SDK_ADVECT_THREADS / SDK_ADVECT_DEFAULT_THREADS; }
 
 cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaStream_t stream) {
-    const size_t smem = sizeof(float) * (size_t)(args.g.n_zl + args.g.n_z);
+    const size_t smem = advect_smem_bytes(args.g.n_zl, args.g.n_z, threads);
     const bool f32 = args.v.dtype == SDK_F32;
+    static bool attr_done = false;
+    if (!attr_done) {  // CTAs of more than ~384 threads need more than the default 48 KB of dynamic shared memory
+        const int cap = 200 * 1024;
+        cudaFuncSetAttribute(advect_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(advect_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(advect_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        cudaFuncSetAttribute(advect_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+        attr_done = true;
+    }
     if (args.has_log) {
         if (f32) advect_kernel<float, true><<<blocks, threads, smem, stream>>>(args);
         else advect_kernel<double, true><<<blocks, threads, smem, stream>>>(args);
@@ -575,8 +645,9 @@ cudaError_t launch_get_u_du(const AdvectArgs &args, cudaStream_t stream) {
     const int threads = 128;
     const int blocks = (int)((args.p.n + threads - 1) / threads);
     if (blocks == 0) return cudaSuccess;
-    if (args.v.dtype == SDK_F32) get_u_du_kernel<float><<<blocks, threads, 0, stream>>>(args);
-    else get_u_du_kernel<double><<<blocks, threads, 0, stream>>>(args);
+    const size_t smem = advect_smem_bytes(0, 0, threads);
+    if (args.v.dtype == SDK_F32) get_u_du_kernel<float><<<blocks, threads, smem, stream>>>(args);
+    else get_u_du_kernel<double><<<blocks, threads, smem, stream>>>(args);
     return cudaGetLastError();
 }
 

@@ -196,7 +196,7 @@ int sdk_advect(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particle
     cudaError_t e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_advect: memset");
     const int threads = (par && par->threads_per_block > 0) ? par->threads_per_block : sdk::advect_default_threads();
-    const int per_sm = (par && par->blocks_per_sm > 0) ? par->blocks_per_sm : 512 / threads;
+    const int per_sm = (par && par->blocks_per_sm > 0) ? par->blocks_per_sm : sdk::advect_default_blocks_per_sm() * sdk::advect_default_threads() / threads;
     int64_t need = (p->n + threads - 1) / threads;
     int sms = grid->sm_count - ((par && par->reserve_sms > 0) ? par->reserve_sms : 0);
     if (sms < 1) sms = 1;
