@@ -61,7 +61,8 @@ def run_case(case):
     warnings.simplefilter("ignore")
     od = sd.OceData(case["ds"])
     with contextlib.redirect_stdout(io.StringIO()):
-        pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, save_raw=True, **case["kw"])
+        where = case["seeding"] if "seeding" in case else dict(x=case["x"], y=case["y"], z=case["z"], t=case["t"])
+        pt = sd.Particle(data=od, save_raw=True, **where, **case["kw"])
     out = {}
     grab_state(pt, out, "init_")
     if case.get("list_of_time"):

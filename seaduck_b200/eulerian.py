@@ -161,6 +161,96 @@ class Position:
             self.t = None
         return self
 
+    def from_bool_array(self, t=None, data=None, bool_array=None, num=None, random_seed=None):
+        """Random points in the grid boxes where ``bool_array`` is true, in numbers proportional to the
+        (weighted) cell volume (reference ``eulerian.py:219``).
+
+        Seeding is host work on purpose: it draws from ``np.random`` in the reference's order (rx, ry,
+        rzl_lin), so a given ``random_seed`` yields the reference's particles.  The points are then
+        staged on the device like the result of ``from_latlon``.
+        """
+        import torch  # noqa: PLC0415
+
+        if random_seed is not None:
+            np.random.seed(random_seed)
+        if not isinstance(data, OceData):
+            raise ValueError("Input data must be OceData")
+        if data.readiness["h"] != "oceanparcel":
+            raise NotImplementedError("This method only support datasets that has XG, YG in it.")
+        if not (data.readiness["Z"] and data.readiness["Zl"]):
+            raise NotImplementedError("This method only support datasets that has all Z coords.")
+        self.ocedata = od = data
+        try:
+            od["Vol"]
+        except KeyError:
+            od._add_missing_vol()
+        self.tp = od.tp
+        bool_array = np.asarray(bool_array)
+        inds = np.where(bool_array)
+        np_vol = np.array(od["Vol"] * bool_array)
+        vols = np.array(np_vol[inds])
+        num_each = np.round(vols * num / np.sum(vols)).astype(int)
+        num = int(np.sum(num_each))
+        self.N = num
+        inds = tuple(np.repeat(np.array(i), num_each) for i in inds)
+        if len(inds) == 3:
+            iz, iy, ix = inds
+            ind, face = (iy, ix), None
+        elif len(inds) == 4:
+            iz, face, iy, ix = inds
+            ind = (face, iy, ix)
+        else:
+            raise ValueError("bool_array must be 3 or 4 dimensional")
+        pick = lambda arr: None if arr is None else arr[ind]  # noqa: E731
+        cs, sn, dx, dy, bx, by = pick(od.CS), pick(od.SN), pick(od.dX), pick(od.dY), od.XC[ind], od.YC[ind]
+        rx = np.random.random(num) - 0.5
+        ry = np.random.random(num) - 0.5
+        rzl_lin = np.random.random(num)
+        self.rel.update(HRel(face, iy, ix, rx, ry, cs, sn, dx, dy, bx, by))
+        izl_lin = iz + 1
+        bzl_lin = od.Zl[izl_lin]
+        dzl_lin = od.dZl[izl_lin]  # sic (reference eulerian.py:287)
+        self.rel.update(VlLinRel(izl_lin, rzl_lin, dzl_lin, bzl_lin))
+        self.lon = bx  # temporarily: the corners are unwrapped around it
+        px, py = self.get_px_py()
+        w = self.get_f_node_weight()
+        self.lon = np.einsum("nj,nj->n", w, px.T)
+        self.lat = np.einsum("nj,nj->n", w, py.T)
+        self.dep = self.bzl_lin + self.dzl_lin * self.rzl_lin
+        self.rel.update(od._find_rel_v(self.dep))
+        self.rel.update(od._find_rel_vl(self.dep))
+        if isinstance(t, (int, float, np.floating)):
+            t = np.ones(self.N, float) * t
+        elif isinstance(t, np.ndarray):
+            if len(t) != self.N:
+                raise ValueError("Mismatch between input t and final particle number")
+        if t is not None:
+            self.t = copy.deepcopy(t)
+            if od.readiness["time"]:
+                self.rel.update(od._find_rel_t(t))
+            else:
+                self.rel.update(TRel._make(None for i in range(4)))
+        else:
+            self.rel.update(TRel._make(None for i in range(4)))
+            self.t = None
+        # device copy in the layout sdk_locate produces (Particle takes it from here)
+        dev = od._torch_device()
+        px, py = self.get_px_py()
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dt)).to(dev)  # noqa: E731
+        loc = {
+            "iy": up(iy, np.int32), "ix": up(ix, np.int32), "rx": up(rx, np.float64), "ry": up(ry, np.float64),
+            "px": up(px.reshape(-1), np.float64), "py": up(py.reshape(-1), np.float64),
+            "dx": up(dx if dx is not None else np.zeros(num), np.float32), "dy": up(dy if dy is not None else np.zeros(num), np.float32),
+            "izl": up(izl_lin, np.int32), "rzl": up(rzl_lin, np.float64), "dzl": up(dzl_lin, np.float64), "bzl": up(bzl_lin, np.float64),
+            "_inputs": (up(self.lon, np.float64), up(self.lat, np.float64), up(self.dep, np.float64), None if self.t is None else up(self.t, np.float64)),
+        }
+        if face is not None:
+            loc["face"] = up(face, np.int32)
+        if self.t is not None and od.readiness["time"]:
+            loc["it"] = up(self.it, np.int32)
+        self._located = loc
+        return self
+
     def subset(self, which):
         """Subset of the points (reference ``eulerian.py:319``)."""
         p = object.__new__(type(self))

@@ -103,8 +103,9 @@ class Particle(Position):
     ):
         Position.__init__(self)
         if "bool_array" in kwarg.keys():
-            raise NotImplementedError("from_bool_array seeding is not part of the hot path yet (SURVEY §8f-2)")
-        self.from_latlon(**kwarg)
+            self.from_bool_array(**kwarg)
+        else:
+            self.from_latlon(**kwarg)
         od = self.ocedata
         self.uname, self.vname, self.wname = uname, vname, wname
         self.wknw, self.dwknw = wknw, dwknw

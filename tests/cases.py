@@ -84,7 +84,25 @@ def case_llc_surface2d(n=300, ngrid=48):
     )
 
 
-ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d]
+def case_llc_bool_array(ngrid=24, nz=8):
+    """Particles seeded by ``from_bool_array`` (reference eulerian.py:219): volume-weighted random
+    positions inside a masked region, then advected."""
+    ds = synthetic.llc(n=ngrid, nz=nz)
+    yc = np.asarray(ds["YC"])
+    xc = np.asarray(ds["XC"])
+    region = (np.abs(yc - 20.0) < 14.0) & (np.abs(xc + 10.0) < 16.0)
+    bool_array = np.zeros((nz, 13, ngrid, ngrid), bool)
+    bool_array[1:4] = region[None] & (np.asarray(ds["maskC"])[1:4] > 0)
+    return dict(
+        name="llc_bool_array",
+        ds=ds,
+        seeding=dict(bool_array=bool_array, num=600, random_seed=2024, t=0.0),
+        stops=[15 * DAY, 40 * DAY],
+        kw=dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True),
+    )
+
+
+ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_bool_array]
 
 LOG_INT = ["fc", "it", "izl", "iy", "ix", "vs"]
 LOG_FLT = ["rzl", "rx", "ry", "tt", "uu", "vv", "ww", "du", "dv", "dw", "xx", "yy", "zz"]

@@ -40,6 +40,8 @@ def test_oracle_matches_reference_golden(make, oracle_lib):
     case = make()
     gold = np.load(os.path.join(GOLD, f"lagrangian_{case['name']}.npz"))
     od = OceData(case["ds"])
+    if "seeding" in case:
+        pytest.skip("from_bool_array seeding is host logic of the product; its golden is checked on the GPU path")
     op = oracle_lib.oracle_particle_from_od(od, case["x"], case["y"], case["z"], case["t"], save_raw=True, **case["kw"])
     get = lambda k: getattr(op, STATE_MAP[k])  # noqa: E731
     compare_state(gold, "init_", get)

@@ -50,7 +50,8 @@ def test_cuda_matches_reference_golden(make):
     case = make()
     gold = np.load(os.path.join(GOLD, f"lagrangian_{case['name']}.npz"))
     od = sd.OceData(case["ds"])
-    pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, save_raw=True, **case["kw"])
+    where = case["seeding"] if "seeding" in case else dict(x=case["x"], y=case["y"], z=case["z"], t=case["t"])
+    pt = sd.Particle(data=od, save_raw=True, **where, **case["kw"])
     compare_state(gold, "init_", pt)
     if case.get("list_of_time"):
         stops, snaps = pt.to_list_of_time(normal_stops=case["stops"])
