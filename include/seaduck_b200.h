@@ -290,6 +290,9 @@ typedef struct sdk_points {
     const int32_t *kt;
     const double *rt;
     const float *cs, *sn;
+    /* optional: result of point i goes to out[out_index[i]] (the caller runs the kernel over a
+     * cell-sorted copy of the points and wants the results in its own order); NULL = out[i] */
+    const int32_t *out_index;
 } sdk_points;
 
 /* scalar variable */

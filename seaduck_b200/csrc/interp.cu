@@ -199,8 +199,9 @@ __global__ void __launch_bounds__(128, MAXM <= 9 ? SDK_INTERP_MIN_BLOCKS : 1) in
     find_nodes<MAXM>(a.g, a.ku, f, iy, ix, ns);
     const double rxs = a.fu.xstag ? p.rx[i] + 0.5 : p.rx[i];
     const double rys = a.fu.ystag ? p.ry[i] + 0.5 : p.ry[i];
-    a.out_u[i] = interp_value<MAXM>(a.g, a.ku, a.fu, a.fu, ns, rxs, rys, p.kz ? p.kz[i] : 0, p.rz ? p.rz[i] : 0.0,
-                                    p.kt ? p.kt[i] : 0, p.rt ? p.rt[i] : 0.0);
+    const double r = interp_value<MAXM>(a.g, a.ku, a.fu, a.fu, ns, rxs, rys, p.kz ? p.kz[i] : 0, p.rz ? p.rz[i] : 0.0,
+                                        p.kt ? p.kt[i] : 0, p.rt ? p.rt[i] : 0.0);
+    a.out_u[p.out_index ? (int64_t)p.out_index[i] : i] = r;
 }
 
 template <int MAXM>
@@ -222,8 +223,9 @@ __global__ void __launch_bounds__(128, MAXM <= 9 ? SDK_INTERP_MIN_BLOCKS : 1) in
         u = uu;
         v = vv;
     }
-    a.out_u[i] = u;
-    a.out_v[i] = v;
+    const int64_t o = p.out_index ? (int64_t)p.out_index[i] : i;
+    a.out_u[o] = u;
+    a.out_v[o] = v;
 }
 
 // K4: a dry cell's west / south wall is wet when the cell on the other side is wet; a W point is

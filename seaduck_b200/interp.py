@@ -174,7 +174,7 @@ class Field(C.Structure):
 
 
 class Points(C.Structure):
-    _fields_ = [("n", C.c_int64)] + [(n, C.c_void_p) for n in "face iy ix rx ry kz rz kt rt cs sn".split()]
+    _fields_ = [("n", C.c_int64)] + [(n, C.c_void_p) for n in "face iy ix rx ry kz rz kt rt cs sn out_index".split()]
 
 
 def axis_polynomial(nodes, target, order):
@@ -413,12 +413,52 @@ class _DevicePoints:
     """Device tensors of the attributes of a Position (borrowed from ``from_latlon`` when the
     position has not been edited since, uploaded from the numpy mirrors otherwise)."""
 
+    SORT_THRESHOLD = 200_000
+
     def __init__(self, pos):
         self.pos = pos
         self.od = pos.ocedata
         self.cache = {}
+        self.perm = None
+        self._sorted = None
+        self._setup_sort()
+
+    def _setup_sort(self):
+        """Scattered points make every 8-byte gather cost a 32-byte sector.  For a large, located
+        ``Position`` the kernels therefore run over a cell-sorted copy of the point arrays (threads
+        of a warp then read neighbouring cells) and the results are scattered back to the caller's
+        order.  Permutation and sorted copies are cached with the located state, so several
+        variables (and repeated calls) share them."""
+        import torch  # noqa: PLC0415
+
+        d = self.pos.__dict__
+        loc = d.get("_located")
+        if "_st" in d or loc is None or self.pos.N < self.SORT_THRESHOLD or "iy" not in loc:
+            return
+        if "_perm" not in loc:
+            tp = self.od.tp
+            ny, nx = tp.h_shape[-2:]
+            key = loc["iy"].long() * nx + loc["ix"].long()
+            if "face" in loc:
+                key += loc["face"].long() * (ny * nx)
+            lev = loc.get("iz", loc.get("izl"))
+            if lev is not None:
+                key += lev.long() * (ny * nx * (tp.h_shape[0] if tp.has_face else 1))
+            loc["_perm"] = torch.argsort(key).to(torch.int32)
+            loc["_sorted"] = {}
+        self.perm = loc["_perm"]
+        self._sorted = loc["_sorted"]
+
 
     def get(self, name, integer=False):
+        t = self._get(name, integer)
+        if t is None or self.perm is None:
+            return t
+        if name not in self._sorted:
+            self._sorted[name] = t[self.perm.long()]
+        return self._sorted[name]
+
+    def _get(self, name, integer=False):
         import torch  # noqa: PLC0415
 
         if name in self.cache:
@@ -503,6 +543,9 @@ def _points_struct(pts):
         t = pts.get(name, integer)
         keep.append(t)
         setattr(p, name, None if t is None else t.data_ptr())
+    if pts.perm is not None:
+        p.out_index = pts.perm.data_ptr()  # results go straight back to the caller's order
+        keep.append(pts.perm)
     return p, keep
 
 

@@ -119,3 +119,25 @@ def test_oceinterp_matches_reference():
         sd.OceInterp(od, "T", case["x"], case["y"], case["z"], 5)  # int time: "time format not supported"
     with pytest.raises(AttributeError):
         sd.OceInterp(od, ["__particle.lon"], case["x"], case["y"], case["z"], case["t_euler"])
+
+
+def test_sorted_execution_equals_plain(monkeypatch):
+    """Large located Positions are interpolated in cell-sorted order and scattered back: same numbers."""
+    import seaduck_b200 as sd
+    from seaduck_b200 import interp
+
+    case = ci.case_llc3d(n=3000)
+    od = sd.OceData(case["ds"])
+    knw = sd.KnW(vkernel="linear", tkernel="linear")
+    var = ["T", ("UVELMASS", "VVELMASS")]
+    kernels = [knw, (knw, knw)]
+    pos = sd.Position().from_latlon(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od)
+    plain = ci.flatten_result(pos.interpolate(list(var), list(kernels)))
+    monkeypatch.setattr(interp._DevicePoints, "SORT_THRESHOLD", 100)
+    pos2 = sd.Position().from_latlon(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od)
+    sorted_ = ci.flatten_result(pos2.interpolate(list(var), list(kernels)))
+    assert "_perm" in pos2._located
+    again = ci.flatten_result(pos2.interpolate(list(var), list(kernels)))  # cached permutation
+    for a, b, c in zip(plain, sorted_, again):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)
