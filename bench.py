@@ -296,6 +296,25 @@ def run_cuda(a):
     crossings = sum(pt.crossings for pt in batches) - c0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
 
+    budget = None
+    if a.save_raw:
+        # crossing-log post-processing of the Lagrangian budget on the log of the last step (K5)
+        from seaduck_b200 import lagrangian_budget as lb
+
+        pt = batches[(a.warmup + a.steps - 1) % nb]
+        lb.find_ind_frac_tres_device(pt)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(3):
+            out_b = lb.find_ind_frac_tres_device(pt)
+        b1.record()
+        torch.cuda.synchronize()
+        n_rec = int(out_b[2].shape[0])
+        bms = b0.elapsed_time(b1) / 3
+        budget = {"records": n_rec, "ms": bms, "records_per_s": n_rec / (bms * 1e-3),
+                  "what": "sdk_log_budget: wall indices, cell-traverse fractions and residence times of every log record"}
+
     # ---- the dominant kernel alone: CUDA events right around the C-ABI launch, fresh state each time
     kern_ms, kern_cross = [], []
     stats = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -400,6 +419,8 @@ def run_cuda(a):
             "gpu_launches": a.steps * world,
             "clocks": sampler.summary(),
         }
+        if budget:
+            line["config"]["budget_postprocessing"] = budget
         if e2e:
             line["e2e"] = {"value": e2e_cross_all / e2e_time if e2e_time else None, "unit": "crossings/s",
                            "h2d_bytes_per_step": e2e[2], "d2h_bytes_per_step": e2e[3],

@@ -319,6 +319,14 @@ int sdk_finish_stop(double *t, int32_t *it, const double *time_midp, int32_t n_m
 int sdk_time_index(const double *t, const double *time_midp, int32_t n_midp, int32_t *it, int64_t n,
                    void *stream);
 
+/* Crossing-log post-processing of the Lagrangian budget (seaduck/lagrangian_budget.py:245
+ * find_ind_frac_tres with by_type=True) on a log that is still on the device: records [offset[p],
+ * offset[p+1]) belong to particle p.  ind1 / ind2: int16 [rows][n_rec] (rows = 5 with a face dimension:
+ * iw, iz, face, iy, ix; else 4), frac / tres: double [n_rec]; work: scratch of n_rec doubles.  Device
+ * pointers.  Needs particles with a depth (the reference does too). */
+int sdk_log_budget(const sdk_grid *grid, const sdk_log_record *records, const int64_t *offset, int64_t n_particles,
+                   int64_t n_rec, int16_t *ind1, int16_t *ind2, double *frac, double *tres, double *work, void *stream);
+
 /* Output snapshot of a stop in 32 bytes per particle (what Particle.to_list_of_time returns per stop
  * and the ranks exchange): out[0..2][n_pad] = lon, lat, dep; out[3][n_pad] = one 64-bit word
  * face << 34 | iy << 21 | ix << 8 | izl (6 + 13 + 13 + 8 bits).  NULL inputs read as zero; device pointers. */

@@ -1,0 +1,145 @@
+// K5: crossing-log post-processing of the Lagrangian budget, on the device.
+//
+// Replaces lagrangian_budget.find_ind_frac_tres (reference seaduck/lagrangian_budget.py:245) for a
+// log that is still in HBM (the 128-byte records sdk_advect writes): per record the index of the
+// wall the particle is on (which_wall :85, wall_index :192 incl. the LLC face-edge cases of
+// ind_tend_uv :163), for the first and last record of every particle the walls it came from / goes to
+// and the fraction of the cell traverse (redo_index :223, pseudo_motion :97), and the residence time
+// (residence_time :139, tres_update :144).  One thread per particle walks its records.
+#include <cuda_runtime.h>
+
+#include "budget_args.cuh"
+
+namespace sdk {
+
+// wall_index (lagrangian_budget.py:192): index of wall `iwall` (0 left, 1 right, 2 down, 3 up, 4 deep,
+// 5 shallow) of cell (izl, f, iy, ix) as (iw, iz, [face,] iy, ix)
+__device__ __forceinline__ void wall_index(const GridDev &g, int iwall, int izl, int f, int iy, int ix, int16_t *out,
+                                           int64_t stride, int rows) {
+    int iw = iwall / 2;
+    int iz = izl + (iwall == 4) - 1;
+    int ny_ = iy + (iwall == 3), nx_ = ix + (iwall == 1);
+    int nf = f;
+    if (g.typ == SDK_TYP_LLC && (ny_ > g.gny - 1 || nx_ > g.gnx - 1)) {
+        // the right / top wall of an edge cell lives on the neighbouring face, possibly as the other
+        // component (ind_tend_uv :163 -> Topology._ind_tend_U / _ind_tend_V)
+        int cf = f, cy = iy, cx = ix, came;
+        const int st = cell_move(g, iw == 0 ? 3 : 0, cf, cy, cx, came);
+        if (st == 0) {
+            nf = cf, ny_ = cy, nx_ = cx;
+            if (iw == 0 && came == 1) iw = 1;       // arrived through a "down" edge: a V wall
+            else if (iw == 1 && came == 2) iw = 0;  // arrived through a "left" edge: a U wall
+        }
+    }
+    out[0] = (int16_t)iw;
+    out[stride] = (int16_t)iz;
+    if (rows == 5) {
+        out[2 * stride] = (int16_t)nf;
+        out[3 * stride] = (int16_t)ny_;
+        out[4 * stride] = (int16_t)nx_;
+    } else {
+        out[2 * stride] = (int16_t)ny_;
+        out[3 * stride] = (int16_t)nx_;
+    }
+}
+
+// pseudo_motion (lagrangian_budget.py:97): first wall and time forward (sg = +1) or backward (-1)
+__device__ __forceinline__ void first_wall(const sdk_log_record &r, double sg, int &tend, double &t_event) {
+    double ts[7];
+    wall_times(r.uu, r.du, r.rx, sg, ts[0], ts[1]);
+    wall_times(r.vv, r.dv, r.ry, sg, ts[2], ts[3]);
+    wall_times(r.ww, r.dw, r.rzl - 0.5, sg, ts[4], ts[5]);
+    ts[6] = sg * 1e80;
+    tend = 0;
+    double best = INFINITY;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        double d = ts[k] * sg;
+        if (isnan(d) || d < 0) d = INFINITY;
+        if (d < best) {
+            best = d;
+            tend = k;
+        }
+    }
+    t_event = ts[0];
+#pragma unroll
+    for (int k = 1; k < 7; ++k)
+        if (tend == k) t_event = ts[k];
+}
+
+__global__ void __launch_bounds__(128) budget_kernel(const __grid_constant__ BudgetArgs a) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_particles) return;
+    const int64_t o = a.offset[p], e = a.offset[p + 1];
+    for (int64_t i = o; i < e; ++i) {
+        const sdk_log_record r = a.rec[i];
+        const int f = a.g.has_face ? r.fc : 0;
+        double frac = 1.0;
+        if (i == o || i == e - 1) {
+            // redo_index (:223)
+            int tendf, tendb;
+            double tf, tb;
+            first_wall(r, 1.0, tendf, tf);
+            first_wall(r, -1.0, tendb, tb);
+            if (tendf == 6) tendf = 0;
+            if (tendb == 6) tendb = 0;
+            wall_index(a.g, tendf, r.izl, f, r.iy, r.ix, a.ind1 + i, a.n_rec, a.rows);
+            wall_index(a.g, tendb, r.izl, f, r.iy, r.ix, a.ind2 + i, a.n_rec, a.rows);
+            const double tim = tf - tb;
+            frac = -tb / tim;
+            if (frac != frac) frac = 1.0;  // np.nan_to_num(frac, nan=1)
+            else frac = nan_to_num(frac);
+        } else {
+            // which_wall (:85): the nearest of the six walls
+            const double d[6] = {fabs(0.5 + r.rx), fabs(0.5 - r.rx), fabs(0.5 + r.ry), fabs(0.5 - r.ry), fabs(r.rzl), fabs(1 - r.rzl)};
+            int iwall = 0;
+#pragma unroll
+            for (int k = 1; k < 6; ++k)
+                if (d[k] < d[iwall]) iwall = k;
+            wall_index(a.g, iwall, r.izl, f, r.iy, r.ix, a.ind1 + i, a.n_rec, a.rows);
+            for (int k = 0; k < a.rows; ++k) a.ind2[k * a.n_rec + i] = 1;
+        }
+        a.frac[i] = frac;
+        // residence_time (:139): 2 / sum |u| over the six walls
+        const double z0 = r.rzl - 0.5;
+        const double ul = r.uu - (r.rx + 0.5) * r.du, ur = r.uu + (0.5 - r.rx) * r.du;
+        const double vl = r.vv - (r.ry + 0.5) * r.dv, vr = r.vv + (0.5 - r.ry) * r.dv;
+        const double wl = r.ww - (z0 + 0.5) * r.dw, wr = r.ww + (0.5 - z0) * r.dw;
+        a.tres[i] = 2 / (((((fabs(ul) + fabs(ur)) + fabs(vl)) + fabs(vr)) + fabs(wl)) + fabs(wr));
+        a.work[i] = 1.0;
+    }
+}
+
+// tres_update (:144): fracs[first + 1] = fraction_first, then fracs[last] -= fraction_last (in this
+// order, for all particles), tres = tres0 * fracs, zero where the stamp is > 6
+__global__ void budget_first_kernel(const __grid_constant__ BudgetArgs a) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_particles) return;
+    const int64_t o = a.offset[p];
+    if (a.offset[p + 1] > o && o + 1 < a.n_rec) a.work[o + 1] = a.frac[o];
+}
+
+__global__ void budget_last_kernel(const __grid_constant__ BudgetArgs a) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_particles) return;
+    const int64_t o = a.offset[p], e = a.offset[p + 1];
+    if (e > o) a.work[e - 1] -= a.frac[e - 1];
+}
+
+__global__ void budget_tres_kernel(const __grid_constant__ BudgetArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_rec) return;
+    a.tres[i] = a.rec[i].vs > 6 ? 0.0 : a.tres[i] * a.work[i];
+}
+
+cudaError_t launch_budget(const BudgetArgs &a, cudaStream_t s) {
+    if (a.n_particles == 0 || a.n_rec == 0) return cudaSuccess;
+    const unsigned pb = (unsigned)((a.n_particles + 127) / 128), rb = (unsigned)((a.n_rec + 255) / 256);
+    budget_kernel<<<pb, 128, 0, s>>>(a);
+    budget_first_kernel<<<pb, 128, 0, s>>>(a);
+    budget_last_kernel<<<pb, 128, 0, s>>>(a);
+    budget_tres_kernel<<<rb, 256, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace sdk

@@ -1,0 +1,22 @@
+// Arguments of the budget post-processing kernels (shared by budget.cu and capi.cu).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "sdk_device.cuh"
+
+namespace sdk {
+
+struct BudgetArgs {
+    GridDev g;
+    const sdk_log_record *rec;
+    const int64_t *offset;
+    int64_t n_particles, n_rec;
+    int16_t *ind1, *ind2;  // [rows][n_rec]
+    double *frac, *tres, *work;
+    int rows;
+};
+
+cudaError_t launch_budget(const BudgetArgs &a, cudaStream_t s);
+
+}  // namespace sdk

@@ -10,6 +10,7 @@
 
 #include "advect_args.cuh"
 #include "interp_args.cuh"
+#include "budget_args.cuh"
 #include "locate_args.cuh"
 
 namespace sdk {
@@ -437,6 +438,29 @@ int sdk_build_masks(const sdk_grid *grid, const uint8_t *maskC, int32_t nz, uint
 }
 
 // ---- device math self-test --------------------------------------------------------------------------
+int sdk_log_budget(const sdk_grid *grid, const sdk_log_record *records, const int64_t *offset, int64_t n_particles,
+                   int64_t n_rec, int16_t *ind1, int16_t *ind2, double *frac, double *tres, double *work, void *stream) {
+    if (!grid || n_particles < 0 || n_rec < 0) return fail(SDK_EINVAL, "sdk_log_budget: bad argument");
+    if (n_rec > 0 && (!records || !offset || !ind1 || !ind2 || !frac || !tres || !work))
+        return fail(SDK_EINVAL, "sdk_log_budget: null array");
+    if (grid->dev.n_zl < 2) return fail(SDK_EUNSUPPORTED, "sdk_log_budget: the grid has no vertical levels");
+    sdk::BudgetArgs a;
+    a.g = grid->dev;
+    a.rec = records;
+    a.offset = offset;
+    a.n_particles = n_particles;
+    a.n_rec = n_rec;
+    a.ind1 = ind1;
+    a.ind2 = ind2;
+    a.frac = frac;
+    a.tres = tres;
+    a.work = work;
+    a.rows = grid->dev.has_face ? 5 : 4;
+    cudaError_t e = sdk::launch_budget(a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_log_budget: launch");
+    return SDK_OK;
+}
+
 int sdk_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
                       const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl, double *out,
                       void *stream) {
