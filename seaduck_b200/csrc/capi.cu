@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <cstdlib>
 #include <string>
 
 #include "advect_args.cuh"
@@ -36,7 +37,8 @@ int cuda_fail(cudaError_t e, const char *what) {
 }  // namespace
 
 constexpr unsigned kQueueSlots = 64;
-constexpr int kTrackChunks = 8;
+constexpr int kTrackChunks = 6;
+constexpr int kTrackChunksMax = 32;
 
 struct sdk_grid {
     sdk::GridDev dev;
@@ -522,7 +524,7 @@ int sdk_selftest_math(int op, int64_t n, const double *a, const double *b, doubl
 
 // ---- positions in, positions out ------------------------------------------------------------------
 // (room for the per-chunk alignment of the pipelined path: up to kTrackChunks carvings of ~30 arrays)
-int64_t sdk_track_scratch_bytes(int64_t n) { return sdk_particles_bytes(n) + 8 * (int64_t)align256((size_t)n * 8) + kTrackChunks * 40 * 256; }
+int64_t sdk_track_scratch_bytes(int64_t n) { return sdk_particles_bytes(n) + 8 * (int64_t)align256((size_t)n * 8) + kTrackChunksMax * 40 * 256; }
 
 // One chunk of sdk_track_host: H2D, locate, velocity read, advect, D2H -- all asynchronous on `stream`.
 static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev,
@@ -600,7 +602,12 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
     // chunk k+1 and the read-back of chunk k-1 (copy engines) overlap the kernels of chunk k.
     const int64_t min_chunk = 65536;
     int nchunks = (int)(n / min_chunk);
-    if (nchunks > kTrackChunks) nchunks = kTrackChunks;
+    int max_chunks = kTrackChunks;
+    if (const char *env = std::getenv("SDK_TRACK_CHUNKS")) {  // tuning knob, 1 .. kTrackChunksMax
+        const int v = std::atoi(env);
+        if (v >= 1 && v <= kTrackChunksMax) max_chunks = v;
+    }
+    if (nchunks > max_chunks) nchunks = max_chunks;
     if (nchunks < 2) {
         int rc = track_chunk(grid, vel, io, ts_dev, n_t, t_stop, par, scratch, stream);
         if (rc) return rc;
