@@ -340,6 +340,23 @@ class Particle(Position):
         self.__dict__["_vel"] = v
         self.__dict__["_vel_keep"] = keep
 
+    def _prefetch_slab_for(self, t_stop):
+        """After a stop every particle sits at ``t_stop``, i.e. in one known time level: start the
+        upload of that snapshot of u, v, w (streaming ingest)."""
+        od = self.ocedata
+        midp = np.asarray(od.time_midp, float)
+        if t_stop < midp[0]:
+            it = 0
+        else:
+            k = int(np.argmin(np.abs(midp - t_stop)))
+            if midp[k] > t_stop:
+                k -= 1
+            it = max(k, 0) + 1
+        sl = slice(it, it + 1)
+        for name in (self.uname, self.vname, self.wname):
+            if name is not None:
+                od.prefetch_field(name, sl)
+
     def get_vol(self):
         """Cell volume at the particles (reference :202); done together with get_u_du on the device."""
         self._mark_stale(["vol"])
@@ -622,6 +639,9 @@ class Particle(Position):
             if self.save_raw:
                 self.note_taking(stamp=15)
             self.to_next_stop(tl)
+            if has_time and self.lazy and (update[i] or i == 0):
+                # the leg is queued, not finished: copy the snapshot it ends in while it runs
+                self._prefetch_slab_for(tl)
             if update[i] or i == 0:
                 if has_time:
                     self.update_uvw_array()

@@ -436,29 +436,65 @@ class OceData:
         except Exception:  # noqa: BLE001
             pass
 
+    @staticmethod
+    def _slab_key(name, time_slice):
+        return (name, None if time_slice is None else (time_slice.start, time_slice.stop))
+
+    def _host_slab(self, name, time_slice):
+        da = self[name]
+        arr = np.asarray(da[time_slice] if time_slice is not None else da)
+        if arr.dtype not in (np.float32, np.float64):
+            arr = arr.astype(np.float64)
+        return np.ascontiguousarray(arr)
+
+    def _remember_slab(self, key, value):
+        # keep at most two slabs per variable (current + previous / prefetched)
+        same = [k for k in self._field_cache if k[0] == key[0]]
+        for k in same[:-1]:
+            del self._field_cache[k]
+        self._field_cache[key] = value
+
     def device_field(self, name, time_slice=None):
         """Device copy of a data variable (optionally a slab of snapshots), cached.
 
         Replaces ``Particle.update_uvw_array`` / ``smart_read`` gathers from host memory
         (reference ``lagrangian.py:175``, ``smart_read.py:22``): fields stay resident in HBM.
+        A slab that :meth:`prefetch_field` is still copying is waited for on the current stream.
         """
         import torch  # noqa: PLC0415
 
-        key = (name, None if time_slice is None else (time_slice.start, time_slice.stop))
+        key = self._slab_key(name, time_slice)
         hit = self._field_cache.get(key)
         if hit is not None:
+            if isinstance(hit, tuple):  # (tensor, event, pinned staging buffer) from prefetch_field
+                t, ev, _ = hit
+                torch.cuda.current_stream(t.device).wait_event(ev)
+                self._field_cache[key] = t
+                return t
             return hit
-        da = self[name]
-        arr = np.asarray(da[time_slice] if time_slice is not None else da)
-        if arr.dtype not in (np.float32, np.float64):
-            arr = arr.astype(np.float64)
-        t = torch.from_numpy(np.ascontiguousarray(arr)).to(self._torch_device())
-        # keep at most two slabs per variable (current + previous)
-        same = [k for k in self._field_cache if k[0] == name]
-        for k in same[:-1]:
-            del self._field_cache[k]
-        self._field_cache[key] = t
+        t = torch.from_numpy(self._host_slab(name, time_slice)).to(self._torch_device())
+        self._remember_slab(key, t)
         return t
+
+    def prefetch_field(self, name, time_slice):
+        """Start copying a slab to the device on a side stream and return at once (streaming ingest for
+        time-varying runs: the copy of the next velocity snapshot overlaps the current leg).  The
+        staging buffer is pinned; :meth:`device_field` picks the slab up later."""
+        import torch  # noqa: PLC0415
+
+        key = self._slab_key(name, time_slice)
+        if key in self._field_cache:
+            return
+        dev = self._torch_device()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(dev)
+        host = torch.from_numpy(self._host_slab(name, time_slice)).pin_memory()
+        with torch.cuda.stream(self._copy_stream):
+            t = torch.empty(host.shape, dtype=host.dtype, device=dev)
+            t.copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+        self._remember_slab(key, (t, ev, host))
 
     # ---- rel-coordinate lookups (reference ocedata.py:422-488), all on the device ---------------
     def locate(self, x=None, y=None, z=None, t=None):

@@ -129,7 +129,23 @@ def test_lazy_mode_list_of_time_matches_golden():
     od = sd.OceData(case["ds"])
     pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, **case["kw"])
     pt.lazy = True
+    # streaming ingest: the snapshot a leg ends in is uploaded on a side stream while the leg runs, and
+    # update_uvw_array then finds it on the device
+    calls, hits = [], []
+    prefetch, device_field = od.prefetch_field, od.device_field
+
+    def counting_prefetch(name, sl):
+        calls.append((name, sl.start))
+        return prefetch(name, sl)
+
+    def counting_device_field(name, sl=None):
+        key = od._slab_key(name, sl)
+        hits.append(isinstance(od._field_cache.get(key), tuple))
+        return device_field(name, sl)
+
+    od.prefetch_field, od.device_field = counting_prefetch, counting_device_field
     stops, snaps = pt.to_list_of_time(normal_stops=case["stops"])
+    assert len(calls) >= 3 and any(hits), (calls, hits)
     np.testing.assert_allclose(stops, gold["stops"])
     for i, snap in enumerate(snaps):
         compare_state(gold, f"s{i}_", snap)
