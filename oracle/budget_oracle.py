@@ -1,0 +1,141 @@
+"""TEST INFRASTRUCTURE -- numpy restatement of the crossing-log post-processing of the Lagrangian budget
+(reference ``seaduck/lagrangian_budget.py``: ``find_ind_frac_tres`` :245 with ``by_type=True``,
+``first_last_neither`` :114, ``which_wall`` :85, ``wall_index`` :192, ``ind_tend_uv`` :163,
+``pseudo_motion`` :97, ``redo_index`` :223, ``residence_time`` :139, ``tres_update`` :144;
+``_time2wall`` / ``_which_early`` ``utils.py:859,875``).
+
+Parity status: PINNED -- ``tests/test_budget_oracle.py`` feeds it the crossing logs of the Lagrangian
+goldens and compares with ``tests/golden/budget_*.npz`` (both made by the unmodified reference).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import oracle as ora
+
+MOVE = {0: (0, 0), 1: (0, 1), 2: (0, 0), 3: (1, 0), 4: (0, 0), 5: (0, 0)}  # delta_y, delta_x
+
+
+def first_last_neither(shapes):
+    acc = np.cumsum(shapes)
+    last = acc - 1
+    first = np.roll(acc, 1)
+    first[0] = 0
+    neither = np.array([first[i] + j for i, n in enumerate(shapes) for j in range(1, n - 1)], dtype=int)
+    return first, last, neither
+
+
+def stationary_time(u, du, x0):
+    """utils.py:821"""
+    with np.errstate(all="ignore"):
+        tl = np.log(1 - du / u * (0.5 + x0)) / du
+        tr = np.log(1 + du / u * (0.5 - x0)) / du
+        flat = np.abs(du) < 1e-12
+        tl[flat] = (-x0[flat] - 0.5) / u[flat]
+        tr[flat] = (0.5 - x0[flat]) / u[flat]
+    return tl, tr
+
+
+def time2wall(xs, us, dus, tf):
+    """utils.py:859"""
+    ts = []
+    sign = np.sign(tf)
+    for x0, u, du in zip(xs, us, dus):
+        tl, tr = stationary_time(u, du, x0)
+        ul = u - (x0 + 0.5) * du
+        ur = u + (0.5 - x0) * du
+        tl[-ul * sign <= 1e-12] = -sign[-ul * sign <= 1e-12]
+        tr[ur * sign <= 1e-12] = -sign[ur * sign <= 1e-12]
+        ts += [tl, tr]
+    return ts
+
+
+def which_early(tf, ts):
+    """utils.py:875"""
+    ts = ts + [np.ones(len(ts[0])) * tf]
+    with np.errstate(all="ignore"):
+        directed = np.array(ts) * np.sign(tf)
+    directed[np.isnan(directed)] = np.inf
+    directed[directed < 0] = np.inf
+    tend = directed.argmin(axis=0)
+    return tend, np.array(ts)[tend, np.arange(len(tend))]
+
+
+def wall_index(og, izl, face, iy, ix, iwall):
+    """lagrangian_budget.py:192"""
+    lib = ora.lib()
+    iw = iwall // 2
+    iz = izl.copy()
+    ny = iy + np.array([MOVE[int(k)][0] for k in iwall], dtype=int)
+    nx = ix + np.array([MOVE[int(k)][1] for k in iwall], dtype=int)
+    iz[iwall == 4] += 1
+    iz -= 1
+    if og.typ != "LLC":
+        return np.array([iw, iz, ny, nx]).astype(int)
+    nf = face.copy()
+    gny, gnx = og.g_shape[-2:]
+    for j in np.where((ny > gny - 1) | (nx > gnx - 1))[0]:
+        ind = (C.c_int32 * 3)(int(face[j]), int(iy[j]), int(ix[j]))
+        out = (C.c_int32 * 3)()
+        new_iw = C.c_int(0)
+        err = lib.ora_ind_tend_uv(C.byref(og.c), int(iw[j]), ind, C.byref(new_iw), out)
+        if err:
+            raise IndexError(f"no wall next to cell {tuple(ind)}")
+        iw[j], nf[j], ny[j], nx[j] = new_iw.value, out[0], out[1], out[2]
+    return np.array([iw, iz, nf, ny, nx]).astype(int)
+
+
+def redo_index(og, rec, sel):
+    """lagrangian_budget.py:223 for the records ``sel``"""
+    g = lambda k: np.asarray(rec[k])[sel]  # noqa: E731
+    xs = [g("rx"), g("ry"), g("rzl") - 1 / 2]
+    us, dus = [g("uu"), g("vv"), g("ww")], [g("du"), g("dv"), g("dw")]
+    n = len(xs[0])
+    tendf, tf = which_early(1e80, time2wall(xs, us, dus, 1e80 * np.ones(n)))
+    tendb, tb = which_early(-1e80, time2wall(xs, us, dus, -1e80 * np.ones(n)))
+    tendf[tendf == 6] = 0
+    tendb[tendb == 6] = 0
+    face = g("fc").astype(int) if og.has_face else np.zeros(n, int)
+    inds = (g("izl").astype(int), face, g("iy").astype(int), g("ix").astype(int))
+    vf = wall_index(og, *inds, tendf)
+    vb = wall_index(og, *inds, tendb)
+    with np.errstate(all="ignore"):
+        frac = -tb / (tf - tb)
+    return vf, vb, np.nan_to_num(frac, nan=1)
+
+
+def find_ind_frac_tres(og, rec, offset):
+    """lagrangian_budget.py:245; ``rec`` = dict of flat log arrays, ``offset`` = per-particle starts (n+1)."""
+    shapes = np.diff(offset)
+    n = int(offset[-1])
+    first, last, neither = first_last_neither(shapes)
+    rows = 5 if og.has_face else 4
+    ind1 = np.zeros((rows, n), "int16")
+    ind2 = np.ones((rows, n), "int16")
+    frac = np.ones(n)
+    g = lambda k, sel: np.asarray(rec[k])[sel]  # noqa: E731
+    if len(neither) > 0:
+        rx, ry, rzl = g("rx", neither), g("ry", neither), g("rzl", neither)
+        dist = np.vstack([np.abs(0.5 + rx), np.abs(0.5 - rx), np.abs(0.5 + ry), np.abs(0.5 - ry), np.abs(rzl), np.abs(1 - rzl)])
+        iwall = np.argmin(dist, axis=0)  # which_wall :85
+        face = g("fc", neither).astype(int) if og.has_face else np.zeros(len(neither), int)
+        ind1[:, neither] = wall_index(og, g("izl", neither).astype(int), face, g("iy", neither).astype(int), g("ix", neither).astype(int), iwall)
+    ind1[:, first], ind2[:, first], frac[first] = redo_index(og, rec, first)
+    ind1[:, last], ind2[:, last], frac[last] = redo_index(og, rec, last)
+    # residence_time :139, tres_update :144
+    u, du, x = np.asarray(rec["uu"]), np.asarray(rec["du"]), np.asarray(rec["rx"])
+    v, dv, y = np.asarray(rec["vv"]), np.asarray(rec["dv"]), np.asarray(rec["ry"])
+    w, dw, z = np.asarray(rec["ww"]), np.asarray(rec["dw"]), np.asarray(rec["rzl"]) - 0.5
+    ulist = np.array([u - (x + 0.5) * du, u + (0.5 - x) * du, v - (y + 0.5) * dv, v + (0.5 - y) * dv, w - (z + 0.5) * dw, w + (0.5 - z) * dw])
+    with np.errstate(all="ignore"):
+        tres0 = 2 / np.sum(np.abs(ulist), axis=0)
+    fracs = np.ones(n)
+    fracs[first + 1] = frac[first]
+    fracs[last] -= frac[last]
+    with np.errstate(all="ignore"):
+        tres = tres0 * fracs
+    tres[np.asarray(rec["vs"]) > 6] = 0.0
+    return ind1, ind2, frac, tres, last, first

@@ -839,6 +839,17 @@ int ora_fatten_h(const ora_grid *g, int64_t n, const int32_t *face, const int32_
     return ORA_OK;
 }
 
+/* ind_tend_uv, lagrangian_budget.py:163: the U wall to the right (iw = 0) or the V wall above (iw = 1)
+ * of a cell, as (new iw, new index), through Topology._ind_tend_U / _ind_tend_V */
+int ora_ind_tend_uv(const ora_grid *g, int iw, const int32_t ind[3], int *new_iw, int32_t out[3]) {
+    int is_v = 0, err;
+    if (iw == 1) err = ind_tend_V(g, ind, 0, &is_v, out);
+    else if (iw == 0) err = ind_tend_U(g, ind, 3, &is_v, out);
+    else return ORA_VALUE_ERROR;
+    *new_iw = is_v;
+    return err;
+}
+
 /* Topology.four_matrix_for_uv, topology.py:689, rounded as in eulerian.py:934-937: for an (n, m) array
  * of faces (node 0 is the reference) the four coefficients UfromU, UfromV, VfromU, VfromV. */
 int ora_four_matrix_for_uv(const ora_grid *g, int64_t n, int m, const int32_t *faces, double *ufu, double *ufv,

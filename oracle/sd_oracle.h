@@ -98,6 +98,7 @@ int ora_ind_moves(const ora_grid *g, const int32_t ind[3], const int *moves, int
 int ora_fatten_h(const ora_grid *g, int64_t n, const int32_t *face, const int32_t *iy, const int32_t *ix, int m,
                  const int32_t *kx, const int32_t *ky, char cuvwg, int32_t *of, int32_t *oy, int32_t *ox,
                  int32_t *oerr);
+int ora_ind_tend_uv(const ora_grid *g, int iw, const int32_t ind[3], int *new_iw, int32_t out[3]);
 int ora_four_matrix_for_uv(const ora_grid *g, int64_t n, int m, const int32_t *faces, double *ufu, double *ufv,
                            double *vfu, double *vfv, int32_t *oerr);
 int ora_corners(const ora_grid *g, const int32_t ind[3], int32_t out[4][3]);

@@ -1,0 +1,33 @@
+"""CPU: the numpy oracle of the Lagrangian-budget post-processing (oracle/budget_oracle.py) on the crossing
+logs of the Lagrangian goldens against the budget goldens -- both produced by the unmodified reference."""
+
+import os
+
+import numpy as np
+import pytest
+
+import cases
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("make", [cases.case_llc_transport, cases.case_overturning], ids=lambda f: f.__name__)
+def test_budget_oracle_matches_reference(make, oracle_lib):
+    import seaduck_b200 as sd
+    from oracle import budget_oracle as bo
+
+    case = make()
+    logs = np.load(os.path.join(GOLD, f"lagrangian_{case['name']}.npz"))
+    gold = np.load(os.path.join(GOLD, f"budget_{case['name']}.npz"))
+    og = oracle_lib.OracleGrid(sd.OceData(case["ds"]))
+    for i in range(len(case["stops"])):
+        rec = {k: logs[f"s{i}_log_{k}"] for k in cases.LOG_INT + cases.LOG_FLT if f"s{i}_log_{k}" in logs}
+        if "fc" not in rec:
+            rec["fc"] = np.zeros_like(rec["iy"])
+        ind1, ind2, frac, tres, last, first = bo.find_ind_frac_tres(og, rec, logs[f"s{i}_log_offset"])
+        np.testing.assert_array_equal(first, gold[f"s{i}_first"])
+        np.testing.assert_array_equal(last, gold[f"s{i}_last"])
+        np.testing.assert_array_equal(ind1, gold[f"s{i}_ind1"])
+        np.testing.assert_array_equal(ind2, gold[f"s{i}_ind2"])
+        np.testing.assert_allclose(frac, gold[f"s{i}_frac"], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(tres, gold[f"s{i}_tres"], rtol=1e-12, atol=0)

@@ -42,3 +42,31 @@ def test_budget_postprocessing_matches_reference(make):
         np.testing.assert_array_equal(ind2, gold[f"s{i}_ind2"], err_msg="ind2")
         cases.assert_close("frac", frac, gold[f"s{i}_frac"])
         cases.assert_close("tres", tres, gold[f"s{i}_tres"])
+
+
+def test_budget_matches_oracle_on_own_log(oracle_lib):
+    """Larger seeded run: the device post-processing against the numpy oracle fed with the very same log
+    (so ties of which_wall have the same inputs on both sides): indices bit-exact, floats 1e-9."""
+    import seaduck_b200 as sd
+    from oracle import budget_oracle as bo
+    from seaduck_b200 import lagrangian_budget as lb
+    from seaduck_b200 import synthetic
+
+    ds = synthetic.llc(n=45, nz=12)
+    n = 5000
+    lon, lat, dep = synthetic.llc_seed_particles(ds, n, seed=13, depth_range=(5, 700))
+    od = sd.OceData(ds)
+    pt = sd.Particle(x=lon, y=lat, z=dep, t=np.zeros(n), data=od, save_raw=True, uname="utrans", vname="vtrans", wname="wtrans", transport=True)
+    pt.note_taking(stamp=15)
+    pt.to_next_stop(40 * cases.DAY)
+    ind1, ind2, frac, tres, last, first = lb.find_ind_frac_tres(pt, od)
+    rec = pt.raw_arrays()[-1]
+    og = oracle_lib.OracleGrid(od)
+    r1, r2, rfrac, rtres, rlast, rfirst = bo.find_ind_frac_tres(og, rec, rec["offset"])
+    assert ind1.shape[1] > 50_000
+    np.testing.assert_array_equal(first, rfirst)
+    np.testing.assert_array_equal(last, rlast)
+    np.testing.assert_array_equal(ind1, r1)
+    np.testing.assert_array_equal(ind2, r2)
+    cases.assert_close("frac", frac, rfrac)
+    cases.assert_close("tres", tres, rtres)
