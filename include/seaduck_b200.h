@@ -149,7 +149,10 @@ typedef struct sdk_log {
     int32_t *count;
     sdk_log_record *records;
     int32_t emit_start; /* write the stamp-15 record first (lagrangian.py:887) */
-    int32_t reserved;
+    /* bit 0: do NOT write the stamp-7 record after a crossing (the host decides who continues: Python
+     * callback, lagrangian.py:787); bit 1: write a stamp-7 record for every active live particle when
+     * it is loaded (the record deferred from the previous one-iteration launch) */
+    int32_t continue_mode;
 } sdk_log;
 
 int sdk_abi_version(void);

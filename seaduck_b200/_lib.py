@@ -98,7 +98,7 @@ LOG_F64 = "rzl rx ry tt uu vv ww du dv dw xx yy zz".split()
 
 
 class Log(C.Structure):
-    _fields_ = [("capacity", C.c_int64), ("offset", vp), ("count", vp), ("records", vp), ("emit_start", C.c_int32), ("reserved", C.c_int32)]
+    _fields_ = [("capacity", C.c_int64), ("offset", vp), ("count", vp), ("records", vp), ("emit_start", C.c_int32), ("continue_mode", C.c_int32)]
 
 
 # numpy view of sdk_log_record (128 bytes)

@@ -469,7 +469,7 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
     read_velocity<T>(g, a.v, has_dep, s);
     s.niter += 1;
     live = fabs(a.t_stop - s.t) > a.tol;
-    if (LOG && live) note(a, s, 7);
+    if (LOG && live && !(a.log.continue_mode & 1)) note(a, s, 7);
 }
 
 // Tuning knobs (profiles/README.md, round 1 iterations d-g).  The particle step is ~2000 SASS
@@ -539,6 +539,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
                     if (LOG && a.log.emit_start) note(a, s, 15);
                     live = fabs(a.t_stop - s.t) > a.tol;
                     if (a.p.active && !a.p.active[pid]) live = false;
+                    if (LOG && live && (a.log.continue_mode & 2)) note(a, s, 7);
                     acc_live += live;
                 }
             }

@@ -265,6 +265,15 @@ class Particle(Position):
             d["_stale"].discard(attr)
         Position.__setattr__(self, attr, value)
 
+    def subset(self, which):
+        """Host-side subset of the particles (reference ``eulerian.py:319``): what a ``callback`` receives.
+        The host mirrors are refreshed first; the result holds numpy arrays only."""
+        for attr in list(self._stale):
+            self._pull(attr)
+        if not self.__dict__.get("_derived_ok", True):
+            self._refresh_derived()
+        return Position.subset(self, which)
+
     def _rel_get(self, key):
         if key in self._stale:
             return self._pull(key)
@@ -412,16 +421,36 @@ class Particle(Position):
                 out[i].extend(vals[off[i] : off[i + 1]].tolist())
         return out
 
-    def raw_arrays(self):
-        """Crossing log of the last stop(s): per chunk a dict of flat numpy arrays (views into the
-        128-byte records) + per-particle ``offset``."""
+    def raw_arrays(self, merged=False):
+        """Crossing log of the last stop(s): per chunk (one per launch) a dict of flat numpy arrays
+        (views into the 128-byte records) + per-particle ``offset``.  ``merged=True`` returns ONE such
+        dict with the records of every particle concatenated in launch order (what the reference's
+        per-particle lists hold after a stop that took several launches, e.g. with a ``callback``)."""
         out = []
         for ch in self._raw:
             rec, off = self._host_chunk(ch)
             d = {k: rec[k] for k in _lib.LOG_I32 + _lib.LOG_F64}
             d["offset"] = off
             out.append(d)
-        return out
+        if not merged:
+            return out
+        if len(out) == 1:
+            return out[0]
+        counts = [np.diff(d["offset"]) for d in out]
+        total = np.sum(counts, axis=0)
+        offset = np.zeros(self.N + 1, np.int64)
+        np.cumsum(total, out=offset[1:])
+        merged_rec = {k: np.empty(int(offset[-1]), out[0][k].dtype) for k in _lib.LOG_I32 + _lib.LOG_F64}
+        start = offset[:-1].copy()
+        for d, cnt in zip(out, counts):
+            # destination of every record of this chunk: start of its particle + position inside the chunk
+            pid = np.repeat(np.arange(self.N), cnt)
+            dst = start[pid] + (np.arange(len(pid)) - d["offset"][:-1][pid])
+            for k in merged_rec:
+                merged_rec[k][dst] = d[k]
+            start += cnt
+        merged_rec["offset"] = offset
+        return merged_rec
 
     # ------------------------------------------------------------------------------------------
     # time stepping
@@ -448,7 +477,7 @@ class Particle(Position):
         self._stats.zero_()
         return vals
 
-    def _launch(self, t_stop, max_iteration, active=None, emit_start=False):
+    def _launch(self, t_stop, max_iteration, active=None, emit_start=False, continue_mode=0):
         import torch  # noqa: PLC0415
 
         L = _lib.lib()
@@ -464,6 +493,7 @@ class Particle(Position):
         lg = _lib.Log()
         lg.count = cnt.data_ptr()
         lg.emit_start = int(emit_start)
+        lg.continue_mode = int(continue_mode)
         # pass 1: count the records of every particle without committing the state
         par_count = self._params(max_iteration)
         par_count.stats = None
@@ -532,7 +562,9 @@ class Particle(Position):
             hit_max = False
             for i in range(self.max_iteration):
                 active = torch.as_tensor(alive.astype(np.int32)).to(dev)
-                self._launch(t_stop, 1, active=active, emit_start=emit_start and i == 0)
+                # the host decides who continues: the kernel leaves the stamp-7 record of a crossing to the
+                # next launch, which writes it for the particles that are still active
+                self._launch(t_stop, 1, active=active, emit_start=emit_start and i == 0, continue_mode=1 if i == 0 else 3)
                 self.__dict__["_crossings"] += int(self._read_stats()[1])
                 self._mark_stale()
                 still = ((t_stop - st["t"]).abs() > tol).cpu().numpy()
@@ -544,6 +576,12 @@ class Particle(Position):
                     break
             if i == self.max_iteration - 1:
                 hit_max = True
+                if self.save_raw and alive.any():
+                    # out of iterations with particles still going: the reference has already logged
+                    # their stamp-7 record (lagrangian.py:789-792); a zero-iteration launch writes it
+                    active = torch.as_tensor(alive.astype(np.int32)).to(dev)
+                    self._launch(t_stop, 0, active=active, continue_mode=3)
+                    self._stats.zero_()
         if hit_max:
             warnings.warn("maximum iteration count reached")
         st["t"].fill_(t_stop)

@@ -102,7 +102,24 @@ def case_llc_bool_array(ngrid=24, nz=8):
     )
 
 
-ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_bool_array]
+def _stay_south(p):
+    """Particle callback: keep integrating only while south of 31.3N (not a grid line: a threshold on a cell wall is decided by the last bit) (reference lagrangian.py:757,787)."""
+    return p.lat < 31.3
+
+
+def case_llc_callback(n=200, ngrid=24, nz=6):
+    ds = synthetic.llc(n=ngrid, nz=nz)
+    lon, lat, dep = synthetic.llc_seed_particles(ds, n, seed=6, lat_range=(-40.0, 45.0), depth_range=(5, 150))
+    return dict(
+        name="llc_callback",
+        ds=ds,
+        x=lon, y=lat, z=dep, t=np.zeros(n),
+        stops=[25 * DAY, 50 * DAY],
+        kw=dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True, callback=_stay_south, max_iteration=40),
+    )
+
+
+ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_bool_array, case_llc_callback]
 
 LOG_INT = ["fc", "it", "izl", "iy", "ix", "vs"]
 LOG_FLT = ["rzl", "rx", "ry", "tt", "uu", "vv", "ww", "du", "dv", "dw", "xx", "yy", "zz"]

@@ -20,9 +20,7 @@ def _sd():
 
 
 def log_of(pt):
-    chunks = pt.raw_arrays()
-    assert len(chunks) == 1
-    return chunks[0]
+    return pt.raw_arrays(merged=True)
 
 
 def compare_log(gold, prefix, rec):
