@@ -114,6 +114,42 @@ def overturning_cell(nx=100, nz=50, dtype=np.float64, as_xarray=False):
     )
 
 
+def channel(ny=20, nx=72, nz=4, dtype=np.float64, as_xarray=False):
+    """Zonally periodic curvilinear channel (auto-detected as ``x_periodic``, reference
+    ``topology.py:325-337``): lon 0..360 in ``nx`` cells, lat -50..50, ``nz`` levels, velocities in m/s."""
+    xg1 = np.linspace(0.0, 360.0, nx + 1)[:-1]
+    yg1 = np.linspace(-50.0, 50.0, ny + 1)
+    dlon = 360.0 / nx
+    xg, yg = np.meshgrid(np.append(xg1, 360.0), yg1)
+    xc = 0.25 * (xg[:-1, :-1] + xg[1:, :-1] + xg[:-1, 1:] + xg[1:, 1:])
+    yc = 0.25 * (yg[:-1, :-1] + yg[1:, :-1] + yg[:-1, 1:] + yg[1:, 1:])
+    phi = np.deg2rad(yc)
+    lam = np.deg2rad(xc)
+    dxg = np.broadcast_to(R_EARTH * np.cos(np.deg2rad(yg[:-1, :-1])) * np.deg2rad(dlon), (ny, nx)).copy()
+    dyg = np.full((ny, nx), R_EARTH * np.deg2rad(100.0 / ny))
+    drf = np.linspace(20.0, 200.0, nz)
+    zp1 = np.concatenate([[0.0], -np.cumsum(drf)])
+    z = 0.5 * (zp1[1:] + zp1[:-1])
+    decay = np.exp(z / 300.0)[:, None, None]
+    u = decay * (0.6 * np.cos(phi) * (1 + 0.4 * np.sin(2 * lam)))[None]
+    v = decay * (0.15 * np.sin(3 * lam) * np.cos(phi) ** 2)[None]
+    v[:, 0, :] = 0.0  # closed southern wall; the northern one is closed by the missing row
+    w = np.zeros((nz, ny, nx))
+    w[1:] = 1e-5 * np.sin(lam)[None] * np.cos(phi)[None] * (np.arange(1, nz)[:, None, None] / nz)
+    return _dataset(
+        dict(
+            XC=(["Y", "X"], xc), YC=(["Y", "X"], yc), XG=(["Yp1", "Xp1"], xg[:, :]), YG=(["Yp1", "Xp1"], yg[:, :]),
+            dxG=(["Yp1", "X"], np.vstack([dxg, dxg[-1:]])), dyG=(["Y", "Xp1"], np.hstack([dyg, dyg[:, -1:]])),
+            rA=(["Y", "X"], dxg * dyg), Z=(["Z"], z), Zl=(["Zl"], zp1[:-1]), Zp1=(["Zp1"], zp1), drF=(["Z"], drf),
+        ),
+        dict(
+            UVELMASS=(["Z", "Y", "X"], u.astype(dtype)), VVELMASS=(["Z", "Y", "X"], v.astype(dtype)),
+            WVELMASS=(["Zl", "Y", "X"], w.astype(dtype)),
+        ),
+        as_xarray,
+    )
+
+
 def rectilinear(nlat=60, nlon=120, nt=1, dtype=np.float64, as_xarray=False):
     """Global 1-D lon/lat grid (``readiness['h'] == 'rectilinear'``, reference ``ocedata.py:255``)."""
     lon = np.linspace(-180, 180, nlon, endpoint=False)

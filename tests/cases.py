@@ -102,6 +102,22 @@ def case_llc_bool_array(ngrid=24, nz=8):
     )
 
 
+def case_channel_kickback(n=250):
+    """Zonally periodic channel, velocities in m/s (transport=False), free_surface="kick_back"."""
+    ds = synthetic.channel()
+    rng = np.random.default_rng(12)
+    x = rng.uniform(0.0, 360.0, n)
+    y = rng.uniform(-46.0, 46.0, n)
+    z = -rng.uniform(2.0, 350.0, n)
+    return dict(
+        name="channel_kickback",
+        ds=ds,
+        x=x, y=y, z=z, t=np.zeros(n),
+        stops=[25 * DAY, 70 * DAY, 40 * DAY],
+        kw=dict(transport=False, free_surface="kick_back"),
+    )
+
+
 def _stay_south(p):
     """Particle callback: keep integrating only while south of 31.3N (not a grid line: a threshold on a cell wall is decided by the last bit) (reference lagrangian.py:757,787)."""
     return p.lat < 31.3
@@ -119,7 +135,7 @@ def case_llc_callback(n=200, ngrid=24, nz=6):
     )
 
 
-ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_bool_array, case_llc_callback]
+ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_bool_array, case_llc_callback, case_channel_kickback]
 
 LOG_INT = ["fc", "it", "izl", "iy", "ix", "vs"]
 LOG_FLT = ["rzl", "rx", "ry", "tt", "uu", "vv", "ww", "du", "dv", "dw", "xx", "yy", "zz"]
