@@ -31,6 +31,15 @@ sd = load_reference()
 import cases_interp as ci  # noqa: E402
 
 
+FATTEN_JOBS = [
+    ("all", {}, {}),
+    ("all_lin", dict(vkernel="linear", tkernel="linear"), {}),
+    ("four_d_YX", dict(kernel="cross5"), dict(four_d=True, required=("Y", "X"))),
+    ("U", ci.UKNW, dict(required=("Z", "face", "Y", "X"), four_d=True, ind_moves_kwarg={"cuvwg": "U"})),
+    ("Zl", dict(vkernel="dz"), dict(required=("Zl", "Y", "X"))),
+]
+
+
 def _kernels_of(spec):
     if isinstance(spec, (tuple, list)):
         out = []
@@ -99,6 +108,16 @@ def run_case(case):
             res = pos.interpolate(var, knw, vec_transform=vec_transform)
         for k, arr in enumerate(ci.flatten_result(res)):
             out[f"job_{label}_{k}"] = arr
+    # Position.fatten (eulerian.py:520): the index sets themselves, for the host-side API
+    for tag, spec, kw in FATTEN_JOBS:
+        knw = ci.make_knw(sd.KnW, spec)
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                res = pos.fatten(knw, **kw)
+        except (IndexError, ValueError, TypeError, AttributeError, KeyError):
+            continue  # e.g. a vertical dimension required on a dataset without one
+        for k, arr in enumerate(res):
+            out[f"fatten_{tag}_{k}"] = np.asarray(arr)
     # lazily computed linear rel-coords, after the jobs that need them ran
     for key in ("iz_lin", "it_lin"):
         try:

@@ -291,6 +291,106 @@ class Position:
             elif isinstance(item, list):
                 setattr(self, key, item)
 
+    # ---- neighbour index sets on the host (the device kernels do this per point internally) -----------
+    def _fatten_h(self, knw, ind_moves_kwarg={}):
+        """Horizontal indices of every kernel node of every point, ``(faces | None, iys, ixs)`` each
+        ``(N, M)`` (reference ``eulerian.py:386``): naive offsets, topology walk where they leave the grid."""
+        kernel = np.asarray(knw.kernel).astype(int)
+        cuvwg = ind_moves_kwarg.get("cuvwg", "C")
+        tp = self.ocedata.tp
+        has_face = self.face is not None
+        ind = (self.face, self.iy, self.ix) if has_face else (self.iy, self.ix)
+        cols = []
+        for node in kernel:
+            out, status = tp.fatten_node(ind, node, cuvwg)
+            bad = np.where(status != 0)[0]
+            if len(bad):
+                tp._raise(int(status[bad[0]]), tuple(int(a[bad[0]]) for a in ind))
+            cols.append(out)
+        stack = lambda k: np.stack([np.asarray(c[k]) for c in cols], axis=1).astype(int)  # noqa: E731
+        if has_face:
+            return stack(0), stack(1), stack(2)
+        return None, stack(0), stack(1)
+
+    def _fatten_v(self, knw):
+        """``iz`` or ``[iz_lin, iz_lin - 1]`` (reference ``eulerian.py:451``)."""
+        if self.iz is None:
+            return None
+        if knw.vkernel == "nearest":
+            return copy.deepcopy(self.iz)
+        if knw.vkernel in ["dz", "linear"]:
+            return np.vstack([self.iz_lin, self.iz_lin - 1]).T
+        raise ValueError("vkernel not supported")
+
+    def _fatten_vl(self, knw):
+        """``izl`` or ``[izl_lin, izl_lin - 1]`` (reference ``eulerian.py:474``)."""
+        if self.izl is None:
+            return None
+        if knw.vkernel == "nearest":
+            return copy.deepcopy(self.izl)
+        if knw.vkernel in ["dz", "linear"]:
+            return np.vstack([self.izl_lin, self.izl_lin - 1]).T
+        raise ValueError("vkernel not supported")
+
+    def _fatten_t(self, knw):
+        """``it`` or ``[it_lin, it_lin + 1]`` (reference ``eulerian.py:497``)."""
+        if self.it is None:
+            return None
+        if knw.tkernel == "nearest":
+            return copy.deepcopy(self.it)
+        if knw.tkernel in ["dt", "linear"]:
+            return np.vstack([self.it_lin, self.it_lin + 1]).T
+        raise ValueError("tkernel not supported")
+
+    def fatten(self, knw, four_d=False, required="all", ind_moves_kwarg={}):
+        """Indices of all the grid points a kernel touches, in the requested dimensions (reference
+        ``eulerian.py:520``).  New dimensions are appended as trailing axes: ``(N, M[, nz][, nt])``."""
+        if required != "all" and isinstance(required, str):
+            required = (required,)
+        elif required != "all" and not isinstance(required, tuple):
+            required = tuple(required)
+        want = lambda name: required == "all" or name in required  # noqa: E731
+
+        def add_axis(new, arrays):
+            # broadcast `new` (N,) or (N, k) against arrays (N, ...) -> all (N, ..., k)
+            new = np.asarray(new)
+            new = new.reshape(len(new), -1)
+            shape = arrays[0].shape
+            tail = (1,) * (len(shape) - 1)
+            full = shape + (new.shape[1],)
+            first = np.broadcast_to(new.reshape((shape[0],) + tail + (new.shape[1],)), full).astype(int)
+            rest = [np.broadcast_to(a[..., None], full).astype(int) for a in arrays]
+            return [first] + rest
+
+        if want("X") or want("Y") or want("face"):
+            ffc, fiy, fix = self._fatten_h(knw, ind_moves_kwarg=ind_moves_kwarg)
+            if ffc is not None:
+                arrays, keys = [ffc, fiy, fix], ["face", "Y", "X"]
+            else:
+                arrays, keys = [fiy, fix], ["Y", "X"]
+        else:
+            arrays, keys = [np.zeros(self.N)], ["place_holder"]
+        vertical = None
+        if want("Z"):
+            vertical, vkey = self._fatten_v(knw), "Z"
+        elif want("Zl"):
+            vertical, vkey = self._fatten_vl(knw), "Zl"
+        if vertical is not None:
+            arrays = add_axis(vertical, arrays)
+            keys.insert(0, vkey)
+        elif four_d and not (want("Z") or want("Zl")):
+            arrays = [np.expand_dims(a, axis=-1) for a in arrays]
+        temporal = self._fatten_t(knw) if want("time") else None
+        if temporal is not None:
+            arrays = add_axis(temporal, arrays)
+            keys.insert(0, "time")
+        elif four_d and not want("time"):
+            arrays = [np.expand_dims(a, axis=-1) for a in arrays]
+        table = dict(zip(keys, arrays))
+        if required == "all":
+            required = [k for k in keys if k != "place_holder"]
+        return tuple(table[k] for k in required)
+
     def get_px_py(self):
         """Longitude / latitude of the 4 corners around each point (reference ``eulerian.py:592``)."""
         od = self.ocedata
