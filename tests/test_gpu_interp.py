@@ -141,3 +141,34 @@ def test_sorted_execution_equals_plain(monkeypatch):
     for a, b, c in zip(plain, sorted_, again):
         np.testing.assert_array_equal(a, b)
         np.testing.assert_array_equal(a, c)
+
+
+def test_partition_of_unity_at_scale():
+    """Size-independent property on 2 x 10^6 scattered points (LLC90 x 50): whatever stencil the land mask
+    selects, interpolation weights sum to one and derivative weights to zero -- a constant field comes
+    back as that constant (or NaN where even the centre cell is dry), its derivatives as zero."""
+    import seaduck_b200 as sd
+    from seaduck_b200 import synthetic
+
+    ds = synthetic.llc(n=90, nz=50, land_blobs=True, tracers=True)
+    ds["T"].values[...] = 7.25
+    od = sd.OceData(ds)
+    n = 2_000_000
+    lon, lat, _ = synthetic.llc_seed_particles(ds, n, seed=31, lat_range=(-72.0, 88.0))
+    dep = -np.random.default_rng(32).uniform(5.0, 4000.0, n)
+    pos = sd.Position().from_latlon(x=lon, y=lat, z=dep, data=od)
+    all9 = list(range(9))
+    val, lin, ddx, ddz = pos.interpolate(
+        ["T", "T", "T", "T"],
+        [sd.KnW(), sd.KnW(vkernel="linear"), sd.KnW(hkernel="dx", h_order=1, inheritance=[all9, [0, 1, 3, 5, 7]]), sd.KnW(vkernel="dz")],
+    )
+    wet = ~np.isnan(val)
+    assert 0.5 < wet.mean() < 0.95  # the land blobs and the bathymetry-free ocean
+    np.testing.assert_allclose(val[wet], 7.25, rtol=0, atol=1e-12)
+    ok = ~np.isnan(lin)
+    np.testing.assert_allclose(lin[ok], 7.25, rtol=0, atol=1e-11)
+    ok = ~np.isnan(ddx)
+    assert ok.any()
+    np.testing.assert_allclose(ddx[ok], 0.0, rtol=0, atol=1e-11)
+    ok = ~np.isnan(ddz)
+    np.testing.assert_allclose(ddz[ok], 0.0, rtol=0, atol=1e-11)
