@@ -330,6 +330,24 @@ int sdk_time_index(const double *t, const double *time_midp, int32_t n_midp, int
 int sdk_log_budget(const sdk_grid *grid, const sdk_log_record *records, const int64_t *offset, int64_t n_particles,
                    int64_t n_rec, int16_t *ind1, int16_t *ind2, double *frac, double *tres, double *work, void *stream);
 
+/* ---- stencils of the Eulerian budget (seaduck/eulerian_budget.py); fp64, device pointers ------------- */
+/* Halo gather: out[o][k] = map[k] < 0 ? 0 : src[o * src_plane + map[k]] for o < n_outer, k < n_map.  The host
+ * builds `map` for buffer_x_withface :214 / buffer_y_withface :262 (LLC faces incl. rotation),
+ * buffer_x_periodic :309, buffer_y_periodic :321 and buffer_z_nearest :333. */
+int sdk_gather_plane(const double *src, int64_t n_outer, int64_t src_plane, const int64_t *map, int64_t n_map,
+                     double *out, void *stream);
+/* Tracer concentration on cell walls from a buffered field: buf [n_outer][n_out + 3][n_inner] (two halo
+ * points before, one after), vel and out [n_outer][n_out][n_inner]. */
+enum {
+    SDK_STENCIL_DST3 = 0,      /* third_order_DST_x / _y :477-532 */
+    SDK_STENCIL_LIMITER = 1,   /* second_order_flux_limiter_x / _y :363-417 (superbee) */
+    SDK_STENCIL_LIMITER_Z = 2  /* second_order_flux_limiter_z :419 */
+};
+int sdk_wall_stencil(int scheme, const double *buf, const double *vel, double *out, int64_t n_outer, int64_t n_out,
+                     int64_t n_inner, void *stream);
+/* third_order_upwind_z :448: s, w, out [nz][n_inner]; sets w[0][:] = 0 like the reference does */
+int sdk_upwind3_z(const double *s, double *w, double *out, int64_t nz, int64_t n_inner, void *stream);
+
 /* Output snapshot of a stop in 32 bytes per particle (what Particle.to_list_of_time returns per stop
  * and the ranks exchange): out[0..2][n_pad] = lon, lat, dep; out[3][n_pad] = one 64-bit word
  * face << 34 | iy << 21 | ix << 8 | izl (6 + 13 + 13 + 8 bits).  NULL inputs read as zero; device pointers. */

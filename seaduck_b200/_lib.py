@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.environ.get("SEADUCK_B200_LIB") or os.path.join(_HERE, "libseaduck_b200.so")
-SOURCES = ["advect.cu", "locate.cu", "interp.cu", "budget.cu", "selftest.cu", "capi.cu"]
+SOURCES = ["advect.cu", "locate.cu", "interp.cu", "budget.cu", "stencil.cu", "selftest.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",
@@ -171,6 +171,9 @@ def lib():
         L.sdk_track_scratch_bytes.argtypes = [C.c_int64]
         L.sdk_track_host.argtypes = [vp, C.POINTER(Velocity), C.POINTER(TrackIO), vp, C.c_int32, C.c_double, C.POINTER(AdvectParams), vp, vp]
         L.sdk_finish_stop.argtypes = [vp, vp, vp, C.c_int32, C.c_double, vp, vp, C.c_int64, vp]
+        L.sdk_gather_plane.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp]
+        L.sdk_wall_stencil.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64, vp]
+        L.sdk_upwind3_z.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, vp]
         L.sdk_log_budget.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]
         L.sdk_pack_snapshot.argtypes = [C.c_int64, C.c_int64] + [vp] * 9
         L.sdk_peer_enable.argtypes = [C.c_int]

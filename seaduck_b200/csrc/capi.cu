@@ -15,6 +15,11 @@
 #include "locate_args.cuh"
 
 namespace sdk {
+cudaError_t launch_gather_plane(const double *src, int64_t n_outer, int64_t src_plane, const int64_t *map, int64_t n_map,
+                                double *out, cudaStream_t s);
+cudaError_t launch_wall_stencil(int scheme, const double *buf, const double *vel, double *out, int64_t n_outer, int64_t n_out,
+                                int64_t n_inner, cudaStream_t s);
+cudaError_t launch_upwind3_z(const double *sfield, double *w, double *out, int64_t nz, int64_t n_inner, cudaStream_t s);
 cudaError_t launch_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
                                  const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl, double *out,
                                  cudaStream_t s);
@@ -460,6 +465,33 @@ int sdk_log_budget(const sdk_grid *grid, const sdk_log_record *records, const in
     a.rows = grid->dev.has_face ? 5 : 4;
     cudaError_t e = sdk::launch_budget(a, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_log_budget: launch");
+    return SDK_OK;
+}
+
+int sdk_gather_plane(const double *src, int64_t n_outer, int64_t src_plane, const int64_t *map, int64_t n_map,
+                     double *out, void *stream) {
+    if (n_outer < 0 || n_map < 0 || src_plane < 0) return fail(SDK_EINVAL, "sdk_gather_plane: negative size");
+    if (n_outer * n_map > 0 && (!src || !map || !out)) return fail(SDK_EINVAL, "sdk_gather_plane: null array");
+    cudaError_t e = sdk::launch_gather_plane(src, n_outer, src_plane, map, n_map, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_gather_plane: launch");
+    return SDK_OK;
+}
+
+int sdk_wall_stencil(int scheme, const double *buf, const double *vel, double *out, int64_t n_outer, int64_t n_out,
+                     int64_t n_inner, void *stream) {
+    if (scheme < SDK_STENCIL_DST3 || scheme > SDK_STENCIL_LIMITER_Z) return fail(SDK_EINVAL, "sdk_wall_stencil: unknown scheme");
+    if (n_outer < 0 || n_out < 0 || n_inner < 0) return fail(SDK_EINVAL, "sdk_wall_stencil: negative size");
+    if (n_outer * n_out * n_inner > 0 && (!buf || !vel || !out)) return fail(SDK_EINVAL, "sdk_wall_stencil: null array");
+    cudaError_t e = sdk::launch_wall_stencil(scheme, buf, vel, out, n_outer, n_out, n_inner, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_wall_stencil: launch");
+    return SDK_OK;
+}
+
+int sdk_upwind3_z(const double *s, double *w, double *out, int64_t nz, int64_t n_inner, void *stream) {
+    if (nz < 0 || n_inner < 0) return fail(SDK_EINVAL, "sdk_upwind3_z: negative size");
+    if (nz * n_inner > 0 && (!s || !w || !out)) return fail(SDK_EINVAL, "sdk_upwind3_z: null array");
+    cudaError_t e = sdk::launch_upwind3_z(s, w, out, nz, n_inner, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_upwind3_z: launch");
     return SDK_OK;
 }
 
