@@ -158,7 +158,7 @@ typedef struct sdk_log {
 int sdk_abi_version(void);
 /* sizeof() of the structures above as the library was compiled (binding self-check): 0 sdk_grid_desc,
  * 1 sdk_velocity, 2 sdk_particles, 3 sdk_advect_params, 4 sdk_log, 5 sdk_located, 6 sdk_track_io,
- * 7 sdk_kernel_desc, 8 sdk_field, 9 sdk_points; -1 for anything else */
+ * 7 sdk_kernel_desc, 8 sdk_field, 9 sdk_points, 10 sdk_budget_fields; -1 for anything else */
 int64_t sdk_struct_size(int which);
 const char *sdk_last_error(void);
 /* number of SMs of the current device (grid sizing), <0 on error */
@@ -329,6 +329,30 @@ int sdk_time_index(const double *t, const double *time_midp, int32_t n_midp, int
  * pointers.  Needs particles with a depth (the reference does too). */
 int sdk_log_budget(const sdk_grid *grid, const sdk_log_record *records, const int64_t *offset, int64_t n_particles,
                    int64_t n_rec, int16_t *ind1, int16_t *ind2, double *frac, double *tres, double *work, void *stream);
+
+/* calculate_budget (lagrangian_budget.py:603) on what sdk_log_budget produced: tracer concentration at every
+ * record from the wall concentrations (prefetch_vector :548), its change between consecutive records of a
+ * particle, the part explained by the Eulerian tendency (lhs_contribution :575) and the split of the rest
+ * over the right-hand-side terms in proportion to term^2 (contr_p_relaxed :583 with p = 1).  Device pointers;
+ * fields are one model time step in the dataset's layout. */
+#define SDK_MAX_BUDGET_TERMS 8
+typedef struct sdk_budget_fields {
+    int32_t n_terms;     /* right-hand-side terms, <= SDK_MAX_BUDGET_TERMS */
+    int32_t dir_of_time; /* -1: the particles ran backward in time, +1 forward */
+    int32_t rows;        /* rows of ind1 / ind2: 5 (iw, iz, face, iy, ix) or 4 (no face) */
+    int32_t reserved;
+    int32_t cell_shape[4]; /* (nz, nface, ny, nx) of term[] and lhs; nface = 1 without faces */
+    int32_t wall_shape[4]; /* same for each of the three arrays stacked in walls */
+    const double *term[SDK_MAX_BUDGET_TERMS];
+    const double *lhs;
+    const double *walls; /* [3][wall_shape] */
+} sdk_budget_fields;
+/* conc: [n_rec]; contr: [n_terms + 2][n_rec - 1] = the terms in order, then "error", then the lhs
+ * contribution; work: n_rec bytes of scratch.  Indices follow numpy (negative values count from the end). */
+int sdk_log_calculate_budget(const sdk_log_record *records, const int64_t *offset, int64_t n_particles, int64_t n_rec,
+                             const int16_t *ind1, const int16_t *ind2, const double *frac, const double *tres,
+                             const sdk_budget_fields *fields, double *conc, double *contr, unsigned char *work,
+                             void *stream);
 
 /* ---- stencils of the Eulerian budget (seaduck/eulerian_budget.py); fp64, device pointers ------------- */
 /* Halo gather: out[o][k] = map[k] < 0 ? 0 : src[o * src_plane + map[k]] for o < n_outer, k < n_map.  The host

@@ -139,3 +139,55 @@ def find_ind_frac_tres(og, rec, offset):
         tres = tres0 * fracs
     tres[np.asarray(rec["vs"]) > 6] = 0.0
     return ind1, ind2, frac, tres, last, first
+
+
+def wall_concentration_array(fields, xname="sxprime", yname="syprime", zname="szprime"):
+    """lagrangian_budget.py:548 (``prefetch_vector``): the three wall fields stacked, padded to a common shape."""
+    parts = [np.asarray(fields[k], float) for k in (xname, yname, zname)]
+    shape = tuple(max(p.shape[d] for p in parts) for d in range(parts[0].ndim))
+    out = np.full((3,) + shape, np.nan)
+    for k, p in enumerate(parts):
+        out[(k,) + tuple(slice(0, m) for m in p.shape)] = p
+    return out
+
+
+def calculate_budget(rec, offset, ind1, ind2, frac, tres, fields, rhs_list, lhs_name="lhs", dir_of_time=-1, wall_names=None):
+    """lagrangian_budget.py:603 with ``lhs_contribution`` :575 and ``contr_p_relaxed`` :583 (p = 1), record by
+    record.  ``rec`` = flat log arrays (tt, izl, fc, iy, ix), ``fields`` = name -> array of one model step."""
+    walls = wall_concentration_array(fields, *(wall_names or ()))
+    n = int(offset[-1])
+    is_last = np.zeros(n, bool)
+    is_last[np.asarray(offset[1:]) - 1] = True
+    conc = np.empty(n)
+    for i in range(n):
+        s1 = walls[tuple(int(v) for v in ind1[:, i])]
+        s2 = walls[tuple(int(v) for v in ind2[:, i])]
+        conc[i] = s1 * frac[i] + (1 - frac[i]) * s2
+    names = list(rhs_list)
+    out = {k: np.empty(n - 1) for k in names + ["error", lhs_name]}
+    tt = np.asarray(rec["tt"], float)
+    with np.errstate(all="ignore"):
+        for i in range(n - 1):
+            cell = (int(rec["izl"][i]) - 1, int(rec["fc"][i]), int(rec["iy"][i]), int(rec["ix"][i]))
+            if is_last[i]:
+                delta = span = dt = 0.0
+            else:
+                delta = float(np.nan_to_num(conc[i + 1] - conc[i]))
+                span = dir_of_time * tres[i + 1]
+                dt = float(np.nan_to_num(tt[i + 1] - tt[i]))
+            lhs = dt * fields[lhs_name][cell]
+            target = delta - lhs
+            x = [np.float64(fields[k][cell]) for k in names]
+            deno, total = np.float64(0.0), np.float64(0.0)
+            for v in x:
+                deno = deno + v * v
+                total = total + v
+            gap = target - total * span
+            acc = np.float64(0.0)
+            for k, v in zip(names, x):
+                c = v * span + (v * v) / deno * gap
+                out[k][i] = c
+                acc = acc + c
+            out["error"][i] = 0.0 + (target - acc)
+            out[lhs_name][i] = lhs
+    return out, conc

@@ -3,6 +3,11 @@
 ``which_wall`` :85, ``wall_index`` :192, ``redo_index`` :223, ``residence_time`` :139, ``tres_update``
 :144), made by running the UNMODIFIED reference on Lagrangian cases of ``tests/cases.py``.
 
+For the LLC case the budget itself is evaluated too: ``calculate_budget`` :603 (``lhs_contribution`` :575,
+``contr_p_relaxed`` :583, ``prefetch_vector`` :548) on seeded random budget terms and wall concentrations
+(``tests/cases.py: budget_fields``, rebuilt from the same seed by the tests), with the in-memory equivalent of what
+``dump_to_zarr`` :348 stores.
+
     python oracle/make_golden_budget.py        # writes tests/golden/budget_*.npz
 """
 
@@ -30,6 +35,36 @@ import cases  # noqa: E402
 BUDGET_CASES = [cases.case_llc_transport, cases.case_overturning]
 
 
+class _Var:
+    """The little of an xarray.DataArray that ``calculate_budget`` touches."""
+
+    def __init__(self, a):
+        self.values = np.asarray(a)
+
+    def __array__(self, dtype=None, copy=None):
+        return self.values if dtype is None else self.values.astype(dtype)
+
+    def __sub__(self, other):
+        return _Var(self.values - other)
+
+
+class _Stored(dict):
+    """What ``dump_to_zarr`` would have written, held in memory."""
+
+    __getattr__ = dict.__getitem__
+
+
+def stored_particle_array(neo, ind1, ind2, frac, tres):
+    st = _Stored()
+    for k in ("tt", "iz", "iy", "ix"):
+        st[k] = _Var(np.asarray(neo[k]))
+    st["face"] = _Var(np.asarray(neo["fc"]).astype("int16"))
+    st["shapes"] = _Var(np.asarray(neo["shapes"]))
+    st["ind1"], st["ind2"] = _Var(np.asarray(ind1).astype("int16")), _Var(np.asarray(ind2).astype("int16"))
+    st["frac"], st["tres"] = _Var(frac), _Var(tres)
+    return st
+
+
 def run_case(case):
     warnings.simplefilter("ignore")
     od = sd.OceData(case["ds"])
@@ -45,6 +80,19 @@ def run_case(case):
         out[f"s{i}_ind1"], out[f"s{i}_ind2"] = np.asarray(ind1), np.asarray(ind2)
         out[f"s{i}_frac"], out[f"s{i}_tres"] = np.asarray(frac, float), np.asarray(tres, float)
         out[f"s{i}_first"], out[f"s{i}_last"] = np.asarray(first), np.asarray(last)
+        if od.tp.typ == "LLC":
+            fields = cases.budget_fields(np.asarray(case["ds"]["maskC"]).shape, seed=100 + i)
+            stored = stored_particle_array(neo, ind1, ind2, frac, tres)
+            for tag, kw, direction in (
+                ("pad", dict(same_size=False), -1),
+                ("same", dict(zname="szprime_same"), 1),
+            ):
+                with np.errstate(all="ignore"):
+                    contr, conc, bfirst, blast = lb.calculate_budget(stored, fields, list(cases.RHS_TERMS), kw, "lhs", direction)
+                for k, v in contr.items():
+                    out[f"s{i}_bud_{tag}_{k}"] = np.asarray(v, float)
+                out[f"s{i}_bud_{tag}_conc"] = np.asarray(conc, float)
+                assert np.array_equal(bfirst, first) and np.array_equal(blast, last)
     return out
 
 

@@ -122,6 +122,17 @@ class TrackIO(C.Structure):
     ]
 
 
+MAX_BUDGET_TERMS = 8
+
+
+class BudgetFields(C.Structure):
+    _fields_ = [
+        ("n_terms", C.c_int32), ("dir_of_time", C.c_int32), ("rows", C.c_int32), ("reserved", C.c_int32),
+        ("cell_shape", C.c_int32 * 4), ("wall_shape", C.c_int32 * 4),
+        ("term", C.c_void_p * MAX_BUDGET_TERMS), ("lhs", C.c_void_p), ("walls", C.c_void_p),
+    ]
+
+
 class SdkError(RuntimeError):
     pass
 
@@ -171,6 +182,7 @@ def lib():
         L.sdk_track_scratch_bytes.argtypes = [C.c_int64]
         L.sdk_track_host.argtypes = [vp, C.POINTER(Velocity), C.POINTER(TrackIO), vp, C.c_int32, C.c_double, C.POINTER(AdvectParams), vp, vp]
         L.sdk_finish_stop.argtypes = [vp, vp, vp, C.c_int32, C.c_double, vp, vp, C.c_int64, vp]
+        L.sdk_log_calculate_budget.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, C.POINTER(BudgetFields), vp, vp, vp, vp]
         L.sdk_gather_plane.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp]
         L.sdk_wall_stencil.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64, vp]
         L.sdk_upwind3_z.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, vp]

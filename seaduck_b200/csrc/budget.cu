@@ -142,4 +142,83 @@ cudaError_t launch_budget(const BudgetArgs &a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ---- calculate_budget (lagrangian_budget.py:603) ---------------------------------------------------------
+
+__global__ void budget_mark_last_kernel(const __grid_constant__ BudgetTermArgs a) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n_particles) return;
+    const int64_t end = a.offset[p + 1];
+    if (end > a.offset[p]) a.is_last[end - 1] = 1;
+}
+
+// numpy fancy indexing of a [3][shape] array with one column of ind1 / ind2
+__device__ __forceinline__ double wall_value(const BudgetTermArgs &a, const int16_t *ind, int64_t i) {
+    const int32_t *sh = a.f.wall_shape;
+    int r = 0;
+    const int iw = wrap_index(ind[(r++) * a.n_rec + i], 3);
+    const int iz = wrap_index(ind[(r++) * a.n_rec + i], sh[0]);
+    const int fc = a.f.rows == 5 ? wrap_index(ind[(r++) * a.n_rec + i], sh[1]) : 0;
+    const int iy = wrap_index(ind[(r++) * a.n_rec + i], sh[2]);
+    const int ix = wrap_index(ind[r * a.n_rec + i], sh[3]);
+    return __ldg(a.f.walls + ((((int64_t)iw * sh[0] + iz) * sh[1] + fc) * sh[2] + iy) * sh[3] + ix);
+}
+
+// trc_conc = s1 * frac + (1 - frac) * s2   (:652-655)
+__global__ void budget_conc_kernel(const __grid_constant__ BudgetTermArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_rec) return;
+    const double fr = a.frac[i];
+    a.conc[i] = wall_value(a, a.ind1, i) * fr + (1 - fr) * wall_value(a, a.ind2, i);
+}
+
+__global__ void budget_contr_kernel(const __grid_constant__ BudgetTermArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t m = a.n_rec - 1;
+    if (i >= m) return;
+    double delta = 0.0, span = 0.0, dt = 0.0;
+    const sdk_log_record &r = a.rec[i];
+    if (!a.is_last[i]) {
+        delta = nan_to_num(a.conc[i + 1] - a.conc[i]);     // :656-657
+        span = (double)a.f.dir_of_time * a.tres[i + 1];    // :658-659
+        dt = nan_to_num(a.rec[i + 1].tt - r.tt);           // lhs_contribution :575
+    }
+    const int32_t *sh = a.f.cell_shape;
+    const int64_t cell = (((int64_t)wrap_index(r.izl - 1, sh[0]) * sh[1] + (a.f.rows == 5 ? wrap_index(r.fc, sh[1]) : 0)) * sh[2] +
+                          wrap_index(r.iy, sh[2])) * sh[3] + wrap_index(r.ix, sh[3]);
+    const double lhs = dt * __ldg(a.f.lhs + cell);
+    const double target = delta - lhs;  // :662
+    // contr_p_relaxed :583, p = 1
+    double x[SDK_MAX_BUDGET_TERMS];
+    double deno = 0.0, sums = 0.0;
+#pragma unroll
+    for (int k = 0; k < SDK_MAX_BUDGET_TERMS; ++k)
+        if (k < a.f.n_terms) {
+            x[k] = __ldg(a.f.term[k] + cell);
+            deno += x[k] * x[k];
+            sums += x[k];
+        }
+    const double gap = target - sums * span;
+    double total = 0.0;
+#pragma unroll
+    for (int k = 0; k < SDK_MAX_BUDGET_TERMS; ++k)
+        if (k < a.f.n_terms) {
+            const double c = x[k] * span + x[k] * x[k] / deno * gap;
+            a.contr[k * m + i] = c;
+            total += c;
+        }
+    a.contr[(int64_t)a.f.n_terms * m + i] = 0.0 + (target - total);
+    a.contr[(int64_t)(a.f.n_terms + 1) * m + i] = lhs;
+}
+
+cudaError_t launch_budget_terms(const BudgetTermArgs &a, cudaStream_t s) {
+    if (a.n_rec == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(a.is_last, 0, (size_t)a.n_rec, s);
+    if (e != cudaSuccess) return e;
+    const int t = 256;
+    if (a.n_particles > 0) budget_mark_last_kernel<<<(unsigned)((a.n_particles + t - 1) / t), t, 0, s>>>(a);
+    budget_conc_kernel<<<(unsigned)((a.n_rec + t - 1) / t), t, 0, s>>>(a);
+    if (a.n_rec > 1) budget_contr_kernel<<<(unsigned)((a.n_rec - 1 + t - 1) / t), t, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 }  // namespace sdk

@@ -19,4 +19,17 @@ struct BudgetArgs {
 
 cudaError_t launch_budget(const BudgetArgs &a, cudaStream_t s);
 
+struct BudgetTermArgs {
+    const sdk_log_record *rec;
+    const int64_t *offset;
+    int64_t n_particles, n_rec;
+    const int16_t *ind1, *ind2;
+    const double *frac, *tres;
+    sdk_budget_fields f;
+    double *conc, *contr;
+    unsigned char *is_last;
+};
+
+cudaError_t launch_budget_terms(const BudgetTermArgs &a, cudaStream_t s);
+
 }  // namespace sdk

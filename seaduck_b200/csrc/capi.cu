@@ -468,6 +468,44 @@ int sdk_log_budget(const sdk_grid *grid, const sdk_log_record *records, const in
     return SDK_OK;
 }
 
+int sdk_log_calculate_budget(const sdk_log_record *records, const int64_t *offset, int64_t n_particles, int64_t n_rec,
+                             const int16_t *ind1, const int16_t *ind2, const double *frac, const double *tres,
+                             const sdk_budget_fields *fields, double *conc, double *contr, unsigned char *work,
+                             void *stream) {
+    if (!fields || n_particles < 0 || n_rec < 0) return fail(SDK_EINVAL, "sdk_log_calculate_budget: bad argument");
+    if (fields->n_terms < 1 || fields->n_terms > SDK_MAX_BUDGET_TERMS)
+        return fail(SDK_EINVAL, "sdk_log_calculate_budget: between 1 and SDK_MAX_BUDGET_TERMS right-hand-side terms");
+    if (fields->rows != 4 && fields->rows != 5) return fail(SDK_EINVAL, "sdk_log_calculate_budget: rows must be 4 or 5");
+    if (fields->dir_of_time != 1 && fields->dir_of_time != -1)
+        return fail(SDK_EINVAL, "sdk_log_calculate_budget: dir_of_time must be +1 or -1");
+    for (int d = 0; d < 4; ++d)
+        if (fields->cell_shape[d] < 1 || fields->wall_shape[d] < 1)
+            return fail(SDK_EINVAL, "sdk_log_calculate_budget: empty field");
+    if (n_rec > 0) {
+        if (!records || !offset || !ind1 || !ind2 || !frac || !tres || !conc || !work || !fields->lhs || !fields->walls)
+            return fail(SDK_EINVAL, "sdk_log_calculate_budget: null array");
+        if (n_rec > 1 && !contr) return fail(SDK_EINVAL, "sdk_log_calculate_budget: null array");
+        for (int k = 0; k < fields->n_terms; ++k)
+            if (!fields->term[k]) return fail(SDK_EINVAL, "sdk_log_calculate_budget: null term");
+    }
+    sdk::BudgetTermArgs a;
+    a.rec = records;
+    a.offset = offset;
+    a.n_particles = n_particles;
+    a.n_rec = n_rec;
+    a.ind1 = ind1;
+    a.ind2 = ind2;
+    a.frac = frac;
+    a.tres = tres;
+    a.f = *fields;
+    a.conc = conc;
+    a.contr = contr;
+    a.is_last = work;
+    cudaError_t e = sdk::launch_budget_terms(a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_log_calculate_budget: launch");
+    return SDK_OK;
+}
+
 int sdk_gather_plane(const double *src, int64_t n_outer, int64_t src_plane, const int64_t *map, int64_t n_map,
                      double *out, void *stream) {
     if (n_outer < 0 || n_map < 0 || src_plane < 0) return fail(SDK_EINVAL, "sdk_gather_plane: negative size");
@@ -542,6 +580,7 @@ int64_t sdk_struct_size(int which) {
         case 7: return sizeof(sdk_kernel_desc);
         case 8: return sizeof(sdk_field);
         case 9: return sizeof(sdk_points);
+        case 10: return sizeof(sdk_budget_fields);
         default: return -1;
     }
 }

@@ -156,3 +156,26 @@ def assert_close(name, got, ref, rtol=1e-9):
     err = np.abs(got - ref)
     bad = err > rtol * np.maximum(np.abs(ref), scale)
     assert not bad.any(), f"{name}: {int(bad.sum())} of {ref.size} beyond {rtol} (max err {err.max():.3e}, scale {scale:.3e})"
+
+
+# ---- Lagrangian budget: terms and wall concentrations of one model time step ------------------------------
+
+RHS_TERMS = ["adv", "dif", "forc"]
+
+
+def budget_fields(shape, seed):
+    """Budget terms + wall concentrations of one time step: name -> array (a stand-in for the model output)."""
+    rng = np.random.default_rng(seed)
+    nz = shape[0]
+    out = {k: rng.normal(size=shape) * 1e-7 for k in RHS_TERMS + ["lhs"]}
+    dead = rng.random(shape) < 0.03  # cells where every term vanishes: the relaxation divides 0 by 0
+    for k in RHS_TERMS:
+        out[k][dead] = 0.0
+    out["forc"][rng.random(shape) < 0.3] = 0.0
+    for k in ("sxprime", "syprime"):
+        out[k] = rng.normal(size=shape)
+    out["szprime"] = rng.normal(size=(nz + 1,) + tuple(shape[1:]))
+    out["szprime_same"] = out["szprime"][:nz].copy()
+    for k in ("sxprime", "syprime", "szprime"):
+        out[k][rng.random(out[k].shape) < 0.02] = np.nan
+    return out

@@ -31,3 +31,27 @@ def test_budget_oracle_matches_reference(make, oracle_lib):
         np.testing.assert_array_equal(ind2, gold[f"s{i}_ind2"])
         np.testing.assert_allclose(frac, gold[f"s{i}_frac"], rtol=1e-12, atol=0)
         np.testing.assert_allclose(tres, gold[f"s{i}_tres"], rtol=1e-12, atol=0)
+
+
+def test_calculate_budget_oracle_matches_reference():
+    """oracle/budget_oracle.calculate_budget against the reference's calculate_budget (:603) on the reference's
+    own ind / frac / tres: every term, the error and the concentrations, to the bit (NaN where it has NaN)."""
+    from oracle import budget_oracle as bo
+
+    case = cases.case_llc_transport()
+    logs = np.load(os.path.join(GOLD, "lagrangian_llc_transport.npz"))
+    gold = np.load(os.path.join(GOLD, "budget_llc_transport.npz"))
+    shape = np.asarray(case["ds"]["maskC"]).shape
+    for i in range(len(case["stops"])):
+        rec = {k: logs[f"s{i}_log_{k}"] for k in ("tt", "izl", "fc", "iy", "ix")}
+        fields = cases.budget_fields(shape, seed=100 + i)
+        for tag, names, direction in (("pad", None, -1), ("same", ("sxprime", "syprime", "szprime_same"), 1)):
+            out, conc = bo.calculate_budget(
+                rec, logs[f"s{i}_log_offset"], gold[f"s{i}_ind1"], gold[f"s{i}_ind2"], gold[f"s{i}_frac"], gold[f"s{i}_tres"],
+                fields, cases.RHS_TERMS, "lhs", direction, names,
+            )
+            np.testing.assert_array_equal(conc, gold[f"s{i}_bud_{tag}_conc"])
+            assert set(out) == set(cases.RHS_TERMS) | {"error", "lhs"}
+            for k, v in out.items():
+                np.testing.assert_array_equal(v, gold[f"s{i}_bud_{tag}_{k}"], err_msg=f"{tag} {k}")
+            assert np.isnan(out["adv"]).any()  # the 0 / 0 cells are in the sample

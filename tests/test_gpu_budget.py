@@ -70,3 +70,96 @@ def test_budget_matches_oracle_on_own_log(oracle_lib):
     np.testing.assert_array_equal(ind2, r2)
     cases.assert_close("frac", frac, rfrac)
     cases.assert_close("tres", tres, rtres)
+
+
+BUDGET_VARIANTS = (("pad", dict(same_size=False), -1), ("same", dict(zname="szprime_same"), 1))
+
+
+def test_calculate_budget_matches_reference():
+    """calculate_budget (:603) on the device log against the reference's on its own log: wherever both chose the
+    same walls (see the tie note above) the concentrations and every contribution agree to 1e-9."""
+    import seaduck_b200 as sd
+    from seaduck_b200 import lagrangian_budget as lb
+
+    case = cases.case_llc_transport()
+    gold = np.load(os.path.join(GOLD, "budget_llc_transport.npz"))
+    od = sd.OceData(case["ds"])
+    pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, save_raw=True, **case["kw"])
+    shape = np.asarray(case["ds"]["maskC"]).shape
+    for i, ts in enumerate(case["stops"]):
+        pt.empty_lists()
+        pt.note_taking(stamp=15)
+        pt.to_next_stop(ts)
+        ind1, ind2, _, _, _, _ = lb.find_ind_frac_tres(pt, od)
+        same = (ind1 == gold[f"s{i}_ind1"]).all(axis=0) & (ind2 == gold[f"s{i}_ind2"]).all(axis=0)
+        assert same.mean() > 0.98
+        fields = cases.budget_fields(shape, seed=100 + i)
+        for tag, kw, direction in BUDGET_VARIANTS:
+            contr, conc, first, last = lb.calculate_budget(pt, fields, list(cases.RHS_TERMS), kw, "lhs", direction)
+            np.testing.assert_array_equal(first, gold[f"s{i}_first"])
+            np.testing.assert_array_equal(last, gold[f"s{i}_last"])
+            want = gold[f"s{i}_bud_{tag}_conc"]
+            np.testing.assert_array_equal(np.isnan(conc[same]), np.isnan(want[same]))
+            cases.assert_close("conc", conc[same], want[same])
+            pair = same[:-1] & same[1:]
+            assert set(contr) == set(cases.RHS_TERMS) | {"error", "lhs"}
+            for k, v in contr.items():
+                w = gold[f"s{i}_bud_{tag}_{k}"]
+                assert v.shape == w.shape
+                np.testing.assert_array_equal(np.isnan(v[pair]), np.isnan(w[pair]), err_msg=k)
+                if k == "error":  # a rounding residue of O(1e-16): only its size is meaningful
+                    assert np.nanmax(np.abs(v[pair])) < 1e-13
+                else:
+                    cases.assert_close(k, v[pair], w[pair], rtol=1e-8)
+
+
+def test_calculate_budget_matches_oracle_on_own_log():
+    """Same inputs on both sides (the device's own log, indices, fractions and residence times): bit-exact."""
+    import seaduck_b200 as sd
+    from oracle import budget_oracle as bo
+    from seaduck_b200 import lagrangian_budget as lb
+    from seaduck_b200 import synthetic
+
+    ds = synthetic.llc(n=30, nz=10)
+    n = 1500
+    lon, lat, dep = synthetic.llc_seed_particles(ds, n, seed=21, depth_range=(5, 300))
+    od = sd.OceData(ds)
+    pt = sd.Particle(x=lon, y=lat, z=dep, t=np.zeros(n), data=od, save_raw=True, uname="utrans", vname="vtrans", wname="wtrans", transport=True)
+    pt.note_taking(stamp=15)
+    pt.to_next_stop(-30 * cases.DAY)
+    ind1, ind2, frac, tres, last, first = lb.find_ind_frac_tres(pt, od)
+    rec = pt.raw_arrays()[-1]
+    fields = cases.budget_fields(np.asarray(ds["maskC"]).shape, seed=5)
+    assert ind1.shape[1] > 10_000
+    for tag, kw, direction in BUDGET_VARIANTS:
+        contr, conc, bfirst, blast = lb.calculate_budget(pt, fields, list(cases.RHS_TERMS), kw, "lhs", direction)
+        names = None if tag == "pad" else ("sxprime", "syprime", "szprime_same")
+        want, wconc = bo.calculate_budget(rec, rec["offset"], ind1, ind2, frac, tres, fields, cases.RHS_TERMS, "lhs", direction, names)
+        np.testing.assert_array_equal(bfirst, first)
+        np.testing.assert_array_equal(blast, last)
+        np.testing.assert_array_equal(conc, wconc)
+        for k in want:
+            np.testing.assert_array_equal(contr[k], want[k], err_msg=f"{tag} {k}")
+
+
+def test_calculate_budget_argument_checks():
+    import seaduck_b200 as sd
+    from seaduck_b200 import lagrangian_budget as lb
+
+    case = cases.case_llc_transport(n=20)
+    od = sd.OceData(case["ds"])
+    pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, save_raw=True, **case["kw"])
+    pt.note_taking(stamp=15)
+    pt.to_next_stop(5 * cases.DAY)
+    fields = cases.budget_fields(np.asarray(case["ds"]["maskC"]).shape, seed=1)
+    with pytest.raises(KeyError):
+        lb.calculate_budget(pt, fields, ["nope"])
+    with pytest.raises(ValueError):
+        lb.calculate_budget(pt, fields, [])
+    with pytest.raises(ValueError):
+        lb.calculate_budget(pt, fields, ["adv"], dir_of_time=0)
+    with pytest.raises(RuntimeError):  # sxprime / syprime / szprime differ in shape: same_size=True cannot stack them
+        lb.calculate_budget(pt, fields, ["adv"])
+    bad = dict(fields, adv=fields["adv"][:-1])
+    with pytest.raises(ValueError):
+        lb.calculate_budget(pt, bad, ["adv"], dict(same_size=False))
