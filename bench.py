@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=100_000, help="particles of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-sweep", default="", help="tuning aid: chunks:blocks_per_sm,... for sdk_track_host")
     ap.add_argument("--refill", type=int, default=0)
     ap.add_argument("--blocks-per-sm", type=int, default=0)
     ap.add_argument("--threads", type=int, default=0)
@@ -367,18 +368,32 @@ def run_cuda(a):
         par = batches[0]._params(200)
         par.stats = None
         in_bytes, out_bytes = 4 * 8 * n, 3 * 8 * n + 6 * 4 * n
-        e2e_cross, e2e_t = 0, 0.0
-        for i in range(2 + a.steps):
-            if world > 1:
-                dist.barrier()
-            torch.cuda.synchronize()
-            t0 = time.perf_counter()
-            _lib.check(L.sdk_track_host(handle, C.byref(batches[0]._vel), C.byref(io), None, 0, float(t_stop), C.byref(par),
-                                        scratch.data_ptr(), _lib.current_stream()), "sdk_track_host")
-            dt = time.perf_counter() - t0
-            if i >= 2:
-                e2e_t += dt
-                e2e_cross += int(hout_i[4].sum().item())
+
+        def run_e2e(steps):
+            cross, secs = 0, 0.0
+            for i in range(2 + steps):
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                _lib.check(L.sdk_track_host(handle, C.byref(batches[0]._vel), C.byref(io), None, 0, float(t_stop), C.byref(par),
+                                            scratch.data_ptr(), _lib.current_stream()), "sdk_track_host")
+                dt = time.perf_counter() - t0
+                if i >= 2:
+                    secs += dt
+                    cross += int(hout_i[4].sum().item())
+            return cross, secs
+
+        if a.e2e_sweep:  # tuning aid: "chunks:blocks_per_sm,..." -> one line per setting on stderr
+            for item in a.e2e_sweep.split(","):
+                chunks, bps = (int(v) for v in item.split(":"))
+                os.environ["SDK_TRACK_CHUNKS"] = str(chunks)
+                par.blocks_per_sm = bps
+                cross, secs = run_e2e(a.steps)
+                print(f"e2e sweep chunks={chunks} blocks_per_sm={bps}: {cross / secs:.4e} crossings/s, {secs / a.steps * 1e3:.3f} ms/step", file=sys.stderr)
+            os.environ.pop("SDK_TRACK_CHUNKS", None)
+            par.blocks_per_sm = a.blocks_per_sm
+        e2e_cross, e2e_t = run_e2e(a.steps)
         e2e = (e2e_cross, e2e_t, in_bytes, out_bytes)
 
     # ---- aggregate over ranks ------------------------------------------------------------------------------

@@ -27,6 +27,17 @@ namespace sdk {
 #ifndef SDK_ADVECT_COLD_SMEM
 #define SDK_ADVECT_COLD_SMEM 0
 #endif
+// Skip the wall-time logarithm of an axis that provably cannot give the first event (axis_is_late,
+// sdk_device.cuh): 0 never, 1 test z, 2 test y and z, 3 test x, y and z.  Parity stays green, but the
+// tests cost more than the skipped logarithms save (1.93 / 2.00 / 2.00 ms against 1.61 ms per launch,
+// profiles/README.md r01k): lanes of a warp rarely agree on skipping and the extra code pushes the loop
+// further past the instruction cache -- off.
+#ifndef SDK_ADVECT_DEFER_STORE
+#define SDK_ADVECT_DEFER_STORE 1
+#endif
+#ifndef SDK_ADVECT_PRUNE
+#define SDK_ADVECT_PRUNE 0
+#endif
 constexpr int kColdDoubles = 12;  // px[4], py[4], bzl, dzl, vol, pid
 [[maybe_unused]] constexpr int kColdInts = 7;  // dx, dy (float bits), it, status, niter, ncross, nrec
 
@@ -351,15 +362,28 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
     }
 #else
     {
-        const AxisTimes tx = axis_wall_times(s.u, s.du, s.rx, sg);
-        const AxisTimes ty = axis_wall_times(s.v, s.dv, s.ry, sg);
-        ts[0] = tx.x, ts[1] = tx.y, ts[2] = ty.x, ts[3] = ty.y;
-        if (has_dep) {
+        // An axis whose wall is provably reached later than an event already found keeps "never" (-sign(tf)),
+        // which the argmin below treats like any later time: its logarithm is not evaluated (axis_is_late).
+        double cap = tf * sg;  // directed time of the earliest event so far; the stop itself to begin with
+        auto earliest = [&](const AxisTimes &t) {
+            const double a = t.x * sg, b = t.y * sg;
+            if (a >= 0) cap = fmin(cap, a);
+            if (b >= 0) cap = fmin(cap, b);
+        };
+        ts[0] = ts[1] = ts[2] = ts[3] = ts[4] = ts[5] = -sg;
+        if (SDK_ADVECT_PRUNE < 3 || !axis_is_late(s.u, s.du, s.rx, sg, cap)) {
+            const AxisTimes tx = axis_wall_times(s.u, s.du, s.rx, sg);
+            ts[0] = tx.x, ts[1] = tx.y;
+            earliest(tx);
+        }
+        if (SDK_ADVECT_PRUNE < 2 || !axis_is_late(s.v, s.dv, s.ry, sg, cap)) {
+            const AxisTimes ty = axis_wall_times(s.v, s.dv, s.ry, sg);
+            ts[2] = ty.x, ts[3] = ty.y;
+            earliest(ty);
+        }
+        if (has_dep && (SDK_ADVECT_PRUNE < 1 || !axis_is_late(s.w, s.dw, z0, sg, cap))) {
             const AxisTimes tz = axis_wall_times(s.w, s.dw, z0, sg);
             ts[4] = tz.x, ts[5] = tz.y;
-        } else {
-            ts[4] = -sg;
-            ts[5] = -sg;
         }
     }
 #endif
@@ -522,6 +546,54 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
 #if SDK_ADVECT_LOCKSTEP
     unsigned iter = 0;
 #endif
+#if SDK_ADVECT_DEFER_STORE && !SDK_ADVECT_LOCKSTEP
+    // A lane that has finished its particle keeps it until the warp next goes to the queue: write-back and
+    // refill then run once for all those lanes together instead of once per finishing lane (on the bench
+    // workload: 93 k passes with 10.8 lanes instead of 278 k passes with 3.6), and that code stays out of the
+    // instruction cache in between.
+    for (;;) {
+        const bool working = have && live && s.niter < a.max_iteration;
+        const unsigned idle = __ballot_sync(full, !working);
+        const unsigned pending = __ballot_sync(full, have && !working);
+        if (idle == full || (__popc(idle) >= a.refill_threshold && (pending != 0 || !queue_empty))) {
+            if (have && !working) {
+                // done (or out of iterations): write back and free the lane
+                if (live) s.status |= SDK_ST_MAX_ITER;
+                if (a.commit) store_lane(a.p, a.has_dep, s);
+                if (a.p.status) a.p.status[s.pid] = s.status;
+                if (a.p.niter) a.p.niter[s.pid] = s.niter;
+                if (a.p.ncross) a.p.ncross[s.pid] = s.ncross;
+                if (LOG && a.log.count) a.log.count[s.pid] = s.nrec;
+                acc_cross += s.ncross;
+                acc_max += live;
+                acc_flag += s.status != 0;
+                have = false;
+                live = false;
+            }
+            if (!queue_empty) {
+                const int cnt = __popc(idle);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.queue, (unsigned long long)cnt);
+                base = __shfl_sync(full, base, 0);
+                if ((int64_t)base + cnt >= n) queue_empty = true;
+                if (!have) {
+                    const int64_t pid = (int64_t)base + __popc(idle & ((1u << lane) - 1));
+                    if (pid < n) {
+                        load_lane(a.p, pid, a.has_dep, s);
+                        have = true;
+                        if (LOG && a.log.emit_start) note(a, s, 15);
+                        live = fabs(a.t_stop - s.t) > a.tol;
+                        if (a.p.active && !a.p.active[pid]) live = false;
+                        if (LOG && live && (a.log.continue_mode & 2)) note(a, s, 7);
+                        acc_live += live;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(full, have)) break;
+        if (have && live && s.niter < a.max_iteration) step<T, LOG>(a, sZl, sdZl, s, live);
+    }
+#else
     for (;;) {
         // ---- refill idle lanes from the global queue (warp-aggregated)
         const unsigned idle = __ballot_sync(full, !have);
@@ -569,6 +641,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
             }
         }
     }
+#endif
     if (a.stats) {
         acc_live = __reduce_add_sync(full, acc_live);
         acc_cross = __reduce_add_sync(full, acc_cross);

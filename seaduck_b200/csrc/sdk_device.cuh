@@ -316,6 +316,35 @@ static __device__ __noinline__ AxisTimes axis_wall_times(double u, double du, do
     return make_double2(tl, tr);
 }
 
+// True when none of this axis' walls can be the first event: both are closed, or the time the reference
+// would compute for the one reachable wall is certainly later than `tcap` (a directed time that some
+// other candidate already achieves), so the logarithm behind it never needs to be evaluated.
+//
+// Rigorous bound: between the particle and the wall the speed never exceeds umax = max(|u|, |u_wall|)
+// (it varies linearly), so the exact travel time is at least d / umax.  The reference's value is
+// log(fl(1 + fl(fl(du / u) d))) / du; the roundings inside the logarithm shift its argument u_wall / u by at
+// most 1.1e-16 (1 + 2 |du d| / |u_wall| + |du| / |u_wall|) relatively, i.e. the time by less than
+// (5e-16 (|u| + |u_wall|) + 2e-16 |du|) / (|u_wall| |du|); what the logarithm and the division add is
+// relative (< 1e-15) and sits in the 1e-9 margin.  The reciprocal is a float rounded up: it only has to be an
+// upper bound.  In the linear branch (|du| < 1e-12) the reference divides d by u: no absolute term.
+__device__ __forceinline__ bool axis_is_late(double u, double du, double x0, double sg, double tcap) {
+    const double ul = u - (x0 + 0.5) * du;
+    const double ur = u + (0.5 - x0) * du;
+    const bool open_l = !(-ul * sg <= 1e-12);
+    const bool open_r = !(ur * sg <= 1e-12);
+    if (open_l && open_r) return false;  // diverging flow: two candidate walls, leave it to the exact code
+    if (!(open_l || open_r)) return true;
+    const double uw = open_l ? ul : ur;
+    if (!(u * uw > 0)) return false;  // a stagnation point on the way (logarithm of a negative number)
+    const double d = fabs(open_l ? -0.5 - x0 : 0.5 - x0);
+    const double au = fabs(u), aw = fabs(uw), adu = fabs(du);
+    const bool lin = adu < 1e-12;
+    const double umax = lin ? au : fmax(au, aw);
+    const double rc = (double)__frcp_ru((float)(aw * adu)) * 1.001;  // inf when the product underflows: never "late"
+    const double slack = lin ? 0.0 : (5e-16 * (au + aw) + 2e-16 * adu) * umax * rc;
+    return d - slack > tcap * umax * (1 + 1e-9);
+}
+
 // The same for the usual case only (exactly one reachable wall), to be inlined three times so that
 // ptxas can interleave the axes; `redo` asks for axis_wall_times.
 __device__ __forceinline__ void wall_times_fast_inline(double u, double du, double x0, double sg, double &tl, double &tr,
