@@ -90,6 +90,16 @@ __host__ __device__ inline size_t advect_smem_bytes(int n_zl, int n_z, int threa
     return b;
 }
 
+// What is known about a launch at compile time.  Profile 0 reads every switch from the arguments.  Profile 1
+// is the production case of the north star -- LLC faces, particles with a depth, vertical velocity, volume
+// transports, level-dependent volumes -- with those switches folded: fewer instructions per step and, what
+// matters more for a loop that overflows the instruction cache, less code in the loop body.
+#ifndef SDK_ADVECT_PROFILES
+#define SDK_ADVECT_PROFILES 1
+#endif
+#define SDK_KNOWN(P, fixed_value, runtime_expr) ((P) == 1 ? (fixed_value) : (runtime_expr))
+
+template <int P = 0>
 __device__ __forceinline__ void load_lane(const sdk_particles &p, int64_t i, int has_dep, Lane &s) {
     s.pid = i;
     s.lon = p.lon[i];
@@ -106,14 +116,15 @@ __device__ __forceinline__ void load_lane(const sdk_particles &p, int64_t i, int
         s.px[j] = p.px[j * p.n + i];
         s.py[j] = p.py[j * p.n + i];
     }
-    s.f = p.face ? p.face[i] : 0;
+    s.f = SDK_KNOWN(P, true, p.face != nullptr) ? p.face[i] : 0;
     s.iy = p.iy[i];
     s.ix = p.ix[i];
     s.it = p.it ? p.it[i] : 0;
-    s.dx = p.dx ? p.dx[i] : 1.0f;
-    s.dy = p.dy ? p.dy[i] : 1.0f;
-    s.vol = p.vol ? p.vol[i] : 1.0;
-    if (has_dep) {
+    // (with transports everything is scaled by the cell volume, dx and dy are never read)
+    s.dx = SDK_KNOWN(P, false, p.dx != nullptr) ? p.dx[i] : 1.0f;
+    s.dy = SDK_KNOWN(P, false, p.dy != nullptr) ? p.dy[i] : 1.0f;
+    s.vol = SDK_KNOWN(P, true, p.vol != nullptr) ? p.vol[i] : 1.0;
+    if (SDK_KNOWN(P, true, has_dep != 0)) {
         s.dep = p.dep[i];
         s.rzl = p.rzl[i];
         s.w = p.w[i];
@@ -136,6 +147,7 @@ __device__ __forceinline__ void load_lane(const sdk_particles &p, int64_t i, int
     s.nrec = 0;
 }
 
+template <int P = 0>
 __device__ __forceinline__ void store_lane(const sdk_particles &p, int has_dep, const Lane &s) {
     const long long i = s.pid;
     p.lon[i] = s.lon;
@@ -152,11 +164,11 @@ __device__ __forceinline__ void store_lane(const sdk_particles &p, int has_dep, 
         p.px[j * p.n + i] = s.px[j];
         p.py[j * p.n + i] = s.py[j];
     }
-    if (p.face) p.face[i] = s.f;
+    if (SDK_KNOWN(P, true, p.face != nullptr)) p.face[i] = s.f;
     p.iy[i] = s.iy;
     p.ix[i] = s.ix;
-    if (p.vol) p.vol[i] = s.vol;
-    if (has_dep) {
+    if (SDK_KNOWN(P, true, p.vol != nullptr)) p.vol[i] = s.vol;
+    if (SDK_KNOWN(P, true, has_dep != 0)) {
         p.dep[i] = s.dep;
         p.rzl[i] = s.rzl;
         p.w[i] = s.w;
@@ -206,13 +218,18 @@ __device__ __forceinline__ void trim_axis(double &x, double &u, double du, doubl
 // kernels of lagrangian.py:25-53; on LLC grids the right / top wall may live on the neighbouring
 // face and be the other velocity component, reference eulerian.py:887 + topology.py:618-647).
 // Index arithmetic: 32-bit within a horizontal plane, one 64-bit multiply-add for the level/time.
-template <typename T>
+template <typename T, int P = 0>
 __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v, int has_dep, Lane &s) {
+    const bool k_face = SDK_KNOWN(P, true, g.has_face != 0);
+    const bool k_w = SDK_KNOWN(P, true, v.has_w != 0);
+    const bool k_tr = SDK_KNOWN(P, true, v.transport != 0);
+    const bool k_z = SDK_KNOWN(P, true, v.has_z != 0);
+    const bool k_volz = SDK_KNOWN(P, true, v.vol_has_z != 0);
     // ---- where do the right and top wall values live?
     int rf = s.f, ry_ = s.iy, rx_ = s.ix, r_in;
     int tf = s.f, ty_ = s.iy, tx_ = s.ix, t_in;
     bool r_is_v = false, t_is_u = false;
-    if (g.has_face) {
+    if (k_face) {
         int st = cell_move(g, 3, rf, ry_, rx_, r_in);
         if (st) {
             s.status |= SDK_ST_BAD_CELL;
@@ -248,7 +265,7 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
         s.status |= SDK_ST_OOB_T;
         tlev = tlev < 0 ? 0 : v.nt - 1;
     }
-    const int64_t lev_uv = v.has_z ? (int64_t)(tlev * v.nzU + wrap_index(s.izl - 1, v.nzU)) : (int64_t)tlev;
+    const int64_t lev_uv = k_z ? (int64_t)(tlev * v.nzU + wrap_index(s.izl - 1, v.nzU)) : (int64_t)tlev;
     const int c_ul = (s.f * v.nyU + s.iy) * v.nxU + s.ix;
     const int c_vl = (s.f * v.nyV + s.iy) * v.nxV + s.ix;
     const int c_ur = r_is_v ? (rf * v.nyV + ry_) * v.nxV + rx_ : (rf * v.nyU + ry_) * v.nxU + rx_;
@@ -260,18 +277,18 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
     const double vr = ldf<T>(t_is_u ? v.U : v.V, lev_uv * (t_is_u ? v.planeU : v.planeV) + c_vr);
     const int cell = (s.f * g.ny + s.iy) * g.nx + s.ix;
     double w0 = 0.0, w1 = 0.0;
-    if (v.has_w) {
+    if (k_w) {
         const int64_t wl = (int64_t)tlev * v.nzW;
         w0 = ldf<T>(v.W, (wl + wrap_index(s.izl, v.nzW)) * v.planeC + cell);
         w1 = ldf<T>(v.W, (wl + wrap_index(s.izl - 1, v.nzW)) * v.planeC + cell);
     }
-    if (v.transport) {
-        const int64_t idx = (v.vol_has_z ? (int64_t)wrap_index(s.izl - 1, g.n_z > 0 ? g.n_z : 1) : 0) * v.planeC + cell;
+    if (k_tr) {
+        const int64_t idx = (k_volz ? (int64_t)wrap_index(s.izl - 1, g.n_z > 0 ? g.n_z : 1) : 0) * v.planeC + cell;
         s.vol = v.vol_dtype == SDK_F64 ? ldf<double>(v.Vol, idx) : ldf<float>(v.Vol, idx);
     }
     double ul_ = ul, ur_ = ur, vl_ = vl, vr_ = vr;
     nan_to_num4(ul_, ur_, vl_, vr_);
-    const bool stag_x = g.has_face || v.u_stag, stag_y = g.has_face || v.v_stag;
+    const bool stag_x = k_face || v.u_stag, stag_y = k_face || v.v_stag;
     const double rxs = stag_x ? s.rx + 0.5 : s.rx;
     const double rys = stag_y ? s.ry + 0.5 : s.ry;
     // Lagrange weights of the two-node kernels (reference kernel_weight.py:211-229)
@@ -282,11 +299,11 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
     double du = ul_ * -1.0 + ur_;
     double vv = vl_ * wy0 + vr_ * wy1;
     double dv = vl_ * -1.0 + vr_;
-    const double sx = v.transport ? s.vol : (double)s.dx;
-    const double sy = v.transport ? s.vol : (double)s.dy;
-    const double sz = v.transport ? s.vol : s.dzl;
+    const double sx = k_tr ? s.vol : (double)s.dx;
+    const double sy = k_tr ? s.vol : (double)s.dy;
+    const double sz = k_tr ? s.vol : s.dzl;
     double w = 0.0, dw = 0.0;
-    if (v.has_w) {
+    if (k_w) {
         const double w0_ = nan_to_num(w0), w1_ = nan_to_num(w1);
         w = w0_ * (1 - s.rzl) + w1_ * s.rzl;
         dw = w0_ * -1.0 + w1_;
@@ -295,36 +312,36 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
     // refined reciprocal is shared, each quotient costs three more operations (fastmath.cuh)
     bool redo = false;
     const double yx = rcp_refined(sx);
-    const double yy = v.transport ? yx : rcp_refined(sy);
-    const double yz = v.transport ? yx : rcp_refined(sz);
+    const double yy = k_tr ? yx : rcp_refined(sy);
+    const double yz = k_tr ? yx : rcp_refined(sz);
     double qu = div_with(u, sx, yx, redo), qdu = div_with(du, sx, yx, redo);
     double qv = div_with(vv, sy, yy, redo), qdv = div_with(dv, sy, yy, redo);
     double qw = 0.0, qdw = 0.0;
-    if (v.has_w) {
+    if (k_w) {
         qw = div_with(w, sz, yz, redo);
         qdw = div_with(dw, sz, yz, redo);
     }
     if (redo) {  // zero / denormal / non-finite scale: plain operators
         qu = u / sx, qdu = du / sx, qv = vv / sy, qdv = dv / sy;
-        if (v.has_w) qw = w / sz, qdw = dw / sz;
+        if (k_w) qw = w / sz, qdw = dw / sz;
     }
     nan_to_num4(qu, qv, qdu, qdv);
     s.u = qu;
     s.v = qv;
     s.du = qdu;
     s.dv = qdv;
-    if (v.has_w) {
+    if (k_w) {
         s.w = nan_to_num(qw);
         s.dw = nan_to_num(qdw);
     }
 }
 
 // One iteration of the reference loop (lagrangian.py:766-791) for one particle.
-template <typename T, bool LOG>
+template <typename T, bool LOG, int P>
 __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, const float *sdZl, Lane &s,
                                      bool &live) {
     const GridDev &g = a.g;
-    const int has_dep = a.has_dep;
+    const int has_dep = SDK_KNOWN(P, 1, a.has_dep);
     // trim, lagrangian.py:400
     const double lo = -0.5 + a.trim_tol, hi = 0.5 - a.trim_tol;
     trim_axis(s.rx, s.u, s.du, lo, hi);
@@ -490,7 +507,7 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
         }
     }
     // get_vol + get_u_du
-    read_velocity<T>(g, a.v, has_dep, s);
+    read_velocity<T, P>(g, a.v, has_dep, s);
     s.niter += 1;
     live = fabs(a.t_stop - s.t) > a.tol;
     if (LOG && live && !(a.log.continue_mode & 1)) note(a, s, 7);
@@ -522,7 +539,7 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
 #define SDK_ADVECT_INLINE_AXES 0
 #endif
 
-template <typename T, bool LOG>
+template <typename T, bool LOG, int P>
 __global__ void __launch_bounds__(SDK_ADVECT_THREADS, SDK_ADVECT_MIN_BLOCKS)
 advect_kernel(const __grid_constant__ AdvectArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -559,7 +576,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
             if (have && !working) {
                 // done (or out of iterations): write back and free the lane
                 if (live) s.status |= SDK_ST_MAX_ITER;
-                if (a.commit) store_lane(a.p, a.has_dep, s);
+                if (a.commit) store_lane<P>(a.p, a.has_dep, s);
                 if (a.p.status) a.p.status[s.pid] = s.status;
                 if (a.p.niter) a.p.niter[s.pid] = s.niter;
                 if (a.p.ncross) a.p.ncross[s.pid] = s.ncross;
@@ -579,7 +596,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
                 if (!have) {
                     const int64_t pid = (int64_t)base + __popc(idle & ((1u << lane) - 1));
                     if (pid < n) {
-                        load_lane(a.p, pid, a.has_dep, s);
+                        load_lane<P>(a.p, pid, a.has_dep, s);
                         have = true;
                         if (LOG && a.log.emit_start) note(a, s, 15);
                         live = fabs(a.t_stop - s.t) > a.tol;
@@ -591,7 +608,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
             }
         }
         if (!__any_sync(full, have)) break;
-        if (have && live && s.niter < a.max_iteration) step<T, LOG>(a, sZl, sdZl, s, live);
+        if (have && live && s.niter < a.max_iteration) step<T, LOG, P>(a, sZl, sdZl, s, live);
     }
 #else
     for (;;) {
@@ -606,7 +623,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
             if (!have) {
                 const int64_t pid = (int64_t)base + __popc(idle & ((1u << lane) - 1));
                 if (pid < n) {
-                    load_lane(a.p, pid, a.has_dep, s);
+                    load_lane<P>(a.p, pid, a.has_dep, s);
                     have = true;
                     if (LOG && a.log.emit_start) note(a, s, 15);
                     live = fabs(a.t_stop - s.t) > a.tol;
@@ -625,11 +642,11 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
 #endif
         if (have) {
             if (live && s.niter < a.max_iteration) {
-                step<T, LOG>(a, sZl, sdZl, s, live);
+                step<T, LOG, P>(a, sZl, sdZl, s, live);
             } else {
                 // done (or out of iterations): write back and free the lane
                 if (live) s.status |= SDK_ST_MAX_ITER;
-                if (a.commit) store_lane(a.p, a.has_dep, s);
+                if (a.commit) store_lane<P>(a.p, a.has_dep, s);
                 if (a.p.status) a.p.status[s.pid] = s.status;
                 if (a.p.niter) a.p.niter[s.pid] = s.niter;
                 if (a.p.ncross) a.p.ncross[s.pid] = s.ncross;
@@ -696,22 +713,22 @@ int advect_default_blocks_per_sm() { return SDK_ADVECT_MIN_BLOCKS * SDK_ADVECT_T
 cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaStream_t stream) {
     const size_t smem = advect_smem_bytes(args.g.n_zl, args.g.n_z, threads);
     const bool f32 = args.v.dtype == SDK_F32;
-    static bool attr_done = false;
-    if (!attr_done) {  // CTAs of more than ~384 threads need more than the default 48 KB of dynamic shared memory
-        const int cap = 200 * 1024;
-        cudaFuncSetAttribute(advect_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-        cudaFuncSetAttribute(advect_kernel<double, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-        cudaFuncSetAttribute(advect_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-        cudaFuncSetAttribute(advect_kernel<double, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
-        attr_done = true;
-    }
+    // profile 1: what the folded switches of the specialised kernel assume
+    const bool p1 = SDK_ADVECT_PROFILES && args.g.has_face && args.g.typ == SDK_TYP_LLC && args.has_dep && args.v.has_w &&
+                    args.v.transport && args.v.has_z && args.v.vol_has_z && args.p.face && args.p.vol;
+    void (*kern)(AdvectArgs);
     if (args.has_log) {
-        if (f32) advect_kernel<float, true><<<blocks, threads, smem, stream>>>(args);
-        else advect_kernel<double, true><<<blocks, threads, smem, stream>>>(args);
+        if (f32) kern = p1 ? advect_kernel<float, true, 1> : advect_kernel<float, true, 0>;
+        else kern = p1 ? advect_kernel<double, true, 1> : advect_kernel<double, true, 0>;
     } else {
-        if (f32) advect_kernel<float, false><<<blocks, threads, smem, stream>>>(args);
-        else advect_kernel<double, false><<<blocks, threads, smem, stream>>>(args);
+        if (f32) kern = p1 ? advect_kernel<float, false, 1> : advect_kernel<float, false, 0>;
+        else kern = p1 ? advect_kernel<double, false, 1> : advect_kernel<double, false, 0>;
     }
+    if (smem > 48 * 1024) {  // CTAs of more than ~384 threads need more than the default 48 KB of dynamic shared memory
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<blocks, threads, smem, stream>>>(args);
     return cudaGetLastError();
 }
 
