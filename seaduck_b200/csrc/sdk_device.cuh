@@ -302,14 +302,23 @@ static __device__ __noinline__ AxisTimes axis_wall_times(double u, double du, do
     const double den = lin ? u : du;
     // left wall if it is open, else the right one
     const double d1 = open_l ? dl : dr;
-    const double lg1 = flog(lin ? 1.0 : 1 + k * d1, bl);
-    const double t1 = div_with(lin ? d1 : lg1, den, inv, bt);
+    // A stagnation point between the particle and an open wall (diverging flow, the particle on the other
+    // side) makes 1 + k d <= 0: the reference takes the logarithm anyway and gets NaN (-inf for 0), which
+    // its argmin reads as "never".  Return the NaN without evaluating anything.
+    const double arg1 = lin ? 1.0 : 1 + k * d1;
+    const bool never1 = arg1 <= 0.0;
+    const double lg1 = flog(never1 ? 1.0 : arg1, bl);
+    double t1 = div_with(lin ? d1 : lg1, den, inv, bt);
+    t1 = never1 ? __longlong_as_double(0x7ff8000000000000LL) : t1;
     tl = open_l ? t1 : -sg;
     tr = (open_r && !open_l) ? t1 : -sg;
     bool redo = (open_l || open_r) && (bt || (!lin && (bk || bl)));
     if (open_l && open_r) {  // diverging flow inside the cell: the right wall needs its own logarithm
-        const double lg2 = flog(lin ? 1.0 : 1 + k * dr, bl);
+        const double arg2 = lin ? 1.0 : 1 + k * dr;
+        const bool never2 = arg2 <= 0.0;
+        const double lg2 = flog(never2 ? 1.0 : arg2, bl);
         tr = div_with(lin ? dr : lg2, den, inv, bt);
+        tr = never2 ? __longlong_as_double(0x7ff8000000000000LL) : tr;
         redo = bt || (!lin && (bk || bl));
     }
     if (redo) wall_times(u, du, x0, sg, tl, tr);
