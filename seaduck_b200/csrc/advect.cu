@@ -286,8 +286,8 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
         const int64_t idx = (k_volz ? (int64_t)wrap_index(s.izl - 1, g.n_z > 0 ? g.n_z : 1) : 0) * v.planeC + cell;
         s.vol = v.vol_dtype == SDK_F64 ? ldf<double>(v.Vol, idx) : ldf<float>(v.Vol, idx);
     }
-    double ul_ = ul, ur_ = ur, vl_ = vl, vr_ = vr;
-    nan_to_num4(ul_, ur_, vl_, vr_);
+    double ul_ = ul, ur_ = ur, vl_ = vl, vr_ = vr, w0_ = w0, w1_ = w1;
+    nan_to_num6(ul_, ur_, vl_, vr_, w0_, w1_);
     const bool stag_x = k_face || v.u_stag, stag_y = k_face || v.v_stag;
     const double rxs = stag_x ? s.rx + 0.5 : s.rx;
     const double rys = stag_y ? s.ry + 0.5 : s.ry;
@@ -304,7 +304,6 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
     const double sz = k_tr ? s.vol : s.dzl;
     double w = 0.0, dw = 0.0;
     if (k_w) {
-        const double w0_ = nan_to_num(w0), w1_ = nan_to_num(w1);
         w = w0_ * (1 - s.rzl) + w1_ * s.rzl;
         dw = w0_ * -1.0 + w1_;
     }
@@ -321,18 +320,18 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
         qw = div_with(w, sz, yz, redo);
         qdw = div_with(dw, sz, yz, redo);
     }
-    if (redo) {  // zero / denormal / non-finite scale: plain operators
-        qu = u / sx, qdu = du / sx, qv = vv / sy, qdv = dv / sy;
-        if (k_w) qw = w / sz, qdw = dw / sz;
+    if (redo) {  // zero / denormal / non-finite scale: plain operators (out of line)
+        qu = div_cold(u, sx), qdu = div_cold(du, sx), qv = div_cold(vv, sy), qdv = div_cold(dv, sy);
+        if (k_w) qw = div_cold(w, sz), qdw = div_cold(dw, sz);
     }
-    nan_to_num4(qu, qv, qdu, qdv);
+    nan_to_num6(qu, qv, qdu, qdv, qw, qdw);
     s.u = qu;
     s.v = qv;
     s.du = qdu;
     s.dv = qdv;
     if (k_w) {
-        s.w = nan_to_num(qw);
-        s.dw = nan_to_num(qdw);
+        s.w = qw;
+        s.dw = qdw;
     }
 }
 
@@ -496,7 +495,7 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
         }
         if (redo) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) s.px[j] = s.lon + to_180((double)gx[j] - s.lon);
+            for (int j = 0; j < 4; ++j) s.px[j] = s.lon + to_180_cold((double)gx[j] - s.lon);
         }
         redo = false;
         const double qx[4] = {s.px[0], s.px[1], s.px[2], s.px[3]}, qy[4] = {s.py[0], s.py[1], s.py[2], s.py[3]};

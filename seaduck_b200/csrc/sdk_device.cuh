@@ -66,16 +66,27 @@ __device__ __forceinline__ double to_180(double x) {
 //   (360 - 360); the last line adds -360 in the upper half and -0.0 otherwise.
 __device__ __forceinline__ double to_180_fast(double x, bool &bad) {
     const double ax = fabs(x);
-    bad = bad || !(ax < 720.0);
+    bad |= !(ax < 720.0);
     x = x - copysign(ax >= 360.0 ? 360.0 : 0.0, x);
     const double m = x + (x < 0.0 ? 360.0 : 0.0);
     return m + (m >= 180.0 ? -360.0 : -0.0);
 }
 
-// numpy.nan_to_num: nan -> 0, +-inf -> +-DBL_MAX.  One integer test on the exponent in the common
-// (finite) case.
+// numpy.nan_to_num: nan -> 0, +-inf -> +-DBL_MAX.  Fields and quotients are finite almost always: the
+// callers test a whole group of values with integer operations on the exponents and only then come here
+// (out of line, so that the step's hot path stays one contiguous run of code).
+static __device__ __noinline__ double nan_to_num_cold(double x) {
+    if (x != x) return 0.0;
+    if (x == INFINITY) return DBL_MAX;
+    if (x == -INFINITY) return -DBL_MAX;
+    return x;
+}
+
+__device__ __forceinline__ bool not_finite(double x) { return (__double2hiint(x) & 0x7ff00000) == 0x7ff00000; }
+
+// inline form for kernels where NaN is ordinary data (land points of a field)
 __device__ __forceinline__ double nan_to_num(double x) {
-    if ((__double2hiint(x) & 0x7ff00000) == 0x7ff00000) {
+    if (not_finite(x)) {
         if (x != x) return 0.0;
         return x > 0 ? DBL_MAX : -DBL_MAX;
     }
@@ -92,16 +103,24 @@ __device__ __forceinline__ double div_maybe_zero(double a, double b) {
     return z ? a * q : q;
 }
 
-// nan_to_num of four values at once: one test in the (finite) common case
+// nan_to_num of four / six values at once: one test in the (finite) common case
 __device__ __forceinline__ void nan_to_num4(double &a, double &b, double &c, double &d) {
-    const int e = 0x7ff00000;
-    const bool fin = ((__double2hiint(a) & e) != e) && ((__double2hiint(b) & e) != e) && ((__double2hiint(c) & e) != e) &&
-                     ((__double2hiint(d) & e) != e);
-    if (!fin) {
-        a = nan_to_num(a);
-        b = nan_to_num(b);
-        c = nan_to_num(c);
-        d = nan_to_num(d);
+    if (not_finite(a) | not_finite(b) | not_finite(c) | not_finite(d)) {
+        a = nan_to_num_cold(a);
+        b = nan_to_num_cold(b);
+        c = nan_to_num_cold(c);
+        d = nan_to_num_cold(d);
+    }
+}
+
+__device__ __forceinline__ void nan_to_num6(double &a, double &b, double &c, double &d, double &e, double &f) {
+    if (not_finite(a) | not_finite(b) | not_finite(c) | not_finite(d) | not_finite(e) | not_finite(f)) {
+        a = nan_to_num_cold(a);
+        b = nan_to_num_cold(b);
+        c = nan_to_num_cold(c);
+        d = nan_to_num_cold(d);
+        e = nan_to_num_cold(e);
+        f = nan_to_num_cold(f);
     }
 }
 
@@ -117,39 +136,56 @@ __device__ __forceinline__ double ldf(const void *base, int64_t idx) {
 // One C-grid step across cell walls (reference _llc_ind_tend topology.py:149, _box_ind_tend :100,
 // _x_per_ind_tend :124).  dir: 0 up, 1 down, 2 left, 3 right.  Returns SDK_ST_* bits (0 = fine)
 // and, when a face edge was crossed, the edge of the new face we came in through (else -1).
+// the step off the face / off the array (rare): out of line; (face, iy, ix, came_in + 1 | status << 8)
+static __device__ __noinline__ int4 cell_move_off_face(const GridDev &g, int dir, int f, int iy, int ix) {
+    const int iymax = g.ny - 1, ixmax = g.nx - 1;
+    const int ny_ = iy + (dir == 0) - (dir == 1);
+    const int nx_ = ix + (dir == 3) - (dir == 2);
+    int came_in = -1, st = 0;
+    if (g.typ == SDK_TYP_LLC) {
+        const int nf = g.nbr_face[f * 4 + dir];
+        if (nf < 0) {
+            st = SDK_ST_EDGE;  // reference keeps the old index and warns
+        } else {
+            const int ne = g.nbr_edge[f * 4 + dir];
+            const int s = dir >= 2 ? iy : ix;  // coordinate along the crossed edge
+            const bool flip = ((dir & 1) == 0) == ((ne & 1) == 0);
+            const bool dest_x = ne <= 1;
+            const int s_new = flip ? (dest_x ? ixmax : iymax) - s : s;
+            f = nf;
+            iy = ne == 0 ? iymax : (ne == 1 ? 0 : s_new);
+            ix = ne == 2 ? 0 : (ne == 3 ? ixmax : s_new);
+            came_in = ne;
+        }
+    } else if (ny_ < 0 || ny_ > iymax) {
+        st = SDK_ST_OUT;
+    } else if (g.typ == SDK_TYP_XPERIODIC) {
+        iy = ny_;
+        ix = nx_ > ixmax ? nx_ - ixmax : ixmax + nx_ + 1;  // sic: reference wraps to 1, not 0
+    } else {
+        st = SDK_ST_OUT;
+    }
+    return make_int4(f, iy, ix, (came_in + 1) | (st << 8));
+}
+
 __device__ __forceinline__ int cell_move(const GridDev &g, int dir, int &f, int &iy, int &ix,
                                          int &came_in) {
     came_in = -1;
-    int ny_ = iy + (dir == 0) - (dir == 1);
-    int nx_ = ix + (dir == 3) - (dir == 2);
-    const int iymax = g.ny - 1, ixmax = g.nx - 1;
-    const bool off = ny_ < 0 || ny_ > iymax || nx_ < 0 || nx_ > ixmax;
+    const int ny_ = iy + (dir == 0) - (dir == 1);
+    const int nx_ = ix + (dir == 3) - (dir == 2);
+    // one unsigned comparison per coordinate: negative values wrap to huge ones
+    const bool off = ((unsigned)ny_ >= (unsigned)g.ny) | ((unsigned)nx_ >= (unsigned)g.nx);
     if (!off) {
         iy = ny_;
         ix = nx_;
         return 0;
     }
-    if (g.typ == SDK_TYP_LLC) {
-        const int nf = g.nbr_face[f * 4 + dir];
-        if (nf < 0) return SDK_ST_EDGE;  // reference keeps the old index and warns
-        const int ne = g.nbr_edge[f * 4 + dir];
-        const int s = dir >= 2 ? iy : ix;                  // coordinate along the crossed edge
-        const bool flip = ((dir & 1) == 0) == ((ne & 1) == 0);
-        const bool dest_x = ne <= 1;
-        const int s_new = flip ? (dest_x ? ixmax : iymax) - s : s;
-        f = nf;
-        iy = ne == 0 ? iymax : (ne == 1 ? 0 : s_new);
-        ix = ne == 2 ? 0 : (ne == 3 ? ixmax : s_new);
-        came_in = ne;
-        return 0;
-    }
-    if (ny_ < 0 || ny_ > iymax) return SDK_ST_OUT;
-    if (g.typ == SDK_TYP_XPERIODIC) {
-        iy = ny_;
-        ix = nx_ > ixmax ? nx_ - ixmax : ixmax + nx_ + 1;  // sic: reference wraps to 1, not 0
-        return 0;
-    }
-    return SDK_ST_OUT;
+    const int4 r = cell_move_off_face(g, dir, f, iy, ix);
+    f = r.x;
+    iy = r.y;
+    ix = r.z;
+    came_in = (r.w & 0xff) - 1;
+    return r.w >> 8;
 }
 
 // Flat XG indices of the four corners LL, LR, UR, UL of cell (f, iy, ix)
@@ -176,6 +212,12 @@ __device__ __forceinline__ int corner_indices(const GridDev &g, int f, int iy, i
     c[3] = d;
     return 0;
 }
+
+// out-of-line copies of plain-operator fallbacks: the hot path only carries the calls
+static __device__ __noinline__ double div_cold(double a, double b) { return a / b; }
+static __device__ __noinline__ double to_180_cold(double x) { return to_180(x); }
+// the root of the quadratic for curved cells (find_rx_ry_oceanparcel utils.py:568)
+static __device__ __noinline__ double curved_root_cold(double bb, double det2, double aa) { return (-bb + sqrt(det2)) / (2 * aa); }
 
 // reference find_rx_ry_oceanparcel, utils.py:532 (plain operators; also the slow path of
 // inverse_bilinear_fast)
@@ -236,16 +278,18 @@ __device__ __forceinline__ void inverse_bilinear_fast(double x, double y, const 
     const double det2 = bb * bb - 4 * aa * cc;
     const bool order1 = fabs(aa) < 1e-12;
     const bool order2 = !order1 && det2 >= 0;
-    bool b1_ = false, b2_ = false;
+    bool b1_ = false, b2_ = false, b3_ = false;
     double r = -fdiv(cc, bb, b1_);
-    if (order2) r = (-bb + sqrt(det2)) / (2 * aa);  // curved cells only (polar cap)
+    if (order2) r = curved_root_cold(bb, det2, aa);  // curved cells only (polar cap)
     const double den = a1 + a3 * r;
-    double q;
-    if (fabs(den) < 1e-12)  // cells whose x axis runs along a meridian (the rotated LLC faces)
-        q = (div_maybe_zero(y - py[0], py[1] - py[0]) + div_maybe_zero(y - py[3], py[2] - py[3])) * 0.5;
-    else
-        q = fdiv(x - a0 - a2 * r, den, b2_);
-    bad = bad || (!order2 && b1_) || b2_;
+    // Cells whose x axis runs along a meridian (the rotated LLC faces) take the mean of two ratios in y
+    // instead.  Both forms go through the same two divisions with the operands selected: no branch, the
+    // second quotient is simply not used by the ordinary form.
+    const bool mer = fabs(den) < 1e-12;
+    const double q1 = fdiv(mer ? y - py[0] : x - a0 - a2 * r, mer ? py[1] - py[0] : den, b2_);
+    const double q2 = fdiv(y - py[3], py[2] - py[3], b3_);
+    const double q = mer ? (q1 + q2) * 0.5 : q1;
+    bad |= (!order2 & b1_) | b2_ | (mer & b3_);
     rx = q - 0.5;
     ry = r - 0.5;
 }
@@ -277,6 +321,13 @@ __device__ __forceinline__ void wall_times(double u, double du, double x0, doubl
     if (open_l) tl = t1;
     else tr = t1;
     if (open_l && open_r) tr = log(1 + k * dr) / du;  // diverging flow inside the cell: rare
+}
+
+// out-of-line copies of the plain-operator fallbacks: the hot path only carries the calls
+static __device__ __noinline__ double2 wall_times_cold(double u, double du, double x0, double sg) {
+    double tl, tr;
+    wall_times(u, du, x0, sg, tl, tr);
+    return make_double2(tl, tr);
 }
 
 // One copy of the per-axis code, called for x, y and z: the particle step has to stay inside the
@@ -321,7 +372,7 @@ static __device__ __noinline__ AxisTimes axis_wall_times(double u, double du, do
         tr = never2 ? __longlong_as_double(0x7ff8000000000000LL) : tr;
         redo = bt || (!lin && (bk || bl));
     }
-    if (redo) wall_times(u, du, x0, sg, tl, tr);
+    if (redo) return wall_times_cold(u, du, x0, sg);
     return make_double2(tl, tr);
 }
 
@@ -384,14 +435,16 @@ __device__ __forceinline__ double increment_fast_inline(double t, double u, doub
     bool bq = false, be = false;
     const double q = fdiv(u, du, bq);
     const double e = fexp(du * t, be);
-    redo = redo || (!lin && (bq || be));
+    redo |= !lin & (bq | be);
     return lin ? u * t : q * (e - 1);
 }
+
+static __device__ __noinline__ double increment_cold(double t, double u, double du) { return increment(t, u, du); }
 
 static __device__ __noinline__ double axis_increment(double t, double u, double du) {
     bool redo = false;
     double r = increment_fast_inline(t, u, du, redo);
-    if (redo) r = increment(t, u, du);
+    if (redo) r = increment_cold(t, u, du);
     return r;
 }
 
