@@ -426,11 +426,11 @@ def run_cuda(a):
                 "step_ms_first10": [round(x, 3) for x in step_ms[:10]], "host_wall_s": wall,
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "advect_kernel<double,false>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "advect_kernel<%s,false>" % ("float" if a.dtype == "f32" else "double"),
                          "kernel_ms": kms, "crossings_per_launch": kcr, "algorithmic_bytes_per_launch": algo_bytes,
-                         "note": "instruction-supply bound, not bandwidth bound (DRAM 3.5 % busy, fields L2 resident, "
-                                 "SM instruction cache hit rate 79 %, GPC instruction cache at 96 % of its request rate): "
-                                 "profiles/README.md r01c-r01g"},
+                         "note": "instruction-supply bound, not bandwidth bound (DRAM 4.5 % busy, fields L2 resident, "
+                                 "SM instruction cache hit rate 88 %, GPC instruction cache at 94 % of its request rate; the "
+                                 "launch time follows the number of GPC instruction-cache requests): profiles/README.md r01k-r01m"},
             "gpu_launches": a.steps * world,
             "clocks": sampler.summary(),
         }

@@ -320,7 +320,7 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
         qw = div_with(w, sz, yz, redo);
         qdw = div_with(dw, sz, yz, redo);
     }
-    if (redo) {  // zero / denormal / non-finite scale: plain operators (out of line)
+    if (SDK_UNLIKELY(redo)) {  // zero / denormal / non-finite scale: plain operators (out of line)
         qu = div_cold(u, sx), qdu = div_cold(du, sx), qv = div_cold(vv, sy), qdv = div_cold(dv, sy);
         if (k_w) qw = div_cold(w, sz), qdw = div_cold(dw, sz);
     }
@@ -493,14 +493,14 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
             s.px[j] = s.lon + to_180_fast((double)gx[j] - s.lon, redo);  // eulerian.py:618
             s.py[j] = (double)gy[j];
         }
-        if (redo) {
+        if (SDK_UNLIKELY(redo)) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) s.px[j] = s.lon + to_180_cold((double)gx[j] - s.lon);
         }
         redo = false;
         const double qx[4] = {s.px[0], s.px[1], s.px[2], s.px[3]}, qy[4] = {s.py[0], s.py[1], s.py[2], s.py[3]};
         inverse_bilinear_fast(s.lon, s.lat, qx, qy, s.rx, s.ry, redo);
-        if (redo) {
+        if (SDK_UNLIKELY(redo)) {
             const double2 r = inverse_bilinear_slow(s.lon, s.lat, s.px[0], s.px[1], s.px[2], s.px[3], s.py[0], s.py[1], s.py[2], s.py[3]);
             s.rx = r.x, s.ry = r.y;
         }
@@ -532,7 +532,7 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
 #define SDK_ADVECT_MIN_BLOCKS 1
 #endif
 #ifndef SDK_ADVECT_DEFAULT_THREADS
-#define SDK_ADVECT_DEFAULT_THREADS (SDK_ADVECT_LOCKSTEP ? 512 : 128)
+#define SDK_ADVECT_DEFAULT_THREADS 128
 #endif
 #ifndef SDK_ADVECT_INLINE_AXES
 #define SDK_ADVECT_INLINE_AXES 0
@@ -562,7 +562,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
 #if SDK_ADVECT_LOCKSTEP
     unsigned iter = 0;
 #endif
-#if SDK_ADVECT_DEFER_STORE && !SDK_ADVECT_LOCKSTEP
+#if SDK_ADVECT_DEFER_STORE
     // A lane that has finished its particle keeps it until the warp next goes to the queue: write-back and
     // refill then run once for all those lanes together instead of once per finishing lane (on the bench
     // workload: 93 k passes with 10.8 lanes instead of 278 k passes with 3.6), and that code stays out of the
@@ -606,7 +606,14 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
                 }
             }
         }
+#if SDK_ADVECT_LOCKSTEP
+        // the warps of a CTA start every SDK_ADVECT_LOCKSTEP-th step together, so that they walk through the
+        // same instruction-cache lines at the same time (the exit test has to be block-uniform, so it is
+        // only made there; a warp without work idles in between)
+        if ((iter++ % SDK_ADVECT_LOCKSTEP) == 0 && !__syncthreads_or(have)) break;
+#else
         if (!__any_sync(full, have)) break;
+#endif
         if (have && live && s.niter < a.max_iteration) step<T, LOG, P>(a, sZl, sdZl, s, live);
     }
 #else

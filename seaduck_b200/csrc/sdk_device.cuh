@@ -12,6 +12,9 @@
 #include "../../include/seaduck_b200.h"
 #include "fastmath.cuh"
 
+// branch hint: keeps the rarely taken side out of the fall-through path
+#define SDK_UNLIKELY(x) __builtin_expect(!!(x), 0)
+
 namespace sdk {
 
 // Grid description as the kernels see it.  Passed as a __grid_constant__ kernel parameter, so the
@@ -105,7 +108,7 @@ __device__ __forceinline__ double div_maybe_zero(double a, double b) {
 
 // nan_to_num of four / six values at once: one test in the (finite) common case
 __device__ __forceinline__ void nan_to_num4(double &a, double &b, double &c, double &d) {
-    if (not_finite(a) | not_finite(b) | not_finite(c) | not_finite(d)) {
+    if (SDK_UNLIKELY(not_finite(a) | not_finite(b) | not_finite(c) | not_finite(d))) {
         a = nan_to_num_cold(a);
         b = nan_to_num_cold(b);
         c = nan_to_num_cold(c);
@@ -114,7 +117,7 @@ __device__ __forceinline__ void nan_to_num4(double &a, double &b, double &c, dou
 }
 
 __device__ __forceinline__ void nan_to_num6(double &a, double &b, double &c, double &d, double &e, double &f) {
-    if (not_finite(a) | not_finite(b) | not_finite(c) | not_finite(d) | not_finite(e) | not_finite(f)) {
+    if (SDK_UNLIKELY(not_finite(a) | not_finite(b) | not_finite(c) | not_finite(d) | not_finite(e) | not_finite(f))) {
         a = nan_to_num_cold(a);
         b = nan_to_num_cold(b);
         c = nan_to_num_cold(c);
@@ -175,7 +178,7 @@ __device__ __forceinline__ int cell_move(const GridDev &g, int dir, int &f, int 
     const int nx_ = ix + (dir == 3) - (dir == 2);
     // one unsigned comparison per coordinate: negative values wrap to huge ones
     const bool off = ((unsigned)ny_ >= (unsigned)g.ny) | ((unsigned)nx_ >= (unsigned)g.nx);
-    if (!off) {
+    if (!SDK_UNLIKELY(off)) {
         iy = ny_;
         ix = nx_;
         return 0;
@@ -280,7 +283,7 @@ __device__ __forceinline__ void inverse_bilinear_fast(double x, double y, const 
     const bool order2 = !order1 && det2 >= 0;
     bool b1_ = false, b2_ = false, b3_ = false;
     double r = -fdiv(cc, bb, b1_);
-    if (order2) r = curved_root_cold(bb, det2, aa);  // curved cells only (polar cap)
+    if (SDK_UNLIKELY(order2)) r = curved_root_cold(bb, det2, aa);  // curved cells only (polar cap)
     const double den = a1 + a3 * r;
     // Cells whose x axis runs along a meridian (the rotated LLC faces) take the mean of two ratios in y
     // instead.  Both forms go through the same two divisions with the operands selected: no branch, the
@@ -364,7 +367,7 @@ static __device__ __noinline__ AxisTimes axis_wall_times(double u, double du, do
     tl = open_l ? t1 : -sg;
     tr = (open_r && !open_l) ? t1 : -sg;
     bool redo = (open_l || open_r) && (bt || (!lin && (bk || bl)));
-    if (open_l && open_r) {  // diverging flow inside the cell: the right wall needs its own logarithm
+    if (SDK_UNLIKELY(open_l & open_r)) {  // diverging flow inside the cell: the right wall needs its own logarithm
         const double arg2 = lin ? 1.0 : 1 + k * dr;
         const bool never2 = arg2 <= 0.0;
         const double lg2 = flog(never2 ? 1.0 : arg2, bl);
@@ -372,7 +375,7 @@ static __device__ __noinline__ AxisTimes axis_wall_times(double u, double du, do
         tr = never2 ? __longlong_as_double(0x7ff8000000000000LL) : tr;
         redo = bt || (!lin && (bk || bl));
     }
-    if (redo) return wall_times_cold(u, du, x0, sg);
+    if (SDK_UNLIKELY(redo)) return wall_times_cold(u, du, x0, sg);
     return make_double2(tl, tr);
 }
 
@@ -444,7 +447,7 @@ static __device__ __noinline__ double increment_cold(double t, double u, double 
 static __device__ __noinline__ double axis_increment(double t, double u, double du) {
     bool redo = false;
     double r = increment_fast_inline(t, u, du, redo);
-    if (redo) r = increment_cold(t, u, du);
+    if (SDK_UNLIKELY(redo)) r = increment_cold(t, u, du);
     return r;
 }
 
