@@ -387,10 +387,13 @@ int sdk_peer_enable(int peer_device);
 int sdk_peer_copy_async(void *dst, int dst_device, const void *src, int src_device, int64_t bytes, void *stream);
 
 /* Self-test of the device math helpers used by sdk_advect (csrc/fastmath.cuh): out[i] = op(a[i], b[i]),
- * bad[i] = 1 where the helper asked for the slow path.  Device pointers; b may be NULL for unary ops. */
+ * bad[i] = 1 where the helper asked for the slow path.  Device pointers; b may be NULL for unary ops.
+ * SDK_SELFTEST_STEP runs one analytic in-cell step (time to the walls, first event, move: _time2wall
+ * seaduck/utils.py:859, _which_early :875, _increment :777) per element instead: a = [n][10] doubles
+ * (x0[3], u[3], du[3], tf), out = [n][8] (tend, t_event, newx[3], newu[3]); b and bad are not used. */
 enum {
     SDK_SELFTEST_DIV = 0, SDK_SELFTEST_LOG = 1, SDK_SELFTEST_EXP = 2,
-    SDK_SELFTEST_DIV_IEEE = 3, SDK_SELFTEST_LOG_CUDA = 4, SDK_SELFTEST_EXP_CUDA = 5
+    SDK_SELFTEST_DIV_IEEE = 3, SDK_SELFTEST_LOG_CUDA = 4, SDK_SELFTEST_EXP_CUDA = 5, SDK_SELFTEST_STEP = 6
 };
 int sdk_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad, void *stream);
 

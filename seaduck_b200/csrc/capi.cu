@@ -586,7 +586,8 @@ int64_t sdk_struct_size(int which) {
 }
 
 int sdk_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad, void *stream) {
-    if (n < 0 || (n > 0 && (!a || !out || !bad))) return fail(SDK_EINVAL, "sdk_selftest_math: bad argument");
+    if (op < SDK_SELFTEST_DIV || op > SDK_SELFTEST_STEP) return fail(SDK_EINVAL, "sdk_selftest_math: unknown op");
+    if (n < 0 || (n > 0 && (!a || !out || (!bad && op != SDK_SELFTEST_STEP)))) return fail(SDK_EINVAL, "sdk_selftest_math: bad argument");
     if ((op == SDK_SELFTEST_DIV || op == SDK_SELFTEST_DIV_IEEE) && n > 0 && !b) return fail(SDK_EINVAL, "sdk_selftest_math: b missing");
     cudaError_t e = sdk::launch_selftest_math(op, n, a, b ? b : a, out, bad, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_selftest_math: launch");

@@ -107,3 +107,29 @@ def test_fexp_flags_out_of_range():
     got, bad = run(EXP, x)
     assert bad[:5].all() and not bad[5:].any()
     assert got[5] == 1.0 and got[6] == 1.0
+
+
+def test_analytic_step_on_the_reference_test_vectors():
+    """One analytic in-cell step on the device (axis_wall_times -> first event -> axis_increment, the helpers of the
+    advection kernel) on the vectors of the reference's own unit tests (tests/test_particle.py:75-209 there; outputs
+    of the unmodified reference in tests/golden/analytic_step.npz): the event is the same one, times and positions
+    agree to 1e-11 (north star 1e-9)."""
+    import os
+
+    import torch
+
+    from seaduck_b200 import _lib
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "analytic_step.npz"))
+    n = len(g["tf"])
+    packed = np.concatenate([g["x0"], g["u"], g["du"], g["tf"][:, None]], axis=1)
+    assert packed.shape == (n, 10)
+    dev = torch.device("cuda")
+    a = torch.from_numpy(np.ascontiguousarray(packed)).to(dev)
+    out = torch.full((n, 8), np.nan, dtype=torch.float64, device=dev)
+    _lib.check(_lib.lib().sdk_selftest_math(6, n, a.data_ptr(), None, out.data_ptr(), None, _lib.current_stream()), "sdk_selftest_math")
+    out = out.cpu().numpy()
+    np.testing.assert_array_equal(out[:, 0].astype(int), g["tend"])
+    np.testing.assert_allclose(out[:, 1], g["t_event"], rtol=1e-11, atol=0)
+    np.testing.assert_allclose(out[:, 2:5], g["newx"], rtol=1e-11, atol=1e-15)
+    np.testing.assert_allclose(out[:, 5:8], g["newu"], rtol=1e-11, atol=1e-25)
