@@ -158,7 +158,7 @@ typedef struct sdk_log {
 int sdk_abi_version(void);
 /* sizeof() of the structures above as the library was compiled (binding self-check): 0 sdk_grid_desc,
  * 1 sdk_velocity, 2 sdk_particles, 3 sdk_advect_params, 4 sdk_log, 5 sdk_located, 6 sdk_track_io,
- * 7 sdk_kernel_desc, 8 sdk_field, 9 sdk_points, 10 sdk_budget_fields; -1 for anything else */
+ * 7 sdk_kernel_desc, 8 sdk_field, 9 sdk_points, 10 sdk_budget_fields, 11 sdk_wall_fields; -1 for anything else */
 int64_t sdk_struct_size(int which);
 const char *sdk_last_error(void);
 /* number of SMs of the current device (grid sizing), <0 on error */
@@ -353,6 +353,27 @@ int sdk_log_calculate_budget(const sdk_log_record *records, const int64_t *offse
                              const int16_t *ind1, const int16_t *ind2, const double *frac, const double *tres,
                              const sdk_budget_fields *fields, double *conc, double *contr, unsigned char *work,
                              void *stream);
+
+/* read_wall_list (lagrangian_budget.py:406, the branch for grids with faces) and the quantities that
+ * check_particle_data_compat (:470) compares: for every record of the crossing log the values of three wall fields on
+ * the six walls of its cell (left, right, y-bottom, y-top, deep, shallow; the right / top wall may lie on a
+ * neighbouring, rotated face), the wall velocities from (u, du, r) (_uleftright_from_udu utils.py:852), the
+ * convergence of their products (crude_convergence :464) and the Eulerian convergence at the cell.  Device
+ * pointers; c_list and u_list are [6][n_rec], lag_conv and eul_conv [n_rec]; u_list, lag_conv, eul_conv and
+ * fields->conv may be NULL. */
+typedef struct sdk_wall_fields {
+    const double *x_walls, *y_walls, *z_walls; /* each [nz'][nface][ny'][nx'] with its own shape below */
+    const double *conv;                        /* Eulerian convergence, shape_c */
+    int32_t shape_x[4], shape_y[4], shape_z[4], shape_c[4];
+    /* cos and sin of pi - DIRECTIONS[edge] + DIRECTIONS[new_edge] (topology.py:248) for edge, new_edge in
+     * 0..3, index edge * 4 + new_edge, as the host's libm computes them: the reference multiplies with these
+     * unrounded numbers (cos(pi/2) = 6e-17 ...), so they are data, not something to recompute on the device */
+    double rot_cos[16], rot_sin[16];
+    int32_t scalar; /* 1: absolute values of the coefficients (scalar fields on walls) */
+    int32_t reserved;
+} sdk_wall_fields;
+int sdk_log_wall_values(const sdk_grid *grid, const sdk_log_record *records, int64_t n_rec, const sdk_wall_fields *fields,
+                        double *c_list, double *u_list, double *lag_conv, double *eul_conv, void *stream);
 
 /* ---- stencils of the Eulerian budget (seaduck/eulerian_budget.py); fp64, device pointers ------------- */
 /* Halo gather: out[o][k] = map[k] < 0 ? 0 : src[o * src_plane + map[k]] for o < n_outer, k < n_map.  The host

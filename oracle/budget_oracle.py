@@ -191,3 +191,55 @@ def calculate_budget(rec, offset, ind1, ind2, frac, tres, fields, rhs_list, lhs_
             out["error"][i] = 0.0 + (target - acc)
             out[lhs_name][i] = lhs
     return out, conc
+
+
+def read_wall_list(og, rec, prefetch, scalar=True):
+    """lagrangian_budget.py:406 for grids with faces: the values of three wall fields (x walls, y walls, z walls) on
+    the six walls of the cell of every record -> (6, n): left, right, bottom-y, top-y, deep, shallow."""
+    if not og.has_face:
+        raise NotImplementedError("the oracle restates the branch for grids with faces")
+    ua, va, wa = (np.asarray(p, float) for p in prefetch)
+    fc, iy, ix = (np.asarray(rec[k]).astype(int) for k in ("fc", "iy", "ix"))
+    izl = np.asarray(rec["izl"]).astype(int)
+    n = len(fc)
+    right, up = np.empty((3, n), int), np.empty((3, n), int)
+    for j in range(n):
+        here = (fc[j], iy[j], ix[j])
+        for move, out in ((3, right), (0, up)):
+            err, new = og.ind_tend(here, move)  # ind_tend_vec :526 keeps the old index where there is no neighbour
+            out[:, j] = here if err else new
+    # rotation of the neighbouring face, cos / sin as they come (topology.py:248-253: not rounded here)
+    lib = ora.lib()
+    rot_r, rot_u = np.zeros((n, 4)), np.zeros((n, 4))
+    m4 = (C.c_double * 4)()
+    for j in range(n):
+        for nf, out in ((right[0, j], rot_r), (up[0, j], rot_u)):
+            if lib.ora_uv_rotation_raw(C.byref(og.c), int(fc[j]), int(nf), m4):
+                raise ValueError("faces not connected")
+            out[j] = m4[:]
+    if scalar:
+        rot_r, rot_u = np.abs(rot_r), np.abs(rot_u)
+    lev = izl - 1
+    at = lambda a, k, idx: np.nan_to_num(a[k, idx[0], idx[1], idx[2]])  # noqa: E731
+    ur = at(ua, lev, right) * rot_r[:, 0] + at(va, lev, right) * rot_r[:, 1]
+    vr = at(ua, lev, up) * rot_u[:, 2] + at(va, lev, up) * rot_u[:, 3]
+    own = (fc, iy, ix)
+    return np.array([np.nan_to_num(v) for v in (ua[(lev,) + own], ur, va[(lev,) + own], vr, wa[(izl,) + own], wa[(lev,) + own])])
+
+
+def particle_data_compat(og, rec, fields, wall_names=("sx", "sy", "sz"), conv_name="divus"):
+    """lagrangian_budget.py:470 (``check_particle_data_compat`` with ``debug=True``): wall velocities from (u, du, r)
+    (``_uleftright_from_udu`` utils.py:852), wall values, the convergence of their products (``crude_convergence``
+    :464) and the Eulerian convergence at the records' cells."""
+    c_list = read_wall_list(og, rec, [fields[k] for k in wall_names])
+    g = lambda k: np.asarray(rec[k], float)  # noqa: E731
+    walls = []
+    for u, du, r in ((g("uu"), g("du"), g("rx")), (g("vv"), g("dv"), g("ry")), (g("ww"), g("dw"), g("rzl") - 0.5)):
+        walls += [u - (r + 0.5) * du, u + (0.5 - r) * du]
+    u_list = np.array(walls)
+    flux = c_list * u_list
+    conv = np.zeros(flux.shape[1])
+    for k, sign in enumerate((1, -1, 1, -1, 1, -1)):
+        conv = conv + flux[k] * sign
+    cell = (np.asarray(rec["izl"]).astype(int) - 1,) + tuple(np.asarray(rec[k]).astype(int) for k in ("fc", "iy", "ix"))
+    return u_list, c_list, conv, np.asarray(fields[conv_name], float)[cell]

@@ -93,6 +93,20 @@ def run_case(case):
                     out[f"s{i}_bud_{tag}_{k}"] = np.asarray(v, float)
                 out[f"s{i}_bud_{tag}_conc"] = np.asarray(conc, float)
                 assert np.array_equal(bfirst, first) and np.array_equal(blast, last)
+            # the consistency check between the particle log and the Eulerian budget (read_wall_list :406,
+            # check_particle_data_compat :470): wall values around every record, wall velocities from
+            # (u, du, r), their flux convergence, and the Eulerian convergence it should equal
+            neo["face"] = neo["fc"]
+            fields["sx"], fields["sy"], fields["sz"] = fields["sxprime"], fields["syprime"], fields["szprime"]
+            fields["divus"] = np.random.default_rng(200 + i).normal(size=np.asarray(case["ds"]["maskC"]).shape)
+            walls = [fields["sx"], fields["sy"], fields["sz"]]
+            with np.errstate(all="ignore"), contextlib.redirect_stdout(io.StringIO()):
+                out[f"s{i}_walls_scalar"] = np.asarray(lb.read_wall_list(neo, od.tp, walls, scalar=True), float)
+                out[f"s{i}_walls_vector"] = np.asarray(lb.read_wall_list(neo, od.tp, walls, scalar=False), float)
+                same, extra = lb.check_particle_data_compat(neo, fields, od.tp, wall_names=("sx", "sy", "sz"), conv_name="divus", debug=True)
+            out[f"s{i}_compat_ok"] = np.array(bool(same))
+            for k, v in zip(("u_list", "c_list", "lagrangian_conv", "eulerian_conv"), extra):
+                out[f"s{i}_compat_{k}"] = np.asarray(v, float)
     return out
 
 

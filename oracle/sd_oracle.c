@@ -852,6 +852,22 @@ int ora_ind_tend_uv(const ora_grid *g, int iw, const int32_t ind[3], int *new_iw
 
 /* Topology.four_matrix_for_uv, topology.py:689, rounded as in eulerian.py:934-937: for an (n, m) array
  * of faces (node 0 is the reference) the four coefficients UfromU, UfromV, VfromU, VfromV. */
+/* _llc_get_uv_mask_from_face topology.py:222 as it stands (cos / sin of the rotation, not rounded: what
+ * lagrangian_budget.read_wall_list :406 multiplies with): m = UfromU UfromV VfromU VfromV of face f1 seen from f0 */
+int ora_uv_rotation_raw(const ora_grid *g, int f0, int f1, double m[4]) {
+    m[0] = 1; m[1] = 0; m[2] = 0; m[3] = 1;
+    if (f0 == f1) return ORA_OK;
+    int edge, new_edge;
+    int err = mutual_direction(g, f0, f1, 1, &edge, &new_edge);
+    if (err) return err;
+    double rot = PI - DIRECTIONS[edge] + DIRECTIONS[new_edge];
+    m[0] = cos(rot);
+    m[1] = sin(rot);
+    m[2] = -sin(rot);
+    m[3] = cos(rot);
+    return ORA_OK;
+}
+
 int ora_four_matrix_for_uv(const ora_grid *g, int64_t n, int m, const int32_t *faces, double *ufu, double *ufv,
                            double *vfu, double *vfv, int32_t *oerr) {
     for (int64_t j = 0; j < n; ++j) {

@@ -101,6 +101,7 @@ int ora_fatten_h(const ora_grid *g, int64_t n, const int32_t *face, const int32_
 int ora_ind_tend_uv(const ora_grid *g, int iw, const int32_t ind[3], int *new_iw, int32_t out[3]);
 int ora_four_matrix_for_uv(const ora_grid *g, int64_t n, int m, const int32_t *faces, double *ufu, double *ufv,
                            double *vfu, double *vfv, int32_t *oerr);
+int ora_uv_rotation_raw(const ora_grid *g, int f0, int f1, double m[4]);
 int ora_corners(const ora_grid *g, const int32_t ind[3], int32_t out[4][3]);
 void ora_get_u_du(const ora_grid *g, const ora_vel *vel, ora_particles *p, int64_t i, int has_dep);
 void ora_analytic(const double x0[3], const double u[3], const double du[3], double tf, int *tend,

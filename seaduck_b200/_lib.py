@@ -133,6 +133,15 @@ class BudgetFields(C.Structure):
     ]
 
 
+class WallFields(C.Structure):
+    _fields_ = [
+        ("x_walls", C.c_void_p), ("y_walls", C.c_void_p), ("z_walls", C.c_void_p), ("conv", C.c_void_p),
+        ("shape_x", C.c_int32 * 4), ("shape_y", C.c_int32 * 4), ("shape_z", C.c_int32 * 4), ("shape_c", C.c_int32 * 4),
+        ("rot_cos", C.c_double * 16), ("rot_sin", C.c_double * 16),
+        ("scalar", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
 class SdkError(RuntimeError):
     pass
 
@@ -183,6 +192,7 @@ def lib():
         L.sdk_track_host.argtypes = [vp, C.POINTER(Velocity), C.POINTER(TrackIO), vp, C.c_int32, C.c_double, C.POINTER(AdvectParams), vp, vp]
         L.sdk_finish_stop.argtypes = [vp, vp, vp, C.c_int32, C.c_double, vp, vp, C.c_int64, vp]
         L.sdk_log_calculate_budget.argtypes = [vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, C.POINTER(BudgetFields), vp, vp, vp, vp]
+        L.sdk_log_wall_values.argtypes = [vp, vp, C.c_int64, C.POINTER(WallFields), vp, vp, vp, vp, vp]
         L.sdk_gather_plane.argtypes = [vp, C.c_int64, C.c_int64, vp, C.c_int64, vp, vp]
         L.sdk_wall_stencil.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64, vp]
         L.sdk_upwind3_z.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, vp]

@@ -221,4 +221,73 @@ cudaError_t launch_budget_terms(const BudgetTermArgs &a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// ---- read_wall_list / check_particle_data_compat (lagrangian_budget.py:406, :470) --------------------------
+
+__device__ __forceinline__ double field_at(const double *a, const int32_t *sh, int iz, int f, int iy, int ix) {
+    return __ldg(a + (((int64_t)wrap_index(iz, sh[0]) * sh[1] + wrap_index(f, sh[1])) * sh[2] + wrap_index(iy, sh[2])) * sh[3] +
+                 wrap_index(ix, sh[3]));
+}
+
+__global__ void wall_values_kernel(const __grid_constant__ WallValueArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n_rec) return;
+    const sdk_log_record &r = a.rec[i];
+    const sdk_wall_fields &w = a.f;
+    const int f = r.fc, iy = r.iy, ix = r.ix, lev = r.izl - 1;
+    // neighbours to the right and above; where a face has none the old index stays (ind_tend_vec topology.py:554-562)
+    int rf = f, ry = iy, rx = ix, in_r, uf = f, uy = iy, ux = ix, in_u;
+    cell_move(a.g, 3, rf, ry, rx, in_r);
+    cell_move(a.g, 0, uf, uy, ux, in_u);
+    // rotation of the neighbouring face (_llc_get_uv_mask_from_face topology.py:222): identity on the same face
+    double ufu = 1.0, ufv = 0.0, vfu = 0.0, vfv = 1.0;
+    if (rf != f) {
+        ufu = w.rot_cos[3 * 4 + in_r];
+        ufv = w.rot_sin[3 * 4 + in_r];
+    }
+    if (uf != f) {
+        vfu = -w.rot_sin[0 * 4 + in_u];
+        vfv = w.rot_cos[0 * 4 + in_u];
+    }
+    if (w.scalar) ufu = fabs(ufu), ufv = fabs(ufv), vfu = fabs(vfu), vfv = fabs(vfv);
+    const double ur = nan_to_num(field_at(w.x_walls, w.shape_x, lev, rf, ry, rx)) * ufu +
+                      nan_to_num(field_at(w.y_walls, w.shape_y, lev, rf, ry, rx)) * ufv;
+    const double vr = nan_to_num(field_at(w.x_walls, w.shape_x, lev, uf, uy, ux)) * vfu +
+                      nan_to_num(field_at(w.y_walls, w.shape_y, lev, uf, uy, ux)) * vfv;
+    double c[6];
+    c[0] = nan_to_num(field_at(w.x_walls, w.shape_x, lev, f, iy, ix));
+    c[1] = nan_to_num(ur);
+    c[2] = nan_to_num(field_at(w.y_walls, w.shape_y, lev, f, iy, ix));
+    c[3] = nan_to_num(vr);
+    c[4] = nan_to_num(field_at(w.z_walls, w.shape_z, r.izl, f, iy, ix));
+    c[5] = nan_to_num(field_at(w.z_walls, w.shape_z, lev, f, iy, ix));
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a.c_list[k * a.n_rec + i] = c[k];
+    // wall velocities from (u, du, r): _uleftright_from_udu utils.py:852; the vertical coordinate is rz - 1/2
+    const double z = r.rzl - 0.5;
+    double u[6];
+    u[0] = r.uu - (r.rx + 0.5) * r.du;
+    u[1] = r.uu + (0.5 - r.rx) * r.du;
+    u[2] = r.vv - (r.ry + 0.5) * r.dv;
+    u[3] = r.vv + (0.5 - r.ry) * r.dv;
+    u[4] = r.ww - (z + 0.5) * r.dw;
+    u[5] = r.ww + (0.5 - z) * r.dw;
+    if (a.u_list) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a.u_list[k * a.n_rec + i] = u[k];
+    }
+    if (a.lag_conv) {  // crude_convergence :464: the six products with alternating sign, summed in order
+        double conv = (c[0] * u[0]) * 1.0;
+#pragma unroll
+        for (int k = 1; k < 6; ++k) conv = conv + (c[k] * u[k]) * ((k & 1) ? -1.0 : 1.0);
+        a.lag_conv[i] = conv;
+    }
+    if (a.eul_conv && w.conv) a.eul_conv[i] = field_at(w.conv, w.shape_c, lev, f, iy, ix);
+}
+
+cudaError_t launch_wall_values(const WallValueArgs &a, cudaStream_t s) {
+    if (a.n_rec == 0) return cudaSuccess;
+    wall_values_kernel<<<(unsigned)((a.n_rec + 127) / 128), 128, 0, s>>>(a);
+    return cudaGetLastError();
+}
+
 }  // namespace sdk

@@ -32,4 +32,14 @@ struct BudgetTermArgs {
 
 cudaError_t launch_budget_terms(const BudgetTermArgs &a, cudaStream_t s);
 
+struct WallValueArgs {
+    GridDev g;
+    const sdk_log_record *rec;
+    int64_t n_rec;
+    sdk_wall_fields f;
+    double *c_list, *u_list, *lag_conv, *eul_conv;
+};
+
+cudaError_t launch_wall_values(const WallValueArgs &a, cudaStream_t s);
+
 }  // namespace sdk

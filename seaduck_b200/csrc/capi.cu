@@ -506,6 +506,30 @@ int sdk_log_calculate_budget(const sdk_log_record *records, const int64_t *offse
     return SDK_OK;
 }
 
+int sdk_log_wall_values(const sdk_grid *grid, const sdk_log_record *records, int64_t n_rec, const sdk_wall_fields *fields,
+                        double *c_list, double *u_list, double *lag_conv, double *eul_conv, void *stream) {
+    if (!grid || !fields || n_rec < 0) return fail(SDK_EINVAL, "sdk_log_wall_values: bad argument");
+    if (!grid->dev.has_face) return fail(SDK_EUNSUPPORTED, "sdk_log_wall_values: only grids with faces (like the reference's tested branch)");
+    if (n_rec > 0 && (!records || !c_list || !fields->x_walls || !fields->y_walls || !fields->z_walls))
+        return fail(SDK_EINVAL, "sdk_log_wall_values: null array");
+    if (eul_conv && !fields->conv) return fail(SDK_EINVAL, "sdk_log_wall_values: eul_conv asked for without a convergence field");
+    for (int d = 0; d < 4; ++d)
+        if (fields->shape_x[d] < 1 || fields->shape_y[d] < 1 || fields->shape_z[d] < 1 || (fields->conv && fields->shape_c[d] < 1))
+            return fail(SDK_EINVAL, "sdk_log_wall_values: empty field");
+    sdk::WallValueArgs a;
+    a.g = grid->dev;
+    a.rec = records;
+    a.n_rec = n_rec;
+    a.f = *fields;
+    a.c_list = c_list;
+    a.u_list = u_list;
+    a.lag_conv = lag_conv;
+    a.eul_conv = eul_conv;
+    cudaError_t e = sdk::launch_wall_values(a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_log_wall_values: launch");
+    return SDK_OK;
+}
+
 int sdk_gather_plane(const double *src, int64_t n_outer, int64_t src_plane, const int64_t *map, int64_t n_map,
                      double *out, void *stream) {
     if (n_outer < 0 || n_map < 0 || src_plane < 0) return fail(SDK_EINVAL, "sdk_gather_plane: negative size");
@@ -581,6 +605,7 @@ int64_t sdk_struct_size(int which) {
         case 8: return sizeof(sdk_field);
         case 9: return sizeof(sdk_points);
         case 10: return sizeof(sdk_budget_fields);
+        case 11: return sizeof(sdk_wall_fields);
         default: return -1;
     }
 }

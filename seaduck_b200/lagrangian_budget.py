@@ -161,3 +161,86 @@ def calculate_budget(particle_array, data_slice, rhs_list, prefetch_vector_kwarg
     model time step.  numpy arrays come back."""
     contr, conc, first, last = calculate_budget_device(particle_array, data_slice, rhs_list, prefetch_vector_kwarg, lhs_name, dir_of_time)
     return {k: v.cpu().numpy() for k, v in contr.items()}, conc.cpu().numpy(), first.cpu().numpy(), last.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# wall values around every record and the particle / data consistency check (reference :406, :470)
+# ---------------------------------------------------------------------------------------------------------
+
+_DIRECTIONS = np.array([np.pi / 2, -np.pi / 2, np.pi, 0])  # up, down, left, right (reference topology.py:30)
+
+
+def _wall_values_device(particle, walls, conv=None, scalar=True, chunk=-1, want_velocities=False):
+    """``c_list`` (6, n) [, ``u_list`` (6, n), Lagrangian convergence (n), Eulerian convergence (n)] as CUDA tensors."""
+    import torch  # noqa: PLC0415
+
+    if not particle.save_raw:
+        raise AttributeError("This is not a particle_rawlist object")
+    if not particle._raw:
+        raise ValueError("the particle has no crossing log yet")
+    od = particle.ocedata
+    if not od.tp.has_face:
+        raise NotImplementedError("wall values are implemented for grids with faces (the branch the reference tests)")
+    ch = particle._raw[chunk]
+    records = ch["records"]
+    n_rec = records.shape[0]
+    dev = records.device
+    arrays = [_field_on_device(a, dev) for a in walls]
+    f = _lib.WallFields()
+    for t, name in zip(arrays, ("x", "y", "z")):
+        if t.ndim != 4:
+            raise ValueError(f"the {name}-wall field has {t.ndim} dimensions, (Z, face, Y, X) expected")
+        getattr(f, f"shape_{name}")[:] = tuple(t.shape)
+    f.x_walls, f.y_walls, f.z_walls = (t.data_ptr() for t in arrays)
+    conv_t = None
+    if conv is not None:
+        conv_t = _field_on_device(conv, dev)
+        if conv_t.ndim != 4:
+            raise ValueError("the convergence field must be (Z, face, Y, X)")
+        f.conv = conv_t.data_ptr()
+        f.shape_c[:] = tuple(conv_t.shape)
+    rot = np.pi - _DIRECTIONS[:, None] + _DIRECTIONS[None, :]  # topology.py:248, [edge][new_edge]
+    f.rot_cos[:] = np.cos(rot).reshape(-1).tolist()
+    f.rot_sin[:] = np.sin(rot).reshape(-1).tolist()
+    f.scalar = int(bool(scalar))
+    c_list = torch.empty((6, n_rec), dtype=torch.float64, device=dev)
+    u_list = torch.empty((6, n_rec), dtype=torch.float64, device=dev) if want_velocities else None
+    lag = torch.empty(n_rec, dtype=torch.float64, device=dev) if want_velocities else None
+    eul = torch.empty(n_rec, dtype=torch.float64, device=dev) if (want_velocities and conv_t is not None) else None
+    ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+    _lib.check(
+        _lib.lib().sdk_log_wall_values(od.grid_handle(), records.data_ptr(), n_rec, f, c_list.data_ptr(), ptr(u_list), ptr(lag), ptr(eul), _lib.current_stream()),
+        "sdk_log_wall_values",
+    )
+    return c_list, u_list, lag, eul
+
+
+def read_wall_list(neo, tp=None, prefetch=None, scalar=True):
+    """The values of the three wall fields ``prefetch = (x walls, y walls, z walls)`` on the six walls of the cell
+    of every record of the particle's crossing log: ``(6, n)`` = left, right, y-bottom, y-top, deep, shallow.
+    Reference ``read_wall_list(neo, tp, prefetch, scalar)`` (:406); ``neo`` is the :class:`Particle` whose log is on
+    the device."""
+    del tp  # the particle's OceData knows its topology
+    if prefetch is None or len(prefetch) != 3:
+        raise ValueError("prefetch must be the three wall arrays (x, y, z)")
+    return _wall_values_device(neo, prefetch, scalar=scalar)[0].cpu().numpy()
+
+
+def check_particle_data_compat(xrpt, xrslc, tp=None, use_tracer_name=None, wall_names=("sx", "sy", "sz"), conv_name="divus",
+                               debug=False, allclose_kwarg={}):  # noqa: B006
+    """Can the Lagrangian budget be closed with this model output?  The convergence of the wall fluxes seen by the
+    particles must equal the Eulerian convergence ``xrslc[conv_name]`` at their cells.  Reference
+    ``check_particle_data_compat`` (:470); returns ``(ok, extra)`` with ``extra = (u_list, c_list, lagrangian_conv,
+    eulerian_conv)`` when ``debug`` else ``None``."""
+    del tp
+    if isinstance(use_tracer_name, str):
+        wall_names = tuple(use_tracer_name + i for i in ["x", "y", "z"])
+        conv_name = "divu" + use_tracer_name
+    elif use_tracer_name is not None:
+        raise ValueError("use_tracer_name has to be a string.")
+    if not xrpt._has_dep:
+        raise NotImplementedError("This functionality only support 3D simulation at the moment.")
+    c_list, u_list, lag, eul = _wall_values_device(xrpt, [xrslc[k] for k in wall_names], conv=xrslc[conv_name], want_velocities=True)
+    lag_h, eul_h = lag.cpu().numpy(), eul.cpu().numpy()
+    extra = (u_list.cpu().numpy(), c_list.cpu().numpy(), lag_h, eul_h) if debug else None
+    return bool(np.allclose(lag_h, eul_h, **allclose_kwarg)), extra

@@ -55,3 +55,29 @@ def test_calculate_budget_oracle_matches_reference():
             for k, v in out.items():
                 np.testing.assert_array_equal(v, gold[f"s{i}_bud_{tag}_{k}"], err_msg=f"{tag} {k}")
             assert np.isnan(out["adv"]).any()  # the 0 / 0 cells are in the sample
+
+
+def test_wall_values_and_compat_oracle_match_reference(oracle_lib):
+    """read_wall_list (:406) and check_particle_data_compat (:470) of the reference on its own log against the
+    oracle's restatement: everything to the bit."""
+    import seaduck_b200 as sd
+    from oracle import budget_oracle as bo
+
+    case = cases.case_llc_transport()
+    logs = np.load(os.path.join(GOLD, "lagrangian_llc_transport.npz"))
+    gold = np.load(os.path.join(GOLD, "budget_llc_transport.npz"))
+    og = oracle_lib.OracleGrid(sd.OceData(case["ds"]))
+    shape = np.asarray(case["ds"]["maskC"]).shape
+    for i in range(len(case["stops"])):
+        rec = {k: logs[f"s{i}_log_{k}"] for k in cases.LOG_INT + cases.LOG_FLT if f"s{i}_log_{k}" in logs}
+        fields = cases.budget_fields(shape, seed=100 + i)
+        fields.update(sx=fields["sxprime"], sy=fields["syprime"], sz=fields["szprime"],
+                      divus=np.random.default_rng(200 + i).normal(size=shape))
+        walls = [fields["sx"], fields["sy"], fields["sz"]]
+        np.testing.assert_array_equal(bo.read_wall_list(og, rec, walls, scalar=True), gold[f"s{i}_walls_scalar"])
+        np.testing.assert_array_equal(bo.read_wall_list(og, rec, walls, scalar=False), gold[f"s{i}_walls_vector"])
+        u_list, c_list, lag, eul = bo.particle_data_compat(og, rec, fields)
+        np.testing.assert_array_equal(u_list, gold[f"s{i}_compat_u_list"])
+        np.testing.assert_array_equal(c_list, gold[f"s{i}_compat_c_list"])
+        np.testing.assert_array_equal(eul, gold[f"s{i}_compat_eulerian_conv"])
+        np.testing.assert_array_equal(lag, gold[f"s{i}_compat_lagrangian_conv"])

@@ -45,7 +45,7 @@ def test_struct_sizes_match_header():
     L.sdk_struct_size.restype = ctypes.c_int64
     mirrors = [
         _lib.GridDesc, _lib.Velocity, _lib.Particles, _lib.AdvectParams, _lib.Log, _lib.Located, _lib.TrackIO,
-        interp.KernelDesc, interp.Field, interp.Points, _lib.BudgetFields,
+        interp.KernelDesc, interp.Field, interp.Points, _lib.BudgetFields, _lib.WallFields,
     ]
     for which, cls in enumerate(mirrors):
         assert ctypes.sizeof(cls) == L.sdk_struct_size(which), cls.__name__

@@ -163,3 +163,59 @@ def test_calculate_budget_argument_checks():
     bad = dict(fields, adv=fields["adv"][:-1])
     with pytest.raises(ValueError):
         lb.calculate_budget(pt, bad, ["adv"], dict(same_size=False))
+
+
+def test_wall_values_and_compat_check_match_oracle_and_reference(oracle_lib):
+    """read_wall_list (:406) / check_particle_data_compat (:470) on the device: bit-exact against the numpy oracle fed
+    with the device's own log (wall values incl. the 1e-16 leak of the unrounded rotation coefficients, wall
+    velocities, both convergences), and 1e-9 against the reference's run wherever both logs sit in the same cell."""
+    import seaduck_b200 as sd
+    from oracle import budget_oracle as bo
+    from seaduck_b200 import lagrangian_budget as lb
+
+    case = cases.case_llc_transport()
+    gold = np.load(os.path.join(GOLD, "budget_llc_transport.npz"))
+    logs = np.load(os.path.join(GOLD, "lagrangian_llc_transport.npz"))
+    od = sd.OceData(case["ds"])
+    og = oracle_lib.OracleGrid(od)
+    pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, save_raw=True, **case["kw"])
+    shape = np.asarray(case["ds"]["maskC"]).shape
+    for i, ts in enumerate(case["stops"]):
+        pt.empty_lists()
+        pt.note_taking(stamp=15)
+        pt.to_next_stop(ts)
+        rec = pt.raw_arrays()[-1]
+        fields = cases.budget_fields(shape, seed=100 + i)
+        fields.update(sx=fields["sxprime"], sy=fields["syprime"], sz=fields["szprime"],
+                      divus=np.random.default_rng(200 + i).normal(size=shape))
+        walls = [fields["sx"], fields["sy"], fields["sz"]]
+        for scalar in (True, False):
+            got = lb.read_wall_list(pt, od.tp, walls, scalar=scalar)
+            np.testing.assert_array_equal(got, bo.read_wall_list(og, rec, walls, scalar=scalar))
+        ok, (u_list, c_list, lag, eul) = lb.check_particle_data_compat(pt, fields, od.tp, debug=True)
+        wu, wc, wlag, weul = bo.particle_data_compat(og, rec, fields)
+        np.testing.assert_array_equal(u_list, wu)
+        np.testing.assert_array_equal(c_list, wc)
+        np.testing.assert_array_equal(lag, wlag)
+        np.testing.assert_array_equal(eul, weul)
+        assert ok == bool(gold[f"s{i}_compat_ok"])
+        # against the reference's own run: same number of records, same cells (indices are bit-exact), values 1e-9
+        assert c_list.shape == gold[f"s{i}_compat_c_list"].shape
+        same_cell = np.ones(c_list.shape[1], bool)
+        for k in ("fc", "iy", "ix", "izl"):
+            same_cell &= rec[k] == logs[f"s{i}_log_{k}"]
+        assert same_cell.all()
+        np.testing.assert_array_equal(c_list, gold[f"s{i}_compat_c_list"])
+        np.testing.assert_array_equal(eul, gold[f"s{i}_compat_eulerian_conv"])
+        cases.assert_close("u_list", u_list, gold[f"s{i}_compat_u_list"])
+        cases.assert_close("lagrangian_conv", lag, gold[f"s{i}_compat_lagrangian_conv"])
+    # a field whose Eulerian convergence is made to fit passes the check, the random one above does not
+    fields["divus"] = np.zeros(shape)
+    fields["divus"][rec["izl"] - 1, rec["fc"], rec["iy"], rec["ix"]] = lag
+    cells, first_at = np.unique(np.stack([rec["izl"], rec["fc"], rec["iy"], rec["ix"]]), axis=1, return_index=True)
+    if cells.shape[1] == len(lag):  # only meaningful when no two records share a cell
+        assert lb.check_particle_data_compat(pt, fields, od.tp)[0]
+    with pytest.raises(ValueError):
+        lb.read_wall_list(pt, od.tp, walls[:2])
+    with pytest.raises(ValueError):
+        lb.check_particle_data_compat(pt, fields, od.tp, use_tracer_name=3)
