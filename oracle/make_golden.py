@@ -86,7 +86,10 @@ def run_case(case):
 def main():
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
-    for make in cases.ALL_CASES:
+    only = sys.argv[1:]
+    for make in cases.ALL_CASES + cases.ORACLE_ONLY_CASES:
+        if only and make.__name__ not in only:
+            continue
         case = make()
         out = run_case(case)
         path = os.path.join(gold, f"lagrangian_{case['name']}.npz")

@@ -32,7 +32,7 @@ class _Grid(C.Structure):
         [(n, C.c_int32) for n in ("typ", "has_face", "nface", "ny", "nx", "gny", "gnx", "hmode", "n_zl", "n_z")]
         + [("face_connect", c_i32p)]
         + [(n, c_f32p) for n in ("XC", "YC", "XG", "YG", "dX", "dY", "CS", "SN", "Zl", "dZl", "Z", "dZ", "lon", "lat")]
-        + [("dlon", c_f64p), ("dlat", c_f64p)]
+        + [("dlon", c_f64p), ("dlat", c_f64p), ("coslat32", c_f32p)]
     )
 
 
@@ -218,8 +218,8 @@ class OracleGrid:
         self.h_shape = tuple(tp.h_shape)
         self.g_shape = tuple(tp.g_shape)
         self.has_face = len(self.h_shape) == 3
-        if self.readiness["h"] != "oceanparcel":
-            raise NotImplementedError("oracle: only the oceanparcel horizontal scheme is restated in C")
+        if self.readiness["h"] not in ("oceanparcel", "rectilinear"):
+            raise NotImplementedError("oracle: the local_cartesian horizontal scheme is not restated")
         get = lambda n: getattr(od, n, None)  # noqa: E731
         f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
         self.XC, self.YC, self.XG, self.YG = (f32(get(n)) for n in ("XC", "YC", "XG", "YG"))
@@ -245,6 +245,18 @@ class OracleGrid:
         g.face_connect = _ptr(self.face_connect, c_i32p)
         for n in ("XC", "YC", "XG", "YG", "dX", "dY", "CS", "SN", "Zl", "dZl", "Z", "dZ"):
             setattr(g, n, _ptr(getattr(self, n), c_f32p))
+        if self.readiness["h"] == "rectilinear":
+            # ocedata.py:255-259, 368-370: lon / lat as float32, their spacing in metres from np.gradient (R = 6371 km)
+            self.lon, self.lat = f32(get("lon")), f32(get("lat"))
+            self.dlon = np.ascontiguousarray(get("dlon"), dtype=np.float64)
+            self.dlat = np.ascontiguousarray(get("dlat"), dtype=np.float64)
+            # what lagrangian.py:671 / :693 evaluate for a float32 latitude (float32 arithmetic and numpy's float32
+            # cosine): taken from numpy on the same array, element by element
+            self.coslat32 = np.ascontiguousarray(np.cos(self.lat * np.pi / 180), dtype=np.float32)
+            assert self.coslat32.dtype == np.float32 and (self.lat * np.pi / 180).dtype == np.float32
+            g.lon, g.lat = _ptr(self.lon, c_f32p), _ptr(self.lat, c_f32p)
+            g.dlon, g.dlat = _ptr(self.dlon, c_f64p), _ptr(self.dlat, c_f64p)
+            g.coslat32 = _ptr(self.coslat32, c_f32p)
         self.c = g
 
     # -- topology restatement exposed for tests -------------------------------------------------
@@ -336,22 +348,19 @@ class OracleParticle:
         self.t = np.array(t, float)
         self.has_dep = z is not None and g.readiness["Zl"]
         self.dep = np.array(z, float) if z is not None else np.zeros(n)
-        # horizontal rel-coords: reference find_rel_h_oceanparcel, utils.py:614
-        ind = g.find_ind_h(self.lon, self.lat)
-        if g.has_face:
-            self.face, self.iy, self.ix = (np.ascontiguousarray(a, np.int32) for a in ind)
-        else:
+        if g.readiness["h"] == "rectilinear":
+            # reference find_rel_h_rectilinear, utils.py:602 (two periodic 1-D lookups; spacing from np.diff, R = 6271 km)
+            ix, rx, dxd, bx = find_rel(self.lon, g.lon, peri=360.0)
+            iy, ry, dyd, by = find_rel(self.lat, g.lat, peri=360.0)
             self.face = np.zeros(n, np.int32)
-            self.iy, self.ix = (np.ascontiguousarray(a, np.int32) for a in ind)
-        self.bx = g.XC[ind].astype(float)
-        self.by = g.YC[ind].astype(float)
-        self.dx = g.dX[ind].astype(float) if g.dX is not None else np.ones(n)
-        self.dy = g.dY[ind].astype(float) if g.dY is not None else np.ones(n)
-        self.cs = g.CS[ind].astype(float) if g.CS is not None else np.ones(n)
-        self.sn = g.SN[ind].astype(float) if g.SN is not None else np.zeros(n)
-        px, py = g.px_py(ind, self.lon)
-        self.rx, self.ry = find_rx_ry_oceanparcel(self.lon, self.lat, px, py)
-        self.px, self.py = np.ascontiguousarray(px), np.ascontiguousarray(py)
+            self.iy, self.ix = np.ascontiguousarray(iy, np.int32), np.ascontiguousarray(ix, np.int32)
+            self.rx, self.ry, self.bx, self.by = rx, ry, bx, by
+            self.dx = np.cos(by * np.pi / 180) * DEG2M * dxd
+            self.dy = DEG2M * dyd
+            self.cs, self.sn = np.ones(n), np.zeros(n)
+            self.px, self.py = np.zeros((4, n)), np.zeros((4, n))
+        else:
+            self._init_h_oceanparcel(g, n)
         if self.has_dep:
             # reference OceData._find_rel_vl_lin, ocedata.py:475
             izl, rzl, dzl, bzl = find_rel(self.dep, g.Zl, g.dZl, ascending=-1, dx_right=True)
@@ -375,6 +384,24 @@ class OracleParticle:
             self.get_vol()
         self.get_u_du()
         self.records = None
+
+    def _init_h_oceanparcel(self, g, n):
+        # horizontal rel-coords: reference find_rel_h_oceanparcel, utils.py:614
+        ind = g.find_ind_h(self.lon, self.lat)
+        if g.has_face:
+            self.face, self.iy, self.ix = (np.ascontiguousarray(a, np.int32) for a in ind)
+        else:
+            self.face = np.zeros(n, np.int32)
+            self.iy, self.ix = (np.ascontiguousarray(a, np.int32) for a in ind)
+        self.bx = g.XC[ind].astype(float)
+        self.by = g.YC[ind].astype(float)
+        self.dx = g.dX[ind].astype(float) if g.dX is not None else np.ones(n)
+        self.dy = g.dY[ind].astype(float) if g.dY is not None else np.ones(n)
+        self.cs = g.CS[ind].astype(float) if g.CS is not None else np.ones(n)
+        self.sn = g.SN[ind].astype(float) if g.SN is not None else np.zeros(n)
+        px, py = g.px_py(ind, self.lon)
+        self.rx, self.ry = find_rx_ry_oceanparcel(self.lon, self.lat, px, py)
+        self.px, self.py = np.ascontiguousarray(px), np.ascontiguousarray(py)
 
     # -- velocity staging -------------------------------------------------------------------------
     def set_velocity(self, uarr, varr, warr, vol, u_dims, v_dims, it0=0):

@@ -13,6 +13,7 @@
 
 #define NOFACE 999
 static const double PI = 3.141592653589793;
+static const double DEG2M = 6271e3 * 3.141592653589793 / 180; /* sic: lagrangian.py:22, utils.py:306 */
 /* DIRECTIONS, topology.py:30 */
 static const double DIRECTIONS[4] = {3.141592653589793 / 2, -3.141592653589793 / 2,
                                      3.141592653589793, 0.0};
@@ -708,7 +709,7 @@ static void advect_one(const ora_grid *g, const ora_vel *vel, ora_particles *p, 
         p->w[i] = nu[2];
         /* _sync_latlondep_before_cross, lagrangian.py:539 */
         if (has_dep) p->dep[i] = p->bzl[i] + p->dzl[i] * p->rzl[i];
-        {
+        if (g->hmode == ORA_H_OCEANPARCEL) {
             double rx = p->rx[i], ry = p->ry[i];
             double w4[4] = {(0.5 - rx) * (0.5 - ry), (0.5 + rx) * (0.5 - ry), (0.5 + rx) * (0.5 + ry),
                             (0.5 - rx) * (0.5 + ry)};
@@ -719,6 +720,15 @@ static void advect_one(const ora_grid *g, const ora_vel *vel, ora_particles *p, 
             }
             p->lon[i] = lon;
             p->lat[i] = lat;
+        } else {
+            /* rel2latlon, utils.py:214 (no px / py on the particle: lagrangian.py:549); compiled by numba in the
+             * reference, so the cosine is taken in double precision */
+            double temp_x = p->rx[i] * p->dx[i] / DEG2M;
+            double temp_y = p->ry[i] * p->dy[i] / DEG2M;
+            double dlon = (temp_x * p->cs[i] - temp_y * p->sn[i]) / cos(p->by[i] * PI / 180);
+            double dlat = temp_x * p->sn[i] + temp_y * p->cs[i];
+            p->lon[i] = dlon + p->bx[i];
+            p->lat[i] = dlat + p->by[i];
         }
         note(log, p, i, tend, has_dep, &cursor);
         if (tend < 6) ncross += 1;
@@ -740,13 +750,23 @@ static void advect_one(const ora_grid *g, const ora_vel *vel, ora_particles *p, 
             else if (p->izl[i] == 1) p->dep[i] = p->bzl[i] + p->dzl[i] / 2;
             else p->izl[i] -= 1;
         }
-        /* _cross_cell_wall_read, lagrangian.py:640 (oceanparcel branch) */
-        {
+        /* _cross_cell_wall_read, lagrangian.py:640 */
+        double cos_by32 = 1.0;
+        if (g->hmode == ORA_H_OCEANPARCEL) {
             int64_t hidx = ((int64_t)(g->has_face ? p->face[i] : 0) * g->ny + wrap(p->iy[i], g->ny)) *
                                g->nx + wrap(p->ix[i], g->nx);
             p->bx[i] = (double)g->XC[hidx];
             p->by[i] = (double)g->YC[hidx];
             if (read_corners(g, p, i)) p->status[i] |= 2;
+        } else if (g->hmode == ORA_H_RECTILINEAR) { /* :667-672 */
+            int ix = wrap(p->ix[i], g->nx), iy = wrap(p->iy[i], g->ny);
+            p->bx[i] = (double)g->lon[ix];
+            p->by[i] = (double)g->lat[iy];
+            p->cs[i] = 1.0;
+            p->sn[i] = 0.0;
+            cos_by32 = (double)g->coslat32[iy]; /* np.cos(float32 lat * np.pi / 180): float32 arithmetic */
+            p->dx[i] = g->dlon[ix] * cos_by32;
+            p->dy[i] = g->dlat[iy];
         }
         if (has_dep) {
             p->bzl[i] = (double)g->Zl[wrap(p->izl[i], g->n_zl)];
@@ -754,13 +774,18 @@ static void advect_one(const ora_grid *g, const ora_vel *vel, ora_particles *p, 
         }
         /* _cross_cell_wall_rel, lagrangian.py:681 */
         if (has_dep) p->rzl[i] = (p->dep[i] - p->bzl[i]) / p->dzl[i];
-        {
+        if (g->hmode == ORA_H_OCEANPARCEL) {
             double px[4], py[4];
             for (int j = 0; j < 4; ++j) {
                 px[j] = p->px[j * n + i];
                 py[j] = p->py[j * n + i];
             }
             find_rx_ry_oceanparcel(p->lon[i], p->lat[i], px, py, &p->rx[i], &p->ry[i]);
+        } else { /* :693-703; by is the float32 array just read, so is its cosine */
+            double dlon = to_180(p->lon[i] - p->bx[i]);
+            double dlat = to_180(p->lat[i] - p->by[i]);
+            p->rx[i] = (dlon * cos_by32 * p->cs[i] + dlat * p->sn[i]) * DEG2M / p->dx[i];
+            p->ry[i] = (dlat * p->cs[i] - dlon * p->sn[i] * cos_by32) * DEG2M / p->dy[i];
         }
         if (vel->transport)
             p->vol[i] = get_vol(g, vel, has_dep ? p->izl[i] : 0, g->has_face ? p->face[i] : 0,
@@ -886,7 +911,7 @@ int ora_four_matrix_for_uv(const ora_grid *g, int64_t n, int m, const int32_t *f
 
 int ora_advect(const ora_grid *g, const ora_vel *vel, ora_particles *p, double t_stop,
                const ora_params *par, ora_log *log) {
-    if (g->hmode != ORA_H_OCEANPARCEL) return -1;
+    if (g->hmode == ORA_H_LOCAL_CARTESIAN) return -1; /* not restated */
     int nthreads = par->nthreads > 0 ? par->nthreads : 1;
     if (nthreads == 1) {
         for (int64_t i = 0; i < p->n; ++i) advect_one(g, vel, p, i, t_stop, par, log);

@@ -151,23 +151,23 @@ def channel(ny=20, nx=72, nz=4, dtype=np.float64, as_xarray=False):
 
 
 def rectilinear(nlat=60, nlon=120, nt=1, dtype=np.float64, as_xarray=False):
-    """Global 1-D lon/lat grid (``readiness['h'] == 'rectilinear'``, reference ``ocedata.py:255``)."""
+    """Global 1-D lon/lat grid (``readiness['h'] == 'rectilinear'``, reference ``ocedata.py:255``): dimensions
+    ``Y`` / ``X`` (the names ``Position.fatten`` knows, ``eulerian.py:520``) with the 1-D variables ``lon(X)``,
+    ``lat(Y)`` and unstaggered velocities ``u, v`` in m/s -- the shape of an altimetry product."""
     lon = np.linspace(-180, 180, nlon, endpoint=False)
     lat = np.linspace(-75, 75, nlat)
     lam, phi = np.meshgrid(np.deg2rad(lon), np.deg2rad(lat))
     u = 0.4 * np.cos(phi) * (1 + 0.5 * np.sin(3 * lam))
     v = 0.12 * np.sin(2 * lam) * np.cos(phi) ** 2
-    coords = dict(lon=(["lon"], lon), lat=(["lat"], lat))
+    coords = dict(X=(["X"], np.arange(nlon)), Y=(["Y"], np.arange(nlat)))
+    data = dict(lon=(["X"], lon), lat=(["Y"], lat))
     if nt > 1:
         time = np.arange(nt) * 86400.0 * 5
         coords["time"] = (["time"], time)
         scale = (1 + 0.25 * np.arange(nt)).reshape(nt, 1, 1)
-        data = dict(
-            u=(["time", "lat", "lon"], (u * scale).astype(dtype)),
-            v=(["time", "lat", "lon"], (v * scale).astype(dtype)),
-        )
+        data.update(u=(["time", "Y", "X"], (u * scale).astype(dtype)), v=(["time", "Y", "X"], (v * scale).astype(dtype)))
     else:
-        data = dict(u=(["lat", "lon"], u.astype(dtype)), v=(["lat", "lon"], v.astype(dtype)))
+        data.update(u=(["Y", "X"], u.astype(dtype)), v=(["Y", "X"], v.astype(dtype)))
     return _dataset(coords, data, as_xarray)
 
 

@@ -135,6 +135,23 @@ def case_llc_callback(n=200, ngrid=24, nz=6):
     )
 
 
+def case_rectilinear(n=300):
+    """1-D lon / lat grid (altimetry-like), velocities in m/s, x-periodic: the `rectilinear` horizontal scheme
+    (reference ocedata.py:255, utils.py:602, lagrangian.py:667-672, :693-703)."""
+    ds = synthetic.rectilinear(nlat=40, nlon=80)
+    rng = np.random.default_rng(11)
+    return dict(
+        name="rectilinear",
+        ds=ds,
+        x=rng.uniform(-179.0, 179.0, n), y=rng.uniform(-65.0, 65.0, n), z=np.full(n, -1.0), t=np.zeros(n),
+        stops=[80 * DAY, -50 * DAY],
+        kw=dict(uname="u", vname="v", wname=None, transport=False),
+    )
+
+
+# cases the CPU oracle is pinned on but the device path does not take yet (sdk_locate raises for this scheme)
+ORACLE_ONLY_CASES = [case_rectilinear]
+
 ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_bool_array, case_llc_callback, case_channel_kickback]
 
 LOG_INT = ["fc", "it", "izl", "iy", "ix", "vs"]

@@ -35,7 +35,7 @@ def compare_state(gold, prefix, get, has_dep=True):
             cases.assert_close(k, get(k), gold[f"{prefix}{k}"])
 
 
-@pytest.mark.parametrize("make", cases.ALL_CASES, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("make", cases.ALL_CASES + cases.ORACLE_ONLY_CASES, ids=lambda f: f.__name__)
 def test_oracle_matches_reference_golden(make, oracle_lib):
     case = make()
     gold = np.load(os.path.join(GOLD, f"lagrangian_{case['name']}.npz"))
