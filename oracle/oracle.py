@@ -218,8 +218,6 @@ class OracleGrid:
         self.h_shape = tuple(tp.h_shape)
         self.g_shape = tuple(tp.g_shape)
         self.has_face = len(self.h_shape) == 3
-        if self.readiness["h"] not in ("oceanparcel", "rectilinear"):
-            raise NotImplementedError("oracle: the local_cartesian horizontal scheme is not restated")
         get = lambda n: getattr(od, n, None)  # noqa: E731
         f32 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.float32)  # noqa: E731
         self.XC, self.YC, self.XG, self.YG = (f32(get(n)) for n in ("XC", "YC", "XG", "YG"))
@@ -256,6 +254,10 @@ class OracleGrid:
             assert self.coslat32.dtype == np.float32 and (self.lat * np.pi / 180).dtype == np.float32
             g.lon, g.lat = _ptr(self.lon, c_f32p), _ptr(self.lat, c_f32p)
             g.dlon, g.dlat = _ptr(self.dlon, c_f64p), _ptr(self.dlat, c_f64p)
+            g.coslat32 = _ptr(self.coslat32, c_f32p)
+        elif self.readiness["h"] == "local_cartesian":
+            self.coslat32 = np.ascontiguousarray(np.cos(self.YC * np.pi / 180), dtype=np.float32)
+            assert (self.YC * np.pi / 180).dtype == np.float32
             g.coslat32 = _ptr(self.coslat32, c_f32p)
         self.c = g
 
@@ -358,6 +360,22 @@ class OracleParticle:
             self.dx = np.cos(by * np.pi / 180) * DEG2M * dxd
             self.dy = DEG2M * dyd
             self.cs, self.sn = np.ones(n), np.zeros(n)
+            self.px, self.py = np.zeros((4, n)), np.zeros((4, n))
+        elif g.readiness["h"] == "local_cartesian":
+            # reference find_rel_h_naive, utils.py:577 (find_rx_ry_naive :522 is compiled: float64 cosine)
+            ind = g.find_ind_h(self.lon, self.lat)
+            if g.has_face:
+                self.face, self.iy, self.ix = (np.ascontiguousarray(a, np.int32) for a in ind)
+            else:
+                self.face = np.zeros(n, np.int32)
+                self.iy, self.ix = (np.ascontiguousarray(a, np.int32) for a in ind)
+            self.bx, self.by = g.XC[ind].astype(float), g.YC[ind].astype(float)
+            self.cs, self.sn = g.CS[ind].astype(float), g.SN[ind].astype(float)
+            self.dx, self.dy = g.dX[ind].astype(float), g.dY[ind].astype(float)
+            dlon, dlat = to_180(self.lon - self.bx), to_180(self.lat - self.by)
+            cosby = np.cos(self.by * np.pi / 180)
+            self.rx = (dlon * cosby * self.cs + dlat * self.sn) * DEG2M / self.dx
+            self.ry = (dlat * self.cs - dlon * self.sn * cosby) * DEG2M / self.dy
             self.px, self.py = np.zeros((4, n)), np.zeros((4, n))
         else:
             self._init_h_oceanparcel(g, n)

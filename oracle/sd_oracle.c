@@ -758,6 +758,16 @@ static void advect_one(const ora_grid *g, const ora_vel *vel, ora_particles *p, 
             p->bx[i] = (double)g->XC[hidx];
             p->by[i] = (double)g->YC[hidx];
             if (read_corners(g, p, i)) p->status[i] |= 2;
+        } else if (g->hmode == ORA_H_LOCAL_CARTESIAN) { /* :647-659 */
+            int64_t hidx = ((int64_t)(g->has_face ? p->face[i] : 0) * g->ny + wrap(p->iy[i], g->ny)) *
+                               g->nx + wrap(p->ix[i], g->nx);
+            p->bx[i] = (double)g->XC[hidx];
+            p->by[i] = (double)g->YC[hidx];
+            p->cs[i] = (double)g->CS[hidx];
+            p->sn[i] = (double)g->SN[hidx];
+            p->dx[i] = (double)g->dX[hidx];
+            p->dy[i] = (double)g->dY[hidx];
+            cos_by32 = (double)g->coslat32[hidx]; /* per cell here: np.cos(YC * np.pi / 180) in float32 */
         } else if (g->hmode == ORA_H_RECTILINEAR) { /* :667-672 */
             int ix = wrap(p->ix[i], g->nx), iy = wrap(p->iy[i], g->ny);
             p->bx[i] = (double)g->lon[ix];
@@ -911,7 +921,6 @@ int ora_four_matrix_for_uv(const ora_grid *g, int64_t n, int m, const int32_t *f
 
 int ora_advect(const ora_grid *g, const ora_vel *vel, ora_particles *p, double t_stop,
                const ora_params *par, ora_log *log) {
-    if (g->hmode == ORA_H_LOCAL_CARTESIAN) return -1; /* not restated */
     int nthreads = par->nthreads > 0 ? par->nthreads : 1;
     if (nthreads == 1) {
         for (int64_t i = 0; i < p->n; ++i) advect_one(g, vel, p, i, t_stop, par, log);

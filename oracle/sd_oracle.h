@@ -32,8 +32,9 @@ typedef struct {
     const float *Zl, *dZl, *Z, *dZ;
     const float *lon, *lat; /* rectilinear */
     const double *dlon, *dlat;
-    /* rectilinear: np.cos(lat * np.pi / 180) of the float32 lat array as the host's numpy evaluates it in float32
-     * (lagrangian.py:671, :693-703 take the cosine of a float32 latitude; its last bit is numpy's, so it is data) */
+    /* np.cos(lat * np.pi / 180) of the float32 latitudes as the host's numpy evaluates it in float32: per row of
+     * `lat` (rectilinear) or per cell of `YC` (local_cartesian).  lagrangian.py:671, :693-703 take the cosine of a
+     * float32 latitude; its last bit is numpy's, so it is data */
     const float *coslat32;
 } ora_grid;
 

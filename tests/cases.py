@@ -149,8 +149,27 @@ def case_rectilinear(n=300):
     )
 
 
-# cases the CPU oracle is pinned on but the device path does not take yet (sdk_locate raises for this scheme)
-ORACLE_ONLY_CASES = [case_rectilinear]
+def case_local_cartesian(n=300, ngrid=24, nz=6):
+    """The LLC grid without its corner coordinates (XG, YG): the `local_cartesian` horizontal scheme
+    (reference ocedata.py:252, utils.py:577, lagrangian.py:647-659, :693-703)."""
+    from seaduck_b200 import minixr  # noqa: PLC0415
+
+    full = synthetic.llc(n=ngrid, nz=nz)
+    keep = {k: (tuple(full[k].dims), np.asarray(full[k])) for k in full.variables if k not in ("XG", "YG")}
+    dims = {d for dd, _ in keep.values() for d in dd}
+    ds = minixr.Dataset(coords={k: v for k, v in keep.items() if k in dims}, data_vars={k: v for k, v in keep.items() if k not in dims})
+    lon, lat, dep = synthetic.llc_seed_particles(full, n, seed=8, depth_range=(5, 300))
+    return dict(
+        name="local_cartesian",
+        ds=ds,
+        x=lon, y=lat, z=dep, t=np.zeros(n),
+        stops=[25 * DAY, -15 * DAY],
+        kw=dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True),
+    )
+
+
+# cases the CPU oracle is pinned on but the device path does not take yet (sdk_locate raises for these schemes)
+ORACLE_ONLY_CASES = [case_rectilinear, case_local_cartesian]
 
 ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_bool_array, case_llc_callback, case_channel_kickback]
 
