@@ -71,15 +71,31 @@ class OraclePosition:
         self.face = self.iy = self.ix = self.rx = self.ry = self.cs = self.sn = None
         if x is not None and y is not None:
             self.lon, self.lat = np.asarray(x, float), np.asarray(y, float)
-            ind = og.find_ind_h(self.lon, self.lat)
-            if og.has_face:
-                self.face, self.iy, self.ix = (np.asarray(a, np.int64) for a in ind)
+            if og.readiness["h"] == "rectilinear":
+                # find_rel_h_rectilinear, utils.py:602: two periodic 1-D lookups, grid aligned with the meridians
+                ix, self.rx, _, _ = ora.find_rel(self.lon, og.lon, peri=360.0)
+                iy, self.ry, _, _ = ora.find_rel(self.lat, og.lat, peri=360.0)
+                self.iy, self.ix = np.asarray(iy, np.int64), np.asarray(ix, np.int64)
+                self.cs, self.sn = np.ones_like(self.lon), np.zeros_like(self.lon)
             else:
-                self.iy, self.ix = (np.asarray(a, np.int64) for a in ind)
-            px, py = og.px_py(ind, self.lon)
-            self.rx, self.ry = ora.find_rx_ry_oceanparcel(self.lon, self.lat, px, py)
-            if og.CS is not None:
-                self.cs, self.sn = og.CS[ind], og.SN[ind]
+                ind = og.find_ind_h(self.lon, self.lat)
+                if og.has_face:
+                    self.face, self.iy, self.ix = (np.asarray(a, np.int64) for a in ind)
+                else:
+                    self.iy, self.ix = (np.asarray(a, np.int64) for a in ind)
+                if og.readiness["h"] == "local_cartesian":
+                    # find_rel_h_naive, utils.py:577 (find_rx_ry_naive :522 is compiled: float64 cosine of a float32 YC)
+                    bx, by = og.XC[ind].astype(float), og.YC[ind].astype(float)
+                    cs, sn = og.CS[ind].astype(float), og.SN[ind].astype(float)
+                    dlon, dlat = ora.to_180(self.lon - bx), ora.to_180(self.lat - by)
+                    cosby = np.cos(by * np.pi / 180)
+                    self.rx = (dlon * cosby * cs + dlat * sn) * ora.DEG2M / og.dX[ind].astype(float)
+                    self.ry = (dlat * cs - dlon * sn * cosby) * ora.DEG2M / og.dY[ind].astype(float)
+                else:
+                    px, py = og.px_py(ind, self.lon)
+                    self.rx, self.ry = ora.find_rx_ry_oceanparcel(self.lon, self.lat, px, py)
+                if og.CS is not None:
+                    self.cs, self.sn = og.CS[ind], og.SN[ind]
         self.dep = None if z is None else np.asarray(z, float)
         self.t = None if t is None else np.asarray(t, float)
         rd = og.readiness

@@ -136,7 +136,7 @@ def main():
     gold = os.path.join(ROOT, "tests", "golden")
     os.makedirs(gold, exist_ok=True)
     only = sys.argv[1:]
-    for make in ci.ALL_CASES:
+    for make in ci.ALL_CASES + ci.ORACLE_ONLY_CASES:
         case = make()
         if only and case["name"] not in only:
             continue

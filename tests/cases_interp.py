@@ -160,7 +160,42 @@ def case_overturning(n=500):
     return dict(name="overturning", ds=ds, x=x, y=np.zeros(n), z=z, t=None, jobs=jobs, reach=0)
 
 
+def case_rectilinear(n=500):
+    """1-D lon / lat grid (altimetry-like, x-periodic), unstaggered u, v in m/s: the `rectilinear` horizontal scheme."""
+    ds = synthetic.rectilinear(nlat=40, nlon=80, nt=3)
+    rng = np.random.RandomState(33)
+    x = rng.uniform(-179.9, 179.9, n)
+    y = rng.uniform(-70.0, 70.0, n)
+    t = rng.uniform(0.0, 9.5 * DAY, n)
+    jobs = [
+        ("u_cross", "u", dict(ignore_mask=True), True),
+        ("u_lin_t", "u", dict(ignore_mask=True, tkernel="linear"), True),
+        ("v_dx", "v", dict(kernel="cross5", inheritance=[[0, 1, 2, 3, 4]], hkernel="dx", h_order=1, ignore_mask=True), True),
+        ("uv_vector", ("u", "v"), (dict(ignore_mask=True), dict(ignore_mask=True)), True),
+    ]
+    return dict(name="rectilinear", ds=ds, x=x, y=y, z=None, t=t, jobs=jobs, reach=2)
+
+
+def case_local_cartesian(n=500, ngrid=24, nz=6):
+    """The LLC grid without XG, YG: the `local_cartesian` horizontal scheme for locating; the stencils are the same."""
+    from seaduck_b200 import minixr  # noqa: PLC0415
+
+    full = synthetic.llc(n=ngrid, nz=nz, tracers=True)
+    keep = {k: (tuple(full[k].dims), np.asarray(full[k])) for k in full.variables if k not in ("XG", "YG")}
+    dims = {d for dd, _ in keep.values() for d in dd}
+    ds = minixr.Dataset(coords={k: v for k, v in keep.items() if k in dims}, data_vars={k: v for k, v in keep.items() if k not in dims})
+    lon, lat, _ = synthetic.llc_seed_particles(full, n, seed=34, lat_range=(-70.0, 85.0))
+    z = -np.random.RandomState(35).uniform(5.0, 600.0, n)
+    jobs = [
+        ("T_masked", "T", {}, True),
+        ("uv_particle", ("UVELMASS", "VVELMASS"), (UKNW, VKNW), True),
+    ]
+    return dict(name="local_cartesian", ds=ds, x=lon, y=lat, z=z, t=None, jobs=jobs, reach=2)
+
+
 ALL_CASES = [case_llc3d, case_llc3d_square, case_llc2d, case_gyre, case_overturning]
+# pinned on the oracle only: the device path does not take these horizontal schemes yet
+ORACLE_ONLY_CASES = [case_rectilinear, case_local_cartesian]
 
 
 def flatten_result(res):

@@ -23,7 +23,7 @@ def _setup(case, gold):
     return sd, io, od, pos
 
 
-@pytest.mark.parametrize("make", ci.ALL_CASES, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("make", ci.ALL_CASES + ci.ORACLE_ONLY_CASES, ids=lambda f: f.__name__)
 def test_oracle_position_matches_reference(make, oracle_lib):
     case = make()
     gold = np.load(os.path.join(GOLD, f"interp_{case['name']}.npz"))
@@ -42,7 +42,7 @@ def test_oracle_position_matches_reference(make, oracle_lib):
         ci.assert_values_close("rt_lin", pos.lin("t")[1], gold["pos_rt_lin"])
 
 
-@pytest.mark.parametrize("make", ci.ALL_CASES, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("make", ci.ALL_CASES + ci.ORACLE_ONLY_CASES, ids=lambda f: f.__name__)
 def test_oracle_interpolate_matches_reference(make, oracle_lib):
     case = make()
     gold = np.load(os.path.join(GOLD, f"interp_{case['name']}.npz"))
