@@ -431,7 +431,10 @@ def run_cuda(a):
                          "note": "instruction-supply bound, not bandwidth bound (DRAM 4.5 % busy, fields L2 resident, "
                                  "SM instruction cache hit rate 88 %, GPC instruction cache at 94 % of its request rate; the "
                                  "launch time follows the number of GPC instruction-cache requests): profiles/README.md r01k-r01m"},
-            "gpu_launches": a.steps * world,
+            # this package's kernels inside the timed region, per rank and step: advect_kernel (two passes with the
+            # crossing log: count, then fill) + finish_stop_kernel in lazy mode + pack_snapshot_kernel before the gather
+            "gpu_launches": a.steps * world * ((2 if a.save_raw else 1) + (0 if (a.eager or a.save_raw) else 1)
+                                               + (1 if (world > 1 and not a.no_gather) else 0)),
             "clocks": sampler.summary(),
         }
         if budget:
