@@ -109,3 +109,19 @@ def test_find_rel_known_answers(oracle_lib, value, array, darray, ascending, abo
     ixs, rxs, dxs, bxs = oracle_lib.find_rel(np.array([float(value)]), array, darray, ascending, above, peri, dx_right)
     assert rxs[0] == ans
     assert np.issubdtype(ixs.dtype, np.integer)
+
+
+def test_to_180_known_answers(oracle_lib):
+    """reference tests/test_utils.py:26-31"""
+    assert oracle_lib.to_180(365) == 5
+    assert abs(oracle_lib.to_180(-1e-20)) < 1e-10
+    # the wrap the particle loop relies on: a tiny negative difference rounds to 360 in the first modulo and
+    # the second one brings it to zero (utils.py:199)
+    assert oracle_lib.to_180(np.array([-1e-20, 180.0, -180.0, 540.0]))[0] == 0.0
+    np.testing.assert_array_equal(oracle_lib.to_180(np.array([180.0, -180.0, 540.0, 190.0])), [-180.0, -180.0, -180.0, -170.0])
+
+
+@pytest.mark.parametrize("lat,lon", [(0, 0), (45, 45), (50, 180)])  # reference tests/test_utils.py:41-51
+def test_spherical2cartesian_radius(oracle_lib, lat, lon):
+    x, y, z = oracle_lib.spherical2cartesian(lon, lat)
+    assert np.isclose(x**2 + y**2 + z**2, 6371.0**2)
