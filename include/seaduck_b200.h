@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SDK_ABI_VERSION 1
+#define SDK_ABI_VERSION 2
 
 enum { SDK_OK = 0, SDK_EINVAL = -1, SDK_ECUDA = -2, SDK_EUNSUPPORTED = -3, SDK_ENOMEM = -4 };
 
@@ -42,8 +42,11 @@ enum {
     /* sdk_locate: value outside the table, the reference raises "Value out of bound." (utils.py:301) */
     SDK_ST_OOB = 16,       /* depth below the last Zl level (linear Zl lookup) */
     SDK_ST_OOB_Z = 32,     /* depth below the last Z level (linear Z lookup, lazily used by interpolation) */
-    SDK_ST_OOB_T = 64      /* sdk_locate: time before the first level (linear time lookup, lazily used);
+    SDK_ST_OOB_T = 64,     /* sdk_locate: time before the first level (linear time lookup, lazily used);
                               sdk_advect: the particle's time level is outside the staged velocity slab */
+    SDK_ST_OOB_LEVEL = 128 /* sdk_advect: the particle left through the deepest staged level (non-zero vertical
+                              velocity at the bottom); the reference raises IndexError at Zl[izl_lin]
+                              (seaduck/lagrangian.py:675).  The particle is frozen on that wall. */
 };
 
 #define SDK_MAX_FACES 16
@@ -76,6 +79,18 @@ typedef struct sdk_grid_desc {
      * row (slot ix) and right column (slot nx+iy) of each face, -1 where the reference raises;
      * required when gny == ny or gnx == nx (reference find_px_py, seaduck/utils.py:495). */
     const int32_t *corner_tab;
+    /* rectilinear scheme (OceData.lon / lat / dlon / dlat, seaduck/ocedata.py:255-259, 368-370): the 1-D axes
+     * lon [nx], lat [ny] (float32, device) and their metric spacing dlon [nx], dlat [ny] (float64 values of
+     * np.gradient(axis) * 6371e3 * pi / 180, device).  XC / YC / XG / YG are not needed for this scheme. */
+    const float *lon, *lat;
+    const double *dlon, *dlat;
+    /* local_cartesian and rectilinear schemes: np.cos(by * np.pi / 180) as the HOST's numpy evaluates it for the
+     * float32 latitude of a cell (seaduck/lagrangian.py:671, :693-703 -- float32 arithmetic and numpy's float32
+     * cosine, which is not correctly rounded, so it is data, not something to recompute on the device):
+     * [nface*ny*nx] from YC (local_cartesian) or [ny] from lat (rectilinear), float32, device. */
+    const float *coslat32;
+    int32_t dlon_is_f32; /* the dataset's lon / lat are float32: dlon[ix] * cos is a float32 product (numpy promotion) */
+    int32_t reserved2;
 } sdk_grid_desc;
 
 /* Velocity (or transport) snapshot slab; replaces Particle.update_uvw_array's uarray/varray/warray
@@ -97,7 +112,11 @@ typedef struct sdk_velocity {
 
 /* Particle state, structure of arrays, DEVICE pointers, n entries each (px, py: 4*n, corner-major).
  * Replaces the attributes of Particle / RelCoord that the time loop touches
- * (seaduck/lagrangian.py:56, seaduck/ocedata.py:119-143). */
+ * (seaduck/lagrangian.py:56, seaduck/ocedata.py:119-143).
+ * px / py hold the horizontal description of the particle's cell: in the oceanparcel scheme the longitudes /
+ * latitudes of its four corners (LL, LR, UR, UL); in the local_cartesian and rectilinear schemes, which have
+ * no corners, rows 0..2 of px are bx, cs, dx and rows 0..2 of py are by, sn, dy as float64 (row 3 unused) --
+ * the attributes the reference refreshes in _cross_cell_wall_read (seaduck/lagrangian.py:647-673). */
 typedef struct sdk_particles {
     int64_t n;
     double *lon, *lat, *dep, *t;
@@ -205,7 +224,9 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
                    void *scratch, void *stream);
 
 /* Output of sdk_locate: DEVICE pointers, n entries each (px, py: 4*n).  NULL members are skipped.
- * Mirrors the RelCoord families of the reference (seaduck/ocedata.py:119-143). */
+ * Mirrors the RelCoord families of the reference (seaduck/ocedata.py:119-143).  px / py as in
+ * sdk_particles (corners, or bx, cs, dx / by, sn, dy in float64 for the schemes without corners: the
+ * rectilinear dx, dy = cos(by) * deg2m * spacing are float64 in the reference, seaduck/utils.py:602). */
 typedef struct sdk_located {
     int32_t *face, *iy, *ix;
     double *rx, *ry;

@@ -45,7 +45,8 @@ class GridDesc(C.Structure):
     _fields_ = _fields(
         [
             (C.c_int32, "typ has_face nface ny nx gny gnx hmode n_zl n_z n_zc reserved"),
-            (vp, "nbr_face nbr_edge XC YC XG YG dX dY CS SN Zl dZl Z dZ corner_tab"),
+            (vp, "nbr_face nbr_edge XC YC XG YG dX dY CS SN Zl dZl Z dZ corner_tab lon lat dlon dlat coslat32"),
+            (C.c_int32, "dlon_is_f32 reserved2"),
         ]
     )
 

@@ -97,7 +97,12 @@ __host__ __device__ inline size_t advect_smem_bytes(int n_zl, int n_z, int threa
 #ifndef SDK_ADVECT_PROFILES
 #define SDK_ADVECT_PROFILES 1
 #endif
+// Profile 2 is profile 0 for the horizontal schemes without corner points (local_cartesian, rectilinear:
+// reference lagrangian.py:647-673, :693-704 and rel2latlon utils.py:214): px / py carry bx, cs, dx / by, sn, dy.
 #define SDK_KNOWN(P, fixed_value, runtime_expr) ((P) == 1 ? (fixed_value) : (runtime_expr))
+
+// sic: lagrangian.py:22, utils.py:306 (6271 km)
+#define SDK_DEG2M (6271e3 * 3.141592653589793 / 180)
 
 template <int P = 0>
 __device__ __forceinline__ void load_lane(const sdk_particles &p, int64_t i, int has_dep, Lane &s) {
@@ -299,8 +304,9 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
     double du = ul_ * -1.0 + ur_;
     double vv = vl_ * wy0 + vr_ * wy1;
     double dv = vl_ * -1.0 + vr_;
-    const double sx = k_tr ? s.vol : (double)s.dx;
-    const double sy = k_tr ? s.vol : (double)s.dy;
+    // (schemes without corners keep dx, dy as float64 in px[2], py[2]: the rectilinear ones are not float32 values)
+    const double sx = k_tr ? s.vol : (P == 2 ? s.px[2] : (double)s.dx);
+    const double sy = k_tr ? s.vol : (P == 2 ? s.py[2] : (double)s.dy);
     const double sz = k_tr ? s.vol : s.dzl;
     double w = 0.0, dw = 0.0;
     if (k_w) {
@@ -447,7 +453,17 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
     }
     // _sync_latlondep_before_cross, lagrangian.py:539
     if (has_dep) s.dep = s.bzl + s.dzl * s.rzl;
-    {
+    if (P == 2) {
+        // rel2latlon, utils.py:214 (no px / py on the particle: lagrangian.py:549).  numba compiles it, so the
+        // cosine of the float32 latitude is taken in double precision.
+        const double bx = s.px[0], cs = s.px[1], dxm = s.px[2], by = s.py[0], sn = s.py[1], dym = s.py[2];
+        const double temp_x = s.rx * dxm / SDK_DEG2M;
+        const double temp_y = s.ry * dym / SDK_DEG2M;
+        const double dlon = (temp_x * cs - temp_y * sn) / cos(by * 3.141592653589793 / 180);
+        const double dlat = temp_x * sn + temp_y * cs;
+        s.lon = dlon + bx;
+        s.lat = dlat + by;
+    } else {
         const double w0 = (0.5 - s.rx) * (0.5 - s.ry), w1 = (0.5 + s.rx) * (0.5 - s.ry);
         const double w2 = (0.5 + s.rx) * (0.5 + s.ry), w3 = (0.5 - s.rx) * (0.5 + s.ry);
         s.lon = ((w0 * s.px[0] + w1 * s.px[1]) + w2 * s.px[2]) + w3 * s.px[3];
@@ -467,18 +483,43 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
         }
     } else if (tend == 4) {
         s.izl += 1;
+        if (SDK_UNLIKELY(s.izl > g.n_zl - 1)) {
+            // through the deepest staged level (a non-zero vertical velocity at the bottom): the reference
+            // raises IndexError at Zl[izl_lin], lagrangian.py:675; freeze the particle on that wall
+            s.izl = g.n_zl - 1;
+            s.status |= SDK_ST_OOB_LEVEL;
+            live = false;
+            return;
+        }
     } else if (tend == 5) {
         if (!a.kick_back || s.izl != 1) s.izl -= 1;
         else s.dep = s.bzl + s.dzl / 2;
     }
-    // _cross_cell_wall_read, lagrangian.py:640 (oceanparcel branch): corners, vertical levels
+    // _cross_cell_wall_read, lagrangian.py:640: corners (oceanparcel) or centre + metric (other schemes), vertical levels
     int64_t c[4];
-    s.status |= corner_indices(g, s.f, s.iy, s.ix, c);
     float gx[4], gy[4];
+    float l_cs = 1.f, l_sn = 0.f, l_dx = 1.f, l_dy = 1.f, l_cos = 1.f, l_bx = 0.f, l_by = 0.f;
+    double l_dlon = 1.0, l_dlat = 1.0;
+    if (P == 2) {
+        if (g.hmode == SDK_H_LOCAL_CARTESIAN) {  // :647-659
+            const int64_t h = ((int64_t)s.f * g.ny + wrap_index(s.iy, g.ny)) * g.nx + wrap_index(s.ix, g.nx);
+            l_bx = __ldg(g.XC + h), l_by = __ldg(g.YC + h);
+            l_cs = __ldg(g.CS + h), l_sn = __ldg(g.SN + h);
+            l_dx = __ldg(g.dX + h), l_dy = __ldg(g.dY + h);
+            l_cos = __ldg(g.coslat32 + h);
+        } else {  // rectilinear, :667-672
+            const int ix = wrap_index(s.ix, g.nx), iy = wrap_index(s.iy, g.ny);
+            l_bx = __ldg(g.lon1 + ix), l_by = __ldg(g.lat1 + iy);
+            l_cos = __ldg(g.coslat32 + iy);
+            l_dlon = __ldg(g.dlon + ix), l_dlat = __ldg(g.dlat + iy);
+        }
+    } else {
+        s.status |= corner_indices(g, s.f, s.iy, s.ix, c);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        gx[j] = __ldg(g.XG + c[j]);
-        gy[j] = __ldg(g.YG + c[j]);
+        for (int j = 0; j < 4; ++j) {
+            gx[j] = __ldg(g.XG + c[j]);
+            gy[j] = __ldg(g.YG + c[j]);
+        }
     }
     if (has_dep) {
         s.bzl = (double)sZl[wrap_index(s.izl, g.n_zl)];
@@ -486,7 +527,26 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
         // _cross_cell_wall_rel, lagrangian.py:681
         s.rzl = div_maybe_zero(s.dep - s.bzl, s.dzl);
     }
-    {
+    if (P == 2) {
+        double dxm, dym;
+        if (g.hmode == SDK_H_LOCAL_CARTESIAN) {
+            dxm = (double)l_dx, dym = (double)l_dy;
+        } else {
+            // dlon[ix] * np.cos(by * np.pi / 180): float64 spacing times the float32 cosine (a float32 product
+            // when the dataset's lon is float32 itself)
+            dxm = g.dlon_is_f32 ? (double)((float)l_dlon * l_cos) : l_dlon * (double)l_cos;
+            dym = l_dlat;
+        }
+        const double bx = (double)l_bx, by = (double)l_by, cs = (double)l_cs, sn = (double)l_sn, cb = (double)l_cos;
+        s.px[0] = bx, s.px[1] = cs, s.px[2] = dxm;
+        s.py[0] = by, s.py[1] = sn, s.py[2] = dym;
+        // _cross_cell_wall_rel, lagrangian.py:693-703 (plain numpy there: by is the float32 array just read,
+        // so its cosine is numpy's float32 one -- the host-made table)
+        const double dlon = to_180(s.lon - bx);
+        const double dlat = to_180(s.lat - by);
+        s.rx = (dlon * cb * cs + dlat * sn) * SDK_DEG2M / dxm;
+        s.ry = (dlat * cs - dlon * sn * cb) * SDK_DEG2M / dym;
+    } else {
         bool redo = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -680,7 +740,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
 }
 
 // get_u_du on its own (after Particle.update_uvw_array swapped the velocity slab)
-template <typename T>
+template <typename T, int P>
 __global__ void __launch_bounds__(128) get_u_du_kernel(const __grid_constant__ AdvectArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.p.n) return;
@@ -689,18 +749,16 @@ __global__ void __launch_bounds__(128) get_u_du_kernel(const __grid_constant__ A
     int *cold_i = reinterpret_cast<int *>(cold_d - threadIdx.x + kColdDoubles * blockDim.x) + threadIdx.x;
     (void)cold_i;
     SDK_LANE(s, cold_d, cold_i, (int)blockDim.x);
-    load_lane(a.p, i, a.has_dep, s);
-    if (a.has_dep) {
-        // keep dzl as stored; only the velocities change
-    }
-    read_velocity<T>(a.g, a.v, a.has_dep, s);
+    load_lane<P>(a.p, i, a.has_dep, s);
+    read_velocity<T, P>(a.g, a.v, a.has_dep, s);
     a.p.u[i] = s.u;
     a.p.v[i] = s.v;
     a.p.du[i] = s.du;
     a.p.dv[i] = s.dv;
-    if (a.has_dep && a.v.has_w) {
-        a.p.w[i] = s.w;
-        a.p.dw[i] = s.dw;
+    if (a.has_dep) {
+        // no vertical velocity field (wname=None): w = dw = 0 like the reference's zero arrays
+        a.p.w[i] = a.v.has_w ? s.w : 0.0;
+        a.p.dw[i] = a.v.has_w ? s.dw : 0.0;
     }
     if (a.p.vol && a.v.transport) a.p.vol[i] = s.vol;
 }
@@ -720,10 +778,13 @@ cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaS
     const size_t smem = advect_smem_bytes(args.g.n_zl, args.g.n_z, threads);
     const bool f32 = args.v.dtype == SDK_F32;
     // profile 1: what the folded switches of the specialised kernel assume
-    const bool p1 = SDK_ADVECT_PROFILES && args.g.has_face && args.g.typ == SDK_TYP_LLC && args.has_dep && args.v.has_w &&
+    const bool p1 = SDK_ADVECT_PROFILES && args.g.hmode == SDK_H_OCEANPARCEL && args.g.has_face && args.g.typ == SDK_TYP_LLC && args.has_dep && args.v.has_w &&
                     args.v.transport && args.v.has_z && args.v.vol_has_z && args.p.face && args.p.vol;
     void (*kern)(AdvectArgs);
-    if (args.has_log) {
+    if (args.g.hmode != SDK_H_OCEANPARCEL) {
+        if (args.has_log) kern = f32 ? advect_kernel<float, true, 2> : advect_kernel<double, true, 2>;
+        else kern = f32 ? advect_kernel<float, false, 2> : advect_kernel<double, false, 2>;
+    } else if (args.has_log) {
         if (f32) kern = p1 ? advect_kernel<float, true, 1> : advect_kernel<float, true, 0>;
         else kern = p1 ? advect_kernel<double, true, 1> : advect_kernel<double, true, 0>;
     } else {
@@ -743,8 +804,14 @@ cudaError_t launch_get_u_du(const AdvectArgs &args, cudaStream_t stream) {
     const int blocks = (int)((args.p.n + threads - 1) / threads);
     if (blocks == 0) return cudaSuccess;
     const size_t smem = advect_smem_bytes(0, 0, threads);
-    if (args.v.dtype == SDK_F32) get_u_du_kernel<float><<<blocks, threads, smem, stream>>>(args);
-    else get_u_du_kernel<double><<<blocks, threads, smem, stream>>>(args);
+    const bool local = args.g.hmode != SDK_H_OCEANPARCEL;
+    if (args.v.dtype == SDK_F32) {
+        if (local) get_u_du_kernel<float, 2><<<blocks, threads, smem, stream>>>(args);
+        else get_u_du_kernel<float, 0><<<blocks, threads, smem, stream>>>(args);
+    } else {
+        if (local) get_u_du_kernel<double, 2><<<blocks, threads, smem, stream>>>(args);
+        else get_u_du_kernel<double, 0><<<blocks, threads, smem, stream>>>(args);
+    }
     return cudaGetLastError();
 }
 

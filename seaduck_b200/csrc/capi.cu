@@ -77,7 +77,13 @@ int sdk_grid_create(const sdk_grid_desc *d, sdk_grid **out) {
     if (d->nface < 1 || d->nface > SDK_MAX_FACES) return fail(SDK_EINVAL, "sdk_grid_create: nface out of range");
     if (d->typ == SDK_TYP_LLC && (!d->nbr_face || !d->nbr_edge))
         return fail(SDK_EINVAL, "sdk_grid_create: LLC grids need the face tables");
-    if (!d->XC || !d->YC) return fail(SDK_EINVAL, "sdk_grid_create: XC / YC missing");
+    if (d->hmode < SDK_H_OCEANPARCEL || d->hmode > SDK_H_RECTILINEAR) return fail(SDK_EINVAL, "sdk_grid_create: unknown horizontal scheme");
+    if (d->hmode != SDK_H_RECTILINEAR && (!d->XC || !d->YC)) return fail(SDK_EINVAL, "sdk_grid_create: XC / YC missing");
+    if (d->hmode == SDK_H_RECTILINEAR && (!d->lon || !d->lat || !d->dlon || !d->dlat || !d->coslat32))
+        return fail(SDK_EINVAL, "sdk_grid_create: the rectilinear scheme needs lon, lat, dlon, dlat and the cosine table");
+    if (d->hmode == SDK_H_RECTILINEAR && d->has_face) return fail(SDK_EINVAL, "sdk_grid_create: a rectilinear grid has no faces");
+    if (d->hmode == SDK_H_LOCAL_CARTESIAN && (!d->dX || !d->dY || !d->CS || !d->SN || !d->coslat32))
+        return fail(SDK_EINVAL, "sdk_grid_create: the local_cartesian scheme needs dX, dY, CS, SN and the cosine table");
     if (d->hmode == SDK_H_OCEANPARCEL && (!d->XG || !d->YG))
         return fail(SDK_EINVAL, "sdk_grid_create: oceanparcel scheme needs XG / YG");
     if (d->hmode == SDK_H_OCEANPARCEL && (d->gny <= d->ny || d->gnx <= d->nx) && !d->corner_tab)
@@ -114,6 +120,9 @@ int sdk_grid_create(const sdk_grid_desc *d, sdk_grid **out) {
     v.dX = d->dX; v.dY = d->dY; v.CS = d->CS; v.SN = d->SN;
     v.Zl = d->Zl; v.dZl = d->dZl; v.Z = d->Z; v.dZ = d->dZ;
     v.corner_tab = d->corner_tab;
+    v.lon1 = d->lon; v.lat1 = d->lat; v.dlon = d->dlon; v.dlat = d->dlat;
+    v.coslat32 = d->coslat32;
+    v.dlon_is_f32 = d->dlon_is_f32;
     g->sm_count = sdk_sm_count();
     if (g->sm_count <= 0) {
         delete g;
@@ -146,8 +155,6 @@ int sdk_grid_destroy(sdk_grid *g) {
 static int fill_args(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, double t_stop,
                      const sdk_advect_params *par, const sdk_log *log, int commit, sdk::AdvectArgs &a) {
     if (!grid || !vel || !p) return fail(SDK_EINVAL, "null argument");
-    if (grid->dev.hmode != SDK_H_OCEANPARCEL)
-        return fail(SDK_EUNSUPPORTED, "only the oceanparcel horizontal scheme is implemented on the device");
     if (!vel->U || !vel->V) return fail(SDK_EINVAL, "velocity arrays missing");
     if (vel->transport && !vel->Vol) return fail(SDK_EINVAL, "transport mode needs Vol");
     if (vel->dtype != SDK_F64 && vel->dtype != SDK_F32) return fail(SDK_EINVAL, "bad velocity dtype");
@@ -161,7 +168,8 @@ static int fill_args(const sdk_grid *grid, const sdk_velocity *vel, const sdk_pa
         if (has_dep && (!p->dep || !p->rzl || !p->w || !p->dw || !p->bzl || !p->dzl || !p->izl))
             return fail(SDK_EINVAL, "vertical state arrays missing");
         if (has_dep && grid->dev.n_zl == 0) return fail(SDK_EINVAL, "particles have depth but the grid has no Zl");
-        if (!vel->transport && (!p->dx || !p->dy)) return fail(SDK_EINVAL, "dx / dy missing (velocity mode)");
+        if (!vel->transport && grid->dev.hmode == SDK_H_OCEANPARCEL && (!p->dx || !p->dy))
+            return fail(SDK_EINVAL, "dx / dy missing (velocity mode)");
         if (vel->has_time && !p->it) return fail(SDK_EINVAL, "time index array missing");
     }
     a.g = grid->dev;
@@ -236,6 +244,7 @@ int sdk_get_u_du(const sdk_grid *grid, const sdk_velocity *vel, const sdk_partic
 int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span_lon, double span_lat,
                            int32_t nlon, int32_t nlat, void *stream) {
     if (!grid) return fail(SDK_EINVAL, "sdk_grid_build_locator: null grid");
+    if (grid->dev.hmode == SDK_H_RECTILINEAR) return SDK_OK;  // two 1-D searches: nothing to build
     if (nlon < 1 || nlat < 1 || !(span_lon > 0) || !(span_lat > 0))
         return fail(SDK_EINVAL, "sdk_grid_build_locator: bad bucket geometry");
     if (grid->has_buckets) {
@@ -265,9 +274,7 @@ int sdk_locate(const sdk_grid *grid, int64_t n, const double *lon, const double 
     if (n < 0) return fail(SDK_EINVAL, "sdk_locate: negative count");
     if ((lon == nullptr) != (lat == nullptr)) return fail(SDK_EINVAL, "sdk_locate: lon and lat go together");
     if (lon) {
-        if (grid->dev.hmode != SDK_H_OCEANPARCEL)
-            return fail(SDK_EUNSUPPORTED, "sdk_locate: only the oceanparcel horizontal scheme is implemented");
-        if (!grid->has_buckets) return fail(SDK_EINVAL, "sdk_locate: call sdk_grid_build_locator first");
+        if (grid->dev.hmode != SDK_H_RECTILINEAR && !grid->has_buckets) return fail(SDK_EINVAL, "sdk_locate: call sdk_grid_build_locator first");
         if (!out->iy || !out->ix || !out->rx || !out->ry) return fail(SDK_EINVAL, "sdk_locate: output arrays missing");
     }
     if (out->izl && (!out->rzl || !out->dzl || !out->bzl)) return fail(SDK_EINVAL, "sdk_locate: vertical output arrays missing");

@@ -156,6 +156,32 @@ __device__ __forceinline__ void find_rel_1d(const float *arr, const float *darr,
     b = bx;
 }
 
+// find_rel_periodic (utils.py:392 -> find_rel :321 with peri=360, find_ind :273) on a float32 axis: nearest node in
+// the periodic distance (first minimum, like np.argmin), spacing |diff(axis)| in float32 with the last value
+// repeated, taken to the right of the node when the point lies to its right, else to the left (numpy index
+// wrap-around for -1 included).
+__device__ __forceinline__ void find_rel_periodic(const float *arr, int n, double x, int &idx, double &r, double &d,
+                                                  double &b) {
+    int best = 0;
+    double bestv = INFINITY;
+    for (int k = 0; k < n; ++k) {
+        const double a = fabs(to_180((double)__ldg(arr + k) - x));
+        if (a < bestv) {
+            bestv = a;
+            best = k;
+        }
+    }
+    const double bx = (double)__ldg(arr + best);
+    const double dx = to_180(x - bx);
+    int j = wrap_index(best + (int)(dx > 0) - 1, n);
+    const int jj = j < n - 1 ? j : n - 2;
+    const double dval = n > 1 ? (double)fabsf(__ldg(arr + jj + 1) - __ldg(arr + jj)) : 1.0;
+    idx = best;
+    r = dx / dval;
+    d = dval;
+    b = bx;
+}
+
 // same for float64 tables (time axes)
 __device__ __forceinline__ void find_rel_1d_f64(const double *arr, int n, double x, bool above, int &idx,
                                                 double &r, double &d, double &b, int &status) {
@@ -190,7 +216,31 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
     if (i >= a.n) return;
     const sdk_located &o = a.out;
     int status = 0;
-    if (a.lon && a.lat) {
+    if (a.lon && a.lat && g.hmode == SDK_H_RECTILINEAR) {
+        // find_rel_h_rectilinear, utils.py:602: two periodic 1-D lookups; dx = cos(by) * deg2m * spacing in float64
+        const double lon = a.lon[i], lat = a.lat[i];
+        int ix, iy;
+        double rx, ry, ddx, ddy, bx, by;
+        find_rel_periodic(g.lon1, g.nx, lon, ix, rx, ddx, bx);
+        find_rel_periodic(g.lat1, g.ny, lat, iy, ry, ddy, by);
+        const double deg2m = 6271e3 * 3.141592653589793 / 180;
+        const double dxm = cos(by * 3.141592653589793 / 180) * deg2m * ddx;
+        const double dym = deg2m * ddy;
+        o.iy[i] = iy;
+        o.ix[i] = ix;
+        o.rx[i] = rx;
+        o.ry[i] = ry;
+        if (o.bx) o.bx[i] = (float)bx;
+        if (o.by) o.by[i] = (float)by;
+        if (o.dx) o.dx[i] = (float)dxm;
+        if (o.dy) o.dy[i] = (float)dym;
+        if (o.cs) o.cs[i] = 1.f;
+        if (o.sn) o.sn[i] = 0.f;
+        if (o.px) {
+            o.px[0 * a.n + i] = bx, o.px[1 * a.n + i] = 1.0, o.px[2 * a.n + i] = dxm, o.px[3 * a.n + i] = 0.0;
+            o.py[0 * a.n + i] = by, o.py[1 * a.n + i] = 0.0, o.py[2 * a.n + i] = dym, o.py[3 * a.n + i] = 0.0;
+        }
+    } else if (a.lon && a.lat) {
         const double lon = a.lon[i], lat = a.lat[i];
         double qx, qy, qz;
         unit_vec(lon, lat, qx, qy, qz);
@@ -227,29 +277,47 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
         o.iy[i] = iy;
         o.ix[i] = ix;
         const int64_t c = ((int64_t)f * g.ny + iy) * g.nx + ix;
-        if (o.bx) o.bx[i] = __ldg(g.XC + c);
-        if (o.by) o.by[i] = __ldg(g.YC + c);
-        if (o.dx) o.dx[i] = g.dX ? __ldg(g.dX + c) : 0.f;
-        if (o.dy) o.dy[i] = g.dY ? __ldg(g.dY + c) : 0.f;
-        if (o.cs) o.cs[i] = g.CS ? __ldg(g.CS + c) : 1.f;
-        if (o.sn) o.sn[i] = g.SN ? __ldg(g.SN + c) : 0.f;
-        // corners + inverse bilinear map
-        int64_t cc[4];
-        status |= corner_indices(g, f, iy, ix, cc);
-        double px[4], py[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            px[j] = lon + to_180((double)__ldg(g.XG + cc[j]) - lon);
-            py[j] = (double)__ldg(g.YG + cc[j]);
+        const float cbx = __ldg(g.XC + c), cby = __ldg(g.YC + c);
+        const float cdx = g.dX ? __ldg(g.dX + c) : 0.f, cdy = g.dY ? __ldg(g.dY + c) : 0.f;
+        const float ccs = g.CS ? __ldg(g.CS + c) : 1.f, csn = g.SN ? __ldg(g.SN + c) : 0.f;
+        if (o.bx) o.bx[i] = cbx;
+        if (o.by) o.by[i] = cby;
+        if (o.dx) o.dx[i] = cdx;
+        if (o.dy) o.dy[i] = cdy;
+        if (o.cs) o.cs[i] = ccs;
+        if (o.sn) o.sn[i] = csn;
+        if (g.hmode == SDK_H_LOCAL_CARTESIAN) {
+            // find_rel_h_naive, utils.py:577 -> find_rx_ry_naive :522 (numba: the cosine of the float32 latitude in
+            // double precision)
+            const double bx = (double)cbx, by = (double)cby, cs = (double)ccs, sn = (double)csn;
+            const double deg2m = 6271e3 * 3.141592653589793 / 180;
+            const double dlon = to_180(lon - bx), dlat = to_180(lat - by);
+            const double cb = cos(by * 3.141592653589793 / 180);
+            o.rx[i] = (dlon * cb * cs + dlat * sn) * deg2m / (double)cdx;
+            o.ry[i] = (dlat * cs - dlon * sn * cb) * deg2m / (double)cdy;
             if (o.px) {
-                o.px[j * a.n + i] = px[j];
-                o.py[j * a.n + i] = py[j];
+                o.px[0 * a.n + i] = bx, o.px[1 * a.n + i] = cs, o.px[2 * a.n + i] = (double)cdx, o.px[3 * a.n + i] = 0.0;
+                o.py[0 * a.n + i] = by, o.py[1 * a.n + i] = sn, o.py[2 * a.n + i] = (double)cdy, o.py[3 * a.n + i] = 0.0;
             }
+        } else {
+            // corners + inverse bilinear map
+            int64_t cc[4];
+            status |= corner_indices(g, f, iy, ix, cc);
+            double px[4], py[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                px[j] = lon + to_180((double)__ldg(g.XG + cc[j]) - lon);
+                py[j] = (double)__ldg(g.YG + cc[j]);
+                if (o.px) {
+                    o.px[j * a.n + i] = px[j];
+                    o.py[j * a.n + i] = py[j];
+                }
+            }
+            double rx, ry;
+            inverse_bilinear(lon, lat, px, py, rx, ry);
+            o.rx[i] = rx;
+            o.ry[i] = ry;
         }
-        double rx, ry;
-        inverse_bilinear(lon, lat, px, py, rx, ry);
-        o.rx[i] = rx;
-        o.ry[i] = ry;
     }
     if (a.dep) {
         const double z = a.dep[i];

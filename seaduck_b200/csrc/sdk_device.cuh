@@ -25,6 +25,10 @@ struct GridDev {
     signed char nbr_edge[SDK_MAX_FACES * 4];
     const float *XC, *YC, *XG, *YG, *dX, *dY, *CS, *SN, *Zl, *dZl, *Z, *dZ;
     const int32_t *corner_tab;
+    // schemes without corner points (SDK_H_RECTILINEAR / SDK_H_LOCAL_CARTESIAN), see sdk_grid_desc
+    const float *lon1, *lat1, *coslat32;
+    const double *dlon, *dlat;
+    int dlon_is_f32;
 };
 
 struct VelDev {

@@ -122,10 +122,15 @@ class Position:
             vals = [npf(loc[k], np.int64) for k in ("iy", "ix")] + [
                 npf(loc[k]) for k in ("rx", "ry", "cs", "sn", "dx", "dy", "bx", "by")
             ]
-            if od.CS is None:
-                vals[4] = vals[5] = None
-            if od.dX is None:
-                vals[6] = vals[7] = None
+            if od.readiness["h"] == "rectilinear":
+                # find_rel_h_rectilinear (utils.py:602) returns float64 arrays throughout
+                for j in (4, 5, 8, 9):
+                    vals[j] = npf(vals[j].tensor, np.float64)
+            else:
+                if od.CS is None:
+                    vals[4] = vals[5] = None
+                if od.dX is None:
+                    vals[6] = vals[7] = None
             self.rel.update(HRel._make([face] + vals))
         else:
             self.rel.update(HRel._make([None for i in range(11)]))

@@ -161,7 +161,8 @@ class Particle(Position):
         st["iy"], st["ix"] = loc["iy"], loc["ix"]
         st["rx"], st["ry"] = loc["rx"], loc["ry"]
         st["px"], st["py"] = loc["px"], loc["py"]
-        st["dx"], st["dy"] = loc["dx"], loc["dy"]
+        # (schemes without corner points keep dx, dy as float64 rows of px / py)
+        st["dx"], st["dy"] = (None, None) if od.readiness["h"] != "oceanparcel" else (loc["dx"], loc["dy"])
         if self._has_dep:
             st["izl"], st["rzl"], st["dzl"], st["bzl"] = loc["izl"], loc["rzl"], loc["dzl"], loc["bzl"]
         else:
@@ -181,10 +182,9 @@ class Particle(Position):
         self.__dict__["_warned"] = 0
         self.__dict__["_stale"] = set()
         self.__dict__["_raw"] = []
-        if not od.readiness["h"] == "oceanparcel":
-            raise NotImplementedError("Particle: only the oceanparcel horizontal scheme runs on the GPU")
+        self.__dict__["_local_h"] = od.readiness["h"] != "oceanparcel"
         # host mirrors of what the constructor of the reference sets as float32 zeros
-        for name in ("u", "v", "w", "du", "dv", "dw", "vol", "px", "py"):
+        for name in ("u", "v", "w", "du", "dv", "dw", "vol") + (() if self._local_h else ("px", "py")):
             self._stale.add(name)
         for key in ("izl_lin", "rzl_lin", "dzl_lin", "bzl_lin"):
             if not self._has_dep and key not in self.rel:
@@ -204,6 +204,15 @@ class Particle(Position):
         """Refresh the host mirror of one attribute from the device."""
         dev_name, in_rel, dtype = _STATE[attr]
         t = self._st.get(dev_name)
+        if self._local_h and attr in ("px", "py", "dx", "dy"):
+            # schemes without corner points: no px / py on the particle (reference lagrangian.py:549), and the
+            # device keeps bx, cs, dx / by, sn, dy as float64 rows of the px / py arrays (include/seaduck_b200.h)
+            if attr in ("px", "py"):
+                self._stale.discard(attr)
+                raise AttributeError(attr)
+            n = self.N
+            t = self._st["px" if attr == "dx" else "py"][2 * n : 3 * n]
+            dtype = np.float64 if self.ocedata.readiness["h"] == "rectilinear" else np.float32
         if t is None:
             val = None
         else:
@@ -227,7 +236,9 @@ class Particle(Position):
                 continue
             if attr == "it" and not self.ocedata.readiness["time"]:
                 continue
-            if attr in ("dx", "dy") and self.ocedata.dX is None:
+            if attr in ("dx", "dy") and not self._local_h and self.ocedata.dX is None:
+                continue
+            if attr in ("px", "py") and self._local_h:
                 continue
             self._stale.add(attr)
             if not in_rel:
@@ -284,10 +295,18 @@ class Particle(Position):
         (the reference refreshes them in cross_cell_wall, lagrangian.py:640-686)."""
         od = self.ocedata
         self.__dict__["_derived_ok"] = True
-        face, iy, ix = self._rel_get("face"), self._rel_get("iy"), self._rel_get("ix")
-        ind = (face, iy, ix) if face is not None else (iy, ix)
-        self.rel["bx"] = od.XC[ind]
-        self.rel["by"] = od.YC[ind]
+        if self._local_h:
+            # bx, cs / by, sn follow the particle on the device (rows 0, 1 of px / py)
+            n = self.N
+            as32 = od.readiness["h"] == "local_cartesian"  # float32 table values there, float64 arrays in rectilinear
+            for key, (arr, row) in dict(bx=("px", 0), cs=("px", 1), by=("py", 0), sn=("py", 1)).items():
+                val = self._st[arr][row * n : (row + 1) * n].cpu().numpy()
+                self.rel[key] = val.astype(np.float32) if as32 else val
+        else:
+            face, iy, ix = self._rel_get("face"), self._rel_get("iy"), self._rel_get("ix")
+            ind = (face, iy, ix) if face is not None else (iy, ix)
+            self.rel["bx"] = od.XC[ind]
+            self.rel["by"] = od.YC[ind]
         # cs, sn keep the values of the starting cell: the reference only refreshes bx, by, px, py in the
         # oceanparcel scheme (_cross_cell_wall_read, lagrangian.py:660-665), and vec_transform uses them
         if self._has_dep:

@@ -337,11 +337,6 @@ class OceData:
         """Create (once) the device grid: uploads the float32 grid and the topology tables."""
         if self._grid_handle is not None:
             return self._grid_handle
-        if self.readiness["h"] != "oceanparcel":
-            raise NotImplementedError(
-                "the CUDA path implements the oceanparcel horizontal scheme (XC, YC, XG, YG); "
-                f"this dataset is '{self.readiness['h']}'"
-            )
         L = _lib.lib()
         tp = self.tp
         d = _lib.GridDesc()
@@ -362,6 +357,18 @@ class OceData:
             arr = getattr(self, name, None)
             if arr is not None:
                 setattr(d, name, self.to_device(name, arr, np.float32).data_ptr())
+        hmode = self.readiness["h"]
+        if hmode == "rectilinear":
+            # the 1-D axes, their metric spacing (ocedata.py:255-259) and numpy's float32 cosine of the float32
+            # latitudes, which Particle._cross_cell_wall_read / _rel evaluate (lagrangian.py:671, :693-703)
+            d.lon = self.to_device("lon", self.lon, np.float32).data_ptr()
+            d.lat = self.to_device("lat", self.lat, np.float32).data_ptr()
+            d.dlon_is_f32 = int(np.asarray(self.dlon).dtype == np.float32)
+            d.dlon = self.to_device("dlon", self.dlon, np.float64).data_ptr()
+            d.dlat = self.to_device("dlat", self.dlat, np.float64).data_ptr()
+            d.coslat32 = self.to_device("coslat32", self._coslat32(self.lat), np.float32).data_ptr()
+        elif hmode == "local_cartesian":
+            d.coslat32 = self.to_device("coslat32", self._coslat32(self.YC), np.float32).data_ptr()
         if self.readiness["Zl"]:
             d.n_zl = len(self.Zl)
             d.n_z = len(self.dZl)
@@ -371,7 +378,7 @@ class OceData:
             d.n_zc = len(self.Z)
             d.Z = self.to_device("Z", self.Z, np.float32).data_ptr()
             d.dZ = self.to_device("dZ", self.dZ, np.float32).data_ptr()
-        if d.gny <= d.ny or d.gnx <= d.nx:
+        if hmode == "oceanparcel" and (d.gny <= d.ny or d.gnx <= d.nx):
             d.corner_tab = self.to_device("corner_tab", self._corner_table(), np.int32).data_ptr()
         handle = C.c_void_p()
         _lib.check(L.sdk_grid_create(C.byref(d), C.byref(handle)), "sdk_grid_create")
@@ -379,6 +386,16 @@ class OceData:
         self._keep = keep
         self._build_locator()
         return handle
+
+    @staticmethod
+    def _coslat32(lat32):
+        """``np.cos(by * np.pi / 180)`` exactly as the reference's plain-numpy code gets it for a float32
+        latitude array (float32 product, quotient and cosine)."""
+        lat32 = np.asarray(lat32)
+        assert lat32.dtype == np.float32
+        out = np.cos(lat32 * np.pi / 180)
+        assert out.dtype == np.float32
+        return out
 
     def _corner_table(self):
         """Flat XG indices of the LR, UR, UL corners of the cells on the top row / right column."""
@@ -407,6 +424,8 @@ class OceData:
         return table.astype(np.int32)
 
     def _build_locator(self):
+        if self.readiness["h"] == "rectilinear":
+            return  # two 1-D searches on the device, nothing to build
         L = _lib.lib()
         xc = np.asarray(self.XC, np.float64)
         yc = np.asarray(self.YC, np.float64)
@@ -527,6 +546,9 @@ class OceData:
                 alloc(nme, torch.float32)
             alloc("px", torch.float64, 4)
             alloc("py", torch.float64, 4)
+            if self.readiness["h"] == "rectilinear":
+                # dx, dy = cos(by) * deg2m * spacing are float64 in the reference (utils.py:602): rows 2 of px / py
+                out["dx"], out["dy"] = out["px"][2 * n : 3 * n], out["py"][2 * n : 3 * n]
         if dz is not None:
             if self.readiness["Z"]:
                 alloc("iz", torch.int32)
@@ -571,10 +593,14 @@ class OceData:
         face = self._np(o["face"], np.int64) if "face" in o else None
         ints = [self._np(o[k], np.int64) for k in ("iy", "ix")]
         rest = [self._np(o[k]) for k in ("rx", "ry", "cs", "sn", "dx", "dy", "bx", "by")]
-        if self.CS is None:
-            rest[2] = rest[3] = None
-        if self.dX is None:
-            rest[4] = rest[5] = None
+        if self.readiness["h"] == "rectilinear":
+            rest[2], rest[3] = rest[2].astype(np.float64), rest[3].astype(np.float64)
+            rest[6], rest[7] = rest[6].astype(np.float64), rest[7].astype(np.float64)
+        else:
+            if self.CS is None:
+                rest[2] = rest[3] = None
+            if self.dX is None:
+                rest[4] = rest[5] = None
         return HRel._make([face] + ints + rest)
 
     def _find_rel_v(self, z):

@@ -168,10 +168,10 @@ def case_local_cartesian(n=300, ngrid=24, nz=6):
     )
 
 
-# cases the CPU oracle is pinned on but the device path does not take yet (sdk_locate raises for these schemes)
-ORACLE_ONLY_CASES = [case_rectilinear, case_local_cartesian]
+# cases only the CPU oracle takes (none: the device runs all three horizontal schemes)
+ORACLE_ONLY_CASES = []
 
-ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_bool_array, case_llc_callback, case_channel_kickback]
+ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_bool_array, case_llc_callback, case_channel_kickback, case_rectilinear, case_local_cartesian]
 
 LOG_INT = ["fc", "it", "izl", "iy", "ix", "vs"]
 LOG_FLT = ["rzl", "rx", "ry", "tt", "uu", "vv", "ww", "du", "dv", "dw", "xx", "yy", "zz"]

@@ -193,9 +193,9 @@ def case_local_cartesian(n=500, ngrid=24, nz=6):
     return dict(name="local_cartesian", ds=ds, x=lon, y=lat, z=z, t=None, jobs=jobs, reach=2)
 
 
-ALL_CASES = [case_llc3d, case_llc3d_square, case_llc2d, case_gyre, case_overturning]
-# pinned on the oracle only: the device path does not take these horizontal schemes yet
-ORACLE_ONLY_CASES = [case_rectilinear, case_local_cartesian]
+ALL_CASES = [case_llc3d, case_llc3d_square, case_llc2d, case_gyre, case_overturning, case_rectilinear, case_local_cartesian]
+# cases only the CPU oracle takes (none: the device runs all three horizontal schemes)
+ORACLE_ONLY_CASES = []
 
 
 def flatten_result(res):
