@@ -146,7 +146,9 @@ typedef struct sdk_advect_params {
      * -- the NCCL all-gather of the previous stop's snapshot -- run beside it; needs one CTA per SM
      * (blocks_per_sm = 1, threads_per_block = 512) to be exact */
     int32_t reserve_sms;
-    int32_t reserved;
+    /* != 0: the status array holds flags from an earlier stage (sdk_locate) that the call ORs its own into
+     * instead of overwriting them */
+    int32_t keep_status;
     /* optional DEVICE array of 4 counters, ADDED to by the call: particles live at the start,
      * wall crossings, particles that hit max_iteration, particles with a non-zero status */
     uint64_t *stats;
@@ -177,7 +179,8 @@ typedef struct sdk_log {
 int sdk_abi_version(void);
 /* sizeof() of the structures above as the library was compiled (binding self-check): 0 sdk_grid_desc,
  * 1 sdk_velocity, 2 sdk_particles, 3 sdk_advect_params, 4 sdk_log, 5 sdk_located, 6 sdk_track_io,
- * 7 sdk_kernel_desc, 8 sdk_field, 9 sdk_points, 10 sdk_budget_fields, 11 sdk_wall_fields; -1 for anything else */
+ * 7 sdk_kernel_desc, 8 sdk_field, 9 sdk_points, 10 sdk_budget_fields, 11 sdk_wall_fields, 12 sdk_snapshot_record,
+ * 13 sdk_exchange; -1 for anything else */
 int64_t sdk_struct_size(int which);
 const char *sdk_last_error(void);
 /* number of SMs of the current device (grid sizing), <0 on error */
@@ -205,6 +208,8 @@ int sdk_advect_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_par
                     double t_stop, const sdk_advect_params *par, void *scratch, void *stream);
 
 
+/* (sdk_snapshot_record is declared further down with the output-record entry points) */
+struct sdk_snapshot_record;
 /* Positions in, positions out, all HOST memory (pinned for full speed): what a user of
  * `Particle(x=..,y=..,z=..,t=..).to_next_stop(t_stop)` followed by reading lon/lat/dep back gets
  * (seaduck/lagrangian.py:93,741; seaduck/oceinterp.py:113-126).  Copies the inputs to the device,
@@ -214,9 +219,19 @@ int sdk_advect_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_par
 typedef struct sdk_track_io {
     int64_t n;
     const double *lon, *lat, *dep, *t;
+    /* results, one 32-byte record per particle in the caller's order (or NULL) */
+    struct sdk_snapshot_record *out_records;
+    /* the same as separate arrays, each optional; not available together with `sort` */
     double *out_lon, *out_lat, *out_dep;
     int32_t *out_face, *out_iy, *out_ix, *out_izl;
     int32_t *out_ncross, *out_status;
+    /* optional, 4 counters: particles live at the start, wall crossings, particles that hit max_iteration,
+     * particles with a non-zero status */
+    uint64_t *out_stats;
+    /* != 0: put the particles of every chunk into cell order on the device before advecting (sdk_cell_sort);
+     * the records come back in the caller's order all the same */
+    int32_t sort;
+    int32_t reserved;
 } sdk_track_io;
 int64_t sdk_track_scratch_bytes(int64_t n);
 int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io,
@@ -414,19 +429,62 @@ int sdk_wall_stencil(int scheme, const double *buf, const double *vel, double *o
 /* third_order_upwind_z :448: s, w, out [nz][n_inner]; sets w[0][:] = 0 like the reference does */
 int sdk_upwind3_z(const double *s, double *w, double *out, int64_t nz, int64_t n_inner, void *stream);
 
-/* Output snapshot of a stop in 32 bytes per particle (what Particle.to_list_of_time returns per stop
- * and the ranks exchange): out[0..2][n_pad] = lon, lat, dep; out[3][n_pad] = one 64-bit word
- * face << 34 | iy << 21 | ix << 8 | izl (6 + 13 + 13 + 8 bits).  NULL inputs read as zero; device pointers. */
-int sdk_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
-                      const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl, double *out,
-                      void *stream);
+/* ---- output records of a stop ---------------------------------------------------------------------------
+ * What Particle.to_list_of_time returns per stop (seaduck/lagrangian.py:804, the deepcopy of :725) and what
+ * the ranks exchange is, per particle, a position and a cell: 32 bytes. */
+typedef struct sdk_snapshot_record {
+    double lon, lat, dep;
+    uint64_t cell; /* SDK_CELL_PACK(face, iy, ix, izl) */
+} sdk_snapshot_record;
+/* izl (= izl_lin) in bits 0..11, ix in 12..31, iy in 32..51, face in 52..57; bits 58..63 are zero */
+#define SDK_CELL_PACK(f, iy, ix, izl) ((((uint64_t)(f) & 0x3f) << 52) | (((uint64_t)(iy) & 0xfffff) << 32) | (((uint64_t)(ix) & 0xfffff) << 12) | ((uint64_t)(izl) & 0xfff))
+#define SDK_CELL_FACE(w) ((int32_t)(((w) >> 52) & 0x3f))
+#define SDK_CELL_IY(w) ((int32_t)(((w) >> 32) & 0xfffff))
+#define SDK_CELL_IX(w) ((int32_t)(((w) >> 12) & 0xfffff))
+#define SDK_CELL_IZL(w) ((int32_t)((w) & 0xfff))
 
-/* Peer-memory plumbing for the output-snapshot exchange (seaduck_b200/parallel.py SnapshotGather):
- * enable direct access from the current device to `peer_device`, and enqueue a copy-engine copy of
- * `bytes` bytes from `src` (on `src_device`) to `dst` (a mapping of memory on `dst_device`, e.g. a CUDA
- * IPC mapping of another rank's receive buffer) on `stream`.  No kernel is launched. */
-int sdk_peer_enable(int peer_device);
-int sdk_peer_copy_async(void *dst, int dst_device, const void *src, int src_device, int64_t bytes, void *stream);
+/* out[out_index ? out_index[i] : i] = record of particle i, i < p->n (reads lon, lat, dep, face, iy, ix, izl of the
+ * device state `p`; NULL members read as zero).  `out_index` restores the caller's order when the state is cell
+ * sorted (sdk_cell_sort).  Device pointers. */
+int sdk_pack_records(const sdk_particles *p, const int32_t *out_index, sdk_snapshot_record *out, void *stream);
+
+/* ---- cell order ----------------------------------------------------------------------
+ * perm[k] = index of the particle that comes k-th when sorted by (izl, face, iy, ix): particles of one warp then
+ * read neighbouring memory.  `scratch`: device buffer of at least sdk_cell_sort_scratch_bytes(n) bytes.
+ * face / izl may be NULL.  sdk_particles_gather applies a permutation to the whole device state
+ * (dst[k] = src[perm[k]] for every array both structures hold; the reference's counterpart is
+ * Position.subset, seaduck/eulerian.py:319). */
+int64_t sdk_cell_sort_scratch_bytes(int64_t n);
+int sdk_cell_sort(const sdk_grid *grid, int64_t n, const int32_t *face, const int32_t *iy, const int32_t *ix,
+                  const int32_t *izl, int32_t *perm, void *scratch, int64_t scratch_bytes, void *stream);
+int sdk_particles_gather(const sdk_particles *src, const sdk_particles *dst, const int32_t *perm, void *stream);
+
+/* ---- exchange of the output records between the GPUs of a node ------------------------------------------
+ * Every rank owns a receive buffer [n_slots][world][n_pad] of records and SDK_SIGNAL_WORDS 64-bit signal
+ * words (zero-initialised), both in memory that every rank has mapped (symmetric memory: the host side
+ * allocates and exchanges the mappings, e.g. torch.distributed._symmetric_memory).  sdk_pack_ship packs this rank's
+ * records (particle i at position out_index ? out_index[i] : i, as in sdk_pack_records) and stores them into block [step % n_slots][rank] of EVERY rank's buffer from inside one kernel --
+ * plain stores through the peer mappings, or one multimem.st per 16 bytes through `recv_multicast` when the
+ * NVSwitch can replicate (NVLS) -- then posts `step` in every rank's arrived[rank].  It first waits until every
+ * rank has consumed the step that last used the slot.  sdk_exchange_wait makes `stream` wait until all
+ * ranks' records of `step` have landed here (wait != 0) and / or tells every rank that this rank is done
+ * reading them (release != 0).  Steps count from 1.  Waits are bounded; a timeout sets signal[rank][SDK_SIGNAL_ERROR].
+ * One exchange belongs to one stream at a time (`ticket` is a device counter of this rank, zero-initialised). */
+#define SDK_MAX_RANKS 16
+#define SDK_SIGNAL_ARRIVED 0
+#define SDK_SIGNAL_CONSUMED SDK_MAX_RANKS
+#define SDK_SIGNAL_ERROR (2 * SDK_MAX_RANKS)
+#define SDK_SIGNAL_WORDS (2 * SDK_MAX_RANKS + 1)
+typedef struct sdk_exchange {
+    int32_t world, rank, n_slots, reserved;
+    int64_t n_pad;                              /* records per rank and slot */
+    sdk_snapshot_record *recv[SDK_MAX_RANKS];   /* recv[r]: this rank's mapping of rank r's receive buffer */
+    sdk_snapshot_record *recv_multicast;        /* multicast mapping of the receive buffers, or NULL */
+    uint64_t *signal[SDK_MAX_RANKS];            /* signal[r]: this rank's mapping of rank r's signal words */
+    uint32_t *ticket;                           /* device, this rank */
+} sdk_exchange;
+int sdk_pack_ship(const sdk_exchange *x, const sdk_particles *p, const int32_t *out_index, uint64_t step, void *stream);
+int sdk_exchange_wait(const sdk_exchange *x, uint64_t step, int wait, int release, void *stream);
 
 /* Self-test of the device math helpers used by sdk_advect (csrc/fastmath.cuh): out[i] = op(a[i], b[i]),
  * bad[i] = 1 where the helper asked for the slow path.  Device pointers; b may be NULL for unary ops.

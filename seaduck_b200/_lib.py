@@ -13,7 +13,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 SO_PATH = os.environ.get("SEADUCK_B200_LIB") or os.path.join(_HERE, "libseaduck_b200.so")
-SOURCES = ["advect.cu", "locate.cu", "interp.cu", "budget.cu", "stencil.cu", "selftest.cu", "capi.cu"]
+SOURCES = ["advect.cu", "locate.cu", "interp.cu", "budget.cu", "stencil.cu", "selftest.cu", "exchange.cu", "sort.cu", "capi.cu"]
 NVCC_FLAGS = [
     "-gencode",
     "arch=compute_100a,code=sm_100a",
@@ -89,7 +89,7 @@ class AdvectParams(C.Structure):
         ("blocks_per_sm", C.c_int32),
         ("threads_per_block", C.c_int32),
         ("reserve_sms", C.c_int32),
-        ("reserved", C.c_int32),
+        ("keep_status", C.c_int32),
         ("stats", vp),
     ]
 
@@ -119,7 +119,23 @@ class Located(C.Structure):
 class TrackIO(C.Structure):
     _fields_ = [("n", C.c_int64)] + [
         (n, vp)
-        for n in "lon lat dep t out_lon out_lat out_dep out_face out_iy out_ix out_izl out_ncross out_status".split()
+        for n in "lon lat dep t out_records out_lon out_lat out_dep out_face out_iy out_ix out_izl out_ncross out_status out_stats".split()
+    ] + [("sort", C.c_int32), ("reserved", C.c_int32)]
+
+
+MAX_RANKS = 16
+SIGNAL_ARRIVED, SIGNAL_CONSUMED, SIGNAL_ERROR, SIGNAL_WORDS = 0, MAX_RANKS, 2 * MAX_RANKS, 2 * MAX_RANKS + 1
+
+# numpy view of sdk_snapshot_record (32 bytes) and the layout of its cell word
+SNAPSHOT_RECORD = [("lon", "<f8"), ("lat", "<f8"), ("dep", "<f8"), ("cell", "<u8")]
+CELL_SHIFT = {"face": 52, "iy": 32, "ix": 12, "izl": 0}
+CELL_BITS = {"face": 6, "iy": 20, "ix": 20, "izl": 12}
+
+
+class Exchange(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("n_slots", C.c_int32), ("reserved", C.c_int32), ("n_pad", C.c_int64),
+        ("recv", vp * MAX_RANKS), ("recv_multicast", vp), ("signal", vp * MAX_RANKS), ("ticket", vp),
     ]
 
 
@@ -150,11 +166,31 @@ class SdkError(RuntimeError):
 _lib = None
 
 
-def build(verbose=False):
-    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_HERE, "csrc", s) for s in SOURCES if os.path.exists(os.path.join(_HERE, "csrc", s))]
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO_PATH] + srcs
-    subprocess.check_call(cmd, cwd=_ROOT)
+def build(verbose=False, force=False):
+    """Compile the CUDA library for sm_100a in-tree (nvcc cross-compiles without a GPU): one object per source
+    file, compiled side by side and only when the file or a header changed, then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    src_dir = os.path.join(_HERE, "csrc")
+    obj_dir = os.path.join(_ROOT, "build", "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(_ROOT, "include", "seaduck_b200.h"))
+    headers.append(os.path.abspath(__file__))  # the flags live here
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    jobs = []
+    for name in SOURCES:
+        src = os.path.join(src_dir, name)
+        obj = os.path.join(obj_dir, name[:-3] + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            jobs.append(["nvcc"] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src])
+    with ThreadPoolExecutor(max_workers=max(1, min(len(jobs), os.cpu_count() or 1))) as pool:
+        for rc, cmd in zip(pool.map(lambda c: subprocess.call(c, cwd=_ROOT), jobs), jobs):
+            if rc != 0:
+                raise subprocess.CalledProcessError(rc, cmd)
+    objs = [os.path.join(obj_dir, name[:-3] + ".o") for name in SOURCES]
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO_PATH] + objs, cwd=_ROOT)
     return SO_PATH
 
 
@@ -198,9 +234,13 @@ def lib():
         L.sdk_wall_stencil.argtypes = [C.c_int, vp, vp, vp, C.c_int64, C.c_int64, C.c_int64, vp]
         L.sdk_upwind3_z.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, vp]
         L.sdk_log_budget.argtypes = [vp, vp, vp, C.c_int64, C.c_int64, vp, vp, vp, vp, vp, vp]
-        L.sdk_pack_snapshot.argtypes = [C.c_int64, C.c_int64] + [vp] * 9
-        L.sdk_peer_enable.argtypes = [C.c_int]
-        L.sdk_peer_copy_async.argtypes = [vp, C.c_int, vp, C.c_int, C.c_int64, vp]
+        L.sdk_pack_records.argtypes = [C.POINTER(Particles), vp, vp, vp]
+        L.sdk_cell_sort_scratch_bytes.restype = C.c_int64
+        L.sdk_cell_sort_scratch_bytes.argtypes = [C.c_int64]
+        L.sdk_cell_sort.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
+        L.sdk_particles_gather.argtypes = [C.POINTER(Particles), C.POINTER(Particles), vp, vp]
+        L.sdk_pack_ship.argtypes = [C.POINTER(Exchange), C.POINTER(Particles), vp, C.c_uint64, vp]
+        L.sdk_exchange_wait.argtypes = [C.POINTER(Exchange), C.c_uint64, C.c_int, C.c_int, vp]
         L.sdk_selftest_math.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp, vp]
         _lib = L
     return _lib

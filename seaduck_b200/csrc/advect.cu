@@ -656,6 +656,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
                     const int64_t pid = (int64_t)base + __popc(idle & ((1u << lane) - 1));
                     if (pid < n) {
                         load_lane<P>(a.p, pid, a.has_dep, s);
+                        if (a.keep_status) s.status = a.p.status[pid];
                         have = true;
                         if (LOG && a.log.emit_start) note(a, s, 15);
                         live = fabs(a.t_stop - s.t) > a.tol;

@@ -13,7 +13,7 @@ struct AdvectArgs {
     sdk_particles p;
     sdk_log log;
     double t_stop, tol, trim_tol;
-    int max_iteration, kick_back, has_dep, has_log, commit, refill_threshold;
+    int max_iteration, kick_back, has_dep, has_log, commit, refill_threshold, keep_status;
     unsigned long long *queue;  // work queue head
     unsigned long long *stats;  // optional [4]: live at start, crossings, hit max_iteration, flagged
 };

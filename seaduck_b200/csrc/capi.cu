@@ -2,6 +2,7 @@
 // handle bookkeeping, launch configuration.  All arithmetic lives in the kernels.
 #include <cuda_runtime.h>
 
+#include <climits>
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
@@ -20,9 +21,15 @@ cudaError_t launch_gather_plane(const double *src, int64_t n_outer, int64_t src_
 cudaError_t launch_wall_stencil(int scheme, const double *buf, const double *vel, double *out, int64_t n_outer, int64_t n_out,
                                 int64_t n_inner, cudaStream_t s);
 cudaError_t launch_upwind3_z(const double *sfield, double *w, double *out, int64_t nz, int64_t n_inner, cudaStream_t s);
-cudaError_t launch_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
-                                 const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl, double *out,
-                                 cudaStream_t s);
+cudaError_t launch_pack_records(const sdk_particles &p, int64_t n, const int32_t *out_index, sdk_snapshot_record *out,
+                                cudaStream_t s);
+cudaError_t launch_pack_ship(const sdk_exchange &x, const sdk_particles &p, int64_t n, const int32_t *out_index,
+                             uint64_t step, int sm_count, cudaStream_t s);
+cudaError_t launch_exchange_wait(const sdk_exchange &x, uint64_t step, int wait, int release, cudaStream_t s);
+size_t cell_sort_scratch_bytes(int64_t n);
+cudaError_t launch_cell_sort(const GridDev &g, int64_t n, const int32_t *face, const int32_t *iy, const int32_t *ix,
+                             const int32_t *izl, int32_t *perm, void *scratch, size_t scratch_bytes, cudaStream_t s);
+cudaError_t launch_particles_gather(const sdk_particles &src, const sdk_particles &dst, const int32_t *perm, cudaStream_t s);
 cudaError_t launch_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad,
                                  cudaStream_t s);
 }
@@ -195,6 +202,7 @@ static int fill_args(const sdk_grid *grid, const sdk_velocity *vel, const sdk_pa
     a.has_dep = has_dep;
     a.has_log = log != nullptr;
     a.commit = commit;
+    a.keep_status = (par && par->keep_status && p->status) ? 1 : 0;
     int thr = par ? par->refill_threshold : 0;
     a.refill_threshold = thr > 0 ? (thr > 32 ? 32 : thr) : 8;
     a.queue = grid->queue + (grid->next_queue++ % kQueueSlots);
@@ -564,38 +572,61 @@ int sdk_upwind3_z(const double *s, double *w, double *out, int64_t nz, int64_t n
     return SDK_OK;
 }
 
-int sdk_pack_snapshot(int64_t n, int64_t n_pad, const double *lon, const double *lat, const double *dep,
-                      const int32_t *face, const int32_t *iy, const int32_t *ix, const int32_t *izl, double *out,
-                      void *stream) {
-    if (n < 0 || n_pad < n || (n_pad > 0 && !out)) return fail(SDK_EINVAL, "sdk_pack_snapshot: bad argument");
-    cudaError_t e = sdk::launch_pack_snapshot(n, n_pad, lon, lat, dep, face, iy, ix, izl, out, (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e, "sdk_pack_snapshot: launch");
+int sdk_pack_records(const sdk_particles *p, const int32_t *out_index, sdk_snapshot_record *out, void *stream) {
+    if (!p || p->n < 0) return fail(SDK_EINVAL, "sdk_pack_records: bad argument");
+    if (p->n > 0 && (!out || !p->lon || !p->lat || !p->iy || !p->ix)) return fail(SDK_EINVAL, "sdk_pack_records: null array");
+    cudaError_t e = sdk::launch_pack_records(*p, p->n, out_index, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_pack_records: launch");
     return SDK_OK;
 }
 
-int sdk_peer_enable(int peer_device) {
-    int cur = 0;
-    cudaError_t e = cudaGetDevice(&cur);
-    if (e != cudaSuccess) return cuda_fail(e, "sdk_peer_enable: cudaGetDevice");
-    if (peer_device == cur) return SDK_OK;
-    int can = 0;
-    e = cudaDeviceCanAccessPeer(&can, cur, peer_device);
-    if (e != cudaSuccess) return cuda_fail(e, "sdk_peer_enable: cudaDeviceCanAccessPeer");
-    if (!can) return fail(SDK_EUNSUPPORTED, "sdk_peer_enable: no peer access between the two devices");
-    e = cudaDeviceEnablePeerAccess(peer_device, 0);
-    if (e == cudaErrorPeerAccessAlreadyEnabled) {
-        cudaGetLastError();
-        return SDK_OK;
-    }
-    if (e != cudaSuccess) return cuda_fail(e, "sdk_peer_enable: cudaDeviceEnablePeerAccess");
+int64_t sdk_cell_sort_scratch_bytes(int64_t n) { return n < 0 ? 0 : (int64_t)sdk::cell_sort_scratch_bytes(n); }
+
+int sdk_cell_sort(const sdk_grid *grid, int64_t n, const int32_t *face, const int32_t *iy, const int32_t *ix,
+                  const int32_t *izl, int32_t *perm, void *scratch, int64_t scratch_bytes, void *stream) {
+    if (!grid || n < 0 || n > INT32_MAX) return fail(SDK_EINVAL, "sdk_cell_sort: bad argument");
+    if (n > 0 && (!iy || !ix || !perm || !scratch)) return fail(SDK_EINVAL, "sdk_cell_sort: null array");
+    if (scratch_bytes < sdk_cell_sort_scratch_bytes(n)) return fail(SDK_EINVAL, "sdk_cell_sort: scratch too small");
+    cudaError_t e = sdk::launch_cell_sort(grid->dev, n, face, iy, ix, izl, perm, scratch, (size_t)scratch_bytes, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_cell_sort");
     return SDK_OK;
 }
 
-int sdk_peer_copy_async(void *dst, int dst_device, const void *src, int src_device, int64_t bytes, void *stream) {
-    if (!dst || !src || bytes < 0) return fail(SDK_EINVAL, "sdk_peer_copy_async: bad argument");
-    if (bytes == 0) return SDK_OK;
-    cudaError_t e = cudaMemcpyPeerAsync(dst, dst_device, src, src_device, (size_t)bytes, (cudaStream_t)stream);
-    if (e != cudaSuccess) return cuda_fail(e, "sdk_peer_copy_async: cudaMemcpyPeerAsync");
+int sdk_particles_gather(const sdk_particles *src, const sdk_particles *dst, const int32_t *perm, void *stream) {
+    if (!src || !dst || dst->n < 0 || src->n < 0) return fail(SDK_EINVAL, "sdk_particles_gather: bad argument");
+    if (dst->n > 0 && !perm) return fail(SDK_EINVAL, "sdk_particles_gather: permutation missing");
+    cudaError_t e = sdk::launch_particles_gather(*src, *dst, perm, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_particles_gather: launch");
+    return SDK_OK;
+}
+
+static int check_exchange(const sdk_exchange *x, const char *who) {
+    if (!x) return fail(SDK_EINVAL, std::string(who) + ": null exchange");
+    if (x->world < 1 || x->world > SDK_MAX_RANKS || x->rank < 0 || x->rank >= x->world || x->n_slots < 1 || x->n_pad < 0)
+        return fail(SDK_EINVAL, std::string(who) + ": bad geometry");
+    for (int r = 0; r < x->world; ++r)
+        if (!x->signal[r] || (!x->recv[r] && !x->recv_multicast)) return fail(SDK_EINVAL, std::string(who) + ": unmapped rank");
+    if (!x->ticket) return fail(SDK_EINVAL, std::string(who) + ": ticket missing");
+    return SDK_OK;
+}
+
+int sdk_pack_ship(const sdk_exchange *x, const sdk_particles *p, const int32_t *out_index, uint64_t step, void *stream) {
+    int rc = check_exchange(x, "sdk_pack_ship");
+    if (rc) return rc;
+    if (!p || p->n < 0 || p->n > x->n_pad) return fail(SDK_EINVAL, "sdk_pack_ship: particle count does not fit n_pad");
+    if (step < 1) return fail(SDK_EINVAL, "sdk_pack_ship: steps count from 1");
+    if (p->n > 0 && (!p->lon || !p->lat || !p->iy || !p->ix)) return fail(SDK_EINVAL, "sdk_pack_ship: null array");
+    const int sms = sdk_sm_count();
+    cudaError_t e = sdk::launch_pack_ship(*x, *p, p->n, out_index, step, sms > 0 ? sms : 1, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_pack_ship: launch");
+    return SDK_OK;
+}
+
+int sdk_exchange_wait(const sdk_exchange *x, uint64_t step, int wait, int release, void *stream) {
+    int rc = check_exchange(x, "sdk_exchange_wait");
+    if (rc) return rc;
+    cudaError_t e = sdk::launch_exchange_wait(*x, step, wait, release, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_exchange_wait: launch");
     return SDK_OK;
 }
 
@@ -613,6 +644,8 @@ int64_t sdk_struct_size(int which) {
         case 9: return sizeof(sdk_points);
         case 10: return sizeof(sdk_budget_fields);
         case 11: return sizeof(sdk_wall_fields);
+        case 12: return sizeof(sdk_snapshot_record);
+        case 13: return sizeof(sdk_exchange);
         default: return -1;
     }
 }
@@ -627,25 +660,43 @@ int sdk_selftest_math(int op, int64_t n, const double *a, const double *b, doubl
 }
 
 // ---- positions in, positions out ------------------------------------------------------------------
-// (room for the per-chunk alignment of the pipelined path: up to kTrackChunks carvings of ~30 arrays)
-int64_t sdk_track_scratch_bytes(int64_t n) { return sdk_particles_bytes(n) + 8 * (int64_t)align256((size_t)n * 8) + kTrackChunksMax * 40 * 256; }
+// per chunk: the located state, a second copy in cell order, the permutation, the sort's workspace, the records
+static size_t track_chunk_bytes(int64_t n) {
+    return 2 * (size_t)sdk_particles_bytes(n) + align256((size_t)n * 4) + align256((size_t)sdk_cell_sort_scratch_bytes(n)) +
+           align256((size_t)n * sizeof(sdk_snapshot_record));
+}
 
-// One chunk of sdk_track_host: H2D, locate, velocity read, advect, D2H -- all asynchronous on `stream`.
-static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev,
-                       int32_t n_t, double t_stop, const sdk_advect_params *par, void *scratch, cudaStream_t stream) {
-    const int64_t n = io->n;
-    const int has_dep = par ? par->has_dep : 0;
-    // carve the device state out of the scratch buffer
-    sdk_particles dp;
+int64_t sdk_track_scratch_bytes(int64_t n) {
+    // chunks are rounded up to 32 particles; 256 bytes for the counters
+    return (int64_t)(track_chunk_bytes(n + 32 * kTrackChunksMax) + (size_t)kTrackChunksMax * 80 * 256 + 256);
+}
+
+static void carve_particles(sdk_particles &dp, int64_t n, char *&cur) {
     std::memset(&dp, 0, sizeof dp);
     dp.n = n;
-    char *cur = (char *)scratch;
     for (const Field &f : kFields) {
         if (f.offset == offsetof(sdk_particles, active)) continue;
         void **ddst = (void **)((char *)&dp + f.offset);
         *ddst = cur;
         cur += align256((size_t)n * f.elem * f.mult);
     }
+}
+
+// One chunk of sdk_track_host: H2D, locate, (cell sort,) velocity read, advect, pack, D2H -- all asynchronous on `stream`.
+static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev,
+                       int32_t n_t, double t_stop, const sdk_advect_params *par_in, uint64_t *stats_dev, void *scratch,
+                       cudaStream_t stream) {
+    const int64_t n = io->n;
+    sdk_advect_params par;
+    if (par_in) par = *par_in;
+    else {
+        std::memset(&par, 0, sizeof par);
+        par.tol = 1e-4, par.trim_tol = 1e-14, par.max_iteration = 200;
+    }
+    const int has_dep = par.has_dep;
+    char *cur = (char *)scratch;
+    sdk_particles dp, sp;
+    carve_particles(dp, n, cur);
     cudaError_t e;
 #define H2D(dst, src) \
     if ((e = cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyHostToDevice, stream)) != cudaSuccess) \
@@ -661,22 +712,50 @@ static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_
     loc.face = grid->dev.has_face ? dp.face : nullptr;
     loc.iy = dp.iy; loc.ix = dp.ix; loc.rx = dp.rx; loc.ry = dp.ry;
     loc.px = dp.px; loc.py = dp.py; loc.dx = dp.dx; loc.dy = dp.dy;
-    loc.izl = dp.izl; loc.rzl = dp.rzl; loc.dzl = dp.dzl; loc.bzl = dp.bzl;
+    const bool vertical = has_dep && grid->dev.n_zl > 1;
+    if (vertical) {
+        loc.izl = dp.izl; loc.rzl = dp.rzl; loc.dzl = dp.dzl; loc.bzl = dp.bzl;
+    } else {
+        dp.izl = nullptr;  // no vertical index: reads as level 0 everywhere
+    }
     loc.it = dp.it;
     loc.status = dp.status;
-    if (!(vel->has_time && ts_dev && n_t > 1)) {
-        if ((e = cudaMemsetAsync(dp.it, 0, (size_t)n * 4, stream)) != cudaSuccess) return cuda_fail(e, "memset");
+    const bool timed = vel->has_time && ts_dev && n_t > 1;
+    if (!timed && (e = cudaMemsetAsync(dp.it, 0, (size_t)n * 4, stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: memset");
+    int rc = sdk_locate(grid, n, dp.lon, dp.lat, vertical ? dp.dep : nullptr, timed ? dp.t : nullptr, ts_dev, n_t, &loc, stream);
+    if (rc) return rc;
+    const sdk_particles *work = &dp;
+    int32_t *perm = nullptr;
+    if (io->sort) {
+        carve_particles(sp, n, cur);
+        if (!vertical) sp.izl = nullptr;
+        perm = (int32_t *)cur;
+        cur += align256((size_t)n * 4);
+        const int64_t sbytes = sdk_cell_sort_scratch_bytes(n);
+        rc = sdk_cell_sort(grid, n, loc.face, dp.iy, dp.ix, vertical ? dp.izl : nullptr, perm, cur, sbytes, stream);
+        if (rc) return rc;
+        cur += align256((size_t)sbytes);
+        // (u, v, w ... are not set yet: the velocity read below fills them in the sorted copy)
+        rc = sdk_particles_gather(&dp, &sp, perm, stream);
+        if (rc) return rc;
+        work = &sp;
     }
-    int rc = sdk_locate(grid, n, dp.lon, dp.lat, (has_dep && grid->dev.n_zl > 1) ? dp.dep : nullptr,
-                        (vel->has_time && ts_dev && n_t > 1) ? dp.t : nullptr, ts_dev, n_t, &loc, stream);
-    if (rc) return rc;
     // Particle.__init__: get_vol + get_u_du, then to_next_stop
-    rc = sdk_get_u_du(grid, vel, &dp, has_dep, stream);
+    rc = sdk_get_u_du(grid, vel, work, has_dep, stream);
     if (rc) return rc;
-    rc = sdk_advect(grid, vel, &dp, t_stop, par, nullptr, 1, stream);
+    par.keep_status = 1;  // what sdk_locate flagged stays flagged
+    par.stats = stats_dev;
+    rc = sdk_advect(grid, vel, work, t_stop, &par, nullptr, 1, stream);
     if (rc) return rc;
+    if (io->out_records) {
+        sdk_snapshot_record *rec = (sdk_snapshot_record *)cur;
+        rc = sdk_pack_records(work, perm, rec, stream);
+        if (rc) return rc;
+        if ((e = cudaMemcpyAsync(io->out_records, rec, (size_t)n * sizeof(sdk_snapshot_record), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+            return cuda_fail(e, "sdk_track_host: D2H");
+    }
 #define D2H(dst, src, esz) \
-    if (dst && (e = cudaMemcpyAsync(dst, src, (size_t)n * esz, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) \
+    if (dst && src && (e = cudaMemcpyAsync(dst, src, (size_t)n * esz, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) \
         return cuda_fail(e, "sdk_track_host: D2H");
     D2H(io->out_lon, dp.lon, 8)
     D2H(io->out_lat, dp.lat, 8)
@@ -684,7 +763,7 @@ static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_
     if (grid->dev.has_face) D2H(io->out_face, dp.face, 4)
     D2H(io->out_iy, dp.iy, 4)
     D2H(io->out_ix, dp.ix, 4)
-    if (has_dep) D2H(io->out_izl, dp.izl, 4)
+    if (vertical) D2H(io->out_izl, dp.izl, 4)
     D2H(io->out_ncross, dp.ncross, 4)
     D2H(io->out_status, dp.status, 4)
 #undef D2H
@@ -694,14 +773,21 @@ static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_
 int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev,
                    int32_t n_t, double t_stop, const sdk_advect_params *par, void *scratch, void *stream_) {
     if (!grid || !vel || !io || !scratch) return fail(SDK_EINVAL, "sdk_track_host: null argument");
-    if (!io->lon || !io->lat || !io->t || !io->out_lon || !io->out_lat)
-        return fail(SDK_EINVAL, "sdk_track_host: lon / lat / t and their outputs are required");
+    if (!io->lon || !io->lat || !io->t) return fail(SDK_EINVAL, "sdk_track_host: lon / lat / t are required");
+    if (!io->out_records && (!io->out_lon || !io->out_lat)) return fail(SDK_EINVAL, "sdk_track_host: no output requested");
+    if (io->sort && (io->out_lon || io->out_lat || io->out_dep || io->out_face || io->out_iy || io->out_ix || io->out_izl ||
+                     io->out_ncross || io->out_status))
+        return fail(SDK_EINVAL, "sdk_track_host: with sort the results come as records (out_records) and counters (out_stats) only");
     const int64_t n = io->n;
     if (n <= 0) return n == 0 ? SDK_OK : fail(SDK_EINVAL, "sdk_track_host: negative count");
     const int has_dep = par ? par->has_dep : 0;
-    if (has_dep && (!io->dep || !io->out_dep)) return fail(SDK_EINVAL, "sdk_track_host: depth arrays missing");
+    if (has_dep && !io->dep) return fail(SDK_EINVAL, "sdk_track_host: depth array missing");
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaError_t e;
+    // the call's counters: first 256 bytes of the scratch buffer
+    uint64_t *stats_dev = (uint64_t *)scratch;
+    char *cur = (char *)scratch + 256;
+    if ((e = cudaMemsetAsync(stats_dev, 0, 4 * sizeof(uint64_t), stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: memset");
     // Small batches: one pass.  Large ones: chunks on three internal streams, so that the upload of
     // chunk k+1 and the read-back of chunk k-1 (copy engines) overlap the kernels of chunk k.
     const int64_t min_chunk = 65536;
@@ -713,43 +799,43 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
     }
     if (nchunks > max_chunks) nchunks = max_chunks;
     if (nchunks < 2) {
-        int rc = track_chunk(grid, vel, io, ts_dev, n_t, t_stop, par, scratch, stream);
+        int rc = track_chunk(grid, vel, io, ts_dev, n_t, t_stop, par, stats_dev, cur, stream);
         if (rc) return rc;
-        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: sync");
-        return SDK_OK;
-    }
-    if (!grid->has_pipe) {
+    } else {
+        if (!grid->has_pipe) {
+            for (auto &st : grid->pipe)
+                if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: stream");
+            for (auto &ev : grid->pipe_ev)
+                if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event");
+            grid->has_pipe = true;
+        }
+        // the internal streams start after whatever the caller queued on `stream`
+        if ((e = cudaEventRecord(grid->pipe_ev[3], stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");
         for (auto &st : grid->pipe)
-            if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: stream");
-        for (auto &ev : grid->pipe_ev)
-            if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event");
-        grid->has_pipe = true;
-    }
-    // the internal streams start after whatever the caller queued on `stream`
-    if ((e = cudaEventRecord(grid->pipe_ev[3], stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");
-    for (auto &st : grid->pipe)
-        if ((e = cudaStreamWaitEvent(st, grid->pipe_ev[3], 0)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: wait");
-    const int64_t per = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
-    char *cur = (char *)scratch;
-    for (int c = 0; c < nchunks; ++c) {
-        const int64_t off = (int64_t)c * per;
-        const int64_t cnt = off + per <= n ? per : n - off;
-        if (cnt <= 0) break;
-        sdk_track_io sub = *io;
-        sub.n = cnt;
+            if ((e = cudaStreamWaitEvent(st, grid->pipe_ev[3], 0)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: wait");
+        const int64_t per = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
+        for (int c = 0; c < nchunks; ++c) {
+            const int64_t off = (int64_t)c * per;
+            const int64_t cnt = off + per <= n ? per : n - off;
+            if (cnt <= 0) break;
+            sdk_track_io sub = *io;
+            sub.n = cnt;
 #define SHIFT(member) \
     if (sub.member) sub.member = sub.member + off;
-        SHIFT(lon) SHIFT(lat) SHIFT(dep) SHIFT(t) SHIFT(out_lon) SHIFT(out_lat) SHIFT(out_dep) SHIFT(out_face)
-        SHIFT(out_iy) SHIFT(out_ix) SHIFT(out_izl) SHIFT(out_ncross) SHIFT(out_status)
+            SHIFT(lon) SHIFT(lat) SHIFT(dep) SHIFT(t) SHIFT(out_records) SHIFT(out_lon) SHIFT(out_lat) SHIFT(out_dep)
+            SHIFT(out_face) SHIFT(out_iy) SHIFT(out_ix) SHIFT(out_izl) SHIFT(out_ncross) SHIFT(out_status)
 #undef SHIFT
-        int rc = track_chunk(grid, vel, &sub, ts_dev, n_t, t_stop, par, cur, grid->pipe[c % 3]);
-        if (rc) return rc;
-        cur += sdk_particles_bytes(cnt);
+            int rc = track_chunk(grid, vel, &sub, ts_dev, n_t, t_stop, par, stats_dev, cur, grid->pipe[c % 3]);
+            if (rc) return rc;
+            cur += track_chunk_bytes(cnt);
+        }
+        for (int k = 0; k < 3; ++k) {
+            if ((e = cudaEventRecord(grid->pipe_ev[k], grid->pipe[k])) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");
+            if ((e = cudaStreamWaitEvent(stream, grid->pipe_ev[k], 0)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: wait");
+        }
     }
-    for (int k = 0; k < 3; ++k) {
-        if ((e = cudaEventRecord(grid->pipe_ev[k], grid->pipe[k])) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");
-        if ((e = cudaStreamWaitEvent(stream, grid->pipe_ev[k], 0)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: wait");
-    }
+    if (io->out_stats && (e = cudaMemcpyAsync(io->out_stats, stats_dev, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+        return cuda_fail(e, "sdk_track_host: D2H");
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: sync");
     return SDK_OK;
 }

@@ -468,6 +468,8 @@ class _DevicePoints:
         t = None
         if "_st" in d and name in _PARTICLE_DEV:
             t = d["_st"].get(_PARTICLE_DEV[name])
+            if t is not None and d.get("_inv") is not None:
+                t = t[d["_inv"]]  # the state is kept in cell order; everything else here is in the caller's
         loc = d.get("_located")
         if t is None and loc is not None:
             key = _LOCATED_NAME.get(name, name)

@@ -77,8 +77,66 @@ _LIST_NAMES = {
 }
 
 
+class RecordSnapshot:
+    """What a stop of ``to_list_of_time`` leaves behind when full clones of the particle state would not fit
+    (``Particle.SNAPSHOT_CLONE_BUDGET``): position and cell of every particle in the caller's order, 32 bytes each
+    (``sdk_snapshot_record``), kept in HBM until somebody reads them.  ``lon, lat, dep, face, iy, ix, izl_lin, t, N``
+    read like the attributes of a ``Particle`` snapshot (reference ``lagrangian.py:725``); the rest of the state
+    (rel-coords, velocities) is not kept."""
+
+    _FIELDS = {"lon": "lon", "lat": "lat", "dep": "dep", "face": "face", "iy": "iy", "ix": "ix", "izl_lin": "izl"}
+
+    def __init__(self, ocedata, t, records, has_face, has_dep):
+        self.ocedata, self.N = ocedata, int(records.shape[0])
+        self._t, self._records, self._host, self._event = float(t), records, None, None
+        self._has_face, self._has_dep = has_face, has_dep
+
+    @property
+    def t(self):
+        return np.full(self.N, self._t)
+
+    def prefetch_to_host(self, stream=None):
+        """Start the device-to-host copy of the records into pinned memory (on ``stream``) and return at once."""
+        import torch  # noqa: PLC0415
+
+        if self._host is None and self._event is None:
+            host = torch.empty(self._records.shape, dtype=self._records.dtype).pin_memory()
+            with torch.cuda.stream(stream) if stream is not None else torch.cuda.stream(torch.cuda.current_stream()):
+                host.copy_(self._records, non_blocking=True)
+                self._event = torch.cuda.Event()
+                self._event.record()
+            self._pinned = host
+
+    def records(self):
+        """numpy structured array of the records (``_lib.SNAPSHOT_RECORD``)."""
+        if self._event is not None:
+            self._event.synchronize()
+            return self._pinned.numpy().reshape(-1).view(np.dtype(_lib.SNAPSHOT_RECORD))
+        return self._records.cpu().numpy().reshape(-1).view(np.dtype(_lib.SNAPSHOT_RECORD))
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name not in self._FIELDS:
+            raise AttributeError(
+                f"'{name}': a record snapshot keeps lon, lat, dep, face, iy, ix, izl_lin only "
+                "(to_list_of_time(..., snapshots='full') keeps the whole state per stop)"
+            )
+        if self._host is None:
+            from .parallel import unpack_records  # noqa: PLC0415
+
+            self.__dict__["_host"] = unpack_records(self.records())
+        if (name == "face" and not self._has_face) or (name in ("izl_lin",) and not self._has_dep):
+            return None
+        return self._host[self._FIELDS[name]]
+
+
 class Particle(Position):
     """Lagrangian particles advected on the GPU.  Parameters as in the reference (``lagrangian.py:93``).
+
+    ``sort`` (not in the reference): keep the device state in cell order -- sorted by (level, face, iy, ix) with
+    ``sdk_cell_sort`` -- so that the lanes of a warp read neighbouring memory.  ``"auto"`` sorts from
+    ``SORT_THRESHOLD`` particles on (never with ``save_raw`` or a ``callback``, whose records / masks are in
+    particle order).  Nothing changes for the caller: every attribute and snapshot comes back in the order the
+    particles were given in.
 
     ``lazy = True`` (not in the reference) keeps ``to_next_stop`` asynchronous: the end-of-stop
     bookkeeping (``t := t_stop`` unless nothing was live, the time index, the crossing counters) is
@@ -88,6 +146,10 @@ class Particle(Position):
     """
 
     lazy = False
+    SORT_THRESHOLD = 100_000
+    # to_list_of_time keeps full clones of the state per stop (what the reference returns) while they fit this many
+    # bytes, 32-byte records per particle beyond that
+    SNAPSHOT_CLONE_BUDGET = 8 << 30
 
     def __init__(
         self,
@@ -99,9 +161,11 @@ class Particle(Position):
         transport=False,
         callback=None,
         max_iteration=200,
+        sort="auto",
         **kwarg,
     ):
         Position.__init__(self)
+        self.__dict__["_sort_request"] = sort
         if "bool_array" in kwarg.keys():
             self.from_bool_array(**kwarg)
         else:
@@ -175,6 +239,13 @@ class Particle(Position):
         st["vol"] = torch.ones(n, dtype=torch.float64, device=dev)
         for name in ("status", "niter", "ncross"):
             st[name] = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.__dict__["_perm"] = None  # device int32: state slot k holds the caller's particle _perm[k]
+        self.__dict__["_inv"] = None   # device int64: the caller's particle i sits in state slot _inv[i]
+        want = self.__dict__.pop("_sort_request", False)
+        if want == "auto":
+            want = n >= self.SORT_THRESHOLD
+        if want and not self.save_raw and self.callback is None and n > 1:
+            st = self._cell_sorted(st, n, dev)
         self.__dict__["_st"] = st
         self.__dict__["_crossings"] = 0
         self.__dict__["_stats"] = torch.zeros(4, dtype=torch.int64, device=dev)
@@ -190,8 +261,35 @@ class Particle(Position):
             if not self._has_dep and key not in self.rel:
                 self.rel[key] = None
 
-    def _cparticles(self, active=None):
-        st = self._st
+    def _cell_sorted(self, st, n, dev):
+        """Permute the freshly located state into cell order (``sdk_cell_sort`` + ``sdk_particles_gather``)."""
+        import torch  # noqa: PLC0415
+
+        L = _lib.lib()
+        stream = _lib.current_stream()
+        perm = torch.empty(n, dtype=torch.int32, device=dev)
+        nbytes = int(L.sdk_cell_sort_scratch_bytes(n))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ptr = lambda t: None if t is None else t.data_ptr()  # noqa: E731
+        _lib.check(
+            L.sdk_cell_sort(self.ocedata.grid_handle(), n, ptr(st.get("face")), ptr(st["iy"]), ptr(st["ix"]),
+                            ptr(st["izl"]) if self._has_dep else None, perm.data_ptr(), scratch.data_ptr(), nbytes, stream),
+            "sdk_cell_sort",
+        )
+        new = {k: (None if v is None else torch.empty_like(v)) for k, v in st.items()}
+        src, dst = self._cparticles(state=st), self._cparticles(state=new)
+        _lib.check(L.sdk_particles_gather(C.byref(src), C.byref(dst), perm.data_ptr(), stream), "sdk_particles_gather")
+        inv = torch.empty(n, dtype=torch.int64, device=dev)
+        inv[perm.long()] = torch.arange(n, dtype=torch.int64, device=dev)
+        self.__dict__["_perm"], self.__dict__["_inv"] = perm, inv
+        return new
+
+    def _out_index(self):
+        """int32 device tensor that puts packed records back into the caller's order, or None."""
+        return self._perm
+
+    def _cparticles(self, active=None, state=None):
+        st = self._st if state is None else state
         p = _lib.Particles()
         p.n = self.N
         for name in _lib.PARTICLE_F64 + _lib.PARTICLE_I32 + _lib.PARTICLE_F64B + _lib.PARTICLE_F32 + _lib.PARTICLE_F64C + ["status", "niter", "ncross"]:
@@ -216,6 +314,9 @@ class Particle(Position):
         if t is None:
             val = None
         else:
+            inv = self._inv
+            if inv is not None:
+                t = t.view(4, -1)[:, inv] if attr in ("px", "py") else t[inv]
             val = t.cpu().numpy().astype(dtype, copy=False)
             if attr in ("px", "py"):
                 val = val.reshape(4, -1)
@@ -271,8 +372,10 @@ class Particle(Position):
             tgt = d["_st"].get(dev_name)
             arr = np.ascontiguousarray(value)
             tdtype = tgt.dtype if tgt is not None else torch.float64
-            new = torch.as_tensor(arr.reshape(-1)).to(device=self.ocedata._torch_device(), dtype=tdtype)
-            d["_st"][dev_name] = new
+            new = torch.as_tensor(arr).to(device=self.ocedata._torch_device(), dtype=tdtype)
+            if d.get("_perm") is not None:
+                new = new[..., d["_perm"].long()]
+            d["_st"][dev_name] = new.reshape(-1).contiguous()
             d["_stale"].discard(attr)
         Position.__setattr__(self, attr, value)
 
@@ -300,7 +403,8 @@ class Particle(Position):
             n = self.N
             as32 = od.readiness["h"] == "local_cartesian"  # float32 table values there, float64 arrays in rectilinear
             for key, (arr, row) in dict(bx=("px", 0), cs=("px", 1), by=("py", 0), sn=("py", 1)).items():
-                val = self._st[arr][row * n : (row + 1) * n].cpu().numpy()
+                val = self._st[arr][row * n : (row + 1) * n]
+                val = (val if self._inv is None else val[self._inv]).cpu().numpy()
                 self.rel[key] = val.astype(np.float32) if as32 else val
         else:
             face, iy, ix = self._rel_get("face"), self._rel_get("iy"), self._rel_get("ix")
@@ -432,13 +536,12 @@ class Particle(Position):
         key = _LIST_NAMES[attr]
         if key == "fc" and self._st.get("face") is None:
             raise AttributeError(attr)
-        out = [[] for _ in range(self.N)]
+        out = None
         for ch in self._raw:
             rec, off = self._host_chunk(ch)
-            vals = rec[key]
-            for i in range(self.N):
-                out[i].extend(vals[off[i] : off[i + 1]].tolist())
-        return out
+            parts = np.split(rec[key], off[1:-1])  # one view per particle, no Python loop over the records
+            out = [p.tolist() for p in parts] if out is None else [a + p.tolist() for a, p in zip(out, parts)]
+        return out if out is not None else [[] for _ in range(self.N)]
 
     def raw_arrays(self, merged=False):
         """Crossing log of the last stop(s): per chunk (one per launch) a dict of flat numpy arrays
@@ -560,8 +663,10 @@ class Particle(Position):
             return
         if self.callback is None:
             self._launch(t_stop, self.max_iteration, emit_start=emit_start)
-            n_live, n_cross, n_max, _ = self._read_stats()
+            n_live, n_cross, n_max, n_flag = self._read_stats()
             self.__dict__["_crossings"] += int(n_cross)
+            if n_flag > n_max:
+                self._raise_for_status()
             if n_live == 0:
                 # the kernel touched nothing; like the reference, return before t := t_stop
                 if self.save_raw and self._raw and not emit_start:
@@ -613,6 +718,12 @@ class Particle(Position):
             )
         self._mark_stale(["t", "it"])
 
+    def _raise_for_status(self):
+        """Status bits the reference answers with an exception: a particle that left through the deepest staged
+        level (``Zl[izl_lin]`` raises IndexError, reference ``lagrangian.py:675``)."""
+        if bool((self._st["status"] & 128).any().item()):  # SDK_ST_OOB_LEVEL
+            raise IndexError("a particle left through the deepest vertical level (non-zero vertical velocity at the bottom)")
+
     def sync(self):
         """Lazy mode: wait for the queued stops, fold their counters in and raise deferred warnings."""
         tot = self._total.cpu().numpy().astype(np.int64)
@@ -620,6 +731,8 @@ class Particle(Position):
         self.__dict__["_crossings"] += int(tot[1])
         if tot[2] > 0:
             warnings.warn("maximum iteration count reached")
+        if tot[3] > tot[2]:
+            self._raise_for_status()
         return tot
 
     @property
@@ -637,7 +750,7 @@ class Particle(Position):
         object.__setattr__(p, "rel", RelCoord())
         for key, item in self.__dict__.items():
             if key in ("_st", "_stale", "_raw", "_crossings", "_stats", "_total"):
-                continue
+                continue  # (_perm / _inv are shared: they never change)
             if isinstance(item, np.ndarray):
                 if item.ndim == 1:
                     p.__dict__[key] = item.copy()
@@ -656,10 +769,25 @@ class Particle(Position):
         p.__dict__["_derived_ok"] = False
         return p
 
+    def record_snapshot(self, t_stop):
+        """Position and cell of every particle, now, as a :class:`RecordSnapshot` (one ``sdk_pack_records`` launch)."""
+        from .parallel import pack_records  # noqa: PLC0415
+
+        rec = pack_records(self._cparticles(), self.N, out_index=self._out_index(), device=self.ocedata._torch_device())
+        return RecordSnapshot(self.ocedata, t_stop, rec, self._st.get("face") is not None, self._has_dep)
+
     def to_list_of_time(
-        self, normal_stops, update_stops="default", return_in_between=True, dump_filename=False, store_kwarg={}
+        self, normal_stops, update_stops="default", return_in_between=True, dump_filename=False, store_kwarg={},
+        snapshots="auto", _on_stop=None,
     ):
-        """Integrate to a list of times, returning a snapshot per stop (reference ``lagrangian.py:804``)."""
+        """Integrate to a list of times, returning a snapshot per stop (reference ``lagrangian.py:804``).
+
+        ``snapshots`` (not in the reference): ``"full"`` returns clones of the whole particle state like the
+        reference does, ``"records"`` returns :class:`RecordSnapshot` objects (32 bytes per particle and stop, in
+        HBM), ``"auto"`` switches to records when the clones would take more than ``SNAPSHOT_CLONE_BUDGET`` bytes.
+        """
+        if snapshots not in ("auto", "full", "records"):
+            raise ValueError("snapshots must be 'auto', 'full' or 'records'")
         od = self.ocedata
         t0 = float(self._st["t"][0].item())
         t_min = np.minimum(np.min(normal_stops), t0)
@@ -690,6 +818,18 @@ class Particle(Position):
         stops, update = list(zip(*temp))
         self.get_u_du()
         to_return = []
+        state_bytes = sum(v.numel() * v.element_size() for v in self._st.values() if v is not None)
+        if snapshots == "auto":
+            snapshots = "records" if (state_bytes * len(stops) > self.SNAPSHOT_CLONE_BUDGET and not self.save_raw) else "full"
+
+        def keep(t_stop):
+            if _on_stop is not None:
+                _on_stop(t_stop)
+            elif snapshots == "records":
+                to_return.append(self.record_snapshot(t_stop))
+            else:
+                to_return.append(self.deepcopy())
+
         for i, tl in enumerate(stops):
             timestr = str(np.datetime64(round(tl), "s"))
             logging.info(timestr)
@@ -704,9 +844,9 @@ class Particle(Position):
                     self.update_uvw_array()
                     self.get_u_du()
                 if return_in_between:
-                    to_return.append(self.deepcopy())
+                    keep(tl)
             else:
-                to_return.append(self.deepcopy())
+                keep(tl)
             if self.save_raw:
                 self.empty_lists()
         return stops, to_return

@@ -46,10 +46,15 @@ def test_struct_sizes_match_header():
     L.sdk_struct_size.restype = ctypes.c_int64
     mirrors = [
         _lib.GridDesc, _lib.Velocity, _lib.Particles, _lib.AdvectParams, _lib.Log, _lib.Located, _lib.TrackIO,
-        interp.KernelDesc, interp.Field, interp.Points, _lib.BudgetFields, _lib.WallFields,
+        interp.KernelDesc, interp.Field, interp.Points, _lib.BudgetFields, _lib.WallFields, None, _lib.Exchange,
     ]
     for which, cls in enumerate(mirrors):
-        assert ctypes.sizeof(cls) == L.sdk_struct_size(which), cls.__name__
+        if cls is not None:
+            assert ctypes.sizeof(cls) == L.sdk_struct_size(which), cls.__name__
+    import numpy as np
+
+    assert np.dtype(_lib.SNAPSHOT_RECORD).itemsize == L.sdk_struct_size(12) == 32
+    assert np.dtype(_lib.LOG_RECORD).itemsize == 128
     assert L.sdk_struct_size(99) == -1
 
 

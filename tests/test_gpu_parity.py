@@ -149,43 +149,89 @@ def test_lazy_mode_list_of_time_matches_golden():
         compare_state(gold, f"s{i}_", snap)
 
 
-def test_pack_snapshot_device_equals_host():
-    """sdk_pack_snapshot (one launch) writes the same 32-byte records as the torch fallback."""
+def _cparticles_of(state, n):
+    from seaduck_b200 import _lib
+
+    p = _lib.Particles()
+    p.n = n
+    for k, v in state.items():
+        setattr(p, k, None if v is None else v.data_ptr())
+    return p
+
+
+def test_pack_records_device_equals_host():
+    """sdk_pack_records (one launch) writes the same 32-byte records as the numpy restatement, also scattered."""
     import torch
 
     from seaduck_b200 import parallel
 
     rng = np.random.default_rng(0)
-    n, n_pad = 1000, 1024
+    n = 1000
     host = {
-        "lon": torch.from_numpy(rng.uniform(-180, 180, n)), "lat": torch.from_numpy(rng.uniform(-90, 90, n)),
-        "dep": torch.from_numpy(rng.uniform(-5000, 0, n)),
-        "face": torch.from_numpy(rng.integers(0, 13, n).astype(np.int32)), "iy": torch.from_numpy(rng.integers(0, 4320, n).astype(np.int32)),
-        "ix": torch.from_numpy(rng.integers(0, 4320, n).astype(np.int32)), "izl": torch.from_numpy(rng.integers(0, 90, n).astype(np.int32)),
+        "lon": rng.uniform(-180, 180, n), "lat": rng.uniform(-90, 90, n), "dep": rng.uniform(-5000, 0, n),
+        "face": rng.integers(0, 13, n).astype(np.int32), "iy": rng.integers(0, 4320, n).astype(np.int32),
+        "ix": rng.integers(0, 4320, n).astype(np.int32), "izl": rng.integers(0, 90, n).astype(np.int32),
     }
-    dev = {k: v.cuda() for k, v in host.items()}
-    a = parallel.pack_snapshot(host, n_pad)
-    b = parallel.pack_snapshot(dev, n_pad).cpu()
-    assert torch.equal(a.view(torch.int64), b.view(torch.int64))
-    back = parallel.unpack_snapshot(b)
-    for k, v in host.items():
-        np.testing.assert_array_equal(back[k][:n], v.numpy(), err_msg=k)
+    dev = {k: torch.from_numpy(v).cuda() for k, v in host.items()}
+    a = parallel.pack_records_host(host)
+    b = parallel.pack_records(_cparticles_of(dev, n), n, device="cuda").cpu().numpy()
+    np.testing.assert_array_equal(a.view(np.uint8).reshape(n, 32), b)
+    perm = torch.from_numpy(rng.permutation(n).astype(np.int32)).cuda()
+    c = parallel.pack_records(_cparticles_of(dev, n), n, out_index=perm, device="cuda").cpu().numpy()
+    np.testing.assert_array_equal(c[perm.cpu().numpy()], b)
     # 2-D runs have no depth / level, single-face grids no face
     dev2 = dict(dev, dep=None, izl=None, face=None)
-    c = parallel.unpack_snapshot(parallel.pack_snapshot(dev2).cpu())
-    assert (c["dep"] == 0).all() and (c["izl"] == 0).all() and (c["face"] == 0).all()
-    np.testing.assert_array_equal(c["ix"], host["ix"].numpy())
+    d = parallel.unpack_records(parallel.pack_records(_cparticles_of(dev2, n), n, device="cuda"))
+    assert (d["dep"] == 0).all() and (d["izl"] == 0).all() and (d["face"] == 0).all()
+    np.testing.assert_array_equal(d["ix"], host["ix"])
+
+
+def test_record_exchange_on_one_rank():
+    """sdk_pack_ship / sdk_exchange_wait with world = 1 (the rank is its own peer): records land in the slot of the
+    step, the flags count up, a slot is reused once it has been released."""
+    import ctypes as C
+
+    import torch
+
+    from seaduck_b200 import _lib, parallel
+
+    rng = np.random.default_rng(5)
+    n, n_pad, slots = 3000, 3072, 2
+    L = _lib.lib()
+    buf = torch.zeros(4096 + slots * n_pad * 32, dtype=torch.uint8, device="cuda")
+    ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+    x = _lib.Exchange()
+    x.world, x.rank, x.n_slots, x.n_pad = 1, 0, slots, n_pad
+    x.signal[0], x.recv[0], x.ticket = buf.data_ptr(), buf.data_ptr() + 4096, ticket.data_ptr()
+    stream = _lib.current_stream()
+    for step in range(1, 6):
+        host = {
+            "lon": rng.uniform(-180, 180, n), "lat": rng.uniform(-90, 90, n), "dep": rng.uniform(-5000, 0, n),
+            "face": rng.integers(0, 13, n).astype(np.int32), "iy": rng.integers(0, 90, n).astype(np.int32),
+            "ix": rng.integers(0, 90, n).astype(np.int32), "izl": rng.integers(0, 50, n).astype(np.int32),
+        }
+        dev = {k: torch.from_numpy(v).cuda() for k, v in host.items()}
+        _lib.check(L.sdk_pack_ship(C.byref(x), C.byref(_cparticles_of(dev, n)), None, step, stream), "sdk_pack_ship")
+        _lib.check(L.sdk_exchange_wait(C.byref(x), step, 1, 0, stream), "sdk_exchange_wait")
+        slot = step % slots
+        got = buf[4096 + slot * n_pad * 32 : 4096 + (slot + 1) * n_pad * 32].cpu().numpy().reshape(n_pad, 32)
+        np.testing.assert_array_equal(got, parallel.pack_records_host(host, n_pad=n_pad).view(np.uint8).reshape(n_pad, 32))
+        _lib.check(L.sdk_exchange_wait(C.byref(x), step, 0, 1, stream), "sdk_exchange_wait")
+        words = buf[: _lib.SIGNAL_WORDS * 8].cpu().numpy().view(np.uint64)
+        assert words[_lib.SIGNAL_ARRIVED] == step and words[_lib.SIGNAL_CONSUMED] == step and words[_lib.SIGNAL_ERROR] == 0
+    assert int(ticket.item()) == 0
 
 
 @pytest.mark.parametrize("n", [1000, 300_000])
 def test_track_host_equals_particle_api(n):
     """sdk_track_host (host buffers in and out; chunked and pipelined over three streams for large
-    batches) gives exactly what Particle(...).to_next_stop(...) gives."""
+    batches) gives exactly what Particle(...).to_next_stop(...) gives -- as separate arrays, as 32-byte records,
+    and with the particles of every chunk cell-sorted on the device."""
     import ctypes as C
 
     import torch
 
-    from seaduck_b200 import _lib, synthetic
+    from seaduck_b200 import _lib, parallel, synthetic
 
     sd = _sd()
     ds = synthetic.llc(n=45, nz=12)
@@ -200,23 +246,87 @@ def test_track_host_equals_particle_api(n):
     hin = [pin(lon), pin(lat), pin(dep), pin(np.zeros(n))]
     outf = [torch.empty(n, dtype=torch.float64).pin_memory() for _ in range(3)]
     outi = [torch.empty(n, dtype=torch.int32).pin_memory() for _ in range(6)]
+    rec = torch.empty((n, 32), dtype=torch.uint8).pin_memory()
+    stats = torch.zeros(4, dtype=torch.int64).pin_memory()
+    scratch = torch.empty(int(L.sdk_track_scratch_bytes(n)), dtype=torch.uint8, device="cuda")
+    par = pt._params(200)
+    par.stats = None
+
+    def run(io):
+        _lib.check(
+            L.sdk_track_host(od.grid_handle(), C.byref(pt._vel), C.byref(io), None, 0, float(t_stop), C.byref(par), scratch.data_ptr(), _lib.current_stream()),
+            "sdk_track_host",
+        )
+
     io = _lib.TrackIO()
     io.n = n
     io.lon, io.lat, io.dep, io.t = (h.data_ptr() for h in hin)
     io.out_lon, io.out_lat, io.out_dep = (h.data_ptr() for h in outf)
     io.out_face, io.out_iy, io.out_ix, io.out_izl, io.out_ncross, io.out_status = (h.data_ptr() for h in outi)
-    scratch = torch.empty(int(L.sdk_track_scratch_bytes(n)), dtype=torch.uint8, device="cuda")
-    par = pt._params(200)
-    par.stats = None
-    _lib.check(
-        L.sdk_track_host(od.grid_handle(), C.byref(pt._vel), C.byref(io), None, 0, float(t_stop), C.byref(par), scratch.data_ptr(), _lib.current_stream()),
-        "sdk_track_host",
-    )
+    io.out_records, io.out_stats = rec.data_ptr(), stats.data_ptr()
+    run(io)
     for got, name in zip(outf, ("lon", "lat", "dep")):
         np.testing.assert_array_equal(got.numpy(), getattr(pt, name), err_msg=name)
     for got, name in zip(outi[:4], ("face", "iy", "ix", "izl_lin")):
         np.testing.assert_array_equal(got.numpy(), getattr(pt, name), err_msg=name)
-    assert int(outi[4].numpy().sum()) == pt.crossings
+    assert int(outi[4].numpy().sum()) == pt.crossings == int(stats[1])
+    for sort in (0, 1):
+        io2 = _lib.TrackIO()
+        io2.n, io2.sort = n, sort
+        io2.lon, io2.lat, io2.dep, io2.t = (h.data_ptr() for h in hin)
+        rec.zero_()
+        stats.zero_()
+        io2.out_records, io2.out_stats = rec.data_ptr(), stats.data_ptr()
+        run(io2)
+        back = parallel.unpack_records(rec.numpy())
+        for name, attr in (("lon", "lon"), ("lat", "lat"), ("dep", "dep"), ("face", "face"), ("iy", "iy"), ("ix", "ix"), ("izl", "izl_lin")):
+            np.testing.assert_array_equal(back[name], getattr(pt, attr), err_msg=f"{name} (sort={sort})")
+        assert int(stats[1]) == pt.crossings
+    # the sorted path refuses the separate arrays
+    io.sort = 1
+    assert L.sdk_track_host(od.grid_handle(), C.byref(pt._vel), C.byref(io), None, 0, float(t_stop), C.byref(par), scratch.data_ptr(), _lib.current_stream()) == -1
+
+
+def test_cell_sorted_particles_equal_plain():
+    """Particle(sort=True) keeps the device state in cell order; every attribute, snapshot and interpolation still
+    comes back in the caller's order and bit for bit equal to the unsorted run."""
+    sd = _sd()
+    case = cases.case_llc_time(n=4000)
+    runs = []
+    for sort in (False, True):
+        od = sd.OceData(case["ds"])
+        pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, sort=sort, **case["kw"])
+        assert (pt._perm is not None) == sort
+        stops, snaps = pt.to_list_of_time(normal_stops=case["stops"])
+        stops_r, recs = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, sort=sort, **case["kw"]).to_list_of_time(
+            normal_stops=case["stops"], snapshots="records")
+        tvals = pt.interpolate("T", sd.KnW()) if "T" in case["ds"].variables else None
+        runs.append((pt, snaps, recs, tvals))
+    (a, sa, ra, ta), (b, sb, rb, tb) = runs
+    assert a.crossings == b.crossings > 0
+    if sort:
+        key = (b._st["izl"].long() * 13 + b._st["face"].long())
+        assert int(b._perm.max()) == b.N - 1 and key.shape[0] == b.N
+    for x, y in zip(sa + [a], sb + [b]):
+        for k in cases.FINAL_INT + cases.FINAL_FLT + ["px", "py", "vol", "dx", "dy", "bzl_lin", "dzl_lin"]:
+            if getattr(x, k, None) is not None:
+                np.testing.assert_array_equal(getattr(y, k), getattr(x, k), err_msg=k)
+    # record snapshots: same positions and cells as the full clones, in both orders
+    assert len(ra) == len(rb) == len(sa)
+    for full, r1, r2 in zip(sa, ra, rb):
+        for k in ("lon", "lat", "dep", "face", "iy", "ix", "izl_lin"):
+            np.testing.assert_array_equal(getattr(r1, k), getattr(full, k), err_msg=k)
+            np.testing.assert_array_equal(getattr(r2, k), getattr(full, k), err_msg=k)
+        assert r1.N == full.N and (r1.t == full.t).all()
+        with pytest.raises(AttributeError):
+            r1.rx
+    if ta is not None:
+        np.testing.assert_array_equal(ta, tb)
+    # writing an attribute goes through the permutation as well
+    new_lon = a.lon + 0.125
+    a.lon, b.lon = new_lon, new_lon
+    np.testing.assert_array_equal(b._st["lon"][b._inv].cpu().numpy(), new_lon)
+    np.testing.assert_array_equal(b.lon, a.lon)
 
 
 def test_sharded_run_equals_single_run():
@@ -239,9 +349,11 @@ def test_sharded_run_equals_single_run():
     blocks = []
     for r in range(world):
         idx = parallel.shard_indices(n, world, r, seed=5)
-        pt = sd.Particle(x=lon[idx], y=lat[idx], z=dep[idx], t=np.zeros(len(idx)), data=od, **kw)
+        pt = sd.Particle(x=lon[idx], y=lat[idx], z=dep[idx], t=np.zeros(len(idx)), data=od, sort=bool(r % 2), **kw)
         pt.to_next_stop(t_stop)
-        blocks.append(parallel.pack_snapshot(pt._st, n_pad=per))
+        rec = torch.zeros((per, 32), dtype=torch.uint8, device="cuda")
+        parallel.pack_records(pt._cparticles(), pt.N, out=rec, out_index=pt._out_index())
+        blocks.append(rec)
     out = parallel.unshard(torch.stack(blocks), n, world, seed=5)
     for name, ref in (("lon", whole.lon), ("lat", whole.lat), ("dep", whole.dep), ("face", whole.face), ("iy", whole.iy),
                       ("ix", whole.ix), ("izl", whole.izl_lin)):

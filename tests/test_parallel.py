@@ -3,6 +3,7 @@
 import os
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -26,14 +27,12 @@ def _worker(rank, world, n, port, ret):
         "ix": torch.tensor((idx * 7) % 90, dtype=torch.int32),
         "izl": torch.tensor(idx % 50, dtype=torch.int32),
     }
-    g = parallel.all_gather_snapshot(parallel.pack_snapshot(state, n_pad=per))
-    # the overlapped gatherer takes the collective route on CPU and must deliver the same thing
-    sg = parallel.SnapshotGather(parallel.SNAPSHOT_ROWS, per, torch.device("cpu"))
-    assert sg.mode == "collective"
-    sg.post(parallel.pack_snapshot(state, n_pad=per), slot=1)
-    sg.wait()
-    assert torch.equal(sg.result(1), g)
-    out = parallel.unshard(g, n, world, seed=3)
+    # the product packs on the device and ships with sdk_pack_ship; here the host restatement of the record and a
+    # gloo all-gather stand in for them: what is under test is the slicing and its inverse
+    mine = torch.from_numpy(parallel.pack_records_host({k: v.numpy() for k, v in state.items()}, n_pad=per).view(np.uint8).copy())
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    out = parallel.unshard([p.numpy() for p in parts], n, world, seed=3)
     ids = np.arange(n)
     ok = (
         np.array_equal(out["lon"], ids * 0.5)
@@ -60,3 +59,32 @@ def test_shards_are_disjoint_and_complete():
     allidx = np.concatenate(parts)
     assert len(allidx) == n and len(set(allidx.tolist())) == n
     assert parallel.shard_indices(0, 2, 0).size == 0  # empty input
+
+
+def test_record_layout_round_trip():
+    """32-byte record: three doubles and a cell word with 6 / 20 / 20 / 12 bits (include/seaduck_b200.h)."""
+    rng = np.random.default_rng(1)
+    n = 257
+    state = {
+        "lon": rng.uniform(-180, 180, n), "lat": rng.uniform(-90, 90, n), "dep": rng.uniform(-6000, 0, n),
+        "face": rng.integers(0, 13, n), "iy": rng.integers(0, 17280, n), "ix": rng.integers(0, 1 << 20, n),
+        "izl": rng.integers(0, 4096, n),
+    }
+    rec = parallel.pack_records_host(state, n_pad=260)
+    assert rec.dtype.itemsize == 32 and rec.shape == (260,)
+    back = parallel.unpack_records(rec.view(np.uint8))
+    for k, v in state.items():
+        np.testing.assert_array_equal(back[k][:n], v, err_msg=k)
+    assert (back["lon"][n:] == 0).all() and (back["ix"][n:] == 0).all()
+    # missing members read as zero (2-D runs have no depth / level, single-face grids no face)
+    rec2 = parallel.unpack_records(parallel.pack_records_host(dict(state, dep=None, izl=None, face=None)))
+    assert (rec2["dep"] == 0).all() and (rec2["izl"] == 0).all() and (rec2["face"] == 0).all()
+
+
+def test_grids_that_do_not_fit_the_record_are_refused():
+    from seaduck_b200.topology import Topology
+
+    parallel.check_grid_fits_record(Topology.from_shape((13, 4320, 4320)), n_zl=90)
+    parallel.check_grid_fits_record(Topology.from_shape((8640, 17280)))
+    with pytest.raises(ValueError):
+        parallel.check_grid_fits_record(Topology.from_shape((10, 10)), n_zl=5000)
