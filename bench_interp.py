@@ -43,8 +43,12 @@ def parse():
     return ap.parse_args()
 
 
-def main():
-    a = parse()
+def measure(points=10_000_000, grid=270, levels=50, steps=10, warmup=3, cpu_sample=20_000, cpu_baseline=True, e2e=True,
+            presorted=False, clock_sampler=None):
+    """Run the benchmark in this process and return the JSON line as a dict (bench.py calls this for its
+    `extra_workloads`; `clock_sampler` is a started-on-demand NVML sampler thread of the caller)."""
+    a = argparse.Namespace(points=points, grid=grid, levels=levels, steps=steps, warmup=warmup, cpu_sample=cpu_sample,
+                           no_cpu_baseline=not cpu_baseline, no_e2e=not e2e, sorted=presorted)
     import torch
 
     import seaduck_b200 as sd
@@ -53,8 +57,6 @@ def main():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import cases_interp as ci
 
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
     t0 = time.perf_counter()
     ds = synthetic.llc(n=a.grid, nz=a.levels, land_blobs=True, tracers=True)
     od = sd.OceData(ds)
@@ -80,6 +82,8 @@ def main():
     for _ in range(a.warmup):
         out = step()
     torch.cuda.synchronize()
+    if clock_sampler is not None:
+        clock_sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
@@ -87,6 +91,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / a.steps
+    clocks = clock_sampler.finish() if clock_sampler is not None else None
     value = n / (ms * 1e-3)
     nan_frac = float(torch.isnan(out[0]).float().mean().item())
 
@@ -111,6 +116,8 @@ def main():
                      "algorithmic_bytes_per_point": ALGO_BYTES_PER_POINT},
         "gpu_launches": 3 * a.steps,
     }
+    if clocks is not None:
+        line["clocks"] = clocks
     if not a.no_e2e:
         # host arrays in -> locate -> interpolate -> host arrays out (what OceInterp does for a user)
         tt = []
@@ -146,6 +153,19 @@ def main():
                                 "sample": f"{m} of the same points, interpolation only (oracle/interp_oracle.py, numpy + C topology walk); "
                                           f"locating them took {t1 - t0:.1f} s more",
                                 "parity_on_sample_max_rel_err": worst}
+    return line
+
+
+def main():
+    a = parse()
+    import torch
+
+    torch.cuda.set_device(0)
+    sys.path.insert(0, ROOT)
+    from bench import ClockSampler
+
+    line = measure(points=a.points, grid=a.grid, levels=a.levels, steps=a.steps, warmup=a.warmup, cpu_sample=a.cpu_sample,
+                   cpu_baseline=not a.no_cpu_baseline, e2e=not a.no_e2e, presorted=a.sorted, clock_sampler=ClockSampler(0))
     print(json.dumps(line))
 
 

@@ -49,6 +49,25 @@ class Deferred:
         return a.astype(self.dtype) if self.dtype is not None else a
 
 
+class DeviceVar:
+    """A data variable that lives on the GPU only (``OceData.stage_device_field``): what ``od[name]`` returns for it.
+    Carries the dimension names and the shape, like the labelled arrays of the dataset do."""
+
+    def __init__(self, tensor, dims):
+        self.tensor, self.dims = tensor, tuple(dims)
+        if len(self.dims) != tensor.ndim:
+            raise ValueError(f"dims {self.dims} do not match a tensor of shape {tuple(tensor.shape)}")
+
+    shape = property(lambda self: tuple(self.tensor.shape))
+    ndim = property(lambda self: self.tensor.ndim)
+    nbytes = property(lambda self: self.tensor.numel() * self.tensor.element_size())
+    dtype = property(lambda self: np.dtype(str(self.tensor.dtype).replace("torch.", "")))
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.tensor.cpu().numpy()
+        return a if dtype is None else a.astype(dtype, copy=False)
+
+
 class RelCoord(dict):
     """Relative coordinates: dictionary with attribute access (reference ``ocedata.py:34``).
     Values may be :class:`Deferred`; every read access materialises them."""
@@ -170,6 +189,7 @@ class OceData:
         self._field_cache = {}
         self._interp_cache = {}  # rim tables and masks of the interpolation kernel
         self._grid_handle = None
+        self._device_vars = {}  # name -> DeviceVar (fields staged on the GPU without a host copy)
         readiness = self.check_readiness()
         self.readiness = readiness
         if readiness:
@@ -205,6 +225,8 @@ class OceData:
         varsdict = vars(self)
         if key in varsdict.keys():
             return object.__getattribute__(self, key)
+        if key in varsdict.get("_device_vars", ()):
+            return self._device_vars[key]
         if key in self.alias.keys():
             return self._ds[self.alias[key]]
         return self._ds[key]
@@ -257,17 +279,18 @@ class OceData:
     # ---- grid extraction ----------------------------------------------------------------------
     def _grid2array(self):
         if self.readiness["h"] == "oceanparcel":
+            # (np.asarray: no second host copy of a grid that already is float32 -- LLC4320 is 1 GB per array)
             for var in ["XC", "YC", "XG", "YG"]:
-                self[var] = np.array(self[var], dtype="float32")
+                self[var] = np.asarray(self[var], dtype="float32")
             for var in ["rA", "CS", "SN"]:
                 try:
-                    self[var] = np.array(self[var], dtype="float32")
+                    self[var] = np.asarray(self[var], dtype="float32")
                 except KeyError:
                     logging.info("no %s in dataset, skip", var)
                     self[var] = None
             try:
-                self.dX = np.array(self["dXG"], dtype="float32")
-                self.dY = np.array(self["dYG"], dtype="float32")
+                self.dX = np.asarray(self["dXG"], dtype="float32")
+                self.dY = np.asarray(self["dYG"], dtype="float32")
             except KeyError:
                 self.dX = None
                 self.dY = None
@@ -473,6 +496,14 @@ class OceData:
             del self._field_cache[k]
         self._field_cache[key] = value
 
+    def stage_device_field(self, name, tensor, dims):
+        """Register a data variable that already is on the GPU (e.g. written there by a model or generated there):
+        no host copy is made or needed; ``dims`` as in the dataset (``("time", "face", "Y", "Xp1")`` ...)."""
+        if tensor.device != self._torch_device():
+            raise ValueError(f"{name}: tensor on {tensor.device}, the dataset lives on {self._torch_device()}")
+        self._device_vars[name] = DeviceVar(tensor.contiguous(), dims)
+        self._field_cache = {k: v for k, v in self._field_cache.items() if k[0] != name}
+
     def device_field(self, name, time_slice=None):
         """Device copy of a data variable (optionally a slab of snapshots), cached.
 
@@ -482,12 +513,17 @@ class OceData:
         """
         import torch  # noqa: PLC0415
 
+        staged = self._device_vars.get(name)
+        if staged is not None:
+            return staged.tensor if time_slice is None else staged.tensor[time_slice]
         key = self._slab_key(name, time_slice)
         hit = self._field_cache.get(key)
         if hit is not None:
             if isinstance(hit, tuple):  # (tensor, event, pinned staging buffer) from prefetch_field
                 t, ev, _ = hit
-                torch.cuda.current_stream(t.device).wait_event(ev)
+                cur = torch.cuda.current_stream(t.device)
+                cur.wait_event(ev)
+                t.record_stream(cur)  # allocated under the copy stream, used on this one from now on
                 self._field_cache[key] = t
                 return t
             return hit
@@ -502,7 +538,7 @@ class OceData:
         import torch  # noqa: PLC0415
 
         key = self._slab_key(name, time_slice)
-        if key in self._field_cache:
+        if key in self._field_cache or name in self._device_vars:
             return
         dev = self._torch_device()
         if getattr(self, "_copy_stream", None) is None:

@@ -23,7 +23,7 @@ from . import minixr
 
 R_EARTH = 6371e3
 
-__all__ = ["gyre", "overturning_cell", "llc", "rectilinear", "llc_seed_particles"]
+__all__ = ["gyre", "overturning_cell", "llc", "llc_surface_device", "rectilinear", "llc_seed_particles"]
 
 
 def _dataset(coords, data_vars, as_xarray=False):
@@ -499,3 +499,143 @@ def llc_seed_particles(ds, num, seed=1, lat_range=(-70.0, 85.0), depth_range=(5.
     dep = -rng.uniform(depth_range[0], depth_range[1], num)
     del wet_only, ds
     return lon, lat, dep
+
+
+# ----------------------------------------------------------------------------------------------
+# the same LLC surface dataset, built on the GPU (BASELINE.json configs[3]: LLC4320 x 2 snapshots)
+# ----------------------------------------------------------------------------------------------
+def _t_face_lonlat(torch, face, fy, fx, n):
+    """torch restatement of :func:`_llc_face_lonlat` (same formulas, float64 on the device)."""
+    dlat = (_LAT_N - _LAT_S) / (3 * n)
+    dlon = 90.0 / n
+    if face < 6:
+        lon = _SECTOR_W[0 if face < 3 else 1] + fx * dlon
+        lat = _LAT_S + ((face % 3) * n + fy) * dlat
+    elif face > 6:
+        lon = _SECTOR_W[2 if face < 10 else 3] + fy * dlon
+        lat = _LAT_N - (((face - 7) % 3) * n + fx) * dlat
+    else:
+        a = (fx - n / 2) / (n / 2)
+        b = (fy - n / 2) / (n / 2)
+        r = torch.maximum(a.abs(), b.abs())
+        rs = torch.where(r == 0, torch.ones_like(r), r)
+        bottom = (b <= -a.abs()) & (r > 0)
+        right = (a >= b.abs()) & ~bottom & (r > 0)
+        top = (b >= a.abs()) & ~bottom & ~right & (r > 0)
+        angle = torch.where(bottom, 45 * a / rs, torch.where(right, 90 + 45 * b / rs, torch.where(top, 180 - 45 * a / rs, 270 - 45 * b / rs)))
+        angle = torch.where(r == 0, torch.zeros_like(angle), angle)
+        lon = _CAP_LON0 + angle
+        lat = 90.0 - (90.0 - _LAT_N) * r
+    lon, lat = torch.broadcast_tensors(lon, lat)
+    lon = torch.remainder(lon + 180.0, 360.0) - 180.0
+    return lon, lat
+
+
+def _t_sph2cart(torch, lon, lat):
+    lam, phi = torch.deg2rad(lon), torch.deg2rad(lat)
+    return torch.stack([torch.cos(phi) * torch.cos(lam), torch.cos(phi) * torch.sin(lam), torch.sin(phi)], dim=-1)
+
+
+def _t_flow_rot(torch, p):
+    """Rotational part of :func:`_flow_cart` at unit vectors ``p`` (unit amplitude)."""
+    x, y, z = p[..., 0], p[..., 1], p[..., 2]
+    lam = torch.atan2(y, x)
+    cphi = torch.sqrt(torch.clamp(x * x + y * y, min=1e-30))
+    ue = cphi * (1 + 0.5 * torch.sin(3 * lam))
+    vn = 0.3 * torch.sin(2 * lam) * cphi**2
+    east = torch.stack([-torch.sin(lam), torch.cos(lam), torch.zeros_like(lam)], dim=-1)
+    north = torch.stack([-z * torch.cos(lam), -z * torch.sin(lam), cphi], dim=-1)
+    return ue[..., None] * east + vn[..., None] * north
+
+
+def llc_surface_device(n=4320, nt=3, u0=0.5, dtype=np.float64, device="cuda"):
+    """:func:`llc` with ``nz = 0`` for grids too large to go through host memory in float64: the geometry and the
+    analytic flow are evaluated face by face on the GPU.  Returns ``(ds, fields)``: ``ds`` holds the float32 grid
+    (``XC YC XG YG dxG dyG rA CS SN`` -- the precision ``OceData`` keeps them in -- and ``time``), ``fields`` maps
+    ``utrans`` / ``vtrans`` to ``(dims, device tensor [nt, 13, n, n])`` for ``OceData.stage_device_field``.
+    Same formulas as :func:`llc` (checked against it at small ``n`` in ``tests/test_gpu_streamfunction.py``).
+    """
+    import torch  # noqa: PLC0415
+
+    from .topology import Topology  # noqa: PLC0415
+
+    dev = torch.device(device)
+    tdt = torch.float64 if np.dtype(dtype) == np.float64 else torch.float32
+    idx = torch.arange(n + 1, dtype=torch.float64, device=dev)
+    gy, gx = idx[:, None], idx[None, :]
+    cy, cx = gy[:n] + 0.5, gx[:, :n] + 0.5
+    names = ("XC", "YC", "XG", "YG", "dxG", "dyG", "rA", "CS", "SN")
+    host = {k: np.empty((13, n, n), np.float32) for k in names}
+    land = torch.from_numpy(_llc_land(n)).to(dev)
+    # land flag of the cell to the left of column 0 / below row 0 of every face (across faces), from the host topology
+    tp = Topology.from_shape((13, n, n))
+    f_e = np.repeat(np.arange(13), n)
+    k_e = np.tile(np.arange(n), 13)
+    zeros = np.zeros_like(k_e)
+    lf, ly, lx = tp.ind_tend_vec((f_e, k_e, zeros), np.full(f_e.size, 2), swallow=True)
+    df, dy_, dx_ = tp.ind_tend_vec((f_e, zeros, k_e), np.full(f_e.size, 1), swallow=True)
+    no_left = torch.from_numpy(((lf == f_e) & (lx == 0)).reshape(13, n)).to(dev)
+    no_down = torch.from_numpy(((df == f_e) & (dy_ == 0)).reshape(13, n)).to(dev)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    left_land = land[t(lf), t(ly), t(lx)].reshape(13, n)
+    down_land = land[t(df), t(dy_), t(dx_)].reshape(13, n)
+    scale = 1.0 + 0.3 * np.sin(np.arange(max(nt, 1)) * 1.3)
+    shape = (nt, 13, n, n) if nt > 0 else (13, n, n)
+    utr = torch.empty(shape, dtype=tdt, device=dev)
+    vtr = torch.empty(shape, dtype=tdt, device=dev)
+    for f in range(13):
+        lon_g, lat_g = _t_face_lonlat(torch, f, gy, gx, n)
+        lon_c, lat_c = _t_face_lonlat(torch, f, cy, cx, n)
+        pg = _t_sph2cart(torch, lon_g, lat_g)
+        tx = pg[:n, 1:] - pg[:n, :n]
+        ty = pg[1:, :n] - pg[:n, :n]
+        dxg = torch.linalg.norm(tx, dim=-1) * R_EARTH
+        dyg = torch.linalg.norm(ty, dim=-1) * R_EARTH
+        d1 = pg[1:, 1:] - pg[:n, :n]
+        area = (0.5 * torch.linalg.norm(torch.linalg.cross(tx, d1), dim=-1) + 0.5 * torch.linalg.norm(torch.linalg.cross(d1, ty), dim=-1)) * R_EARTH**2
+        mu = pg[:n, :n] + 0.5 * ty
+        mu = mu / torch.linalg.norm(mu, dim=-1, keepdim=True)
+        mv = pg[:n, :n] + 0.5 * tx
+        mv = mv / torch.linalg.norm(mv, dim=-1, keepdim=True)
+        nu = torch.linalg.cross(ty, mu)
+        nv = torch.linalg.cross(mv, tx)
+        nu = torch.nan_to_num(nu / torch.linalg.norm(nu, dim=-1, keepdim=True))
+        nv = torch.nan_to_num(nv / torch.linalg.norm(nv, dim=-1, keepdim=True))
+        xdir = 0.5 * (pg[:n, 1:] + pg[1:, 1:]) - 0.5 * (pg[:n, :n] + pg[1:, :n])
+        lam, phi = torch.deg2rad(lon_c), torch.deg2rad(lat_c)
+        east = torch.stack([-torch.sin(lam), torch.cos(lam), torch.zeros_like(lam)], dim=-1)
+        north = torch.stack([-torch.sin(phi) * torch.cos(lam), -torch.sin(phi) * torch.sin(lam), torch.cos(phi)], dim=-1)
+        ce, cn = (xdir * east).sum(-1), (xdir * north).sum(-1)
+        nrm = torch.hypot(ce, cn)
+        nrm = torch.where(nrm == 0, torch.ones_like(nrm), nrm)
+        for key, val in (("XC", lon_c), ("YC", lat_c), ("XG", lon_g[:n, :n]), ("YG", lat_g[:n, :n]), ("dxG", dxg), ("dyG", dyg),
+                         ("rA", area), ("CS", ce / nrm), ("SN", cn / nrm)):
+            host[key][f] = val.to(torch.float32).cpu().numpy()
+        # a wall carries flow only if the cells on both sides are wet
+        own = land[f].to(torch.float64)
+        wet_u = own.clone()
+        wet_u[:, 1:] *= own[:, :-1]
+        wet_u[:, 0] *= torch.where(no_left[f], torch.zeros_like(own[:, 0]), left_land[f].to(torch.float64))
+        wet_v = own.clone()
+        wet_v[1:, :] *= own[:-1, :]
+        wet_v[0, :] *= torch.where(no_down[f], torch.zeros_like(own[0, :]), down_land[f].to(torch.float64))
+        u_face = u0 * (_t_flow_rot(torch, mu) * nu).sum(-1) * wet_u * dyg
+        v_face = u0 * (_t_flow_rot(torch, mv) * nv).sum(-1) * wet_v * dxg
+        if nt > 0:
+            for k in range(nt):
+                utr[k, f] = (u_face * scale[k]).to(tdt)
+                vtr[k, f] = (v_face * scale[k]).to(tdt)
+        else:
+            utr[f], vtr[f] = u_face.to(tdt), v_face.to(tdt)
+        del pg, tx, ty, d1, mu, mv, nu, nv, xdir, east, north
+    coords = dict(
+        XC=(["face", "Y", "X"], host["XC"]), YC=(["face", "Y", "X"], host["YC"]),
+        XG=(["face", "Yp1", "Xp1"], host["XG"]), YG=(["face", "Yp1", "Xp1"], host["YG"]),
+        dxG=(["face", "Yp1", "X"], host["dxG"]), dyG=(["face", "Y", "Xp1"], host["dyG"]),
+        rA=(["face", "Y", "X"], host["rA"]), CS=(["face", "Y", "X"], host["CS"]), SN=(["face", "Y", "X"], host["SN"]),
+    )
+    lead = ["time"] if nt > 0 else []
+    if nt > 0:
+        coords["time"] = (["time"], np.arange(nt) * 86400.0 * 10)
+    fields = {"utrans": (lead + ["face", "Y", "Xp1"], utr), "vtrans": (lead + ["face", "Yp1", "X"], vtr)}
+    return minixr.Dataset(coords=coords, data_vars={}), fields

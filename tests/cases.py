@@ -84,6 +84,22 @@ def case_llc_surface2d(n=300, ngrid=48):
     )
 
 
+def case_llc_surface_time(n=300, ngrid=40):
+    """The shape of BASELINE.json configs[3] (LLC4320 surface, two time snapshots used, reference
+    docs/sciserver_notebooks/LLC4320.md:91-131) at test size: 2-D transports with a time axis, stops every few
+    hours, the run crosses time_midp[0] so the velocity slab is swapped once."""
+    ds = synthetic.llc(n=ngrid, nz=0, nt=3, u0=6.0)
+    lon, lat, _ = synthetic.llc_seed_particles(ds, n, seed=14)
+    return dict(
+        name="llc_surface_time",
+        ds=ds,
+        x=lon, y=lat, z=np.full(n, -1.0), t=np.full(n, 4.5 * DAY),
+        stops=[4.625 * DAY, 4.875 * DAY, 5.25 * DAY, 6.0 * DAY],
+        kw=dict(uname="utrans", vname="vtrans", wname=None, transport=True),
+        list_of_time=True,
+    )
+
+
 def case_llc_bool_array(ngrid=24, nz=8):
     """Particles seeded by ``from_bool_array`` (reference eulerian.py:219): volume-weighted random
     positions inside a masked region, then advected."""
@@ -171,7 +187,7 @@ def case_local_cartesian(n=300, ngrid=24, nz=6):
 # cases only the CPU oracle takes (none: the device runs all three horizontal schemes)
 ORACLE_ONLY_CASES = []
 
-ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_bool_array, case_llc_callback, case_channel_kickback, case_rectilinear, case_local_cartesian]
+ALL_CASES = [case_gyre, case_overturning, case_llc_transport, case_llc_velocity, case_llc_time, case_llc_surface2d, case_llc_surface_time, case_llc_bool_array, case_llc_callback, case_channel_kickback, case_rectilinear, case_local_cartesian]
 
 LOG_INT = ["fc", "it", "izl", "iy", "ix", "vs"]
 LOG_FLT = ["rzl", "rx", "ry", "tt", "uu", "vv", "ww", "du", "dv", "dw", "xx", "yy", "zz"]
