@@ -296,6 +296,8 @@ def run_batches(ctx, a, kind="c2", with_e2e=False, with_orders=False):
         pt.tuning = dict(refill_threshold=a.refill, blocks_per_sm=a.blocks_per_sm, threads_per_block=a.threads)
         return pt, (lon, lat, dep)
 
+    fused = os.environ.get("SDK_BENCH_EXCH", "fused") == "fused"  # (experiments: "kernel" = separate sdk_pack_ship launch)
+
     batches, host_inputs = [], None
     for b in range(nb):
         pt, xyz = make_batch(b, sort)
@@ -307,7 +309,10 @@ def run_batches(ctx, a, kind="c2", with_e2e=False, with_orders=False):
     saved = [{k: (None if v is None else v.clone()) for k, v in pt._st.items()} for pt in batches]
     exchange = None
     if world > 1 and not a.no_gather:
-        exchange = parallel.RecordExchange(n, dev, slots=2, multicast=not a.no_multicast)
+        exchange = parallel.RecordExchange(n, dev, slots=int(os.environ.get("SDK_BENCH_SLOTS", "2")), multicast=not a.no_multicast)
+    if exchange is not None and fused and not a.save_raw:
+        for pt in batches:
+            pt.ship_to(exchange)  # the advection kernel stores the output records into every rank's buffer itself
 
     def restore(group, b):
         for k, v in group[1][b].items():
@@ -323,13 +328,14 @@ def run_batches(ctx, a, kind="c2", with_e2e=False, with_orders=False):
             pt.empty_lists()  # the log of this step only (the reference's to_list_of_time does the same)
         pt.to_next_stop(t_stop)
         if exchange is not None:
-            # output records of all ranks -- the only exchange of the path: packed and stored into every
-            # rank's receive buffer by one kernel on a side stream, while the next step's kernel runs
+            # output records of all ranks -- the only exchange of the path.  Fused: the advection kernel has
+            # stored them into every rank's receive buffer while it ran; what is left is a one-warp kernel on a side
+            # stream that waits for the other ranks' blocks of this step and frees the slot.
             done = torch.cuda.Event()
             done.record()
             ctx.side.wait_event(done)
             with torch.cuda.stream(ctx.side):
-                s = exchange.ship(pt._cparticles(), out_index=pt._out_index())
+                s = pt.last_ship_step if pt.__dict__.get("_exchange") is not None else exchange.ship(pt._cparticles(), out_index=pt._out_index())
                 exchange.wait(s, release=True)  # everybody's records of this step are here; the slot is free again
 
     def timed(group):
@@ -392,11 +398,14 @@ def run_batches(ctx, a, kind="c2", with_e2e=False, with_orders=False):
         "roofline": roof, "clocks": clocks, "step_ms_first10": [round(x, 3) for x in step_ms[:10]], "host_wall_s": wall,
         "batches": f"{nb} distinct batches resident in HBM" + (", reused cyclically with a device-side state restore inside the timed region" if reuse else ", one per step"),
         "particle_order": "seeding order in; kept in cell order on the device by the product (Particle(sort=...), sdk_cell_sort)" if sorted_by_product else "seeding order (no sort)",
-        "collective": (f"sdk_pack_ship per step: 32-byte records stored into every rank's receive buffer from inside the packing kernel ({exchange.mode}), "
-                       f"on a side stream, overlapped with the next step; {32 * n * world} B received per rank and step") if exchange is not None else "none",
+        "collective": ((f"fused into the advection kernel (sdk_advect_params.ship): the write-back of every finished particle also stores its 32-byte record into "
+                        f"every rank's receive buffer ({exchange.mode})" if (fused and not a.save_raw) else
+                        f"sdk_pack_ship per step on a side stream ({exchange.mode})")
+                       + f"; one-warp arrival wait + slot release per step on a side stream; {32 * n * world} B received per rank and step") if exchange is not None else "none",
         # this package's kernels inside the timed region, per rank and step: advect_kernel (two passes with the crossing
-        # log: count, then fill) + finish_stop_kernel in lazy mode + pack_ship_kernel and exchange_wait_kernel at N > 1
-        "gpu_launches": a.steps * world * ((2 if a.save_raw else 1) + (0 if (a.eager or a.save_raw) else 1) + (2 if exchange is not None else 0)),
+        # log: count, then fill) + finish_stop_kernel in lazy mode + exchange_wait_kernel at N > 1 (+ pack_ship_kernel when not fused)
+        "gpu_launches": a.steps * world * ((2 if a.save_raw else 1) + (0 if (a.eager or a.save_raw) else 1)
+                                           + ((1 if (fused and not a.save_raw) else 2) if exchange is not None else 0)),
     }
 
     if a.save_raw:
@@ -527,6 +536,7 @@ def run_stops(ctx, a, grid, particles, hours, nt=3):
         else:
             if exchange is None:
                 exchange = parallel.RecordExchange(n, dev, slots=2, multicast=not a.no_multicast)
+            pt.ship_to(exchange)
             snaps = []
 
             def on_stop(t_stop):
@@ -534,12 +544,12 @@ def run_stops(ctx, a, grid, particles, hours, nt=3):
                 done.record()
                 ctx.side.wait_event(done)
                 with torch.cuda.stream(ctx.side):
-                    s = exchange.ship(pt._cparticles(), out_index=pt._out_index())
-                    exchange.wait(s, release=True)
-                snaps.append(s)
+                    exchange.wait(pt.last_ship_step, release=True)
+                snaps.append(pt.last_ship_step)
 
             pt.to_list_of_time(stops, _on_stop=on_stop)
             torch.cuda.current_stream().wait_stream(ctx.side)
+            pt.ship_to(None)
         e1.record()
         torch.cuda.synchronize()
         ctx.barrier()
@@ -571,7 +581,7 @@ def run_stops(ctx, a, grid, particles, hours, nt=3):
         mx2, sm2 = ctx.reduce([ms2, float(cross2)])
         exchange.check()
         out["all_gather_variant"] = {"value": sm2[1] / (mx2[0] * 1e-3), "ms_per_step": mx2[0] / K,
-                                     "collective": f"sdk_pack_ship per stop ({exchange.mode}): {32 * n * world} B received per rank and stop"}
+                                     "collective": f"fused into the advection kernel of every stop ({exchange.mode}): {32 * n * world} B received per rank and stop"}
     # the kernel alone, on a copy of the state, one more stop ahead
     L = _lib.lib()
     keep = {k: (None if v is None else v.clone()) for k, v in pt._st.items()}

@@ -133,6 +133,8 @@ typedef struct sdk_particles {
     const int32_t *active; /* optional: particles with active[i] == 0 are left untouched (callback) */
 } sdk_particles;
 
+struct sdk_exchange; /* declared with the record exchange further down */
+
 typedef struct sdk_advect_params {
     double tol;            /* 1e-4  (lagrangian.py:754) */
     double trim_tol;       /* 1e-14 (lagrangian.py:765) */
@@ -152,6 +154,14 @@ typedef struct sdk_advect_params {
     /* optional DEVICE array of 4 counters, ADDED to by the call: particles live at the start,
      * wall crossings, particles that hit max_iteration, particles with a non-zero status */
     uint64_t *stats;
+    /* Fused output exchange (optional, NULL = off): when a particle is written back at the end of its leg, the
+     * kernel also stores its 32-byte output record into block [ship_step % n_slots][rank] of every rank's receive
+     * buffer (position ship_index ? ship_index[i] : i) -- the advection kernel is its own sdk_pack_ship, the transfer
+     * rides on the compute instead of following it.  Same protocol as sdk_pack_ship: waits for the slot to be free
+     * before the first store, posts arrived[rank] = ship_step after the last.  Not with a log or an `active` mask. */
+    const struct sdk_exchange *ship;
+    const int32_t *ship_index;
+    uint64_t ship_step;
 } sdk_advect_params;
 
 /* One record of the crossing log: the 19 fields Particle.note_taking appends (seaduck/lagrangian.py:301),

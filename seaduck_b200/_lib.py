@@ -91,6 +91,9 @@ class AdvectParams(C.Structure):
         ("reserve_sms", C.c_int32),
         ("keep_status", C.c_int32),
         ("stats", vp),
+        ("ship", vp),
+        ("ship_index", vp),
+        ("ship_step", C.c_uint64),
     ]
 
 

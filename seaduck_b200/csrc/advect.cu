@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include "advect_args.cuh"
+#include "exchange_device.cuh"
 
 namespace sdk {
 
@@ -598,7 +599,9 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
 #define SDK_ADVECT_INLINE_AXES 0
 #endif
 
-template <typename T, bool LOG, int P>
+// SHIP: the write-back of a finished particle also stores its 32-byte output record into every rank's receive
+// buffer (sdk_advect_params.ship): the exchange of a stop's output rides on the kernel that produces it.
+template <typename T, bool LOG, int P, bool SHIP = false>
 __global__ void __launch_bounds__(SDK_ADVECT_THREADS, SDK_ADVECT_MIN_BLOCKS)
 advect_kernel(const __grid_constant__ AdvectArgs a) {
     extern __shared__ __align__(16) float smem[];
@@ -606,7 +609,10 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
     float *sdZl = smem + a.g.n_zl;
     for (int k = threadIdx.x; k < a.g.n_zl; k += blockDim.x) sZl[k] = a.g.Zl[k];
     for (int k = threadIdx.x; k < a.g.n_z; k += blockDim.x) sdZl[k] = a.g.dZl[k];
+    __shared__ int ship_ok;
+    if (SHIP && threadIdx.x == 0) ship_ok = ship_slot_free(a.x, a.ship_step);
     __syncthreads();
+    const int64_t ship_at = SHIP ? ship_base(a.x, a.ship_step) : 0;
     double *cold_d = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + advect_smem_bytes(a.g.n_zl, a.g.n_z, 0)) + threadIdx.x;
     int *cold_i = reinterpret_cast<int *>(cold_d - threadIdx.x + kColdDoubles * blockDim.x) + threadIdx.x;
     (void)cold_i;
@@ -636,6 +642,12 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
                 // done (or out of iterations): write back and free the lane
                 if (live) s.status |= SDK_ST_MAX_ITER;
                 if (a.commit) store_lane<P>(a.p, a.has_dep, s);
+                if (SHIP && ship_ok) {
+                    const uint64_t cell = SDK_CELL_PACK((uint64_t)(uint32_t)s.f, (uint64_t)(uint32_t)s.iy, (uint64_t)(uint32_t)s.ix,
+                                                        (uint64_t)(uint32_t)s.izl);
+                    ship_record(a.x, ship_at + (a.ship_index ? (int64_t)a.ship_index[s.pid] : (int64_t)s.pid), make_double2(s.lon, s.lat),
+                                make_double2(s.dep, __longlong_as_double((long long)cell)));
+                }
                 if (a.p.status) a.p.status[s.pid] = s.status;
                 if (a.p.niter) a.p.niter[s.pid] = s.niter;
                 if (a.p.ncross) a.p.ncross[s.pid] = s.ncross;
@@ -738,6 +750,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
             if (acc_flag) atomicAdd(a.stats + 3, (unsigned long long)acc_flag);
         }
     }
+    if (SHIP) ship_finish(a.x, a.ship_step);
 }
 
 // get_u_du on its own (after Particle.update_uvw_array swapped the velocity slab)
@@ -782,7 +795,12 @@ cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaS
     const bool p1 = SDK_ADVECT_PROFILES && args.g.hmode == SDK_H_OCEANPARCEL && args.g.has_face && args.g.typ == SDK_TYP_LLC && args.has_dep && args.v.has_w &&
                     args.v.transport && args.v.has_z && args.v.vol_has_z && args.p.face && args.p.vol;
     void (*kern)(AdvectArgs);
-    if (args.g.hmode != SDK_H_OCEANPARCEL) {
+    if (args.ship) {
+        // (launch_advect's caller has checked: no log with the fused exchange)
+        if (args.g.hmode != SDK_H_OCEANPARCEL) kern = f32 ? advect_kernel<float, false, 2, true> : advect_kernel<double, false, 2, true>;
+        else if (f32) kern = p1 ? advect_kernel<float, false, 1, true> : advect_kernel<float, false, 0, true>;
+        else kern = p1 ? advect_kernel<double, false, 1, true> : advect_kernel<double, false, 0, true>;
+    } else if (args.g.hmode != SDK_H_OCEANPARCEL) {
         if (args.has_log) kern = f32 ? advect_kernel<float, true, 2> : advect_kernel<double, true, 2>;
         else kern = f32 ? advect_kernel<float, false, 2> : advect_kernel<double, false, 2>;
     } else if (args.has_log) {

@@ -16,6 +16,11 @@ struct AdvectArgs {
     int max_iteration, kick_back, has_dep, has_log, commit, refill_threshold, keep_status;
     unsigned long long *queue;  // work queue head
     unsigned long long *stats;  // optional [4]: live at start, crossings, hit max_iteration, flagged
+    // fused output exchange (sdk_advect_params.ship): the mappings, the step and the optional position table
+    sdk_exchange x;
+    unsigned long long ship_step;
+    const int32_t *ship_index;
+    int ship;
 };
 
 int advect_max_threads();

@@ -159,6 +159,9 @@ int sdk_grid_destroy(sdk_grid *g) {
     return SDK_OK;
 }
 
+static int check_exchange(const sdk_exchange *x, const char *who);
+int sdk_pack_ship(const sdk_exchange *x, const sdk_particles *p, const int32_t *out_index, uint64_t step, void *stream);
+
 static int fill_args(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, double t_stop,
                      const sdk_advect_params *par, const sdk_log *log, int commit, sdk::AdvectArgs &a) {
     if (!grid || !vel || !p) return fail(SDK_EINVAL, "null argument");
@@ -203,6 +206,22 @@ static int fill_args(const sdk_grid *grid, const sdk_velocity *vel, const sdk_pa
     a.has_log = log != nullptr;
     a.commit = commit;
     a.keep_status = (par && par->keep_status && p->status) ? 1 : 0;
+    a.ship = 0;
+    a.ship_index = nullptr;
+    a.ship_step = 0;
+    std::memset(&a.x, 0, sizeof a.x);
+    if (par && par->ship) {
+        if (log || p->active) return fail(SDK_EINVAL, "the fused output exchange does not go with a crossing log or an active mask");
+        if (!commit) return fail(SDK_EINVAL, "the fused output exchange needs commit != 0");
+        int rc = check_exchange(par->ship, "sdk_advect");
+        if (rc) return rc;
+        if (p->n > par->ship->n_pad) return fail(SDK_EINVAL, "sdk_advect: particle count does not fit the exchange's n_pad");
+        if (par->ship_step < 1) return fail(SDK_EINVAL, "sdk_advect: exchange steps count from 1");
+        a.ship = 1;
+        a.x = *par->ship;
+        a.ship_index = par->ship_index;
+        a.ship_step = par->ship_step;
+    }
     int thr = par ? par->refill_threshold : 0;
     a.refill_threshold = thr > 0 ? (thr > 32 ? 32 : thr) : 8;
     a.queue = grid->queue + (grid->next_queue++ % kQueueSlots);
@@ -215,7 +234,11 @@ int sdk_advect(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particle
     sdk::AdvectArgs a;
     int rc = fill_args(grid, vel, p, t_stop, par, log, commit, a);
     if (rc) return rc;
-    if (p->n == 0) return SDK_OK;
+    if (p->n == 0) {
+        // nothing to advect, but the other ranks still wait for this rank's (empty) block
+        if (par && par->ship) return sdk_pack_ship(par->ship, p, nullptr, par->ship_step, stream_);
+        return SDK_OK;
+    }
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaError_t e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_advect: memset");

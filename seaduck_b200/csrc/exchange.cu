@@ -17,45 +17,9 @@
 
 #include <cstdint>
 
-#include "../../include/seaduck_b200.h"
+#include "exchange_device.cuh"
 
 namespace sdk {
-
-constexpr unsigned long long kSpinLimitNs = 4000000000ull;  // 4 s
-
-__device__ __forceinline__ unsigned long long now_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-__device__ __forceinline__ uint64_t ld_acquire_sys(const uint64_t *p) {
-    uint64_t v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__device__ __forceinline__ void st_release_sys(uint64_t *p, uint64_t v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
-__device__ __forceinline__ void multimem_st16(double2 *dst, double2 v) {
-    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(__double2loint(v.x)),
-                 "r"(__double2hiint(v.x)), "r"(__double2loint(v.y)), "r"(__double2hiint(v.y))
-                 : "memory");
-}
-
-// wait until every counter of `row` (one per rank) has reached `want`; false on timeout
-__device__ __forceinline__ bool wait_all(const uint64_t *row, int world, uint64_t want) {
-    const unsigned long long t0 = now_ns();
-    for (int r = 0; r < world; ++r) {
-        while (ld_acquire_sys(row + r) < want) {
-            if (now_ns() - t0 > kSpinLimitNs) return false;
-            __nanosleep(200);
-        }
-    }
-    return true;
-}
 
 __device__ __forceinline__ uint64_t cell_word(const sdk_particles &p, int64_t i) {
     const uint64_t f = p.face ? (uint64_t)(uint32_t)p.face[i] : 0;
@@ -95,54 +59,22 @@ struct ShipArgs {
 };
 
 // Pack the records of this rank and store them into block [slot][rank] of every rank's receive buffer.
-template <bool MULTICAST>
 __global__ void __launch_bounds__(256) pack_ship_kernel(const __grid_constant__ ShipArgs a) {
     const sdk_exchange &x = a.x;
-    uint64_t *mine = x.signal[x.rank];
     __shared__ int ok;
-    if (threadIdx.x == 0) {
-        // the slot is free once every rank has consumed the step that last used it
-        const uint64_t prev = a.step > (uint64_t)x.n_slots ? a.step - x.n_slots : 0;
-        ok = prev == 0 || wait_all(mine + SDK_SIGNAL_CONSUMED, x.world, prev);
-        if (!ok) atomicExch((unsigned long long *)(mine + SDK_SIGNAL_ERROR), 1ull);
-    }
+    if (threadIdx.x == 0) ok = ship_slot_free(x, a.step);
     __syncthreads();
-    const int slot = (int)(a.step % (uint64_t)x.n_slots);
-    const int64_t base = ((int64_t)slot * x.world + x.rank) * x.n_pad;
+    const int64_t base = ship_base(x, a.step);
     if (ok) {
         // (the padding behind the last particle is written too -- zeros -- unless the records are scattered)
         const int64_t count = a.out_index ? a.n : x.n_pad;
         for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
             double2 ra, rb;
             load_record(a.p, i, a.n, ra, rb);
-            const int64_t at = base + (a.out_index ? (int64_t)a.out_index[i] : i);
-            if (MULTICAST) {
-                // one store, replicated into every rank's buffer by the switch (NVLS)
-                // (multimem.st has no 64-bit vector form: the 16 bytes go as four 32-bit words; a store moves bits)
-                double2 *dst = reinterpret_cast<double2 *>(x.recv_multicast + at);
-                multimem_st16(dst, ra);
-                multimem_st16(dst + 1, rb);
-            } else {
-                for (int k = 0; k < x.world; ++k) {
-                    const int r = (x.rank + k) % x.world;  // own copy first, then round the ring
-                    double2 *dst = reinterpret_cast<double2 *>(x.recv[r] + at);
-                    dst[0] = ra;
-                    dst[1] = rb;
-                }
-            }
+            ship_record(x, base + (a.out_index ? (int64_t)a.out_index[i] : i), ra, rb);
         }
     }
-    // every store of this CTA is visible system-wide before its ticket is; the last CTA posts the flags
-    __threadfence_system();
-    __syncthreads();
-    __shared__ unsigned last;
-    if (threadIdx.x == 0) last = atomicAdd(x.ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (last) {
-        __threadfence_system();
-        if (threadIdx.x < (unsigned)x.world) st_release_sys(x.signal[threadIdx.x] + SDK_SIGNAL_ARRIVED + x.rank, a.step);
-        if (threadIdx.x == 0) *x.ticket = 0;
-    }
+    ship_finish(x, a.step);
 }
 
 // All ranks' records of `step` are in this rank's buffer; optionally tell everyone that this rank is done
@@ -177,8 +109,7 @@ cudaError_t launch_pack_ship(const sdk_exchange &x, const sdk_particles &p, int6
     const int64_t cap = (int64_t)sm_count * 2;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (x.recv_multicast) pack_ship_kernel<true><<<(unsigned)blocks, 256, 0, s>>>(a);
-    else pack_ship_kernel<false><<<(unsigned)blocks, 256, 0, s>>>(a);
+    pack_ship_kernel<<<(unsigned)blocks, 256, 0, s>>>(a);
     return cudaGetLastError();
 }
 

@@ -592,6 +592,17 @@ class Particle(Position):
         par.stats = self._stats.data_ptr()
         return par
 
+    def ship_to(self, exchange):
+        """Multi-GPU runs (``parallel.RecordExchange``): the advection kernel of every leg whose end is an output stop
+        also stores the particles' 32-byte output records into every rank's receive buffer (``sdk_advect_params.ship``).
+        The caller waits for and releases each shipped step (``exchange.wait(step, release=True)``;
+        ``last_ship_step`` says which).  ``None`` switches it off."""
+        if exchange is not None and (self.save_raw or self.callback is not None):
+            raise ValueError("the fused output exchange does not go with save_raw or a callback")
+        self.__dict__["_exchange"] = exchange
+        self.__dict__["_ship_leg"] = exchange is not None
+        self.__dict__["last_ship_step"] = None
+
     def _read_stats(self):
         """(live at start, crossings, hit max_iteration, flagged) of the launches since the last
         call -- one small device-to-host copy, the only synchronisation of a stop."""
@@ -608,6 +619,12 @@ class Particle(Position):
         par = self._params(max_iteration)
         stream = _lib.current_stream()
         if not self.save_raw:
+            ex = self.__dict__.get("_exchange")
+            if ex is not None and self.__dict__.get("_ship_leg", False):
+                par.ship = C.addressof(ex.x)
+                par.ship_index = None if self._perm is None else self._perm.data_ptr()
+                par.ship_step = ex.next_step()
+                self.__dict__["last_ship_step"] = par.ship_step
             _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par), None, 1, stream), "sdk_advect")
             return
         dev = self.ocedata._torch_device()
@@ -835,6 +852,9 @@ class Particle(Position):
             logging.info(timestr)
             if self.save_raw:
                 self.note_taking(stamp=15)
+            if self.__dict__.get("_exchange") is not None:
+                # the fused output exchange ships the legs that end in a stop somebody keeps
+                self.__dict__["_ship_leg"] = return_in_between or not (update[i] or i == 0)
             self.to_next_stop(tl)
             if has_time and self.lazy and (update[i] or i == 0):
                 # the leg is queued, not finished: copy the snapshot it ends in while it runs

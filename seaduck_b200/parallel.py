@@ -162,6 +162,11 @@ class RecordExchange:
         )
         return self.step
 
+    def next_step(self):
+        """Step number for a kernel that ships on its own (``sdk_advect`` with ``sdk_advect_params.ship``)."""
+        self.step += 1
+        return self.step
+
     def wait(self, step, release=False):
         """The current stream waits until every rank's records of ``step`` are here; ``release`` also frees the slot."""
         _lib.check(_lib.lib().sdk_exchange_wait(C.byref(self.x), step, 1, int(release), _lib.current_stream()), "sdk_exchange_wait")
@@ -236,6 +241,7 @@ class ShardedParticle:
         self.exchange = None
         if self.world > 1 and gather == "all":
             self.exchange = RecordExchange(self.n_pad, data._torch_device(), group=group, slots=slots)
+            self.local.ship_to(self.exchange)  # the advection kernel ships the records itself
 
     def to_list_of_time(self, normal_stops, update_stops="default", return_in_between=True):
         import torch
@@ -253,7 +259,7 @@ class ShardedParticle:
                 pack_records(cp, pt.N, out=rec[0], out_index=pt._out_index())
                 snaps.append(ShardedSnapshot(self, t_stop, rec, everyone=False))
                 return
-            step = self.exchange.ship(cp, out_index=pt._out_index())
+            step = pt.last_ship_step  # shipped by the leg that just ended (sdk_advect with the fused exchange)
             done = torch.cuda.Event()
             done.record()
             side.wait_event(done)

@@ -222,6 +222,56 @@ def test_record_exchange_on_one_rank():
     assert int(ticket.item()) == 0
 
 
+@pytest.mark.parametrize("sort", [False, True])
+def test_fused_ship_equals_pack_records(sort):
+    """sdk_advect with sdk_advect_params.ship (world = 1: the rank is its own peer): the records the advection kernel
+    stores while it writes particles back are the records sdk_pack_records packs afterwards, stop after stop."""
+    import ctypes as C
+
+    import torch
+
+    from seaduck_b200 import _lib, parallel
+
+    sd = _sd()
+    case = cases.case_llc_transport(n=3000)
+    od = sd.OceData(case["ds"])
+    pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, sort=sort, **case["kw"])
+    plain = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, sort=False, **case["kw"])
+    n, n_pad, slots = pt.N, 3008, 2
+
+    class OneRank:
+        def __init__(self):
+            self.buf = torch.zeros(4096 + slots * n_pad * 32, dtype=torch.uint8, device="cuda")
+            self.ticket = torch.zeros(1, dtype=torch.int32, device="cuda")
+            self.x = _lib.Exchange()
+            self.x.world, self.x.rank, self.x.n_slots, self.x.n_pad = 1, 0, slots, n_pad
+            self.x.signal[0], self.x.recv[0], self.x.ticket = self.buf.data_ptr(), self.buf.data_ptr() + 4096, self.ticket.data_ptr()
+            self.step = 0
+
+        def next_step(self):
+            self.step += 1
+            return self.step
+
+    ex = OneRank()
+    pt.ship_to(ex)
+    L = _lib.lib()
+    for k, ts in enumerate([5 * cases.DAY, 20 * cases.DAY, 20 * cases.DAY, 60 * cases.DAY, 31 * cases.DAY]):
+        pt.to_next_stop(ts)
+        plain.to_next_stop(ts)
+        step = pt.last_ship_step
+        assert step == k + 1
+        _lib.check(L.sdk_exchange_wait(C.byref(ex.x), step, 1, 1, _lib.current_stream()), "sdk_exchange_wait")
+        slot = step % slots
+        got = ex.buf[4096 + slot * n_pad * 32 : 4096 + (slot + 1) * n_pad * 32].view(n_pad, 32)[:n]
+        want = parallel.pack_records(plain._cparticles(), n, device="cuda")
+        np.testing.assert_array_equal(got.cpu().numpy(), want.cpu().numpy(), err_msg=f"stop {k}")
+    words = ex.buf[: _lib.SIGNAL_WORDS * 8].cpu().numpy().view(np.uint64)
+    assert words[_lib.SIGNAL_ARRIVED] == 5 and words[_lib.SIGNAL_CONSUMED] == 5 and words[_lib.SIGNAL_ERROR] == 0
+    for k in cases.FINAL_INT + cases.FINAL_FLT:
+        if getattr(plain, k, None) is not None:
+            np.testing.assert_array_equal(getattr(pt, k), getattr(plain, k), err_msg=k)
+
+
 @pytest.mark.parametrize("n", [1000, 300_000])
 def test_track_host_equals_particle_api(n):
     """sdk_track_host (host buffers in and out; chunked and pipelined over three streams for large
@@ -358,6 +408,32 @@ def test_sharded_run_equals_single_run():
     for name, ref in (("lon", whole.lon), ("lat", whole.lat), ("dep", whole.dep), ("face", whole.face), ("iy", whole.iy),
                       ("ix", whole.ix), ("izl", whole.izl_lin)):
         np.testing.assert_array_equal(out[name], ref, err_msg=name)
+
+
+@pytest.mark.parametrize("sort", [False, True])
+def test_sharded_particle_api_on_one_rank(sort):
+    """parallel.ShardedParticle without a process group (one rank owns every particle, in the order of the sharding
+    permutation): to_list_of_time over a time-dependent field gives the snapshots of a plain Particle run."""
+    from seaduck_b200 import parallel, synthetic
+
+    sd = _sd()
+    ds = synthetic.llc(n=30, nz=8, nt=4)
+    od = sd.OceData(ds)
+    n = 5001
+    lon, lat, dep = synthetic.llc_seed_particles(None, n, seed=77, depth_range=(5, 300))
+    kw = dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True)
+    stops = [4 * cases.DAY, 12 * cases.DAY, 17 * cases.DAY]
+    whole = sd.Particle(x=lon, y=lat, z=dep, t=np.full(n, cases.DAY), data=od, sort=False, **kw)
+    ref_stops, ref = whole.to_list_of_time(stops, snapshots="full")
+    sp = parallel.ShardedParticle(lon, lat, dep, np.full(n, cases.DAY), data=od, gather="all", seed=3, sort=sort, **kw)
+    got_stops, snaps = sp.to_list_of_time(stops)
+    np.testing.assert_allclose(got_stops, ref_stops)
+    assert len(snaps) == len(ref)
+    for i, (s, r) in enumerate(zip(snaps, ref)):
+        out = s.assemble()
+        assert s.t == float(r.t[0])
+        for k, attr in (("face", "face"), ("iy", "iy"), ("ix", "ix"), ("izl", "izl_lin"), ("lon", "lon"), ("lat", "lat"), ("dep", "dep")):
+            np.testing.assert_array_equal(out[k], getattr(r, attr), err_msg=f"snapshot {i}: {k}")
 
 
 def test_full_size_round_trip_and_idempotence():
