@@ -30,6 +30,10 @@ size_t cell_sort_scratch_bytes(int64_t n);
 cudaError_t launch_cell_sort(const GridDev &g, int64_t n, const int32_t *face, const int32_t *iy, const int32_t *ix,
                              const int32_t *izl, int32_t *perm, void *scratch, size_t scratch_bytes, cudaStream_t s);
 cudaError_t launch_particles_gather(const sdk_particles &src, const sdk_particles &dst, const int32_t *perm, cudaStream_t s);
+cudaError_t launch_point_sort(const GridDev &g, const BucketGrid &b, int64_t n, const double *lon, const double *lat, const double *dep,
+                              int32_t *perm, void *scratch, size_t scratch_bytes, cudaStream_t s);
+cudaError_t launch_points_gather(int64_t n, const int32_t *perm, const double *lon, const double *lat, const double *dep, const double *t,
+                                 double *olon, double *olat, double *odep, double *ot, cudaStream_t s);
 cudaError_t launch_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad,
                                  cudaStream_t s);
 }
@@ -49,7 +53,7 @@ int cuda_fail(cudaError_t e, const char *what) {
 }  // namespace
 
 constexpr unsigned kQueueSlots = 64;
-constexpr int kTrackChunks = 6;
+constexpr int kTrackChunks = 3;  // measured best for 10^6 particles (tools/exp_e2e.py): 2-4 chunks within 3 %, more chunks = more kernel tails
 constexpr int kTrackChunksMax = 32;
 
 struct sdk_grid {
@@ -683,15 +687,20 @@ int sdk_selftest_math(int op, int64_t n, const double *a, const double *b, doubl
 }
 
 // ---- positions in, positions out ------------------------------------------------------------------
-// per chunk: the located state, a second copy in cell order, the permutation, the sort's workspace, the records
+// per chunk: the particle state, the coordinates as they came in (sorted runs), the permutation, the sort's workspace,
+// the records
 static size_t track_chunk_bytes(int64_t n) {
-    return 2 * (size_t)sdk_particles_bytes(n) + align256((size_t)n * 4) + align256((size_t)sdk_cell_sort_scratch_bytes(n)) +
-           align256((size_t)n * sizeof(sdk_snapshot_record));
+    return (size_t)sdk_particles_bytes(n) + 4 * align256((size_t)n * 8) + align256((size_t)n * 4) +
+           align256((size_t)sdk_cell_sort_scratch_bytes(n)) + align256((size_t)n * sizeof(sdk_snapshot_record));
 }
 
+// head of the scratch buffer: the call's counters, then signal words + ticket of every chunk's record output
+constexpr size_t kTrackSignalBytes = 512;
+constexpr size_t kTrackHeadBytes = 256 + (size_t)kTrackChunksMax * kTrackSignalBytes;
+
 int64_t sdk_track_scratch_bytes(int64_t n) {
-    // chunks are rounded up to 32 particles; 256 bytes for the counters
-    return (int64_t)(track_chunk_bytes(n + 32 * kTrackChunksMax) + (size_t)kTrackChunksMax * 80 * 256 + 256);
+    // chunks are rounded up to 32 particles
+    return (int64_t)(track_chunk_bytes(n + 32 * kTrackChunksMax) + (size_t)kTrackChunksMax * 80 * 256 + kTrackHeadBytes);
 }
 
 static void carve_particles(sdk_particles &dp, int64_t n, char *&cur) {
@@ -706,9 +715,12 @@ static void carve_particles(sdk_particles &dp, int64_t n, char *&cur) {
 }
 
 // One chunk of sdk_track_host: H2D, locate, (cell sort,) velocity read, advect, pack, D2H -- all asynchronous on `stream`.
+// `records_dev`: device-visible address of io->out_records when that is mapped pinned host memory (the advection kernel
+// then stores the records there itself, over PCIe, while it runs), else NULL (pack on the device, copy afterwards);
+// `signal`: kTrackSignalBytes of zeroed device memory of this chunk.
 static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev,
                        int32_t n_t, double t_stop, const sdk_advect_params *par_in, uint64_t *stats_dev, void *scratch,
-                       cudaStream_t stream) {
+                       sdk_snapshot_record *records_dev, void *signal, cudaStream_t stream) {
     const int64_t n = io->n;
     sdk_advect_params par;
     if (par_in) par = *par_in;
@@ -718,24 +730,48 @@ static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_
     }
     const int has_dep = par.has_dep;
     char *cur = (char *)scratch;
-    sdk_particles dp, sp;
+    sdk_particles dp;
     carve_particles(dp, n, cur);
     cudaError_t e;
+    const bool vertical = has_dep && grid->dev.n_zl > 1;
+    const bool timed = vel->has_time && ts_dev && n_t > 1;
+    // with `sort` the coordinates land in a staging area first and are put into (level, bucket) order on their way
+    // into the state: everything after that -- locating included -- works on coherent particles
+    const bool sorted = io->sort && grid->dev.hmode != SDK_H_RECTILINEAR && grid->has_buckets;
+    double *in[4] = {dp.lon, dp.lat, dp.dep, dp.t};
+    if (sorted) {
+        for (auto &a : in) {
+            a = (double *)cur;
+            cur += align256((size_t)n * 8);
+        }
+    }
 #define H2D(dst, src) \
     if ((e = cudaMemcpyAsync(dst, src, (size_t)n * 8, cudaMemcpyHostToDevice, stream)) != cudaSuccess) \
         return cuda_fail(e, "sdk_track_host: H2D");
-    H2D(dp.lon, io->lon)
-    H2D(dp.lat, io->lat)
-    H2D(dp.t, io->t)
-    if (io->dep) H2D(dp.dep, io->dep)
+    H2D(in[0], io->lon)
+    H2D(in[1], io->lat)
+    H2D(in[3], io->t)
+    if (io->dep) H2D(in[2], io->dep)
 #undef H2D
+    int32_t *perm = nullptr;
+    if (sorted) {
+        perm = (int32_t *)cur;
+        cur += align256((size_t)n * 4);
+        const size_t sbytes = (size_t)sdk_cell_sort_scratch_bytes(n);
+        if ((e = sdk::launch_point_sort(grid->dev, grid->buckets, n, in[0], in[1], (vertical && io->dep) ? in[2] : nullptr, perm, cur, sbytes,
+                                        stream)) != cudaSuccess)
+            return cuda_fail(e, "sdk_track_host: sort");
+        cur += align256(sbytes);
+        if ((e = sdk::launch_points_gather(n, perm, in[0], in[1], io->dep ? in[2] : nullptr, in[3], dp.lon, dp.lat, dp.dep, dp.t, stream)) !=
+            cudaSuccess)
+            return cuda_fail(e, "sdk_track_host: gather");
+    }
     // Position.from_latlon: indices + rel-coords straight into the particle state
     sdk_located loc;
     std::memset(&loc, 0, sizeof loc);
     loc.face = grid->dev.has_face ? dp.face : nullptr;
     loc.iy = dp.iy; loc.ix = dp.ix; loc.rx = dp.rx; loc.ry = dp.ry;
     loc.px = dp.px; loc.py = dp.py; loc.dx = dp.dx; loc.dy = dp.dy;
-    const bool vertical = has_dep && grid->dev.n_zl > 1;
     if (vertical) {
         loc.izl = dp.izl; loc.rzl = dp.rzl; loc.dzl = dp.dzl; loc.bzl = dp.bzl;
     } else {
@@ -743,34 +779,34 @@ static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_
     }
     loc.it = dp.it;
     loc.status = dp.status;
-    const bool timed = vel->has_time && ts_dev && n_t > 1;
     if (!timed && (e = cudaMemsetAsync(dp.it, 0, (size_t)n * 4, stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: memset");
     int rc = sdk_locate(grid, n, dp.lon, dp.lat, vertical ? dp.dep : nullptr, timed ? dp.t : nullptr, ts_dev, n_t, &loc, stream);
     if (rc) return rc;
     const sdk_particles *work = &dp;
-    int32_t *perm = nullptr;
-    if (io->sort) {
-        carve_particles(sp, n, cur);
-        if (!vertical) sp.izl = nullptr;
-        perm = (int32_t *)cur;
-        cur += align256((size_t)n * 4);
-        const int64_t sbytes = sdk_cell_sort_scratch_bytes(n);
-        rc = sdk_cell_sort(grid, n, loc.face, dp.iy, dp.ix, vertical ? dp.izl : nullptr, perm, cur, sbytes, stream);
-        if (rc) return rc;
-        cur += align256((size_t)sbytes);
-        // (u, v, w ... are not set yet: the velocity read below fills them in the sorted copy)
-        rc = sdk_particles_gather(&dp, &sp, perm, stream);
-        if (rc) return rc;
-        work = &sp;
-    }
     // Particle.__init__: get_vol + get_u_du, then to_next_stop
     rc = sdk_get_u_du(grid, vel, work, has_dep, stream);
     if (rc) return rc;
     par.keep_status = 1;  // what sdk_locate flagged stays flagged
     par.stats = stats_dev;
+    sdk_exchange to_host;
+    if (perm) records_dev = nullptr;  // (scattered 32-byte stores over PCIe are slow: sorted runs pack on the device and copy)
+    if (records_dev) {
+        // the fused output exchange with the host as the only "rank": every particle's record goes to the caller's
+        // pinned buffer (in the caller's order) from the write-back of the advection kernel -- no pack pass, no copy
+        std::memset(&to_host, 0, sizeof to_host);
+        to_host.world = 1;
+        to_host.n_slots = 1;
+        to_host.n_pad = n;
+        to_host.recv[0] = records_dev;
+        to_host.signal[0] = (uint64_t *)signal;
+        to_host.ticket = (uint32_t *)((char *)signal + SDK_SIGNAL_WORDS * sizeof(uint64_t));
+        par.ship = &to_host;
+        par.ship_index = nullptr;
+        par.ship_step = 1;
+    }
     rc = sdk_advect(grid, vel, work, t_stop, &par, nullptr, 1, stream);
     if (rc) return rc;
-    if (io->out_records) {
+    if (io->out_records && !records_dev) {
         sdk_snapshot_record *rec = (sdk_snapshot_record *)cur;
         rc = sdk_pack_records(work, perm, rec, stream);
         if (rc) return rc;
@@ -807,10 +843,20 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
     if (has_dep && !io->dep) return fail(SDK_EINVAL, "sdk_track_host: depth array missing");
     cudaStream_t stream = (cudaStream_t)stream_;
     cudaError_t e;
-    // the call's counters: first 256 bytes of the scratch buffer
+    // the call's counters and the chunks' signal words: head of the scratch buffer
     uint64_t *stats_dev = (uint64_t *)scratch;
-    char *cur = (char *)scratch + 256;
-    if ((e = cudaMemsetAsync(stats_dev, 0, 4 * sizeof(uint64_t), stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: memset");
+    char *signals = (char *)scratch + 256;
+    char *cur = (char *)scratch + kTrackHeadBytes;
+    if ((e = cudaMemsetAsync(scratch, 0, kTrackHeadBytes, stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: memset");
+    // records straight into the caller's buffer if the device can address it (pinned, mapped host memory)
+    sdk_snapshot_record *records_dev = nullptr;
+    if (io->out_records && !std::getenv("SDK_TRACK_NO_ZEROCOPY")) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, io->out_records) == cudaSuccess && attr.type == cudaMemoryTypeHost && attr.devicePointer)
+            records_dev = (sdk_snapshot_record *)attr.devicePointer;
+        else
+            cudaGetLastError();  // (pageable memory: not an error, the copy path takes it)
+    }
     // Small batches: one pass.  Large ones: chunks on three internal streams, so that the upload of
     // chunk k+1 and the read-back of chunk k-1 (copy engines) overlap the kernels of chunk k.
     const int64_t min_chunk = 65536;
@@ -822,7 +868,7 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
     }
     if (nchunks > max_chunks) nchunks = max_chunks;
     if (nchunks < 2) {
-        int rc = track_chunk(grid, vel, io, ts_dev, n_t, t_stop, par, stats_dev, cur, stream);
+        int rc = track_chunk(grid, vel, io, ts_dev, n_t, t_stop, par, stats_dev, cur, records_dev, signals, stream);
         if (rc) return rc;
     } else {
         if (!grid->has_pipe) {
@@ -848,7 +894,8 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
             SHIFT(lon) SHIFT(lat) SHIFT(dep) SHIFT(t) SHIFT(out_records) SHIFT(out_lon) SHIFT(out_lat) SHIFT(out_dep)
             SHIFT(out_face) SHIFT(out_iy) SHIFT(out_ix) SHIFT(out_izl) SHIFT(out_ncross) SHIFT(out_status)
 #undef SHIFT
-            int rc = track_chunk(grid, vel, &sub, ts_dev, n_t, t_stop, par, stats_dev, cur, grid->pipe[c % 3]);
+            int rc = track_chunk(grid, vel, &sub, ts_dev, n_t, t_stop, par, stats_dev, cur, records_dev ? records_dev + off : nullptr,
+                                 signals + (size_t)c * kTrackSignalBytes, grid->pipe[c % 3]);
             if (rc) return rc;
             cur += track_chunk_bytes(cnt);
         }

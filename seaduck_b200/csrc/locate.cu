@@ -363,6 +363,30 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
     if (o.status) o.status[i] = status;
 }
 
+// sort key of a point that has not been located yet: (vertical level, locator bucket), see launch_point_sort (sort.cu)
+__global__ void __launch_bounds__(256) point_key_kernel(GridDev g, BucketGrid b, int64_t n, const double *lon, const double *lat,
+                                                        const double *dep, uint64_t *key, int32_t *idx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t level = 0;
+    if (dep && g.n_zl > 1) {
+        int k, st = 0;
+        double r, d, bb;
+        find_rel_1d(g.Zl, g.dZl, g.n_zl, g.n_z, dep[i], -1, true, true, k, r, d, bb, st);
+        level = (uint64_t)k;
+    }
+    const double x = lon[i], y = lat[i];
+    const uint64_t bucket = (x == x && y == y) ? (uint64_t)bucket_of(b, x, y) : 0;
+    key[i] = level * ((uint64_t)b.nlat * (uint64_t)b.nlon) + bucket;
+    idx[i] = (int32_t)i;
+}
+
+cudaError_t launch_point_keys(const GridDev &g, const BucketGrid &b, int64_t n, const double *lon, const double *lat, const double *dep,
+                              uint64_t *key, int32_t *idx, cudaStream_t s) {
+    point_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, b, n, lon, lat, dep, key, idx);
+    return cudaGetLastError();
+}
+
 // it = 0 before time_midp[0], else find_rel(t, time_midp)[0] + 1 (reference lagrangian.py:796-802)
 __global__ void time_index_kernel(const double *t, const double *midp, int n_midp, int32_t *it, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

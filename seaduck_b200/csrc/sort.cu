@@ -12,7 +12,7 @@
 
 #include <cstdint>
 
-#include "sdk_device.cuh"
+#include "locate_args.cuh"
 
 namespace sdk {
 
@@ -25,12 +25,13 @@ __global__ void __launch_bounds__(256) cell_key_kernel(int64_t n, int nface, int
     idx[i] = (int32_t)i;
 }
 
-static int key_bits(const GridDev &g) {
-    const uint64_t top = (uint64_t)(g.n_zl > 0 ? g.n_zl + 1 : 1) * g.nface * g.ny * g.nx;
+static int bits_for(uint64_t top) {
     int bits = 1;
     while (bits < 64 && (top >> bits) != 0) ++bits;
     return bits;
 }
+
+static int key_bits(const GridDev &g) { return bits_for((uint64_t)(g.n_zl > 0 ? g.n_zl + 1 : 1) * g.nface * g.ny * g.nx); }
 
 static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
@@ -41,21 +42,73 @@ size_t cell_sort_scratch_bytes(int64_t n) {
     return align256(tmp) + 2 * align256((size_t)n * 8) + align256((size_t)n * 4);
 }
 
+// the scratch buffer of a sort: keys in, keys out, indices in, CUB's workspace
+struct SortScratch {
+    uint64_t *key_in, *key_out;
+    int32_t *idx_in;
+    void *tmp;
+    size_t tmp_bytes;
+};
+
+static SortScratch carve_sort(int64_t n, void *scratch, size_t scratch_bytes) {
+    SortScratch w;
+    char *cur = (char *)scratch;
+    w.key_in = (uint64_t *)cur;
+    cur += align256((size_t)n * 8);
+    w.key_out = (uint64_t *)cur;
+    cur += align256((size_t)n * 8);
+    w.idx_in = (int32_t *)cur;
+    cur += align256((size_t)n * 4);
+    w.tmp = cur;
+    w.tmp_bytes = scratch_bytes - (size_t)(cur - (char *)scratch);
+    return w;
+}
+
 cudaError_t launch_cell_sort(const GridDev &g, int64_t n, const int32_t *face, const int32_t *iy, const int32_t *ix,
                              const int32_t *izl, int32_t *perm, void *scratch, size_t scratch_bytes, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    char *cur = (char *)scratch;
-    uint64_t *key_in = (uint64_t *)cur;
-    cur += align256((size_t)n * 8);
-    uint64_t *key_out = (uint64_t *)cur;
-    cur += align256((size_t)n * 8);
-    int32_t *idx_in = (int32_t *)cur;
-    cur += align256((size_t)n * 4);
-    size_t tmp = scratch_bytes - (size_t)(cur - (char *)scratch);
-    cell_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, g.nface, g.ny, g.nx, face, iy, ix, izl, key_in, idx_in);
+    const SortScratch w = carve_sort(n, scratch, scratch_bytes);
+    cell_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, g.nface, g.ny, g.nx, face, iy, ix, izl, w.key_in, w.idx_in);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    return cub::DeviceRadixSort::SortPairs(cur, tmp, key_in, key_out, idx_in, perm, (int)n, 0, key_bits(g), s);
+    return cub::DeviceRadixSort::SortPairs(w.tmp, const_cast<size_t &>(w.tmp_bytes), w.key_in, w.key_out, w.idx_in, perm, (int)n, 0, key_bits(g), s);
+}
+
+// Order for points that have not been located yet (sdk_track_host): the key is (vertical level, bucket of the
+// locator's lat / lon grid) -- about one cell per bucket, so it is the cell order up to the walk of sdk_locate -- and it
+// only needs the coordinates.  Sorting the 32 bytes of input of a point before locating it is cheaper than sorting
+// the 220 bytes of state afterwards, and sdk_locate itself runs on coherent points.
+cudaError_t launch_point_keys(const GridDev &g, const BucketGrid &b, int64_t n, const double *lon, const double *lat, const double *dep,
+                              uint64_t *key, int32_t *idx, cudaStream_t s);  // locate.cu
+
+cudaError_t launch_point_sort(const GridDev &g, const BucketGrid &b, int64_t n, const double *lon, const double *lat, const double *dep,
+                              int32_t *perm, void *scratch, size_t scratch_bytes, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    const SortScratch w = carve_sort(n, scratch, scratch_bytes);
+    cudaError_t e = launch_point_keys(g, b, n, lon, lat, dep, w.key_in, w.idx_in, s);
+    if (e != cudaSuccess) return e;
+    const int bits = bits_for((uint64_t)(g.n_zl > 0 ? g.n_zl + 1 : 1) * (uint64_t)b.nlat * (uint64_t)b.nlon);
+    return cub::DeviceRadixSort::SortPairs(w.tmp, const_cast<size_t &>(w.tmp_bytes), w.key_in, w.key_out, w.idx_in, perm, (int)n, 0, bits, s);
+}
+
+// out[k] = in[perm[k]] for the four coordinate arrays of a batch of points
+__global__ void __launch_bounds__(256) points_gather_kernel(int64_t n, const int32_t *perm, const double *lon, const double *lat,
+                                                            const double *dep, const double *t, double *olon, double *olat, double *odep,
+                                                            double *ot) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = perm[k];
+    olon[k] = lon[i];
+    olat[k] = lat[i];
+    if (dep) odep[k] = dep[i];
+    if (t) ot[k] = t[i];
+}
+
+cudaError_t launch_points_gather(int64_t n, const int32_t *perm, const double *lon, const double *lat, const double *dep, const double *t,
+                                 double *olon, double *olat, double *odep, double *ot, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    points_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, perm, lon, lat, dep, t, olon, olat, odep, ot);
+    return cudaGetLastError();
 }
 
 // dst[k] = src[perm[k]] for every array both structures hold: one pass over the state, one thread per particle
