@@ -330,8 +330,9 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
     if (SDK_UNLIKELY(redo)) {  // zero / denormal / non-finite scale: plain operators (out of line)
         qu = div_cold(u, sx), qdu = div_cold(du, sx), qv = div_cold(vv, sy), qdv = div_cold(dv, sy);
         if (k_w) qw = div_cold(w, sz), qdw = div_cold(dw, sz);
+        // (a quotient the fast path vouches for is finite: nan_to_num has something to do only here)
+        nan_to_num6(qu, qv, qdu, qdv, qw, qdw);
     }
-    nan_to_num6(qu, qv, qdu, qdv, qw, qdw);
     s.u = qu;
     s.v = qv;
     s.du = qdu;

@@ -79,6 +79,14 @@ __device__ __forceinline__ double to_180_fast(double x, bool &bad) {
     return m + (m >= 180.0 ? -360.0 : -0.0);
 }
 
+// to_180 for |x| < 360 -- the difference of two longitudes that both lie within 180 degrees of a third one (the
+// corners of a cell, unwrapped around the particle) -- the same steps as to_180_fast without the fmod stage, which
+// is the identity there.
+__device__ __forceinline__ double to_180_near(double x) {
+    const double m = x + (x < 0.0 ? 360.0 : 0.0);
+    return m + (m >= 180.0 ? -360.0 : -0.0);
+}
+
 // numpy.nan_to_num: nan -> 0, +-inf -> +-DBL_MAX.  Fields and quotients are finite almost always: the
 // callers test a whole group of values with integer operations on the exponents and only then come here
 // (out of line, so that the step's hot path stays one contiguous run of code).
@@ -269,12 +277,14 @@ static __device__ __noinline__ double2 inverse_bilinear_slow(double x, double y,
 // Same arithmetic with the branch-free helpers of fastmath.cuh; `bad` asks for inverse_bilinear_slow.
 __device__ __forceinline__ void inverse_bilinear_fast(double x, double y, const double pxi[4], const double py[4],
                                                       double &rx, double &ry, bool &bad) {
+    // (pxi[j] = x + to_180(XG - x) lie within 180 degrees of x: every difference below is smaller than 360 in
+    // magnitude unless a coordinate is not finite, which the divisions further down flag)
     const double x0 = pxi[0];
     double px[4];
-    x = to_180_fast(x - x0, bad);
+    x = to_180_near(x - x0);
     px[0] = 0.0;  // to_180(x0 - x0)
 #pragma unroll
-    for (int j = 1; j < 4; ++j) px[j] = to_180_fast(pxi[j] - x0, bad);
+    for (int j = 1; j < 4; ++j) px[j] = to_180_near(pxi[j] - x0);
     const double a0 = px[0], a1 = -px[0] + px[1], a2 = -px[0] + px[3];
     const double a3 = ((px[0] - px[1]) + px[2]) - px[3];
     const double b0 = py[0], b1 = -py[0] + py[1], b2 = -py[0] + py[3];
