@@ -506,6 +506,10 @@ enum {
     SDK_SELFTEST_DIV_IEEE = 3, SDK_SELFTEST_LOG_CUDA = 4, SDK_SELFTEST_EXP_CUDA = 5, SDK_SELFTEST_STEP = 6
 };
 int sdk_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad, void *stream);
+/* Self-test of the device's cell-to-cell move (the closed form behind Topology.ind_tend, seaduck/topology.py:389: LLC and
+ * ASTE face tables, x-periodic wrap, closed boxes): in = [n][4] (face, iy, ix, direction 0 up / 1 down / 2 left / 3 right),
+ * out = [n][5] (face, iy, ix, edge of the new face the move came in through or -1, SDK_ST_* status).  Device pointers. */
+int sdk_selftest_cell_move(const sdk_grid *grid, int64_t n, const int32_t *in, int32_t *out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -288,7 +288,9 @@ class OracleGrid:
             from scipy import spatial  # noqa: PLC0415
 
             x, y, z = spherical2cartesian(lat=self.YC, lon=self.XC)
-            self._tree = spatial.cKDTree(np.vstack((x.ravel(), y.ravel(), z.ravel())).T, leafsize=16)
+            pts = np.vstack((x.ravel(), y.ravel(), z.ravel())).T
+            pts = np.nan_to_num(pts, nan=777777)  # the reference's "ridiculous value" for NaN centres (utils.py:243-253)
+            self._tree = spatial.cKDTree(pts, leafsize=16)
         return self._tree
 
     def find_ind_h(self, lons, lats):

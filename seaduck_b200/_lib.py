@@ -245,6 +245,7 @@ def lib():
         L.sdk_pack_ship.argtypes = [C.POINTER(Exchange), C.POINTER(Particles), vp, C.c_uint64, vp]
         L.sdk_exchange_wait.argtypes = [C.POINTER(Exchange), C.c_uint64, C.c_int, C.c_int, vp]
         L.sdk_selftest_math.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp, vp]
+        L.sdk_selftest_cell_move.argtypes = [vp, C.c_int64, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -600,6 +600,15 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
 #define SDK_ADVECT_INLINE_AXES 0
 #endif
 
+// one out-of-line copy of the record store of the fused exchange: it runs once per particle, the step loop must not
+// carry its code (the kernel is bound by the instruction lines it has to fetch, profiles/README.md)
+static __device__ __noinline__ void ship_lane_cold(const AdvectArgs &a, long long base, long long pid, double lon, double lat, double dep,
+                                                   int f, int iy, int ix, int izl) {
+    const unsigned long long cell = SDK_CELL_PACK((uint64_t)(uint32_t)f, (uint64_t)(uint32_t)iy, (uint64_t)(uint32_t)ix, (uint64_t)(uint32_t)izl);
+    const long long at = base + (a.ship_index ? (long long)a.ship_index[pid] : pid);
+    ship_record(a.x, at, make_double2(lon, lat), make_double2(dep, __longlong_as_double((long long)cell)));
+}
+
 // SHIP: the write-back of a finished particle also stores its 32-byte output record into every rank's receive
 // buffer (sdk_advect_params.ship): the exchange of a stop's output rides on the kernel that produces it.
 template <typename T, bool LOG, int P, bool SHIP = false>
@@ -613,7 +622,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
     __shared__ int ship_ok;
     if (SHIP && threadIdx.x == 0) ship_ok = ship_slot_free(a.x, a.ship_step);
     __syncthreads();
-    const int64_t ship_at = SHIP ? ship_base(a.x, a.ship_step) : 0;
+    const long long ship_at = (SHIP && ship_ok) ? ship_base(a.x, a.ship_step) : -1;  // -1: the slot never came free
     double *cold_d = reinterpret_cast<double *>(reinterpret_cast<char *>(smem) + advect_smem_bytes(a.g.n_zl, a.g.n_z, 0)) + threadIdx.x;
     int *cold_i = reinterpret_cast<int *>(cold_d - threadIdx.x + kColdDoubles * blockDim.x) + threadIdx.x;
     (void)cold_i;
@@ -643,12 +652,7 @@ advect_kernel(const __grid_constant__ AdvectArgs a) {
                 // done (or out of iterations): write back and free the lane
                 if (live) s.status |= SDK_ST_MAX_ITER;
                 if (a.commit) store_lane<P>(a.p, a.has_dep, s);
-                if (SHIP && ship_ok) {
-                    const uint64_t cell = SDK_CELL_PACK((uint64_t)(uint32_t)s.f, (uint64_t)(uint32_t)s.iy, (uint64_t)(uint32_t)s.ix,
-                                                        (uint64_t)(uint32_t)s.izl);
-                    ship_record(a.x, ship_at + (a.ship_index ? (int64_t)a.ship_index[s.pid] : (int64_t)s.pid), make_double2(s.lon, s.lat),
-                                make_double2(s.dep, __longlong_as_double((long long)cell)));
-                }
+                if (SHIP && ship_at >= 0) ship_lane_cold(a, ship_at, s.pid, s.lon, s.lat, s.dep, s.f, s.iy, s.ix, s.izl);
                 if (a.p.status) a.p.status[s.pid] = s.status;
                 if (a.p.niter) a.p.niter[s.pid] = s.niter;
                 if (a.p.ncross) a.p.ncross[s.pid] = s.ncross;

@@ -36,6 +36,7 @@ cudaError_t launch_points_gather(int64_t n, const int32_t *perm, const double *l
                                  double *olon, double *olat, double *odep, double *ot, cudaStream_t s);
 cudaError_t launch_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad,
                                  cudaStream_t s);
+cudaError_t launch_selftest_cell_move(const GridDev &g, int64_t n, const int32_t *in, int32_t *out, cudaStream_t s);
 }
 
 namespace {
@@ -158,7 +159,10 @@ int sdk_grid_destroy(sdk_grid *g) {
         for (auto &st : g->pipe) cudaStreamDestroy(st);
         for (auto &ev : g->pipe_ev) cudaEventDestroy(ev);
     }
-    if (g->has_buckets) cudaFree(g->buckets.table);
+    if (g->has_buckets) {
+        cudaFree(g->buckets.table);
+        cudaFree((void *)g->buckets.cxyz);
+    }
     delete g;
     return SDK_OK;
 }
@@ -284,6 +288,7 @@ int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span
         return fail(SDK_EINVAL, "sdk_grid_build_locator: bad bucket geometry");
     if (grid->has_buckets) {
         cudaFree(grid->buckets.table);
+        cudaFree((void *)grid->buckets.cxyz);
         grid->has_buckets = false;
     }
     sdk::BucketGrid &b = grid->buckets;
@@ -297,6 +302,7 @@ int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span
     b.inv_dlon = nlon / b.span_lon;
     b.inv_dlat = nlat / b.span_lat;
     b.table = nullptr;
+    b.cxyz = nullptr;
     cudaError_t e = sdk::build_buckets(grid->dev, b, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_grid_build_locator");
     grid->has_buckets = true;
@@ -683,6 +689,13 @@ int sdk_selftest_math(int op, int64_t n, const double *a, const double *b, doubl
     if ((op == SDK_SELFTEST_DIV || op == SDK_SELFTEST_DIV_IEEE) && n > 0 && !b) return fail(SDK_EINVAL, "sdk_selftest_math: b missing");
     cudaError_t e = sdk::launch_selftest_math(op, n, a, b ? b : a, out, bad, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_selftest_math: launch");
+    return SDK_OK;
+}
+
+int sdk_selftest_cell_move(const sdk_grid *grid, int64_t n, const int32_t *in, int32_t *out, void *stream) {
+    if (!grid || n < 0 || (n > 0 && (!in || !out))) return fail(SDK_EINVAL, "sdk_selftest_cell_move: bad argument");
+    cudaError_t e = sdk::launch_selftest_cell_move(grid->dev, n, in, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_selftest_cell_move: launch");
     return SDK_OK;
 }
 

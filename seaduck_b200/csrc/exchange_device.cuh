@@ -53,6 +53,7 @@ __device__ __forceinline__ void ship_record(const sdk_exchange &x, int64_t at, d
         multimem_st16(dst, ra);
         multimem_st16(dst + 1, rb);
     } else {
+#pragma unroll 1
         for (int k = 0; k < x.world; ++k) {
             const int r = (x.rank + k) % x.world;  // own copy first, then round the ring
             double2 *dst = reinterpret_cast<double2 *>(x.recv[r] + at);
@@ -76,18 +77,19 @@ __device__ __forceinline__ bool ship_slot_free(const sdk_exchange &x, unsigned l
     return ok;
 }
 
-// Called by every thread of a CTA after its last store: makes the stores visible system-wide, and the CTA that
-// finishes last posts `step` in every rank's arrived[rank].  Contains __syncthreads().
+// Called by every thread of a CTA after its last store; the CTA that finishes last posts `step` in every rank's
+// arrived[rank].  One system-scope fence per CTA, not per thread: the barrier orders the CTA's stores before thread 0,
+// whose fence (cumulative) then orders them before the ticket and the flags.  Contains __syncthreads().
 __device__ __forceinline__ void ship_finish(const sdk_exchange &x, unsigned long long step) {
-    __threadfence_system();
     __syncthreads();
-    __shared__ unsigned ship_last;
-    if (threadIdx.x == 0) ship_last = atomicAdd(x.ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (ship_last) {
+    if (threadIdx.x == 0) {
         __threadfence_system();
-        if (threadIdx.x < (unsigned)x.world) st_release_sys(x.signal[threadIdx.x] + SDK_SIGNAL_ARRIVED + x.rank, step);
-        if (threadIdx.x == 0) *x.ticket = 0;
+        if (atomicAdd(x.ticket, 1u) == gridDim.x - 1) {
+            __threadfence_system();
+#pragma unroll 1
+            for (int r = 0; r < x.world; ++r) st_release_sys(x.signal[r] + SDK_SIGNAL_ARRIVED + x.rank, step);
+            *x.ticket = 0;
+        }
     }
 }
 

@@ -109,15 +109,47 @@ __device__ __forceinline__ bool neighbour(const GridDev &g, int f, int iy, int i
     return true;
 }
 
-__device__ __forceinline__ double dist2_to_cell(const GridDev &g, int f, int iy, int ix, double qx,
+__device__ __forceinline__ double dist2_to_cell(const GridDev &g, const double *cxyz, int f, int iy, int ix, double qx,
                                                 double qy, double qz) {
     const int64_t c = ((int64_t)f * g.ny + iy) * g.nx + ix;
-    const float lon = __ldg(g.XC + c), lat = __ldg(g.YC + c);
-    if (!(lon == lon) || !(lat == lat)) return INFINITY;
     double x, y, z;
-    unit_vec((double)lon, (double)lat, x, y, z);
+    if (cxyz) {
+        x = __ldg(cxyz + 3 * c), y = __ldg(cxyz + 3 * c + 1), z = __ldg(cxyz + 3 * c + 2);
+    } else {
+        const float lon = __ldg(g.XC + c), lat = __ldg(g.YC + c);
+        if (!(lon == lon) || !(lat == lat)) return INFINITY;
+        unit_vec((double)lon, (double)lat, x, y, z);
+    }
     const double dx = x - qx, dy = y - qy, dz = z - qz;
     return dx * dx + dy * dy + dz * dz;
+}
+
+// the table behind dist2_to_cell: the same unit_vec of the same float32 centre, evaluated once per cell
+__global__ void cell_xyz_kernel(GridDev g, double *cxyz) {
+    const int64_t ncell = (int64_t)g.nface * g.ny * g.nx;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (int64_t)gridDim.x * blockDim.x) {
+        const float lon = g.XC[c], lat = g.YC[c];
+        double x = INFINITY, y = INFINITY, z = INFINITY;
+        if (lon == lon && lat == lat) unit_vec((double)lon, (double)lat, x, y, z);
+        cxyz[3 * c] = x, cxyz[3 * c + 1] = y, cxyz[3 * c + 2] = z;
+    }
+}
+
+// The cell (dy, dx) index steps away from (f, iy, ix), |dy|, |dx| <= 2: vertical steps first, then horizontal ones,
+// every remaining step re-labelled after a face change (reference ind_moves, topology.py:436).  false = no such cell.
+__device__ __forceinline__ bool cell_at_offset(const GridDev &g, int f, int iy, int ix, int dy, int dx, int &nf, int &ny, int &nx) {
+    int moves[4], m = 0;
+    for (int k = 0; k < abs(dy); ++k) moves[m++] = dy > 0 ? 0 : 1;
+    for (int k = 0; k < abs(dx); ++k) moves[m++] = dx > 0 ? 3 : 2;
+    nf = f, ny = iy, nx = ix;
+    for (int k = 0; k < m; ++k) {
+        int came;
+        const int d = moves[k];
+        if (cell_move(g, d, nf, ny, nx, came)) return false;
+        if (came >= 0)
+            for (int j = k + 1; j < m; ++j) moves[j] = remap_dir(moves[j], d, came);
+    }
+    return true;
 }
 
 // reference find_rel (utils.py:321) with find_ind (utils.py:273) for a 1-D table in shared/global
@@ -248,8 +280,12 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
         int f = c0 / (g.ny * g.nx);
         int rem = c0 - f * (g.ny * g.nx);
         int iy = rem / g.nx, ix = rem - iy * g.nx;
-        double best = dist2_to_cell(g, f, iy, ix, qx, qy, qz);
-        // greedy walk to the nearest centre
+        const double *cxyz = a.b.cxyz;
+        double best = dist2_to_cell(g, cxyz, f, iy, ix, qx, qy, qz);
+        // Greedy walk to the nearest centre over the 8 neighbours; where it stops, the 16 cells of the second ring
+        // are looked at as well (on a sheared or strongly stretched grid the Voronoi neighbours of a cell are not all
+        // among its 8 index neighbours, and the descent could stop one cell short) and the walk resumes from a closer
+        // one if there is any.
         for (int iter = 0; iter < a.max_walk; ++iter) {
             int bf = f, by = iy, bx = ix;
             double bd = best;
@@ -259,7 +295,7 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
             for (int k = 0; k < 8; ++k) {
                 int nf, ny, nx;
                 if (!neighbour(g, f, iy, ix, d1s[k], d2s[k], nf, ny, nx)) continue;
-                const double dd = dist2_to_cell(g, nf, ny, nx, qx, qy, qz);
+                const double dd = dist2_to_cell(g, cxyz, nf, ny, nx, qx, qy, qz);
                 if (dd < bd) {
                     bd = dd;
                     bf = nf;
@@ -267,7 +303,23 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
                     bx = nx;
                 }
             }
-            if (bd >= best) break;
+            if (bd >= best) {
+                for (int dy = -2; dy <= 2; ++dy) {
+                    for (int dx = -2; dx <= 2; ++dx) {
+                        if (abs(dy) != 2 && abs(dx) != 2) continue;
+                        int nf, ny, nx;
+                        if (!cell_at_offset(g, f, iy, ix, dy, dx, nf, ny, nx)) continue;
+                        const double dd = dist2_to_cell(g, cxyz, nf, ny, nx, qx, qy, qz);
+                        if (dd < bd) {
+                            bd = dd;
+                            bf = nf;
+                            by = ny;
+                            bx = nx;
+                        }
+                    }
+                }
+                if (bd >= best) break;
+            }
             best = bd;
             f = bf;
             iy = by;
@@ -461,6 +513,17 @@ cudaError_t build_buckets(const GridDev &g, BucketGrid &b, cudaStream_t s) {
     }
     if (e == cudaSuccess && src != b.table)
         e = cudaMemcpyAsync(b.table, src, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess) {
+        // unit vectors of the cell centres (24 bytes per cell); a grid too large for it keeps the sincos path
+        double *cxyz = nullptr;
+        if (cudaMalloc(&cxyz, sizeof(double) * 3 * (size_t)ncell) == cudaSuccess) {
+            cell_xyz_kernel<<<(int)sblocks, threads, 0, s>>>(g, cxyz);
+            b.cxyz = cxyz;
+        } else {
+            cudaGetLastError();
+            b.cxyz = nullptr;
+        }
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
     cudaFree(tmp);
     cudaFree(remaining);

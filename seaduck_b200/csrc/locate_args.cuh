@@ -12,6 +12,9 @@ struct BucketGrid {
     double lon0, lat0, span_lon, span_lat, inv_dlon, inv_dlat;
     int nlon, nlat, periodic;
     int *table;  // one nearby cell (flat index) per bucket
+    // unit vector of every cell centre (3 doubles per cell, +inf for a NaN centre), or NULL when the table did not fit:
+    // a distance is then three loads and three multiply-adds instead of two sincos
+    const double *cxyz;
 };
 
 struct LocateArgs {

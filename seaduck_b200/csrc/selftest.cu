@@ -67,6 +67,20 @@ __global__ void selftest_step_kernel(int64_t n, const double *a, double *out) {
     }
 }
 
+__global__ void selftest_cell_move_kernel(GridDev g, int64_t n, const int32_t *in, int32_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int f = in[4 * i], iy = in[4 * i + 1], ix = in[4 * i + 2], came;
+    const int st = cell_move(g, in[4 * i + 3], f, iy, ix, came);
+    out[5 * i] = f, out[5 * i + 1] = iy, out[5 * i + 2] = ix, out[5 * i + 3] = came, out[5 * i + 4] = st;
+}
+
+cudaError_t launch_selftest_cell_move(const GridDev &g, int64_t n, const int32_t *in, int32_t *out, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    selftest_cell_move_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, n, in, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad,
                                  cudaStream_t s) {
     if (n == 0) return cudaSuccess;

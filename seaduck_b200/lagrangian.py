@@ -786,11 +786,12 @@ class Particle(Position):
         p.__dict__["_derived_ok"] = False
         return p
 
-    def record_snapshot(self, t_stop):
-        """Position and cell of every particle, now, as a :class:`RecordSnapshot` (one ``sdk_pack_records`` launch)."""
+    def record_snapshot(self, t_stop, out=None):
+        """Position and cell of every particle, now, as a :class:`RecordSnapshot` (one ``sdk_pack_records`` launch);
+        ``out``: uint8 device tensor [N, 32] to pack into."""
         from .parallel import pack_records  # noqa: PLC0415
 
-        rec = pack_records(self._cparticles(), self.N, out_index=self._out_index(), device=self.ocedata._torch_device())
+        rec = pack_records(self._cparticles(), self.N, out=out, out_index=self._out_index(), device=self.ocedata._torch_device())
         return RecordSnapshot(self.ocedata, t_stop, rec, self._st.get("face") is not None, self._has_dep)
 
     def to_list_of_time(
@@ -839,11 +840,20 @@ class Particle(Position):
         if snapshots == "auto":
             snapshots = "records" if (state_bytes * len(stops) > self.SNAPSHOT_CLONE_BUDGET and not self.save_raw) else "full"
 
+        ring = None
+        if snapshots == "records" and _on_stop is None:
+            # one allocation for the records of every stop that is kept (a fresh 32 N-byte block per stop would go to
+            # the driver every time: cudaMalloc is slow and serialised across the processes of a node)
+            import torch  # noqa: PLC0415
+
+            n_keep = sum(1 for i in range(len(stops)) if return_in_between or not (update[i] or i == 0))
+            ring = torch.empty((max(n_keep, 1), self.N, 32), dtype=torch.uint8, device=od._torch_device())
+
         def keep(t_stop):
             if _on_stop is not None:
                 _on_stop(t_stop)
             elif snapshots == "records":
-                to_return.append(self.record_snapshot(t_stop))
+                to_return.append(self.record_snapshot(t_stop, out=ring[len(to_return)]))
             else:
                 to_return.append(self.deepcopy())
 

@@ -250,12 +250,23 @@ class ShardedParticle:
         dev = pt.ocedata._torch_device()
         side = torch.cuda.Stream(dev)
         snaps = []
+        # one block for the records of all stops (at most one per stop in the two lists)
+        od = pt.ocedata
+        if isinstance(update_stops, str):
+            n_update = len(od.time_midp) if (od.readiness["time"] and "time" in od[pt.uname].dims) else 0
+        else:
+            n_update = len(list(update_stops))
+        n_max = len(list(normal_stops)) + n_update
+        blocks_per = self.world if self.exchange is not None else 1
+        pool = torch.zeros((n_max, blocks_per, self.n_pad, RECORD_BYTES), dtype=torch.uint8, device=dev)
 
         def on_stop(t_stop):
             # runs right after the leg to t_stop was queued
             cp = pt._cparticles()
+            if len(snaps) >= pool.shape[0]:
+                raise RuntimeError("more stops than expected: pass the update stops explicitly")
             if self.exchange is None:
-                rec = torch.zeros((1, self.n_pad, RECORD_BYTES), dtype=torch.uint8, device=dev)
+                rec = pool[len(snaps)]
                 pack_records(cp, pt.N, out=rec[0], out_index=pt._out_index())
                 snaps.append(ShardedSnapshot(self, t_stop, rec, everyone=False))
                 return
@@ -266,9 +277,9 @@ class ShardedParticle:
             with torch.cuda.stream(side):
                 # off the critical path: wait for everybody's block, keep a copy, free the slot
                 self.exchange.wait(step)
-                blocks = self.exchange.slot_view(step).clone()
+                blocks = pool[len(snaps)]
+                blocks.copy_(self.exchange.slot_view(step))
                 self.exchange.release(step)
-            blocks.record_stream(side)
             snaps.append(ShardedSnapshot(self, t_stop, blocks, everyone=True))
 
         stops, _ = pt.to_list_of_time(normal_stops, update_stops, return_in_between, _on_stop=on_stop)

@@ -172,3 +172,51 @@ def test_partition_of_unity_at_scale():
     np.testing.assert_allclose(ddx[ok], 0.0, rtol=0, atol=1e-11)
     ok = ~np.isnan(ddz)
     np.testing.assert_allclose(ddz[ok], 0.0, rtol=0, atol=1e-11)
+
+
+@pytest.mark.parametrize("shear", [0.0, 0.9, 1.8])
+def test_locate_on_a_sheared_grid_matches_kdtree(shear, oracle_lib):
+    """Nearest cell centre on a sheared curvilinear box with NaN (land) centres: the device search (bucket grid, greedy
+    walk over the 8 neighbours, second-ring confirmation) against scipy's cKDTree on the same centres, the way the
+    reference finds it (utils.py:225,309).  With shear the Voronoi neighbours of a cell are not all among its 8 index
+    neighbours, which is what the second ring is for."""
+    import seaduck_b200 as sd
+    from seaduck_b200 import minixr
+
+    ny, nx = 60, 80
+    dlon, dlat = 0.25, 0.2
+    j, i = np.meshgrid(np.arange(ny + 1), np.arange(nx + 1), indexing="ij")
+    xg = -30.0 + dlon * i + shear * dlon * (j - ny / 2) * 0.8
+    yg = 10.0 + dlat * j + 0.02 * np.sin(i / 7.0)
+    xc = 0.25 * (xg[:-1, :-1] + xg[1:, :-1] + xg[:-1, 1:] + xg[1:, 1:])
+    yc = 0.25 * (yg[:-1, :-1] + yg[1:, :-1] + yg[:-1, 1:] + yg[1:, 1:])
+    rng = np.random.default_rng(17)
+    land = rng.random((ny, nx)) < 0.04
+    xc_nan, yc_nan = xc.copy(), yc.copy()
+    xc_nan[land] = np.nan
+    yc_nan[land] = np.nan
+    ds = minixr.Dataset(coords=dict(XC=(["Y", "X"], xc_nan), YC=(["Y", "X"], yc_nan), XG=(["Yp1", "Xp1"], xg), YG=(["Yp1", "Xp1"], yg)), data_vars={})
+    od = sd.OceData(ds)
+    n = 20000
+    # points well inside the grid (the outer two rows / columns are left alone: past the edge "nearest" is all there is)
+    jj = rng.uniform(3, ny - 3, n)
+    ii = rng.uniform(3, nx - 3, n)
+    lon = -30.0 + dlon * ii + shear * dlon * (jj - ny / 2) * 0.8
+    lat = 10.0 + dlat * jj
+    pos = sd.Position().from_latlon(x=lon, y=lat, data=od)
+    og = oracle_lib.OracleGrid(od)
+    ry, rx = og.find_ind_h(lon, lat)
+    same = (pos.iy == ry) & (pos.ix == rx)
+    if not same.all():
+        # a query within rounding of a Voronoi edge may legitimately go either way: allow it only if both centres are
+        # equally far to 1e-12 relative
+        bad = np.flatnonzero(~same)
+        from oracle.oracle import spherical2cartesian
+
+        def d2(y_, x_):
+            cx, cy, cz = spherical2cartesian(og.YC[y_, x_].astype(float), og.XC[y_, x_].astype(float))
+            qx, qy, qz = spherical2cartesian(lat[bad], lon[bad])
+            return (cx - qx) ** 2 + (cy - qy) ** 2 + (cz - qz) ** 2
+
+        mine, ref = d2(pos.iy[bad], pos.ix[bad]), d2(ry[bad], rx[bad])
+        assert np.all(np.abs(mine - ref) <= 1e-12 * ref), f"{bad.size} of {n} points in a farther cell (shear {shear})"
