@@ -135,10 +135,10 @@ __global__ void cell_xyz_kernel(GridDev g, double *cxyz) {
     }
 }
 
-// The cell (dy, dx) index steps away from (f, iy, ix), |dy|, |dx| <= 2: vertical steps first, then horizontal ones,
+// The cell (dy, dx) index steps away from (f, iy, ix), |dy|, |dx| <= 3: vertical steps first, then horizontal ones,
 // every remaining step re-labelled after a face change (reference ind_moves, topology.py:436).  false = no such cell.
 __device__ __forceinline__ bool cell_at_offset(const GridDev &g, int f, int iy, int ix, int dy, int dx, int &nf, int &ny, int &nx) {
-    int moves[4], m = 0;
+    int moves[6], m = 0;
     for (int k = 0; k < abs(dy); ++k) moves[m++] = dy > 0 ? 0 : 1;
     for (int k = 0; k < abs(dx); ++k) moves[m++] = dx > 0 ? 3 : 2;
     nf = f, ny = iy, nx = ix;
@@ -289,6 +289,7 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
         for (int iter = 0; iter < a.max_walk; ++iter) {
             int bf = f, by = iy, bx = ix;
             double bd = best;
+            bool near_hole = false;
             const int d1s[8] = {0, 1, 2, 3, 0, 0, 1, 1};
             const int d2s[8] = {-1, -1, -1, -1, 2, 3, 2, 3};
 #pragma unroll
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
                 int nf, ny, nx;
                 if (!neighbour(g, f, iy, ix, d1s[k], d2s[k], nf, ny, nx)) continue;
                 const double dd = dist2_to_cell(g, cxyz, nf, ny, nx, qx, qy, qz);
+                near_hole |= !(dd < INFINITY);
                 if (dd < bd) {
                     bd = dd;
                     bf = nf;
@@ -304,17 +306,23 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
                 }
             }
             if (bd >= best) {
-                for (int dy = -2; dy <= 2; ++dy) {
-                    for (int dx = -2; dx <= 2; ++dx) {
-                        if (abs(dy) != 2 && abs(dx) != 2) continue;
-                        int nf, ny, nx;
-                        if (!cell_at_offset(g, f, iy, ix, dy, dx, nf, ny, nx)) continue;
-                        const double dd = dist2_to_cell(g, cxyz, nf, ny, nx, qx, qy, qz);
-                        if (dd < bd) {
-                            bd = dd;
-                            bf = nf;
-                            by = ny;
-                            bx = nx;
+                // second ring; a third one where a centre nearby is NaN (land without coordinates: the nearest valid
+                // centre may then lie beyond the hole)
+                bool hole = near_hole;
+                for (int ring = 2; ring <= (hole ? 3 : 2); ++ring) {
+                    for (int dy = -ring; dy <= ring; ++dy) {
+                        for (int dx = -ring; dx <= ring; ++dx) {
+                            if (abs(dy) != ring && abs(dx) != ring) continue;
+                            int nf, ny, nx;
+                            if (!cell_at_offset(g, f, iy, ix, dy, dx, nf, ny, nx)) continue;
+                            const double dd = dist2_to_cell(g, cxyz, nf, ny, nx, qx, qy, qz);
+                            hole |= !(dd < INFINITY);
+                            if (dd < bd) {
+                                bd = dd;
+                                bf = nf;
+                                by = ny;
+                                bx = nx;
+                            }
                         }
                     }
                 }

@@ -38,7 +38,19 @@ def test_budget_postprocessing_matches_reference(make):
         clear[last] = True
         np.testing.assert_array_equal(ind1[:, clear], gold[f"s{i}_ind1"][:, clear], err_msg="ind1")
         same_on_ties = (ind1[:, ~clear] == gold[f"s{i}_ind1"][:, ~clear]).all(axis=0)
-        assert same_on_ties.size == 0 or same_on_ties.mean() > 0.8  # exact ties resolve alike, noisy ones may not
+        # The tie records are the ones the reference itself does not resolve reproducibly: tests/golden/budget_ties.npz
+        # (oracle/make_golden_budget_ties.py) holds what its numba-on and numba-off runs -- same code, libm of numba vs
+        # numpy -- give for this case, and how often THEY differ.  The device may differ from the golden (numba on) on
+        # tie records only, and not more often than twice the reference differs from itself (+2).
+        n_tie, n_diff = int((~clear).sum()), int((~same_on_ties).sum())
+        ref_self = 0
+        if case["name"] == "llc_transport":
+            ties = np.load(os.path.join(GOLD, "budget_ties.npz"))
+            if bool(ties[f"s{i}_same_log_shape"]):
+                ref_self = int(ties[f"s{i}_modes_differ"].sum())
+        print(f"{case['name']} stop {i}: {ind1.shape[1]} records, {n_tie} which_wall ties, device differs from the golden on {n_diff} "
+              f"of them; the reference's numba-on and numba-off runs differ on {ref_self} records")
+        assert n_diff <= 2 * ref_self + 2, (n_diff, ref_self, n_tie)
         np.testing.assert_array_equal(ind2, gold[f"s{i}_ind2"], err_msg="ind2")
         cases.assert_close("frac", frac, gold[f"s{i}_frac"])
         cases.assert_close("tres", tres, gold[f"s{i}_tres"])

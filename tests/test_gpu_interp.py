@@ -219,4 +219,9 @@ def test_locate_on_a_sheared_grid_matches_kdtree(shear, oracle_lib):
             return (cx - qx) ** 2 + (cy - qy) ** 2 + (cz - qz) ** 2
 
         mine, ref = d2(pos.iy[bad], pos.ix[bad]), d2(ry[bad], rx[bad])
-        assert np.all(np.abs(mine - ref) <= 1e-12 * ref), f"{bad.size} of {n} points in a farther cell (shear {shear})"
+        worse = np.abs(mine - ref) > 1e-12 * ref
+        off = np.stack([pos.iy[bad] - ry[bad], pos.ix[bad] - rx[bad]], axis=1)[worse][:8]
+        assert not worse.any(), (
+            f"{int(worse.sum())} of {n} points in a farther cell (shear {shear}); index offsets (dy, dx) of the first: {off.tolist()}, "
+            f"distance ratios {np.sqrt(mine[worse] / ref[worse])[:8].round(4).tolist()}"
+        )
