@@ -20,7 +20,6 @@ node ``x`` for the ``k``-th derivative is, as in the reference (:84-306),
 
 from __future__ import annotations
 
-import copy
 import logging
 from itertools import combinations
 from math import factorial
@@ -200,28 +199,33 @@ def _find_pk_4d(masked, inheritance=DEFAULT_INHERITANCE):
     return pk4d
 
 
-def _kash(kernel):
-    return hash(tuple((int(i), int(j)) for (i, j) in kernel))
+# Nodes at the same distance from the centre are ordered by a slightly skewed distance, so that +x comes before +y
+# before -x / -y exactly as in the reference's node order (kernel_weight.py:623-642, :675-680): the skew is the
+# reference's and part of the observable behaviour (it fixes the column order of every weight matrix).
+_SKEW = np.array([0.01, 0.00618])
+_LEVELS_PER_MODE = {"dz": 2, "linear": 2, "dt": 2, "nearest": 1}
+
+
+def _node_key(kernel):
+    return tuple((int(i), int(j)) for (i, j) in kernel)
 
 
 def _auto_inheritance(kernel, hkernel="interp"):
-    """Natural nesting of smaller stencils inside ``kernel`` (reference :623)."""
-    if hkernel == "interp":
-        doll = [list(range(len(kernel)))]
-    elif hkernel == "dx":
-        doll = [[i for i in range(len(kernel)) if kernel[i][1] == 0]]
-    elif hkernel == "dy":
-        doll = [[i for i in range(len(kernel)) if kernel[i][0] == 0]]
-    doll[0] = sorted(doll[0], key=lambda i: max(abs(kernel[i] + np.array([0.01, 0.00618]))))
-    last = doll[-1]
-    lask = np.array([kernel[i] for i in last])
-    dist = round(max(np.max(abs(lask), axis=1)))
-    for radius in range(dist - 1, -1, -1):
-        new = [i for i in last if max(abs(kernel[i])) <= radius]
-        if new != last:
-            last = new
-            doll.append(last)
-    return doll
+    """The nested stencils a kernel falls back on next to land, largest first (reference :623): all nodes (for a
+    derivative: the nodes on the axis it acts along), then the nodes within Chebyshev distance R - 1, R - 2 ... 0 of the
+    centre, every level in skewed-distance order and listed only when it differs from the one before."""
+    kernel = np.asarray(kernel)
+    on_axis = {"interp": np.ones(len(kernel), bool), "dx": kernel[:, 1] == 0, "dy": kernel[:, 0] == 0}[hkernel]
+    reach = np.abs(kernel).max(axis=1)
+    skewed = np.abs(kernel + _SKEW).max(axis=1)
+    members = np.flatnonzero(on_axis)
+    members = members[np.argsort(skewed[members], kind="stable")].tolist()
+    levels = [members]
+    for radius in range(int(round(reach[members].max())) - 1, -1, -1):
+        inner = [i for i in levels[-1] if reach[i] <= radius]
+        if inner != levels[-1]:
+            levels.append(inner)
+    return levels
 
 
 class KnW:
@@ -237,28 +241,27 @@ class KnW:
         h_order=0,
         ignore_mask=False,
     ):
-        kernel = np.asarray(kernel)
-        kernel_sort = np.abs(kernel + np.array([0.01, 0.00618])).sum(axis=1).argsort()
-        kernel_sort_inv = kernel_sort.argsort()
-        if (inheritance is not None) and ignore_mask:
+        given = np.asarray(kernel)
+        if inheritance is not None and ignore_mask:
             logging.info("Overwriting the inheritance object to None, because we ignore masking")
-        if isinstance(inheritance, str) and inheritance == "auto":
-            inheritance = _auto_inheritance(kernel, hkernel=hkernel)
+        if isinstance(inheritance, str):
+            if inheritance != "auto":
+                raise ValueError("Unknown type of inherirance")
+            inheritance = _auto_inheritance(given, hkernel=hkernel)
         elif inheritance is None:
-            inheritance = [list(range(len(kernel)))]
-        elif isinstance(inheritance, list):
-            pass
-        else:
+            inheritance = [list(range(len(given)))]
+        elif not isinstance(inheritance, list):
             raise ValueError("Unknown type of inherirance")
-        self.kernel = kernel[kernel_sort]
-        self.inheritance = [sorted([int(kernel_sort_inv[i]) for i in heir]) for heir in inheritance]
-        self.hkernel = hkernel
-        self.vkernel = vkernel
-        self.tkernel = tkernel
-        self.h_order = h_order
-        self.ignore_mask = ignore_mask
-        self.kernels = [np.array([self.kernel[i] for i in doll]) for doll in self.inheritance]
-        self.hfuncs = [_Stencil(a_kernel, self.hkernel, self.h_order) for a_kernel in self.kernels]
+        # canonical node order: by (skewed) L1 distance from the centre; the levels are re-expressed in it
+        order = np.abs(given + _SKEW).sum(axis=1).argsort()
+        position = np.empty(len(order), int)
+        position[order] = np.arange(len(order))
+        self.kernel = given[order]
+        self.inheritance = [sorted(int(position[i]) for i in level) for level in inheritance]
+        self.hkernel, self.vkernel, self.tkernel = hkernel, vkernel, tkernel
+        self.h_order, self.ignore_mask = h_order, ignore_mask
+        self.kernels = [self.kernel[np.array(level, int)] for level in self.inheritance]
+        self.hfuncs = [_Stencil(nodes, hkernel, h_order) for nodes in self.kernels]
 
     def same_hsize(self, other):
         if not isinstance(other, type(self)):
@@ -269,75 +272,52 @@ class KnW:
             return False
 
     def same_size(self, other):
-        only_size = {"dz": 2, "linear": 2, "dt": 2, "nearest": 1}
-        return (
-            self.same_hsize(other)
-            and only_size[self.vkernel] == only_size[other.vkernel]
-            and only_size[self.tkernel] == only_size[other.tkernel]
-        )
+        return self.same_hsize(other) and self.nz == other.nz and self.nt == other.nt
+
+    def _modes(self):
+        return (self.hkernel, self.vkernel, self.tkernel)
 
     def __eq__(self, other):
+        # (like the reference, h_order and ignore_mask take part in the hash but not in the comparison)
         if not isinstance(other, type(self)):
             return False
-        shpe_same = self.same_hsize(other) and self.inheritance == other.inheritance
-        diff_same = (self.hkernel == other.hkernel) and (self.vkernel == other.vkernel) and (self.tkernel == other.tkernel)
-        return shpe_same and diff_same
+        return self.same_hsize(other) and self.inheritance == other.inheritance and self._modes() == other._modes()
 
     def __hash__(self):
-        return hash(
-            (
-                _kash(self.kernel),
-                tuple(tuple(i for i in heir) for heir in self.inheritance),
-                self.ignore_mask,
-                self.h_order,
-                self.hkernel,
-                self.vkernel,
-                self.tkernel,
-            )
-        )
+        levels = tuple(tuple(level) for level in self.inheritance)
+        return hash((_node_key(self.kernel), levels, self.ignore_mask, self.h_order) + self._modes())
 
     def size_hash(self):
-        only_size = {"dz": 2, "linear": 2, "dt": 2, "nearest": 1}
-        return hash((_kash(self.kernel), only_size[self.vkernel], only_size[self.tkernel]))
+        return hash((_node_key(self.kernel), self.nz, self.nt))
 
     @property
     def nz(self):
-        return 2 if self.vkernel in ["linear", "dz"] else 1
+        return _LEVELS_PER_MODE[self.vkernel]
 
     @property
     def nt(self):
-        return 2 if self.tkernel in ["linear", "dt"] else 1
+        return _LEVELS_PER_MODE[self.tkernel]
+
+    @staticmethod
+    def _line_factors(mode, r, n, interp, deriv):
+        """Factors of the (up to two) nodes along z or t as an ``(n, levels)`` array: ``[1 - r, r]`` to interpolate,
+        ``[-1, 1]`` to differentiate, ``[1]`` for the nearest node."""
+        if mode == interp:
+            r = np.full(n, float(r)) if np.ndim(r) == 0 else np.array(r, float)
+            return np.stack([1 - r, r], axis=1)
+        if mode == deriv:
+            return np.tile(np.array([-1.0, 1.0]), (n, 1))
+        return np.ones((n, 1))
 
     def get_weight(self, rx, ry, rz=0, rt=0, pk4d=None, bottom_scheme="no flux"):
-        """Weights ``(N, M, nz, nt)`` given the rel-coords (reference :772). Host mirror."""
-        nz, nt = self.nz, self.nt
-        rx = np.asarray(rx, float)
-        ry = np.asarray(ry, float)
-        n = len(rx)
+        """Weights ``(N, M, nz, nt)`` given the rel-coords (reference :772).  Host mirror of what the CUDA interpolation
+        kernel evaluates per point: horizontal Lagrange weights of the stencil each (z, t) node can use
+        (``pk4d`` from :func:`_find_pk_4d`; the full stencil without it), times the vertical and the temporal factor."""
+        rx, ry = np.asarray(rx, float), np.asarray(ry, float)
+        n, nz, nt = len(rx), self.nz, self.nt
         weight = np.zeros((n, len(self.kernel), nz, nt))
-        if isinstance(rz, (int, float)) and self.vkernel != "nearest":
-            rz = np.array([rz for i in range(n)])
-        if isinstance(rt, (int, float)) and self.tkernel != "nearest":
-            rt = np.array([rt for i in range(n)])
-        if self.tkernel == "linear":
-            rpt = copy.deepcopy(rt)
-            tweight = [(1 - rpt).reshape((n, 1, 1)), rpt.reshape((n, 1, 1))]
-        elif self.tkernel == "dt":
-            tweight = [-1, 1]
-        else:
-            tweight = [1]
-        if self.vkernel == "linear":
-            rpz = copy.deepcopy(rz)
-            zweight = [(1 - rpz).reshape((n, 1)), rpz.reshape((n, 1))]
-        elif self.vkernel == "dz":
-            zweight = [-1, 1]
-        else:
-            zweight = [1]
         if pk4d is None:
-            base = self.hfuncs[0](rx, ry)
-            for jt in range(nt):
-                for jz in range(nz):
-                    weight[:, self.inheritance[0], jz, jt] = base
+            weight[:, self.inheritance[0]] = self.hfuncs[0](rx, ry)[:, :, None, None]
         else:
             if nt != len(pk4d) or nz != len(pk4d[0]):
                 raise ValueError("The kernel and the input pk4d does not match")
@@ -346,16 +326,20 @@ class KnW:
                     weight[:, :, jz, jt] = get_weight_cascade(
                         rx, ry, pk4d[jt][jz], kernel_large=self.kernel, inheritance=self.inheritance, funcs=self.hfuncs
                     )
+        along_z = self._line_factors(self.vkernel, rz, n, "linear", "dz")
+        along_t = self._line_factors(self.tkernel, rt, n, "linear", "dt")
+        ghost_below = self.vkernel == "linear" and bottom_scheme == "no flux"
         for jt in range(nt):
-            if (self.vkernel == "linear") and (bottom_scheme == "no flux"):
-                secondlayermasked = np.isnan(weight[:, :, 0, jt]).any(axis=1)
-                weight[secondlayermasked, :, 0, jt] = 0
-                shouldbemasked = np.logical_and(secondlayermasked, rz < 1 / 2)
-                weight[shouldbemasked, :, 1, jt] = 0
-                zweight[1][secondlayermasked] = 1
-            for jz in range(nz):
-                weight[:, :, jz, jt] *= zweight[jz]
-            weight[:, :, :, jt] *= tweight[jt]
+            if ghost_below:
+                # No-flux bottom: where the deeper of the two levels (index 0) has no usable stencil it is treated as a
+                # ghost point carrying the value of the level above -- all the weight goes to level 1 -- unless the
+                # point lies in the lower half of the layer (rz < 1/2), which is inside the bottom: no weight at all.
+                # (The factor of level 1 stays 1 for the time nodes that follow, as in the reference.)
+                dry_below = np.isnan(weight[:, :, 0, jt]).any(axis=1)
+                weight[dry_below, :, 0, jt] = 0
+                weight[dry_below & (np.asarray(rz) < 0.5), :, 1, jt] = 0
+                along_z[dry_below, 1] = 1
+            weight[:, :, :, jt] = weight[:, :, :, jt] * along_z[:, None, :] * along_t[:, None, None, jt]
         return weight
 
     def describe(self):

@@ -1,4 +1,12 @@
-"""``OceInterp``: one call for Eulerian or Lagrangian interpolation (reference ``seaduck/oceinterp.py:14``)."""
+"""``OceInterp``: one call for Eulerian or Lagrangian interpolation (same signature, return values and exceptions
+as the reference's ``seaduck/oceinterp.py:14``).
+
+The call is a thin front end: it pairs every requested variable with a kernel, turns the time argument into seconds,
+and then either locates the points once and interpolates (``Position``), or carries particles through the requested
+times (``Particle.to_list_of_time``) and evaluates every request on every snapshot.  Requests of the form
+``"__particle.<attr>"`` read an attribute of the snapshots instead of interpolating; ``"__particle.raw"`` hands the
+snapshots themselves back.
+"""
 
 import warnings
 
@@ -11,6 +19,57 @@ from .ocedata import OceData
 from .utils import convert_time
 
 lagrange_token = "__particle."
+
+
+def _requests(var_list, kernel_list, kernel_kwarg):
+    """``(variables, kernels)`` as two parallel lists.  A dict maps variables to kernels; without kernels every scalar
+    gets ``KnW(**kernel_kwarg)`` and every (u, v) pair the particle kernels (or that same kernel twice when
+    ``kernel_kwarg`` asks for something specific)."""
+    if isinstance(var_list, dict):
+        return list(var_list), list(var_list.values())
+    if isinstance(var_list, (str, tuple)):
+        var_list = [var_list]
+    if not isinstance(var_list, list):
+        raise ValueError("var_list type not recognized.")
+    if kernel_list is not None:
+        return var_list, kernel_list
+    shared = KnW(**kernel_kwarg)
+    pair = (shared, shared) if kernel_kwarg else (uknw, vknw)
+    kernels = []
+    for var in var_list:
+        if not isinstance(var, (str, tuple)):
+            raise ValueError("members of var_list need to be made up of string or tuples")
+        kernels.append(shared if isinstance(var, str) else pair)
+    return var_list, kernels
+
+
+def _seconds(t):
+    """Time argument -> seconds since 1970: floats pass, datetime64 / strings (scalars or arrays) are converted."""
+    if isinstance(t, np.ndarray):
+        stamped = np.issubdtype(t.dtype, np.datetime64) or np.issubdtype(t.dtype, str)
+        return np.array([convert_time(one) for one in t]) if stamped else t
+    if isinstance(t, (np.datetime64, str)):
+        return convert_time(t)
+    if isinstance(t, float):
+        return t
+    raise ValueError("time format not supported")
+
+
+def _along_trajectories(od, variables, kernels, x, y, z, t, lagrange_kwarg, update_stops, return_in_between):
+    if np.ndim(t) == 0 or len(t) < 2:
+        raise ValueError("There needs to be at least two time steps to run the lagrangian Particle")
+    pt = Particle(x=x, y=y, z=z, t=np.ones_like(x) * t[0], data=od, **lagrange_kwarg)
+    stops, snapshots = pt.to_list_of_time(t[1:], update_stops=update_stops, return_in_between=return_in_between)
+
+    def answer(var, knw):
+        if var == lagrange_token + "raw":
+            return snapshots
+        if isinstance(var, str) and lagrange_token in var:
+            attr = var[len(lagrange_token):]
+            return [getattr(snap, attr) for snap in snapshots]
+        return [snap.interpolate(var, knw) for snap in snapshots]
+
+    return stops, [answer(var, knw) for var, knw in zip(variables, kernels)]
 
 
 def OceInterp(
@@ -31,57 +90,15 @@ def OceInterp(
     """Interpolate ``var_list`` at points, or along trajectories when ``lagrangian=True``."""
     if not isinstance(od, OceData):
         od = OceData(od)
-    if isinstance(var_list, dict):
-        kernel_list = list(var_list.values())
-        var_list = list(var_list.keys())
-    elif isinstance(var_list, (str, tuple)):
-        var_list = [var_list]
-    elif not isinstance(var_list, list):
-        raise ValueError("var_list type not recognized.")
-    if kernel_list is None:
-        kernel_list = []
-        the_kernel = KnW(**kernel_kwarg)
-        for i in var_list:
-            if isinstance(i, str):
-                kernel_list.append(the_kernel)
-            elif isinstance(i, tuple):
-                kernel_list.append((the_kernel, the_kernel) if kernel_kwarg != {} else (uknw, vknw))
-            else:
-                raise ValueError("members of var_list need to be made up of string or tuples")
-    if isinstance(t, np.ndarray):
-        if np.issubdtype(t.dtype, np.datetime64) or np.issubdtype(t.dtype, str):
-            t = np.array([convert_time(some_t) for some_t in t])
-    elif isinstance(t, (np.datetime64, str)):
-        t = convert_time(t)
-    elif isinstance(t, float):
-        pass
-    else:
-        raise ValueError("time format not supported")
+    variables, kernels = _requests(var_list, kernel_list, kernel_kwarg)
+    t = _seconds(t)
     if not lagrangian:
-        pt = Position()
-        pt.from_latlon(x=x, y=y, z=z, t=t, data=od)
-        for var in var_list:
-            if lagrange_token in var:
-                raise AttributeError("__particle variables is only available for Lagrangian Particles")
-        return pt.interpolate(var_list, kernel_list)
-    try:
-        assert len(t) > 1
-    except AssertionError as exc:
-        raise ValueError("There needs to be at least two time steps to run the lagrangian Particle") from exc
-    t_start = t[0]
-    t_nec = t[1:]
-    pt = Particle(x=x, y=y, z=z, t=np.ones_like(x) * t_start, data=od, **lagrange_kwarg)
-    stops, raw = pt.to_list_of_time(t_nec, update_stops=update_stops, return_in_between=return_in_between)
-    to_return = []
-    for i, var in enumerate(var_list):
-        if var == lagrange_token + "raw":
-            to_return.append(raw)
-        elif lagrange_token in var:
-            to_return.append([getattr(snap, var[len(lagrange_token):]) for snap in raw])
-        else:
-            to_return.append([snap.interpolate(var, kernel_list[i]) for snap in raw])
+        if any(lagrange_token in var for var in variables):
+            raise AttributeError("__particle variables is only available for Lagrangian Particles")
+        return Position().from_latlon(x=x, y=y, z=z, t=t, data=od).interpolate(variables, kernels)
+    stops, results = _along_trajectories(od, variables, kernels, x, y, z, t, lagrange_kwarg, update_stops, return_in_between)
     if return_pt_time:
-        return stops, to_return
+        return stops, results
     if return_in_between:
         warnings.warn("Some of the returns is not on the times you specified.")
-    return to_return
+    return results
