@@ -347,6 +347,13 @@ typedef struct sdk_points {
 /* scalar variable */
 int sdk_interp_scalar(const sdk_grid *grid, const sdk_points *pts, const sdk_field *field,
                       const sdk_kernel_desc *knw, double *out, void *stream);
+/* several scalar variables in one launch (at most SDK_MAX_MULTI_FIELDS): they must share the kernel, the grid position
+ * (dimensions, staggering), the mask and the time / vertical layout -- T and S of an ocean model, say.  Node indices, wet
+ * flags, the choice of the stencil and the weights are worked out once per point; every field adds its gathers and a dot
+ * product.  fields: HOST array of n_fields descriptors, outs: HOST array of n_fields DEVICE pointers. */
+#define SDK_MAX_MULTI_FIELDS 4
+int sdk_interp_scalar_multi(const sdk_grid *grid, const sdk_points *pts, const sdk_field *fields, int32_t n_fields,
+                            const sdk_kernel_desc *knw, double *const *outs, void *stream);
 /* horizontal vector on a grid with faces (components may swap / change sign across faces);
  * vec_transform != 0 rotates the result to east/north with cs, sn (utils.py:206). */
 int sdk_interp_vector(const sdk_grid *grid, const sdk_points *pts, const sdk_field *fu, const sdk_field *fv,

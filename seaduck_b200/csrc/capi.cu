@@ -460,6 +460,31 @@ int sdk_interp_scalar(const sdk_grid *grid, const sdk_points *pts, const sdk_fie
     return SDK_OK;
 }
 
+int sdk_interp_scalar_multi(const sdk_grid *grid, const sdk_points *pts, const sdk_field *fields, int32_t n_fields,
+                            const sdk_kernel_desc *knw, double *const *outs, void *stream) {
+    if (!fields || !outs || n_fields < 1 || n_fields > SDK_MAX_MULTI_FIELDS)
+        return fail(SDK_EINVAL, "sdk_interp_scalar_multi: between 1 and SDK_MAX_MULTI_FIELDS fields");
+    sdk::InterpMultiArgs a;
+    for (int k = 0; k < n_fields; ++k) {
+        int rc = check_interp(grid, pts, &fields[k], knw);
+        if (rc) return rc;
+        if (!outs[k]) return fail(SDK_EINVAL, "sdk_interp_scalar_multi: output missing");
+        const sdk_field &f = fields[k], &f0 = fields[0];
+        if (f.has_time != f0.has_time || f.nt != f0.nt || f.it0 != f0.it0 || f.has_z != f0.has_z || f.nz != f0.nz || f.ny != f0.ny ||
+            f.nx != f0.nx || f.xstag != f0.xstag || f.ystag != f0.ystag || f.mask != f0.mask)
+            return fail(SDK_EINVAL, "sdk_interp_scalar_multi: the fields must share shape, staggering and mask");
+        a.f[k] = f;
+        a.out[k] = outs[k];
+    }
+    a.g = grid->dev;
+    a.pts = *pts;
+    a.k = *knw;
+    a.n_fields = n_fields;
+    cudaError_t e = sdk::launch_interp_multi(a, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_interp_scalar_multi: launch");
+    return SDK_OK;
+}
+
 int sdk_interp_vector(const sdk_grid *grid, const sdk_points *pts, const sdk_field *fu, const sdk_field *fv,
                       const sdk_kernel_desc *ku, const sdk_kernel_desc *kv, int vec_transform, double *out_u,
                       double *out_v, void *stream) {

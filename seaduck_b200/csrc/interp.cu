@@ -228,6 +228,93 @@ __global__ void __launch_bounds__(128, MAXM <= 9 ? SDK_INTERP_MIN_BLOCKS : 1) in
     a.out_v[o] = v;
 }
 
+// Several scalar variables at once (T and S with one KnW, say): node indices, wet flags, the choice of the stencil and
+// the Lagrange weights depend on the points and the kernel only -- they are worked out once, as a weight per node and
+// vertical level, and every field then costs its gathers and a dot product.  TWO: vertical or temporal kernels with two
+// nodes (otherwise the second set of weights does not exist and takes no registers).
+template <int MAXM, bool TWO>
+__global__ void __launch_bounds__(128, MAXM <= 9 ? (TWO ? 4 : 6) : 1) interp_scalar_multi_kernel(const __grid_constant__ InterpMultiArgs a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.pts.n) return;
+    const sdk_points &p = a.pts;
+    const sdk_kernel_desc &K = a.k;
+    const sdk_field &F0 = a.f[0];
+    const int f = p.face ? p.face[i] : 0, iy = p.iy[i], ix = p.ix[i];
+    NodeSet<MAXM> ns;
+    find_nodes<MAXM>(a.g, K, f, iy, ix, ns);
+    const double rxs = F0.xstag ? p.rx[i] + 0.5 : p.rx[i];
+    const double rys = F0.ystag ? p.ry[i] + 0.5 : p.ry[i];
+    const int kz0 = p.kz ? p.kz[i] : 0, kt0 = p.kt ? p.kt[i] : 0;
+    const double rz = p.rz ? p.rz[i] : 0.0, rt = p.rt ? p.rt[i] : 0.0;
+    const int nz = (TWO && K.vmode != SDK_MODE_NEAREST) ? 2 : 1;
+    const int nt = (TWO && K.tmode != SDK_MODE_NEAREST) ? 2 : 1;
+    const bool use_mask = !K.ignore_mask && F0.mask != nullptr;
+    constexpr int NZ = TWO ? 2 : 1;
+    double w[NZ][MAXM];
+    uint32_t use[NZ];  // nodes of the stencil chosen for this vertical level
+    bool znan[NZ];
+#pragma unroll
+    for (int jz = 0; jz < NZ; ++jz) {
+        znan[jz] = false;
+        int level = 0;
+        if (jz < nz && use_mask) {
+            unsigned wet = 0;
+#pragma unroll
+            for (int m = 0; m < MAXM; ++m)
+                if (m < K.n_nodes && is_wet(a.g, F0, ns.packed[m], kz0 - jz)) wet |= 1u << m;
+            level = -1;
+            for (int l = K.n_levels - 1; l >= 0; --l)
+                if ((wet & K.level[l].node_mask) == K.level[l].node_mask) level = l;
+        }
+        znan[jz] = level < 0;
+        const uint32_t mask = (level < 0 || jz >= nz) ? 0u : K.level[level].node_mask;
+        use[jz] = mask;
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) w[jz][m] = (m < K.n_nodes && (mask >> m & 1u)) ? node_weight(K, level, m, rxs, rys) : 0.0;
+    }
+    // vertical factors and the ghost point below the bottom (same rule as interp_value)
+    double zw[2] = {1.0, 0.0};
+    bool kill[2] = {false, false};
+    if (K.vmode == SDK_MODE_LINEAR) {
+        zw[0] = 1 - rz, zw[1] = rz;
+        if (TWO && K.bottom_no_flux && znan[0]) {
+            znan[0] = false, kill[0] = true;
+            if (rz < 0.5) znan[NZ - 1] = false, kill[1] = true;
+            zw[1] = 1.0;
+        }
+    } else if (K.vmode == SDK_MODE_DERIV) {
+        zw[0] = -1.0, zw[1] = 1.0;
+    }
+    const int64_t o = p.out_index ? (int64_t)p.out_index[i] : i;
+    for (int k = 0; k < a.n_fields; ++k) {
+        const sdk_field &F = a.f[k];
+        double total = 0.0;
+        for (int jt = 0; jt < nt; ++jt) {
+            const double tw = K.tmode == SDK_MODE_LINEAR ? (jt == 0 ? 1 - rt : rt) : (K.tmode == SDK_MODE_DERIV ? (jt == 0 ? -1.0 : 1.0) : 1.0);
+            double part = 0.0;
+#pragma unroll
+            for (int jz = 0; jz < NZ; ++jz) {
+                if (jz >= nz) continue;
+                double acc = 0.0;
+                if (!kill[jz]) {
+#pragma unroll
+                    for (int m = 0; m < MAXM; ++m) {
+                        // (same expression as the single-field kernel: value times weight, summed over the stencil's nodes
+                        // in node order; nodes outside the chosen stencil are not read)
+                        if (m < K.n_nodes && (use[jz] >> m & 1u)) {
+                            const double v = ns.packed[m] == SDK_NODE_RAISES ? NAN : field_value(a.g, F, ns.packed[m], kz0 - jz, kt0 + jt);
+                            acc += v * w[jz][m];
+                        }
+                    }
+                }
+                part += znan[jz] ? NAN : acc * zw[jz];
+            }
+            total += part * tw;
+        }
+        a.out[k][o] = total;
+    }
+}
+
 // K4: a dry cell's west / south wall is wet when the cell on the other side is wet; a W point is
 // wet when the cell below or above it is (reference get_masks.py:12,46,79).
 __global__ void build_masks_kernel(GridDev g, const uint8_t *maskC, int nz, uint8_t *maskU, uint8_t *maskV,
@@ -270,6 +357,21 @@ cudaError_t launch_interp(const InterpArgs &a, bool vector, cudaStream_t s) {
     } else {
         if (small) interp_scalar_kernel<9><<<blocks, threads, 0, s>>>(a);
         else interp_scalar_kernel<SDK_MAX_NODES><<<blocks, threads, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_interp_multi(const InterpMultiArgs &a, cudaStream_t s) {
+    if (a.pts.n == 0) return cudaSuccess;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((a.pts.n + threads - 1) / threads);
+    const bool two = a.k.vmode != SDK_MODE_NEAREST || a.k.tmode != SDK_MODE_NEAREST;
+    if (a.k.n_nodes <= 9) {
+        if (two) interp_scalar_multi_kernel<9, true><<<blocks, threads, 0, s>>>(a);
+        else interp_scalar_multi_kernel<9, false><<<blocks, threads, 0, s>>>(a);
+    } else {
+        if (two) interp_scalar_multi_kernel<SDK_MAX_NODES, true><<<blocks, threads, 0, s>>>(a);
+        else interp_scalar_multi_kernel<SDK_MAX_NODES, false><<<blocks, threads, 0, s>>>(a);
     }
     return cudaGetLastError();
 }

@@ -562,6 +562,7 @@ def _bind():
         L.sdk_interp_vector.argtypes = [
             vp, C.POINTER(Points), C.POINTER(Field), C.POINTER(Field), C.POINTER(KernelDesc), C.POINTER(KernelDesc), C.c_int, vp, vp, vp,
         ]
+        L.sdk_interp_scalar_multi.argtypes = [vp, C.POINTER(Points), C.POINTER(Field), C.c_int32, C.POINTER(KernelDesc), vp, vp]
         L.sdk_build_masks.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp]
         L._interp_bound = True
     return L
@@ -598,6 +599,37 @@ def interp_scalar_device(pts, name, dims, knw, prefetched=None, prefix=None):
     )
     del keep_k, keep_f, keep_p, keep_v
     return out
+
+
+MAX_MULTI_FIELDS = 4
+
+
+def interp_scalars_device(pts, names, dims, knw):
+    """Several scalar variables that share dims, dtype layout and kernel -> list of device tensors, one launch
+    (``sdk_interp_scalar_multi``): indices, wet flags, stencil choice and weights are worked out once per point."""
+    import torch  # noqa: PLC0415
+
+    od = pts.od
+    L = _bind()
+    cuvwg = "G" if ("Xp1" in dims or "Yp1" in dims) else "C"
+    mask = _mask_for(od, dims, knw.ignore_mask)
+    k, keep_k = kernel_desc(od, knw, cuvwg, knw.ignore_mask or mask is None, bottom_no_flux=False)
+    fields = (Field * len(names))()
+    keep_f = []
+    for j, name in enumerate(names):
+        f, keep = _field(od, name, dims, None, None, mask)
+        fields[j] = f
+        keep_f.append(keep)
+    p, keep_p = _points_struct(pts)
+    keep_v = _vertical_time(pts, dims, knw, p)
+    outs = [torch.empty(pts.pos.N, dtype=torch.float64, device=od._torch_device()) for _ in names]
+    out_ptrs = (C.c_void_p * len(names))(*[o.data_ptr() for o in outs])
+    _lib.check(
+        L.sdk_interp_scalar_multi(od.grid_handle(), C.byref(p), fields, len(names), C.byref(k), out_ptrs, _lib.current_stream()),
+        "sdk_interp_scalar_multi",
+    )
+    del keep_k, keep_f, keep_p, keep_v
+    return outs
 
 
 def interp_vector_device(pts, names, dims, knws, vec_transform, prefetched=None, prefix=None):
@@ -732,6 +764,19 @@ def interpolate_device(pos, var_name, knw, vec_transform=True, prefetched=None, 
         else:
             raise ValueError("var_name needs to be string, tuple, or a list of the above.")
     final = {}
+    # scalar variables that share the kernel and the grid position go through one launch, up to four at a time
+    groups = {}
+    for key, kind, names, kernels, pre, prefix in jobs:
+        if kind == "s" and pre is None and prefix is None:
+            gkey = (kernels, tuple(od[names].dims), str(od[names].dtype))
+            if key not in groups.setdefault(gkey, []):
+                groups[gkey].append(key)
+    for (kernels, dims, _), keys in groups.items():
+        for at in range(0, len(keys), MAX_MULTI_FIELDS):
+            chunk = keys[at : at + MAX_MULTI_FIELDS]
+            if len(chunk) > 1:
+                for key, out in zip(chunk, interp_scalars_device(pts, [k[0] for k in chunk], dims, kernels)):
+                    final[key] = out
     for key, kind, names, kernels, pre, prefix in jobs:
         if key in final:
             continue  # same variable and kernel twice: computed once (the reference hashes likewise)

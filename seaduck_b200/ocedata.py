@@ -578,12 +578,14 @@ class OceData:
                 alloc(nme, torch.int32)
             for nme in ("rx", "ry"):
                 alloc(nme, torch.float64)
-            for nme in ("cs", "sn", "dx", "dy", "bx", "by"):
+            rectilinear = self.readiness["h"] == "rectilinear"
+            for nme in ("cs", "sn", "bx", "by") + (() if rectilinear else ("dx", "dy")):
                 alloc(nme, torch.float32)
             alloc("px", torch.float64, 4)
             alloc("py", torch.float64, 4)
-            if self.readiness["h"] == "rectilinear":
+            if rectilinear:
                 # dx, dy = cos(by) * deg2m * spacing are float64 in the reference (utils.py:602): rows 2 of px / py
+                # (no float32 copy is asked for: sdk_located.dx / dy stay NULL)
                 out["dx"], out["dy"] = out["px"][2 * n : 3 * n], out["py"][2 * n : 3 * n]
         if dz is not None:
             if self.readiness["Z"]:

@@ -225,3 +225,50 @@ def test_locate_on_a_sheared_grid_matches_kdtree(shear, oracle_lib):
             f"{int(worse.sum())} of {n} points in a farther cell (shear {shear}); index offsets (dy, dx) of the first: {off.tolist()}, "
             f"distance ratios {np.sqrt(mine[worse] / ref[worse])[:8].round(4).tolist()}"
         )
+
+
+def test_multi_field_launch_equals_single_launches():
+    """Scalars that share a kernel go through one ``sdk_interp_scalar_multi`` launch: bit for bit what one launch per
+    variable gives, for nearest / linear / derivative kernels in z and t, masked and unmasked."""
+    import seaduck_b200 as sd
+
+    case = ci.case_llc3d(n=4000)
+    od = sd.OceData(case["ds"])
+    pos = sd.Position().from_latlon(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od)
+    for spec in ({}, dict(vkernel="linear", tkernel="linear"), dict(vkernel="dz", tkernel="dt"), dict(ignore_mask=True, vkernel="linear"),
+                 dict(hkernel="dx", h_order=1, inheritance=[ci.ALL9, [0, 1, 3, 5, 7]]), dict(kernel="cross5", tkernel="linear")):
+        knw = ci.make_knw(sd.KnW, spec)
+        together = pos.interpolate(["T", "S", "T"], knw)
+        alone = [pos.interpolate("T", knw), pos.interpolate("S", knw)]
+        np.testing.assert_array_equal(together[0], alone[0], err_msg=str(spec))
+        np.testing.assert_array_equal(together[1], alone[1], err_msg=str(spec))
+        np.testing.assert_array_equal(together[2], alone[0], err_msg=str(spec))
+        assert np.isnan(alone[0]).any() or spec.get("ignore_mask")  # the land / bottom rows are part of the comparison
+
+
+def test_interpolate_a_million_points_matches_oracle(oracle_lib):
+    """BASELINE.json configs[2] at test size: T, S (masked 9-point kernel, one multi-field launch) and (u, v) at 10^6
+    scattered points on an LLC90-shaped grid with land, through the cell-sorted copy of the points -- against the numpy
+    oracle on the same points: NaN pattern identical, values to 1e-9."""
+    import seaduck_b200 as sd
+    from oracle import interp_oracle as io
+    from seaduck_b200 import synthetic
+
+    ds = synthetic.llc(n=90, nz=20, land_blobs=True, tracers=True)
+    od = sd.OceData(ds)
+    n = 1_000_000
+    lon, lat, _ = synthetic.llc_seed_particles(None, n, seed=3, lat_range=(-72.0, 88.0))
+    dep = -np.random.default_rng(4).uniform(5.0, 3000.0, n)
+    var = ["T", "S", ("UVELMASS", "VVELMASS")]
+    uknw, vknw = ci.make_knw(sd.KnW, (ci.UKNW, ci.VKNW))
+    kernels = [sd.KnW(), sd.KnW(), (uknw, vknw)]
+    pos = sd.Position().from_latlon(x=lon, y=lat, z=dep, data=od)
+    got = ci.flatten_result(pos.interpolate(list(var), list(kernels)))
+    opos = io.OraclePosition(od, x=lon, y=lat, z=dep)
+    same_cell = (pos.face == opos.face) & (pos.iy == opos.iy) & (pos.ix == opos.ix)
+    assert same_cell.mean() > 1 - 1e-5  # (a query within rounding of a Voronoi edge may go either way)
+    ref = ci.flatten_result(io.InterpOracle(od, opos).interpolate(list(var), list(kernels)))
+    assert len(got) == len(ref) == 4
+    for k, (g, r) in enumerate(zip(got, ref)):
+        ci.assert_values_close(f"variable {k}", g[same_cell], r[same_cell])
+    assert np.isnan(ref[0]).mean() > 0.02  # land is part of the comparison
