@@ -79,6 +79,15 @@ def measure(points=10_000_000, grid=270, levels=50, steps=10, warmup=3, cpu_samp
     def step():
         return interp.interpolate_device(pos, list(var), list(kernels))
 
+    # the first pass also builds the cell-sorted copy of the located points that the kernels run over (one argsort +
+    # one gather per point array, cached with the Position): timed on its own, reported, and part of `e2e`
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    f0.record()
+    out = step()
+    f1.record()
+    torch.cuda.synchronize()
+    first_ms = f0.elapsed_time(f1)
     for _ in range(a.warmup):
         out = step()
     torch.cuda.synchronize()
@@ -106,15 +115,20 @@ def measure(points=10_000_000, grid=270, levels=50, steps=10, warmup=3, cpu_samp
         "metric": "interpolated points/sec", "value": value, "unit": "points/s", "n_gpus": 1, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": f"OceInterp-style sampling of T, S (masked 9-point KnW) and (u, v) (particle kernels) at {n} "
-                        f"{'cell-sorted' if a.sorted else 'scattered'} points, LLC{a.grid}-shaped grid (13x{a.grid}x{a.grid}x{a.levels}), fp64 fields",
+            "workload": f"OceInterp-style sampling of T, S (masked 9-point KnW, one multi-field launch) and (u, v) (particle kernels) at {n} "
+                        f"{'cell-sorted' if a.sorted else 'scattered'} points, LLC{a.grid}-shaped grid (13x{a.grid}x{a.grid}x{a.levels}), fp64 fields; "
+                        f"a step is one pass over the located points",
+            "point_order": "points come in scattered; the product keeps a cell-sorted copy of the located points (built during the first "
+                           f"pass: {first_ms:.1f} ms for that pass against {ms:.2f} ms afterwards) and scatters the results back to the caller's order; "
+                           "the timed steps reuse that copy, `e2e` pays for it every time",
+            "first_pass_ms": first_ms,
             "l2": f"inputs larger than L2 (four fields {field_mb:.0f} MB + {n * 60 / 1e6:.0f} MB of point state); no flush",
             "nan_fraction_T": nan_frac, "dataset_build_s": build_s,
         },
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                     "peak_source": peak_src, "kernel": "interp_scalar_kernel x2 + interp_vector_kernel",
+                     "peak_source": peak_src, "kernel": "interp_scalar_multi_kernel (T, S) + interp_vector_kernel (u, v)",
                      "algorithmic_bytes_per_point": ALGO_BYTES_PER_POINT},
-        "gpu_launches": 3 * a.steps,
+        "gpu_launches": 2 * a.steps,
     }
     if clocks is not None:
         line["clocks"] = clocks

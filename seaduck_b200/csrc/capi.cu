@@ -162,6 +162,7 @@ int sdk_grid_destroy(sdk_grid *g) {
     if (g->has_buckets) {
         cudaFree(g->buckets.table);
         cudaFree((void *)g->buckets.cxyz);
+        cudaFree((void *)g->buckets.wide);
     }
     delete g;
     return SDK_OK;
@@ -289,6 +290,7 @@ int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span
     if (grid->has_buckets) {
         cudaFree(grid->buckets.table);
         cudaFree((void *)grid->buckets.cxyz);
+        cudaFree((void *)grid->buckets.wide);
         grid->has_buckets = false;
     }
     sdk::BucketGrid &b = grid->buckets;
@@ -303,6 +305,7 @@ int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span
     b.inv_dlat = nlat / b.span_lat;
     b.table = nullptr;
     b.cxyz = nullptr;
+    b.wide = nullptr;
     cudaError_t e = sdk::build_buckets(grid->dev, b, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_grid_build_locator");
     grid->has_buckets = true;

@@ -81,16 +81,11 @@ __global__ void bucket_dilate_kernel(BucketGrid b, const int *src, int *dst, int
 // rot in quarter turns when leaving through edge e and arriving through edge ne
 // (reference topology.py:470: rot = pi - DIRECTIONS[e] + DIRECTIONS[ne])
 __device__ __forceinline__ int remap_dir(int dir, int e, int ne) {
-    const int dq[4] = {1, 3, 2, 0};
-    const int q = (2 - dq[e] + dq[ne] + 8) & 3;
-    if (q == 1) {
-        const int r[4] = {2, 3, 1, 0};
-        return r[dir];
-    }
-    if (q == 3) {
-        const int r[4] = {3, 2, 0, 1};
-        return r[dir];
-    }
+    // (the small tables are packed into immediates, two bits per entry: indexed local arrays would live on the stack)
+    const unsigned dq = 0x2Du;  // {1, 3, 2, 0}: quarter turns of the edge directions up, down, left, right
+    const int q = (2 - (int)(dq >> (2 * e) & 3u) + (int)(dq >> (2 * ne) & 3u) + 8) & 3;
+    if (q == 1) return (int)(0x1Eu >> (2 * dir) & 3u);  // {2, 3, 1, 0}
+    if (q == 3) return (int)(0x4Bu >> (2 * dir) & 3u);  // {3, 2, 0, 1}
     return dir;
 }
 
@@ -138,16 +133,22 @@ __global__ void cell_xyz_kernel(GridDev g, double *cxyz) {
 // The cell (dy, dx) index steps away from (f, iy, ix), |dy|, |dx| <= 3: vertical steps first, then horizontal ones,
 // every remaining step re-labelled after a face change (reference ind_moves, topology.py:436).  false = no such cell.
 __device__ __forceinline__ bool cell_at_offset(const GridDev &g, int f, int iy, int ix, int dy, int dx, int &nf, int &ny, int &nx) {
-    int moves[6], m = 0;
-    for (int k = 0; k < abs(dy); ++k) moves[m++] = dy > 0 ? 0 : 1;
-    for (int k = 0; k < abs(dx); ++k) moves[m++] = dx > 0 ? 3 : 2;
+    // the moves live in one word, two bits each (no indexed local array: that would put the whole kernel on the stack)
+    unsigned moves = 0;
+    int m = 0;
+    for (int k = 0; k < abs(dy); ++k) moves |= (dy > 0 ? 0u : 1u) << (2 * m++);
+    for (int k = 0; k < abs(dx); ++k) moves |= (dx > 0 ? 3u : 2u) << (2 * m++);
     nf = f, ny = iy, nx = ix;
     for (int k = 0; k < m; ++k) {
         int came;
-        const int d = moves[k];
+        const int d = (int)(moves >> (2 * k) & 3u);
         if (cell_move(g, d, nf, ny, nx, came)) return false;
-        if (came >= 0)
-            for (int j = k + 1; j < m; ++j) moves[j] = remap_dir(moves[j], d, came);
+        if (came >= 0) {
+            for (int j = k + 1; j < m; ++j) {
+                const unsigned old = moves >> (2 * j) & 3u;
+                moves = (moves & ~(3u << (2 * j))) | ((unsigned)remap_dir((int)old, d, came) << (2 * j));
+            }
+        }
     }
     return true;
 }
@@ -242,6 +243,86 @@ __device__ __forceinline__ void find_rel_1d_f64(const double *arr, int n, double
     b = bx;
 }
 
+// Which cells need the second ring: with a = centre -> right neighbour and b = centre -> upper neighbour, the Voronoi
+// neighbours of a lattice point all lie among the 8 index neighbours when the basis is (nearly) reduced,
+// |a.b| <= min(|a|^2, |b|^2) / 2; real ocean grids are orthogonal (a.b ~ 0), a sheared or kinked patch is flagged cell by
+// cell (threshold 0.35, and any cell with a missing or NaN neighbour).
+__global__ void cell_wide_kernel(GridDev g, const double *cxyz, unsigned char *wide) {
+    const int64_t ncell = (int64_t)g.nface * g.ny * g.nx;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(c / ((int64_t)g.ny * g.nx));
+        const int rem = (int)(c - (int64_t)f * g.ny * g.nx);
+        const int iy = rem / g.nx, ix = rem - iy * g.nx;
+        double v[2][3];
+        bool flag = false;
+        for (int k = 0; k < 2; ++k) {
+            int nf, ny, nx;
+            // right / up neighbour, or left / down where there is none (the sign does not matter)
+            if (!neighbour(g, f, iy, ix, k == 0 ? 3 : 0, -1, nf, ny, nx) && !neighbour(g, f, iy, ix, k == 0 ? 2 : 1, -1, nf, ny, nx)) {
+                flag = true;
+                v[k][0] = v[k][1] = v[k][2] = 0.0;
+                continue;
+            }
+            const int64_t n = ((int64_t)nf * g.ny + ny) * g.nx + nx;
+            for (int j = 0; j < 3; ++j) v[k][j] = cxyz[3 * n + j] - cxyz[3 * c + j];
+        }
+        const double ab = v[0][0] * v[1][0] + v[0][1] * v[1][1] + v[0][2] * v[1][2];
+        const double aa = v[0][0] * v[0][0] + v[0][1] * v[0][1] + v[0][2] * v[0][2];
+        const double bb = v[1][0] * v[1][0] + v[1][1] * v[1][1] + v[1][2] * v[1][2];
+        const double lim = 0.35 * fmin(aa, bb);
+        flag |= !(fabs(ab) <= lim) || !(lim > 0.0);  // (also true for NaN / inf operands)
+        wide[c] = flag ? 1 : 0;
+    }
+}
+
+// Second ring around a cell where the walk over the 8 neighbours has stopped -- on a sheared or strongly stretched grid
+// the Voronoi neighbours of a cell are not all among its 8 index neighbours, and the descent could stop one cell short
+// -- and a third ring where a centre nearby is NaN (land without coordinates: the nearest valid centre may lie beyond
+// the hole).  Returns the closest cell found (d2 >= best: none closer).
+struct Nearest {
+    double d2;
+    int f, iy, ix;
+};
+
+static __device__ __noinline__ Nearest confirm_rings(const GridDev &g, const double *cxyz, int f, int iy, int ix, double qx, double qy,
+                                                     double qz, double best, bool hole) {
+    Nearest r = {best, f, iy, ix};
+#ifndef SDK_LOCATE_INTERIOR
+#define SDK_LOCATE_INTERIOR 1
+#endif
+#ifndef SDK_LOCATE_MAXRING
+#define SDK_LOCATE_MAXRING 3
+#endif
+    const bool inside = SDK_LOCATE_INTERIOR && cxyz && iy >= 2 && iy < g.ny - 2 && ix >= 2 && ix < g.nx - 2;
+    if (inside) {
+        // away from the face edges the second ring is plain index arithmetic on the centre table
+        const int64_t c0 = ((int64_t)f * g.ny + iy) * g.nx + ix;
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+            const int dy = k < 5 ? -2 : (k < 10 ? 2 : (k < 13 ? k - 11 : k - 14));
+            const int dx = k < 5 ? k - 2 : (k < 10 ? k - 7 : (k < 13 ? -2 : 2));
+            const int64_t c = c0 + (int64_t)dy * g.nx + dx;
+            const double ex = __ldg(cxyz + 3 * c) - qx, ey = __ldg(cxyz + 3 * c + 1) - qy, ez = __ldg(cxyz + 3 * c + 2) - qz;
+            const double dd = ex * ex + ey * ey + ez * ez;
+            hole |= !(dd < INFINITY);
+            if (dd < r.d2) r = {dd, f, iy + dy, ix + dx};
+        }
+    }
+    for (int ring = inside ? 3 : 2; ring <= ((hole && SDK_LOCATE_MAXRING >= 3) ? 3 : (SDK_LOCATE_MAXRING >= 2 ? 2 : 0)); ++ring) {
+        for (int dy = -ring; dy <= ring; ++dy) {
+            for (int dx = -ring; dx <= ring; ++dx) {
+                if (abs(dy) != ring && abs(dx) != ring) continue;
+                int nf, ny, nx;
+                if (!cell_at_offset(g, f, iy, ix, dy, dx, nf, ny, nx)) continue;
+                const double dd = dist2_to_cell(g, cxyz, nf, ny, nx, qx, qy, qz);
+                hole |= !(dd < INFINITY);
+                if (dd < r.d2) r = {dd, nf, ny, nx};
+            }
+        }
+    }
+    return r;
+}
+
 __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ LocateArgs a) {
     const GridDev &g = a.g;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -306,27 +387,11 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
                 }
             }
             if (bd >= best) {
-                // second ring; a third one where a centre nearby is NaN (land without coordinates: the nearest valid
-                // centre may then lie beyond the hole)
-                bool hole = near_hole;
-                for (int ring = 2; ring <= (hole ? 3 : 2); ++ring) {
-                    for (int dy = -ring; dy <= ring; ++dy) {
-                        for (int dx = -ring; dx <= ring; ++dx) {
-                            if (abs(dy) != ring && abs(dx) != ring) continue;
-                            int nf, ny, nx;
-                            if (!cell_at_offset(g, f, iy, ix, dy, dx, nf, ny, nx)) continue;
-                            const double dd = dist2_to_cell(g, cxyz, nf, ny, nx, qx, qy, qz);
-                            hole |= !(dd < INFINITY);
-                            if (dd < bd) {
-                                bd = dd;
-                                bf = nf;
-                                by = ny;
-                                bx = nx;
-                            }
-                        }
-                    }
-                }
-                if (bd >= best) break;
+                // the walk has stopped: where the grid is sheared (or has holes) look further out once
+                if (a.b.wide && !near_hole && !__ldg(a.b.wide + ((int64_t)f * g.ny + iy) * g.nx + ix)) break;
+                const Nearest far = confirm_rings(g, cxyz, f, iy, ix, qx, qy, qz, best, near_hole);
+                if (far.d2 >= best) break;
+                bd = far.d2, bf = far.f, by = far.iy, bx = far.ix;
             }
             best = bd;
             f = bf;
@@ -524,12 +589,20 @@ cudaError_t build_buckets(const GridDev &g, BucketGrid &b, cudaStream_t s) {
     if (e == cudaSuccess) {
         // unit vectors of the cell centres (24 bytes per cell); a grid too large for it keeps the sincos path
         double *cxyz = nullptr;
+        unsigned char *wide = nullptr;
+        b.cxyz = nullptr;
+        b.wide = nullptr;
         if (cudaMalloc(&cxyz, sizeof(double) * 3 * (size_t)ncell) == cudaSuccess) {
             cell_xyz_kernel<<<(int)sblocks, threads, 0, s>>>(g, cxyz);
             b.cxyz = cxyz;
+            if (cudaMalloc(&wide, (size_t)ncell) == cudaSuccess) {
+                cell_wide_kernel<<<(int)sblocks, threads, 0, s>>>(g, cxyz, wide);
+                b.wide = wide;
+            } else {
+                cudaGetLastError();
+            }
         } else {
             cudaGetLastError();
-            b.cxyz = nullptr;
         }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);

@@ -15,6 +15,9 @@ struct BucketGrid {
     // unit vector of every cell centre (3 doubles per cell, +inf for a NaN centre), or NULL when the table did not fit:
     // a distance is then three loads and three multiply-adds instead of two sincos
     const double *cxyz;
+    // one byte per cell (with cxyz): 1 where the local grid vectors are sheared / stretched enough (or a neighbour is
+    // missing) that a cell outside the 8 index neighbours can be the nearest one, so the walk has to look at the second ring
+    const unsigned char *wide;
 };
 
 struct LocateArgs {
