@@ -224,10 +224,27 @@ class Ctx:
         self.local = int(os.environ.get("LOCAL_RANK", "0"))
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
+        self.affinity = self._bind_to_gpu_cpus(self.local) if self.world > 1 else "unchanged (one rank)"
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
         self.torch, self.dist = torch, dist
         self.side = torch.cuda.Stream(self.dev)
+
+    @staticmethod
+    def _bind_to_gpu_cpus(index):
+        """Run this rank on the CPUs next to its GPU (NVML's ideal affinity), so that its pinned buffers are first touched
+        -- and therefore allocated -- on the GPU's own NUMA node.  Best effort: a container that does not own those
+        CPUs keeps what it has."""
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            before = sorted(os.sched_getaffinity(0))
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+            after = sorted(os.sched_getaffinity(0))
+            return f"cpus {after[0]}-{after[-1]} ({len(after)}), was {before[0]}-{before[-1]} ({len(before)})"
+        except Exception as exc:  # noqa: BLE001
+            return f"unchanged ({type(exc).__name__})"
 
     def barrier(self):
         if self.world > 1:
@@ -475,7 +492,7 @@ def run_batches(ctx, a, kind="c2", with_e2e=False, with_orders=False):
                       "api": "sdk_track_host (C ABI): pinned host lon/lat/dep/t in seeding order in, one 32-byte record per particle "
                              "(position + cell, caller's order) and 4 counters out; locate + velocity read + advect on the device, the advection "
                              "kernel stores the records into the caller's pinned buffer itself (no pack pass, no D2H copy); 3 chunks pipelined "
-                             "over three streams", "gpu_launches_per_step": 9,
+                             "over three streams", "cpu_affinity_rank0": ctx.affinity, "gpu_launches_per_step": 9,
                       "gpu_launches_note": "3 chunks x (locate, get_u_du, advect)"}
         if with_orders:
             # the same call without the device-side sort, and with host input that already is in cell order
@@ -557,6 +574,7 @@ def run_stops(ctx, a, grid, particles, hours, nt=3):
         return e0.elapsed_time(e1), pt.crossings - c0, len(snaps)
 
     W, K = a.warmup, a.steps
+    pt.reserve_records(W + K + 4)  # the records of every stop of this run, allocated once, outside the timed region
     run(0, W, "owner")
     sampler = ClockSampler(ctx.local)
     sampler.start()

@@ -14,5 +14,6 @@ from .ocedata import OceData  # noqa: E402
 from .eulerian import Position  # noqa: E402
 from .lagrangian import Particle  # noqa: E402
 from .oceinterp import OceInterp  # noqa: E402
+from . import get_masks  # noqa: E402,F401
 
 __all__ = ["__version__", "Position", "KnW", "Particle", "OceData", "OceInterp", "rcParam", "Topology"]

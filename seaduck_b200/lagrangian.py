@@ -786,6 +786,26 @@ class Particle(Position):
         p.__dict__["_derived_ok"] = False
         return p
 
+    def reserve_records(self, n_stops):
+        """Set aside HBM for the 32-byte records of ``n_stops`` future stops in one allocation (``cudaMalloc`` of a
+        block per ``to_list_of_time`` call is slow, and serialised across the processes of a node); the calls that
+        follow take their blocks from it in order."""
+        import torch  # noqa: PLC0415
+
+        arena = torch.empty((int(n_stops), self.N, 32), dtype=torch.uint8, device=self.ocedata._torch_device())
+        self.__dict__["_record_arena"] = [arena, 0]
+
+    def _record_blocks(self, n_keep):
+        """``n_keep`` blocks [N, 32] for record snapshots: from the reserved arena while it lasts, else a fresh one."""
+        import torch  # noqa: PLC0415
+
+        arena = self.__dict__.get("_record_arena")
+        if arena is not None and arena[1] + n_keep <= arena[0].shape[0]:
+            blocks = arena[0][arena[1] : arena[1] + n_keep]
+            arena[1] += n_keep
+            return blocks
+        return torch.empty((max(n_keep, 1), self.N, 32), dtype=torch.uint8, device=self.ocedata._torch_device())
+
     def record_snapshot(self, t_stop, out=None):
         """Position and cell of every particle, now, as a :class:`RecordSnapshot` (one ``sdk_pack_records`` launch);
         ``out``: uint8 device tensor [N, 32] to pack into."""
@@ -844,10 +864,8 @@ class Particle(Position):
         if snapshots == "records" and _on_stop is None:
             # one allocation for the records of every stop that is kept (a fresh 32 N-byte block per stop would go to
             # the driver every time: cudaMalloc is slow and serialised across the processes of a node)
-            import torch  # noqa: PLC0415
-
             n_keep = sum(1 for i in range(len(stops)) if return_in_between or not (update[i] or i == 0))
-            ring = torch.empty((max(n_keep, 1), self.N, 32), dtype=torch.uint8, device=od._torch_device())
+            ring = self._record_blocks(n_keep)
 
         def keep(t_stop):
             if _on_stop is not None:

@@ -480,3 +480,32 @@ def test_full_size_round_trip_and_idempotence():
 
 def to180(x):
     return (x + 180.0) % 360.0 - 180.0
+
+
+def test_stuck_particle_callbacks():
+    """get_masks.which_not_stuck / abandon_stuck (reference get_masks.py:219,231): the mask of the cell a particle sits
+    in, as a ``callback`` that takes grounded particles out of the integration."""
+    sd = _sd()
+    from seaduck_b200 import get_masks
+
+    import cases_interp as ci
+
+    case = ci.case_llc3d(n=600)
+    ds = case["ds"]
+    od = sd.OceData(ds)
+    kw = dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True)
+    t0 = np.zeros(len(case["x"]))
+    pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=t0, data=od, callback=get_masks.which_not_stuck, **kw)
+    wet = get_masks.which_not_stuck(pt)
+    maskc = np.asarray(ds["maskC"])
+    np.testing.assert_array_equal(wet, maskc[pt.izl_lin - 1, pt.face, pt.iy, pt.ix] != 0)
+    assert 0 < wet.sum() < pt.N  # both kinds are present
+    start = pt.lon.copy()
+    pt.to_next_stop(5 * cases.DAY)
+    moved = pt.lon != start
+    assert not moved[~wet].any() and moved[wet].mean() > 0.5  # grounded particles stay where they are
+    sub = pt.subset(np.arange(pt.N))
+    get_masks.abandon_stuck(sub)
+    assert sub.N == int(get_masks.which_not_stuck(pt).sum()) == len(sub.lon) == len(sub.ix)
+    mc, mu, mv, mw = get_masks.get_mask_arrays(od)
+    assert mc.shape == maskc.shape and ((mu != 0) >= (mc != 0)[..., : mu.shape[-1]]).all() and mw.shape[0] == mc.shape[0]
