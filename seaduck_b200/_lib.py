@@ -246,6 +246,14 @@ def lib():
         L.sdk_exchange_wait.argtypes = [C.POINTER(Exchange), C.c_uint64, C.c_int, C.c_int, vp]
         L.sdk_selftest_math.argtypes = [C.c_int, C.c_int64, vp, vp, vp, vp, vp]
         L.sdk_selftest_cell_move.argtypes = [vp, C.c_int64, vp, vp, vp]
+        # (interp.py narrows the structure pointers of these; typed here so that no caller can reach them untyped:
+        # ctypes would pass 64-bit pointers as 32-bit ints)
+        L.sdk_build_masks.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp]
+        L.sdk_struct_size.argtypes = [C.c_int]
+        L.sdk_struct_size.restype = C.c_int64
+        L.sdk_interp_scalar.argtypes = [vp] * 6
+        L.sdk_interp_scalar_multi.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp]
+        L.sdk_interp_vector.argtypes = [vp] * 6 + [C.c_int, vp, vp, vp]
         _lib = L
     return _lib
 

@@ -312,7 +312,7 @@ def _device_masks(od):
     if need:
         tu, tv, tw = (torch.empty_like(tc) for _ in range(3))
         _lib.check(
-            _lib.lib().sdk_build_masks(od.grid_handle(), tc.data_ptr(), nz, tu.data_ptr(), tv.data_ptr(), tw.data_ptr(), _lib.current_stream()),
+            _bind().sdk_build_masks(od.grid_handle(), tc.data_ptr(), nz, tu.data_ptr(), tv.data_ptr(), tw.data_ptr(), _lib.current_stream()),
             "sdk_build_masks",
         )
         small.update({"U": tu, "V": tv, "Wvel": tw})

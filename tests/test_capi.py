@@ -63,3 +63,11 @@ def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "SO_PATH", "/nonexistent/libseaduck_b200.so")
     with pytest.raises(_lib.SdkError):
         _lib.lib()
+
+
+def test_every_entry_point_is_typed():
+    """ctypes passes untyped integer arguments as 32-bit ints: a 64-bit device pointer would be cut in half.  Every
+    function the header declares must therefore have its argument types set by ``_lib.lib()`` itself."""
+    L = _lib.lib()
+    untyped = [n for n in declared_functions() if getattr(L, n).argtypes is None and n not in ("sdk_abi_version", "sdk_last_error", "sdk_sm_count")]
+    assert not untyped, untyped

@@ -508,4 +508,6 @@ def test_stuck_particle_callbacks():
     get_masks.abandon_stuck(sub)
     assert sub.N == int(get_masks.which_not_stuck(pt).sum()) == len(sub.lon) == len(sub.ix)
     mc, mu, mv, mw = get_masks.get_mask_arrays(od)
-    assert mc.shape == maskc.shape and ((mu != 0) >= (mc != 0)[..., : mu.shape[-1]]).all() and mw.shape[0] == mc.shape[0]
+    assert mc.shape == maskc.shape and mu.ndim == mv.ndim == mw.ndim == 4
+    common = tuple(slice(0, min(a, b)) for a, b in zip(mc.shape, mu.shape))
+    assert ((mu[common] != 0) | (mc[common] == 0)).all()  # the west wall of a wet cell is wet
