@@ -262,6 +262,23 @@ class Ctx:
         return mx.tolist(), sm.tolist()
 
 
+def nvlink_bytes(index):
+    """(tx, rx) data bytes this GPU has moved over all its NVLinks so far (NVML throughput counters, KiB), or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        every_link = 0xFFFFFFFF
+        vals = pynvml.nvmlDeviceGetFieldValues(h, [(pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX, every_link),
+                                                   (pynvml.NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX, every_link)])
+        if any(v.nvmlReturn != 0 for v in vals):
+            return None
+        return tuple(int(v.value.ullVal) * 1024 for v in vals)
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def roofline_of(kernel, kms, crossings, n, dtype, three_d, traffic=None, traffic_source=None):
     """Roofline of the advection kernel from a live CUDA-event timing: algorithmic bytes per SURVEY.md §8d."""
     peak, peak_src = hbm_peak()
@@ -328,8 +345,17 @@ def run_batches(ctx, a, kind="c2", with_e2e=False, with_orders=False):
     if world > 1 and not a.no_gather:
         exchange = parallel.RecordExchange(n, dev, slots=int(os.environ.get("SDK_BENCH_SLOTS", "2")), multicast=not a.no_multicast)
     if exchange is not None and fused and not a.save_raw:
+        # the advection kernel stores the output records into every rank's buffer itself, in the cell order of its state
+        # (contiguous stores); the permutation that says which record is which particle is exchanged once per batch,
+        # at set-up time, like ShardedParticle does at construction
+        order = os.environ.get("SDK_BENCH_SHIP_ORDER", "state")
+        perms = []
         for pt in batches:
-            pt.ship_to(exchange)  # the advection kernel stores the output records into every rank's buffer itself
+            pt.ship_to(exchange, order=order)
+            if order == "state" and pt._perm is not None:
+                everyone = torch.empty((world, n), dtype=torch.int32, device=dev)
+                ctx.dist.all_gather_into_tensor(everyone, pt._perm)
+                perms.append(everyone)
 
     def restore(group, b):
         for k, v in group[1][b].items():
@@ -382,8 +408,21 @@ def run_batches(ctx, a, kind="c2", with_e2e=False, with_orders=False):
     sampler = ClockSampler(ctx.local)
     sampler.start()
     elapsed_ms, crossings, step_ms, wall = timed((batches, saved))
+    nvlink = {}
     if exchange is not None:
         exchange.check()
+        # NVLink data bytes of this GPU per step: NVML throughput counters around a few more (untimed) steps -- reading
+        # them next to the timed region stalls a step by ~10 ms
+        link0 = nvlink_bytes(ctx.local)
+        extra = 5
+        for i in range(extra):
+            step((batches, saved), a.warmup + a.steps + i)
+        torch.cuda.current_stream().wait_stream(ctx.side)
+        torch.cuda.synchronize()
+        ctx.barrier()
+        link1 = nvlink_bytes(ctx.local)
+        if link0 is not None and link1 is not None:
+            nvlink = {"tx_bytes_per_step": (link1[0] - link0[0]) / extra, "rx_bytes_per_step": (link1[1] - link0[1]) / extra}
 
     # ---- the dominant kernel alone: CUDA events right around the C-ABI launch, fresh state each time
     kern_ms, kern_cross = [], []
@@ -416,9 +455,12 @@ def run_batches(ctx, a, kind="c2", with_e2e=False, with_orders=False):
         "batches": f"{nb} distinct batches resident in HBM" + (", reused cyclically with a device-side state restore inside the timed region" if reuse else ", one per step"),
         "particle_order": "seeding order in; kept in cell order on the device by the product (Particle(sort=...), sdk_cell_sort)" if sorted_by_product else "seeding order (no sort)",
         "collective": ((f"fused into the advection kernel (sdk_advect_params.ship): the write-back of every finished particle also stores its 32-byte record into "
-                        f"every rank's receive buffer ({exchange.mode})" if (fused and not a.save_raw) else
+                        f"every rank's receive buffer ({exchange.mode}), in the cell order of the sender's state (its permutation was "
+                        f"exchanged once, at set-up)" if (fused and not a.save_raw) else
                         f"sdk_pack_ship per step on a side stream ({exchange.mode})")
                        + f"; one-warp arrival wait + slot release per step on a side stream; {32 * n * world} B received per rank and step") if exchange is not None else "none",
+        "nvlink": dict(nvlink, source="NVML NVLINK_THROUGHPUT_DATA_TX / RX of rank 0's GPU, all links, around 5 untimed steps after the timed region",
+                       expected_rx_bytes_per_step=32 * n * (world - 1)) if nvlink else None,
         # this package's kernels inside the timed region, per rank and step: advect_kernel (two passes with the crossing
         # log: count, then fill) + finish_stop_kernel in lazy mode + exchange_wait_kernel at N > 1 (+ pack_ship_kernel when not fused)
         "gpu_launches": a.steps * world * ((2 if a.save_raw else 1) + (0 if (a.eager or a.save_raw) else 1)
@@ -688,7 +730,8 @@ def run_cuda(a):
                 "workload": workload_name(a), "transport": True, "particles_per_gpu_per_step": a.particles, "days_per_step": a.days,
                 "crossings_per_step": main["crossings_per_step"], "particle_order": main["particle_order"], "batches": main["batches"],
                 "l2": "inputs larger than L2 (fields 168 MB + 220 MB of particle state per batch, a different batch every step); no flush",
-                "collective": main["collective"], "step_ms_first10": main["step_ms_first10"], "host_wall_s": main["host_wall_s"],
+                "collective": main["collective"], "nvlink": main.get("nvlink"), "step_ms_first10": main["step_ms_first10"],
+                "host_wall_s": main["host_wall_s"],
             },
             "roofline": main["roofline"], "gpu_launches": main["gpu_launches"], "clocks": main["clocks"],
         }

@@ -592,14 +592,18 @@ class Particle(Position):
         par.stats = self._stats.data_ptr()
         return par
 
-    def ship_to(self, exchange):
+    def ship_to(self, exchange, order="caller"):
         """Multi-GPU runs (``parallel.RecordExchange``): the advection kernel of every leg whose end is an output stop
         also stores the particles' 32-byte output records into every rank's receive buffer (``sdk_advect_params.ship``).
         The caller waits for and releases each shipped step (``exchange.wait(step, release=True)``;
-        ``last_ship_step`` says which).  ``None`` switches it off."""
+        ``last_ship_step`` says which).  ``order="caller"``: record i of the block is particle i as the caller numbered
+        them; ``order="state"``: the records go out in the order of the device state (cell order when the particles are
+        sorted -- contiguous stores; the receiver needs this rank's permutation, see ``parallel.ShardedParticle``).
+        ``None`` switches it off."""
         if exchange is not None and (self.save_raw or self.callback is not None):
             raise ValueError("the fused output exchange does not go with save_raw or a callback")
         self.__dict__["_exchange"] = exchange
+        self.__dict__["_ship_order"] = order
         self.__dict__["_ship_leg"] = exchange is not None
         self.__dict__["last_ship_step"] = None
 
@@ -622,7 +626,8 @@ class Particle(Position):
             ex = self.__dict__.get("_exchange")
             if ex is not None and self.__dict__.get("_ship_leg", False):
                 par.ship = C.addressof(ex.x)
-                par.ship_index = None if self._perm is None else self._perm.data_ptr()
+                scatter = self._perm is not None and self.__dict__.get("_ship_order", "caller") == "caller"
+                par.ship_index = self._perm.data_ptr() if scatter else None
                 par.ship_step = ex.next_step()
                 self.__dict__["last_ship_step"] = par.ship_step
             _lib.check(L.sdk_advect(handle, C.byref(self._vel), C.byref(p), t_stop, C.byref(par), None, 1, stream), "sdk_advect")

@@ -85,14 +85,17 @@ def unpack_records(rec):
     return out
 
 
-def unshard(blocks, n, world, seed=0):
+def unshard(blocks, n, world, seed=0, orders=None):
     """Undo :func:`shard_indices`: ``blocks`` = per-rank record arrays ([world, n_pad] or a list) -> dict of arrays
-    of length ``n`` in the user's particle order."""
+    of length ``n`` in the user's particle order.  ``orders[r]`` (optional): record k of rank r's block belongs to
+    particle ``orders[r][k]`` of that rank's slice (a rank that ships its records in the cell order of its device state)."""
     perm = permutation(n, seed)
     per = -(-n // world)
     out = {name: np.empty(n, np.float64 if name in ("lon", "lat", "dep") else np.int64) for name in SNAPSHOT_FIELDS}
     for r in range(world):
         idx = perm[r * per : min((r + 1) * per, n)]
+        if orders is not None and orders[r] is not None:
+            idx = idx[np.asarray(orders[r])[: len(idx)]]
         block = unpack_records(blocks[r])
         for name in SNAPSHOT_FIELDS:
             out[name][idx] = block[name][: len(idx)]
@@ -202,7 +205,7 @@ class ShardedSnapshot:
 
         o = self.owner
         if self.everyone or o.world == 1:
-            return unshard(self.blocks.cpu().numpy(), o.n_total, o.world, o.seed)
+            return unshard(self.blocks.cpu().numpy(), o.n_total, o.world, o.seed, orders=o.orders if self.everyone else None)
         mine = self.blocks[0].contiguous()
         parts = [torch.empty_like(mine) for _ in range(o.world)] if o.rank == dst else None
         dist.gather(mine, parts, dst=dst, group=o.group)
@@ -239,9 +242,29 @@ class ShardedParticle:
         self.local.lazy = True
         check_grid_fits_record(data.tp, len(data.Zl) if data.readiness["Zl"] else 0)
         self.exchange = None
+        self.orders = None
         if self.world > 1 and gather == "all":
             self.exchange = RecordExchange(self.n_pad, data._torch_device(), group=group, slots=slots)
-            self.local.ship_to(self.exchange)  # the advection kernel ships the records itself
+            # The advection kernel ships the records itself, in the (cell) order of its device state: stores of lanes
+            # that finish together are neighbours in the receive buffer.  Which particle a record belongs to is told
+            # once, here: every rank's permutation goes to every rank.
+            self.local.ship_to(self.exchange, order="state")
+            self.orders = self._exchange_orders(group)
+
+    def _exchange_orders(self, group):
+        """numpy permutations of all ranks (None for a rank whose state is in slice order)."""
+        import torch
+        import torch.distributed as dist
+
+        pt = self.local
+        dev = pt.ocedata._torch_device()
+        mine = torch.full((self.n_pad,), -1, dtype=torch.int32, device=dev)
+        if pt._perm is not None:
+            mine[: pt.N] = pt._perm
+        everyone = torch.empty((self.world, self.n_pad), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        host = everyone.cpu().numpy()
+        return [None if row[0] < 0 else row for row in host]
 
     def to_list_of_time(self, normal_stops, update_stops="default", return_in_between=True):
         import torch

@@ -88,3 +88,22 @@ def test_grids_that_do_not_fit_the_record_are_refused():
     parallel.check_grid_fits_record(Topology.from_shape((8640, 17280)))
     with pytest.raises(ValueError):
         parallel.check_grid_fits_record(Topology.from_shape((10, 10)), n_zl=5000)
+
+
+def test_unshard_with_sender_orders():
+    """A rank may ship its records in the (cell) order of its device state; its permutation undoes that."""
+    n, world, seed = 103, 3, 9
+    rng = np.random.default_rng(0)
+    truth = {"lon": rng.uniform(-180, 180, n), "lat": rng.uniform(-90, 90, n), "dep": -rng.uniform(0, 5000, n),
+             "face": rng.integers(0, 13, n), "iy": rng.integers(0, 90, n), "ix": rng.integers(0, 90, n), "izl": rng.integers(0, 50, n)}
+    per = -(-n // world)
+    blocks, orders = [], []
+    for r in range(world):
+        idx = parallel.shard_indices(n, world, r, seed)
+        order = rng.permutation(len(idx)) if r != 1 else None  # rank 1 ships in slice order
+        sel = idx if order is None else idx[order]
+        blocks.append(parallel.pack_records_host({k: v[sel] for k, v in truth.items()}, n_pad=per))
+        orders.append(order)
+    out = parallel.unshard(blocks, n, world, seed, orders=orders)
+    for k, v in truth.items():
+        np.testing.assert_array_equal(out[k], v, err_msg=k)
