@@ -923,11 +923,18 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
         if ((e = cudaEventRecord(grid->pipe_ev[3], stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");
         for (auto &st : grid->pipe)
             if ((e = cudaStreamWaitEvent(st, grid->pipe_ev[3], 0)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: wait");
-        const int64_t per = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
+        // Chunk sizes grow 1 : 2 : 3 ...: the upload of the first chunk is the only one nothing overlaps, so it is the
+        // smallest (SDK_TRACK_RAMP=0: equal chunks).
+        const char *ramp_env = std::getenv("SDK_TRACK_RAMP");
+        const bool ramp = !(ramp_env && ramp_env[0] == '0');
+        const int64_t weight_sum = ramp ? (int64_t)nchunks * (nchunks + 1) / 2 : nchunks;
+        int64_t off = 0;
         for (int c = 0; c < nchunks; ++c) {
-            const int64_t off = (int64_t)c * per;
-            const int64_t cnt = off + per <= n ? per : n - off;
-            if (cnt <= 0) break;
+            const int64_t upto = ramp ? (int64_t)(c + 1) * (c + 2) / 2 : c + 1;
+            int64_t end = c == nchunks - 1 ? n : (n * upto / weight_sum + 31) / 32 * 32;
+            if (end > n) end = n;
+            const int64_t cnt = end - off;
+            if (cnt <= 0) continue;
             sdk_track_io sub = *io;
             sub.n = cnt;
 #define SHIFT(member) \
@@ -939,6 +946,7 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
                                  signals + (size_t)c * kTrackSignalBytes, grid->pipe[c % 3]);
             if (rc) return rc;
             cur += track_chunk_bytes(cnt);
+            off = end;
         }
         for (int k = 0; k < 3; ++k) {
             if ((e = cudaEventRecord(grid->pipe_ev[k], grid->pipe[k])) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");

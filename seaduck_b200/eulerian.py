@@ -77,34 +77,14 @@ class Position:
 
     def from_latlon(self, x=None, y=None, z=None, t=None, data=None):
         """Fill in the coordinate info from lat-lon-dep-time (reference ``eulerian.py:138``)."""
-        if data is None:
-            try:
-                self.ocedata
-            except AttributeError as exc:
-                raise ValueError("data not provided") from exc
-        else:
-            if isinstance(data, OceData):
-                self.ocedata = data
-            else:
+        if data is not None:
+            if not isinstance(data, OceData):
                 raise ValueError("Input data must be OceData")
+            self.ocedata = data
+        elif "ocedata" not in self.__dict__:
+            raise ValueError("data not provided")
         self.tp = self.ocedata.tp
-        length = [_general_len(i) for i in [x, y, z, t]]
-        self.N = max(length)
-        if any(i != self.N for i in length if i > 1):
-            raise ValueError("Shapes of input coordinates are not compatible")
-        if isinstance(x, (int, float, np.floating)):
-            x = np.ones(self.N, float) * x
-        if isinstance(y, (int, float, np.floating)):
-            y = np.ones(self.N, float) * y
-        if isinstance(z, (int, float, np.floating)):
-            z = np.ones(self.N, float) * z
-        if isinstance(t, (int, float, np.floating)):
-            t = np.ones(self.N, float) * t
-        for thing in [x, y, z, t]:
-            if thing is None:
-                continue
-            if len(np.shape(thing)) > 1:
-                raise ValueError("Input need to be 1D numpy arrays")
+        x, y, z, t = self._coordinate_arrays(x, y, z, t)
         od = self.ocedata
         # one fused device pass for all four coordinates
         loc = od.locate(
@@ -165,6 +145,22 @@ class Position:
             self.rel.update(TRel._make(None for i in range(4)))
             self.t = None
         return self
+
+    def _coordinate_arrays(self, *coords):
+        """The four coordinate arguments as 1-D arrays of one common length ``self.N`` (scalars are repeated; ``None``
+        stays ``None``), with the reference's complaints about shapes (``eulerian.py:160-181``)."""
+        sizes = [_general_len(c) for c in coords]
+        self.N = max(sizes)
+        if any(size > 1 and size != self.N for size in sizes):
+            raise ValueError("Shapes of input coordinates are not compatible")
+        out = []
+        for c in coords:
+            if isinstance(c, (int, float, np.floating)):
+                c = np.full(self.N, float(c))
+            if c is not None and np.ndim(c) > 1:
+                raise ValueError("Input need to be 1D numpy arrays")
+            out.append(c)
+        return out
 
     def from_bool_array(self, t=None, data=None, bool_array=None, num=None, random_seed=None):
         """Random points in the grid boxes where ``bool_array`` is true, in numbers proportional to the
@@ -277,24 +273,26 @@ class Position:
         return p
 
     def update_from_subset(self, sub, which):
-        """Write a subset back (reference ``eulerian.py:353``)."""
+        """Write a subset back (reference ``eulerian.py:353``): per-particle arrays and rel-coordinates of ``sub`` go into
+        rows ``which`` of this object; an attribute this object does not know yet is adopted as it is (with a warning)."""
         for key, item in vars(sub).items():
             if key.startswith("_"):
                 continue
             if not hasattr(self, key):
                 logging.warning(f"A new attribute {key} defined after updating from subset")
                 setattr(self, key, item)
-            if getattr(self, key) is None:
+            mine = getattr(self, key)
+            if mine is None:
                 continue
-            if isinstance(item, np.ndarray):
-                if len(item.shape) == 1:
-                    getattr(self, key)[which] = item
-                elif key in ["px", "py"]:
-                    getattr(self, key)[:, which] = item
-            elif isinstance(item, RelCoord):
+            if isinstance(item, RelCoord):
                 self.rel.update_from_subset(item, which)
             elif isinstance(item, list):
                 setattr(self, key, item)
+            elif isinstance(item, np.ndarray):
+                if item.ndim == 1:
+                    mine[which] = item
+                elif key in ("px", "py"):
+                    mine[:, which] = item
 
     # ---- neighbour index sets on the host (the device kernels do this per point internally) -----------
     def _fatten_h(self, knw, ind_moves_kwarg={}):

@@ -254,6 +254,9 @@ class Particle(Position):
         self.__dict__["_stale"] = set()
         self.__dict__["_raw"] = []
         self.__dict__["_local_h"] = od.readiness["h"] != "oceanparcel"
+        from .parallel import check_grid_fits_record  # noqa: PLC0415
+
+        check_grid_fits_record(od.tp, len(od.Zl) if od.readiness["Zl"] else 0)  # (the 32-byte output record's cell word)
         # host mirrors of what the constructor of the reference sets as float32 zeros
         for name in ("u", "v", "w", "du", "dv", "dw", "vol") + (() if self._local_h else ("px", "py")):
             self._stale.add(name)

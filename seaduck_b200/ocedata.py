@@ -116,28 +116,23 @@ class RelCoord(dict):
 
     @classmethod
     def create_class(cls, class_name, fields):
-        class NewClass(cls):
-            __slots__ = ()
-            _fields = fields
+        """A named family of rel-coordinates (reference ``ocedata.py:95``): a ``RelCoord`` whose positional arguments
+        fill ``fields`` in order, with ``_make`` / ``_fields`` like a namedtuple."""
+        fields = tuple(fields)
 
-            def __init__(self, *args):
-                if len(args) > len(fields):
-                    raise TypeError(
-                        f"{class_name} takes {len(fields)} positional arguments but {len(args)} were given"
-                    )
-                for name, value in zip(fields, args):
-                    setattr(self, name, value)
+        def fill(self, *values):
+            if len(values) > len(fields):
+                raise TypeError(f"{class_name} takes {len(fields)} positional arguments but {len(values)} were given")
+            self.update(zip(fields, values))
 
-            @classmethod
-            def _make(cls, iterable):
-                return cls(*iterable)
-
-            def __repr__(self):
-                vals = ", ".join(f"{name}={getattr(self, name)!r}" for name in self._fields)
-                return f"{class_name}({vals})"
-
-        NewClass.__name__ = class_name
-        return NewClass
+        family = type(class_name, (cls,), {
+            "__slots__": (),
+            "_fields": fields,
+            "__init__": fill,
+            "_make": classmethod(lambda kind, values: kind(*values)),
+            "__repr__": lambda self: class_name + "(" + ", ".join(f"{k}={self[k]!r}" for k in fields if k in self) + ")",
+        })
+        return family
 
 
 HRel = RelCoord.create_class("HRel", ["face", "iy", "ix", "rx", "ry", "cs", "sn", "dx", "dy", "bx", "by"])
@@ -167,85 +162,77 @@ class OceData:
     (default: current).
     """
 
+    # canonical order of the dimensions every array of the dataset is brought into (reference ocedata.py:165-179)
+    _DIM_ORDER = ("time", "time_midp", "time_outer", "Z", "Zl", "Zp1", "face", "Y", "Yp1", "X", "Xp1")
+    # what each horizontal scheme needs to be in the dataset, in order of preference (reference ocedata.py:231)
+    _SCHEMES = (
+        ("oceanparcel", ("XC", "YC", "XG", "YG")),
+        ("local_cartesian", ("XC", "YC", "dxG", "dyG", "CS", "SN")),
+        ("rectilinear", ("lon", "lat")),
+    )
+
     def __init__(self, data, alias=None, memory_limit=1e7, device=None):
         self._xr = _xr_module(data)
-        self._ds = data.transpose(
-            "time", "time_midp", "time_outer", "Z", "Zl", "Zp1", "face", "Y", "Yp1", "X", "Xp1",
-            ..., missing_dims="ignore",
-        )
+        self._ds = data.transpose(*self._DIM_ORDER, ..., missing_dims="ignore")
         self.tp = Topology(self._ds)
+        if alias == "auto":
+            raise NotImplementedError("auto alias not yet implemented")
         if alias is None:
             self.alias = NO_ALIAS
-        elif alias == "auto":
-            raise NotImplementedError("auto alias not yet implemented")
         elif isinstance(alias, dict):
             self.alias = alias
-        try:
-            self.too_large = self._ds["XC"].nbytes > memory_limit
-        except KeyError:
-            self.too_large = False
+        self.too_large = "XC" in self._ds.variables and self._ds["XC"].nbytes > memory_limit
         self.device = device
         self._dev = {}  # name -> torch tensor on the GPU
         self._field_cache = {}
         self._interp_cache = {}  # rim tables and masks of the interpolation kernel
         self._grid_handle = None
         self._device_vars = {}  # name -> DeviceVar (fields staged on the GPU without a host copy)
-        readiness = self.check_readiness()
-        self.readiness = readiness
-        if readiness:
-            self._grid2array()
-
+        self.readiness = self.check_readiness()
+        self._grid2array()
         if self.readiness["Zl"]:
-            # zero bottom level on every Zl variable (reference ocedata.py:197-210)
-            xr = self._xr
-            with_zl = [i for i in self._ds.data_vars if "Zl" in self._ds[i].dims]
-            if len(with_zl) > 0:
-                without_zl = [i for i in self._ds.data_vars if i not in with_zl]
-                bottom_buffer = xr.zeros_like(self._ds[with_zl].isel(Zl=slice(1)))
-                bottom_buffer["Zl"] = [self.Zl[-1]]
-                neods = xr.merge(
-                    [
-                        xr.concat([self._ds[with_zl], bottom_buffer], dim="Zl"),
-                        self._ds[without_zl],
-                    ]
-                )
-                self._ds = neods
+            self._append_zero_bottom_level()
+
+    def _append_zero_bottom_level(self):
+        """Every variable on ``Zl`` gets one more level of zeros below the deepest one, at ``Zl[-1]`` of the extended
+        axis (reference ``ocedata.py:197-210``): the vertical velocity at the sea floor, which the particle kernels read
+        as the lower wall of the deepest cell."""
+        xr, ds = self._xr, self._ds
+        on_zl = [name for name in ds.data_vars if "Zl" in ds[name].dims]
+        if not on_zl:
+            return
+        elsewhere = [name for name in ds.data_vars if name not in on_zl]
+        floor = xr.zeros_like(ds[on_zl].isel(Zl=slice(1)))
+        floor["Zl"] = [self.Zl[-1]]
+        self._ds = xr.merge([xr.concat([ds[on_zl], floor], dim="Zl"), ds[elsewhere]])
 
     # ---- mapping surface (reference ocedata.py:212-229) ---------------------------------------
+    def _dataset_name(self, key):
+        return self.alias.get(key, key)
+
     def __setitem__(self, key, item):
+        # labelled arrays go into the dataset (under the aliased name), anything else becomes an attribute
         if isinstance(item, self._xr.DataArray):
-            if key in self.alias.keys():
-                self._ds[self.alias[key]] = item
-            else:
-                self._ds[key] = item
+            self._ds[self._dataset_name(key)] = item
         else:
             object.__setattr__(self, key, item)
 
     def __getitem__(self, key):
-        varsdict = vars(self)
-        if key in varsdict.keys():
-            return object.__getattribute__(self, key)
-        if key in varsdict.get("_device_vars", ()):
-            return self._device_vars[key]
-        if key in self.alias.keys():
-            return self._ds[self.alias[key]]
-        return self._ds[key]
+        # attributes (the float32 grid arrays, Vol ...) shadow staged device fields, which shadow the dataset
+        own = vars(self)
+        if key in own:
+            return own[key]
+        staged = own.get("_device_vars", {})
+        if key in staged:
+            return staged[key]
+        return self._ds[self._dataset_name(key)]
 
     def check_readiness(self):
-        """Which interpolation schemes the dataset supports (reference ``ocedata.py:231``)."""
-        varnames = list(self._ds.variables)
-        readiness = {}
-        if all(i in varnames for i in ["XC", "YC", "XG", "YG"]):
-            readiness["h"] = "oceanparcel"
-        elif all(i in varnames for i in ["XC", "YC", "dxG", "dyG", "CS", "SN"]):
-            readiness["h"] = "local_cartesian"
-        elif all(i in varnames for i in ["lon", "lat"]):
-            ratio = 6371e3 * np.pi / 180
-            self.dlon = np.gradient(self["lon"]) * ratio
-            self.dlat = np.gradient(self["lat"]) * ratio
-            readiness["h"] = "rectilinear"
-        else:
-            readiness["h"] = False
+        """Which interpolation schemes the dataset supports (reference ``ocedata.py:231``): ``h`` names the horizontal
+        scheme, ``Z`` / ``Zl`` / ``time`` say whether that axis exists with more than one entry."""
+        present = set(self._ds.variables)
+        scheme = next((name for name, needs in self._SCHEMES if present.issuperset(needs)), None)
+        if scheme is None:
             raise ValueError(
                 """
                 Need a full set of the following to create the object:
@@ -255,8 +242,13 @@ class OceData:
                 See add_missing variable or set_alias.
                 """
             )
-        for _ in ["time", "Z", "Zl"]:
-            readiness[_] = (_ in varnames) and (_general_len(self[_]) > 1)
+        if scheme == "rectilinear":
+            metres_per_degree = 6371e3 * np.pi / 180
+            self.dlon = np.gradient(self["lon"]) * metres_per_degree
+            self.dlat = np.gradient(self["lat"]) * metres_per_degree
+        readiness = {"h": scheme}
+        for axis in ("time", "Z", "Zl"):
+            readiness[axis] = axis in present and _general_len(self[axis]) > 1
         return readiness
 
     def _add_missing_vol(self, as_numpy=False):

@@ -99,6 +99,54 @@ def test_cuda_matches_oracle_llc90(oracle_lib):
     assert total > 2e5
 
 
+@pytest.mark.parametrize("scheme", ["rectilinear", "local_cartesian"])
+def test_cuda_matches_oracle_on_the_schemes_without_corners(scheme, oracle_lib):
+    """The rectilinear (1-D lon / lat, BASELINE.json configs[0]'s grid kind, 10^4 particles as there) and local_cartesian
+    (LLC without XG / YG) horizontal schemes at a size the goldens do not reach: CUDA against the C oracle, full crossing
+    log, indices bit for bit (reference lagrangian.py:647-704, utils.py:214,577-612)."""
+    sd = _sd()
+    from seaduck_b200 import minixr, synthetic
+
+    if scheme == "rectilinear":
+        ds = synthetic.rectilinear(nlat=100, nlon=100)
+        n = 10_000
+        rng = np.random.default_rng(31)
+        lon, lat, dep = rng.uniform(-179.5, 179.5, n), rng.uniform(-70.0, 70.0, n), np.full(n, -1.0)
+        kw = dict(uname="u", vname="v", wname=None, transport=False)
+        stops = (60 * cases.DAY, 20 * cases.DAY)
+    else:
+        full = synthetic.llc(n=45, nz=12)
+        keep = {k: (tuple(full[k].dims), np.asarray(full[k])) for k in full.variables if k not in ("XG", "YG")}
+        dims = {d for dd, _ in keep.values() for d in dd}
+        ds = minixr.Dataset(coords={k: v for k, v in keep.items() if k in dims}, data_vars={k: v for k, v in keep.items() if k not in dims})
+        n = 10_000
+        lon, lat, dep = synthetic.llc_seed_particles(None, n, seed=32, depth_range=(5, 600))
+        kw = dict(uname="utrans", vname="vtrans", wname="wtrans", transport=True)
+        stops = (30 * cases.DAY, 10 * cases.DAY)
+    od = sd.OceData(ds)
+    assert od.readiness["h"] == scheme
+    pt = sd.Particle(x=lon, y=lat, z=dep, t=np.zeros(n), data=od, save_raw=True, **kw)
+    op = oracle_lib.oracle_particle_from_od(od, lon, lat, dep, np.zeros(n), save_raw=True, nthreads=8, **kw)
+    same = (pt.iy == op.iy) & (pt.ix == op.ix)
+    assert same.all(), f"{int((~same).sum())} particles located in another cell"
+    for k, ref in (("rx", op.rx), ("ry", op.ry), ("u", op.u), ("v", op.v), ("du", op.du), ("dv", op.dv)):
+        cases.assert_close(k, getattr(pt, k), ref)
+    total = 0
+    for ts in stops:
+        pt.empty_lists()
+        pt.note_taking(stamp=15)
+        pt.to_next_stop(ts)
+        op.to_next_stop(ts, emit_start=True)
+        rec, ref = log_of(pt), op.records
+        np.testing.assert_array_equal(rec["offset"], ref["offset"])
+        for k in cases.LOG_INT:
+            np.testing.assert_array_equal(rec[k], ref[k], err_msg=k)
+        for k in cases.LOG_FLT:
+            cases.assert_close(k, rec[k], ref[k])
+        total += int((ref["vs"] < 6).sum())
+    assert pt.crossings == total and total > 3e4, total
+
+
 def test_lazy_mode_equals_eager():
     """``Particle.lazy``: end-of-stop bookkeeping on the device, same state and counts as the eager path."""
     sd = _sd()
