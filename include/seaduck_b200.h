@@ -190,7 +190,7 @@ int sdk_abi_version(void);
 /* sizeof() of the structures above as the library was compiled (binding self-check): 0 sdk_grid_desc,
  * 1 sdk_velocity, 2 sdk_particles, 3 sdk_advect_params, 4 sdk_log, 5 sdk_located, 6 sdk_track_io,
  * 7 sdk_kernel_desc, 8 sdk_field, 9 sdk_points, 10 sdk_budget_fields, 11 sdk_wall_fields, 12 sdk_snapshot_record,
- * 13 sdk_exchange; -1 for anything else */
+ * 13 sdk_exchange, 14 sdk_interp_job, 15 sdk_interp_io; -1 for anything else */
 int64_t sdk_struct_size(int which);
 const char *sdk_last_error(void);
 /* number of SMs of the current device (grid sizing), <0 on error */
@@ -362,6 +362,41 @@ int sdk_interp_vector(const sdk_grid *grid, const sdk_points *pts, const sdk_fie
 /* maskU / maskV / maskWvel from maskC (seaduck/get_masks.py:12,46,79), all [nz][face][ny][nx] uint8 */
 int sdk_build_masks(const sdk_grid *grid, const uint8_t *maskC, int32_t nz, uint8_t *maskU, uint8_t *maskV,
                     uint8_t *maskW, void *stream);
+
+/* Coordinates in, interpolated values out, all HOST memory (pinned for full speed): what
+ * `OceInterp(od, var_list, x, y, z, t)` does for Eulerian points (seaduck/oceinterp.py:107-112 ->
+ * Position.from_latlon eulerian.py:138 + Position.interpolate :1268).  The points are cut into chunks that go
+ * round three internal streams: upload, (level, bucket) sort, sdk_locate, one launch per job with the results
+ * scattered back to the caller's order, read-back -- the copies of one chunk overlap the kernels of the others.
+ * A job is what one launch computes: up to SDK_MAX_MULTI_FIELDS scalars that share a kernel and a grid position,
+ * or one horizontal vector.  `zsel` / `tsel` say which of sdk_locate's index families the variable and the
+ * kernel's vkernel / tkernel ask for (eulerian.py:451-518, 1196-1224). */
+enum { SDK_SEL_NONE = 0, SDK_SEL_Z = 1, SDK_SEL_Z_LIN = 2, SDK_SEL_ZL = 3, SDK_SEL_ZL_LIN = 4 };
+enum { SDK_SEL_T = 1, SDK_SEL_T_LIN = 2 };
+enum { SDK_JOB_SCALARS = 0, SDK_JOB_VECTOR = 1 };
+typedef struct sdk_interp_job {
+    int32_t kind;     /* SDK_JOB_* */
+    int32_t n_fields; /* scalars: 1 .. SDK_MAX_MULTI_FIELDS; vector: 2 (u, v) */
+    int32_t zsel, tsel;
+    int32_t vec_transform, reserved;
+    sdk_field fields[SDK_MAX_MULTI_FIELDS];
+    sdk_kernel_desc knw[2]; /* scalars: knw[0]; vector: kernels of u and v */
+    double *out[SDK_MAX_MULTI_FIELDS]; /* HOST arrays of n doubles, one per field */
+} sdk_interp_job;
+typedef struct sdk_interp_io {
+    int64_t n;
+    const double *lon, *lat, *dep, *t; /* HOST; dep and t may be NULL */
+    int32_t sort;       /* != 0: order the points of a chunk by (level, bucket) before locating them */
+    int32_t max_chunks; /* 0 = the library's default */
+    /* optional HOST word: OR of sdk_locate's status bits over all points (SDK_ST_OOB* = the reference's
+     * "Value out of bound.", SDK_ST_BAD_CELL) */
+    uint32_t *out_flags;
+} sdk_interp_io;
+int64_t sdk_interp_host_scratch_bytes(int64_t n, int32_t n_outputs);
+int sdk_interp_host(const sdk_grid *grid, const sdk_interp_io *io, const double *ts_dev, int32_t n_t,
+                    const sdk_interp_job *jobs, int32_t n_jobs, void *scratch, void *stream);
+/* OR of n status words (device) into *flags (device, not cleared first) */
+int sdk_status_or(const int32_t *status, int64_t n, uint32_t *flags, void *stream);
 
 /* End of Particle.to_next_stop without a host round trip (seaduck/lagrangian.py:793-802): if the
  * advect call counted live particles (stats[0] > 0; the reference returns early otherwise) set

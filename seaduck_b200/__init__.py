@@ -15,5 +15,6 @@ from .eulerian import Position  # noqa: E402
 from .lagrangian import Particle  # noqa: E402
 from .oceinterp import OceInterp  # noqa: E402
 from . import get_masks  # noqa: E402,F401
+from .interp import pinned  # noqa: E402  (numpy arrays in page-locked memory for the host-buffer entry points)
 
-__all__ = ["__version__", "Position", "KnW", "Particle", "OceData", "OceInterp", "rcParam", "Topology"]
+__all__ = ["__version__", "Position", "KnW", "Particle", "OceData", "OceInterp", "rcParam", "Topology", "pinned"]

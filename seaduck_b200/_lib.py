@@ -254,6 +254,10 @@ def lib():
         L.sdk_interp_scalar.argtypes = [vp] * 6
         L.sdk_interp_scalar_multi.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp]
         L.sdk_interp_vector.argtypes = [vp] * 6 + [C.c_int, vp, vp, vp]
+        L.sdk_interp_host_scratch_bytes.restype = C.c_int64
+        L.sdk_interp_host_scratch_bytes.argtypes = [C.c_int64, C.c_int32]
+        L.sdk_interp_host.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_int32, vp, vp]
+        L.sdk_status_or.argtypes = [vp, C.c_int64, vp, vp]
         _lib = L
     return _lib
 

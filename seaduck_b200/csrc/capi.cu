@@ -707,6 +707,8 @@ int64_t sdk_struct_size(int which) {
         case 11: return sizeof(sdk_wall_fields);
         case 12: return sizeof(sdk_snapshot_record);
         case 13: return sizeof(sdk_exchange);
+        case 14: return sizeof(sdk_interp_job);
+        case 15: return sizeof(sdk_interp_io);
         default: return -1;
     }
 }
@@ -724,6 +726,18 @@ int sdk_selftest_cell_move(const sdk_grid *grid, int64_t n, const int32_t *in, i
     if (!grid || n < 0 || (n > 0 && (!in || !out))) return fail(SDK_EINVAL, "sdk_selftest_cell_move: bad argument");
     cudaError_t e = sdk::launch_selftest_cell_move(grid->dev, n, in, out, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_selftest_cell_move: launch");
+    return SDK_OK;
+}
+
+// the three internal streams (+ events) the *_host entry points pipeline their chunks over
+static int ensure_pipe(const sdk_grid *grid) {
+    if (grid->has_pipe) return SDK_OK;
+    cudaError_t e;
+    for (auto &st : grid->pipe)
+        if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "internal stream");
+    for (auto &ev : grid->pipe_ev)
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "internal event");
+    grid->has_pipe = true;
     return SDK_OK;
 }
 
@@ -912,13 +926,7 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
         int rc = track_chunk(grid, vel, io, ts_dev, n_t, t_stop, par, stats_dev, cur, records_dev, signals, stream);
         if (rc) return rc;
     } else {
-        if (!grid->has_pipe) {
-            for (auto &st : grid->pipe)
-                if ((e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: stream");
-            for (auto &ev : grid->pipe_ev)
-                if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event");
-            grid->has_pipe = true;
-        }
+        if (int rc = ensure_pipe(grid)) return rc;
         // the internal streams start after whatever the caller queued on `stream`
         if ((e = cudaEventRecord(grid->pipe_ev[3], stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");
         for (auto &st : grid->pipe)
@@ -956,6 +964,218 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
     if (io->out_stats && (e = cudaMemcpyAsync(io->out_stats, stats_dev, 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
         return cuda_fail(e, "sdk_track_host: D2H");
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: sync");
+    return SDK_OK;
+}
+
+// ---- coordinates in, interpolated values out ------------------------------------------------------
+namespace {
+constexpr int kInterpChunksDefault = 8;
+constexpr int kInterpChunksMax = 64;
+constexpr int64_t kInterpMinChunk = 262144;
+constexpr size_t kInterpHeadBytes = 256;
+
+// device memory of one chunk in flight (there are three: one per internal stream)
+size_t interp_slot_bytes(int64_t c, int n_outputs) {
+    const size_t d = align256((size_t)c * 8), w = align256((size_t)c * 4);
+    return 8 * d                                                            // coordinates as they came in + in sorted order
+           + w + align256((size_t)sdk_cell_sort_scratch_bytes(c))           // permutation, sort workspace
+           + 3 * w + 2 * d + 2 * w                                          // face iy ix, rx ry, cs sn
+           + 6 * (w + 3 * d)                                                // six index families of sdk_locate
+           + w                                                              // status
+           + (size_t)n_outputs * d;
+}
+
+int64_t interp_chunk_count(int64_t n, int max_chunks) {
+    int64_t k = n / kInterpMinChunk;
+    if (k > max_chunks) k = max_chunks;
+    return k < 1 ? 1 : k;
+}
+}  // namespace
+
+int64_t sdk_interp_host_scratch_bytes(int64_t n, int32_t n_outputs) {
+    if (n < 0 || n_outputs < 0) return 0;
+    // the largest chunk any chunk count can produce: n itself (one chunk) or n / k rounded up to 32
+    int64_t c = n;
+    if (n >= 2 * kInterpMinChunk) c = (n / 2 + 32);
+    return (int64_t)(kInterpHeadBytes + 3 * interp_slot_bytes(c, n_outputs));
+}
+
+int sdk_status_or(const int32_t *status, int64_t n, uint32_t *flags, void *stream) {
+    if (n < 0 || !flags || (n > 0 && !status)) return fail(SDK_EINVAL, "sdk_status_or: bad argument");
+    cudaError_t e = sdk::launch_status_or(status, n, flags, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "sdk_status_or: launch");
+    return SDK_OK;
+}
+
+// One chunk of sdk_interp_host, asynchronous on `stream`: H2D, sort, locate, one launch per job, D2H.
+static int interp_chunk(const sdk_grid *grid, const sdk_interp_io *io, int64_t off, int64_t n, const double *ts_dev, int32_t n_t,
+                        const sdk_interp_job *jobs, int32_t n_jobs, uint32_t *flags_dev, char *cur, cudaStream_t stream) {
+    cudaError_t e;
+    const bool timed = io->t && ts_dev && n_t > 1;
+    const bool sorted = io->sort && grid->dev.hmode != SDK_H_RECTILINEAR && grid->has_buckets;
+    auto take = [&cur](size_t bytes) {
+        char *p = cur;
+        cur += align256(bytes);
+        return p;
+    };
+    double *in[4], *pt[4];
+    for (auto &a : in) a = (double *)take((size_t)n * 8);
+    if (sorted)
+        for (auto &a : pt) a = (double *)take((size_t)n * 8);
+    else
+        for (int k = 0; k < 4; ++k) pt[k] = in[k];
+    const double *host[4] = {io->lon, io->lat, io->dep, io->t};
+    for (int k = 0; k < 4; ++k)
+        if (host[k] && (e = cudaMemcpyAsync(in[k], host[k] + off, (size_t)n * 8, cudaMemcpyHostToDevice, stream)) != cudaSuccess)
+            return cuda_fail(e, "sdk_interp_host: H2D");
+    // which index families the jobs ask for (the linear Zl lookup always runs when there is a depth: it is the one whose
+    // "Value out of bound." Position.from_latlon raises, eulerian.py:199)
+    bool want_z[5] = {false, false, false, false, false}, want_t[3] = {false, false, false};
+    bool want_cs = false;
+    for (int j = 0; j < n_jobs; ++j) {
+        want_z[jobs[j].zsel] = true;
+        want_t[jobs[j].tsel] = true;
+        want_cs |= jobs[j].kind == SDK_JOB_VECTOR && jobs[j].vec_transform;
+    }
+    const bool vertical = io->dep != nullptr;
+    if (vertical && grid->dev.n_zl > 1) want_z[SDK_SEL_ZL_LIN] = true;
+    int32_t *perm = nullptr;
+    if (sorted) {
+        perm = (int32_t *)take((size_t)n * 4);
+        const size_t sbytes = (size_t)sdk_cell_sort_scratch_bytes(n);
+        char *sort_ws = take(sbytes);
+        if ((e = sdk::launch_point_sort(grid->dev, grid->buckets, n, in[0], in[1], (vertical && grid->dev.n_zl > 1) ? in[2] : nullptr, perm,
+                                        sort_ws, sbytes, stream)) != cudaSuccess)
+            return cuda_fail(e, "sdk_interp_host: sort");
+        if ((e = sdk::launch_points_gather(n, perm, in[0], in[1], io->dep ? in[2] : nullptr, io->t ? in[3] : nullptr, pt[0], pt[1], pt[2], pt[3],
+                                           stream)) != cudaSuccess)
+            return cuda_fail(e, "sdk_interp_host: gather");
+    }
+    sdk_located loc;
+    std::memset(&loc, 0, sizeof loc);
+    if (grid->dev.has_face) loc.face = (int32_t *)take((size_t)n * 4);
+    loc.iy = (int32_t *)take((size_t)n * 4);
+    loc.ix = (int32_t *)take((size_t)n * 4);
+    loc.rx = (double *)take((size_t)n * 8);
+    loc.ry = (double *)take((size_t)n * 8);
+    if (want_cs) {
+        loc.cs = (float *)take((size_t)n * 4);
+        loc.sn = (float *)take((size_t)n * 4);
+    }
+    struct Family {
+        int32_t **k;
+        double **r, **d, **b;
+    };
+    const Family zfam[5] = {{nullptr, nullptr, nullptr, nullptr},
+                            {&loc.iz, &loc.rz, &loc.dz, &loc.bz},
+                            {&loc.iz_lin, &loc.rz_lin, &loc.dz_lin, &loc.bz_lin},
+                            {&loc.izl_near, &loc.rzl_near, &loc.dzl_near, &loc.bzl_near},
+                            {&loc.izl, &loc.rzl, &loc.dzl, &loc.bzl}};
+    const Family tfam[3] = {{nullptr, nullptr, nullptr, nullptr}, {&loc.it, &loc.rt, &loc.dt, &loc.bt}, {&loc.it_lin, &loc.rt_lin, &loc.dt_lin, &loc.bt_lin}};
+    auto carve = [&](const Family &f) {
+        *f.k = (int32_t *)take((size_t)n * 4);
+        *f.r = (double *)take((size_t)n * 8);
+        *f.d = (double *)take((size_t)n * 8);
+        *f.b = (double *)take((size_t)n * 8);
+    };
+    for (int s = 1; s < 5; ++s)
+        if (want_z[s] && vertical) carve(zfam[s]);
+    for (int s = 1; s < 3; ++s)
+        if (want_t[s] && timed) carve(tfam[s]);
+    loc.status = (int32_t *)take((size_t)n * 4);
+    int rc = sdk_locate(grid, n, pt[0], pt[1], vertical ? pt[2] : nullptr, timed ? pt[3] : nullptr, ts_dev, n_t, &loc, stream);
+    if (rc) return rc;
+    if ((e = sdk::launch_status_or(loc.status, n, flags_dev, stream)) != cudaSuccess) return cuda_fail(e, "sdk_interp_host: status");
+    for (int j = 0; j < n_jobs; ++j) {
+        const sdk_interp_job &job = jobs[j];
+        sdk_points p;
+        std::memset(&p, 0, sizeof p);
+        p.n = n;
+        p.face = loc.face; p.iy = loc.iy; p.ix = loc.ix; p.rx = loc.rx; p.ry = loc.ry;
+        if (job.zsel) {
+            if (!vertical) return fail(SDK_EINVAL, "sdk_interp_host: the variable has a vertical dimension but the points have no depth");
+            p.kz = *zfam[job.zsel].k;
+            p.rz = *zfam[job.zsel].r;
+        }
+        if (job.tsel) {
+            if (!timed) return fail(SDK_EINVAL, "sdk_interp_host: the variable has a time dimension but the points have no time");
+            p.kt = *tfam[job.tsel].k;
+            p.rt = *tfam[job.tsel].r;
+        }
+        p.cs = loc.cs; p.sn = loc.sn;
+        p.out_index = perm;
+        double *out[SDK_MAX_MULTI_FIELDS];
+        for (int k = 0; k < job.n_fields; ++k) out[k] = (double *)take((size_t)n * 8);
+        if (job.kind == SDK_JOB_VECTOR)
+            rc = sdk_interp_vector(grid, &p, &job.fields[0], &job.fields[1], &job.knw[0], &job.knw[1], job.vec_transform, out[0], out[1], stream);
+        else if (job.n_fields == 1)
+            rc = sdk_interp_scalar(grid, &p, &job.fields[0], &job.knw[0], out[0], stream);
+        else
+            rc = sdk_interp_scalar_multi(grid, &p, job.fields, job.n_fields, &job.knw[0], out, stream);
+        if (rc) return rc;
+        for (int k = 0; k < job.n_fields; ++k)
+            if ((e = cudaMemcpyAsync(job.out[k] + off, out[k], (size_t)n * 8, cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+                return cuda_fail(e, "sdk_interp_host: D2H");
+    }
+    return SDK_OK;
+}
+
+int sdk_interp_host(const sdk_grid *grid, const sdk_interp_io *io, const double *ts_dev, int32_t n_t, const sdk_interp_job *jobs,
+                    int32_t n_jobs, void *scratch, void *stream_) {
+    if (!grid || !io || !scratch || (n_jobs > 0 && !jobs) || n_jobs < 0) return fail(SDK_EINVAL, "sdk_interp_host: null argument");
+    if (!io->lon || !io->lat) return fail(SDK_EINVAL, "sdk_interp_host: lon / lat are required");
+    if (grid->dev.hmode != SDK_H_RECTILINEAR && !grid->has_buckets) return fail(SDK_EINVAL, "sdk_interp_host: call sdk_grid_build_locator first");
+    int n_outputs = 0;
+    for (int j = 0; j < n_jobs; ++j) {
+        const sdk_interp_job &job = jobs[j];
+        if (job.kind != SDK_JOB_SCALARS && job.kind != SDK_JOB_VECTOR) return fail(SDK_EINVAL, "sdk_interp_host: unknown job kind");
+        if (job.kind == SDK_JOB_VECTOR ? job.n_fields != 2 : (job.n_fields < 1 || job.n_fields > SDK_MAX_MULTI_FIELDS))
+            return fail(SDK_EINVAL, "sdk_interp_host: bad number of fields in a job");
+        if (job.zsel < 0 || job.zsel > SDK_SEL_ZL_LIN || job.tsel < 0 || job.tsel > SDK_SEL_T_LIN)
+            return fail(SDK_EINVAL, "sdk_interp_host: bad index family");
+        for (int k = 0; k < job.n_fields; ++k)
+            if (!job.out[k]) return fail(SDK_EINVAL, "sdk_interp_host: output array missing");
+        n_outputs += job.n_fields;
+    }
+    const int64_t n = io->n;
+    if (n < 0) return fail(SDK_EINVAL, "sdk_interp_host: negative count");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    cudaError_t e;
+    uint32_t *flags_dev = (uint32_t *)scratch;
+    if ((e = cudaMemsetAsync(scratch, 0, kInterpHeadBytes, stream)) != cudaSuccess) return cuda_fail(e, "sdk_interp_host: memset");
+    int max_chunks = io->max_chunks > 0 ? io->max_chunks : kInterpChunksDefault;
+    if (const char *env = std::getenv("SDK_INTERP_CHUNKS")) {  // tuning knob
+        const int v = std::atoi(env);
+        if (v >= 1) max_chunks = v;
+    }
+    if (max_chunks > kInterpChunksMax) max_chunks = kInterpChunksMax;
+    const int64_t nchunks = interp_chunk_count(n, max_chunks);
+    char *base = (char *)scratch + kInterpHeadBytes;
+    if (n > 0 && nchunks < 2) {
+        int rc = interp_chunk(grid, io, 0, n, ts_dev, n_t, jobs, n_jobs, flags_dev, base, stream);
+        if (rc) return rc;
+    } else if (n > 0) {
+        if (int rc = ensure_pipe(grid)) return rc;
+        if ((e = cudaEventRecord(grid->pipe_ev[3], stream)) != cudaSuccess) return cuda_fail(e, "sdk_interp_host: event record");
+        for (auto &st : grid->pipe)
+            if ((e = cudaStreamWaitEvent(st, grid->pipe_ev[3], 0)) != cudaSuccess) return cuda_fail(e, "sdk_interp_host: wait");
+        const int64_t per = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
+        const size_t slot = interp_slot_bytes(per, n_outputs);
+        int c = 0;
+        for (int64_t off = 0; off < n; off += per, ++c) {
+            const int64_t cnt = n - off < per ? n - off : per;
+            // chunk c and chunk c + 3 share a slot and a stream: the stream's order keeps them apart
+            int rc = interp_chunk(grid, io, off, cnt, ts_dev, n_t, jobs, n_jobs, flags_dev, base + (size_t)(c % 3) * slot, grid->pipe[c % 3]);
+            if (rc) return rc;
+        }
+        for (int k = 0; k < 3; ++k) {
+            if ((e = cudaEventRecord(grid->pipe_ev[k], grid->pipe[k])) != cudaSuccess) return cuda_fail(e, "sdk_interp_host: event record");
+            if ((e = cudaStreamWaitEvent(stream, grid->pipe_ev[k], 0)) != cudaSuccess) return cuda_fail(e, "sdk_interp_host: wait");
+        }
+    }
+    if (io->out_flags && (e = cudaMemcpyAsync(io->out_flags, flags_dev, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+        return cuda_fail(e, "sdk_interp_host: D2H");
+    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_fail(e, "sdk_interp_host: sync");
     return SDK_OK;
 }
 

@@ -635,4 +635,20 @@ cudaError_t launch_time_index(const double *t, const double *midp, int n_midp, i
     return cudaGetLastError();
 }
 
+// OR of the status words of a batch of points (what sdk_locate flagged anywhere): warp reduction, one atomic per warp that saw a bit
+__global__ void __launch_bounds__(256) status_or_kernel(const int32_t *status, int64_t n, unsigned int *flags) {
+    unsigned int mine = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) mine |= (unsigned int)status[i];
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicOr(flags, mine);
+}
+
+cudaError_t launch_status_or(const int32_t *status, int64_t n, unsigned int *flags, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    int64_t blocks = (n + 1023) / 1024;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    status_or_kernel<<<(unsigned)blocks, 256, 0, s>>>(status, n, flags);
+    return cudaGetLastError();
+}
+
 }  // namespace sdk

@@ -35,5 +35,6 @@ cudaError_t launch_finish_stop(double *t, int32_t *it, const double *midp, int n
                                const unsigned long long *stats, unsigned long long *total, int64_t n, cudaStream_t s);
 cudaError_t launch_time_index(const double *t, const double *midp, int n_midp, int32_t *it, int64_t n,
                               cudaStream_t s);
+cudaError_t launch_status_or(const int32_t *status, int64_t n, unsigned int *flags, cudaStream_t s);
 
 }  // namespace sdk

@@ -177,6 +177,24 @@ class Points(C.Structure):
     _fields_ = [("n", C.c_int64)] + [(n, C.c_void_p) for n in "face iy ix rx ry kz rz kt rt cs sn out_index".split()]
 
 
+MAX_MULTI_FIELDS = 4
+SEL_NONE, SEL_Z, SEL_Z_LIN, SEL_ZL, SEL_ZL_LIN = range(5)
+SEL_T, SEL_T_LIN = 1, 2
+JOB_SCALARS, JOB_VECTOR = 0, 1
+
+
+class InterpJob(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in "kind n_fields zsel tsel vec_transform reserved".split()] + [
+        ("fields", Field * MAX_MULTI_FIELDS), ("knw", KernelDesc * 2), ("out", C.c_void_p * MAX_MULTI_FIELDS),
+    ]
+
+
+class InterpIO(C.Structure):
+    _fields_ = [("n", C.c_int64)] + [(n, C.c_void_p) for n in "lon lat dep t".split()] + [
+        ("sort", C.c_int32), ("max_chunks", C.c_int32), ("out_flags", C.c_void_p),
+    ]
+
+
 def axis_polynomial(nodes, target, order):
     """Coefficients (ascending powers of r) of the Lagrange weight of ``target`` among the 1-D
     ``nodes`` for the ``order``-th derivative, as the reference defines it (kernel_weight.py:136-230:
@@ -564,6 +582,7 @@ def _bind():
         ]
         L.sdk_interp_scalar_multi.argtypes = [vp, C.POINTER(Points), C.POINTER(Field), C.c_int32, C.POINTER(KernelDesc), vp, vp]
         L.sdk_build_masks.argtypes = [vp, vp, C.c_int32, vp, vp, vp, vp]
+        L.sdk_interp_host.argtypes = [vp, C.POINTER(InterpIO), vp, C.c_int32, C.POINTER(InterpJob), C.c_int32, vp, vp]
         L._interp_bound = True
     return L
 
@@ -599,9 +618,6 @@ def interp_scalar_device(pts, name, dims, knw, prefetched=None, prefix=None):
     )
     del keep_k, keep_f, keep_p, keep_v
     return out
-
-
-MAX_MULTI_FIELDS = 4
 
 
 def interp_scalars_device(pts, names, dims, knw):
@@ -734,14 +750,12 @@ def _broadcast_inputs(pos, var_name, knw, prefetched, prefetch_prefix):
     return single, var_name, knw, prefetched, prefetch_prefix
 
 
-def interpolate_device(pos, var_name, knw, vec_transform=True, prefetched=None, prefetch_prefix=None):
-    """Like :func:`interpolate` but the results stay on the device (torch tensors)."""
-    single, var_name, knw, prefetched, prefetch_prefix = _broadcast_inputs(pos, var_name, knw, prefetched, prefetch_prefix)
-    od = pos.ocedata
-    has_face = pos.rel.has("face") if "_st" not in pos.__dict__ else pos.__dict__["_st"].get("face") is not None
-    pts = _DevicePoints(pos)
-    ori_list = list(zip(var_name, knw))
-    jobs = []  # (key, kind, names, kernels, prefetched, prefix)
+def _plan(od, has_face, var_name, knw, prefetched, prefetch_prefix):
+    """What has to be launched for a request, in order: a list of ``(keys, kind, names, kernels, prefetched, prefix)``
+    with kind ``"m"`` (several scalars that share the kernel and the grid position: one launch, up to four at a time),
+    ``"s"`` (one scalar) or ``"v"`` (a horizontal vector on a grid with faces).  ``keys`` are the ``(variable, kernel)``
+    pairs the launch answers; a pair asked for twice is computed once (the reference hashes likewise)."""
+    jobs = []
     for i, var in enumerate(var_name):
         if isinstance(var, str):
             if not isinstance(knw[i], KnW):
@@ -763,8 +777,7 @@ def interpolate_device(pos, var_name, knw, vec_transform=True, prefetched=None, 
             pass
         else:
             raise ValueError("var_name needs to be string, tuple, or a list of the above.")
-    final = {}
-    # scalar variables that share the kernel and the grid position go through one launch, up to four at a time
+    launches, done = [], set()
     groups = {}
     for key, kind, names, kernels, pre, prefix in jobs:
         if kind == "s" and pre is None and prefix is None:
@@ -775,30 +788,167 @@ def interpolate_device(pos, var_name, knw, vec_transform=True, prefetched=None, 
         for at in range(0, len(keys), MAX_MULTI_FIELDS):
             chunk = keys[at : at + MAX_MULTI_FIELDS]
             if len(chunk) > 1:
-                for key, out in zip(chunk, interp_scalars_device(pts, [k[0] for k in chunk], dims, kernels)):
-                    final[key] = out
+                launches.append((chunk, "m", [k[0] for k in chunk], kernels, None, None))
+                done.update(chunk)
     for key, kind, names, kernels, pre, prefix in jobs:
-        if key in final:
-            continue  # same variable and kernel twice: computed once (the reference hashes likewise)
-        if kind == "s":
-            final[key] = interp_scalar_device(pts, names, od[names].dims, kernels, pre, prefix)
-        else:
-            dims = (od[names[0]].dims, od[names[1]].dims)
-            final[key] = interp_vector_device(pts, names, dims, kernels, vec_transform, pre, prefix)
+        if key not in done:
+            launches.append(([key], kind, names, kernels, pre, prefix))
+            done.add(key)
+    return launches
+
+
+def _assemble(final, var_name, knw, has_face, single):
+    """Results in the nesting of the request."""
     output = []
-    for var, kk in ori_list:
+    for var, kk in zip(var_name, knw):
         if var is None:
             output.append(None)
-        elif isinstance(var, tuple):
-            if not has_face:
-                output.append(tuple(final.get((var[i], kk[i])) for i in range(len(var))))
-            else:
-                output.append(final.get((var, kk)))
+        elif isinstance(var, tuple) and not has_face:
+            output.append(tuple(final.get((var[i], kk[i])) for i in range(len(var))))
         else:
             output.append(final.get((var, kk)))
-    if single:
-        output = output[0]
-    return output
+    return output[0] if single else output
+
+
+def interpolate_device(pos, var_name, knw, vec_transform=True, prefetched=None, prefetch_prefix=None):
+    """Like :func:`interpolate` but the results stay on the device (torch tensors)."""
+    single, var_name, knw, prefetched, prefetch_prefix = _broadcast_inputs(pos, var_name, knw, prefetched, prefetch_prefix)
+    od = pos.ocedata
+    has_face = pos.rel.has("face") if "_st" not in pos.__dict__ else pos.__dict__["_st"].get("face") is not None
+    pts = _DevicePoints(pos)
+    final = {}
+    for keys, kind, names, kernels, pre, prefix in _plan(od, has_face, var_name, knw, prefetched, prefetch_prefix):
+        if kind == "m":
+            for key, out in zip(keys, interp_scalars_device(pts, names, od[names[0]].dims, kernels)):
+                final[key] = out
+        elif kind == "s":
+            final[keys[0]] = interp_scalar_device(pts, names, od[names].dims, kernels, pre, prefix)
+        else:
+            dims = (od[names[0]].dims, od[names[1]].dims)
+            final[keys[0]] = interp_vector_device(pts, names, dims, kernels, vec_transform, pre, prefix)
+    return _assemble(final, var_name, knw, has_face, single)
+
+
+# ------------------------------------------------------------------------------------------------
+# host arrays in, host arrays out: one call, chunks pipelined inside the library
+# ------------------------------------------------------------------------------------------------
+HOST_PATH_THRESHOLD = 200_000
+
+
+def pinned(shape, dtype=np.float64):
+    """A numpy array in page-locked host memory (from torch's caching host allocator, so repeated requests of a
+    size reuse the same pages).  Coordinates handed to ``OceInterp`` / ``interpolate_host`` in such arrays are
+    uploaded by DMA at PCIe speed; ordinary numpy arrays work too and go through the driver's staging copy."""
+    import torch  # noqa: PLC0415
+
+    tdt = {np.dtype(np.float64): torch.float64, np.dtype(np.float32): torch.float32, np.dtype(np.int32): torch.int32,
+           np.dtype(np.int64): torch.int64, np.dtype(np.uint8): torch.uint8}[np.dtype(dtype)]
+    return torch.empty(shape, dtype=tdt, pin_memory=True).numpy()
+
+
+def _vertical_time_selectors(od, dims, knw, have_dep, have_time):
+    """Which index family of ``sdk_locate`` a variable and its kernel read (same choices as :func:`_vertical_time`)."""
+    zsel = tsel = SEL_NONE
+    if "Z" in dims or "Zl" in dims:
+        if knw.vkernel not in ("nearest", "linear", "dz"):
+            raise ValueError("vkernel not supported")
+        if not have_dep or not od.readiness["Z" if "Z" in dims else "Zl"]:
+            raise ValueError("the variable has a vertical dimension but the points have no depth")
+        near = knw.vkernel == "nearest"
+        zsel = (SEL_Z if near else SEL_Z_LIN) if "Z" in dims else (SEL_ZL if near else SEL_ZL_LIN)
+    if "time" in dims:
+        if knw.tkernel not in ("nearest", "linear", "dt"):
+            raise ValueError("tkernel not supported")
+        if not have_time:
+            raise ValueError("the variable has a time dimension but the points have no time")
+        tsel = SEL_T if knw.tkernel == "nearest" else SEL_T_LIN
+    return zsel, tsel
+
+
+def interpolate_host(od, x, y, z, t, var_name, knw, vec_transform=True, sort=True, max_chunks=0):
+    """``Position().from_latlon(x, y, z, t, data=od).interpolate(var_name, knw)`` for host arrays as ONE library call
+    (``sdk_interp_host``): the points are cut into chunks whose upload, locating, interpolation and read-back overlap
+    on three streams, and nothing but the requested values comes back.  Same values, same nesting of the result, same
+    exceptions as the two-step route (``tests/test_gpu_interp.py``); the results are numpy arrays in pinned memory."""
+    import torch  # noqa: PLC0415
+
+    single, var_name, knw, prefetched, prefix = _broadcast_inputs(None, var_name, knw, None, None)
+    n = len(x)
+    have_dep = z is not None and (od.readiness["Z"] or od.readiness["Zl"])
+    have_time = t is not None and bool(od.readiness["time"])
+    has_face = bool(od.tp.has_face)
+    launches = _plan(od, has_face, var_name, knw, prefetched, prefix)
+    L = _bind()
+    jobs = (InterpJob * max(len(launches), 1))()
+    keep, final = [], {}
+    for job, (keys, kind, names, kernels, _, _) in zip(jobs, launches):
+        if kind == "v":
+            uk, vk = kernels
+            udims, vdims = od[names[0]].dims, od[names[1]].dims
+            if uk.vkernel != vk.vkernel or uk.tkernel != vk.tkernel:
+                raise NotImplementedError("the two kernels of a vector must share vkernel and tkernel")
+            ignore = uk.ignore_mask or vk.ignore_mask
+            umask, vmask = _mask_for(od, udims, ignore, "U"), _mask_for(od, vdims, ignore, "V")
+            ignore = ignore or umask is None or vmask is None
+            ku, keep_ku = kernel_desc(od, uk, "U", ignore, bottom_no_flux=uk.vkernel == "linear")
+            kv, keep_kv = kernel_desc(od, vk, "V", ignore, bottom_no_flux=vk.vkernel == "linear")
+            fu, keep_fu = _field(od, names[0], udims, None, None, umask)
+            fv, keep_fv = _field(od, names[1], vdims, None, None, vmask)
+            if vec_transform and (od.CS is None or od.SN is None):
+                raise ValueError("vec_transform needs CS and SN in the dataset")
+            job.kind, job.n_fields, job.vec_transform = JOB_VECTOR, 2, int(bool(vec_transform))
+            job.fields[0], job.fields[1], job.knw[0], job.knw[1] = fu, fv, ku, kv
+            job.zsel, job.tsel = _vertical_time_selectors(od, udims, uk, have_dep, have_time)
+            keep += [keep_ku, keep_kv, keep_fu, keep_fv]
+            outs = [pinned(n), pinned(n)]
+            final[keys[0]] = (outs[0], outs[1])
+        else:
+            names = [names] if kind == "s" else names
+            dims = od[names[0]].dims
+            cuvwg = "G" if ("Xp1" in dims or "Yp1" in dims) else "C"
+            mask = _mask_for(od, dims, kernels.ignore_mask)
+            k, keep_k = kernel_desc(od, kernels, cuvwg, kernels.ignore_mask or mask is None, bottom_no_flux=False)
+            job.kind, job.n_fields = JOB_SCALARS, len(names)
+            job.knw[0] = k
+            keep.append(keep_k)
+            for j, name in enumerate(names):
+                f, keep_f = _field(od, name, dims, None, None, mask)
+                job.fields[j] = f
+                keep.append(keep_f)
+            job.zsel, job.tsel = _vertical_time_selectors(od, dims, kernels, have_dep, have_time)
+            outs = [pinned(n) for _ in names]
+            for key, out in zip(keys, outs):
+                final[key] = out
+        for j, out in enumerate(outs):
+            job.out[j] = out.ctypes.data
+    coords = [np.ascontiguousarray(c, np.float64) if c is not None else None for c in (x, y, z if have_dep else None, t if have_time else None)]
+    io = InterpIO()
+    io.n = n
+    io.lon, io.lat, io.dep, io.t = (None if c is None else c.ctypes.data for c in coords)
+    io.sort, io.max_chunks = int(bool(sort)), int(max_chunks)
+    flags = np.zeros(1, np.uint32)
+    io.out_flags = flags.ctypes.data
+    n_out = sum(job.n_fields for job in jobs[: len(launches)])
+    need = int(L.sdk_interp_host_scratch_bytes(n, n_out))
+    scratch = od._interp_cache.get("host_scratch")
+    if scratch is None or scratch.numel() < need:
+        od._interp_cache.pop("host_scratch", None)
+        del scratch
+        scratch = od._interp_cache["host_scratch"] = torch.empty(need, dtype=torch.uint8, device=od._torch_device())
+    ts_dev, n_t = None, 0
+    if have_time:
+        ts_dev, n_t = od.to_device("ts", od.ts, np.float64), len(od.ts)
+    _lib.check(
+        L.sdk_interp_host(od.grid_handle(), C.byref(io), _lib.ptr(ts_dev), n_t, jobs, len(launches), scratch.data_ptr(), _lib.current_stream()),
+        "sdk_interp_host",
+    )
+    bits = int(flags[0])
+    used_z = {job.zsel for job in jobs[: len(launches)]}
+    used_t = {job.tsel for job in jobs[: len(launches)]}
+    if bits & 16 or (bits & 32 and SEL_Z_LIN in used_z) or (bits & 64 and SEL_T_LIN in used_t):
+        raise ValueError("Value out of bound.")  # reference find_ind, utils.py:301
+    del keep
+    return _assemble(final, var_name, knw, has_face, single)
 
 
 def _to_host(x):
@@ -808,7 +958,12 @@ def _to_host(x):
         return tuple(_to_host(v) for v in x)
     if isinstance(x, list):
         return [_to_host(v) for v in x]
-    return x.cpu().numpy()
+    # through pinned memory (torch's caching host allocator): DMA at PCIe speed instead of a pageable copy
+    import torch  # noqa: PLC0415
+
+    out = torch.empty(x.shape, dtype=x.dtype, pin_memory=True)
+    out.copy_(x)
+    return out.numpy()
 
 
 def interpolate(pos, var_name, knw, vec_transform=True, prefetched=None, prefetch_prefix=None):

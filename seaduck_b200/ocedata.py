@@ -552,7 +552,8 @@ class OceData:
         handle = self.grid_handle()
         dev = self._torch_device()
         n = max(_general_len(v) for v in (x, y, z, t) if v is not None)
-        up = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, np.float64)).to(dev)  # noqa: E731
+        # (non_blocking: arrays from interp.pinned() go up by DMA; pageable ones are staged by the driver as before)
+        up = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, np.float64)).to(dev, non_blocking=True)  # noqa: E731
         dx, dy, dz, dt = up(x), up(y), up(z), up(t)
         out = {}
         loc = _lib.Located()
@@ -607,7 +608,9 @@ class OceData:
             "sdk_locate",
         )
         out["_inputs"] = (dx, dy, dz, dt)
-        flags = int(out["status"].max().item()) if n > 0 else 0
+        word = torch.zeros(1, dtype=torch.int32, device=dev)  # OR of everybody's status bits
+        _lib.check(L.sdk_status_or(out["status"].data_ptr(), n, word.data_ptr(), _lib.current_stream()), "sdk_status_or")
+        flags = int(word.item())
         if flags & 16:
             raise ValueError("Value out of bound.")  # reference find_ind, utils.py:301
         out["_flags"] = flags

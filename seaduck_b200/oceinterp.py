@@ -55,6 +55,23 @@ def _seconds(t):
     raise ValueError("time format not supported")
 
 
+def _at_points(od, variables, kernels, x, y, z, t):
+    """Eulerian branch (reference ``oceinterp.py:107-112``).  Large batches of host coordinates go through the library's
+    pipelined host entry (``interp.interpolate_host``: upload, locate, interpolate and read-back of different chunks
+    overlap); anything else through ``Position.from_latlon`` + ``Position.interpolate``.  Same values either way."""
+    from . import interp  # noqa: PLC0415
+
+    if isinstance(x, np.ndarray) and isinstance(y, np.ndarray) and x.ndim == 1 and len(x) >= interp.HOST_PATH_THRESHOLD:
+        # (a coordinate the dataset has no axis for is never looked at: do not broadcast a scalar to N values for it)
+        if not od.readiness["time"] and np.ndim(t) == 0:
+            t = None
+        if not (od.readiness["Z"] or od.readiness["Zl"]) and np.ndim(z) == 0:
+            z = None
+        x, y, z, t = Position()._coordinate_arrays(x, y, z, t)
+        return interp.interpolate_host(od, x, y, z, t, variables, kernels)
+    return Position().from_latlon(x=x, y=y, z=z, t=t, data=od).interpolate(variables, kernels)
+
+
 def _along_trajectories(od, variables, kernels, x, y, z, t, lagrange_kwarg, update_stops, return_in_between):
     if np.ndim(t) == 0 or len(t) < 2:
         raise ValueError("There needs to be at least two time steps to run the lagrangian Particle")
@@ -95,7 +112,7 @@ def OceInterp(
     if not lagrangian:
         if any(lagrange_token in var for var in variables):
             raise AttributeError("__particle variables is only available for Lagrangian Particles")
-        return Position().from_latlon(x=x, y=y, z=z, t=t, data=od).interpolate(variables, kernels)
+        return _at_points(od, variables, kernels, x, y, z, t)
     stops, results = _along_trajectories(od, variables, kernels, x, y, z, t, lagrange_kwarg, update_stops, return_in_between)
     if return_pt_time:
         return stops, results

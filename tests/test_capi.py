@@ -47,6 +47,7 @@ def test_struct_sizes_match_header():
     mirrors = [
         _lib.GridDesc, _lib.Velocity, _lib.Particles, _lib.AdvectParams, _lib.Log, _lib.Located, _lib.TrackIO,
         interp.KernelDesc, interp.Field, interp.Points, _lib.BudgetFields, _lib.WallFields, None, _lib.Exchange,
+        interp.InterpJob, interp.InterpIO,
     ]
     for which, cls in enumerate(mirrors):
         if cls is not None:

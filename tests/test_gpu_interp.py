@@ -272,3 +272,93 @@ def test_interpolate_a_million_points_matches_oracle(oracle_lib):
     for k, (g, r) in enumerate(zip(got, ref)):
         ci.assert_values_close(f"variable {k}", g[same_cell], r[same_cell])
     assert np.isnan(ref[0]).mean() > 0.02  # land is part of the comparison
+
+
+def _same(a, b, label=""):
+    fa, fb = ci.flatten_result(a), ci.flatten_result(b)
+    assert len(fa) == len(fb), label
+    for k, (x, y) in enumerate(zip(fa, fb)):
+        np.testing.assert_array_equal(x, y, err_msg=f"{label}[{k}]")
+
+
+@pytest.mark.parametrize("sort", [True, False])
+def test_host_pipeline_equals_position_interpolate(sort, monkeypatch):
+    """``sdk_interp_host`` (coordinates in, values out, chunks pipelined over three streams inside the library) returns
+    bit for bit what ``Position.from_latlon`` + ``Position.interpolate`` return: several chunks with a ragged last one,
+    time-dependent 3-D variables with nearest / linear / derivative kernels, a masked multi-field group and a vector
+    with face rotation; with and without the (level, bucket) sort of the points."""
+    import seaduck_b200 as sd
+    from seaduck_b200 import interp
+
+    monkeypatch.setenv("SDK_INTERP_CHUNKS", "5")
+    case = ci.case_llc3d(n=700_001, ngrid=24, nz=8)
+    od = sd.OceData(case["ds"])
+    x, y, z, t = case["x"], case["y"], case["z"], case["t"]
+    uknw, vknw = ci.make_knw(sd.KnW, (ci.UKNW, ci.VKNW))
+    lin = sd.KnW(vkernel="linear", tkernel="linear")
+    requests = [
+        (["T", "S", ("UVELMASS", "VVELMASS")], [sd.KnW(), sd.KnW(), (uknw, vknw)]),
+        (["T", "S", "T"], [lin, lin, sd.KnW(vkernel="dz", tkernel="dt")]),
+        ("T", sd.KnW(ignore_mask=True)),
+        (("UVELMASS", "VVELMASS"), (ci.make_knw(sd.KnW, ci.DUKNW), ci.make_knw(sd.KnW, ci.DVKNW))),
+        (["WVELMASS"], [ci.make_knw(sd.KnW, ci.WKNW)]),
+    ]
+    pos = sd.Position().from_latlon(x=x, y=y, z=z, t=t, data=od)
+    for var, knw in requests:
+        ref = pos.interpolate(var, knw)
+        got = interp.interpolate_host(od, x, y, z, t, var, knw, sort=sort)
+        assert type(got) is type(ref)
+        _same(got, ref, str(var))
+    # pinned coordinates take the same route
+    xp, yp, zp, tp = (interp.pinned(len(x)) for _ in range(4))
+    xp[:], yp[:], zp[:], tp[:] = x, y, z, t
+    var, knw = requests[0]
+    _same(interp.interpolate_host(od, xp, yp, zp, tp, var, knw, sort=sort), pos.interpolate(var, knw), "pinned")
+    # vec_transform off
+    _same(interp.interpolate_host(od, x, y, z, t, var[2], knw[2], vec_transform=False, sort=sort),
+          pos.interpolate(var[2], knw[2], vec_transform=False), "no transform")
+
+
+def test_host_pipeline_on_grids_without_faces():
+    """The same on a rectilinear grid (no bucket locator, vectors are two scalars) and a 2-D curvilinear box."""
+    import seaduck_b200 as sd
+    from seaduck_b200 import interp
+
+    for make, n in ((ci.case_rectilinear, 300_000), (ci.case_gyre, 280_000)):
+        case = make(n=n)
+        od = sd.OceData(case["ds"])
+        get = lambda k: case.get(k)  # noqa: E731
+        pos = sd.Position().from_latlon(x=get("x"), y=get("y"), z=get("z"), t=get("t"), data=od)
+        for label, var, spec, vec_transform in case["jobs"]:
+            knw = ci.make_knw(sd.KnW, spec)
+            ref = pos.interpolate(var, knw, vec_transform=vec_transform)
+            got = interp.interpolate_host(od, get("x"), get("y"), get("z"), get("t"), var, knw, vec_transform=vec_transform)
+            _same(got, ref, f"{case['name']} {label}")
+
+
+def test_oceinterp_takes_the_host_pipeline_for_large_batches(monkeypatch):
+    """``OceInterp`` hands batches of 2 x 10^5 points or more to ``interpolate_host``; results equal the two-step route,
+    and a depth below the last level raises the reference's "Value out of bound." from there too."""
+    import seaduck_b200 as sd
+    from seaduck_b200 import interp
+
+    case = ci.case_llc3d(n=250_000, ngrid=24, nz=8)
+    od = sd.OceData(case["ds"])
+    x, y, z = case["x"], case["y"], case["z"]
+    t0 = float(case["t"][0])
+    calls = []
+    real = interp.interpolate_host
+    monkeypatch.setattr(interp, "interpolate_host", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    got = sd.OceInterp(od, ["T", ("UVELMASS", "VVELMASS")], x, y, z, t0)
+    assert calls == [1]
+    ref = sd.Position().from_latlon(x=x, y=y, z=z, t=t0, data=od).interpolate(
+        ["T", ("UVELMASS", "VVELMASS")], [sd.KnW(), (sd.lagrangian.uknw, sd.lagrangian.vknw)])
+    _same(got, ref, "OceInterp")
+    small = sd.OceInterp(od, "T", x[:100], y[:100], z[:100], t0)
+    assert calls == [1] and small.shape == (100,)
+    deep = z.copy()
+    deep[123_456] = -1e5
+    with pytest.raises(ValueError, match="out of bound"):
+        sd.OceInterp(od, "T", x, y, deep, t0)
+    with pytest.raises(ValueError, match="out of bound"):
+        sd.Position().from_latlon(x=x, y=y, z=deep, t=t0, data=od)
