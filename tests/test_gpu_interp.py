@@ -355,7 +355,7 @@ def test_oceinterp_takes_the_host_pipeline_for_large_batches(monkeypatch):
         ["T", ("UVELMASS", "VVELMASS")], [sd.KnW(), (sd.lagrangian.uknw, sd.lagrangian.vknw)])
     _same(got, ref, "OceInterp")
     small = sd.OceInterp(od, "T", x[:100], y[:100], z[:100], t0)
-    assert calls == [1] and small.shape == (100,)
+    assert calls == [1] and small[0].shape == (100,)
     deep = z.copy()
     deep[123_456] = -1e5
     with pytest.raises(ValueError, match="out of bound"):
