@@ -171,7 +171,7 @@ class OceData:
         ("rectilinear", ("lon", "lat")),
     )
 
-    def __init__(self, data, alias=None, memory_limit=1e7, device=None):
+    def __init__(self, data, alias=None, memory_limit=1e7, device=None, device_memory_limit=None):
         self._xr = _xr_module(data)
         self._ds = data.transpose(*self._DIM_ORDER, ..., missing_dims="ignore")
         self.tp = Topology(self._ds)
@@ -183,6 +183,12 @@ class OceData:
             self.alias = alias
         self.too_large = "XC" in self._ds.variables and self._ds["XC"].nbytes > memory_limit
         self.device = device
+        # Out-of-core fields (the reference's `too_large` route, ocedata.py:188-191 + smart_read.py:73-107, which
+        # gathers only the needed values from a dask array): a data variable (or time slab of one) larger than
+        # `device_memory_limit` bytes -- default: 70 % of the free device memory at the time it is first needed -- is not
+        # uploaded; it stays in page-locked host memory and the kernels gather from it in place over the bus.
+        self.device_memory_limit = device_memory_limit
+        self._host_resident = set()  # names forced to stay on the host (keep_on_host)
         self._dev = {}  # name -> torch tensor on the GPU
         self._field_cache = {}
         self._interp_cache = {}  # rim tables and masks of the interpolation kernel
@@ -519,9 +525,32 @@ class OceData:
                 self._field_cache[key] = t
                 return t
             return hit
-        t = torch.from_numpy(self._host_slab(name, time_slice)).to(self._torch_device())
+        host = self._host_slab(name, time_slice)
+        if self._stays_on_host(name, host.nbytes):
+            # page-locked and mapped: under unified addressing the kernels read it through the same pointer
+            t = torch.from_numpy(host).pin_memory()
+        else:
+            t = torch.from_numpy(host).to(self._torch_device())
         self._remember_slab(key, t)
         return t
+
+    def keep_on_host(self, *names):
+        """Never upload these data variables: the kernels read them in place from page-locked host memory (for
+        fields that do not fit the device next to everything else; every gather then crosses the bus)."""
+        self._host_resident.update(names)
+        self._field_cache = {k: v for k, v in self._field_cache.items() if k[0] not in names}
+        return self
+
+    def _stays_on_host(self, name, nbytes):
+        import torch  # noqa: PLC0415
+
+        if name in self._host_resident:
+            return True
+        limit = self.device_memory_limit
+        if limit is None:
+            free, _ = torch.cuda.mem_get_info(self._torch_device())
+            limit = 0.7 * free
+        return nbytes > limit
 
     def prefetch_field(self, name, time_slice):
         """Start copying a slab to the device on a side stream and return at once (streaming ingest for
@@ -530,12 +559,15 @@ class OceData:
         import torch  # noqa: PLC0415
 
         key = self._slab_key(name, time_slice)
-        if key in self._field_cache or name in self._device_vars:
+        if key in self._field_cache or name in self._device_vars or name in self._host_resident:
             return
         dev = self._torch_device()
         if getattr(self, "_copy_stream", None) is None:
             self._copy_stream = torch.cuda.Stream(dev)
         host = torch.from_numpy(self._host_slab(name, time_slice)).pin_memory()
+        if self._stays_on_host(name, host.numel() * host.element_size()):
+            self._remember_slab(key, host)  # too large to upload: read in place
+            return
         with torch.cuda.stream(self._copy_stream):
             t = torch.empty(host.shape, dtype=host.dtype, device=dev)
             t.copy_(host, non_blocking=True)

@@ -320,12 +320,18 @@ def test_fused_ship_equals_pack_records(sort):
             np.testing.assert_array_equal(getattr(pt, k), getattr(plain, k), err_msg=k)
 
 
-@pytest.mark.parametrize("n", [1000, 300_000])
-def test_track_host_equals_particle_api(n):
+@pytest.mark.parametrize("n,mode", [(1000, "0"), (300_000, "0"), (300_000, "1"), (300_001, "1s")])
+def test_track_host_equals_particle_api(n, mode, monkeypatch):
     """sdk_track_host (host buffers in and out; chunked and pipelined over three streams for large
     batches) gives exactly what Particle(...).to_next_stop(...) gives -- as separate arrays, as 32-byte records,
-    and with the particles of every chunk cell-sorted on the device."""
+    and with the particles of every chunk cell-sorted on the device.  Both ways of cutting the call up: a pipeline of
+    whole chunks (mode 0) and one state with chunked upload / locate and a single advection launch (mode 1; "1s": the
+    records of a sorted run scattered into the caller's pinned buffer by the kernel)."""
     import ctypes as C
+
+    monkeypatch.setenv("SDK_TRACK_MODE", mode[0])
+    if mode.endswith("s"):
+        monkeypatch.setenv("SDK_TRACK_SCATTER", "1")
 
     import torch
 
@@ -559,3 +565,45 @@ def test_stuck_particle_callbacks():
     assert mc.shape == maskc.shape and mu.ndim == mv.ndim == mw.ndim == 4
     common = tuple(slice(0, min(a, b)) for a, b in zip(mc.shape, mu.shape))
     assert ((mu[common] != 0) | (mc[common] == 0)).all()  # the west wall of a wet cell is wet
+
+
+def test_fields_left_in_host_memory_give_the_same_run():
+    """Out-of-core fields (the reference's ``too_large`` route): data variables that are not uploaded but read in place
+    from page-locked host memory -- forced by name (``keep_on_host``) or by size (``device_memory_limit``) -- give bit
+    for bit the run and the interpolated values of fields resident in HBM, time slabs included."""
+    import torch
+
+    sd = _sd()
+    case = cases.case_llc_time(n=3000)
+    runs = []
+    for how in ("resident", "by name", "by size"):
+        od = sd.OceData(case["ds"], device_memory_limit=1 if how == "by size" else None)
+        if how == "by name":
+            od.keep_on_host(case["kw"]["uname"], case["kw"]["vname"], case["kw"]["wname"], "T")
+        pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, **case["kw"])
+        stops, snaps = pt.to_list_of_time(normal_stops=case["stops"])
+        tvals = pt.interpolate("T", sd.KnW()) if "T" in case["ds"].variables else None
+        where = {k[0]: v.device.type for k, v in od._field_cache.items() if isinstance(v, torch.Tensor)}
+        runs.append((pt, snaps, tvals, where))
+    (a, sa, ta, wa), (b, sb, tb, wb), (c, sc, tc, wc) = runs
+    assert set(wa.values()) == {"cuda"} and wb[case["kw"]["uname"]] == "cpu" and set(wc.values()) == {"cpu"}
+    assert a.crossings == b.crossings == c.crossings > 0
+    for other, snaps in ((b, sb), (c, sc)):
+        for x, y in zip(sa + [a], snaps + [other]):
+            for k in cases.FINAL_INT + cases.FINAL_FLT:
+                if getattr(x, k, None) is not None:
+                    np.testing.assert_array_equal(getattr(y, k), getattr(x, k), err_msg=k)
+    if ta is not None:
+        np.testing.assert_array_equal(tb, ta)
+        np.testing.assert_array_equal(tc, ta)
+    # Eulerian interpolation of host-resident tracers and velocities (time-dependent, masked and vector kernels)
+    import cases_interp as ci
+
+    case = ci.case_llc3d(n=2000)
+    res = []
+    for limit in (None, 1):
+        od = sd.OceData(case["ds"], device_memory_limit=limit)
+        pos = sd.Position().from_latlon(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od)
+        res.append(ci.flatten_result(pos.interpolate(["T", "S", ("UVELMASS", "VVELMASS")], [sd.KnW(), sd.KnW(vkernel="linear", tkernel="linear"), (sd.KnW(), sd.KnW())])))
+    for x, y in zip(*res):
+        np.testing.assert_array_equal(x, y)
