@@ -32,9 +32,9 @@ cudaError_t launch_cell_sort(const GridDev &g, int64_t n, const int32_t *face, c
                              const int32_t *izl, int32_t *perm, void *scratch, size_t scratch_bytes, cudaStream_t s);
 cudaError_t launch_particles_gather(const sdk_particles &src, const sdk_particles &dst, const int32_t *perm, cudaStream_t s);
 cudaError_t launch_point_sort(const GridDev &g, const BucketGrid &b, int64_t n, const double *lon, const double *lat, const double *dep,
-                              int32_t *perm, void *scratch, size_t scratch_bytes, int32_t base, cudaStream_t s);
+                              int32_t *perm, void *scratch, size_t scratch_bytes, cudaStream_t s);
 cudaError_t launch_points_gather(int64_t n, const int32_t *perm, const double *lon, const double *lat, const double *dep, const double *t,
-                                 double *olon, double *olat, double *odep, double *ot, int32_t base, cudaStream_t s);
+                                 double *olon, double *olat, double *odep, double *ot, cudaStream_t s);
 cudaError_t launch_selftest_math(int op, int64_t n, const double *a, const double *b, double *out, int32_t *bad,
                                  cudaStream_t s);
 cudaError_t launch_selftest_cell_move(const GridDev &g, int64_t n, const int32_t *in, int32_t *out, cudaStream_t s);
@@ -55,9 +55,12 @@ int cuda_fail(cudaError_t e, const char *what) {
 }  // namespace
 
 constexpr unsigned kQueueSlots = 64;
-constexpr int kTrackChunks = 3;  // measured best for 10^6 particles (tools/exp_e2e.py): 2-4 chunks within 3 %, more chunks = more kernel tails
+// measured best for 10^6 particles (tools/exp_e2e.py): 2-4 chunks within 3 %, more chunks = more kernel tails.  Two other
+// ways of cutting the call up were built and measured in round 2 (profiles/README.md, profiles/r02d_fed_queue_experiment.patch):
+// chunked upload + locate into one state with ONE advection launch (2.31 ms against 2.32 ms), and one advection launch fed
+// through a gated queue while the upload is still running (2.43 - 2.9 ms: the locate kernels crawl beside the persistent grid).
+constexpr int kTrackChunks = 3;
 constexpr int kTrackChunksMax = 32;
-constexpr bool kTrackTwoPhase = false;  // sdk_track_host: one state + one advection launch (track_two_phase) or a pipeline of whole chunks
 
 struct sdk_grid {
     sdk::GridDev dev;
@@ -314,10 +317,6 @@ int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span
     return SDK_OK;
 }
 
-// (sdk_track_host locates batches straight into a state that holds all of them: the four rows of px / py are then
-// the size of that state apart, not the size of the batch)
-static thread_local int64_t g_locate_pstride = 0;
-
 int sdk_locate(const sdk_grid *grid, int64_t n, const double *lon, const double *lat, const double *dep,
                const double *t, const double *ts, int32_t n_t, const sdk_located *out, void *stream) {
     if (!grid || !out) return fail(SDK_EINVAL, "sdk_locate: null argument");
@@ -340,7 +339,6 @@ int sdk_locate(const sdk_grid *grid, int64_t n, const double *lon, const double 
     a.lon = lon; a.lat = lat; a.dep = dep; a.t = t; a.ts = ts;
     a.n_t = n_t;
     a.max_walk = 4 * (grid->dev.ny + grid->dev.nx);
-    a.pstride = g_locate_pstride > 0 ? g_locate_pstride : n;
     a.out = *out;
     cudaError_t e = sdk::launch_locate(a, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_locate: launch");
@@ -760,13 +758,9 @@ static size_t track_chunk_bytes(int64_t n) {
 constexpr size_t kTrackSignalBytes = 512;
 constexpr size_t kTrackHeadBytes = 256 + (size_t)kTrackChunksMax * kTrackSignalBytes;
 
-static size_t track_two_phase_bytes(int64_t n);
-
 int64_t sdk_track_scratch_bytes(int64_t n) {
     // chunks are rounded up to 32 particles
-    const size_t chunked = track_chunk_bytes(n + 32 * kTrackChunksMax) + (size_t)kTrackChunksMax * 80 * 256;
-    const size_t whole = track_two_phase_bytes(n) + 64 * 256;
-    return (int64_t)((chunked > whole ? chunked : whole) + kTrackHeadBytes);
+    return (int64_t)(track_chunk_bytes(n + 32 * kTrackChunksMax) + (size_t)kTrackChunksMax * 80 * 256 + kTrackHeadBytes);
 }
 
 static void carve_particles(sdk_particles &dp, int64_t n, char *&cur) {
@@ -781,7 +775,7 @@ static void carve_particles(sdk_particles &dp, int64_t n, char *&cur) {
 }
 
 // SDK_TRACK_TIMELINE=1: CUDA events between the stages of every chunk, printed (ms since the start of the call) when
-// the call has synchronised.  A measuring aid (tools/exp_e2e.py); costs nothing when the variable is not set.
+// the call has synchronised.  A measuring aid (tools/exp_timeline.py); costs nothing when the variable is not set.
 namespace {
 struct TrackTimeline {
     bool on = false;
@@ -866,10 +860,10 @@ static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_
         cur += align256((size_t)n * 4);
         const size_t sbytes = (size_t)sdk_cell_sort_scratch_bytes(n);
         if ((e = sdk::launch_point_sort(grid->dev, grid->buckets, n, in[0], in[1], (vertical && io->dep) ? in[2] : nullptr, perm, cur, sbytes,
-                                        0, stream)) != cudaSuccess)
+                                        stream)) != cudaSuccess)
             return cuda_fail(e, "sdk_track_host: sort");
         cur += align256(sbytes);
-        if ((e = sdk::launch_points_gather(n, perm, in[0], in[1], io->dep ? in[2] : nullptr, in[3], dp.lon, dp.lat, dp.dep, dp.t, 0, stream)) !=
+        if ((e = sdk::launch_points_gather(n, perm, in[0], in[1], io->dep ? in[2] : nullptr, in[3], dp.lon, dp.lat, dp.dep, dp.t, stream)) !=
             cudaSuccess)
             return cuda_fail(e, "sdk_track_host: gather");
         TL("sort");
@@ -941,148 +935,6 @@ static int track_chunk(const sdk_grid *grid, const sdk_velocity *vel, const sdk_
     return SDK_OK;
 }
 
-// The other way to cut the call up (SDK_TRACK_MODE=1): ONE particle state for all n particles.  Phase 1 -- upload, (sort,)
-// locate -- goes chunk by chunk round the three internal streams, short kernels that overlap the uploads of the chunks
-// behind them; phase 2 is one velocity read and ONE advection launch over everything.  A persistent advection grid
-// per chunk (track_chunk) keeps the kernels of the next chunk off the SMs until it drains, and every launch pays its own
-// drain (the longest particle of the chunk, alone on the GPU): three launches of 1/6, 2/6 and 3/6 of 10^6 particles take
-// 2.06 ms of advection against 1.47 ms for one launch (tools/exp_timeline.py).
-static size_t track_two_phase_bytes(int64_t n) {
-    const int64_t c = n / 2 + 64;  // the largest chunk: there are at least two
-    return (size_t)sdk_particles_bytes(n) + 4 * align256((size_t)n * 8) + align256((size_t)n * 4) +
-           3 * align256((size_t)sdk_cell_sort_scratch_bytes(c)) + align256((size_t)n * sizeof(sdk_snapshot_record));
-}
-
-static int track_two_phase(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev, int32_t n_t,
-                           double t_stop, const sdk_advect_params *par_in, uint64_t *stats_dev, char *cur, sdk_snapshot_record *records_dev,
-                           void *signal, int nchunks, cudaStream_t stream) {
-    const int64_t n = io->n;
-    sdk_advect_params par;
-    if (par_in) par = *par_in;
-    else {
-        std::memset(&par, 0, sizeof par);
-        par.tol = 1e-4, par.trim_tol = 1e-14, par.max_iteration = 200;
-    }
-    const int has_dep = par.has_dep;
-    cudaError_t e;
-    sdk_particles dp;
-    carve_particles(dp, n, cur);
-    const bool vertical = has_dep && grid->dev.n_zl > 1;
-    const bool timed = vel->has_time && ts_dev && n_t > 1;
-    const bool sorted = io->sort && grid->dev.hmode != SDK_H_RECTILINEAR && grid->has_buckets;
-    double *in[4] = {dp.lon, dp.lat, dp.dep, dp.t};
-    int32_t *perm = nullptr;
-    const int64_t per = ((n + nchunks - 1) / nchunks + 31) / 32 * 32;
-    const size_t sbytes = (size_t)sdk_cell_sort_scratch_bytes(per);
-    char *sort_ws[3] = {nullptr, nullptr, nullptr};
-    if (sorted) {
-        for (auto &a : in) {
-            a = (double *)cur;
-            cur += align256((size_t)n * 8);
-        }
-        perm = (int32_t *)cur;
-        cur += align256((size_t)n * 4);
-        for (auto &w : sort_ws) {
-            w = cur;
-            cur += align256(sbytes);
-        }
-    }
-    if (!vertical) dp.izl = nullptr;  // no vertical index: reads as level 0 everywhere
-    if (!timed && (e = cudaMemsetAsync(dp.it, 0, (size_t)n * 4, stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: memset");
-    if ((e = cudaEventRecord(grid->pipe_ev[3], stream)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");
-    for (auto &st : grid->pipe)
-        if ((e = cudaStreamWaitEvent(st, grid->pipe_ev[3], 0)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: wait");
-    int c = 0;
-    for (int64_t off = 0; off < n; off += per, ++c) {
-        const int64_t cnt = n - off < per ? n - off : per;
-        cudaStream_t st = grid->pipe[c % 3];
-        g_timeline.mark(c, "start", st);
-        const double *host[4] = {io->lon, io->lat, io->dep, io->t};
-        for (int k = 0; k < 4; ++k)
-            if (host[k] && (e = cudaMemcpyAsync(in[k] + off, host[k] + off, (size_t)cnt * 8, cudaMemcpyHostToDevice, st)) != cudaSuccess)
-                return cuda_fail(e, "sdk_track_host: H2D");
-        g_timeline.mark(c, "h2d", st);
-        if (sorted) {
-            // the chunk's points in (level, bucket) order; perm holds indices into the whole batch
-            if ((e = sdk::launch_point_sort(grid->dev, grid->buckets, cnt, in[0] + off, in[1] + off, (vertical && io->dep) ? in[2] + off : nullptr,
-                                            perm + off, sort_ws[c % 3], sbytes, (int32_t)off, st)) != cudaSuccess)
-                return cuda_fail(e, "sdk_track_host: sort");
-            if ((e = sdk::launch_points_gather(cnt, perm + off, in[0] + off, in[1] + off, io->dep ? in[2] + off : nullptr, in[3] + off, dp.lon + off,
-                                               dp.lat + off, dp.dep + off, dp.t + off, (int32_t)off, st)) != cudaSuccess)
-                return cuda_fail(e, "sdk_track_host: gather");
-            g_timeline.mark(c, "sort", st);
-        }
-        sdk_located loc;
-        std::memset(&loc, 0, sizeof loc);
-        loc.face = grid->dev.has_face ? dp.face + off : nullptr;
-        loc.iy = dp.iy + off; loc.ix = dp.ix + off; loc.rx = dp.rx + off; loc.ry = dp.ry + off;
-        loc.px = dp.px + off; loc.py = dp.py + off;  // rows n apart (g_locate_pstride)
-        loc.dx = dp.dx + off; loc.dy = dp.dy + off;
-        if (vertical) {
-            loc.izl = dp.izl + off; loc.rzl = dp.rzl + off; loc.dzl = dp.dzl + off; loc.bzl = dp.bzl + off;
-        }
-        loc.it = dp.it + off;
-        loc.status = dp.status + off;
-        g_locate_pstride = n;
-        const int rc = sdk_locate(grid, cnt, dp.lon + off, dp.lat + off, vertical ? dp.dep + off : nullptr, timed ? dp.t + off : nullptr, ts_dev, n_t,
-                                  &loc, st);
-        g_locate_pstride = 0;
-        if (rc) return rc;
-        g_timeline.mark(c, "locate", st);
-    }
-    for (int k = 0; k < 3; ++k) {
-        if ((e = cudaEventRecord(grid->pipe_ev[k], grid->pipe[k])) != cudaSuccess) return cuda_fail(e, "sdk_track_host: event record");
-        if ((e = cudaStreamWaitEvent(stream, grid->pipe_ev[k], 0)) != cudaSuccess) return cuda_fail(e, "sdk_track_host: wait");
-    }
-    g_timeline_chunk = -1;
-    int rc = sdk_get_u_du(grid, vel, &dp, has_dep, stream);
-    if (rc) return rc;
-    TL("get_u_du");
-    par.keep_status = 1;  // what sdk_locate flagged stays flagged
-    par.stats = stats_dev;
-    sdk_exchange to_host;
-    // sorted runs: the records go to the caller's order through the permutation -- scattered 32-byte stores; over PCIe
-    // only on request (SDK_TRACK_SCATTER=1), else packed on the device and copied
-    if (perm && !std::getenv("SDK_TRACK_SCATTER")) records_dev = nullptr;
-    if (records_dev) {
-        std::memset(&to_host, 0, sizeof to_host);
-        to_host.world = 1;
-        to_host.n_slots = 1;
-        to_host.n_pad = n;
-        to_host.recv[0] = records_dev;
-        to_host.signal[0] = (uint64_t *)signal;
-        to_host.ticket = (uint32_t *)((char *)signal + SDK_SIGNAL_WORDS * sizeof(uint64_t));
-        par.ship = &to_host;
-        par.ship_index = perm;
-        par.ship_step = 1;
-    }
-    rc = sdk_advect(grid, vel, &dp, t_stop, &par, nullptr, 1, stream);
-    if (rc) return rc;
-    TL("advect");
-    if (io->out_records && !records_dev) {
-        sdk_snapshot_record *rec = (sdk_snapshot_record *)cur;
-        rc = sdk_pack_records(&dp, perm, rec, stream);
-        if (rc) return rc;
-        if ((e = cudaMemcpyAsync(io->out_records, rec, (size_t)n * sizeof(sdk_snapshot_record), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
-            return cuda_fail(e, "sdk_track_host: D2H");
-    }
-#define D2H(dst, src, esz) \
-    if (dst && src && (e = cudaMemcpyAsync(dst, src, (size_t)n * esz, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) \
-        return cuda_fail(e, "sdk_track_host: D2H");
-    D2H(io->out_lon, dp.lon, 8)
-    D2H(io->out_lat, dp.lat, 8)
-    if (has_dep) D2H(io->out_dep, dp.dep, 8)
-    if (grid->dev.has_face) D2H(io->out_face, dp.face, 4)
-    D2H(io->out_iy, dp.iy, 4)
-    D2H(io->out_ix, dp.ix, 4)
-    if (vertical) D2H(io->out_izl, dp.izl, 4)
-    D2H(io->out_ncross, dp.ncross, 4)
-    D2H(io->out_status, dp.status, 4)
-#undef D2H
-    TL("d2h");
-    return SDK_OK;
-}
-
 int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_track_io *io, const double *ts_dev,
                    int32_t n_t, double t_stop, const sdk_advect_params *par, void *scratch, void *stream_) {
     if (!grid || !vel || !io || !scratch) return fail(SDK_EINVAL, "sdk_track_host: null argument");
@@ -1123,14 +975,8 @@ int sdk_track_host(const sdk_grid *grid, const sdk_velocity *vel, const sdk_trac
         if (v >= 1 && v <= kTrackChunksMax) max_chunks = v;
     }
     if (nchunks > max_chunks) nchunks = max_chunks;
-    const char *mode_env = std::getenv("SDK_TRACK_MODE");
-    const bool two_phase = mode_env ? mode_env[0] == '1' : kTrackTwoPhase;
     if (nchunks < 2) {
         int rc = track_chunk(grid, vel, io, ts_dev, n_t, t_stop, par, stats_dev, cur, records_dev, signals, stream);
-        if (rc) return rc;
-    } else if (two_phase) {
-        if (int rc = ensure_pipe(grid)) return rc;
-        int rc = track_two_phase(grid, vel, io, ts_dev, n_t, t_stop, par, stats_dev, cur, records_dev, signals, nchunks, stream);
         if (rc) return rc;
     } else {
         if (int rc = ensure_pipe(grid)) return rc;
@@ -1254,10 +1100,10 @@ static int interp_chunk(const sdk_grid *grid, const sdk_interp_io *io, int64_t o
         const size_t sbytes = (size_t)sdk_cell_sort_scratch_bytes(n);
         char *sort_ws = take(sbytes);
         if ((e = sdk::launch_point_sort(grid->dev, grid->buckets, n, in[0], in[1], (vertical && grid->dev.n_zl > 1) ? in[2] : nullptr, perm,
-                                        sort_ws, sbytes, 0, stream)) != cudaSuccess)
+                                        sort_ws, sbytes, stream)) != cudaSuccess)
             return cuda_fail(e, "sdk_interp_host: sort");
         if ((e = sdk::launch_points_gather(n, perm, in[0], in[1], io->dep ? in[2] : nullptr, io->t ? in[3] : nullptr, pt[0], pt[1], pt[2], pt[3],
-                                           0, stream)) != cudaSuccess)
+                                           stream)) != cudaSuccess)
             return cuda_fail(e, "sdk_interp_host: gather");
     }
     sdk_located loc;

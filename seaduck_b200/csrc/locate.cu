@@ -350,8 +350,8 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
         if (o.cs) o.cs[i] = 1.f;
         if (o.sn) o.sn[i] = 0.f;
         if (o.px) {
-            o.px[0 * a.pstride + i] = bx, o.px[1 * a.pstride + i] = 1.0, o.px[2 * a.pstride + i] = dxm, o.px[3 * a.pstride + i] = 0.0;
-            o.py[0 * a.pstride + i] = by, o.py[1 * a.pstride + i] = 0.0, o.py[2 * a.pstride + i] = dym, o.py[3 * a.pstride + i] = 0.0;
+            o.px[0 * a.n + i] = bx, o.px[1 * a.n + i] = 1.0, o.px[2 * a.n + i] = dxm, o.px[3 * a.n + i] = 0.0;
+            o.py[0 * a.n + i] = by, o.py[1 * a.n + i] = 0.0, o.py[2 * a.n + i] = dym, o.py[3 * a.n + i] = 0.0;
         }
     } else if (a.lon && a.lat) {
         const double lon = a.lon[i], lat = a.lat[i];
@@ -421,8 +421,8 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
             o.rx[i] = (dlon * cb * cs + dlat * sn) * deg2m / (double)cdx;
             o.ry[i] = (dlat * cs - dlon * sn * cb) * deg2m / (double)cdy;
             if (o.px) {
-                o.px[0 * a.pstride + i] = bx, o.px[1 * a.pstride + i] = cs, o.px[2 * a.pstride + i] = (double)cdx, o.px[3 * a.pstride + i] = 0.0;
-                o.py[0 * a.pstride + i] = by, o.py[1 * a.pstride + i] = sn, o.py[2 * a.pstride + i] = (double)cdy, o.py[3 * a.pstride + i] = 0.0;
+                o.px[0 * a.n + i] = bx, o.px[1 * a.n + i] = cs, o.px[2 * a.n + i] = (double)cdx, o.px[3 * a.n + i] = 0.0;
+                o.py[0 * a.n + i] = by, o.py[1 * a.n + i] = sn, o.py[2 * a.n + i] = (double)cdy, o.py[3 * a.n + i] = 0.0;
             }
         } else {
             // corners + inverse bilinear map
@@ -434,8 +434,8 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
                 px[j] = lon + to_180((double)__ldg(g.XG + cc[j]) - lon);
                 py[j] = (double)__ldg(g.YG + cc[j]);
                 if (o.px) {
-                    o.px[j * a.pstride + i] = px[j];
-                    o.py[j * a.pstride + i] = py[j];
+                    o.px[j * a.n + i] = px[j];
+                    o.py[j * a.n + i] = py[j];
                 }
             }
             double rx, ry;
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
 
 // sort key of a point that has not been located yet: (vertical level, locator bucket), see launch_point_sort (sort.cu)
 __global__ void __launch_bounds__(256) point_key_kernel(GridDev g, BucketGrid b, int64_t n, const double *lon, const double *lat,
-                                                        const double *dep, uint64_t *key, int32_t *idx, int32_t base) {
+                                                        const double *dep, uint64_t *key, int32_t *idx) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t level = 0;
@@ -503,12 +503,12 @@ __global__ void __launch_bounds__(256) point_key_kernel(GridDev g, BucketGrid b,
     const double x = lon[i], y = lat[i];
     const uint64_t bucket = (x == x && y == y) ? (uint64_t)bucket_of(b, x, y) : 0;
     key[i] = level * ((uint64_t)b.nlat * (uint64_t)b.nlon) + bucket;
-    idx[i] = base + (int32_t)i;
+    idx[i] = (int32_t)i;
 }
 
 cudaError_t launch_point_keys(const GridDev &g, const BucketGrid &b, int64_t n, const double *lon, const double *lat, const double *dep,
-                              uint64_t *key, int32_t *idx, int32_t base, cudaStream_t s) {
-    point_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, b, n, lon, lat, dep, key, idx, base);
+                              uint64_t *key, int32_t *idx, cudaStream_t s) {
+    point_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(g, b, n, lon, lat, dep, key, idx);
     return cudaGetLastError();
 }
 

@@ -26,7 +26,6 @@ struct LocateArgs {
     int64_t n;
     const double *lon, *lat, *dep, *t, *ts;
     int n_t, max_walk;
-    int64_t pstride;  // distance between the four rows of out.px / out.py (n, or the size of the state a batch is part of)
     sdk_located out;
 };
 

@@ -79,14 +79,13 @@ cudaError_t launch_cell_sort(const GridDev &g, int64_t n, const int32_t *face, c
 // only needs the coordinates.  Sorting the 32 bytes of input of a point before locating it is cheaper than sorting
 // the 220 bytes of state afterwards, and sdk_locate itself runs on coherent points.
 cudaError_t launch_point_keys(const GridDev &g, const BucketGrid &b, int64_t n, const double *lon, const double *lat, const double *dep,
-                              uint64_t *key, int32_t *idx, int32_t base, cudaStream_t s);  // locate.cu
+                              uint64_t *key, int32_t *idx, cudaStream_t s);  // locate.cu
 
-// `base` is added to every index of the permutation (a batch that is part of a larger set of points).
 cudaError_t launch_point_sort(const GridDev &g, const BucketGrid &b, int64_t n, const double *lon, const double *lat, const double *dep,
-                              int32_t *perm, void *scratch, size_t scratch_bytes, int32_t base, cudaStream_t s) {
+                              int32_t *perm, void *scratch, size_t scratch_bytes, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
     const SortScratch w = carve_sort(n, scratch, scratch_bytes);
-    cudaError_t e = launch_point_keys(g, b, n, lon, lat, dep, w.key_in, w.idx_in, base, s);
+    cudaError_t e = launch_point_keys(g, b, n, lon, lat, dep, w.key_in, w.idx_in, s);
     if (e != cudaSuccess) return e;
     const int bits = bits_for((uint64_t)(g.n_zl > 0 ? g.n_zl + 1 : 1) * (uint64_t)b.nlat * (uint64_t)b.nlon);
     return cub::DeviceRadixSort::SortPairs(w.tmp, const_cast<size_t &>(w.tmp_bytes), w.key_in, w.key_out, w.idx_in, perm, (int)n, 0, bits, s);
@@ -95,10 +94,10 @@ cudaError_t launch_point_sort(const GridDev &g, const BucketGrid &b, int64_t n, 
 // out[k] = in[perm[k]] for the four coordinate arrays of a batch of points
 __global__ void __launch_bounds__(256) points_gather_kernel(int64_t n, const int32_t *perm, const double *lon, const double *lat,
                                                             const double *dep, const double *t, double *olon, double *olat, double *odep,
-                                                            double *ot, int32_t base) {
+                                                            double *ot) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const int64_t i = perm[k] - base;
+    const int64_t i = perm[k];
     olon[k] = lon[i];
     olat[k] = lat[i];
     if (dep) odep[k] = dep[i];
@@ -106,9 +105,9 @@ __global__ void __launch_bounds__(256) points_gather_kernel(int64_t n, const int
 }
 
 cudaError_t launch_points_gather(int64_t n, const int32_t *perm, const double *lon, const double *lat, const double *dep, const double *t,
-                                 double *olon, double *olat, double *odep, double *ot, int32_t base, cudaStream_t s) {
+                                 double *olon, double *olat, double *odep, double *ot, cudaStream_t s) {
     if (n == 0) return cudaSuccess;
-    points_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, perm, lon, lat, dep, t, olon, olat, odep, ot, base);
+    points_gather_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, perm, lon, lat, dep, t, olon, olat, odep, ot);
     return cudaGetLastError();
 }
 

@@ -320,18 +320,12 @@ def test_fused_ship_equals_pack_records(sort):
             np.testing.assert_array_equal(getattr(pt, k), getattr(plain, k), err_msg=k)
 
 
-@pytest.mark.parametrize("n,mode", [(1000, "0"), (300_000, "0"), (300_000, "1"), (300_001, "1s")])
-def test_track_host_equals_particle_api(n, mode, monkeypatch):
+@pytest.mark.parametrize("n", [1000, 300_000])
+def test_track_host_equals_particle_api(n):
     """sdk_track_host (host buffers in and out; chunked and pipelined over three streams for large
     batches) gives exactly what Particle(...).to_next_stop(...) gives -- as separate arrays, as 32-byte records,
-    and with the particles of every chunk cell-sorted on the device.  Both ways of cutting the call up: a pipeline of
-    whole chunks (mode 0) and one state with chunked upload / locate and a single advection launch (mode 1; "1s": the
-    records of a sorted run scattered into the caller's pinned buffer by the kernel)."""
+    and with the particles of every chunk cell-sorted on the device."""
     import ctypes as C
-
-    monkeypatch.setenv("SDK_TRACK_MODE", mode[0])
-    if mode.endswith("s"):
-        monkeypatch.setenv("SDK_TRACK_SCATTER", "1")
 
     import torch
 

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Experiment: (1) the timeline of one sdk_track_host call (SDK_TRACK_TIMELINE: CUDA events between the stages of every
+"""Experiment (EXP_MODES other than 0 need the library built from profiles/r02d_fed_queue_experiment.patch):
+(1) the timeline of one sdk_track_host call (SDK_TRACK_TIMELINE: CUDA events between the stages of every
 chunk) for the default chunking, with and without the device-side sort; (2) chunk-count sweep of sdk_interp_host on
 the configs[2] workload.  Prints to stdout / stderr; nothing here is a bench value."""
 
@@ -53,9 +54,11 @@ def track():
         os.environ.pop("SDK_TRACK_SCATTER", None)
         if mode.endswith("s"):
             os.environ["SDK_TRACK_SCATTER"] = "1"
+        if len(mode) > 1 and mode[1:].isdigit():
+            os.environ["SDK_TRACK_FEED_CTAS"] = mode[1:]  # "23" = mode 2 with 3 CTA slots for the fed launch
         for chunks in os.environ.get("EXP_CHUNKS", "3").split(","):
             os.environ["SDK_TRACK_CHUNKS"] = chunks
-            for sort in (0, 1):
+            for sort in ((0,) if mode[0] == "2" else (0, 1)):
                 os.environ.pop("SDK_TRACK_TIMELINE", None)
                 best, cross = call(sort)
                 print(f"mode {mode} chunks {chunks} sort {sort}: best {best:.3f} ms -> {cross / best / 1e6:.2f}e9 crossings/s", flush=True)
