@@ -15,6 +15,14 @@
 
 namespace sdk {
 
+// unroll factor of the loops over the stencil's nodes (1 = rolled; see the note above `struct Stencil`)
+#ifndef SDK_INTERP_UNROLL
+#define SDK_INTERP_UNROLL 1
+#endif
+#define SDK_STR2(x) #x
+#define SDK_STR(x) SDK_STR2(x)
+#define SDK_NODE_LOOP _Pragma(SDK_STR(unroll SDK_INTERP_UNROLL))
+
 __device__ __forceinline__ int rim_slot(int ny, int nx, int r, int dense, int iy, int ix) {
     if (dense) return iy * nx + ix;
     if (iy >= ny - r) return (iy - (ny - r)) * nx + ix;
@@ -24,35 +32,39 @@ __device__ __forceinline__ int rim_slot(int ny, int nx, int r, int dense, int iy
     return -1;
 }
 
-// Everything per point lives in registers: the loops over nodes are fully unrolled up to the
-// compile-time bound MAXM (9 covers the default 9-point cross, 3 x 3 squares and the particle
-// kernels; 32 is the general case), with `m < n_nodes` guards that cost a predicate each.
-template <int MAXM>
-struct NodeSet {
-    int32_t packed[MAXM];  // SDK_PACK(face, iy, ix), SDK_NODE_RAISES or SDK_NODE_LAST
-    uint8_t code[MAXM];    // bit0 other component, bit1 negative
+// The stencil of a point, node by node.  Away from the face edges a node is the cell plus the kernel's offset; cells closer
+// than `reach` to an edge read the host-built rim table (index and, for vectors, the component / sign code).
+//
+// The kernels below loop over the nodes instead of unrolling them into register arrays.  Round 2's profile of the unrolled
+// version (profiles/r02b_interp_*): 4000 static / 3460 executed warp instructions per 32 points, most of them index
+// arithmetic repeated per node and per field, the SM instruction cache missing 16 % of its requests and the GPC
+// instruction cache at 84 % of its request rate -- a kernel bound by instruction supply like K1, not by its gathers.
+// Rolled, the body is a few hundred instructions, per-node state lives in a handful of registers (more warps per SM to
+// hide the gathers' latency instead of more loads per thread), and the per-node work is done once for all the fields
+// that share it.  Sums run over the nodes in ascending order exactly as before: results are bit-identical.
+struct Stencil {
+    int f, iy, ix;
+    int slot;          // rim slot of the cell, -1 = interior
+    int64_t rim_base;  // first entry of the cell's row in the rim table
 };
 
-template <int MAXM>
-__device__ __forceinline__ void find_nodes(const GridDev &g, const sdk_kernel_desc &K, int f, int iy, int ix,
-                                           NodeSet<MAXM> &ns) {
-    const int slot = rim_slot(g.ny, g.nx, K.reach, K.rim_dense, iy, ix);
-    if (slot < 0 || K.rim == nullptr) {
-#pragma unroll
-        for (int m = 0; m < MAXM; ++m) {
-            ns.packed[m] = SDK_PACK(f, iy + K.dy[m], ix + K.dx[m]);
-            ns.code[m] = 0;
-        }
-        return;
-    }
+__device__ __forceinline__ Stencil stencil_of(const GridDev &g, const sdk_kernel_desc &K, int f, int iy, int ix) {
+    Stencil st;
+    st.f = f, st.iy = iy, st.ix = ix;
+    st.slot = K.rim ? rim_slot(g.ny, g.nx, K.reach, K.rim_dense, iy, ix) : -1;
     const int per_face = K.rim_dense ? g.ny * g.nx : 2 * K.reach * g.nx + 2 * K.reach * (g.ny - 2 * K.reach);
-    const int64_t base = ((int64_t)f * per_face + slot) * K.n_nodes;
-#pragma unroll
-    for (int m = 0; m < MAXM; ++m) {
-        const bool on = m < K.n_nodes;
-        ns.packed[m] = on ? __ldg(K.rim + base + m) : SDK_NODE_RAISES;
-        ns.code[m] = (on && K.rim_code) ? __ldg(K.rim_code + base + m) : 0;
+    st.rim_base = st.slot < 0 ? 0 : ((int64_t)f * per_face + st.slot) * K.n_nodes;
+    return st;
+}
+
+// node m: SDK_PACK(face, iy, ix), SDK_NODE_RAISES or SDK_NODE_LAST; code bit0 = other component, bit1 = negative
+__device__ __forceinline__ int node_of(const sdk_kernel_desc &K, const Stencil &st, int m, int &code) {
+    if (st.slot < 0) {
+        code = 0;
+        return SDK_PACK(st.f, st.iy + K.dy[m], st.ix + K.dx[m]);
     }
+    code = K.rim_code ? __ldg(K.rim_code + st.rim_base + m) : 0;
+    return __ldg(K.rim + st.rim_base + m);
 }
 
 // SDK_NODE_LAST: the reference walked off a closed box and indexes [-1, -1], numpy's last element
@@ -62,11 +74,15 @@ __device__ __forceinline__ int64_t plane_index(int packed, int nface, int fny, i
     return ((int64_t)f * fny + y) * fnx + x;
 }
 
-__device__ __forceinline__ double field_value(const GridDev &g, const sdk_field &F, int packed, int kz, int kt) {
+// element index of a node in a field at vertical / time level (kz, kt) -- the same for every field of that shape
+__device__ __forceinline__ int64_t field_index(const GridDev &g, const sdk_field &F, int packed, int kz, int kt) {
     int64_t lev = 0;
     if (F.has_time) lev = wrap_index(kt - F.it0, F.nt);
     if (F.has_z) lev = lev * F.nz + wrap_index(kz, F.nz);
-    const int64_t idx = lev * ((int64_t)g.nface * F.ny * F.nx) + plane_index(packed, g.nface, F.ny, F.nx);
+    return lev * ((int64_t)g.nface * F.ny * F.nx) + plane_index(packed, g.nface, F.ny, F.nx);
+}
+
+__device__ __forceinline__ double field_load(const sdk_field &F, int64_t idx) {
     const double v = F.dtype == SDK_F64 ? ldf<double>(F.data, idx) : ldf<float>(F.data, idx);
     return nan_to_num(v);
 }
@@ -86,8 +102,7 @@ __device__ __forceinline__ bool is_wet(const GridDev &g, const sdk_field &F, int
 
 // Lagrange weight of node m in one inheritance level: two polynomials A(rx), C(ry) (Horner on the
 // host-expanded coefficients; every lane of a warp that picked the same level reads the same
-// coefficients) combined as the node's mode says.  Evaluated on the fly inside the dot product: the
-// kernel is bound by the latency of its gathers, so registers (occupancy) matter more than ALU work.
+// coefficients) combined as the node's mode says.
 __device__ __forceinline__ double node_weight(const sdk_kernel_desc &K, int level, int m, double rx, double ry) {
     const int nc = K.n_coef;
     const double *ca = K.coef + ((int64_t)level * K.n_nodes + m) * 2 * nc, *cc = ca + nc;
@@ -104,83 +119,93 @@ __device__ __forceinline__ double node_weight(const sdk_kernel_desc &K, int leve
     return mode == SDK_W_A ? a : (mode == SDK_W_C ? c : (mode == SDK_W_A_PLUS_C ? a + c : a * c));
 }
 
-// One interpolated value.  P = field of the kernel's own component, O = the other component
-// (vectors on multi-face grids), both may be the same.
-template <int MAXM>
-__device__ __forceinline__ double interp_value(const GridDev &g, const sdk_kernel_desc &K, const sdk_field &P,
-                                               const sdk_field &O, const NodeSet<MAXM> &ns, double rxs, double rys, int kz0,
-                                               double rz, int kt0, double rt) {
+// the largest stencil of the inheritance whose nodes are all wet (reference find_which_points_for_each_kernel :481); -1: none
+__device__ __forceinline__ int pick_level(const sdk_kernel_desc &K, unsigned wet) {
+    int level = -1;
+    for (int l = K.n_levels - 1; l >= 0; --l)
+        if ((wet & K.level[l].node_mask) == K.level[l].node_mask) level = l;
+    return level;
+}
+
+// vertical factors of the two levels, and the ghost point below the bottom (reference kernel_weight.py:860-869):
+// `kill[j]` drops level j's sum (it counts as zero), `znan[j]` makes it NaN
+__device__ __forceinline__ void vertical_rule(const sdk_kernel_desc &K, double rz, bool two, double zw[2], bool znan[2], bool kill[2]) {
+    zw[0] = 1.0, zw[1] = 0.0;
+    kill[0] = kill[1] = false;
+    if (K.vmode == SDK_MODE_LINEAR) {
+        zw[0] = 1 - rz, zw[1] = rz;
+        if (two && K.bottom_no_flux && znan[0]) {
+            znan[0] = false, kill[0] = true;
+            if (rz < 0.5) znan[1] = false, kill[1] = true;
+            zw[1] = 1.0;
+        }
+    } else if (K.vmode == SDK_MODE_DERIV) {
+        zw[0] = -1.0, zw[1] = 1.0;
+    }
+}
+
+__device__ __forceinline__ double time_factor(const sdk_kernel_desc &K, int jt, double rt) {
+    return K.tmode == SDK_MODE_LINEAR ? (jt == 0 ? 1 - rt : rt) : (K.tmode == SDK_MODE_DERIV ? (jt == 0 ? -1.0 : 1.0) : 1.0);
+}
+
+// One interpolated value.  P = field of the kernel's own component, O = the other component (vectors on multi-face
+// grids; a node's wet flag and value come from the component the rim code names), both may be the same.
+// (out of line: the vector kernel calls it twice, and one copy of the body is all the instruction cache should hold)
+static __device__ __noinline__ double interp_value(const GridDev &g, const sdk_kernel_desc &K, const sdk_field &P, const sdk_field &O,
+                                                    int f, int iy, int ix, double rxs, double rys, int kz0, double rz, int kt0, double rt) {
+    const Stencil st = stencil_of(g, K, f, iy, ix);
     const int nz = K.vmode == SDK_MODE_NEAREST ? 1 : 2;
     const int nt = K.tmode == SDK_MODE_NEAREST ? 1 : 2;
     const bool use_mask = !K.ignore_mask && P.mask != nullptr;
+    // pass 1: wet flags of all nodes on both vertical levels (masks do not depend on time) -> the stencil of each level
+    int level[2] = {0, 0};
+    if (use_mask) {
+        unsigned wet[2] = {0u, 0u};
+SDK_NODE_LOOP
+        for (int m = 0; m < K.n_nodes; ++m) {
+            int code;
+            const int packed = node_of(K, st, m, code);
+            const sdk_field &F = (code & 1) ? O : P;
+            if (is_wet(g, F, packed, kz0)) wet[0] |= 1u << m;
+            if (nz == 2 && is_wet(g, F, packed, kz0 - 1)) wet[1] |= 1u << m;
+        }
+        level[0] = pick_level(K, wet[0]);
+        level[1] = nz == 2 ? pick_level(K, wet[1]) : 0;
+    }
+    bool znan[2] = {level[0] < 0, nz == 2 && level[1] < 0};
+    const unsigned use[2] = {znan[0] ? 0u : K.level[level[0]].node_mask, (nz < 2 || znan[1]) ? 0u : K.level[level[1]].node_mask};
+    // pass 2: value times weight, summed over the nodes of the level's stencil in node order, per (time, vertical) level
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};  // [jt][jz]
+SDK_NODE_LOOP
+    for (int m = 0; m < K.n_nodes; ++m) {
+        if (!((use[0] | use[1]) >> m & 1u)) continue;
+        int code;
+        const int packed = node_of(K, st, m, code);
+        const sdk_field &F = (code & 1) ? O : P;
+#pragma unroll
+        for (int jz = 0; jz < 2; ++jz) {
+            if (!(use[jz] >> m & 1u)) continue;
+            const double w = node_weight(K, level[jz], m, rxs, rys);
+#pragma unroll
+            for (int jt = 0; jt < 2; ++jt) {
+                if (jt >= nt) continue;
+                double v = NAN;
+                if (packed != SDK_NODE_RAISES) {
+                    v = field_load(F, field_index(g, F, packed, kz0 - jz, kt0 + jt));
+                    if (code & 2) v = -v;
+                }
+                acc[jt][jz] += v * w;
+            }
+        }
+    }
+    double zw[2];
+    bool kill[2];
+    vertical_rule(K, rz, nz == 2, zw, znan, kill);
     double total = 0.0;
-    // Per vertical level: the wet flags of all nodes and (speculatively) their values are requested
-    // together, so a point costs one round trip to memory instead of two; the values of nodes that
-    // the chosen (smaller) stencil does not use are simply dropped.  Masks do not depend on time.
-    int level_z[2] = {0, 0};
     for (int jt = 0; jt < nt; ++jt) {
-        const int kt = kt0 + jt;
-        const double tw = K.tmode == SDK_MODE_LINEAR ? (jt == 0 ? 1 - rt : rt) : (K.tmode == SDK_MODE_DERIV ? (jt == 0 ? -1.0 : 1.0) : 1.0);
-        double zsum[2] = {0.0, 0.0};
-        bool znan[2] = {false, false};
-        for (int jz = 0; jz < nz; ++jz) {
-            const int kz = kz0 - jz;
-            double val[MAXM];
-            unsigned wet = 0;
-#pragma unroll
-            for (int m = 0; m < MAXM; ++m) {
-                val[m] = 0.0;
-                if (m < K.n_nodes) {
-                    const bool other = ns.code[m] & 1;
-                    if (use_mask && jt == 0 && is_wet(g, other ? O : P, ns.packed[m], kz)) wet |= 1u << m;
-                    if (ns.packed[m] == SDK_NODE_RAISES) {
-                        val[m] = NAN;
-                    } else {
-                        const double v = field_value(g, other ? O : P, ns.packed[m], kz, kt);
-                        val[m] = (ns.code[m] & 2) ? -v : v;
-                    }
-                }
-            }
-            if (use_mask && jt == 0) {
-                // the largest stencil whose nodes are all wet (reference find_which_points_for_each_kernel :481)
-                int level = -1;
-                for (int l = K.n_levels - 1; l >= 0; --l)
-                    if ((wet & K.level[l].node_mask) == K.level[l].node_mask) level = l;
-                level_z[jz] = level;
-            }
-            const int level = level_z[jz];
-            if (level < 0) {
-                znan[jz] = true;  // weight[:, 0] = nan (reference :557-558)
-                continue;
-            }
-            const uint32_t mask = K.level[level].node_mask;
-            double acc = 0.0;
-#pragma unroll
-            for (int m = 0; m < MAXM; ++m)
-                if (m < K.n_nodes && (mask >> m & 1u)) acc += val[m] * node_weight(K, level, m, rxs, rys);
-            zsum[jz] = acc;
-        }
-        double zw0 = 1.0, zw1 = 0.0;
-        if (K.vmode == SDK_MODE_LINEAR) {
-            zw0 = 1 - rz;
-            zw1 = rz;
-            if (K.bottom_no_flux && znan[0]) {
-                // ghost point below the bottom (reference kernel_weight.py:860-869)
-                znan[0] = false;
-                zsum[0] = 0.0;
-                if (rz < 0.5) {
-                    zsum[1] = 0.0;
-                    znan[1] = false;
-                }
-                zw1 = 1.0;
-            }
-        } else if (K.vmode == SDK_MODE_DERIV) {
-            zw0 = -1.0;
-            zw1 = 1.0;
-        }
-        double part = znan[0] ? NAN : zsum[0] * zw0;
-        if (nz == 2) part += znan[1] ? NAN : zsum[1] * zw1;
-        total += part * tw;
+        double part = znan[0] ? NAN : (kill[0] ? 0.0 : acc[jt][0]) * zw[0];
+        if (nz == 2) part += znan[1] ? NAN : (kill[1] ? 0.0 : acc[jt][1]) * zw[1];
+        total += part * time_factor(K, jt, rt);
     }
     return total;
 }
@@ -189,34 +214,27 @@ __device__ __forceinline__ double interp_value(const GridDev &g, const sdk_kerne
 #define SDK_INTERP_MIN_BLOCKS 8
 #endif
 
-template <int MAXM>
-__global__ void __launch_bounds__(128, MAXM <= 9 ? SDK_INTERP_MIN_BLOCKS : 1) interp_scalar_kernel(const __grid_constant__ InterpArgs a) {
+__global__ void __launch_bounds__(128, SDK_INTERP_MIN_BLOCKS) interp_scalar_kernel(const __grid_constant__ InterpArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.pts.n) return;
     const sdk_points &p = a.pts;
-    const int f = p.face ? p.face[i] : 0, iy = p.iy[i], ix = p.ix[i];
-    NodeSet<MAXM> ns;
-    find_nodes<MAXM>(a.g, a.ku, f, iy, ix, ns);
     const double rxs = a.fu.xstag ? p.rx[i] + 0.5 : p.rx[i];
     const double rys = a.fu.ystag ? p.ry[i] + 0.5 : p.ry[i];
-    const double r = interp_value<MAXM>(a.g, a.ku, a.fu, a.fu, ns, rxs, rys, p.kz ? p.kz[i] : 0, p.rz ? p.rz[i] : 0.0,
-                                        p.kt ? p.kt[i] : 0, p.rt ? p.rt[i] : 0.0);
+    const double r = interp_value(a.g, a.ku, a.fu, a.fu, p.face ? p.face[i] : 0, p.iy[i], p.ix[i], rxs, rys, p.kz ? p.kz[i] : 0, p.rz ? p.rz[i] : 0.0, p.kt ? p.kt[i] : 0,
+                                  p.rt ? p.rt[i] : 0.0);
     a.out_u[p.out_index ? (int64_t)p.out_index[i] : i] = r;
 }
 
-template <int MAXM>
-__global__ void __launch_bounds__(128, MAXM <= 9 ? SDK_INTERP_MIN_BLOCKS : 1) interp_vector_kernel(const __grid_constant__ InterpArgs a) {
+__global__ void __launch_bounds__(128, SDK_INTERP_MIN_BLOCKS) interp_vector_kernel(const __grid_constant__ InterpArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.pts.n) return;
     const sdk_points &p = a.pts;
     const int f = p.face ? p.face[i] : 0, iy = p.iy[i], ix = p.ix[i];
     const int kz = p.kz ? p.kz[i] : 0, kt = p.kt ? p.kt[i] : 0;
     const double rz = p.rz ? p.rz[i] : 0.0, rt = p.rt ? p.rt[i] : 0.0;
-    NodeSet<MAXM> ns;
-    find_nodes<MAXM>(a.g, a.ku, f, iy, ix, ns);
-    double u = interp_value<MAXM>(a.g, a.ku, a.fu, a.fv, ns, p.rx[i] + 0.5, p.ry[i], kz, rz, kt, rt);
-    find_nodes<MAXM>(a.g, a.kv, f, iy, ix, ns);
-    double v = interp_value<MAXM>(a.g, a.kv, a.fv, a.fu, ns, p.rx[i], p.ry[i] + 0.5, kz, rz, kt, rt);
+    const double rx = p.rx[i], ry = p.ry[i];
+    double u = interp_value(a.g, a.ku, a.fu, a.fv, f, iy, ix, rx + 0.5, ry, kz, rz, kt, rt);
+    double v = interp_value(a.g, a.kv, a.fv, a.fu, f, iy, ix, rx, ry + 0.5, kz, rz, kt, rt);
     if (a.vec_transform) {
         const double cs = (double)p.cs[i], sn = (double)p.sn[i];
         const double uu = u * cs - v * sn, vv = u * sn + v * cs;
@@ -228,88 +246,85 @@ __global__ void __launch_bounds__(128, MAXM <= 9 ? SDK_INTERP_MIN_BLOCKS : 1) in
     a.out_v[o] = v;
 }
 
-// Several scalar variables at once (T and S with one KnW, say): node indices, wet flags, the choice of the stencil and
-// the Lagrange weights depend on the points and the kernel only -- they are worked out once, as a weight per node and
-// vertical level, and every field then costs its gathers and a dot product.  TWO: vertical or temporal kernels with two
-// nodes (otherwise the second set of weights does not exist and takes no registers).
-template <int MAXM, bool TWO>
-__global__ void __launch_bounds__(128, MAXM <= 9 ? (TWO ? 4 : 6) : 1) interp_scalar_multi_kernel(const __grid_constant__ InterpMultiArgs a) {
+// Several scalar variables at once (T and S with one KnW, say): wet flags, the choice of the stencil, the Lagrange weight
+// and the element index of a node depend on the points and the kernel only -- they are worked out once per node, and every
+// field then costs one gather and one multiply-add.  TWO: vertical or temporal kernels with two nodes (otherwise the
+// second set of sums does not exist and takes no registers).
+template <bool TWO>
+__global__ void __launch_bounds__(128, TWO ? 6 : SDK_INTERP_MIN_BLOCKS) interp_scalar_multi_kernel(const __grid_constant__ InterpMultiArgs a) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.pts.n) return;
     const sdk_points &p = a.pts;
     const sdk_kernel_desc &K = a.k;
     const sdk_field &F0 = a.f[0];
-    const int f = p.face ? p.face[i] : 0, iy = p.iy[i], ix = p.ix[i];
-    NodeSet<MAXM> ns;
-    find_nodes<MAXM>(a.g, K, f, iy, ix, ns);
+    const Stencil st = stencil_of(a.g, K, p.face ? p.face[i] : 0, p.iy[i], p.ix[i]);
     const double rxs = F0.xstag ? p.rx[i] + 0.5 : p.rx[i];
     const double rys = F0.ystag ? p.ry[i] + 0.5 : p.ry[i];
     const int kz0 = p.kz ? p.kz[i] : 0, kt0 = p.kt ? p.kt[i] : 0;
     const double rz = p.rz ? p.rz[i] : 0.0, rt = p.rt ? p.rt[i] : 0.0;
+    constexpr int N2 = TWO ? 2 : 1;
     const int nz = (TWO && K.vmode != SDK_MODE_NEAREST) ? 2 : 1;
     const int nt = (TWO && K.tmode != SDK_MODE_NEAREST) ? 2 : 1;
     const bool use_mask = !K.ignore_mask && F0.mask != nullptr;
-    constexpr int NZ = TWO ? 2 : 1;
-    double w[NZ][MAXM];
-    uint32_t use[NZ];  // nodes of the stencil chosen for this vertical level
-    bool znan[NZ];
-#pragma unroll
-    for (int jz = 0; jz < NZ; ++jz) {
-        znan[jz] = false;
-        int level = 0;
-        if (jz < nz && use_mask) {
-            unsigned wet = 0;
-#pragma unroll
-            for (int m = 0; m < MAXM; ++m)
-                if (m < K.n_nodes && is_wet(a.g, F0, ns.packed[m], kz0 - jz)) wet |= 1u << m;
-            level = -1;
-            for (int l = K.n_levels - 1; l >= 0; --l)
-                if ((wet & K.level[l].node_mask) == K.level[l].node_mask) level = l;
+    int level[2] = {0, 0};
+    if (use_mask) {
+        unsigned wet[2] = {0u, 0u};
+SDK_NODE_LOOP
+        for (int m = 0; m < K.n_nodes; ++m) {
+            int code;
+            const int packed = node_of(K, st, m, code);
+            if (is_wet(a.g, F0, packed, kz0)) wet[0] |= 1u << m;
+            if (TWO && nz == 2 && is_wet(a.g, F0, packed, kz0 - 1)) wet[1] |= 1u << m;
         }
-        znan[jz] = level < 0;
-        const uint32_t mask = (level < 0 || jz >= nz) ? 0u : K.level[level].node_mask;
-        use[jz] = mask;
-#pragma unroll
-        for (int m = 0; m < MAXM; ++m) w[jz][m] = (m < K.n_nodes && (mask >> m & 1u)) ? node_weight(K, level, m, rxs, rys) : 0.0;
+        level[0] = pick_level(K, wet[0]);
+        level[1] = nz == 2 ? pick_level(K, wet[1]) : 0;
     }
-    // vertical factors and the ghost point below the bottom (same rule as interp_value)
-    double zw[2] = {1.0, 0.0};
-    bool kill[2] = {false, false};
-    if (K.vmode == SDK_MODE_LINEAR) {
-        zw[0] = 1 - rz, zw[1] = rz;
-        if (TWO && K.bottom_no_flux && znan[0]) {
-            znan[0] = false, kill[0] = true;
-            if (rz < 0.5) znan[NZ - 1] = false, kill[1] = true;
-            zw[1] = 1.0;
-        }
-    } else if (K.vmode == SDK_MODE_DERIV) {
-        zw[0] = -1.0, zw[1] = 1.0;
-    }
-    const int64_t o = p.out_index ? (int64_t)p.out_index[i] : i;
-    for (int k = 0; k < a.n_fields; ++k) {
-        const sdk_field &F = a.f[k];
-        double total = 0.0;
-        for (int jt = 0; jt < nt; ++jt) {
-            const double tw = K.tmode == SDK_MODE_LINEAR ? (jt == 0 ? 1 - rt : rt) : (K.tmode == SDK_MODE_DERIV ? (jt == 0 ? -1.0 : 1.0) : 1.0);
-            double part = 0.0;
+    bool znan[2] = {level[0] < 0, nz == 2 && level[1] < 0};
+    const unsigned use[2] = {znan[0] ? 0u : K.level[level[0]].node_mask, (nz < 2 || znan[1]) ? 0u : K.level[level[1]].node_mask};
+    double acc[SDK_MAX_MULTI_FIELDS][N2][N2];  // [field][jt][jz]
 #pragma unroll
-            for (int jz = 0; jz < NZ; ++jz) {
-                if (jz >= nz) continue;
-                double acc = 0.0;
-                if (!kill[jz]) {
+    for (int k = 0; k < SDK_MAX_MULTI_FIELDS; ++k)
 #pragma unroll
-                    for (int m = 0; m < MAXM; ++m) {
-                        // (same expression as the single-field kernel: value times weight, summed over the stencil's nodes
-                        // in node order; nodes outside the chosen stencil are not read)
-                        if (m < K.n_nodes && (use[jz] >> m & 1u)) {
-                            const double v = ns.packed[m] == SDK_NODE_RAISES ? NAN : field_value(a.g, F, ns.packed[m], kz0 - jz, kt0 + jt);
-                            acc += v * w[jz][m];
-                        }
-                    }
+        for (int jt = 0; jt < N2; ++jt)
+#pragma unroll
+            for (int jz = 0; jz < N2; ++jz) acc[k][jt][jz] = 0.0;
+SDK_NODE_LOOP
+    for (int m = 0; m < K.n_nodes; ++m) {
+        if (!((use[0] | use[1]) >> m & 1u)) continue;
+        int code;
+        const int packed = node_of(K, st, m, code);
+#pragma unroll
+        for (int jz = 0; jz < N2; ++jz) {
+            if (!(use[jz] >> m & 1u)) continue;
+            const double w = node_weight(K, level[jz], m, rxs, rys);
+#pragma unroll
+            for (int jt = 0; jt < N2; ++jt) {
+                if (jt >= nt) continue;
+                // (the fields share shape, staggering and time / vertical layout: one index for all of them)
+                const int64_t idx = packed == SDK_NODE_RAISES ? 0 : field_index(a.g, F0, packed, kz0 - jz, kt0 + jt);
+#pragma unroll
+                for (int k = 0; k < SDK_MAX_MULTI_FIELDS; ++k) {
+                    if (k >= a.n_fields) continue;
+                    const double v = packed == SDK_NODE_RAISES ? NAN : field_load(a.f[k], idx);
+                    acc[k][jt][jz] += v * w;
                 }
-                part += znan[jz] ? NAN : acc * zw[jz];
             }
-            total += part * tw;
+        }
+    }
+    double zw[2];
+    bool kill[2];
+    vertical_rule(K, rz, TWO, zw, znan, kill);
+    const int64_t o = p.out_index ? (int64_t)p.out_index[i] : i;
+#pragma unroll
+    for (int k = 0; k < SDK_MAX_MULTI_FIELDS; ++k) {
+        if (k >= a.n_fields) continue;
+        double total = 0.0;
+#pragma unroll
+        for (int jt = 0; jt < N2; ++jt) {
+            if (jt >= nt) continue;
+            double part = znan[0] ? NAN : (kill[0] ? 0.0 : acc[k][jt][0]) * zw[0];
+            if (nz == 2) part += znan[1] ? NAN : (kill[1] ? 0.0 : acc[k][jt][N2 - 1]) * zw[1];
+            total += part * time_factor(K, jt, rt);
         }
         a.out[k][o] = total;
     }
@@ -350,14 +365,8 @@ cudaError_t launch_interp(const InterpArgs &a, bool vector, cudaStream_t s) {
     if (a.pts.n == 0) return cudaSuccess;
     const int threads = 128;
     const unsigned blocks = (unsigned)((a.pts.n + threads - 1) / threads);
-    const bool small = a.ku.n_nodes <= 9 && (!vector || a.kv.n_nodes <= 9);
-    if (vector) {
-        if (small) interp_vector_kernel<9><<<blocks, threads, 0, s>>>(a);
-        else interp_vector_kernel<SDK_MAX_NODES><<<blocks, threads, 0, s>>>(a);
-    } else {
-        if (small) interp_scalar_kernel<9><<<blocks, threads, 0, s>>>(a);
-        else interp_scalar_kernel<SDK_MAX_NODES><<<blocks, threads, 0, s>>>(a);
-    }
+    if (vector) interp_vector_kernel<<<blocks, threads, 0, s>>>(a);
+    else interp_scalar_kernel<<<blocks, threads, 0, s>>>(a);
     return cudaGetLastError();
 }
 
@@ -365,14 +374,8 @@ cudaError_t launch_interp_multi(const InterpMultiArgs &a, cudaStream_t s) {
     if (a.pts.n == 0) return cudaSuccess;
     const int threads = 128;
     const unsigned blocks = (unsigned)((a.pts.n + threads - 1) / threads);
-    const bool two = a.k.vmode != SDK_MODE_NEAREST || a.k.tmode != SDK_MODE_NEAREST;
-    if (a.k.n_nodes <= 9) {
-        if (two) interp_scalar_multi_kernel<9, true><<<blocks, threads, 0, s>>>(a);
-        else interp_scalar_multi_kernel<9, false><<<blocks, threads, 0, s>>>(a);
-    } else {
-        if (two) interp_scalar_multi_kernel<SDK_MAX_NODES, true><<<blocks, threads, 0, s>>>(a);
-        else interp_scalar_multi_kernel<SDK_MAX_NODES, false><<<blocks, threads, 0, s>>>(a);
-    }
+    if (a.k.vmode != SDK_MODE_NEAREST || a.k.tmode != SDK_MODE_NEAREST) interp_scalar_multi_kernel<true><<<blocks, threads, 0, s>>>(a);
+    else interp_scalar_multi_kernel<false><<<blocks, threads, 0, s>>>(a);
     return cudaGetLastError();
 }
 
