@@ -62,6 +62,22 @@ constexpr unsigned kQueueSlots = 64;
 constexpr int kTrackChunks = 3;
 constexpr int kTrackChunksMax = 32;
 
+// +1 / -1 when the n floats of a DEVICE table are strictly ascending / descending, else 0
+static int table_order(const float *dev, int n) {
+    if (!dev || n < 2) return 0;
+    std::vector<float> h((size_t)n);
+    if (cudaMemcpy(h.data(), dev, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    bool up = true, down = true;
+    for (int k = 1; k < n; ++k) {
+        up = up && h[k] > h[k - 1];
+        down = down && h[k] < h[k - 1];
+    }
+    return up ? 1 : (down ? -1 : 0);
+}
+
 struct sdk_grid {
     sdk::GridDev dev;
     int sm_count;
@@ -145,6 +161,9 @@ int sdk_grid_create(const sdk_grid_desc *d, sdk_grid **out) {
         delete g;
         return fail(SDK_ECUDA, "sdk_grid_create: no CUDA device");
     }
+    // strictly monotonic vertical tables are searched by bisection (locate.cu: nearest_index)
+    v.z_order = table_order(d->Z, d->n_zc);
+    v.zl_order = table_order(d->Zl, d->n_zl);
     g->next_queue = 0;
     g->has_pipe = false;
     cudaError_t e = cudaMalloc(&g->queue, kQueueSlots * sizeof(unsigned long long));

@@ -153,10 +153,12 @@ __device__ __forceinline__ bool cell_at_offset(const GridDev &g, int f, int iy, 
     return true;
 }
 
-// reference find_rel (utils.py:321) with find_ind (utils.py:273) for a 1-D table in shared/global
-__device__ __forceinline__ void find_rel_1d(const float *arr, const float *darr, int n, int n_d,
-                                            double x, int ascending, bool above, bool dx_right,
-                                            int &idx, double &r, double &d, double &b, int &status) {
+// np.argmin(np.abs(arr - x)) (find_ind, utils.py:273): the first of the nearest entries.  `order` = +1 / -1 for a strictly
+// ascending / descending table (GridDev::z_order), which is then bisected: the distance falls, then rises, so the minimum
+// is one of the two entries around x -- the lower index on a tie, as argmin has it; before the table it is entry 0, past
+// its end the last entry.  Anything unusual (unsorted table, NaN, a value further past the end than the table is long,
+// where rounding could make distant entries tie) takes the scan.
+static __device__ __noinline__ int nearest_index_scan(const float *arr, int n, double x) {
     int best = 0;
     double bestv = INFINITY;
     for (int k = 0; k < n; ++k) {
@@ -166,6 +168,33 @@ __device__ __forceinline__ void find_rel_1d(const float *arr, const float *darr,
             best = k;
         }
     }
+    return best;
+}
+
+__device__ __forceinline__ int nearest_index(const float *arr, int n, double x, int order) {
+    if (order != 0 && x == x) {
+        const double s = (double)order, sx = s * x;
+        const double first = s * (double)arr[0], last = s * (double)arr[n - 1];
+        if (sx < first) return 0;
+        if (sx < last) {
+            int lo = 0, hi = n - 1;  // s * arr[lo] <= sx < s * arr[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s * (double)arr[mid] <= sx) lo = mid;
+                else hi = mid;
+            }
+            return fabs((double)arr[hi] - x) < fabs((double)arr[lo] - x) ? hi : lo;
+        }
+        if (sx - last <= last - first) return n - 1;
+    }
+    return nearest_index_scan(arr, n, x);
+}
+
+// reference find_rel (utils.py:321) with find_ind (utils.py:273) for a 1-D table in shared/global
+__device__ __forceinline__ void find_rel_1d(const float *arr, const float *darr, int n, int n_d,
+                                            double x, int ascending, bool above, bool dx_right,
+                                            int &idx, double &r, double &d, double &b, int &status, int order = 0) {
+    int best = nearest_index(arr, n, x, order);
     if (above && (double)arr[best] > x) best -= ascending;
     if (best < 0 || best > n - 1) status |= SDK_ST_OOB;  // reference raises "Value out of bound."
     best = min(max(best, 0), n - 1);
@@ -282,11 +311,12 @@ __global__ void cell_wide_kernel(GridDev g, const double *cxyz, unsigned char *w
 struct Nearest {
     double d2;
     int f, iy, ix;
+    bool hole;  // scan_neighbours_cold: one of the cells looked at has no centre (NaN coordinates)
 };
 
 static __device__ __noinline__ Nearest confirm_rings(const GridDev &g, const double *cxyz, int f, int iy, int ix, double qx, double qy,
                                                      double qz, double best, bool hole) {
-    Nearest r = {best, f, iy, ix};
+    Nearest r = {best, f, iy, ix, false};
 #ifndef SDK_LOCATE_INTERIOR
 #define SDK_LOCATE_INTERIOR 1
 #endif
@@ -305,7 +335,7 @@ static __device__ __noinline__ Nearest confirm_rings(const GridDev &g, const dou
             const double ex = __ldg(cxyz + 3 * c) - qx, ey = __ldg(cxyz + 3 * c + 1) - qy, ez = __ldg(cxyz + 3 * c + 2) - qz;
             const double dd = ex * ex + ey * ey + ez * ez;
             hole |= !(dd < INFINITY);
-            if (dd < r.d2) r = {dd, f, iy + dy, ix + dx};
+            if (dd < r.d2) r = {dd, f, iy + dy, ix + dx, false};
         }
     }
     for (int ring = inside ? 3 : 2; ring <= ((hole && SDK_LOCATE_MAXRING >= 3) ? 3 : (SDK_LOCATE_MAXRING >= 2 ? 2 : 0)); ++ring) {
@@ -316,9 +346,29 @@ static __device__ __noinline__ Nearest confirm_rings(const GridDev &g, const dou
                 if (!cell_at_offset(g, f, iy, ix, dy, dx, nf, ny, nx)) continue;
                 const double dd = dist2_to_cell(g, cxyz, nf, ny, nx, qx, qy, qz);
                 hole |= !(dd < INFINITY);
-                if (dd < r.d2) r = {dd, nf, ny, nx};
+                if (dd < r.d2) r = {dd, nf, ny, nx, false};
             }
         }
+    }
+    return r;
+}
+
+// The 8 neighbours of a cell next to a face edge (or of any cell when there is no centre table): one or two cell moves
+// each, across faces where need be.  Out of line and rolled (the two moves of neighbour k are packed two bits each):
+// only a few per cent of the cells come here, and the walk's loop should not carry eight inlined copies of cell_move.
+static __device__ __noinline__ Nearest scan_neighbours_cold(const GridDev &g, const double *cxyz, int f, int iy, int ix, double qx, double qy,
+                                                            double qz, double best) {
+    Nearest r = {best, f, iy, ix, false};
+#pragma unroll 1
+    for (int k = 0; k < 8; ++k) {
+        const int d1 = (int)(0x50E4u >> (2 * k) & 3u);                       // {0, 1, 2, 3, 0, 0, 1, 1}
+        const int d2 = k < 4 ? -1 : (int)(0xEEu >> (2 * (k - 4)) & 3u);      // {-, -, -, -, 2, 3, 2, 3}
+        int nf, ny, nx;
+        if (!neighbour(g, f, iy, ix, d1, d2, nf, ny, nx)) continue;
+        const double dd = dist2_to_cell(g, cxyz, nf, ny, nx, qx, qy, qz);
+        const bool hole = r.hole || !(dd < INFINITY);
+        if (dd < r.d2) r = {dd, nf, ny, nx, false};
+        r.hole = hole;
     }
     return r;
 }
@@ -371,20 +421,27 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
             int bf = f, by = iy, bx = ix;
             double bd = best;
             bool near_hole = false;
-            const int d1s[8] = {0, 1, 2, 3, 0, 0, 1, 1};
-            const int d2s[8] = {-1, -1, -1, -1, 2, 3, 2, 3};
+            if (cxyz && iy >= 1 && iy < g.ny - 1 && ix >= 1 && ix < g.nx - 1) {
+                // away from the face edges the 8 neighbours are index offsets into the centre table -- in the order of
+                // the general scan (up, down, left, right, up-left, up-right, down-left, down-right: ties go to the first)
+                const int64_t c0 = ((int64_t)f * g.ny + iy) * g.nx + ix;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                int nf, ny, nx;
-                if (!neighbour(g, f, iy, ix, d1s[k], d2s[k], nf, ny, nx)) continue;
-                const double dd = dist2_to_cell(g, cxyz, nf, ny, nx, qx, qy, qz);
-                near_hole |= !(dd < INFINITY);
-                if (dd < bd) {
-                    bd = dd;
-                    bf = nf;
-                    by = ny;
-                    bx = nx;
+                for (int k = 0; k < 8; ++k) {
+                    const int dy = (k == 0 || k == 4 || k == 5) ? 1 : ((k == 1 || k == 6 || k == 7) ? -1 : 0);
+                    const int dx = (k == 3 || k == 5 || k == 7) ? 1 : ((k == 2 || k == 4 || k == 6) ? -1 : 0);
+                    const int64_t c = c0 + dy * g.nx + dx;
+                    const double ex = __ldg(cxyz + 3 * c) - qx, ey = __ldg(cxyz + 3 * c + 1) - qy, ez = __ldg(cxyz + 3 * c + 2) - qz;
+                    const double dd = ex * ex + ey * ey + ez * ez;
+                    near_hole |= !(dd < INFINITY);
+                    if (dd < bd) {
+                        bd = dd;
+                        by = iy + dy;
+                        bx = ix + dx;
+                    }
                 }
+            } else {
+                const Nearest nb = scan_neighbours_cold(g, cxyz, f, iy, ix, qx, qy, qz, best);
+                bd = nb.d2, bf = nb.f, by = nb.iy, bx = nb.ix, near_hole = nb.hole;
             }
             if (bd >= best) {
                 // the walk has stopped: where the grid is sheared (or has holes) look further out once
@@ -449,23 +506,23 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
         int k;
         double r, d, b;
         if (g.n_zc > 1 && o.iz) {  // _find_rel_v: nearest Z
-            find_rel_1d(g.Z, nullptr, g.n_zc, 0, z, 1, false, true, k, r, d, b, status);
+            find_rel_1d(g.Z, nullptr, g.n_zc, 0, z, 1, false, true, k, r, d, b, status, g.z_order);
             o.iz[i] = k; o.rz[i] = r; o.dz[i] = d; o.bz[i] = b;
         }
         if (g.n_zc > 1 && o.iz_lin) {  // _find_rel_v_lin: find_rel_z(z, Z, dZ) -> ascending=-1, dx_right=False
             int st = 0;
-            find_rel_1d(g.Z, g.dZ, g.n_zc, g.n_zc, z, -1, true, false, k, r, d, b, st);
+            find_rel_1d(g.Z, g.dZ, g.n_zc, g.n_zc, z, -1, true, false, k, r, d, b, st, g.z_order);
             if (st) status |= SDK_ST_OOB_Z;
             o.iz_lin[i] = k; o.rz_lin[i] = r; o.dz_lin[i] = d; o.bz_lin[i] = b;
         }
         if (g.n_zl > 1) {
             if (o.izl_near) {  // _find_rel_vl: nearest Zl
-                find_rel_1d(g.Zl, nullptr, g.n_zl, 0, z, 1, false, true, k, r, d, b, status);
+                find_rel_1d(g.Zl, nullptr, g.n_zl, 0, z, 1, false, true, k, r, d, b, status, g.zl_order);
                 o.izl_near[i] = k; o.rzl_near[i] = r; o.dzl_near[i] = d; o.bzl_near[i] = b;
             }
             // _find_rel_vl_lin: find_rel_z(z, Zl, dZl, dz_above_z=False) -> ascending=-1, dx_right=True
             if (o.izl) {
-                find_rel_1d(g.Zl, g.dZl, g.n_zl, g.n_z, z, -1, true, true, k, r, d, b, status);
+                find_rel_1d(g.Zl, g.dZl, g.n_zl, g.n_z, z, -1, true, true, k, r, d, b, status, g.zl_order);
                 o.izl[i] = k; o.rzl[i] = r; o.dzl[i] = d; o.bzl[i] = b;
             }
         }
@@ -497,7 +554,7 @@ __global__ void __launch_bounds__(256) point_key_kernel(GridDev g, BucketGrid b,
     if (dep && g.n_zl > 1) {
         int k, st = 0;
         double r, d, bb;
-        find_rel_1d(g.Zl, g.dZl, g.n_zl, g.n_z, dep[i], -1, true, true, k, r, d, bb, st);
+        find_rel_1d(g.Zl, g.dZl, g.n_zl, g.n_z, dep[i], -1, true, true, k, r, d, bb, st, g.zl_order);
         level = (uint64_t)k;
     }
     const double x = lon[i], y = lat[i];

@@ -29,6 +29,8 @@ struct GridDev {
     const float *lon1, *lat1, *coslat32;
     const double *dlon, *dlat;
     int dlon_is_f32;
+    // +1 / -1: the vertical table is strictly ascending / descending (looked up by bisection), 0: it is not (linear scan)
+    int z_order, zl_order;
 };
 
 struct VelDev {
