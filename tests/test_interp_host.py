@@ -82,3 +82,59 @@ def test_weight_polynomials_equal_stencil_weights(spec):
             pc = np.polynomial.polynomial.polyval(ry, c)
             w = {interp.W_A: pa, interp.W_C: pc, interp.W_A_PLUS_C: pa + pc, interp.W_A_TIMES_C: pa * pc}[mode]
             np.testing.assert_allclose(w, ref[:, j], rtol=1e-12, atol=1e-13)
+
+
+def test_launch_plan_groups_scalars_and_keeps_the_nesting():
+    """``_plan`` (what has to be launched for a request) and ``_assemble`` (results back in the request's nesting):
+    scalars that share kernel, grid position and dtype go into one multi-field launch of at most four, a repeated
+    (variable, kernel) pair is computed once, vectors stay whole on grids with faces and split without."""
+    import seaduck_b200 as sd
+
+    ds = synthetic.llc(n=8, nz=3, tracers=True)
+    od = sd.OceData(ds)
+    k1, k2 = KnW(), KnW(vkernel="linear")
+    uk, vk = ci.make_knw(KnW, (ci.UKNW, ci.VKNW))
+    var = ["T", "S", ("UVELMASS", "VVELMASS"), "T", "S"]
+    knw = [k1, k1, (uk, vk), k2, k1]
+    single, v, k, pre, prefix = interp._broadcast_inputs(None, list(var), list(knw), None, None)
+    assert not single
+    plan = interp._plan(od, True, v, k, pre, prefix)
+    kinds = [(kind, names) for _, kind, names, *_ in plan]
+    assert kinds == [("m", ["T", "S"]), ("v", ("UVELMASS", "VVELMASS")), ("s", "T")]
+    final = {}
+    for keys, kind, names, kernels, _, _ in plan:
+        for key in keys:
+            final[key] = ("result", key[0] if kind != "v" else names)
+    out = interp._assemble(final, v, k, True, single)
+    assert [o[1] for o in out] == ["T", "S", ("UVELMASS", "VVELMASS"), "T", "S"]
+    assert out[0] is out[0] and out[1] is out[4]  # the repeated (S, k1) request is answered by the same launch
+    # without faces a vector is two scalar jobs on staggered grids
+    plan2 = interp._plan(od, False, [("UVELMASS", "VVELMASS")], [(k1, k1)], [None], [None])
+    assert [kind for _, kind, *_ in plan2] == ["s", "s"]
+    tup = interp._assemble({("UVELMASS", k1): 1, ("VVELMASS", k1): 2}, [("UVELMASS", "VVELMASS")], [(k1, k1)], False, True)
+    assert tup == (1, 2)
+    # five scalars with one kernel: one launch of four and one single
+    plan3 = interp._plan(od, True, ["T", "S", "maskC", "T", "S"], [k1] * 5, [None] * 5, [None] * 5)
+    assert [kind for _, kind, *_ in plan3][:1] == ["m"] and sum(len(keys) for keys, *_ in plan3) == 3
+
+
+def test_index_family_selectors_follow_the_kernel():
+    """Which of sdk_locate's index families a variable reads in the host pipeline: Z or Zl by the variable's dims, nearest
+    or linear by the kernel's vkernel / tkernel -- and the reference's complaints when the points lack the coordinate."""
+    import seaduck_b200 as sd
+
+    od = sd.OceData(synthetic.llc(n=8, nz=3, nt=3, tracers=True))
+    sel = interp._vertical_time_selectors
+    tdims = od["T"].dims
+    wdims = od["WVELMASS"].dims
+    assert sel(od, tdims, KnW(), True, True) == (interp.SEL_Z, interp.SEL_T)
+    assert sel(od, tdims, KnW(vkernel="linear", tkernel="dt"), True, True) == (interp.SEL_Z_LIN, interp.SEL_T_LIN)
+    assert sel(od, wdims, KnW(vkernel="dz"), True, True) == (interp.SEL_ZL_LIN, interp.SEL_T)
+    assert sel(od, wdims, KnW(), True, True)[0] == interp.SEL_ZL
+    assert sel(od, ("face", "Y", "X"), KnW(), False, False) == (interp.SEL_NONE, interp.SEL_NONE)
+    with pytest.raises(ValueError, match="no depth"):
+        sel(od, tdims, KnW(), False, True)
+    with pytest.raises(ValueError, match="no time"):
+        sel(od, tdims, KnW(), True, False)
+    with pytest.raises(ValueError, match="vkernel"):
+        sel(od, tdims, type("K", (), {"vkernel": "cubic", "tkernel": "nearest"})(), True, True)
