@@ -666,7 +666,7 @@ def run_stops(ctx, a, grid, particles, hours, nt=3):
         kern_ms.append(e0.elapsed_time(e1))
         kern_cross.append(int(stats[1].item()))
     out["clocks"] = sampler.finish()
-    out["roofline"] = roofline_of("advect_kernel<double,false,0>", float(np.mean(kern_ms)), float(np.mean(kern_cross)), n, "f64", False)
+    out["roofline"] = roofline_of("advect_kernel<double,false,3>", float(np.mean(kern_ms)), float(np.mean(kern_cross)), n, "f64", False)
     return out
 
 

@@ -206,6 +206,14 @@ int sdk_grid_destroy(sdk_grid *grid);
 int sdk_advect(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, double t_stop,
                const sdk_advect_params *par, const sdk_log *log, int commit, void *stream);
 
+/* Which compile-time variant of the advection kernel sdk_advect would launch for these arguments (no launch, no device
+ * access; no reference counterpart -- the reference has one numpy code path): 0 = every switch read from the arguments,
+ * 1 = LLC faces + depth + vertical velocity + volume transports (BASELINE.json configs[1]), 2 = the horizontal schemes
+ * without corner points (local_cartesian, rectilinear), 3 = LLC surface run with 2-D transports (configs[3]).  All variants
+ * give bit-identical results (tests/test_gpu_parity.py); negative = SDK_E* error. */
+int sdk_advect_profile(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, const sdk_advect_params *par,
+                       const sdk_log *log);
+
 /* Particle.get_u_du alone, seaduck/lagrangian.py:218 (after a velocity-slab swap). */
 int sdk_get_u_du(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, int has_dep,
                  void *stream);

@@ -224,6 +224,7 @@ def lib():
         L.sdk_advect.argtypes = [vp, C.POINTER(Velocity), C.POINTER(Particles), C.c_double, C.POINTER(AdvectParams), C.POINTER(Log), C.c_int, vp]
         L.sdk_advect_host.argtypes = [vp, C.POINTER(Velocity), C.POINTER(Particles), C.c_double, C.POINTER(AdvectParams), vp, vp]
         L.sdk_get_u_du.argtypes = [vp, C.POINTER(Velocity), C.POINTER(Particles), C.c_int, vp]
+        L.sdk_advect_profile.argtypes = [vp, C.POINTER(Velocity), C.POINTER(Particles), C.POINTER(AdvectParams), C.POINTER(Log)]
         L.sdk_grid_build_locator.argtypes = [vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32, C.c_int32, vp]
         L.sdk_locate.argtypes = [vp, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, C.POINTER(Located), vp]
         L.sdk_time_index.argtypes = [vp, vp, C.c_int32, vp, C.c_int64, vp]

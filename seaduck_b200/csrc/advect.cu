@@ -100,7 +100,10 @@ __host__ __device__ inline size_t advect_smem_bytes(int n_zl, int n_z, int threa
 #endif
 // Profile 2 is profile 0 for the horizontal schemes without corner points (local_cartesian, rectilinear:
 // reference lagrangian.py:647-673, :693-704 and rel2latlon utils.py:214): px / py carry bx, cs, dx / by, sn, dy.
+// Profile 3 is the other production case, the surface run of the LLC4320 notebook (BASELINE.json configs[3]): LLC faces,
+// volume transports, no depth, no vertical velocity, fields and volumes without a vertical axis.
 #define SDK_KNOWN(P, fixed_value, runtime_expr) ((P) == 1 ? (fixed_value) : (runtime_expr))
+#define SDK_KNOWN3(P, value_1, value_3, runtime_expr) ((P) == 1 ? (value_1) : ((P) == 3 ? (value_3) : (runtime_expr)))
 
 // sic: lagrangian.py:22, utils.py:306 (6271 km)
 #define SDK_DEG2M (6271e3 * 3.141592653589793 / 180)
@@ -122,15 +125,15 @@ __device__ __forceinline__ void load_lane(const sdk_particles &p, int64_t i, int
         s.px[j] = p.px[j * p.n + i];
         s.py[j] = p.py[j * p.n + i];
     }
-    s.f = SDK_KNOWN(P, true, p.face != nullptr) ? p.face[i] : 0;
+    s.f = SDK_KNOWN3(P, true, true, p.face != nullptr) ? p.face[i] : 0;
     s.iy = p.iy[i];
     s.ix = p.ix[i];
     s.it = p.it ? p.it[i] : 0;
     // (with transports everything is scaled by the cell volume, dx and dy are never read)
-    s.dx = SDK_KNOWN(P, false, p.dx != nullptr) ? p.dx[i] : 1.0f;
-    s.dy = SDK_KNOWN(P, false, p.dy != nullptr) ? p.dy[i] : 1.0f;
-    s.vol = SDK_KNOWN(P, true, p.vol != nullptr) ? p.vol[i] : 1.0;
-    if (SDK_KNOWN(P, true, has_dep != 0)) {
+    s.dx = SDK_KNOWN3(P, false, false, p.dx != nullptr) ? p.dx[i] : 1.0f;
+    s.dy = SDK_KNOWN3(P, false, false, p.dy != nullptr) ? p.dy[i] : 1.0f;
+    s.vol = SDK_KNOWN3(P, true, true, p.vol != nullptr) ? p.vol[i] : 1.0;
+    if (SDK_KNOWN3(P, true, false, has_dep != 0)) {
         s.dep = p.dep[i];
         s.rzl = p.rzl[i];
         s.w = p.w[i];
@@ -170,11 +173,11 @@ __device__ __forceinline__ void store_lane(const sdk_particles &p, int has_dep, 
         p.px[j * p.n + i] = s.px[j];
         p.py[j * p.n + i] = s.py[j];
     }
-    if (SDK_KNOWN(P, true, p.face != nullptr)) p.face[i] = s.f;
+    if (SDK_KNOWN3(P, true, true, p.face != nullptr)) p.face[i] = s.f;
     p.iy[i] = s.iy;
     p.ix[i] = s.ix;
-    if (SDK_KNOWN(P, true, p.vol != nullptr)) p.vol[i] = s.vol;
-    if (SDK_KNOWN(P, true, has_dep != 0)) {
+    if (SDK_KNOWN3(P, true, true, p.vol != nullptr)) p.vol[i] = s.vol;
+    if (SDK_KNOWN3(P, true, false, has_dep != 0)) {
         p.dep[i] = s.dep;
         p.rzl[i] = s.rzl;
         p.w[i] = s.w;
@@ -226,11 +229,11 @@ __device__ __forceinline__ void trim_axis(double &x, double &u, double du, doubl
 // Index arithmetic: 32-bit within a horizontal plane, one 64-bit multiply-add for the level/time.
 template <typename T, int P = 0>
 __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v, int has_dep, Lane &s) {
-    const bool k_face = SDK_KNOWN(P, true, g.has_face != 0);
-    const bool k_w = SDK_KNOWN(P, true, v.has_w != 0);
-    const bool k_tr = SDK_KNOWN(P, true, v.transport != 0);
-    const bool k_z = SDK_KNOWN(P, true, v.has_z != 0);
-    const bool k_volz = SDK_KNOWN(P, true, v.vol_has_z != 0);
+    const bool k_face = SDK_KNOWN3(P, true, true, g.has_face != 0);
+    const bool k_w = SDK_KNOWN3(P, true, false, v.has_w != 0);
+    const bool k_tr = SDK_KNOWN3(P, true, true, v.transport != 0);
+    const bool k_z = SDK_KNOWN3(P, true, false, v.has_z != 0);
+    const bool k_volz = SDK_KNOWN3(P, true, false, v.vol_has_z != 0);
     // ---- where do the right and top wall values live?
     int rf = s.f, ry_ = s.iy, rx_ = s.ix, r_in;
     int tf = s.f, ty_ = s.iy, tx_ = s.ix, t_in;
@@ -348,7 +351,7 @@ template <typename T, bool LOG, int P>
 __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, const float *sdZl, Lane &s,
                                      bool &live) {
     const GridDev &g = a.g;
-    const int has_dep = SDK_KNOWN(P, 1, a.has_dep);
+    const int has_dep = SDK_KNOWN3(P, 1, 0, a.has_dep);
     // trim, lagrangian.py:400
     const double lo = -0.5 + a.trim_tol, hi = 0.5 - a.trim_tol;
     trim_axis(s.rx, s.u, s.du, lo, hi);
@@ -417,6 +420,7 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
     double best = INFINITY;
 #pragma unroll
     for (int k = 0; k < 7; ++k) {
+        if (P == 3 && (k == 4 || k == 5)) continue;  // no vertical axis: "never" (a live particle has sg != 0)
         double d = ts[k] * sg;
         if (isnan(d) || d < 0) d = INFINITY;
         if (d < best) {
@@ -427,7 +431,7 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
     double te = ts[0];
 #pragma unroll
     for (int k = 1; k < 7; ++k)
-        if (tend == k) te = ts[k];
+        if (!(P == 3 && (k == 4 || k == 5)) && tend == k) te = ts[k];
     // _move_within_cell, lagrangian.py:528
     s.t += te;
     {
@@ -483,7 +487,7 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
             live = false;  // nothing sensible to read outside a closed domain
             return;
         }
-    } else if (tend == 4) {
+    } else if (P != 3 && tend == 4) {
         s.izl += 1;
         if (SDK_UNLIKELY(s.izl > g.n_zl - 1)) {
             // through the deepest staged level (a non-zero vertical velocity at the bottom): the reference
@@ -493,7 +497,7 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
             live = false;
             return;
         }
-    } else if (tend == 5) {
+    } else if (P != 3 && tend == 5) {
         if (!a.kick_back || s.izl != 1) s.izl -= 1;
         else s.dep = s.bzl + s.dzl / 2;
     }
@@ -611,8 +615,24 @@ static __device__ __noinline__ void ship_lane_cold(const AdvectArgs &a, long lon
 
 // SHIP: the write-back of a finished particle also stores its 32-byte output record into every rank's receive
 // buffer (sdk_advect_params.ship): the exchange of a stop's output rides on the kernel that produces it.
+// Launch bounds per profile.  The 3-D profiles need their 128 registers (4 warps per scheduler; with 96 or 80 the spills
+// and the instruction cache cost more than the extra warps bring, profiles/README.md).  The surface profile carries
+// neither the vertical axis nor its code: it fits 96 registers with five doubles spilled and gains from the fifth CTA
+// per SM (configs[3]: 4.05 -> 3.78 ms per launch).
+#ifndef SDK_ADVECT_P3_BLOCKS
+#define SDK_ADVECT_P3_BLOCKS 5
+#endif
+template <int P>
+struct Bounds {
+    static constexpr int threads = SDK_ADVECT_THREADS, blocks = SDK_ADVECT_MIN_BLOCKS;
+};
+template <>
+struct Bounds<3> {
+    static constexpr int threads = SDK_ADVECT_DEFAULT_THREADS, blocks = SDK_ADVECT_P3_BLOCKS;
+};
+
 template <typename T, bool LOG, int P, bool SHIP = false>
-__global__ void __launch_bounds__(SDK_ADVECT_THREADS, SDK_ADVECT_MIN_BLOCKS)
+__global__ void __launch_bounds__(Bounds<P>::threads, Bounds<P>::blocks)
 advect_kernel(const __grid_constant__ AdvectArgs a) {
     extern __shared__ __align__(16) float smem[];
     float *sZl = smem;
@@ -791,20 +811,36 @@ namespace sdk {
 
 int advect_max_threads() { return SDK_ADVECT_THREADS; }
 int advect_default_threads() { return SDK_ADVECT_DEFAULT_THREADS; }
-int advect_default_blocks_per_sm() { return SDK_ADVECT_MIN_BLOCKS * SDK_ADVECT_THREADS / SDK_ADVECT_DEFAULT_THREADS; }
+
+// which compile-time profile a launch takes (0 = every switch from the arguments)
+int advect_profile(const AdvectArgs &args, int threads) {
+    if (args.g.hmode != SDK_H_OCEANPARCEL) return 2;
+    const bool llc = SDK_ADVECT_PROFILES && args.g.has_face && args.g.typ == SDK_TYP_LLC && args.v.transport && args.p.face && args.p.vol;
+    // profile 1: what the folded switches of the specialised kernel assume
+    if (llc && args.has_dep && args.v.has_w && args.v.has_z && args.v.vol_has_z) return 1;
+    // profile 3: the surface case (no depth, no vertical velocity, 2-D transports and volumes; fp64 fields, no log)
+    if (llc && !args.has_dep && !args.v.has_w && !args.v.has_z && !args.v.vol_has_z && args.v.dtype != SDK_F32 && !args.has_log &&
+        threads <= Bounds<3>::threads)
+        return 3;
+    return 0;
+}
+
+// CTAs of SDK_ADVECT_DEFAULT_THREADS threads per SM a profile is compiled for
+int advect_default_blocks_per_sm(int profile) {
+    return profile == 3 ? Bounds<3>::blocks : SDK_ADVECT_MIN_BLOCKS * SDK_ADVECT_THREADS / SDK_ADVECT_DEFAULT_THREADS;
+}
 
 cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaStream_t stream) {
     const size_t smem = advect_smem_bytes(args.g.n_zl, args.g.n_z, threads);
     const bool f32 = args.v.dtype == SDK_F32;
-    // profile 1: what the folded switches of the specialised kernel assume
-    const bool p1 = SDK_ADVECT_PROFILES && args.g.hmode == SDK_H_OCEANPARCEL && args.g.has_face && args.g.typ == SDK_TYP_LLC && args.has_dep && args.v.has_w &&
-                    args.v.transport && args.v.has_z && args.v.vol_has_z && args.p.face && args.p.vol;
+    const int profile = advect_profile(args, threads);
+    const bool p1 = profile == 1, p3 = profile == 3;
     void (*kern)(AdvectArgs);
     if (args.ship) {
         // (launch_advect's caller has checked: no log with the fused exchange)
         if (args.g.hmode != SDK_H_OCEANPARCEL) kern = f32 ? advect_kernel<float, false, 2, true> : advect_kernel<double, false, 2, true>;
         else if (f32) kern = p1 ? advect_kernel<float, false, 1, true> : advect_kernel<float, false, 0, true>;
-        else kern = p1 ? advect_kernel<double, false, 1, true> : advect_kernel<double, false, 0, true>;
+        else kern = p1 ? advect_kernel<double, false, 1, true> : (p3 ? advect_kernel<double, false, 3, true> : advect_kernel<double, false, 0, true>);
     } else if (args.g.hmode != SDK_H_OCEANPARCEL) {
         if (args.has_log) kern = f32 ? advect_kernel<float, true, 2> : advect_kernel<double, true, 2>;
         else kern = f32 ? advect_kernel<float, false, 2> : advect_kernel<double, false, 2>;
@@ -813,7 +849,7 @@ cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaS
         else kern = p1 ? advect_kernel<double, true, 1> : advect_kernel<double, true, 0>;
     } else {
         if (f32) kern = p1 ? advect_kernel<float, false, 1> : advect_kernel<float, false, 0>;
-        else kern = p1 ? advect_kernel<double, false, 1> : advect_kernel<double, false, 0>;
+        else kern = p1 ? advect_kernel<double, false, 1> : (p3 ? advect_kernel<double, false, 3> : advect_kernel<double, false, 0>);
     }
     if (smem > 48 * 1024) {  // CTAs of more than ~384 threads need more than the default 48 KB of dynamic shared memory
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -25,7 +25,8 @@ struct AdvectArgs {
 
 int advect_max_threads();
 int advect_default_threads();
-int advect_default_blocks_per_sm();
+int advect_profile(const AdvectArgs &args, int threads);
+int advect_default_blocks_per_sm(int profile);
 cudaError_t launch_advect(const AdvectArgs &args, int blocks, int threads, cudaStream_t stream);
 cudaError_t launch_get_u_du(const AdvectArgs &args, cudaStream_t stream);
 

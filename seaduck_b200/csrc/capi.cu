@@ -186,6 +186,7 @@ int sdk_grid_destroy(sdk_grid *g) {
     if (g->has_buckets) {
         cudaFree(g->buckets.table);
         cudaFree((void *)g->buckets.cxyz);
+        cudaFree((void *)g->buckets.rim);
         cudaFree((void *)g->buckets.wide);
     }
     delete g;
@@ -276,7 +277,7 @@ int sdk_advect(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particle
     cudaError_t e = cudaMemsetAsync(a.queue, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_advect: memset");
     const int threads = (par && par->threads_per_block > 0) ? par->threads_per_block : sdk::advect_default_threads();
-    const int per_sm = (par && par->blocks_per_sm > 0) ? par->blocks_per_sm : sdk::advect_default_blocks_per_sm() * sdk::advect_default_threads() / threads;
+    const int per_sm = (par && par->blocks_per_sm > 0) ? par->blocks_per_sm : sdk::advect_default_blocks_per_sm(sdk::advect_profile(a, threads)) * sdk::advect_default_threads() / threads;
     int64_t need = (p->n + threads - 1) / threads;
     int sms = grid->sm_count - ((par && par->reserve_sms > 0) ? par->reserve_sms : 0);
     if (sms < 1) sms = 1;
@@ -287,6 +288,15 @@ int sdk_advect(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particle
     e = sdk::launch_advect(a, (int)blocks, threads, stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_advect: launch");
     return SDK_OK;
+}
+
+int sdk_advect_profile(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, const sdk_advect_params *par,
+                       const sdk_log *log) {
+    sdk::AdvectArgs a;
+    int rc = fill_args(grid, vel, p, 0.0, par, log, 1, a);
+    if (rc) return rc < 0 ? rc : -rc;
+    const int threads = (par && par->threads_per_block > 0) ? par->threads_per_block : sdk::advect_default_threads();
+    return sdk::advect_profile(a, threads);
 }
 
 int sdk_get_u_du(const sdk_grid *grid, const sdk_velocity *vel, const sdk_particles *p, int has_dep,
@@ -314,6 +324,7 @@ int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span
     if (grid->has_buckets) {
         cudaFree(grid->buckets.table);
         cudaFree((void *)grid->buckets.cxyz);
+        cudaFree((void *)grid->buckets.rim);
         cudaFree((void *)grid->buckets.wide);
         grid->has_buckets = false;
     }
@@ -330,6 +341,7 @@ int sdk_grid_build_locator(sdk_grid *grid, double lon0, double lat0, double span
     b.table = nullptr;
     b.cxyz = nullptr;
     b.wide = nullptr;
+    b.rim = nullptr;
     cudaError_t e = sdk::build_buckets(grid->dev, b, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "sdk_grid_build_locator");
     grid->has_buckets = true;

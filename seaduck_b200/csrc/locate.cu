@@ -89,6 +89,18 @@ __device__ __forceinline__ int remap_dir(int dir, int e, int ne) {
     return dir;
 }
 
+// One index step of the SEARCH: cell_move, except on a zonally periodic grid, where the reference's own step across the
+// seam lands on column 1 or nx - 1 (_x_per_ind_tend, topology.py:124 -- kept as it is for particles that cross a wall):
+// the nearest-centre search needs the cells that really lie next to each other there, columns nx - 1 and 0.
+__device__ __forceinline__ int search_move(const GridDev &g, int dir, int &f, int &iy, int &ix, int &came_in) {
+    if (g.typ == SDK_TYP_XPERIODIC && dir >= 2) {
+        came_in = -1;
+        ix = dir == 3 ? (ix + 1 < g.nx ? ix + 1 : 0) : (ix > 0 ? ix - 1 : g.nx - 1);
+        return 0;
+    }
+    return cell_move(g, dir, f, iy, ix, came_in);
+}
+
 // neighbour of a cell after up to two moves (second one re-labelled after a face change)
 __device__ __forceinline__ bool neighbour(const GridDev &g, int f, int iy, int ix, int d1, int d2,
                                           int &nf, int &ny, int &nx) {
@@ -96,21 +108,39 @@ __device__ __forceinline__ bool neighbour(const GridDev &g, int f, int iy, int i
     ny = iy;
     nx = ix;
     int came;
-    if (cell_move(g, d1, nf, ny, nx, came)) return false;
+    if (search_move(g, d1, nf, ny, nx, came)) return false;
     if (d2 >= 0) {
         if (came >= 0) d2 = remap_dir(d2, d1, came);
-        if (cell_move(g, d2, nf, ny, nx, came)) return false;
+        if (search_move(g, d2, nf, ny, nx, came)) return false;
     }
     return true;
 }
 
+// The centre table is HALOED: [nface][ny + 2][nx + 2][3], the ring around a face holding the centres of the cells
+// across its edges (filled once per grid through cell_move, so across LLC faces, the periodic seam, ...).  The 8
+// neighbours of ANY cell are then index offsets, and a point near a face edge costs what an interior one does.
+__device__ __forceinline__ int64_t halo_index(const GridDev &g, int f, int iy, int ix) {
+    return ((int64_t)f * (g.ny + 2) + (iy + 1)) * (g.nx + 2) + (ix + 1);
+}
+
+// slot of a halo position in the per-face rim table (flat index of the cell that lives there, -1 = none):
+// bottom row (ix = -1 .. nx), top row, left column (iy = 0 .. ny - 1), right column
+__device__ __forceinline__ int64_t rim_slot(const GridDev &g, int f, int iy, int ix) {
+    const int row = g.nx + 2;
+    const int64_t base = (int64_t)f * (2 * row + 2 * g.ny);
+    if (iy < 0) return base + ix + 1;
+    if (iy >= g.ny) return base + row + ix + 1;
+    return base + 2 * row + (ix < 0 ? 0 : g.ny) + iy;
+}
+
 __device__ __forceinline__ double dist2_to_cell(const GridDev &g, const double *cxyz, int f, int iy, int ix, double qx,
                                                 double qy, double qz) {
-    const int64_t c = ((int64_t)f * g.ny + iy) * g.nx + ix;
     double x, y, z;
     if (cxyz) {
-        x = __ldg(cxyz + 3 * c), y = __ldg(cxyz + 3 * c + 1), z = __ldg(cxyz + 3 * c + 2);
+        const int64_t h = halo_index(g, f, iy, ix);
+        x = __ldg(cxyz + 3 * h), y = __ldg(cxyz + 3 * h + 1), z = __ldg(cxyz + 3 * h + 2);
     } else {
+        const int64_t c = ((int64_t)f * g.ny + iy) * g.nx + ix;
         const float lon = __ldg(g.XC + c), lat = __ldg(g.YC + c);
         if (!(lon == lon) || !(lat == lat)) return INFINITY;
         unit_vec((double)lon, (double)lat, x, y, z);
@@ -119,14 +149,34 @@ __device__ __forceinline__ double dist2_to_cell(const GridDev &g, const double *
     return dx * dx + dy * dy + dz * dz;
 }
 
-// the table behind dist2_to_cell: the same unit_vec of the same float32 centre, evaluated once per cell
-__global__ void cell_xyz_kernel(GridDev g, double *cxyz) {
-    const int64_t ncell = (int64_t)g.nface * g.ny * g.nx;
-    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell; c += (int64_t)gridDim.x * blockDim.x) {
-        const float lon = g.XC[c], lat = g.YC[c];
-        double x = INFINITY, y = INFINITY, z = INFINITY;
-        if (lon == lon && lat == lat) unit_vec((double)lon, (double)lat, x, y, z);
-        cxyz[3 * c] = x, cxyz[3 * c + 1] = y, cxyz[3 * c + 2] = z;
+// the table behind dist2_to_cell: the same unit_vec of the same float32 centre, evaluated once per cell, and for the
+// halo ring the cell one (edge) or two (corner: vertical move first, as the scan of the 8 neighbours orders them) cell
+// moves away.  A halo position without a cell (closed edge, missing face) gets a far-away FINITE point: never the
+// nearest, and not mistaken for a NaN centre (+inf), which makes the walk look further out.
+__global__ void cell_xyz_kernel(GridDev g, double *cxyz, int *rim) {
+    const int H = g.ny + 2, W = g.nx + 2;
+    const int64_t ntab = (int64_t)g.nface * H * W;
+    for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < ntab; h += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(h / ((int64_t)H * W));
+        const int rem = (int)(h - (int64_t)f * H * W);
+        const int iy = rem / W - 1, ix = rem % W - 1;
+        int nf = f, ny = iy, nx = ix;
+        bool there = true;
+        const bool off_y = iy < 0 || iy >= g.ny, off_x = ix < 0 || ix >= g.nx;
+        if (off_y || off_x) {
+            const int sy = min(max(iy, 0), g.ny - 1), sx = min(max(ix, 0), g.nx - 1);
+            const int dv = iy < 0 ? 1 : 0, dh = ix < 0 ? 2 : 3;
+            there = off_y ? neighbour(g, f, sy, sx, dv, off_x ? dh : -1, nf, ny, nx) : neighbour(g, f, sy, sx, dh, -1, nf, ny, nx);
+            rim[rim_slot(g, f, iy, ix)] = there ? (int)(((int64_t)nf * g.ny + ny) * g.nx + nx) : -1;
+        }
+        double x = 1e150, y = 0.0, z = 0.0;
+        if (there) {
+            const int64_t c = ((int64_t)nf * g.ny + ny) * g.nx + nx;
+            const float lon = g.XC[c], lat = g.YC[c];
+            x = y = z = INFINITY;
+            if (lon == lon && lat == lat) unit_vec((double)lon, (double)lat, x, y, z);
+        }
+        cxyz[3 * h] = x, cxyz[3 * h + 1] = y, cxyz[3 * h + 2] = z;
     }
 }
 
@@ -142,7 +192,7 @@ __device__ __forceinline__ bool cell_at_offset(const GridDev &g, int f, int iy, 
     for (int k = 0; k < m; ++k) {
         int came;
         const int d = (int)(moves >> (2 * k) & 3u);
-        if (cell_move(g, d, nf, ny, nx, came)) return false;
+        if (search_move(g, d, nf, ny, nx, came)) return false;
         if (came >= 0) {
             for (int j = k + 1; j < m; ++j) {
                 const unsigned old = moves >> (2 * j) & 3u;
@@ -292,8 +342,8 @@ __global__ void cell_wide_kernel(GridDev g, const double *cxyz, unsigned char *w
                 v[k][0] = v[k][1] = v[k][2] = 0.0;
                 continue;
             }
-            const int64_t n = ((int64_t)nf * g.ny + ny) * g.nx + nx;
-            for (int j = 0; j < 3; ++j) v[k][j] = cxyz[3 * n + j] - cxyz[3 * c + j];
+            const int64_t n = halo_index(g, nf, ny, nx), h = halo_index(g, f, iy, ix);
+            for (int j = 0; j < 3; ++j) v[k][j] = cxyz[3 * n + j] - cxyz[3 * h + j];
         }
         const double ab = v[0][0] * v[1][0] + v[0][1] * v[1][1] + v[0][2] * v[1][2];
         const double aa = v[0][0] * v[0][0] + v[0][1] * v[0][1] + v[0][2] * v[0][2];
@@ -326,12 +376,12 @@ static __device__ __noinline__ Nearest confirm_rings(const GridDev &g, const dou
     const bool inside = SDK_LOCATE_INTERIOR && cxyz && iy >= 2 && iy < g.ny - 2 && ix >= 2 && ix < g.nx - 2;
     if (inside) {
         // away from the face edges the second ring is plain index arithmetic on the centre table
-        const int64_t c0 = ((int64_t)f * g.ny + iy) * g.nx + ix;
+        const int64_t c0 = halo_index(g, f, iy, ix);
 #pragma unroll 4
         for (int k = 0; k < 16; ++k) {
             const int dy = k < 5 ? -2 : (k < 10 ? 2 : (k < 13 ? k - 11 : k - 14));
             const int dx = k < 5 ? k - 2 : (k < 10 ? k - 7 : (k < 13 ? -2 : 2));
-            const int64_t c = c0 + (int64_t)dy * g.nx + dx;
+            const int64_t c = c0 + (int64_t)dy * (g.nx + 2) + dx;
             const double ex = __ldg(cxyz + 3 * c) - qx, ey = __ldg(cxyz + 3 * c + 1) - qy, ez = __ldg(cxyz + 3 * c + 2) - qz;
             const double dd = ex * ex + ey * ey + ez * ez;
             hole |= !(dd < INFINITY);
@@ -421,15 +471,16 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
             int bf = f, by = iy, bx = ix;
             double bd = best;
             bool near_hole = false;
-            if (cxyz && iy >= 1 && iy < g.ny - 1 && ix >= 1 && ix < g.nx - 1) {
-                // away from the face edges the 8 neighbours are index offsets into the centre table -- in the order of
-                // the general scan (up, down, left, right, up-left, up-right, down-left, down-right: ties go to the first)
-                const int64_t c0 = ((int64_t)f * g.ny + iy) * g.nx + ix;
+            if (cxyz) {
+                // the 8 neighbours are index offsets into the (haloed) centre table -- in the order of the general scan
+                // (up, down, left, right, up-left, up-right, down-left, down-right: ties go to the first)
+                const int64_t c0 = halo_index(g, f, iy, ix);
+                const int row = g.nx + 2;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     const int dy = (k == 0 || k == 4 || k == 5) ? 1 : ((k == 1 || k == 6 || k == 7) ? -1 : 0);
                     const int dx = (k == 3 || k == 5 || k == 7) ? 1 : ((k == 2 || k == 4 || k == 6) ? -1 : 0);
-                    const int64_t c = c0 + dy * g.nx + dx;
+                    const int64_t c = c0 + dy * row + dx;
                     const double ex = __ldg(cxyz + 3 * c) - qx, ey = __ldg(cxyz + 3 * c + 1) - qy, ez = __ldg(cxyz + 3 * c + 2) - qz;
                     const double dd = ex * ex + ey * ey + ez * ez;
                     near_hole |= !(dd < INFINITY);
@@ -438,6 +489,15 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
                         by = iy + dy;
                         bx = ix + dx;
                     }
+                }
+                if (SDK_UNLIKELY(((unsigned)by >= (unsigned)g.ny) | ((unsigned)bx >= (unsigned)g.nx))) {
+                    // the closest neighbour lives across a face edge: the rim table says which cell it is
+                    const int c = __ldg(a.b.rim + rim_slot(g, f, by, bx));
+                    if (c < 0) break;  // (no cell there: its far-away stand-in can only win against a seed without a centre)
+                    bf = c / (g.ny * g.nx);
+                    const int r = c - bf * (g.ny * g.nx);
+                    by = r / g.nx;
+                    bx = r - by * g.nx;
                 }
             } else {
                 const Nearest nb = scan_neighbours_cold(g, cxyz, f, iy, ix, qx, qy, qz, best);
@@ -644,14 +704,22 @@ cudaError_t build_buckets(const GridDev &g, BucketGrid &b, cudaStream_t s) {
     if (e == cudaSuccess && src != b.table)
         e = cudaMemcpyAsync(b.table, src, sizeof(int) * (size_t)nb, cudaMemcpyDeviceToDevice, s);
     if (e == cudaSuccess) {
-        // unit vectors of the cell centres (24 bytes per cell); a grid too large for it keeps the sincos path
+        // unit vectors of the cell centres with a halo ring per face (24 bytes per cell); a grid too large for it keeps the
+        // sincos path and the general neighbour scan
         double *cxyz = nullptr;
         unsigned char *wide = nullptr;
+        int *rim = nullptr;
         b.cxyz = nullptr;
         b.wide = nullptr;
-        if (cudaMalloc(&cxyz, sizeof(double) * 3 * (size_t)ncell) == cudaSuccess) {
-            cell_xyz_kernel<<<(int)sblocks, threads, 0, s>>>(g, cxyz);
+        b.rim = nullptr;
+        const size_t ntab = (size_t)g.nface * (g.ny + 2) * (g.nx + 2);
+        const size_t nrim = (size_t)g.nface * (2 * (g.nx + 2) + 2 * g.ny);
+        if (cudaMalloc(&rim, sizeof(int) * nrim) != cudaSuccess) {
+            cudaGetLastError();
+        } else if (cudaMalloc(&cxyz, sizeof(double) * 3 * ntab) == cudaSuccess) {
+            cell_xyz_kernel<<<(int)sblocks, threads, 0, s>>>(g, cxyz, rim);
             b.cxyz = cxyz;
+            b.rim = rim;
             if (cudaMalloc(&wide, (size_t)ncell) == cudaSuccess) {
                 cell_wide_kernel<<<(int)sblocks, threads, 0, s>>>(g, cxyz, wide);
                 b.wide = wide;
@@ -660,6 +728,7 @@ cudaError_t build_buckets(const GridDev &g, BucketGrid &b, cudaStream_t s) {
             }
         } else {
             cudaGetLastError();
+            cudaFree(rim);
         }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);

@@ -12,9 +12,13 @@ struct BucketGrid {
     double lon0, lat0, span_lon, span_lat, inv_dlon, inv_dlat;
     int nlon, nlat, periodic;
     int *table;  // one nearby cell (flat index) per bucket
-    // unit vector of every cell centre (3 doubles per cell, +inf for a NaN centre), or NULL when the table did not fit:
-    // a distance is then three loads and three multiply-adds instead of two sincos
+    // unit vector of every cell centre (3 doubles per cell, +inf for a NaN centre) as [nface][ny + 2][nx + 2][3]: the ring
+    // around a face holds the centres of the cells across its edges, so the 8 neighbours of any cell are index offsets; NULL
+    // when the table did not fit: a distance is then two sincos and the neighbours come from cell_move
     const double *cxyz;
+    // (with cxyz) flat index of the cell at every halo position, -1 = none; per face: bottom row, top row (nx + 2 each),
+    // left column, right column (ny each)
+    const int *rim;
     // one byte per cell (with cxyz): 1 where the local grid vectors are sheared / stretched enough (or a neighbour is
     // missing) that a cell outside the 8 index neighbours can be the nearest one, so the walk has to look at the second ring
     const unsigned char *wide;

@@ -227,6 +227,60 @@ def test_locate_on_a_sheared_grid_matches_kdtree(shear, oracle_lib):
         )
 
 
+@pytest.mark.parametrize("kind", ["llc", "x_periodic"])
+def test_locate_next_to_face_edges_matches_kdtree(kind, oracle_lib):
+    """Points scattered around the centres of the cells on the rim of every face (so that many of them belong to a cell
+    across the edge, on another face or past the periodic seam): the device search, whose 8 neighbours of a rim cell
+    come from the halo ring of the centre table, against scipy's cKDTree on all centres (reference utils.py:225,309)."""
+    import seaduck_b200 as sd
+    from oracle.oracle import spherical2cartesian
+    from seaduck_b200 import synthetic
+
+    ds = synthetic.llc(n=24, nz=4) if kind == "llc" else synthetic.channel(ny=30, nx=72, nz=4)
+    od = sd.OceData(ds)
+    og = oracle_lib.OracleGrid(od)
+    xc, yc = np.asarray(og.XC, float), np.asarray(og.YC, float)
+    rim = np.zeros(xc.shape, bool)
+    rim[..., 0, :] = rim[..., -1, :] = rim[..., :, 0] = rim[..., :, -1] = True
+    rim &= np.isfinite(xc) & np.isfinite(yc) & (np.abs(yc) < 88.0)
+    idx = np.argwhere(rim)
+    rng = np.random.default_rng(23)
+    rep = 6
+    lon0 = np.repeat(xc[rim], rep)
+    lat0 = np.repeat(yc[rim], rep)
+    # a jitter of about one cell width in every direction (the grid spacing, in degrees, from the neighbouring centre)
+    step = np.abs(np.diff(yc, axis=-2)).max()
+    lon = lon0 + rng.uniform(-1.2, 1.2, lon0.size) * step / np.maximum(np.cos(np.deg2rad(lat0)), 0.05)
+    lat = np.clip(lat0 + rng.uniform(-1.2, 1.2, lon0.size) * step, -89.5, 89.5)
+    lon = (lon + 180.0) % 360.0 - 180.0
+    pos = sd.Position().from_latlon(x=lon, y=lat, data=od)
+    ref = og.find_ind_h(lon, lat)
+    mine = (pos.face, pos.iy, pos.ix) if len(ref) == 3 else (pos.iy, pos.ix)
+    same = np.ones(lon.size, bool)
+    for a, b in zip(mine, ref):
+        same &= np.asarray(a) == np.asarray(b)
+    moved = np.zeros(lon.size, bool)
+    for a, col in zip(mine, np.repeat(idx, rep, axis=0).T):
+        moved |= np.asarray(a) != col
+    assert moved.mean() > 0.2, "the jitter is supposed to push many points into other cells"
+    if not same.all():
+        bad = np.flatnonzero(~same)
+
+        def d2(ind):
+            sel = tuple(np.asarray(a)[bad] for a in ind)
+            cx, cy, cz = spherical2cartesian(yc[sel], xc[sel])
+            qx, qy, qz = spherical2cartesian(lat[bad], lon[bad])
+            return (cx - qx) ** 2 + (cy - qy) ** 2 + (cz - qz) ** 2
+
+        got, want = d2(mine), d2(ref)
+        worse = ~(np.abs(got - want) <= 1e-12 * want)
+        assert not worse.any(), (
+            f"{int(worse.sum())} of {lon.size} points in a farther cell than cKDTree's ({kind}); first: "
+            f"{[tuple(int(np.asarray(a)[bad][worse][0]) for a in mine)]} vs {[tuple(int(np.asarray(a)[bad][worse][0]) for a in ref)]}, "
+            f"distance ratios {np.sqrt(got[worse] / want[worse])[:6].round(4).tolist()}"
+        )
+
+
 def test_multi_field_launch_equals_single_launches():
     """Scalars that share a kernel go through one ``sdk_interp_scalar_multi`` launch: bit for bit what one launch per
     variable gives, for nearest / linear / derivative kernels in z and t, masked and unmasked."""

@@ -197,6 +197,39 @@ def test_lazy_mode_list_of_time_matches_golden():
         compare_state(gold, f"s{i}_", snap)
 
 
+def test_surface_profile_equals_generic_kernel_and_golden():
+    """The surface run of BASELINE.json configs[3] takes its own compile-time variant of the advection kernel (profile 3:
+    no vertical axis, five CTAs per SM); CTAs of 256 threads are outside that variant's launch bounds and fall back to the
+    generic kernel (profile 0).  Same inputs through both: every state array bit for bit, and both the reference's
+    answer at every stop (golden ``lagrangian_llc_surface_time``, which the golden test itself reaches through the
+    logging variant of profile 0)."""
+    import ctypes as C
+
+    sd = _sd()
+    from seaduck_b200 import _lib
+
+    case = cases.case_llc_surface_time()
+    gold = np.load(os.path.join(GOLD, f"lagrangian_{case['name']}.npz"))
+    runs = {}
+    for threads, want in ((0, 3), (256, 0)):
+        od = sd.OceData(case["ds"])
+        pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, **case["kw"])
+        pt.tuning = dict(threads_per_block=threads)
+        par = pt._params(pt.max_iteration)
+        p = pt._cparticles()
+        assert _lib.lib().sdk_advect_profile(od.grid_handle(), C.byref(pt._vel), C.byref(p), C.byref(par), None) == want
+        stops, snaps = pt.to_list_of_time(normal_stops=case["stops"])
+        np.testing.assert_allclose(stops, gold["stops"])
+        for i, snap in enumerate(snaps):
+            compare_state(gold, f"s{i}_", snap)
+        runs[want] = (pt, snaps)
+    assert runs[3][0].crossings == runs[0][0].crossings > 0
+    for a, b in zip(runs[3][1] + [runs[3][0]], runs[0][1] + [runs[0][0]]):
+        for k in cases.FINAL_INT + cases.FINAL_FLT:
+            if getattr(a, k, None) is not None:
+                np.testing.assert_array_equal(getattr(a, k), getattr(b, k), err_msg=k)
+
+
 def _cparticles_of(state, n):
     from seaduck_b200 import _lib
 
