@@ -224,6 +224,17 @@ def test_surface_profile_equals_generic_kernel_and_golden():
             compare_state(gold, f"s{i}_", snap)
         runs[want] = (pt, snaps)
     assert runs[3][0].crossings == runs[0][0].crossings > 0
+    # record snapshots of a lazy run (stored by the kernel when it writes a particle back: the variant with the fused
+    # record store of the same profile), with and without the cell sort
+    for sort in (False, True):
+        od = sd.OceData(case["ds"])
+        pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, sort=sort, **case["kw"])
+        pt.lazy = True
+        _, recs = pt.to_list_of_time(normal_stops=case["stops"], snapshots="records")
+        assert len(recs) == len(runs[3][1])
+        for full, r in zip(runs[3][1], recs):
+            for k in ("lon", "lat", "face", "iy", "ix"):
+                np.testing.assert_array_equal(getattr(r, k), getattr(full, k), err_msg=f"{k} (records, sort={sort})")
     for a, b in zip(runs[3][1] + [runs[3][0]], runs[0][1] + [runs[0][0]]):
         for k in cases.FINAL_INT + cases.FINAL_FLT:
             if getattr(a, k, None) is not None:
@@ -431,6 +442,15 @@ def test_cell_sorted_particles_equal_plain():
         stops, snaps = pt.to_list_of_time(normal_stops=case["stops"])
         stops_r, recs = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, sort=sort, **case["kw"]).to_list_of_time(
             normal_stops=case["stops"], snapshots="records")
+        # lazy runs get their record snapshots from the advection kernel itself (no packing pass)
+        lazy = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, sort=sort, **case["kw"])
+        lazy.lazy = True
+        _, recs_lazy = lazy.to_list_of_time(normal_stops=case["stops"], snapshots="records")
+        assert lazy.crossings == pt.crossings
+        for full, r in zip(snaps, recs_lazy):
+            for k in ("lon", "lat", "dep", "face", "iy", "ix", "izl_lin"):
+                np.testing.assert_array_equal(getattr(r, k), getattr(full, k), err_msg=f"{k} (lazy, sort={sort})")
+        assert len(recs_lazy) == len(snaps)
         tvals = pt.interpolate("T", sd.KnW()) if "T" in case["ds"].variables else None
         runs.append((pt, snaps, recs, tvals))
     (a, sa, ra, ta), (b, sb, rb, tb) = runs
