@@ -634,8 +634,8 @@ def run_stops(ctx, a, grid, particles, hours, nt=3):
         },
         "value": sm[1] / (mx[0] * 1e-3), "unit": "crossings/s", "ms_per_step": mx[0] / K, "n_gpus": world, "steps": K, "warmup": W,
         "scaling": "weak", "collective": "none on the data path (gather='owner': every rank keeps the records of its slice)",
-        # per rank and stop: advect_kernel (which also stores the stop's records) + finish_stop_kernel (+ get_u_du_kernel at the slab swap)
-        "gpu_launches": world * (2 * nsnap + 1),
+        # per rank and stop: advect_kernel + finish_stop_kernel + pack_records_kernel (+ get_u_du_kernel at the slab swap)
+        "gpu_launches": world * (3 * nsnap + 1),
     }
     if world > 1 and not a.no_gather:
         ms2, cross2, _ = run(W + K, K, "all")

@@ -610,25 +610,6 @@ class Particle(Position):
         self.__dict__["_ship_leg"] = exchange is not None
         self.__dict__["last_ship_step"] = None
 
-    def _local_exchange(self, block):
-        """``sdk_exchange`` with this GPU as its only rank and ``block`` (uint8 device tensor [N, 32]) as the receive
-        buffer: ``sdk_advect_params.ship`` then makes the advection kernel store every particle's 32-byte record there
-        when it writes the particle back -- a record snapshot without a second pass over the state."""
-        import torch  # noqa: PLC0415
-
-        sig = self.__dict__.get("_local_signal")
-        if sig is None:
-            sig = torch.zeros(_lib.SIGNAL_WORDS + 1, dtype=torch.int64, device=self.ocedata._torch_device())
-            self.__dict__["_local_signal"] = sig
-        x = _lib.Exchange()
-        x.world, x.rank, x.n_slots, x.n_pad = 1, 0, 1, self.N
-        x.recv[0] = block.data_ptr()
-        x.recv_multicast = None
-        x.signal[0] = sig.data_ptr()
-        x.ticket = sig.data_ptr() + 8 * _lib.SIGNAL_WORDS
-        self.__dict__["_local_x"] = x  # (the struct is read during the call only; kept for the caller's addressof)
-        return x
-
     def _read_stats(self):
         """(live at start, crossings, hit max_iteration, flagged) of the launches since the last
         call -- one small device-to-host copy, the only synchronisation of a stop."""
@@ -646,14 +627,7 @@ class Particle(Position):
         stream = _lib.current_stream()
         if not self.save_raw:
             ex = self.__dict__.get("_exchange")
-            target = self.__dict__.get("_record_target")
-            if target is not None:
-                # records of this leg's end into a block of this GPU's own memory: the exchange with one rank
-                keep_alive = self._local_exchange(target)
-                par.ship = C.addressof(keep_alive)
-                par.ship_index = None if self._perm is None else self._perm.data_ptr()
-                par.ship_step = 1
-            elif ex is not None and self.__dict__.get("_ship_leg", False):
+            if ex is not None and self.__dict__.get("_ship_leg", False):
                 par.ship = C.addressof(ex.x)
                 scatter = self._perm is not None and self.__dict__.get("_ship_order", "caller") == "caller"
                 par.ship_index = self._perm.data_ptr() if scatter else None
@@ -901,23 +875,11 @@ class Particle(Position):
             n_keep = sum(1 for i in range(len(stops)) if return_in_between or not (update[i] or i == 0))
             ring = self._record_blocks(n_keep)
 
-        # Record snapshots of a lazy run come out of the advection kernel itself: the write-back of a particle at the
-        # end of its leg also stores its record into the block of that stop (sdk_advect_params.ship with this GPU as the
-        # only rank) -- no packing pass over the state per stop.
-        fused = (
-            ring is not None and self.lazy and self.callback is None and not self.save_raw and self.__dict__.get("_exchange") is None
-            and (self._has_dep or self._st.get("izl") is None) and self.N > 0
-        )
-
         def keep(t_stop):
             if _on_stop is not None:
                 _on_stop(t_stop)
             elif snapshots == "records":
-                block = ring[len(to_return)]
-                if fused:
-                    to_return.append(RecordSnapshot(self.ocedata, t_stop, block, self._st.get("face") is not None, self._has_dep))
-                else:
-                    to_return.append(self.record_snapshot(t_stop, out=block))
+                to_return.append(self.record_snapshot(t_stop, out=ring[len(to_return)]))
             else:
                 to_return.append(self.deepcopy())
 
@@ -929,13 +891,7 @@ class Particle(Position):
             if self.__dict__.get("_exchange") is not None:
                 # the fused output exchange ships the legs that end in a stop somebody keeps
                 self.__dict__["_ship_leg"] = return_in_between or not (update[i] or i == 0)
-            if fused:
-                kept = return_in_between or not (update[i] or i == 0)
-                self.__dict__["_record_target"] = ring[len(to_return)] if kept else None
-            try:
-                self.to_next_stop(tl)
-            finally:
-                self.__dict__["_record_target"] = None
+            self.to_next_stop(tl)
             if has_time and self.lazy and (update[i] or i == 0):
                 # the leg is queued, not finished: copy the snapshot it ends in while it runs
                 self._prefetch_slab_for(tl)

@@ -224,8 +224,7 @@ def test_surface_profile_equals_generic_kernel_and_golden():
             compare_state(gold, f"s{i}_", snap)
         runs[want] = (pt, snaps)
     assert runs[3][0].crossings == runs[0][0].crossings > 0
-    # record snapshots of a lazy run (stored by the kernel when it writes a particle back: the variant with the fused
-    # record store of the same profile), with and without the cell sort
+    # record snapshots of a lazy run, with and without the cell sort
     for sort in (False, True):
         od = sd.OceData(case["ds"])
         pt = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, sort=sort, **case["kw"])
@@ -442,7 +441,7 @@ def test_cell_sorted_particles_equal_plain():
         stops, snaps = pt.to_list_of_time(normal_stops=case["stops"])
         stops_r, recs = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, sort=sort, **case["kw"]).to_list_of_time(
             normal_stops=case["stops"], snapshots="records")
-        # lazy runs get their record snapshots from the advection kernel itself (no packing pass)
+        # the same through the lazy path (end-of-stop bookkeeping on the device)
         lazy = sd.Particle(x=case["x"], y=case["y"], z=case["z"], t=case["t"], data=od, sort=sort, **case["kw"])
         lazy.lazy = True
         _, recs_lazy = lazy.to_list_of_time(normal_stops=case["stops"], snapshots="records")

@@ -76,6 +76,21 @@ def main():
             if v is not None:
                 pt._st[k].copy_(v)
 
+    sig = torch.zeros(_lib.SIGNAL_WORDS + 1, dtype=torch.int64, device=dev)
+    alive = []
+
+    def local_exchange(block):
+        """sdk_exchange with this GPU as its only rank and `block` as the receive buffer: sdk_advect_params.ship then makes
+        the advection kernel store every particle's record there when it writes the particle back."""
+        x = _lib.Exchange()
+        x.world, x.rank, x.n_slots, x.n_pad = 1, 0, 1, n
+        x.recv[0] = block.data_ptr()
+        x.recv_multicast = None
+        x.signal[0] = sig.data_ptr()
+        x.ticket = sig.data_ptr() + 8 * _lib.SIGNAL_WORDS
+        alive.append(x)
+        return x
+
     def advect(target):
         def run():
             p = pt._cparticles()
@@ -83,7 +98,7 @@ def main():
             stats.zero_()
             par.stats = stats.data_ptr()
             if target is not None:
-                x = pt._local_exchange(target)
+                x = local_exchange(target)
                 par.ship = C.addressof(x)
                 par.ship_index = None if pt._perm is None else pt._perm.data_ptr()
                 par.ship_step = 1
