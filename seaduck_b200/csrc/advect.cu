@@ -523,8 +523,9 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
         s.status |= corner_indices(g, s.f, s.iy, s.ix, c);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            gx[j] = __ldg(g.XG + c[j]);
-            gy[j] = __ldg(g.YG + c[j]);
+            const float2 q = __ldg(g.XYG + c[j]);
+            gx[j] = q.x;
+            gy[j] = q.y;
         }
     }
     if (has_dep) {

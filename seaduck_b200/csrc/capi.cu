@@ -172,6 +172,25 @@ int sdk_grid_create(const sdk_grid_desc *d, sdk_grid **out) {
         return cuda_fail(e, "sdk_grid_create: cudaMalloc");
     }
     g->has_buckets = false;
+    if (d->hmode == SDK_H_OCEANPARCEL) {
+        // corner coordinates as (XG, YG) pairs: one 8-byte read per corner
+        const int64_t ncorner = (int64_t)d->nface * d->gny * d->gnx;
+        float2 *xyg = nullptr;
+        if ((e = cudaMalloc(&xyg, sizeof(float2) * (size_t)ncorner)) != cudaSuccess) {
+            cudaFree(g->queue);
+            delete g;
+            return cuda_fail(e, "sdk_grid_create: cudaMalloc (corner pairs)");
+        }
+        e = sdk::launch_interleave_corners(d->XG, d->YG, xyg, ncorner, nullptr);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+        if (e != cudaSuccess) {
+            cudaFree(xyg);
+            cudaFree(g->queue);
+            delete g;
+            return cuda_fail(e, "sdk_grid_create: corner pairs");
+        }
+        v.XYG = xyg;
+    }
     *out = g;
     return SDK_OK;
 }
@@ -179,6 +198,7 @@ int sdk_grid_create(const sdk_grid_desc *d, sdk_grid **out) {
 int sdk_grid_destroy(sdk_grid *g) {
     if (!g) return SDK_OK;
     cudaFree(g->queue);
+    cudaFree((void *)g->dev.XYG);
     if (g->has_pipe) {
         for (auto &st : g->pipe) cudaStreamDestroy(st);
         for (auto &ev : g->pipe_ev) cudaEventDestroy(ev);

@@ -548,8 +548,9 @@ __global__ void __launch_bounds__(128) locate_kernel(const __grid_constant__ Loc
             double px[4], py[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                px[j] = lon + to_180((double)__ldg(g.XG + cc[j]) - lon);
-                py[j] = (double)__ldg(g.YG + cc[j]);
+                const float2 q = __ldg(g.XYG + cc[j]);
+                px[j] = lon + to_180((double)q.x - lon);
+                py[j] = (double)q.y;
                 if (o.px) {
                     o.px[j * a.n + i] = px[j];
                     o.py[j * a.n + i] = py[j];
@@ -736,6 +737,19 @@ cudaError_t build_buckets(const GridDev &g, BucketGrid &b, cudaStream_t s) {
     cudaFree(remaining);
     if (e == cudaSuccess) e = cudaGetLastError();
     return e;
+}
+
+// (XG, YG) pairs for the corner reads of K1 / K2 (GridDev::XYG)
+__global__ void interleave_corners_kernel(const float *xg, const float *yg, float2 *out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = make_float2(xg[i], yg[i]);
+}
+
+cudaError_t launch_interleave_corners(const float *xg, const float *yg, float2 *out, int64_t n, cudaStream_t s) {
+    if (n == 0) return cudaSuccess;
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    interleave_corners_kernel<<<(unsigned)blocks, 256, 0, s>>>(xg, yg, out, n);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_locate(const LocateArgs &a, cudaStream_t s) {

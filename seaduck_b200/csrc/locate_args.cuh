@@ -34,6 +34,7 @@ struct LocateArgs {
 };
 
 cudaError_t build_buckets(const GridDev &g, BucketGrid &b, cudaStream_t s);
+cudaError_t launch_interleave_corners(const float *xg, const float *yg, float2 *out, int64_t n, cudaStream_t s);
 cudaError_t launch_locate(const LocateArgs &a, cudaStream_t s);
 cudaError_t launch_finish_stop(double *t, int32_t *it, const double *midp, int n_midp, double t_stop,
                                const unsigned long long *stats, unsigned long long *total, int64_t n, cudaStream_t s);

@@ -24,6 +24,9 @@ struct GridDev {
     signed char nbr_face[SDK_MAX_FACES * 4];
     signed char nbr_edge[SDK_MAX_FACES * 4];
     const float *XC, *YC, *XG, *YG, *dX, *dY, *CS, *SN, *Zl, *dZl, *Z, *dZ;
+    // (XG, YG) of every corner point side by side, built by sdk_grid_create: the four corner reads of a crossing touch two
+    // 32-byte sectors per row pair instead of four (oceanparcel scheme only, else NULL)
+    const float2 *XYG;
     const int32_t *corner_tab;
     // schemes without corner points (SDK_H_RECTILINEAR / SDK_H_LOCAL_CARTESIAN), see sdk_grid_desc
     const float *lon1, *lat1, *coslat32;
