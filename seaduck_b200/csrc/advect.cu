@@ -36,6 +36,13 @@ namespace sdk {
 #ifndef SDK_ADVECT_DEFER_STORE
 #define SDK_ADVECT_DEFER_STORE 1
 #endif
+// Profiles (bit P) whose steps issue the loads of the next cell as soon as the wall is known (see step()).  Parity
+// stays green, but the values in flight cost registers: the surface profile spills 13 doubles instead of 5 and
+// configs[3] goes from 3.70 to 4.35 ms per launch (3.72 with 128 registers and four CTAs per SM), profile 1 from 1.10 to
+// 1.14 ms (profiles/README.md, round 2, third session) -- off.
+#ifndef SDK_ADVECT_HOIST
+#define SDK_ADVECT_HOIST 0
+#endif
 #ifndef SDK_ADVECT_PRUNE
 #define SDK_ADVECT_PRUNE 0
 #endif
@@ -223,79 +230,92 @@ __device__ __forceinline__ void trim_axis(double &x, double &u, double du, doubl
     }
 }
 
-// Gather the wall values and form u, du, v, dv, w, dw (reference get_u_du lagrangian.py:218 with the
-// kernels of lagrangian.py:25-53; on LLC grids the right / top wall may live on the neighbouring
-// face and be the other velocity component, reference eulerian.py:887 + topology.py:618-647).
-// Index arithmetic: 32-bit within a horizontal plane, one 64-bit multiply-add for the level/time.
+// the wall values of a cell as they come out of memory (velocity_loads), before the weights are applied (velocity_finish)
+struct VelRaw {
+    double ul, ur, vl, vr, w0, w1, vol;
+};
+
+// First half of read_velocity: where the six wall values and the volume of cell (f, iy, ix) at level izl and time index it
+// live, and the loads.  Needs nothing but the cell, so a step can issue it as soon as it knows which wall the particle
+// leaves through, long before the relative coordinates in the new cell exist.
 template <typename T, int P = 0>
-__device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v, int has_dep, Lane &s) {
+__device__ __forceinline__ void velocity_loads(const GridDev &g, const VelDev &v, int f, int iy, int ix, int izl, int it, int &status, VelRaw &r) {
     const bool k_face = SDK_KNOWN3(P, true, true, g.has_face != 0);
     const bool k_w = SDK_KNOWN3(P, true, false, v.has_w != 0);
     const bool k_tr = SDK_KNOWN3(P, true, true, v.transport != 0);
     const bool k_z = SDK_KNOWN3(P, true, false, v.has_z != 0);
     const bool k_volz = SDK_KNOWN3(P, true, false, v.vol_has_z != 0);
     // ---- where do the right and top wall values live?
-    int rf = s.f, ry_ = s.iy, rx_ = s.ix, r_in;
-    int tf = s.f, ty_ = s.iy, tx_ = s.ix, t_in;
+    int rf = f, ry_ = iy, rx_ = ix, r_in;
+    int tf = f, ty_ = iy, tx_ = ix, t_in;
     bool r_is_v = false, t_is_u = false;
     if (k_face) {
         int st = cell_move(g, 3, rf, ry_, rx_, r_in);
         if (st) {
-            s.status |= SDK_ST_BAD_CELL;
-            rf = s.f, ry_ = s.iy, rx_ = s.ix;
+            status |= SDK_ST_BAD_CELL;
+            rf = f, ry_ = iy, rx_ = ix;
         } else if (r_in >= 0) {
             if (r_in == 1) r_is_v = true;
-            else if (r_in != 2) s.status |= SDK_ST_BAD_CELL;
+            else if (r_in != 2) status |= SDK_ST_BAD_CELL;
         }
         st = cell_move(g, 0, tf, ty_, tx_, t_in);
         if (st) {
-            s.status |= SDK_ST_BAD_CELL;
-            tf = s.f, ty_ = s.iy, tx_ = s.ix;
+            status |= SDK_ST_BAD_CELL;
+            tf = f, ty_ = iy, tx_ = ix;
         } else if (t_in >= 0) {
             if (t_in == 2) t_is_u = true;
-            else if (t_in != 1) s.status |= SDK_ST_BAD_CELL;
+            else if (t_in != 1) status |= SDK_ST_BAD_CELL;
         }
     } else {
         // scalar kernels on a single face: naive neighbour, topology walk only off the array
         // (an index of -1, -1 from a closed box reads the last element, like numpy does)
         const int xlim = v.u_stag ? g.gnx : g.nx, ylim = v.v_stag ? g.gny : g.ny;
-        rx_ = s.ix + 1;
+        rx_ = ix + 1;
         if (rx_ > xlim - 1) {
             if (g.typ == SDK_TYP_XPERIODIC) rx_ = rx_ - (g.nx - 1);
             else { ry_ = v.nyU - 1; rx_ = v.nxU - 1; }
         }
-        ty_ = s.iy + 1;
+        ty_ = iy + 1;
         if (ty_ > ylim - 1) { ty_ = v.nyV - 1; tx_ = v.nxV - 1; }
     }
-    int tlev = v.has_time ? wrap_index(s.it - v.it0, v.nt) : 0;
+    int tlev = v.has_time ? wrap_index(it - v.it0, v.nt) : 0;
     if (tlev < 0 || tlev >= v.nt) {
         // the particle's time level is not in the staged slab (the reference raises IndexError here:
         // Particle.update_uvw_array was not called after crossing time_midp); stay inside the array
-        s.status |= SDK_ST_OOB_T;
+        status |= SDK_ST_OOB_T;
         tlev = tlev < 0 ? 0 : v.nt - 1;
     }
-    const int64_t lev_uv = k_z ? (int64_t)(tlev * v.nzU + wrap_index(s.izl - 1, v.nzU)) : (int64_t)tlev;
-    const int c_ul = (s.f * v.nyU + s.iy) * v.nxU + s.ix;
-    const int c_vl = (s.f * v.nyV + s.iy) * v.nxV + s.ix;
+    const int64_t lev_uv = k_z ? (int64_t)(tlev * v.nzU + wrap_index(izl - 1, v.nzU)) : (int64_t)tlev;
+    const int c_ul = (f * v.nyU + iy) * v.nxU + ix;
+    const int c_vl = (f * v.nyV + iy) * v.nxV + ix;
     const int c_ur = r_is_v ? (rf * v.nyV + ry_) * v.nxV + rx_ : (rf * v.nyU + ry_) * v.nxU + rx_;
     const int c_vr = t_is_u ? (tf * v.nyU + ty_) * v.nxU + tx_ : (tf * v.nyV + ty_) * v.nxV + tx_;
     // issue every load before using any of them
-    const double ul = ldf<T>(v.U, lev_uv * v.planeU + c_ul);
-    const double vl = ldf<T>(v.V, lev_uv * v.planeV + c_vl);
-    const double ur = ldf<T>(r_is_v ? v.V : v.U, lev_uv * (r_is_v ? v.planeV : v.planeU) + c_ur);
-    const double vr = ldf<T>(t_is_u ? v.U : v.V, lev_uv * (t_is_u ? v.planeU : v.planeV) + c_vr);
-    const int cell = (s.f * g.ny + s.iy) * g.nx + s.ix;
-    double w0 = 0.0, w1 = 0.0;
+    r.ul = ldf<T>(v.U, lev_uv * v.planeU + c_ul);
+    r.vl = ldf<T>(v.V, lev_uv * v.planeV + c_vl);
+    r.ur = ldf<T>(r_is_v ? v.V : v.U, lev_uv * (r_is_v ? v.planeV : v.planeU) + c_ur);
+    r.vr = ldf<T>(t_is_u ? v.U : v.V, lev_uv * (t_is_u ? v.planeU : v.planeV) + c_vr);
+    const int cell = (f * g.ny + iy) * g.nx + ix;
+    r.w0 = 0.0, r.w1 = 0.0, r.vol = 1.0;
     if (k_w) {
         const int64_t wl = (int64_t)tlev * v.nzW;
-        w0 = ldf<T>(v.W, (wl + wrap_index(s.izl, v.nzW)) * v.planeC + cell);
-        w1 = ldf<T>(v.W, (wl + wrap_index(s.izl - 1, v.nzW)) * v.planeC + cell);
+        r.w0 = ldf<T>(v.W, (wl + wrap_index(izl, v.nzW)) * v.planeC + cell);
+        r.w1 = ldf<T>(v.W, (wl + wrap_index(izl - 1, v.nzW)) * v.planeC + cell);
     }
     if (k_tr) {
-        const int64_t idx = (k_volz ? (int64_t)wrap_index(s.izl - 1, g.n_z > 0 ? g.n_z : 1) : 0) * v.planeC + cell;
-        s.vol = v.vol_dtype == SDK_F64 ? ldf<double>(v.Vol, idx) : ldf<float>(v.Vol, idx);
+        const int64_t idx = (k_volz ? (int64_t)wrap_index(izl - 1, g.n_z > 0 ? g.n_z : 1) : 0) * v.planeC + cell;
+        r.vol = v.vol_dtype == SDK_F64 ? ldf<double>(v.Vol, idx) : ldf<float>(v.Vol, idx);
     }
-    double ul_ = ul, ur_ = ur, vl_ = vl, vr_ = vr, w0_ = w0, w1_ = w1;
+}
+
+// Second half: the two-node kernels in the particle's relative coordinates, and the division by the cell's scale.
+template <typename T, int P = 0>
+__device__ __forceinline__ void velocity_finish(const GridDev &g, const VelDev &v, Lane &s, const VelRaw &r) {
+    const bool k_face = SDK_KNOWN3(P, true, true, g.has_face != 0);
+    const bool k_w = SDK_KNOWN3(P, true, false, v.has_w != 0);
+    const bool k_tr = SDK_KNOWN3(P, true, true, v.transport != 0);
+    if (k_tr) s.vol = r.vol;
+    double ul_ = r.ul, ur_ = r.ur, vl_ = r.vl, vr_ = r.vr, w0_ = r.w0, w1_ = r.w1;
     nan_to_num6(ul_, ur_, vl_, vr_, w0_, w1_);
     const bool stag_x = k_face || v.u_stag, stag_y = k_face || v.v_stag;
     const double rxs = stag_x ? s.rx + 0.5 : s.rx;
@@ -344,6 +364,18 @@ __device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v,
         s.w = qw;
         s.dw = qdw;
     }
+}
+
+// Gather the wall values and form u, du, v, dv, w, dw (reference get_u_du lagrangian.py:218 with the
+// kernels of lagrangian.py:25-53; on LLC grids the right / top wall may live on the neighbouring
+// face and be the other velocity component, reference eulerian.py:887 + topology.py:618-647).
+// Index arithmetic: 32-bit within a horizontal plane, one 64-bit multiply-add for the level/time.
+template <typename T, int P = 0>
+__device__ __forceinline__ void read_velocity(const GridDev &g, const VelDev &v, int has_dep, Lane &s) {
+    (void)has_dep;
+    VelRaw r;
+    velocity_loads<T, P>(g, v, s.f, s.iy, s.ix, s.izl, s.it, s.status, r);
+    velocity_finish<T, P>(g, v, s, r);
 }
 
 // One iteration of the reference loop (lagrangian.py:766-791) for one particle.
@@ -432,6 +464,39 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
 #pragma unroll
     for (int k = 1; k < 7; ++k)
         if (!(P == 3 && (k == 4 || k == 5)) && tend == k) te = ts[k];
+    // Which wall is known: so is the cell the particle is about to enter (_cross_cell_wall_index, lagrangian.py:598), and
+    // with it every address the rest of the step reads from -- corners, wall values, volume.  With HOIST the loads go
+    // out here, and their latency passes behind the move, the logarithm-free but long inverse bilinear map and the
+    // vertical lookup instead of being waited for twice (corners, then velocities) at the end of the step.
+    constexpr bool HOIST = P != 2 && ((SDK_ADVECT_HOIST >> P) & 1);
+    int nf = s.f, niy = s.iy, nix = s.ix, nizl = s.izl, st_move = 0, st_early = 0;
+    bool leaves = false;  // out of a closed domain / through the deepest level: nothing to read
+    int64_t c[4];
+    float gx[4], gy[4];
+    VelRaw raw;
+    if (HOIST) {
+        if (tend <= 3) {
+            const int dir = tend == 0 ? 2 : (tend == 1 ? 3 : (tend == 2 ? 1 : 0));
+            int came_in;
+            st_move = cell_move(g, dir, nf, niy, nix, came_in);
+            leaves = (st_move & SDK_ST_OUT) != 0;
+        } else if (P != 3 && tend == 4) {
+            nizl += 1;
+            leaves = nizl > g.n_zl - 1;
+        } else if (P != 3 && tend == 5) {
+            if (!a.kick_back || s.izl != 1) nizl -= 1;
+        }
+        if (!leaves) {
+            st_early |= corner_indices(g, nf, niy, nix, c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 q = __ldg(g.XYG + c[j]);
+                gx[j] = q.x;
+                gy[j] = q.y;
+            }
+            velocity_loads<T, P>(g, a.v, nf, niy, nix, nizl, s.it, st_early, raw);
+        }
+    }
     // _move_within_cell, lagrangian.py:528
     s.t += te;
     {
@@ -478,7 +543,19 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
     if (LOG) note(a, s, tend);
     s.ncross += tend < 6;
     // _cross_cell_wall_index, lagrangian.py:598
-    if (tend <= 3) {
+    if (HOIST) {
+        s.status |= st_move | st_early;
+        if (SDK_UNLIKELY(leaves)) {
+            if (tend == 4) {
+                s.izl = g.n_zl - 1;
+                s.status |= SDK_ST_OOB_LEVEL;
+            }
+            live = false;
+            return;
+        }
+        if (P != 3 && tend == 5 && a.kick_back && s.izl == 1) s.dep = s.bzl + s.dzl / 2;
+        s.f = nf, s.iy = niy, s.ix = nix, s.izl = nizl;
+    } else if (tend <= 3) {
         const int dir = tend == 0 ? 2 : (tend == 1 ? 3 : (tend == 2 ? 1 : 0));
         int came_in;
         const int st = cell_move(g, dir, s.f, s.iy, s.ix, came_in);
@@ -502,8 +579,6 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
         else s.dep = s.bzl + s.dzl / 2;
     }
     // _cross_cell_wall_read, lagrangian.py:640: corners (oceanparcel) or centre + metric (other schemes), vertical levels
-    int64_t c[4];
-    float gx[4], gy[4];
     float l_cs = 1.f, l_sn = 0.f, l_dx = 1.f, l_dy = 1.f, l_cos = 1.f, l_bx = 0.f, l_by = 0.f;
     double l_dlon = 1.0, l_dlat = 1.0;
     if (P == 2) {
@@ -519,7 +594,7 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
             l_cos = __ldg(g.coslat32 + iy);
             l_dlon = __ldg(g.dlon + ix), l_dlat = __ldg(g.dlat + iy);
         }
-    } else {
+    } else if (!HOIST) {
         s.status |= corner_indices(g, s.f, s.iy, s.ix, c);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -573,7 +648,8 @@ __device__ __forceinline__ void step(const AdvectArgs &a, const float *sZl, cons
         }
     }
     // get_vol + get_u_du
-    read_velocity<T, P>(g, a.v, has_dep, s);
+    if (HOIST) velocity_finish<T, P>(g, a.v, s, raw);
+    else read_velocity<T, P>(g, a.v, has_dep, s);
     s.niter += 1;
     live = fabs(a.t_stop - s.t) > a.tol;
     if (LOG && live && !(a.log.continue_mode & 1)) note(a, s, 7);
