@@ -26,6 +26,7 @@ each with its own clock record.  With N > 1 ranks the output records of every st
 """
 
 import argparse
+import gc
 import json
 import os
 import sys
@@ -697,6 +698,7 @@ def run_cuda(a):
     else:
         which = [w for w in a.extras.split(",") if w]
     for w in which:
+        gc.collect()  # (the objects of the previous workload hold GBs of device memory through reference cycles)
         ctx.torch.cuda.empty_cache()
         try:
             if w == "c4":
