@@ -301,7 +301,11 @@ def load_traffic(kind):
     if not os.path.exists(path):
         return None, None
     rec = json.load(open(path))
-    if kind != "c2":
+    if kind == "c4":
+        rec = rec.get("configs[3]")
+    elif kind != "c2":
+        rec = None
+    if not rec:
         return None, None
     return rec.get("dram_bytes_per_launch"), f"profiles/traffic_bytes_per_launch.json ({rec.get('source', 'ncu --set full')})"
 
@@ -667,7 +671,8 @@ def run_stops(ctx, a, grid, particles, hours, nt=3):
         kern_ms.append(e0.elapsed_time(e1))
         kern_cross.append(int(stats[1].item()))
     out["clocks"] = sampler.finish()
-    out["roofline"] = roofline_of("advect_kernel<double,false,3>", float(np.mean(kern_ms)), float(np.mean(kern_cross)), n, "f64", False)
+    traffic, traffic_src = load_traffic("c4") if (grid, particles) == (4320, 12_500_000) else (None, None)
+    out["roofline"] = roofline_of("advect_kernel<double,false,3>", float(np.mean(kern_ms)), float(np.mean(kern_cross)), n, "f64", False, traffic, traffic_src)
     return out
 
 
