@@ -193,7 +193,7 @@ int sdk_abi_version(void);
  * 13 sdk_exchange, 14 sdk_interp_job, 15 sdk_interp_io; -1 for anything else */
 int64_t sdk_struct_size(int which);
 const char *sdk_last_error(void);
-/* number of SMs of the current device (grid sizing), <0 on error */
+/* number of SMs of the current device (grid sizing; no reference counterpart), <0 on error */
 int sdk_sm_count(void);
 
 /* OceData(...) grid staging, seaduck/ocedata.py:164,411 */
@@ -352,7 +352,8 @@ typedef struct sdk_points {
     const int32_t *out_index;
 } sdk_points;
 
-/* scalar variable */
+/* Position.interpolate for one scalar variable, seaduck/eulerian.py:1268 (str var_name; the register / mask / read /
+ * weight stages :887-1266 and KnW.get_weight kernel_weight.py:772 in one launch) */
 int sdk_interp_scalar(const sdk_grid *grid, const sdk_points *pts, const sdk_field *field,
                       const sdk_kernel_desc *knw, double *out, void *stream);
 /* several scalar variables in one launch (at most SDK_MAX_MULTI_FIELDS): they must share the kernel, the grid position
@@ -403,7 +404,8 @@ typedef struct sdk_interp_io {
 int64_t sdk_interp_host_scratch_bytes(int64_t n, int32_t n_outputs);
 int sdk_interp_host(const sdk_grid *grid, const sdk_interp_io *io, const double *ts_dev, int32_t n_t,
                     const sdk_interp_job *jobs, int32_t n_jobs, void *scratch, void *stream);
-/* OR of n status words (device) into *flags (device, not cleared first) */
+/* OR of n status words (device) into *flags (device, not cleared first): what decides whether the reference's
+ * "Value out of bound." (find_rel, seaduck/utils.py:321) is raised for a batch of located points */
 int sdk_status_or(const int32_t *status, int64_t n, uint32_t *flags, void *stream);
 
 /* End of Particle.to_next_stop without a host round trip (seaduck/lagrangian.py:793-802): if the
@@ -503,7 +505,8 @@ typedef struct sdk_snapshot_record {
 #define SDK_CELL_IX(w) ((int32_t)(((w) >> 12) & 0xfffff))
 #define SDK_CELL_IZL(w) ((int32_t)((w) & 0xfff))
 
-/* out[out_index ? out_index[i] : i] = record of particle i, i < p->n (reads lon, lat, dep, face, iy, ix, izl of the
+/* What a stop of Particle.to_list_of_time hands back (the deepcopy of seaduck/lagrangian.py:725,804), 32 bytes per particle:
+ * out[out_index ? out_index[i] : i] = record of particle i, i < p->n (reads lon, lat, dep, face, iy, ix, izl of the
  * device state `p`; NULL members read as zero).  `out_index` restores the caller's order when the state is cell
  * sorted (sdk_cell_sort).  Device pointers. */
 int sdk_pack_records(const sdk_particles *p, const int32_t *out_index, sdk_snapshot_record *out, void *stream);
